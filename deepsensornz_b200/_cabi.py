@@ -1,0 +1,136 @@
+"""ctypes binding of ``libconvnp_b200.so`` (the C-ABI declared in ``include/convnp_b200.h``).
+
+The library is the product: there is no CPU or PyTorch fallback.  ``lib()`` raises if the shared
+object is missing (run ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C
+deepsensornz_b200/csrc``) and ``check_device()`` raises if the current GPU is not sm_100.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libconvnp_b200.so")
+
+c_stream = C.c_void_p
+c_fp = C.c_void_p  # device pointers are passed as integers (tensor.data_ptr())
+
+
+class CnpMlpParams(C.Structure):
+    MAX_LAYERS = 6
+    _fields_ = [
+        ("W", C.c_void_p * 6),
+        ("b", C.c_void_p * 6),
+        ("dW", C.c_void_p * 6),
+        ("db", C.c_void_p * 6),
+        ("dims", C.c_int * 7),
+        ("n_layers", C.c_int),
+    ]
+
+
+class CnpBlk(C.Structure):
+    """View of a blocked bf16 activation tensor [B][C/8][H+4][W+4][8]."""
+    _fields_ = [
+        ("base", C.c_void_p),
+        ("bstride", C.c_longlong),
+        ("cb_off", C.c_int),
+        ("H", C.c_int),
+        ("W", C.c_int),
+    ]
+
+
+class CnpConvOut(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int),
+        ("blk", CnpBlk),
+        ("f32", C.c_void_p),
+        ("f32_bstride", C.c_longlong),
+        ("f32_ch_off", C.c_int),
+        ("sy", C.c_int), ("ay", C.c_int), ("sx", C.c_int), ("ax", C.c_int),
+        ("bias", C.c_void_p),
+        ("relu", C.c_int),
+        ("mask", C.POINTER(CnpBlk)),
+        ("accumulate", C.c_int),
+    ]
+
+
+# conv_tc kinds (must match conv_bf16.cu)
+KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD = range(6)
+
+_i, _d, _f, _ll = C.c_int, C.c_double, C.c_float, C.c_longlong
+_GRID = [_d, _i, _d, _i, _d]  # start1, n1, start2, n2, res
+
+_SIGS = {
+    "cnp_version": (C.c_int, []),
+    "cnp_last_error": (C.c_char_p, []),
+    "cnp_check_device": (C.c_int, []),
+    # (1) SetConv encoder
+    "cnp_setconv_enc_offgrid_fwd": (C.c_int, [c_fp, c_fp, c_fp, _i, _i, _i] + _GRID + [_f, _f, c_fp, _i, _i, c_stream]),
+    "cnp_setconv_enc_grid_fwd": (C.c_int, [c_fp, c_fp, _i, c_fp, c_fp, _i, _i, _i, _i, _i, _i] + _GRID +
+                                 [_f, _f, c_fp, _i, _i, c_stream]),
+    # (3) SetConv decoder
+    "cnp_setconv_dec_offgrid_fwd": (C.c_int, [c_fp, _ll, c_fp, _i, _i, _i] + _GRID + [_f, c_fp, _i, c_stream]),
+    "cnp_setconv_dec_offgrid_bwd": (C.c_int, [c_fp, _i, c_fp, _i, _i, _i] + _GRID + [_f, c_fp, _ll, c_stream]),
+    # (2) fp32 UNet blocks
+    "cnp_conv2d_fwd_f32": (C.c_int, [c_fp, _ll, c_fp, c_fp, c_fp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, c_stream]),
+    "cnp_conv2d_dgrad_f32": (C.c_int, [c_fp, _ll, c_fp, c_fp, _ll, _i, _i, _i, _i, _i, _i, _i, _i, c_stream]),
+    "cnp_conv2d_wgrad_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, c_fp, c_fp, _i, _i, _i, _i, _i, _i, _i, c_stream]),
+    "cnp_relu_bwd_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, _i, _ll, c_stream]),
+    "cnp_upsample2x_fwd_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, _i, _i, _i, _i, c_stream]),
+    "cnp_upsample2x_bwd_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, _i, _i, _i, _i, _i, c_stream]),
+    # (4) MLP + Gaussian head + NLL
+    "cnp_mlp_head_fwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp,
+                                   c_fp, c_stream]),
+    "cnp_mlp_head_bwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp,
+                                   c_stream]),
+    # (2) bf16 tensor-core UNet blocks
+    "cnp_conv_tc_packed_bytes": (_ll, [_i, _i]),
+    "cnp_conv_tc_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
+    "cnp_conv_tc": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
+    "cnp_blk_from_nchw_f32": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
+    "cnp_blk_to_nchw_f32": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, _ll, c_stream]),
+    "cnp_conv1x1_in_bf16": (C.c_int, [c_fp, _ll, c_fp, c_fp, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
+    "cnp_blk_upsample2x_fwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
+    "cnp_blk_upsample2x_bwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, _i, c_stream]),
+    "cnp_blk_space_to_depth": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class CnpError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CnpError(f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                           "(there is no CPU fallback for the ConvNP hot path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError if the export is missing
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().cnp_last_error().decode("utf-8", "replace")
+        raise CnpError(f"{what or 'libconvnp_b200'} failed (rc={rc}): {msg}")
+
+
+def check_device() -> None:
+    check(lib().cnp_check_device(), "cnp_check_device")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,725 @@
+// bf16 UNet path for sm_100a: tcgen05 implicit-GEMM convolution (forward, dgrad) plus the
+// memory-bound helpers around it (weight packing, layout conversion, 1x1 input conv, bilinear x2
+// resize forward/backward, space-to-depth for the stride-2 layers).
+//
+// Replaces the torch Conv2d stack of upstream neuralprocesses' UNet (reached
+// from ConvNP.loss_fn nzdownscale/downscaler/train.py:370 and train_epoch train.py:388-394) for the
+// bf16 mode of BASELINE.json's north_star ("UNet conv stack as tcgen05/TMA implicit-GEMM in bf16").
+//
+// ---- activation layout in HBM ("blocked") ---------------------------------------------------
+//   [B][C/8][H+4][W+4][8] bf16 : channels in chunks of 8 (16 B per pixel-chunk), every plane
+//   physically zero-padded by 2 pixels on each side.  The pad is zeroed once at allocation and
+//   never written, so 5x5 / pad-2 convolutions need no boundary logic.
+//
+// ---- implicit GEMM ----------------------------------------------------------------------------
+//   A tile = a (TH+4) x pitch window of the padded input (pitch = TW+4), for 4 channel chunks,
+//   copied row by row with cp.async.bulk into shared memory as [chunk][window pixel][8 ch].
+//   That is exactly the SWIZZLE_NONE K-major UMMA layout (core matrix = 8 consecutive pixels x
+//   8 channels, 16 B rows), and a conv tap (ky,kx) is just a +(ky*pitch+kx)*16 B shift of the
+//   descriptor start address: no im2col, every input byte is fetched from L2 once per tile.
+//   M = 128 consecutive window pixels per accumulator, R <= 4 accumulators per tile (TMEM
+//   columns [64r, 64r+64)), double-buffered across tiles (2 x 256 columns).  Window pixels that
+//   are not valid outputs (the 4 halo columns per row) are computed and dropped: rows of D only
+//   depend on the matching rows of A, so they cannot contaminate valid outputs.
+//   N = 64 output channels, K = 32 input channels x taps per stage; weights are pre-packed per
+//   stage as [tap][k8][n][8] (K-major, SWIZZLE_NONE) and streamed through a 3-deep ring.
+//   Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (one elected thread), 2 = TMEM allocator,
+//   4..7 = epilogue (tcgen05.ld -> bias/ReLU/mask -> bf16 blocked or fp32 NCHW stores).
+#include "tc_common.cuh"
+
+#define CNP_MAX_AB 8
+#define CNP_MAX_ST 24
+#define CNP_MAX_TAP 5
+
+struct cnp_conv_plan {
+  int n_ab;
+  int ab_chunk0[CNP_MAX_AB];       // first of the 4 source chunks of this A-block
+  int ab_wci0[CNP_MAX_AB];         // weight input-channel base of this A-block (for packing)
+  int ab_stage0[CNP_MAX_AB + 1];   // stages [ab_stage0[i], ab_stage0[i+1]) belong to A-block i
+  int st_ntap[CNP_MAX_ST];
+  short st_aoff[CNP_MAX_ST][CNP_MAX_TAP];  // pixel offset of the tap inside the A window
+  signed char st_wky[CNP_MAX_ST][CNP_MAX_TAP];
+  signed char st_wkx[CNP_MAX_ST][CNP_MAX_TAP];
+};
+
+struct cnp_conv_args {
+  const __nv_bfloat16* x; long long x_bs; int x_Hp, x_Wp;
+  const __nv_bfloat16* w;
+  int B, H, W;
+  int TW, TH, pitch, R, plane_sm, tiles_x, tiles_y;
+  int out_mode;                  // 0: blocked bf16, 1: NCHW fp32
+  void* out; long long out_bs; int out_c_off; int out_Hp, out_Wp;
+  int sy, ay, sx, ax;            // output pixel = (y*sy+ay, x*sx+ax)
+  const float* bias; int relu;
+  const __nv_bfloat16* mask; long long mask_bs; int mask_cb_off;
+  int accumulate;
+  cnp_conv_plan plan;
+};
+
+namespace {
+
+constexpr int N_OUT = 64;
+constexpr int W_TAP_BYTES = 4 * N_OUT * 16;             // 4 k-chunks x 64 n x 16 B = 4096
+constexpr int W_STAGE_BYTES = CNP_MAX_TAP * W_TAP_BYTES;  // 20480
+constexpr int W_STAGES = 3;
+constexpr int A_BUFS = 2;
+constexpr int ACC_STAGES = 2;
+constexpr uint32_t TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ cnp_conv_args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int plane_bytes = a.plane_sm * 16;
+  const int abuf_bytes = 4 * plane_bytes;
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = smem + A_BUFS * abuf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + W_STAGES * W_STAGE_BYTES);
+  uint64_t* a_full = bars;             // [2]
+  uint64_t* a_empty = bars + 2;        // [2]
+  uint64_t* w_full = bars + 4;         // [3]
+  uint64_t* w_empty = bars + 7;        // [3]
+  uint64_t* acc_full = bars + 10;      // [2]
+  uint64_t* acc_empty = bars + 12;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 3; ++i) { tc::mbar_init(w_full + i, 1); tc::mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, 4); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int rows = a.TH + 4;
+  const uint32_t row_bytes = (uint32_t)a.pitch * 16u;
+  const long long plane_g = (long long)a.x_Hp * a.x_Wp * 8;  // elements per chunk plane
+
+  if (warp == 0) {
+    // ===================== producer: bulk copies of A windows and weight stages ================
+    if (tc::elect_one()) {
+      uint32_t a_it = 0, w_it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / (a.tiles_x * a.tiles_y), tr = tile % (a.tiles_x * a.tiles_y);
+        const int y0 = (tr / a.tiles_x) * a.TH, x0 = (tr % a.tiles_x) * a.TW;
+        const __nv_bfloat16* xb = a.x + (long long)b * a.x_bs + ((long long)y0 * a.x_Wp + x0) * 8;
+        for (int ab = 0; ab < a.plan.n_ab; ++ab, ++a_it) {
+          const int buf = a_it & 1;
+          tc::mbar_wait(a_empty + buf, ((a_it >> 1) & 1) ^ 1);
+          tc::mbar_expect_tx(a_full + buf, 4u * rows * row_bytes);
+          uint8_t* dst = a_smem + buf * abuf_bytes;
+          for (int c = 0; c < 4; ++c) {
+            const __nv_bfloat16* src = xb + (long long)(a.plan.ab_chunk0[ab] + c) * plane_g;
+            for (int r = 0; r < rows; ++r)
+              tc::bulk_g2s(dst + c * plane_bytes + r * row_bytes, src + (long long)r * a.x_Wp * 8, row_bytes,
+                           a_full + buf);
+          }
+          for (int s = a.plan.ab_stage0[ab]; s < a.plan.ab_stage0[ab + 1]; ++s, ++w_it) {
+            const int ws = w_it % W_STAGES;
+            tc::mbar_wait(w_empty + ws, ((w_it / W_STAGES) & 1) ^ 1);
+            const uint32_t bytes = (uint32_t)a.plan.st_ntap[s] * W_TAP_BYTES;
+            tc::mbar_expect_tx(w_full + ws, bytes);
+            tc::bulk_g2s(w_smem + ws * W_STAGE_BYTES,
+                         reinterpret_cast<const uint8_t*>(a.w) + (size_t)s * W_STAGE_BYTES, bytes, w_full + ws);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer ===========================================================
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, N_OUT, 0, 0);
+      uint32_t a_it = 0, w_it = 0, t_it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_it) {
+        const int as = t_it & 1;
+        tc::mbar_wait(acc_empty + as, ((t_it >> 1) & 1) ^ 1);
+        tc::fence_after_sync();
+        const uint32_t d0 = tmem_base + as * (TMEM_COLS / ACC_STAGES);
+        bool first = true;
+        for (int ab = 0; ab < a.plan.n_ab; ++ab, ++a_it) {
+          const int buf = a_it & 1;
+          tc::mbar_wait(a_full + buf, (a_it >> 1) & 1);
+          const uint32_t a_base = tc::smem_u32(a_smem + buf * abuf_bytes);
+          for (int s = a.plan.ab_stage0[ab]; s < a.plan.ab_stage0[ab + 1]; ++s, ++w_it) {
+            const int ws = w_it % W_STAGES;
+            tc::mbar_wait(w_full + ws, (w_it / W_STAGES) & 1);
+            tc::fence_after_sync();
+            const uint32_t w_base = tc::smem_u32(w_smem + ws * W_STAGE_BYTES);
+            const int ntap = a.plan.st_ntap[s];
+            for (int t = 0; t < ntap; ++t) {
+              const uint32_t aoff = (uint32_t)a.plan.st_aoff[s][t] * 16u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t bdesc = tc::make_smem_desc(w_base + t * W_TAP_BYTES + ks * (2 * N_OUT * 16),
+                                                          N_OUT * 16, 128);
+                for (int r = 0; r < a.R; ++r) {
+                  const uint64_t adesc = tc::make_smem_desc(a_base + 2 * ks * plane_bytes + aoff + r * 2048,
+                                                            plane_bytes, 128);
+                  tc::mma_bf16_ss(d0 + r * N_OUT, adesc, bdesc, idesc, first ? 0u : 1u);
+                }
+                first = false;
+              }
+            }
+            tc::mma_commit(w_empty + ws);
+          }
+          tc::mma_commit(a_empty + buf);
+        }
+        tc::mma_commit(acc_full + as);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue ==============================================================
+    const int q = warp & 3;
+    uint32_t t_it = 0;
+    const long long oplane = (long long)a.out_Hp * a.out_Wp;  // blocked: pixels per chunk plane
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_it) {
+      const int as = t_it & 1;
+      const int b = tile / (a.tiles_x * a.tiles_y), tr = tile % (a.tiles_x * a.tiles_y);
+      const int y0 = (tr / a.tiles_x) * a.TH, x0 = (tr % a.tiles_x) * a.TW;
+      tc::mbar_wait(acc_full + as, (t_it >> 1) & 1);
+      tc::fence_after_sync();
+      for (int r = 0; r < a.R; ++r) {
+        const int m = r * 128 + q * 32 + lane;
+        const int ty = m / a.pitch, tx = m - ty * a.pitch;
+        const int y = y0 + ty, x = x0 + tx;
+        const bool valid = (ty < a.TH) && (tx < a.TW) && (y < a.H) && (x < a.W);
+        const int oy = y * a.sy + a.ay, ox = x * a.sx + a.ax;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (TMEM_COLS / ACC_STAGES) + r * N_OUT;
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          float v[32];
+          tc::tmem_ld32(taddr + hc * 32, v);
+          tc::tmem_ld_wait();
+          if (a.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + hc * 32 + i);
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (valid) {
+            if (a.out_mode == 0) {
+              const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const int chunk = hc * 4 + c8;
+                float* vv = v + c8 * 8;
+                if (a.mask) {
+                  const uint4 mk = __ldg(reinterpret_cast<const uint4*>(
+                      a.mask + (long long)b * a.mask_bs + ((long long)(a.mask_cb_off + chunk) * oplane + pix) * 8));
+                  const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) if (!(__bfloat162float(mb[i]) > 0.f)) vv[i] = 0.f;
+                }
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
+                                     ((long long)(a.out_c_off + chunk) * oplane + pix) * 8;
+                if (a.accumulate) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(dst);
+                  const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(&old);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) vv[i] += __bfloat162float(ob[i]);
+                }
+                uint4 pk;
+                __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(vv[2 * i], vv[2 * i + 1]);
+                *reinterpret_cast<uint4*>(dst) = pk;
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(a.out) + (long long)b * a.out_bs +
+                           ((long long)(a.out_c_off + hc * 32) * a.out_Hp + oy) * a.out_Wp + ox;
+              const long long cs = (long long)a.out_Hp * a.out_Wp;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) dst[i * cs] = a.accumulate ? dst[i * cs] + v[i] : v[i];
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(acc_empty + as);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: torch fp32 [Cout][Cin][k][k] -> bf16 stages [stage][tap][k8][n][8]
+//   transposed = 0: n = output channel (co_off + n), k = input channel ab_wci0 + k8*8 + c
+//   transposed = 1 (dgrad): n = original input channel (co_off + n), k = original output channel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transposed, int co_off,
+                    __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_conv_plan plan) {
+  const int nst = plan.ab_stage0[plan.n_ab];
+  const int total = nst * CNP_MAX_TAP * 4 * N_OUT * 8;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int c = e & 7, n = (e >> 3) & 63, k8 = (e >> 9) & 3, t = (e >> 11) % CNP_MAX_TAP, s = (e >> 11) / CNP_MAX_TAP;
+    int ab = 0;
+    while (ab + 1 < plan.n_ab && s >= plan.ab_stage0[ab + 1]) ++ab;
+    float v = 0.f;
+    if (t < plan.st_ntap[s]) {
+      const int kc = plan.ab_wci0[ab] + k8 * 8 + c, nn = co_off + n;
+      const int ky = plan.st_wky[s][t], kx = plan.st_wkx[s][t];
+      if (!transposed) {
+        if (nn < Cout && kc < Cin) v = w[(((size_t)nn * Cin + kc) * k + ky) * k + kx];
+      } else {
+        if (kc < Cout && nn < Cin) v = w[(((size_t)kc * Cin + nn) * k + ky) * k + kx];
+      }
+    }
+    wpk[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion  NCHW fp32 <-> blocked bf16  (tests, encoder/decoder interfacing)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_blk_kernel(const float* __restrict__ src, long long src_bs, int C, int H, int W,
+                   __nv_bfloat16* __restrict__ dst, long long dst_bs, int cb_off) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int Hp = H + 4, Wp = W + 4;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
+    const int y = e / W, x = e % W;
+    uint4 pk;
+    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = chunk * 8 + i;
+      v[i] = c < C ? src[(size_t)b * src_bs + ((size_t)c * H + y) * W + x] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(dst + (size_t)b * dst_bs + (((size_t)(cb_off + chunk) * Hp + y + 2) * Wp + x + 2) * 8) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+blk_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, long long src_bs, int cb_off, int C, int H, int W,
+                   float* __restrict__ dst, long long dst_bs) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int Hp = H + 4, Wp = W + 4;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
+    const int y = e / W, x = e % W;
+    const uint4 pk = *reinterpret_cast<const uint4*>(
+        src + (size_t)b * src_bs + (((size_t)(cb_off + chunk) * Hp + y + 2) * Wp + x + 2) * 8);
+    const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = chunk * 8 + i;
+      if (c < C) dst[(size_t)b * dst_bs + ((size_t)c * H + y) * W + x] = __bfloat162float(pb[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// initial 1x1 conv: fp32 NCHW [B,Cin,H,W] (encoder output) -> blocked bf16 [B,Cout/8,..] (+bias)
+// ---------------------------------------------------------------------------------------------
+constexpr int IC_MAX_CIN = 40;
+
+__global__ void __launch_bounds__(256)
+conv1x1_in_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, int W,
+                  const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                  __nv_bfloat16* __restrict__ out, long long out_bs, int cb_off) {
+  __shared__ float w_s[IC_MAX_CIN][64];
+  __shared__ float b_s[64];
+  const int b = blockIdx.y;
+  for (int e = threadIdx.x; e < Cin * 64; e += 256) {
+    int ci = e / 64, co = e % 64;
+    w_s[ci][co] = co < Cout ? w[(size_t)co * Cin + ci] : 0.f;
+  }
+  if (threadIdx.x < 64) b_s[threadIdx.x] = threadIdx.x < Cout ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int Hp = H + 4, Wp = W + 4;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
+    const int y = e / W, xx = e % W;
+    float acc[64];
+#pragma unroll
+    for (int co = 0; co < 64; ++co) acc[co] = b_s[co];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float v = __ldg(x + (size_t)b * x_bs + (size_t)ci * H * W + e);
+#pragma unroll
+      for (int co = 0; co < 64; ++co) acc[co] = fmaf(v, w_s[ci][co], acc[co]);
+    }
+#pragma unroll
+    for (int chunk = 0; chunk < 8; ++chunk) {
+      uint4 pk;
+      __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(acc[chunk * 8 + 2 * i], acc[chunk * 8 + 2 * i + 1]);
+      *reinterpret_cast<uint4*>(out + (size_t)b * out_bs + (((size_t)(cb_off + chunk) * Hp + y + 2) * Wp + xx + 2) * 8) = pk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear x2 (align_corners=False) on blocked tensors; backward optionally masks by (act > 0)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_src(int Y, int H, int* y0, int* y1, float* lam) {
+  float src = ((float)Y + 0.5f) * 0.5f - 0.5f;
+  src = fmaxf(src, 0.f);
+  int i0 = (int)src;
+  *y0 = i0; *y1 = min(i0 + 1, H - 1); *lam = src - (float)i0;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* v) {
+  const uint4 pk = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(pb[i]);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+  uint4 pk;
+  __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = pk;
+}
+
+__global__ void __launch_bounds__(256)
+blk_upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, int x_cb, int H, int W,
+                          __nv_bfloat16* __restrict__ y, long long y_bs, int y_cb) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int Wp = W + 4, Hp = H + 4, H2 = 2 * H, W2 = 2 * W, W2p = W2 + 4, H2p = H2 + 4;
+  const __nv_bfloat16* xc = x + (size_t)b * x_bs + (size_t)(x_cb + chunk) * Hp * Wp * 8;
+  __nv_bfloat16* yc = y + (size_t)b * y_bs + (size_t)(y_cb + chunk) * H2p * W2p * 8;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H2 * W2; e += gridDim.x * 256) {
+    const int Y = e / W2, X = e % W2;
+    int y0, y1, x0, x1; float ly, lx;
+    up2_src(Y, H, &y0, &y1, &ly);
+    up2_src(X, W, &x0, &x1, &lx);
+    float a00[8], a01[8], a10[8], a11[8], o[8];
+    ld8(xc + ((size_t)(y0 + 2) * Wp + x0 + 2) * 8, a00);
+    ld8(xc + ((size_t)(y0 + 2) * Wp + x1 + 2) * 8, a01);
+    ld8(xc + ((size_t)(y1 + 2) * Wp + x0 + 2) * 8, a10);
+    ld8(xc + ((size_t)(y1 + 2) * Wp + x1 + 2) * 8, a11);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r0 = (1.f - lx) * a00[i] + lx * a01[i];
+      const float r1 = (1.f - lx) * a10[i] + lx * a11[i];
+      o[i] = (1.f - ly) * r0 + ly * r1;
+    }
+    st8(yc + ((size_t)(Y + 2) * W2p + X + 2) * 8, o);
+  }
+}
+
+// dx[u,v] = sum over the <=4x4 hi-res pixels that reference (u,v); optional ReLU mask by act>0.
+__global__ void __launch_bounds__(256)
+blk_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int H, int W,
+                          __nv_bfloat16* __restrict__ dx, long long dx_bs, int dx_cb,
+                          const __nv_bfloat16* __restrict__ act, long long act_bs, int act_cb, int accumulate) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int Wp = W + 4, Hp = H + 4, H2 = 2 * H, W2 = 2 * W, W2p = W2 + 4, H2p = H2 + 4;
+  const __nv_bfloat16* dyc = dy + (size_t)b * dy_bs + (size_t)(dy_cb + chunk) * H2p * W2p * 8;
+  __nv_bfloat16* dxc = dx + (size_t)b * dx_bs + (size_t)(dx_cb + chunk) * Hp * Wp * 8;
+  const __nv_bfloat16* ac = act ? act + (size_t)b * act_bs + (size_t)(act_cb + chunk) * Hp * Wp * 8 : nullptr;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
+    const int u = e / W, v = e % W;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    for (int Y = max(2 * u - 1, 0); Y <= min(2 * u + 2, H2 - 1); ++Y) {
+      int y0, y1; float ly;
+      up2_src(Y, H, &y0, &y1, &ly);
+      const float wy = (y0 == u ? (1.f - ly) : 0.f) + (y1 == u ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int X = max(2 * v - 1, 0); X <= min(2 * v + 2, W2 - 1); ++X) {
+        int x0, x1; float lx;
+        up2_src(X, W, &x0, &x1, &lx);
+        const float wx = (x0 == v ? (1.f - lx) : 0.f) + (x1 == v ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        ld8(dyc + ((size_t)(Y + 2) * W2p + X + 2) * 8, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = fmaf(wy * wx, g[i], s[i]);
+      }
+    }
+    const size_t pix = ((size_t)(u + 2) * Wp + v + 2) * 8;
+    if (ac) {
+      float av[8];
+      ld8(ac + pix, av);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (!(av[i] > 0.f)) s[i] = 0.f;
+    }
+    if (accumulate) {
+      float old[8];
+      ld8(dxc + pix, old);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += old[i];
+    }
+    st8(dxc + pix, s);
+  }
+}
+
+// space-to-depth for the stride-2 layers: phase (py,px) plane p = py*2+px holds x[2y+py, 2x+px];
+// output chunk index = p*CB + chunk at half resolution.
+__global__ void __launch_bounds__(256)
+blk_space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, int x_cb, int CB, int H, int W,
+                          __nv_bfloat16* __restrict__ y, long long y_bs) {
+  const int b = blockIdx.z, chunk = blockIdx.y;
+  const int Hp = H + 4, Wp = W + 4, H2 = H / 2, W2 = W / 2, H2p = H2 + 4, W2p = W2 + 4;
+  const __nv_bfloat16* xc = x + (size_t)b * x_bs + (size_t)(x_cb + chunk) * Hp * Wp * 8;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
+    const int yy = e / W, xx = e % W;
+    const int p = (yy & 1) * 2 + (xx & 1);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xc + ((size_t)(yy + 2) * Wp + xx + 2) * 8));
+    __nv_bfloat16* yc = y + (size_t)b * y_bs + (size_t)(p * CB + chunk) * H2p * W2p * 8;
+    *reinterpret_cast<uint4*>(yc + ((size_t)(yy / 2 + 2) * W2p + xx / 2 + 2) * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side plan construction
+// ---------------------------------------------------------------------------------------------
+enum { KIND_K5S1 = 0, KIND_K1 = 1, KIND_K5S2 = 2, KIND_K5S1_DGRAD = 3, KIND_K1_DGRAD = 4, KIND_K5S2_DGRAD = 5 };
+
+int build_plan(int kind, int n_chunks, int pitch, int py, int px, cnp_conv_plan* p) {
+  memset(p, 0, sizeof(*p));
+  int st = 0;
+  auto add_ab = [&](int chunk0, int wci0) {
+    p->ab_chunk0[p->n_ab] = chunk0; p->ab_wci0[p->n_ab] = wci0; p->ab_stage0[p->n_ab] = st; ++p->n_ab;
+  };
+  auto add_tap = [&](int s, int aoff, int wky, int wkx) {
+    int t = p->st_ntap[s]++;
+    p->st_aoff[s][t] = (short)aoff; p->st_wky[s][t] = (signed char)wky; p->st_wkx[s][t] = (signed char)wkx;
+  };
+  if (kind == KIND_K5S1 || kind == KIND_K5S1_DGRAD) {
+    CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv plan: 5x5 needs 8 or 16 source chunks");
+    for (int g = 0; g < n_chunks / 4; ++g) {
+      add_ab(4 * g, 32 * g);
+      for (int ky = 0; ky < 5; ++ky, ++st)
+        for (int kx = 0; kx < 5; ++kx)
+          add_tap(st, ky * pitch + kx, kind == KIND_K5S1 ? ky : 4 - ky, kind == KIND_K5S1 ? kx : 4 - kx);
+    }
+  } else if (kind == KIND_K1 || kind == KIND_K1_DGRAD) {
+    CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv plan: 1x1 needs 8 or 16 source chunks");
+    for (int g = 0; g < n_chunks / 4; ++g) { add_ab(4 * g, 32 * g); add_tap(st, 2 * pitch + 2, 0, 0); ++st; }
+  } else if (kind == KIND_K5S2) {
+    CNP_REQUIRE(n_chunks == 32, "conv plan: stride-2 forward reads the 4x8-chunk phase tensor");
+    for (int ph = 0; ph < 4; ++ph) {
+      const int qy = ph >> 1, qx = ph & 1;
+      for (int half = 0; half < 2; ++half) {
+        add_ab(ph * 8 + 4 * half, 32 * half);
+        for (int ky = qy; ky < 5; ky += 2, ++st)
+          for (int kx = qx; kx < 5; kx += 2)
+            add_tap(st, (2 + (ky - 2 - qy) / 2) * pitch + 2 + (kx - 2 - qx) / 2, ky, kx);
+      }
+    }
+  } else if (kind == KIND_K5S2_DGRAD) {
+    CNP_REQUIRE(n_chunks == 8, "conv plan: stride-2 dgrad reads the 8-chunk dy tensor");
+    for (int half = 0; half < 2; ++half) {
+      add_ab(4 * half, 32 * half);
+      for (int ky = py; ky < 5; ky += 2, ++st)
+        for (int kx = px; kx < 5; kx += 2)
+          add_tap(st, (2 + (py + 2 - ky) / 2) * pitch + 2 + (px + 2 - kx) / 2, ky, kx);
+    }
+  } else {
+    CNP_REQUIRE(false, "conv plan: unknown kind %d", kind);
+  }
+  p->ab_stage0[p->n_ab] = st;
+  CNP_REQUIRE(st <= CNP_MAX_ST && p->n_ab <= CNP_MAX_AB, "conv plan: too many stages");
+  return 0;
+}
+
+// pick the tile (TW, TH) maximising useful MMA rows; (TW+4)*TH <= 512 window pixels (R <= 4)
+void choose_tile(int H, int W, int* TW, int* TH, int* R) {
+  double best = -1.0;
+  for (int tw = 4; tw <= 252 && tw <= W + 3; ++tw) {
+    const int pitch = tw + 4;
+    for (int th = 1; th <= 32; ++th) {
+      const int win = pitch * th;
+      if (win > 512) break;
+      const int r = (win + 127) / 128;
+      const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+      const double eff = (double)H * W / ((double)tiles * 128.0 * r);
+      // mild preference for fewer, larger tiles (less halo re-read, fewer barriers)
+      const double score = eff + 1e-4 * r;
+      if (score > best) { best = score; *TW = tw; *TH = th; *R = r; }
+    }
+  }
+}
+
+int fill_geometry(cnp_conv_args* a) {
+  int TW, TH, R;
+  choose_tile(a->H, a->W, &TW, &TH, &R);
+  a->TW = TW; a->TH = TH; a->R = R; a->pitch = TW + 4;
+  a->tiles_x = cnp_cdiv(a->W, TW); a->tiles_y = cnp_cdiv(a->H, TH);
+  a->plane_sm = 128 * R + 4 * a->pitch + 8;
+  return 0;
+}
+
+size_t conv_smem_bytes(const cnp_conv_args& a) {
+  return (size_t)A_BUFS * 4 * a.plane_sm * 16 + (size_t)W_STAGES * W_STAGE_BYTES + 16 * 8 + 16;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+struct cnp_blk {          // view of a blocked bf16 activation tensor
+  void* base;             // first element of batch 0, chunk 0
+  long long bstride;      // elements between batches
+  int cb_off;             // first chunk of the view
+  int H, W;               // interior size (planes are (H+4) x (W+4))
+};
+
+struct cnp_conv_out {
+  int mode;               // 0: blocked bf16 (blk), 1: NCHW fp32 (f32 / f32_bstride / f32_ch_off / H x W)
+  cnp_blk blk;
+  float* f32; long long f32_bstride; int f32_ch_off;
+  int sy, ay, sx, ax;     // output pixel = (y*sy+ay, x*sx+ax); (1,0,1,0) for a plain conv
+  const float* bias;      // [64] or NULL
+  int relu;
+  const cnp_blk* mask;    // zero the result where mask <= 0 (same geometry as the output) or NULL
+  int accumulate;
+};
+
+// Bytes of packed weights for (kind, n_chunks): stages x 20480.
+CNP_API long long cnp_conv_tc_packed_bytes(int kind, int n_chunks) {
+  cnp_conv_plan p;
+  if (build_plan(kind, n_chunks, 8, 0, 0, &p)) return -1;
+  return (long long)p.ab_stage0[p.n_ab] * W_STAGE_BYTES;
+}
+
+// Pack torch-layout fp32 weights [Cout][Cin][k][k] for conv_tc (see pack_weights_kernel).
+CNP_API int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px,
+                             int co_off, void* wpk, cudaStream_t st) {
+  cnp_conv_plan p;
+  if (int e = build_plan(kind, n_chunks, 8, py, px, &p)) return e;
+  const int transposed = (kind >= KIND_K5S1_DGRAD) ? 1 : 0;
+  pack_weights_kernel<<<64, 256, 0, st>>>(w, Cout, Cin, k, transposed, co_off, reinterpret_cast<__nv_bfloat16*>(wpk), p);
+  CNP_LAUNCH_CHECK("pack_weights_kernel");
+  return 0;
+}
+
+// Tensor-core convolution producing 64 output channels.  x: blocked source whose chunks
+// [x->cb_off, x->cb_off + n_chunks) are the K dimension; (x->H, x->W) is the accumulator grid.
+CNP_API int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px,
+                        const cnp_conv_out* o, int B, cudaStream_t st) {
+  CNP_REQUIRE(x && o && wpk && B > 0, "conv_tc: bad arguments");
+  cnp_conv_args a;
+  memset(&a, 0, sizeof(a));
+  a.H = x->H; a.W = x->W; a.B = B;
+  a.x_Hp = x->H + 4; a.x_Wp = x->W + 4;
+  a.x = reinterpret_cast<const __nv_bfloat16*>(x->base) + (long long)x->cb_off * a.x_Hp * a.x_Wp * 8;
+  a.x_bs = x->bstride;
+  a.w = reinterpret_cast<const __nv_bfloat16*>(wpk);
+  fill_geometry(&a);
+  if (int e = build_plan(kind, n_chunks, a.pitch, py, px, &a.plan)) return e;
+  a.out_mode = o->mode;
+  a.sy = o->sy; a.ay = o->ay; a.sx = o->sx; a.ax = o->ax;
+  CNP_REQUIRE(a.sy >= 1 && a.sx >= 1, "conv_tc: output scale must be >= 1");
+  if (o->mode == 0) {
+    CNP_REQUIRE(o->blk.H == x->H * o->sy && o->blk.W == x->W * o->sx, "conv_tc: output geometry mismatch");
+    a.out = o->blk.base; a.out_bs = o->blk.bstride; a.out_c_off = o->blk.cb_off;
+    a.out_Hp = o->blk.H + 4; a.out_Wp = o->blk.W + 4;
+    if (o->mask) {
+      CNP_REQUIRE(o->mask->H == o->blk.H && o->mask->W == o->blk.W, "conv_tc: mask geometry mismatch");
+      a.mask = reinterpret_cast<const __nv_bfloat16*>(o->mask->base);
+      a.mask_bs = o->mask->bstride; a.mask_cb_off = o->mask->cb_off;
+    }
+  } else {
+    CNP_REQUIRE(o->f32 && o->sy == 1 && o->sx == 1 && !o->mask, "conv_tc: fp32 NCHW output is plain only");
+    a.out = o->f32; a.out_bs = o->f32_bstride; a.out_c_off = o->f32_ch_off;
+    a.out_Hp = x->H; a.out_Wp = x->W;
+  }
+  a.bias = o->bias; a.relu = o->relu; a.accumulate = o->accumulate;
+  const size_t smem = conv_smem_bytes(a);
+  CNP_REQUIRE(smem <= 227 * 1024, "conv_tc: tile needs %zu B of shared memory", smem);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cnp_set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr = smem;
+  }
+  const int ntiles = B * a.tiles_x * a.tiles_y;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  conv_tc_kernel<<<grid, 256, smem, st>>>(a);
+  CNP_LAUNCH_CHECK("conv_tc_kernel");
+  return 0;
+}
+
+CNP_API int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B, int C, int H, int W,
+                                  const cnp_blk* dst, cudaStream_t st) {
+  CNP_REQUIRE(dst && dst->H == H && dst->W == W, "blk_from_nchw: geometry mismatch");
+  dim3 grid(min(cnp_cdiv(H * W, 256), 128), cnp_cdiv(C, 8), B);
+  nchw_to_blk_kernel<<<grid, 256, 0, st>>>(src, src_bstride, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst->base),
+                                           dst->bstride, dst->cb_off);
+  CNP_LAUNCH_CHECK("nchw_to_blk_kernel");
+  return 0;
+}
+
+CNP_API int cnp_blk_to_nchw_f32(const cnp_blk* src, int B, int C, float* dst, long long dst_bstride, cudaStream_t st) {
+  CNP_REQUIRE(src, "blk_to_nchw: null source");
+  dim3 grid(min(cnp_cdiv(src->H * src->W, 256), 128), cnp_cdiv(C, 8), B);
+  blk_to_nchw_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src->base), src->bstride, src->cb_off,
+                                           C, src->H, src->W, dst, dst_bstride);
+  CNP_LAUNCH_CHECK("blk_to_nchw_kernel");
+  return 0;
+}
+
+CNP_API int cnp_conv1x1_in_bf16(const float* x, long long x_bstride, const float* w, const float* bias, int B, int Cin,
+                                int Cout, const cnp_blk* out, cudaStream_t st) {
+  CNP_REQUIRE(out && Cin >= 1 && Cin <= IC_MAX_CIN && Cout >= 1 && Cout <= 64, "conv1x1_in: need Cin<=%d, Cout<=64", IC_MAX_CIN);
+  dim3 grid(min(cnp_cdiv(out->H * out->W, 256), 256), B);
+  conv1x1_in_kernel<<<grid, 256, 0, st>>>(x, x_bstride, Cin, out->H, out->W, w, bias, Cout,
+                                          reinterpret_cast<__nv_bfloat16*>(out->base), out->bstride, out->cb_off);
+  CNP_LAUNCH_CHECK("conv1x1_in_kernel");
+  return 0;
+}
+
+CNP_API int cnp_blk_upsample2x_fwd(const cnp_blk* x, int n_chunks, const cnp_blk* y, int B, cudaStream_t st) {
+  CNP_REQUIRE(x && y && y->H == 2 * x->H && y->W == 2 * x->W, "blk_upsample2x_fwd: geometry mismatch");
+  dim3 grid(min(cnp_cdiv(4 * x->H * x->W, 256), 128), n_chunks, B);
+  blk_upsample2x_fwd_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x->base), x->bstride, x->cb_off,
+                                                  x->H, x->W, reinterpret_cast<__nv_bfloat16*>(y->base), y->bstride,
+                                                  y->cb_off);
+  CNP_LAUNCH_CHECK("blk_upsample2x_fwd_kernel");
+  return 0;
+}
+
+CNP_API int cnp_blk_upsample2x_bwd(const cnp_blk* dy, int n_chunks, const cnp_blk* dx, const cnp_blk* act, int accumulate,
+                                   int B, cudaStream_t st) {
+  CNP_REQUIRE(dy && dx && dy->H == 2 * dx->H && dy->W == 2 * dx->W, "blk_upsample2x_bwd: geometry mismatch");
+  CNP_REQUIRE(!act || (act->H == dx->H && act->W == dx->W), "blk_upsample2x_bwd: mask geometry mismatch");
+  dim3 grid(min(cnp_cdiv(dx->H * dx->W, 256), 128), n_chunks, B);
+  blk_upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride, dy->cb_off, dx->H, dx->W,
+      reinterpret_cast<__nv_bfloat16*>(dx->base), dx->bstride, dx->cb_off,
+      act ? reinterpret_cast<const __nv_bfloat16*>(act->base) : nullptr, act ? act->bstride : 0, act ? act->cb_off : 0,
+      accumulate);
+  CNP_LAUNCH_CHECK("blk_upsample2x_bwd_kernel");
+  return 0;
+}
+
+CNP_API int cnp_blk_space_to_depth(const cnp_blk* x, int n_chunks, const cnp_blk* y, int B, cudaStream_t st) {
+  CNP_REQUIRE(x && y && x->H % 2 == 0 && x->W % 2 == 0 && y->H == x->H / 2 && y->W == x->W / 2 && y->cb_off == 0,
+              "blk_space_to_depth: geometry mismatch");
+  dim3 grid(min(cnp_cdiv(x->H * x->W, 256), 128), n_chunks, B);
+  blk_space_to_depth_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x->base), x->bstride, x->cb_off,
+                                                  n_chunks, x->H, x->W, reinterpret_cast<__nv_bfloat16*>(y->base),
+                                                  y->bstride);
+  CNP_LAUNCH_CHECK("blk_space_to_depth_kernel");
+  return 0;
+}

@@ -1,0 +1,267 @@
+// Fused aux-at-target MLP + heterogeneous Gaussian head + normalised NLL, forward and backward.
+//
+// Replaces upstream neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood ->
+// MultiOutputNormal.logpdf -> nps.loglik(normalise=True) (U11) as reached from
+// ConvNP.loss_fn (nzdownscale/downscaler/train.py:370) and train_epoch (train.py:388-394).
+//   o = MLP([f ; aux_t]);  mean = o0;  var = 1e-6 + softplus(o1);
+//   logp_b = -1/2 sum_t [log 2pi + log var + (y-mean)^2/var]   (float64, NaN targets skipped)
+// The backward recomputes the (tiny) forward instead of saving activations.
+#include "common.cuh"
+#include <math.h>
+
+#define CNP_MLP_MAX_LAYERS 6
+
+struct cnp_mlp_params {
+  const float* W[CNP_MLP_MAX_LAYERS];   // [out,in] row-major (torch Linear.weight)
+  const float* b[CNP_MLP_MAX_LAYERS];   // [out]
+  float* dW[CNP_MLP_MAX_LAYERS];        // (+=) gradients, backward only
+  float* db[CNP_MLP_MAX_LAYERS];
+  int dims[CNP_MLP_MAX_LAYERS + 1];     // dims[0] = Cf + Ca, dims[n_layers] = 2
+  int n_layers;
+};
+
+namespace {
+
+constexpr int MAXW = 160;  // max layer width (incl. input)
+
+struct Offsets {
+  int w[CNP_MLP_MAX_LAYERS];  // offset of padded W_l  ([out][in+1]) in the weight arena
+  int b[CNP_MLP_MAX_LAYERS];
+  int total;
+};
+
+__host__ __device__ inline Offsets make_offsets(const cnp_mlp_params& p) {
+  Offsets o;
+  int cur = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    o.w[l] = cur; cur += p.dims[l + 1] * (p.dims[l] + 1);
+    o.b[l] = cur; cur += p.dims[l + 1];
+  }
+  o.total = cur;
+  return o;
+}
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_t(float x) { return x > 20.f ? 1.f : 1.f / (1.f + expf(-x)); }
+
+__device__ void stage_weights(const cnp_mlp_params& p, const Offsets& o, float* ws) {
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int in = p.dims[l], out = p.dims[l + 1];
+    for (int e = threadIdx.x; e < in * out; e += blockDim.x) ws[o.w[l] + (e / in) * (in + 1) + (e % in)] = p.W[l][e];
+    for (int e = threadIdx.x; e < out; e += blockDim.x) ws[o.b[l] + e] = p.b[l][e];
+  }
+}
+
+// one warp evaluates layer l for one point: hout[o] = act(b[o] + sum_i W[o][i] hin[i])
+__device__ __forceinline__ void layer_fwd(const float* ws, const Offsets& o, const cnp_mlp_params& p, int l,
+                                          const float* hin, float* hout, int lane, bool relu) {
+  const int in = p.dims[l], out = p.dims[l + 1];
+  for (int oo = lane; oo < out; oo += 32) {
+    const float* wr = ws + o.w[l] + oo * (in + 1);
+    float s = ws[o.b[l] + oo];
+    for (int i = 0; i < in; ++i) s = fmaf(wr[i], hin[i], s);
+    hout[oo] = relu ? fmaxf(s, 0.f) : s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: grid (chunks, B), 8 warps, PTS points per block
+// ---------------------------------------------------------------------------------------------
+constexpr int FW_PTS = 64;
+
+__global__ void __launch_bounds__(256)
+mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
+                    const float* __restrict__ aux, int Ca, const float* __restrict__ yt, int Nt,
+                    float* __restrict__ mean, float* __restrict__ var, double* __restrict__ logp,
+                    int* __restrict__ count) {
+  extern __shared__ __align__(16) float smem[];
+  const Offsets o = make_offsets(p);
+  float* ws = smem;
+  float* act = smem + o.total;  // [8 warps][2][MAXW]
+  __shared__ double lp_s[8];
+  __shared__ int cnt_s[8];
+  stage_weights(p, o, ws);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+  float* ha = act + warp * 2 * MAXW;
+  float* hb = ha + MAXW;
+  double lp = 0.0;
+  int cnt = 0;
+  const int t0 = blockIdx.x * FW_PTS;
+  for (int t = t0 + warp; t < min(t0 + FW_PTS, Nt); t += 8) {
+    for (int c = lane; c < Cf; c += 32) ha[c] = f[((size_t)b * f_ctotal + c) * Nt + t];
+    for (int c = lane; c < Ca; c += 32) ha[Cf + c] = aux[((size_t)b * Ca + c) * Nt + t];
+    __syncwarp();
+    float* hin = ha; float* hout = hb;
+    for (int l = 0; l < p.n_layers; ++l) {
+      layer_fwd(ws, o, p, l, hin, hout, lane, l < p.n_layers - 1);
+      __syncwarp();
+      float* tmp = hin; hin = hout; hout = tmp;
+    }
+    if (lane == 0) {
+      const float m = hin[0], v = 1e-6f + softplus_t(hin[1]);
+      mean[(size_t)b * Nt + t] = m;
+      var[(size_t)b * Nt + t] = v;
+      if (yt) {
+        const float yv = yt[(size_t)b * Nt + t];
+        if (!isnan(yv)) {
+          const double dm = (double)yv - (double)m, dv = (double)v;
+          lp += -0.5 * (1.8378770664093453 + log(dv) + dm * dm / dv);
+          cnt += 1;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (logp) {
+    if (lane == 0) { lp_s[warp] = lp; cnt_s[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0; int c = 0;
+      for (int w = 0; w < 8; ++w) { s += lp_s[w]; c += cnt_s[w]; }
+      atomicAdd(logp + b, s);
+      atomicAdd(count + b, c);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: grid (chunks, B), BW_PTS points per block
+//   dlogp[b] = d loss / d logp_b (already includes -1/(B*N_b)); outputs df (first Cf channels),
+//   dW_l, db_l (+= via atomics once per block)
+// ---------------------------------------------------------------------------------------------
+constexpr int BW_PTS = 32;
+
+__global__ void __launch_bounds__(256)
+mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
+                    const float* __restrict__ aux, int Ca, const float* __restrict__ yt, int Nt,
+                    const float* __restrict__ dlogp, float* __restrict__ df) {
+  extern __shared__ __align__(16) float smem[];
+  const Offsets o = make_offsets(p);
+  const int L = p.n_layers;
+  float* ws = smem;                       // weights
+  float* acts = ws + o.total;             // per layer input: sum_l dims[l] per point
+  int aoff[CNP_MLP_MAX_LAYERS + 1], goff[CNP_MLP_MAX_LAYERS + 1];
+  int asum = 0, gsum = 0;
+  for (int l = 0; l < L; ++l) { aoff[l] = asum; asum += p.dims[l]; goff[l] = gsum; gsum += p.dims[l + 1]; }
+  float* dpre = acts + asum * BW_PTS;     // per layer pre-activation grads
+  float* scratch = dpre + gsum * BW_PTS;  // [8 warps][MAXW]
+  stage_weights(p, o, ws);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+  const int t0 = blockIdx.x * BW_PTS;
+  const int npts = min(BW_PTS, Nt - t0);
+  const float gl = dlogp[b];
+  float* tmp = scratch + warp * MAXW;
+
+  for (int pt = warp; pt < npts; pt += 8) {
+    const int t = t0 + pt;
+    float* a0 = acts + aoff[0] * BW_PTS + pt * p.dims[0];
+    for (int c = lane; c < Cf; c += 32) a0[c] = f[((size_t)b * f_ctotal + c) * Nt + t];
+    for (int c = lane; c < Ca; c += 32) a0[Cf + c] = aux[((size_t)b * Ca + c) * Nt + t];
+    __syncwarp();
+    // forward, keeping every layer input
+    for (int l = 0; l < L; ++l) {
+      const float* hin = acts + aoff[l] * BW_PTS + pt * p.dims[l];
+      float* hout = (l + 1 < L) ? acts + aoff[l + 1] * BW_PTS + pt * p.dims[l + 1] : tmp;
+      layer_fwd(ws, o, p, l, hin, hout, lane, l < L - 1);
+      __syncwarp();
+    }
+    // head gradient
+    float* gL = dpre + goff[L - 1] * BW_PTS + pt * p.dims[L];
+    if (lane == 0) {
+      const float m = tmp[0], z1 = tmp[1], v = 1e-6f + softplus_t(z1);
+      const float yv = yt[(size_t)b * Nt + t];
+      float dm = 0.f, dz = 0.f;
+      if (!isnan(yv)) {
+        const float r = yv - m;
+        dm = gl * (r / v);
+        const float dvv = gl * (-0.5f) * (1.f / v - r * r / (v * v));
+        dz = dvv * sigmoid_t(z1);
+      }
+      gL[0] = dm; gL[1] = dz;
+    }
+    __syncwarp();
+    // backward through the layers
+    for (int l = L - 1; l >= 0; --l) {
+      const int in = p.dims[l], out = p.dims[l + 1];
+      const float* g = dpre + goff[l] * BW_PTS + pt * out;
+      const float* hin = acts + aoff[l] * BW_PTS + pt * in;
+      for (int i = lane; i < in; i += 32) {
+        float s = 0.f;
+        for (int oo = 0; oo < out; ++oo) s = fmaf(ws[o.w[l] + oo * (in + 1) + i], g[oo], s);
+        if (l > 0) {
+          dpre[goff[l - 1] * BW_PTS + pt * in + i] = (hin[i] > 0.f) ? s : 0.f;
+        } else if (i < Cf) {
+          df[((size_t)b * f_ctotal + i) * Nt + t] = s;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // weight / bias gradients for this block's points
+  for (int l = 0; l < L; ++l) {
+    const int in = p.dims[l], out = p.dims[l + 1];
+    const float* A = acts + aoff[l] * BW_PTS;
+    const float* G = dpre + goff[l] * BW_PTS;
+    for (int e = threadIdx.x; e < in * out; e += blockDim.x) {
+      const int oo = e / in, i = e % in;
+      float s = 0.f;
+      for (int pt = 0; pt < npts; ++pt) s = fmaf(G[pt * out + oo], A[pt * in + i], s);
+      atomicAdd(p.dW[l] + e, s);
+    }
+    for (int oo = threadIdx.x; oo < out; oo += blockDim.x) {
+      float s = 0.f;
+      for (int pt = 0; pt < npts; ++pt) s += G[pt * out + oo];
+      atomicAdd(p.db[l] + oo, s);
+    }
+  }
+}
+
+int check_params(const cnp_mlp_params* p, int Cf, int Ca) {
+  CNP_REQUIRE(p && p->n_layers >= 1 && p->n_layers <= CNP_MLP_MAX_LAYERS, "mlp_head: 1..%d layers", CNP_MLP_MAX_LAYERS);
+  CNP_REQUIRE(p->dims[0] == Cf + Ca, "mlp_head: dims[0]=%d != Cf+Ca=%d", p->dims[0], Cf + Ca);
+  CNP_REQUIRE(p->dims[p->n_layers] == 2, "mlp_head: last layer must have 2 outputs (mean, pre-softplus var)");
+  for (int l = 0; l <= p->n_layers; ++l)
+    CNP_REQUIRE(p->dims[l] >= 1 && p->dims[l] <= MAXW, "mlp_head: layer width %d out of range (<=%d)", p->dims[l], MAXW);
+  return 0;
+}
+
+}  // namespace
+
+CNP_API int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
+                             const float* yt, int B, int Nt, float* mean, float* var, double* logp, int* count,
+                             cudaStream_t st) {
+  if (int e = check_params(p, Cf, Ca)) return e;
+  CNP_REQUIRE(B > 0 && Nt >= 0 && f_ctotal >= Cf, "mlp_head_fwd: bad sizes");
+  CNP_REQUIRE(logp == nullptr || (yt != nullptr && count != nullptr), "mlp_head_fwd: logp needs yt and count");
+  if (Nt == 0) return 0;
+  const Offsets o = make_offsets(*p);
+  const size_t smem = (size_t)(o.total + 8 * 2 * MAXW) * sizeof(float);
+  CNP_REQUIRE(smem <= 200 * 1024, "mlp_head_fwd: MLP too large for shared memory (%zu B)", smem);
+  cudaFuncSetAttribute(mlp_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(cnp_cdiv(Nt, FW_PTS), B);
+  mlp_head_fwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, mean, var, logp, count);
+  CNP_LAUNCH_CHECK("mlp_head_fwd_kernel");
+  return 0;
+}
+
+CNP_API int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
+                             const float* yt, int B, int Nt, const float* dlogp, float* df, cudaStream_t st) {
+  if (int e = check_params(p, Cf, Ca)) return e;
+  CNP_REQUIRE(B > 0 && Nt >= 0 && f_ctotal >= Cf && yt && dlogp && df, "mlp_head_bwd: bad arguments");
+  for (int l = 0; l < p->n_layers; ++l) CNP_REQUIRE(p->dW[l] && p->db[l], "mlp_head_bwd: missing gradient buffers");
+  if (Nt == 0) return 0;
+  const Offsets o = make_offsets(*p);
+  int asum = 0, gsum = 0;
+  for (int l = 0; l < p->n_layers; ++l) { asum += p->dims[l]; gsum += p->dims[l + 1]; }
+  const size_t smem = (size_t)(o.total + (asum + gsum) * BW_PTS + 8 * MAXW) * sizeof(float);
+  CNP_REQUIRE(smem <= 220 * 1024, "mlp_head_bwd: MLP too large for shared memory (%zu B)", smem);
+  cudaFuncSetAttribute(mlp_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(cnp_cdiv(Nt, BW_PTS), B);
+  mlp_head_bwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, dlogp, df);
+  CNP_LAUNCH_CHECK("mlp_head_bwd_kernel");
+  return 0;
+}

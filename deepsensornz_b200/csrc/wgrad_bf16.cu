@@ -1,0 +1,284 @@
+// bf16 weight gradient of the UNet convolutions on tcgen05 (sm_100a).
+//
+//   dW[co][ci][ky][kx] += sum_{b,y,x} dY[b,co,y,x] * X[b,ci, s*y+ky-2, s*x+kx-2]
+//
+// (torch autograd of Conv2d inside upstream neuralprocesses' UNet, reached from
+// mean_batch_loss.backward() in deepsensor.train.train_epoch -- nzdownscale/downscaler/train.py:388-394.)
+//
+// GEMM view: D[ci, co] = sum_p Xs[p, ci] * dY[p, co] with the reduction over pixels p.  Both blocked
+// tensors ([chunk][pixel][8 ch]) are *MN-major* UMMA operands as they lie in memory: 8 channels are
+// contiguous (16 B) and consecutive pixels are 16 B apart, so a run of pixels copied with one
+// cp.async.bulk per chunk plane is directly a SWIZZLE_NONE MN-major tile (SBO = plane stride,
+// LBO = 128 B).  The reduction runs over the padded image in *linear* pixel order: the zero pad of dY
+// annihilates every out-of-image product, so no 2-D tiling or boundary logic is needed, and a tap
+// (ky,kx) is a constant linear shift of X.  One CTA owns one kernel row ky (a "pass") and keeps its
+// taps as separate M=128 x N=64 fp32 accumulators in TMEM for the whole K loop:
+//   * 128-channel inputs: M = the 16 chunks, one accumulator per kx (5 x 64 TMEM columns);
+//   * 64-channel inputs : M = [8 chunks ; the same 8 chunks shifted by 3 pixels], so one MMA yields
+//     taps kx and kx+3 (3 accumulators);
+//   * stride-2 layers   : M = [phase (py,0) ; phase (py,1)] of the space-to-depth tensor.
+// K is split across CTAs; partial sums are reduced with fp32 atomics straight into the torch-layout
+// gradient.
+#include "tc_common.cuh"
+
+#define CNP_WG_MAX_PASS 5
+#define CNP_WG_MAX_ACC 5
+
+struct cnp_blk {
+  void* base; long long bstride; int cb_off; int H, W;
+};
+
+struct cnp_wg_pass {
+  int chunk0;        // first source chunk of the M operand
+  int shift_px;      // >=0: planes 8..15 = chunks chunk0..chunk0+7 shifted by shift_px pixels; -1: real chunks 8..15
+  int base_off;      // linear pixel offset of the X tile relative to the dY tile
+  int n_acc;
+  int a_off[CNP_WG_MAX_ACC];
+  int slot0[CNP_WG_MAX_ACC];   // tap index (ky*k+kx) of rows 0..63, -1 = discard
+  int slot1[CNP_WG_MAX_ACC];   // tap index of rows 64..127
+  int ci0, ci1;                // input-channel base of the two halves
+};
+
+struct cnp_wg_args {
+  const __nv_bfloat16* x; long long x_bs; long long x_plane;   // elements
+  const __nv_bfloat16* dy; long long dy_bs; long long dy_plane;
+  float* dw; int Cin, KK;
+  int B, P, p_start, tiles_per_img, ksplit, n_pass;
+  cnp_wg_pass pass[CNP_WG_MAX_PASS];
+};
+
+namespace {
+
+constexpr int WG_STAGES = 3;
+constexpr int XPAD = 8;  // extra pixels per X plane in shared memory (max tap offset 4, keeps 128 B alignment)
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int P = a.P;
+  const int x_plane_b = (P + XPAD) * 16, dy_plane_b = P * 16;
+  const int x_tile_b = 16 * x_plane_b, dy_tile_b = 8 * dy_plane_b;
+  const int stage_b = x_tile_b + dy_tile_b;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * stage_b);
+  uint64_t* full = bars;                 // [WG_STAGES]
+  uint64_t* empty = bars + WG_STAGES;    // [WG_STAGES]
+  uint64_t* done = bars + 2 * WG_STAGES; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WG_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const cnp_wg_pass& ps = a.pass[blockIdx.y];
+  const int total_tiles = a.B * a.tiles_per_img;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    tc::mbar_init(done, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
+        const int s = it % WG_STAGES;
+        tc::mbar_wait(empty + s, ((it / WG_STAGES) & 1) ^ 1);
+        const int b = t / a.tiles_per_img, ti = t % a.tiles_per_img;
+        const long long p0 = a.p_start + (long long)ti * P;
+        uint8_t* xs = smem + s * stage_b;
+        uint8_t* ds = xs + x_tile_b;
+        tc::mbar_expect_tx(full + s, 16u * (uint32_t)(P + 4) * 16u + 8u * (uint32_t)P * 16u);
+        const __nv_bfloat16* xb = a.x + (long long)b * a.x_bs + (p0 + ps.base_off) * 8;
+        for (int c = 0; c < 16; ++c) {
+          const __nv_bfloat16* src;
+          if (c < 8 || ps.shift_px < 0) src = xb + (long long)(ps.chunk0 + c) * a.x_plane;
+          else src = xb + (long long)(ps.chunk0 + c - 8) * a.x_plane + (long long)ps.shift_px * 8;
+          tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + 4) * 16u, full + s);
+        }
+        const __nv_bfloat16* db = a.dy + (long long)b * a.dy_bs + p0 * 8;
+        for (int c = 0; c < 8; ++c)
+          tc::bulk_g2s(ds + c * dy_plane_b, db + (long long)c * a.dy_plane, (uint32_t)P * 16u, full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
+        const int s = it % WG_STAGES;
+        tc::mbar_wait(full + s, (it / WG_STAGES) & 1);
+        tc::fence_after_sync();
+        const uint32_t xs = tc::smem_u32(smem + s * stage_b);
+        const uint32_t ds = xs + x_tile_b;
+        for (int ks = 0; ks < P / 16; ++ks) {
+          const uint64_t bdesc = tc::make_smem_desc(ds + ks * 256, 128, dy_plane_b);
+          for (int j = 0; j < ps.n_acc; ++j) {
+            const uint64_t adesc = tc::make_smem_desc(xs + (ps.a_off[j] + ks * 16) * 16, 128, x_plane_b);
+            tc::mma_bf16_ss(tmem_base + j * 64, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        tc::mma_commit(empty + s);
+      }
+      tc::mma_commit(done);
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM lane quadrant (warp & 3)
+    const int q = warp & 3;
+    const bool has_work = blockIdx.x < total_tiles;
+    if (has_work) {
+      tc::mbar_wait(done, 0);
+      tc::fence_after_sync();
+      const int m = q * 32 + lane;
+      const int half = m >> 6;
+      const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
+      for (int j = 0; j < ps.n_acc; ++j) {
+        const int slot = half ? ps.slot1[j] : ps.slot0[j];
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 64 + hc * 32, v);
+          tc::tmem_ld_wait();
+          if (slot >= 0 && ci < a.Cin) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int co = hc * 32 + i;
+              atomicAdd(a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot, v[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// per-channel sum of a blocked tensor: out[c] += sum_{b,y,x} v[b,c,y,x]   (bias gradients)
+__global__ void __launch_bounds__(256)
+blk_channel_sum_kernel(const __nv_bfloat16* __restrict__ v, long long bs, int cb_off, int H, int W, int B,
+                       float* __restrict__ out) {
+  __shared__ float red[8][8];
+  const int chunk = blockIdx.x;
+  const int Hp = H + 4, Wp = W + 4;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  const long long total = (long long)B * H * W;
+  for (long long e = (long long)blockIdx.y * 256 + threadIdx.x; e < total; e += (long long)gridDim.y * 256) {
+    const int b = (int)(e / (H * W)), r = (int)(e % (H * W));
+    const int y = r / W, x = r % W;
+    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(
+        v + (size_t)b * bs + (((size_t)(cb_off + chunk) * Hp + y + 2) * Wp + x + 2) * 8));
+    const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += __bfloat162float(pb[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x >> 5][i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + chunk * 8 + threadIdx.x, t);
+  }
+}
+
+}  // namespace
+
+enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2 };
+
+// dw (+=) torch layout [64][Cin][k][k] fp32.  x: source view (n_chunks = 8 or 16; 32 = phase tensor for
+// the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
+CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, int Cin,
+                              int B, cudaStream_t st) {
+  CNP_REQUIRE(x && dy && dw && B > 0, "conv_tc_wgrad: bad arguments");
+  CNP_REQUIRE(x->H == dy->H && x->W == dy->W, "conv_tc_wgrad: x and dy must share the accumulator geometry");
+  cnp_wg_args a;
+  memset(&a, 0, sizeof(a));
+  const int H = dy->H, W = dy->W, Hp = H + 4, Wp = W + 4;
+  a.x_plane = (long long)Hp * Wp * 8; a.dy_plane = a.x_plane;
+  a.x = reinterpret_cast<const __nv_bfloat16*>(x->base) + (long long)x->cb_off * a.x_plane; a.x_bs = x->bstride;
+  a.dy = reinterpret_cast<const __nv_bfloat16*>(dy->base) + (long long)dy->cb_off * a.dy_plane; a.dy_bs = dy->bstride;
+  a.dw = dw; a.Cin = Cin; a.B = B;
+  // reduction tile: the zero pad after the last interior pixel (2*Wp+2 pixels) must cover the overshoot
+  a.P = (2 * Wp + 2 >= 128) ? 128 : (2 * Wp + 2 >= 64 ? 64 : 32);
+  CNP_REQUIRE(2 * Wp + 2 >= a.P, "conv_tc_wgrad: image too narrow");
+  a.p_start = 2 * Wp + 2;
+  const int p_end = (H + 1) * Wp + W + 2;
+  a.tiles_per_img = cnp_cdiv(p_end - a.p_start, a.P);
+  int np = 0;
+  if (kind == WG_K5S1) {
+    CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv_tc_wgrad: 5x5 needs 8 or 16 source chunks");
+    CNP_REQUIRE(Cin == n_chunks * 8, "conv_tc_wgrad: Cin mismatch");
+    a.KK = 25;
+    for (int ky = 0; ky < 5; ++ky, ++np) {
+      cnp_wg_pass& p = a.pass[np];
+      p.chunk0 = 0; p.base_off = (ky - 2) * Wp - 2; p.ci0 = 0;
+      if (n_chunks == 16) {
+        p.shift_px = -1; p.ci1 = 64; p.n_acc = 5;
+        for (int kx = 0; kx < 5; ++kx) { p.a_off[kx] = kx; p.slot0[kx] = ky * 5 + kx; p.slot1[kx] = ky * 5 + kx; }
+      } else {
+        p.shift_px = 3; p.ci1 = 0; p.n_acc = 3;
+        for (int kx = 0; kx < 3; ++kx) {
+          p.a_off[kx] = kx; p.slot0[kx] = ky * 5 + kx; p.slot1[kx] = (kx + 3 < 5) ? ky * 5 + kx + 3 : -1;
+        }
+      }
+    }
+  } else if (kind == WG_K1) {
+    CNP_REQUIRE(n_chunks == 8 && Cin == 64, "conv_tc_wgrad: 1x1 needs an 8-chunk source");
+    a.KK = 1;
+    cnp_wg_pass& p = a.pass[np++];
+    p.chunk0 = 0; p.shift_px = 0; p.base_off = 0; p.n_acc = 1; p.a_off[0] = 0; p.slot0[0] = 0; p.slot1[0] = -1;
+  } else if (kind == WG_K5S2) {
+    CNP_REQUIRE(n_chunks == 32 && Cin == 64, "conv_tc_wgrad: stride-2 reads the 32-chunk phase tensor");
+    a.KK = 25;
+    for (int py = 0; py < 2; ++py)
+      for (int ky = py; ky < 5; ky += 2, ++np) {
+        cnp_wg_pass& p = a.pass[np];
+        const int dyy = (ky - 2 - py) / 2;
+        p.chunk0 = 16 * py; p.shift_px = -1; p.base_off = dyy * Wp - 1; p.ci0 = 0; p.ci1 = 0; p.n_acc = 3;
+        for (int j = 0; j < 3; ++j) {
+          p.a_off[j] = j; p.slot0[j] = ky * 5 + 2 * j; p.slot1[j] = (2 * j + 1 < 5) ? ky * 5 + 2 * j + 1 : -1;
+        }
+      }
+  } else {
+    CNP_REQUIRE(false, "conv_tc_wgrad: unknown kind %d", kind);
+  }
+  a.n_pass = np;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int total_tiles = B * a.tiles_per_img;
+  a.ksplit = sms / np;
+  if (a.ksplit > total_tiles) a.ksplit = total_tiles;
+  if (a.ksplit < 1) a.ksplit = 1;
+  const size_t stage_b = (size_t)16 * (a.P + XPAD) * 16 + (size_t)8 * a.P * 16;
+  const size_t smem = WG_STAGES * stage_b + (2 * WG_STAGES + 1) * 8 + 16;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cnp_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr = smem;
+  }
+  dim3 grid(a.ksplit, np);
+  wgrad_tc_kernel<<<grid, 192, smem, st>>>(a);
+  CNP_LAUNCH_CHECK("wgrad_tc_kernel");
+  return 0;
+}
+
+CNP_API int cnp_blk_channel_sum(const cnp_blk* v, int n_chunks, int B, float* out, cudaStream_t st) {
+  CNP_REQUIRE(v && out && n_chunks > 0 && B > 0, "blk_channel_sum: bad arguments");
+  dim3 grid(n_chunks, 32);
+  blk_channel_sum_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(v->base), v->bstride, v->cb_off,
+                                               v->H, v->W, B, out);
+  CNP_LAUNCH_CHECK("blk_channel_sum_kernel");
+  return 0;
+}

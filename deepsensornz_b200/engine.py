@@ -1,0 +1,585 @@
+"""Forward / backward orchestration of the ConvNP hot path over libconvnp_b200.so.
+
+One ``Engine`` per model.  It owns the device workspaces, launches the C-ABI kernels on the current
+CUDA stream in the order of upstream ``nps.Model.__call__`` + ``nps.loglik``:
+
+    SetConv encoder (1) -> UNet (2) -> SetConv decoder (3) -> aux MLP + Gaussian head + NLL (4)
+
+and runs the hand-written backward of (4), (3) and (2) (the encoder has no trainable inputs).
+Two numeric modes:
+  * ``fp32``  : everything fp32 on NCHW tensors (CUDA-core convolutions) -- the 1e-5 parity mode;
+  * ``bf16``  : UNet activations/weights in bf16 on the blocked layout, tcgen05 implicit-GEMM
+                convolutions with fp32 accumulation; encoder, decoder, head stay fp32.
+PyTorch is used for device memory, streams and the tiny [B]-sized loss algebra only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import CnpBlk, CnpConvOut, CnpMlpParams
+from .discretisation import GridSpec, discretise
+from .model import ConvNPConfig, ConvNPModule
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class DeviceContext:
+    gridded: bool
+    x: Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]  # off-grid [B,2,N] | (x1 [Bx,N1], x2 [Bx,N2])
+    y: torch.Tensor                                             # [B,C,N] | [B,C,N1,N2]  (may hold NaN)
+    mask: Optional[torch.Tensor]                                # [B,1,N] | [B,1,N1,N2] | None
+    mono: Tuple[int, int] = (0, 0)
+    x_batched: bool = False
+
+
+@dataclass
+class DeviceBatch:
+    """One (possibly concatenated) task resident in HBM."""
+    contexts: List[DeviceContext]
+    xt: torch.Tensor            # [B,2,Nt]
+    yt: Optional[torch.Tensor]  # [B,1,Nt]
+    aux_t: Optional[torch.Tensor]  # [B,Ca,Nt]
+    grid: GridSpec
+    B: int
+    Nt: int
+    h2d_bytes: int = 0
+
+
+def _monotone(v: np.ndarray) -> int:
+    d = np.diff(v.astype(np.float64))
+    if d.size == 0 or np.all(d > 0):
+        return 1
+    if np.all(d < 0):
+        return -1
+    return 0
+
+
+def _mono_rows(rows: np.ndarray) -> int:
+    kinds = {_monotone(r) for r in rows}
+    return kinds.pop() if len(kinds) == 1 else 0
+
+
+class _Blk:
+    """A blocked bf16 activation buffer [B][CB][H+4][W+4][8] with a zeroed 2-pixel pad."""
+
+    def __init__(self, B: int, CB: int, H: int, W: int, device):
+        self.B, self.CB, self.H, self.W = B, CB, H, W
+        self.plane = (H + 4) * (W + 4) * 8
+        self.bstride = CB * self.plane
+        slack = (16 * (W + 4) + 512) * 8  # tile over-reads past the last plane stay inside the allocation
+        self.t = torch.zeros(B * self.bstride + slack, dtype=torch.bfloat16, device=device)
+
+    def view(self, cb_off: int = 0) -> CnpBlk:
+        return CnpBlk(self.t.data_ptr(), self.bstride, cb_off, self.H, self.W)
+
+    def zero_(self):
+        self.t.zero_()
+
+
+class Engine:
+    def __init__(self, module: ConvNPModule, precision: str = "fp32"):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.module = module
+        self.cfg: ConvNPConfig = module.cfg
+        self.precision = precision
+        if self.cfg.dim_aux_t <= 0:
+            raise NotImplementedError("the hot path expects aux-at-target channels (dim_aux_t > 0), as the "
+                                      "reference always configures (train.py:160-166)")
+        if precision == "bf16" and any(c != 64 for c in self.cfg.unet_channels):
+            raise NotImplementedError("bf16 tensor-core path is specialised for unet_channels=(64,)*L")
+        self._ws: Dict[tuple, object] = {}
+        self._packed: Dict[str, Tuple[int, torch.Tensor]] = {}
+        self.allreduce_group = None   # set by dist.enable_data_parallel
+        self.world_size = 1
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.module.decoder.unet.initial_linear.weight.device
+
+    def _require_cuda(self):
+        if self.device.type != "cuda":
+            raise _cabi.CnpError("ConvNP parameters are not on a CUDA device: the hot path has no CPU fallback "
+                                 "(call set_gpu_default_device() before building the model, or model.model.cuda())")
+        _cabi.lib()
+
+    def _call(self, name, *args):
+        self.launches += 1
+        _cabi.call(name, *args)
+
+    def _buf(self, key, shape, dtype=torch.float32, zero=False):
+        k = (key, tuple(shape), dtype)
+        t = self._ws.get(k)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.device) if zero else \
+                torch.empty(shape, dtype=dtype, device=self.device)
+            self._ws[k] = t
+        return t
+
+    def _blk(self, key, B, CB, H, W) -> _Blk:
+        k = (key, B, CB, H, W, "blk")
+        t = self._ws.get(k)
+        if t is None:
+            t = _Blk(B, CB, H, W, self.device)
+            self._ws[k] = t
+        return t
+
+    def release_workspaces(self):
+        self._ws.clear()
+        self._packed.clear()
+
+    def _scale2(self, log_scale: torch.Tensor) -> float:
+        return float(np.float32(math.exp(2.0 * float(log_scale))))
+
+    # ------------------------------------------------------------------------------------------
+    # host -> device
+    # ------------------------------------------------------------------------------------------
+    def prepare(self, contexts, xt, yt, aux_t, pinned: bool = False) -> DeviceBatch:
+        """contexts: list of (x, y, mask|None) numpy/torch CPU arrays with a leading batch axis.
+        NaNs may stay in ``y`` (the kernels derive validity on the fly)."""
+        self._require_cuda()
+        dev = self.device
+        nbytes = 0
+
+        def up(a, dtype=torch.float32):
+            nonlocal nbytes
+            if a is None:
+                return None
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            if t.device.type != "cuda":
+                t = t.to(dtype).contiguous()
+                nbytes += t.numel() * t.element_size()
+                if pinned and not t.is_pinned():
+                    t = t.pin_memory()
+                return t.to(dev, non_blocking=True)
+            return t.to(dtype).contiguous()
+
+        def host(a):
+            return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+        if isinstance(xt, tuple):
+            raise NotImplementedError("on-grid targets go through Engine.predict_grid")
+        xs_for_grid = [c[0] for c in contexts] + [xt]
+        xs_for_grid = [tuple(host(v) for v in x) if isinstance(x, tuple) else host(x) for x in xs_for_grid]
+        grid = discretise(xs_for_grid, self.cfg.points_per_unit, self.cfg.margin, self.cfg.grid_multiple)
+        B = int(host(xt).shape[0])
+        dctx = []
+        for (x, y, m), xh in zip(contexts, xs_for_grid[:-1]):
+            if isinstance(x, tuple):
+                x1h, x2h = xh
+                x1h = x1h.reshape(x1h.shape[0], -1)
+                x2h = x2h.reshape(x2h.shape[0], -1)
+                shared = all(np.array_equal(x1h[0], x1h[i]) and np.array_equal(x2h[0], x2h[i])
+                             for i in range(1, x1h.shape[0]))
+                mono1, mono2 = _mono_rows(x1h), _mono_rows(x2h)
+                if shared:
+                    x1h, x2h = x1h[:1], x2h[:1]
+                dctx.append(DeviceContext(True, (up(x1h), up(x2h)), up(y), up(m), (mono1, mono2), not shared))
+            else:
+                dctx.append(DeviceContext(False, up(x), up(y), up(m)))
+        xt_d, yt_d, aux_d = up(xt), up(yt), up(aux_t)
+        return DeviceBatch(dctx, xt_d, yt_d, aux_d, grid, B, int(xt_d.shape[-1]), nbytes)
+
+    # ------------------------------------------------------------------------------------------
+    # (1) encoder
+    # ------------------------------------------------------------------------------------------
+    def encode(self, batch: DeviceBatch) -> torch.Tensor:
+        cfg, g, B = self.cfg, batch.grid, batch.B
+        enc = self._buf("enc", (B, cfg.in_channels, g.n1, g.n2))
+        ch = 0
+        for k, c in enumerate(batch.contexts):
+            s2 = self._scale2(self.module.encoder.set_convs[k].log_scale)
+            Ck = cfg.dim_yc[k]
+            if c.y.shape[1] != Ck:
+                raise ValueError(f"context set {k}: expected {Ck} channels, got {c.y.shape[1]}")
+            if c.gridded:
+                x1, x2 = c.x
+                self._call("cnp_setconv_enc_grid_fwd", _ptr(x1), _ptr(x2), int(c.x_batched), _ptr(c.y), _ptr(c.mask),
+                           B, Ck, int(x1.shape[-1]), int(x2.shape[-1]), c.mono[0], c.mono[1],
+                           g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
+                           _stream())
+            else:
+                self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
+                           int(c.x.shape[-1]), g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch,
+                           cfg.in_channels, _stream())
+            ch += Ck + 1
+        return enc
+
+    # ------------------------------------------------------------------------------------------
+    # (2) UNet, fp32 path
+    # ------------------------------------------------------------------------------------------
+    def _levels(self, n1, n2):
+        res = []
+        h, w = n1, n2
+        for s in self.cfg.unet_strides:
+            h, w = h // s, w // s
+            res.append((h, w))
+        return res
+
+    def _conv_f32(self, x, w, b, y, k, stride, relu):
+        Bn, Cin, H, W = x.shape
+        self._call("cnp_conv2d_fwd_f32", _ptr(x), x.stride(0), _ptr(w), _ptr(b), _ptr(y), y.stride(0), Bn, Cin, H, W,
+                   y.shape[1], k, stride, int(relu), _stream())
+
+    def _unet_fwd_f32(self, enc: torch.Tensor, B: int, n1: int, n2: int) -> Tuple[torch.Tensor, dict]:
+        cfg, u = self.cfg, self.module.decoder.unet
+        ch, st = cfg.unet_channels, cfg.unet_strides
+        L = len(ch)
+        res = self._levels(n1, n2)
+        A = {}
+        h_init = self._buf("h_init", (B, ch[0], n1, n2))
+        self._conv_f32(enc, u.initial_linear.weight, u.initial_linear.bias, h_init, 1, 1, False)
+        A["h_init"] = h_init
+        # skip buffers: cat[i] holds [hs[i] ; h from level i+1] for i < L-1, hs[L-1] alone
+        cat = []
+        for i in range(L):
+            c = ch[i] if i == L - 1 else 2 * ch[i]
+            cat.append(self._buf(f"cat{i}", (B, c, res[i][0], res[i][1])))
+        A["cat"] = cat
+        x = h_init
+        for i in range(L):
+            lyr = u.before_turn_layers[i]
+            y = cat[i][:, :ch[i]]
+            self._conv_f32(x, lyr.weight, lyr.bias, y, 5, st[i], True)
+            x = y
+        ups = [None] * L
+        h = None
+        for i in range(L - 1, -1, -1):
+            inp = cat[i]
+            if st[i] == 2:
+                up = self._buf(f"up{i}", (B, inp.shape[1], 2 * res[i][0], 2 * res[i][1]))
+                self._call("cnp_upsample2x_fwd_f32", _ptr(inp), inp.stride(0), _ptr(up), up.stride(0), B, inp.shape[1],
+                           res[i][0], res[i][1], _stream())
+                inp = up
+            ups[i] = inp
+            lyr = u.after_turn_layers[i]
+            if i > 0:
+                y = cat[i - 1][:, ch[i - 1]:]
+            else:
+                y = self._buf("h_last", (B, ch[0], n1, n2))
+            self._conv_f32(inp, lyr.weight, lyr.bias, y, 5, 1, True)
+            h = y
+        A["ups"], A["h_last"] = ups, h
+        z = self._buf("z", (B, cfg.unet_out_channels, n1, n2))
+        self._conv_f32(h, u.final_linear.weight, u.final_linear.bias, z, 1, 1, False)
+        return z, A
+
+    def _unet_bwd_f32(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads: Dict[str, torch.Tensor], B, n1, n2):
+        cfg, u = self.cfg, self.module.decoder.unet
+        ch, st = cfg.unet_channels, cfg.unet_strides
+        L = len(ch)
+        res = self._levels(n1, n2)
+        cat, ups = A["cat"], A["ups"]
+        S = _stream()
+
+        def wgrad(x, dy, name, k, stride):
+            Bn, Cin, H, W = x.shape
+            self._call("cnp_conv2d_wgrad_f32", _ptr(x), x.stride(0), _ptr(dy), dy.stride(0),
+                       _ptr(grads[name + ".weight"]), _ptr(grads[name + ".bias"]), Bn, Cin, H, W, dy.shape[1], k,
+                       stride, S)
+
+        def dgrad(dy, w, dx, k, stride, accumulate):
+            Bn, Cin, H, W = dx.shape
+            self._call("cnp_conv2d_dgrad_f32", _ptr(dy), dy.stride(0), _ptr(w), _ptr(dx), dx.stride(0), Bn, Cin, H, W,
+                       dy.shape[1], k, stride, int(accumulate), S)
+
+        def relu_bwd(d, y):
+            self._call("cnp_relu_bwd_f32", _ptr(d), d.stride(0), _ptr(y), y.stride(0), B,
+                       d.shape[1] * d.shape[2] * d.shape[3], S)
+
+        P = "decoder.unet."
+        h_last = A["h_last"]
+        wgrad(h_last, dz, P + "final_linear", 1, 1)
+        d_h = self._buf("d_h_last", h_last.shape)
+        dgrad(dz, u.final_linear.weight, d_h, 1, 1, False)
+        relu_bwd(d_h, h_last)
+        d_cat = [self._buf(f"d_cat{i}", cat[i].shape) for i in range(L)]
+        dy = d_h
+        for i in range(0, L):
+            name = P + f"after_turn_layers.{i}"
+            lyr = u.after_turn_layers[i]
+            x_in = ups[i]
+            wgrad(x_in, dy, name, 5, 1)
+            if st[i] == 2:
+                d_up = self._buf(f"d_up{i}", x_in.shape)
+                dgrad(dy, lyr.weight, d_up, 5, 1, False)
+                self._call("cnp_upsample2x_bwd_f32", _ptr(d_up), d_up.stride(0), _ptr(d_cat[i]), d_cat[i].stride(0), B,
+                           d_cat[i].shape[1], res[i][0], res[i][1], 0, S)
+            else:
+                dgrad(dy, lyr.weight, d_cat[i], 5, 1, False)
+            relu_bwd(d_cat[i], cat[i])
+            if i < L - 1:
+                dy = d_cat[i][:, ch[i]:]
+        # down path, deepest first; gradients accumulate into the skip halves
+        for i in range(L - 1, -1, -1):
+            name = P + f"before_turn_layers.{i}"
+            lyr = u.before_turn_layers[i]
+            dy = d_cat[i][:, :ch[i]]
+            x_in = cat[i - 1][:, :ch[i - 1]] if i > 0 else A["h_init"]
+            wgrad(x_in, dy, name, 5, st[i])
+            if i > 0:
+                dx = d_cat[i - 1][:, :ch[i - 1]]
+                tmp = self._buf(f"d_tmp{i}", dx.shape)
+                dgrad(dy, lyr.weight, tmp, 5, st[i], False)
+                relu_bwd(tmp, x_in)
+                dx.add_(tmp)
+            else:
+                d_init = self._buf("d_h_init", x_in.shape)
+                dgrad(dy, lyr.weight, d_init, 5, st[i], False)
+                wgrad(enc, d_init, P + "initial_linear", 1, 1)
+
+    # ------------------------------------------------------------------------------------------
+    # (2) UNet, bf16 tensor-core path
+    # ------------------------------------------------------------------------------------------
+    def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0) -> torch.Tensor:
+        ent = self._packed.get(key)
+        ver = w._version
+        if ent is not None and ent[0] == ver and ent[1].device == w.device:
+            return ent[1]
+        nbytes = _cabi.lib().cnp_conv_tc_packed_bytes(kind, n_chunks)
+        buf = ent[1] if ent is not None else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+        Cout, Cin, k, _ = w.shape
+        self._call("cnp_conv_tc_pack", _ptr(w), Cout, Cin, k, kind, n_chunks, py, px, co_off, _ptr(buf), _stream())
+        self._packed[key] = (ver, buf)
+        return buf
+
+    def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0):
+        self._call("cnp_conv_tc", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, C.byref(out), B, _stream())
+
+    @staticmethod
+    def _out_blk(blk: CnpBlk, bias=None, relu=False, mask: Optional[CnpBlk] = None, accumulate=False,
+                 scatter=(1, 0, 1, 0)) -> CnpConvOut:
+        o = CnpConvOut()
+        o.mode = 0
+        o.blk = blk
+        o.sy, o.ay, o.sx, o.ax = scatter
+        o.bias = _ptr(bias)
+        o.relu = int(relu)
+        o.mask = C.pointer(mask) if mask is not None else None
+        o.accumulate = int(accumulate)
+        o._keep = (bias, mask)
+        return o
+
+    def _unet_fwd_bf16(self, enc: torch.Tensor, B: int, n1: int, n2: int) -> Tuple[torch.Tensor, dict]:
+        K = _cabi
+        cfg, u = self.cfg, self.module.decoder.unet
+        st = cfg.unet_strides
+        L = len(st)
+        res = self._levels(n1, n2)
+        S = _stream()
+        A = {}
+        h_init = self._blk("h_init", B, 8, n1, n2)
+        self._call("cnp_conv1x1_in_bf16", _ptr(enc), enc.stride(0), _ptr(u.initial_linear.weight),
+                   _ptr(u.initial_linear.bias), B, cfg.in_channels, 64, C.byref(h_init.view()), S)
+        cat = [self._blk(f"cat{i}", B, 8 if i == L - 1 else 16, res[i][0], res[i][1]) for i in range(L)]
+        A["h_init"], A["cat"] = h_init, cat
+        phases = [None] * L
+        x = h_init
+        for i in range(L):
+            lyr = u.before_turn_layers[i]
+            out = self._out_blk(cat[i].view(0), bias=lyr.bias, relu=True)
+            if st[i] == 1:
+                wpk = self._packed_weights(f"before{i}", lyr.weight, K.KIND_K5S1, 8)
+                self._conv_tc(x.view(0), 8, wpk, K.KIND_K5S1, out, B)
+            else:
+                ph = self._blk(f"phase{i}", B, 32, res[i][0], res[i][1])
+                self._call("cnp_blk_space_to_depth", C.byref(x.view(0)), 8, C.byref(ph.view()), B, S)
+                phases[i] = ph
+                wpk = self._packed_weights(f"before{i}", lyr.weight, K.KIND_K5S2, 32)
+                self._conv_tc(ph.view(0), 32, wpk, K.KIND_K5S2, out, B)
+            x = cat[i]
+        A["phases"] = phases
+        ups = [None] * L
+        h_last = self._blk("h_last", B, 8, n1, n2)
+        for i in range(L - 1, -1, -1):
+            inp, ncb = cat[i], cat[i].CB
+            if st[i] == 2:
+                up = self._blk(f"up{i}", B, ncb, 2 * res[i][0], 2 * res[i][1])
+                self._call("cnp_blk_upsample2x_fwd", C.byref(inp.view()), ncb, C.byref(up.view()), B, S)
+                inp = up
+            ups[i] = inp
+            lyr = u.after_turn_layers[i]
+            dst = cat[i - 1].view(8) if i > 0 else h_last.view(0)
+            wpk = self._packed_weights(f"after{i}", lyr.weight, K.KIND_K5S1, ncb)
+            self._conv_tc(inp.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(dst, bias=lyr.bias, relu=True), B)
+        A["ups"], A["h_last"] = ups, h_last
+        z = self._buf("z", (B, 64, n1, n2))
+        o = CnpConvOut()
+        o.mode = 1
+        o.f32, o.f32_bstride, o.f32_ch_off = _ptr(z), z.stride(0), 0
+        o.sy, o.ay, o.sx, o.ax = 1, 0, 1, 0
+        o.bias = _ptr(u.final_linear.bias)
+        wpk = self._packed_weights("final", u.final_linear.weight, K.KIND_K1, 8)
+        self._conv_tc(h_last.view(0), 8, wpk, K.KIND_K1, o, B)
+        return z, A
+
+    def _unet_bwd_bf16(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads, B, n1, n2):
+        """Backward of the bf16 UNet: tcgen05 dgrad; wgrad currently runs on fp32 copies (interim)."""
+        K = _cabi
+        cfg, u = self.cfg, self.module.decoder.unet
+        st = cfg.unet_strides
+        L = len(st)
+        res = self._levels(n1, n2)
+        cat, ups, h_last, h_init = A["cat"], A["ups"], A["h_last"], A["h_init"]
+        S = _stream()
+        P = "decoder.unet."
+
+        def to_f32(blk: _Blk, cb_off, nch, key):
+            t = self._buf(key, (B, nch, blk.H, blk.W))
+            self._call("cnp_blk_to_nchw_f32", C.byref(blk.view(cb_off)), B, nch, _ptr(t), t.stride(0), S)
+            return t
+
+        def wgrad_f32(x, dy, name, k, stride):
+            Bn, Cin, H, W = x.shape
+            self._call("cnp_conv2d_wgrad_f32", _ptr(x), x.stride(0), _ptr(dy), dy.stride(0),
+                       _ptr(grads[name + ".weight"]), _ptr(grads[name + ".bias"]), Bn, Cin, H, W, dy.shape[1], k,
+                       stride, S)
+
+        def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
+                     accumulate=False, phase=None):
+            for g in range(n_out_ch // 64):
+                py, px = phase if phase is not None else (0, 0)
+                wpk = self._packed_weights(f"{key}.dg{g}.{py}{px}", w, kind, 8, py, px, 64 * g)
+                mk = mask.view(mask_cb + 8 * g) if mask is not None else None
+                sc = (2, py, 2, px) if phase is not None else (1, 0, 1, 0)
+                o = self._out_blk(dst.view(dst_cb + 8 * g), mask=mk, accumulate=accumulate, scatter=sc)
+                self._conv_tc(dy, 8, wpk, kind, o, B, py, px)
+
+        # final 1x1
+        dz_blk = self._blk("dz_blk", B, 8, n1, n2)
+        self._call("cnp_blk_from_nchw_f32", _ptr(dz), dz.stride(0), B, 64, n1, n2, C.byref(dz_blk.view()), S)
+        wgrad_f32(to_f32(h_last, 0, 64, "w_x"), dz, P + "final_linear", 1, 1)
+        d_hl = self._blk("d_h_last", B, 8, n1, n2)
+        dgrad_tc(dz_blk.view(0), u.final_linear.weight, "final", K.KIND_K1_DGRAD, 64, d_hl, 0, h_last, 0)
+        d_cat = [self._blk(f"d_cat{i}", B, cat[i].CB, res[i][0], res[i][1]) for i in range(L)]
+        dy_blk, dy_cb = d_hl, 0
+        for i in range(0, L):
+            name = P + f"after_turn_layers.{i}"
+            lyr = u.after_turn_layers[i]
+            x_in = ups[i]
+            nch = x_in.CB * 8
+            wgrad_f32(to_f32(x_in, 0, nch, f"w_x{nch}_{x_in.H}"), to_f32(dy_blk, dy_cb, 64, f"w_dy_{dy_blk.H}"), name, 5, 1)
+            if st[i] == 2:
+                d_up = self._blk(f"d_up{i}", B, x_in.CB, x_in.H, x_in.W)
+                dgrad_tc(dy_blk.view(dy_cb), lyr.weight, f"after{i}", K.KIND_K5S1_DGRAD, nch, d_up, 0, None, 0)
+                self._call("cnp_blk_upsample2x_bwd", C.byref(d_up.view()), x_in.CB, C.byref(d_cat[i].view()),
+                           C.byref(cat[i].view()), 0, B, S)
+            else:
+                dgrad_tc(dy_blk.view(dy_cb), lyr.weight, f"after{i}", K.KIND_K5S1_DGRAD, nch, d_cat[i], 0, cat[i], 0)
+            if i < L - 1:
+                dy_blk, dy_cb = d_cat[i], 8
+        for i in range(L - 1, -1, -1):
+            name = P + f"before_turn_layers.{i}"
+            lyr = u.before_turn_layers[i]
+            x_src = cat[i - 1] if i > 0 else h_init
+            wgrad_f32(to_f32(x_src, 0, 64, f"w_x64_{x_src.H}"), to_f32(d_cat[i], 0, 64, f"w_dy_{d_cat[i].H}"), name, 5, st[i])
+            if i > 0:
+                if st[i] == 2:
+                    for py in (0, 1):
+                        for px in (0, 1):
+                            dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S2_DGRAD, 64, d_cat[i - 1], 0,
+                                     cat[i - 1], 0, accumulate=True, phase=(py, px))
+                else:
+                    dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S1_DGRAD, 64, d_cat[i - 1], 0,
+                             cat[i - 1], 0, accumulate=True)
+            else:
+                d_init = self._blk("d_h_init", B, 8, n1, n2)
+                if st[i] == 2:
+                    raise NotImplementedError("first UNet level with stride 2")
+                dgrad_tc(d_cat[0].view(0), lyr.weight, "before0", K.KIND_K5S1_DGRAD, 64, d_init, 0, None, 0)
+                wgrad_f32(enc, to_f32(d_init, 0, 64, "w_dy_init"), P + "initial_linear", 1, 1)
+
+    # ------------------------------------------------------------------------------------------
+    # (3)+(4) decoder, head
+    # ------------------------------------------------------------------------------------------
+    def _mlp_params(self, grads: Optional[Dict[str, torch.Tensor]] = None) -> CnpMlpParams:
+        p = CnpMlpParams()
+        layers = self.module.decoder.mlp.layers
+        p.n_layers = len(layers)
+        dims = self.module.mlp_dims()
+        for i, d in enumerate(dims):
+            p.dims[i] = d
+        for i, l in enumerate(layers):
+            p.W[i], p.b[i] = l.weight.data_ptr(), l.bias.data_ptr()
+            if grads is not None:
+                p.dW[i] = grads[f"decoder.mlp.layers.{i}.weight"].data_ptr()
+                p.db[i] = grads[f"decoder.mlp.layers.{i}.bias"].data_ptr()
+        return p
+
+    def forward(self, batch: DeviceBatch, with_loss: bool = True):
+        """Returns dict(mean [B,Nt], var [B,Nt], logp [B] f64, count [B] i32, ctx)."""
+        self._require_cuda()
+        cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
+        enc = self.encode(batch)
+        if self.precision == "fp32":
+            z, A = self._unet_fwd_f32(enc, B, g.n1, g.n2)
+        else:
+            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2)
+        Cz = z.shape[1]
+        f = self._buf("f", (B, Cz, Nt))
+        s2 = self._scale2(self.module.decoder.set_conv.log_scale)
+        self._call("cnp_setconv_dec_offgrid_fwd", _ptr(z), z.stride(0), _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1,
+                   g.start2, g.n2, g.res, s2, _ptr(f), Cz, _stream())
+        mean = torch.empty((B, Nt), dtype=torch.float32, device=self.device)
+        var = torch.empty((B, Nt), dtype=torch.float32, device=self.device)
+        logp = count = None
+        if with_loss:
+            logp = torch.zeros(B, dtype=torch.float64, device=self.device)
+            count = torch.zeros(B, dtype=torch.int32, device=self.device)
+        p = self._mlp_params()
+        Ca = cfg.dim_aux_t
+        if batch.aux_t is None or batch.aux_t.shape[1] != Ca:
+            raise ValueError(f"task needs Y_t_aux with {Ca} channels")
+        self._call("cnp_mlp_head_fwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(batch.aux_t), Ca,
+                   _ptr(batch.yt) if with_loss else None, B, Nt, _ptr(mean), _ptr(var), _ptr(logp), _ptr(count),
+                   _stream())
+        return dict(mean=mean, var=var, logp=logp, count=count, ctx=dict(enc=enc, z=z, A=A, f=f))
+
+    def backward(self, batch: DeviceBatch, ctx: dict, dlogp: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """dlogp [B] fp32 = d loss / d logp_b.  Returns {param name: grad} (views of one flat buffer)."""
+        cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
+        named = [(n, p) for n, p in self.module.named_parameters() if n.startswith("decoder.") and p.dim() > 0]
+        total = sum(p.numel() for _, p in named)
+        flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        grads, off = {}, 0
+        for n, p in named:
+            grads[n] = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        f, z = ctx["f"], ctx["z"]
+        Cz = z.shape[1]
+        df = self._buf("df", (B, Cz, Nt))
+        p = self._mlp_params(grads)
+        self._call("cnp_mlp_head_bwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(batch.aux_t), cfg.dim_aux_t, _ptr(batch.yt), B,
+                   Nt, _ptr(dlogp), _ptr(df), _stream())
+        dz = self._buf("dz", z.shape)
+        s2 = self._scale2(self.module.decoder.set_conv.log_scale)
+        self._call("cnp_setconv_dec_offgrid_bwd", _ptr(df), Cz, _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1, g.start2,
+                   g.n2, g.res, s2, _ptr(dz), dz.stride(0), _stream())
+        if self.precision == "fp32":
+            self._unet_bwd_f32(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2)
+        else:
+            self._unet_bwd_bf16(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2)
+        if self.allreduce_group is not None and self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat, group=self.allreduce_group)
+            flat.mul_(1.0 / self.world_size)
+        self._flat_grad = flat
+        return grads

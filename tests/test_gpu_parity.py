@@ -1,0 +1,224 @@
+"""-m gpu: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances are the ones BASELINE.json's north_star states: fp32 path 1e-5 relative on mean/std/NLL,
+bf16 UNet 2e-2 relative.  Per-kernel checks use the same fp32 bound against torch fp32 ops.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from deepsensornz_b200 import _cabi, concat_tasks
+from deepsensornz_b200.engine import _Blk
+from deepsensornz_b200.synthetic import make_static, make_task
+from oracle import convnp_oracle as O
+from tests.util import cpu_params, oracle_inputs, rel_err, small_model
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def static():
+    return make_static(seed=7, n_hi=200)
+
+
+def _S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def test_library_loads_on_device():
+    _cabi.check_device()
+    assert _cabi.lib().cnp_version() >= 100
+
+
+# ---------------------------------------------------------------------------------------------
+# per-kernel parity (fp32)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,stride,cin,cout,h,w", [(5, 1, 64, 64, 40, 48), (5, 2, 64, 64, 40, 48), (1, 1, 15, 64, 33, 20),
+                                                   (5, 1, 128, 64, 24, 24), (1, 1, 64, 64, 16, 72)])
+def test_conv_f32_fwd_bwd(k, stride, cin, cout, h, w):
+    torch.manual_seed(1)
+    B = 2
+    x = torch.randn(B, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, k, k, device="cuda") * 0.05
+    b = torch.randn(cout, device="cuda")
+    ref = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=k // 2)
+    y = torch.empty(ref.shape, device="cuda")
+    _cabi.call("cnp_conv2d_fwd_f32", x.data_ptr(), x.stride(0), wt.data_ptr(), b.data_ptr(), y.data_ptr(), y.stride(0),
+               B, cin, h, w, cout, k, stride, 0, _S())
+    assert rel_err(y, ref) < FP32_TOL
+    dy = torch.randn_like(y)
+    xd = x.double().requires_grad_(True)
+    wd = wt.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    F.conv2d(xd, wd, bd, stride=stride, padding=k // 2).backward(dy.double())
+    dx = torch.empty_like(x)
+    _cabi.call("cnp_conv2d_dgrad_f32", dy.data_ptr(), dy.stride(0), wt.data_ptr(), dx.data_ptr(), dx.stride(0), B, cin,
+               h, w, cout, k, stride, 0, _S())
+    assert rel_err(dx, xd.grad) < FP32_TOL
+    dw = torch.zeros_like(wt)
+    db = torch.zeros_like(b)
+    _cabi.call("cnp_conv2d_wgrad_f32", x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), dw.data_ptr(),
+               db.data_ptr(), B, cin, h, w, cout, k, stride, _S())
+    assert rel_err(dw, wd.grad) < 2e-5
+    assert rel_err(db, bd.grad) < 2e-5
+
+
+def test_upsample_f32():
+    torch.manual_seed(2)
+    x = torch.randn(2, 5, 7, 9, device="cuda")
+    xd = x.double().requires_grad_(True)
+    ref = F.interpolate(xd, scale_factor=2, mode="bilinear", align_corners=False)
+    y = torch.empty(2, 5, 14, 18, device="cuda")
+    _cabi.call("cnp_upsample2x_fwd_f32", x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), 2, 5, 7, 9, _S())
+    assert rel_err(y, ref) < FP32_TOL
+    dy = torch.randn_like(y)
+    ref.backward(dy.double())
+    dx = torch.empty_like(x)
+    _cabi.call("cnp_upsample2x_bwd_f32", dy.data_ptr(), dy.stride(0), dx.data_ptr(), dx.stride(0), 2, 5, 7, 9, 0, _S())
+    assert rel_err(dx, xd.grad) < FP32_TOL
+
+
+def test_encoder_matches_oracle(static):
+    m = small_model("fp32")
+    tasks = [make_task(static, 100 + i) for i in range(2)]
+    task = concat_tasks(tasks)
+    batch = m._to_device(task)
+    enc = m.engine.encode(batch)
+    contexts, xt, yt, aux = oracle_inputs(task)
+    P = cpu_params(m)
+    (s1, n1), (s2, n2), res = O.discretise([c[0] for c in contexts] + [xt], m.config.points_per_unit, 0.1, 8)
+    assert (n1, n2) == (batch.grid.n1, batch.grid.n2)
+    ref = O.encoder(P, contexts, O.grid_points(s1, n1, res), O.grid_points(s2, n2, res))
+    assert enc.shape == ref.shape
+    assert rel_err(enc, ref) < FP32_TOL
+    # per-channel check so that small channels are held to the same bound
+    for c in range(ref.shape[1]):
+        assert rel_err(enc[:, c], ref[:, c]) < 5e-5, c
+
+
+def test_raw_task_equals_masked_task(static):
+    """Device-side NaN->mask (raw upload) == host-side Masked path, bit for bit."""
+    m = small_model("fp32")
+    t = make_task(static, 5)
+    e1 = m.engine.encode(m._to_device(t)).clone()
+    e2 = m.engine.encode(m._to_device(m.modify_task(t))).clone()
+    assert torch.equal(e1, e2)
+
+
+def test_decoder_fwd_bwd():
+    torch.manual_seed(3)
+    B, Cz, n1, n2, Nt = 2, 64, 56, 64, 37
+    res, s1, s2 = 0.02, -0.1, -0.14
+    z = torch.randn(B, Cz, n1, n2, device="cuda")
+    xt = torch.rand(B, 2, Nt, device="cuda") * torch.tensor([n1 * res, n2 * res], device="cuda").view(1, 2, 1) + \
+        torch.tensor([s1, s2], device="cuda").view(1, 2, 1)
+    ls = torch.tensor(math.log(res))
+    g1, g2 = O.grid_points(s1, n1, res), O.grid_points(s2, n2, res)
+    zd = z.cpu().double().requires_grad_(True)
+    ref = O.decode({"decoder.set_conv.log_scale": ls.double()}, zd, g1.double(), g2.double(), xt.cpu().double())
+    f = torch.empty(B, Cz, Nt, device="cuda")
+    sc2 = float(np.float32(math.exp(2 * float(ls))))
+    _cabi.call("cnp_setconv_dec_offgrid_fwd", z.data_ptr(), z.stride(0), xt.data_ptr(), B, Cz, Nt, s1, n1, s2, n2, res,
+               sc2, f.data_ptr(), Cz, _S())
+    assert rel_err(f, ref) < FP32_TOL
+    df = torch.randn_like(f)
+    ref.backward(df.cpu().double())
+    dz = torch.empty_like(z)
+    _cabi.call("cnp_setconv_dec_offgrid_bwd", df.data_ptr(), Cz, xt.data_ptr(), B, Cz, Nt, s1, n1, s2, n2, res, sc2,
+               dz.data_ptr(), dz.stride(0), _S())
+    assert rel_err(dz, zd.grad) < FP32_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# full model, fp32 mode: mean / std / NLL and gradients vs oracle autograd
+# ---------------------------------------------------------------------------------------------
+def _oracle_loss_and_grads(m, task):
+    contexts, xt, yt, aux = oracle_inputs(task)
+    P = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in cpu_params(m).items()}
+    mean, var = O.forward(P, contexts, xt, aux, m.config.points_per_unit)
+    loss = -O.loglik(mean, var, yt, True).mean()
+    loss.backward()
+    return mean.detach(), var.detach(), loss.detach(), {k: v.grad for k, v in P.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("nb", [1, 3])
+def test_model_fp32_matches_oracle(static, nb):
+    m = small_model("fp32")
+    tasks = [make_task(static, 200 + i) for i in range(nb)]
+    task = concat_tasks(tasks) if nb > 1 else tasks[0]
+    mean_o, var_o, loss_o, grads_o = _oracle_loss_and_grads(m, task)
+    pred = m(task)
+    assert rel_err(pred["mean"], mean_o) < FP32_TOL
+    assert rel_err(pred["std"], var_o.sqrt()) < FP32_TOL
+    loss = m.loss_fn(task, normalise=True)
+    assert abs(float(loss) - float(loss_o)) / abs(float(loss_o)) < FP32_TOL
+    loss.backward()
+    for n, p in m.model.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None, n
+            assert rel_err(p.grad, grads_o[n]) < 1e-4, n
+
+
+def test_model_bf16_matches_oracle(static):
+    m = small_model("bf16")
+    tasks = [make_task(static, 300 + i) for i in range(2)]
+    task = concat_tasks(tasks)
+    mean_o, var_o, loss_o, grads_o = _oracle_loss_and_grads(m, task)
+    pred = m(task)
+    assert rel_err(pred["mean"], mean_o) < BF16_TOL
+    assert rel_err(pred["std"], var_o.sqrt()) < BF16_TOL
+    loss = m.loss_fn(task, normalise=True)
+    assert abs(float(loss) - float(loss_o)) / abs(float(loss_o)) < BF16_TOL
+    loss.backward()
+    for n, p in m.model.named_parameters():
+        if p.requires_grad:
+            assert rel_err(p.grad, grads_o[n]) < 6e-2, n
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 conv against torch on bf16-rounded operands (isolates the kernel from model effects)
+# ---------------------------------------------------------------------------------------------
+def _to_blk(x, cb_total=None):
+    B, Cc, H, W = x.shape
+    blk = _Blk(B, cb_total or Cc // 8, H, W, x.device)
+    _cabi.call("cnp_blk_from_nchw_f32", x.data_ptr(), x.stride(0), B, Cc, H, W, C.byref(blk.view()), _S())
+    return blk
+
+
+def _from_blk(blk, Cc, cb_off=0):
+    out = torch.empty(blk.B, Cc, blk.H, blk.W, device="cuda")
+    _cabi.call("cnp_blk_to_nchw_f32", C.byref(blk.view(cb_off)), blk.B, Cc, out.data_ptr(), out.stride(0), _S())
+    return out
+
+
+@pytest.mark.parametrize("cin,h,w", [(64, 38, 38), (128, 76, 76), (64, 152, 160), (128, 61, 45)])
+def test_conv_tc_k5s1(cin, h, w):
+    torch.manual_seed(4)
+    B = 2
+    x = torch.randn(B, cin, h, w, device="cuda").bfloat16().float()
+    wt = (torch.randn(64, cin, 5, 5, device="cuda") * 0.05).bfloat16().float()
+    b = torch.randn(64, device="cuda")
+    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), padding=2))
+    xb = _to_blk(x)
+    yb = _Blk(B, 8, h, w, x.device)
+    nbytes = _cabi.lib().cnp_conv_tc_packed_bytes(_cabi.KIND_K5S1, cin // 8)
+    wpk = torch.empty(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+    _cabi.call("cnp_conv_tc_pack", wt.data_ptr(), 64, cin, 5, _cabi.KIND_K5S1, cin // 8, 0, 0, 0, wpk.data_ptr(), _S())
+    o = _cabi.CnpConvOut()
+    o.mode, o.blk = 0, yb.view()
+    o.sy, o.ay, o.sx, o.ax = 1, 0, 1, 0
+    o.bias, o.relu = b.data_ptr(), 1
+    _cabi.call("cnp_conv_tc", C.byref(xb.view()), cin // 8, wpk.data_ptr(), _cabi.KIND_K5S1, 0, 0, C.byref(o), B, _S())
+    y = _from_blk(yb, 64)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) < 1e-2   # bf16 output rounding only (operands are exact in bf16)
+    # the zero pad of the output buffer must be untouched
+    full = yb.t[:B * yb.bstride].view(B, 8, h + 4, w + 4, 8).float()
+    assert float(full[:, :, :2].abs().max()) == 0 and float(full[:, :, :, :2].abs().max()) == 0
+    assert float(full[:, :, -2:].abs().max()) == 0 and float(full[:, :, :, -2:].abs().max()) == 0
