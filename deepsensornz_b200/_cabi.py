@@ -57,6 +57,8 @@ class CnpConvOut(C.Structure):
 
 # conv_tc kinds (must match conv_bf16.cu)
 KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD = range(6)
+# conv_tc_wgrad kinds (must match wgrad_bf16.cu)
+WG_K5S1, WG_K1, WG_K5S2 = range(3)
 
 _i, _d, _f, _ll = C.c_int, C.c_double, C.c_float, C.c_longlong
 _GRID = [_d, _i, _d, _i, _d]  # start1, n1, start2, n2, res
@@ -94,6 +96,8 @@ _SIGS = {
     "cnp_blk_upsample2x_fwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
     "cnp_blk_upsample2x_bwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, _i, c_stream]),
     "cnp_blk_space_to_depth": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
+    "cnp_conv_tc_wgrad": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_fp, _i, _i, c_stream]),
+    "cnp_blk_channel_sum": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, c_stream]),
 }
 
 _lib: Optional[C.CDLL] = None

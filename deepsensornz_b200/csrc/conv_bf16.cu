@@ -577,12 +577,6 @@ int num_sms() {
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-struct cnp_blk {          // view of a blocked bf16 activation tensor
-  void* base;             // first element of batch 0, chunk 0
-  long long bstride;      // elements between batches
-  int cb_off;             // first chunk of the view
-  int H, W;               // interior size (planes are (H+4) x (W+4))
-};
 
 struct cnp_conv_out {
   int mode;               // 0: blocked bf16 (blk), 1: NCHW fp32 (f32 / f32_bstride / f32_ch_off / H x W)

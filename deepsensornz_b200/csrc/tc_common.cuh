@@ -5,6 +5,13 @@
 #pragma once
 #include "common.cuh"
 
+struct cnp_blk {          // view of a blocked bf16 activation tensor [B][C/8][H+4][W+4][8]
+  void* base;             // first element of batch 0, chunk 0
+  long long bstride;      // elements between batches
+  int cb_off;             // first chunk of the view
+  int H, W;               // interior size (planes are (H+4) x (W+4))
+};
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -24,9 +24,6 @@
 #define CNP_WG_MAX_PASS 5
 #define CNP_WG_MAX_ACC 5
 
-struct cnp_blk {
-  void* base; long long bstride; int cb_off; int H, W;
-};
 
 struct cnp_wg_pass {
   int chunk0;        // first source chunk of the M operand
@@ -210,7 +207,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   a.dy = reinterpret_cast<const __nv_bfloat16*>(dy->base) + (long long)dy->cb_off * a.dy_plane; a.dy_bs = dy->bstride;
   a.dw = dw; a.Cin = Cin; a.B = B;
   // reduction tile: the zero pad after the last interior pixel (2*Wp+2 pixels) must cover the overshoot
-  a.P = (2 * Wp + 2 >= 128) ? 128 : (2 * Wp + 2 >= 64 ? 64 : 32);
+  a.P = (2 * Wp + 2 >= 128) ? 128 : (2 * Wp + 2 >= 64 ? 64 : (2 * Wp + 2 >= 32 ? 32 : 16));
   CNP_REQUIRE(2 * Wp + 2 >= a.P, "conv_tc_wgrad: image too narrow");
   a.p_start = 2 * Wp + 2;
   const int p_end = (H + 1) * Wp + W + 2;

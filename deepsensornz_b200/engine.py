@@ -432,7 +432,7 @@ class Engine:
         return z, A
 
     def _unet_bwd_bf16(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads, B, n1, n2):
-        """Backward of the bf16 UNet: tcgen05 dgrad; wgrad currently runs on fp32 copies (interim)."""
+        """Backward of the bf16 UNet: tcgen05 dgrad and wgrad on the blocked bf16 activations."""
         K = _cabi
         cfg, u = self.cfg, self.module.decoder.unet
         st = cfg.unet_strides
@@ -453,6 +453,11 @@ class Engine:
                        _ptr(grads[name + ".weight"]), _ptr(grads[name + ".bias"]), Bn, Cin, H, W, dy.shape[1], k,
                        stride, S)
 
+        def wgrad_tc(x: CnpBlk, n_chunks, dy: CnpBlk, kind, name, Cin):
+            self._call("cnp_conv_tc_wgrad", C.byref(x), n_chunks, C.byref(dy), kind, _ptr(grads[name + ".weight"]),
+                       Cin, B, S)
+            self._call("cnp_blk_channel_sum", C.byref(dy), 8, B, _ptr(grads[name + ".bias"]), S)
+
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
                      accumulate=False, phase=None):
             for g in range(n_out_ch // 64):
@@ -466,7 +471,7 @@ class Engine:
         # final 1x1
         dz_blk = self._blk("dz_blk", B, 8, n1, n2)
         self._call("cnp_blk_from_nchw_f32", _ptr(dz), dz.stride(0), B, 64, n1, n2, C.byref(dz_blk.view()), S)
-        wgrad_f32(to_f32(h_last, 0, 64, "w_x"), dz, P + "final_linear", 1, 1)
+        wgrad_tc(h_last.view(0), 8, dz_blk.view(0), K.WG_K1, P + "final_linear", 64)
         d_hl = self._blk("d_h_last", B, 8, n1, n2)
         dgrad_tc(dz_blk.view(0), u.final_linear.weight, "final", K.KIND_K1_DGRAD, 64, d_hl, 0, h_last, 0)
         d_cat = [self._blk(f"d_cat{i}", B, cat[i].CB, res[i][0], res[i][1]) for i in range(L)]
@@ -476,7 +481,7 @@ class Engine:
             lyr = u.after_turn_layers[i]
             x_in = ups[i]
             nch = x_in.CB * 8
-            wgrad_f32(to_f32(x_in, 0, nch, f"w_x{nch}_{x_in.H}"), to_f32(dy_blk, dy_cb, 64, f"w_dy_{dy_blk.H}"), name, 5, 1)
+            wgrad_tc(x_in.view(0), x_in.CB, dy_blk.view(dy_cb), K.WG_K5S1, name, nch)
             if st[i] == 2:
                 d_up = self._blk(f"d_up{i}", B, x_in.CB, x_in.H, x_in.W)
                 dgrad_tc(dy_blk.view(dy_cb), lyr.weight, f"after{i}", K.KIND_K5S1_DGRAD, nch, d_up, 0, None, 0)
@@ -490,7 +495,10 @@ class Engine:
             name = P + f"before_turn_layers.{i}"
             lyr = u.before_turn_layers[i]
             x_src = cat[i - 1] if i > 0 else h_init
-            wgrad_f32(to_f32(x_src, 0, 64, f"w_x64_{x_src.H}"), to_f32(d_cat[i], 0, 64, f"w_dy_{d_cat[i].H}"), name, 5, st[i])
+            if st[i] == 2:
+                wgrad_tc(A["phases"][i].view(0), 32, d_cat[i].view(0), K.WG_K5S2, name, 64)
+            else:
+                wgrad_tc(x_src.view(0), 8, d_cat[i].view(0), K.WG_K5S1, name, 64)
             if i > 0:
                 if st[i] == 2:
                     for py in (0, 1):
