@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .engine import DeviceBatch, Engine
+from .engine import DeviceBatch, Engine, HostBatch
 from .model import ConvNPConfig, ConvNPModule
 from .task import Masked, Task, convert_task_to_nps_args
 
@@ -170,9 +170,18 @@ class ConvNP:
             task = task.mask_nans_nps()
         return task
 
-    def _to_device(self, task: Task, pinned: bool = False) -> DeviceBatch:
+    def stage_task(self, task: Task, pinned: bool = True) -> HostBatch:
+        """Stage a task once in page-locked host memory; ``loss_fn`` / ``__call__`` accept the result and
+        then only pay the asynchronous H2D copy per call."""
+        return self._to_device(task, pinned=pinned, upload=False)
+
+    def _to_device(self, task, pinned: bool = False, upload: bool = True):
         """Upload a task.  Raw tasks skip the host NaN scans: NaNs travel to the GPU and the encoder
         kernels derive the masks there (identical result to the Masked path, see tests)."""
+        if isinstance(task, DeviceBatch):
+            return task
+        if isinstance(task, HostBatch):
+            return self.engine.upload(task)
         if "nps_mask" in task["ops"] or "numpy_mask" in task["ops"]:
             task = self.modify_task(task)
         else:
@@ -191,14 +200,15 @@ class ConvNP:
                 contexts.append((x, y, None))
         if isinstance(yt, np.ma.MaskedArray):
             yt = yt.filled(np.nan)
-        return self.engine.prepare(contexts, xt, yt, kw.get("aux_t"), pinned=pinned)
+        hb = self.engine.stage_host(contexts, xt, yt, kw.get("aux_t"), pinned=pinned)
+        return self.engine.upload(hb) if upload else hb
 
     # ------------------------------------------------------------------------------------------
     # public API
     # ------------------------------------------------------------------------------------------
     def loss_fn(self, task: Union[Task, DeviceBatch], fix_noise=None, num_lv_samples: int = 8,
                 normalise: bool = False) -> torch.Tensor:
-        batch = task if isinstance(task, DeviceBatch) else self._to_device(task)
+        batch = self._to_device(task)
         if batch.yt is None:
             raise ValueError("loss_fn needs target observations (Y_t)")
         params = [p for _, p in self.model.named_parameters()]
@@ -209,7 +219,7 @@ class ConvNP:
         return -(out["logp"] / denom).mean()
 
     def __call__(self, task: Union[Task, DeviceBatch], n_samples: int = 10, requires_grad: bool = False):
-        batch = task if isinstance(task, DeviceBatch) else self._to_device(task)
+        batch = self._to_device(task)
         with torch.no_grad():
             out = self.engine.forward(batch, with_loss=False)
         mean, var = out["mean"].unsqueeze(1), out["var"].unsqueeze(1)

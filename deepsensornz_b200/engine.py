@@ -59,6 +59,17 @@ class DeviceBatch:
     h2d_bytes: int = 0
 
 
+@dataclass
+class HostBatch:
+    """A task staged on the host as float32 (optionally pinned) tensors, ready for ``Engine.upload``."""
+    contexts: List[DeviceContext]
+    xt: torch.Tensor
+    yt: Optional[torch.Tensor]
+    aux_t: Optional[torch.Tensor]
+    grid: GridSpec
+    B: int
+
+
 def _monotone(v: np.ndarray) -> int:
     d = np.diff(v.astype(np.float64))
     if d.size == 0 or np.all(d > 0):
@@ -107,6 +118,7 @@ class Engine:
         self.allreduce_group = None   # set by dist.enable_data_parallel
         self.world_size = 1
         self.launches = 0
+        self._prof = None
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -121,9 +133,34 @@ class Engine:
                                  "(call set_gpu_default_device() before building the model, or model.model.cuda())")
         _cabi.lib()
 
-    def _call(self, name, *args):
+    def _call(self, name, *args, work=None):
+        """Launch one C-ABI kernel.  ``work`` = (algorithmic flops, algorithmic bytes) for the roofline;
+        with profiling on, every launch is bracketed by CUDA events on the launching stream."""
         self.launches += 1
+        if self._prof is None:
+            _cabi.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         _cabi.call(name, *args)
+        e1.record()
+        self._prof.append((name, e0, e1, work or (0.0, 0.0)))
+
+    def profile_start(self):
+        self._prof = []
+
+    def profile_stop(self) -> Dict[str, dict]:
+        """Per-kernel totals: launches, ms, algorithmic flops / bytes."""
+        torch.cuda.synchronize()
+        out: Dict[str, dict] = {}
+        for name, e0, e1, (fl, by) in self._prof or []:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        self._prof = None
+        return out
 
     def _buf(self, key, shape, dtype=torch.float32, zero=False):
         k = (key, tuple(shape), dtype)
@@ -152,51 +189,69 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # host -> device
     # ------------------------------------------------------------------------------------------
-    def prepare(self, contexts, xt, yt, aux_t, pinned: bool = False) -> DeviceBatch:
+    def stage_host(self, contexts, xt, yt, aux_t, pinned: bool = False) -> "HostBatch":
         """contexts: list of (x, y, mask|None) numpy/torch CPU arrays with a leading batch axis.
-        NaNs may stay in ``y`` (the kernels derive validity on the fly)."""
-        self._require_cuda()
-        dev = self.device
-        nbytes = 0
-
-        def up(a, dtype=torch.float32):
-            nonlocal nbytes
-            if a is None:
-                return None
-            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-            if t.device.type != "cuda":
-                t = t.to(dtype).contiguous()
-                nbytes += t.numel() * t.element_size()
-                if pinned and not t.is_pinned():
-                    t = t.pin_memory()
-                return t.to(dev, non_blocking=True)
-            return t.to(dtype).contiguous()
+        NaNs may stay in ``y`` (the kernels derive validity on the fly).  Returns float32 contiguous
+        CPU tensors (page-locked when ``pinned``) plus the host-side discretisation."""
+        if isinstance(xt, tuple):
+            raise NotImplementedError("on-grid targets go through ConvNP.predict")
 
         def host(a):
             return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
 
-        if isinstance(xt, tuple):
-            raise NotImplementedError("on-grid targets go through Engine.predict_grid")
-        xs_for_grid = [c[0] for c in contexts] + [xt]
-        xs_for_grid = [tuple(host(v) for v in x) if isinstance(x, tuple) else host(x) for x in xs_for_grid]
-        grid = discretise(xs_for_grid, self.cfg.points_per_unit, self.cfg.margin, self.cfg.grid_multiple)
-        B = int(host(xt).shape[0])
-        dctx = []
-        for (x, y, m), xh in zip(contexts, xs_for_grid[:-1]):
+        def cpu(a):
+            if a is None:
+                return None
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            t = t.to(torch.float32).contiguous()
+            if pinned and t.device.type == "cpu" and not t.is_pinned():
+                t = t.pin_memory()
+            return t
+
+        xs = [c[0] for c in contexts] + [xt]
+        xs = [tuple(host(v) for v in x) if isinstance(x, tuple) else host(x) for x in xs]
+        grid = discretise(xs, self.cfg.points_per_unit, self.cfg.margin, self.cfg.grid_multiple)
+        B = int(xs[-1].shape[0])
+        hctx = []
+        for (x, y, m), xh in zip(contexts, xs[:-1]):
             if isinstance(x, tuple):
                 x1h, x2h = xh
                 x1h = x1h.reshape(x1h.shape[0], -1)
                 x2h = x2h.reshape(x2h.shape[0], -1)
                 shared = all(np.array_equal(x1h[0], x1h[i]) and np.array_equal(x2h[0], x2h[i])
                              for i in range(1, x1h.shape[0]))
-                mono1, mono2 = _mono_rows(x1h), _mono_rows(x2h)
+                mono = (_mono_rows(x1h), _mono_rows(x2h))
                 if shared:
                     x1h, x2h = x1h[:1], x2h[:1]
-                dctx.append(DeviceContext(True, (up(x1h), up(x2h)), up(y), up(m), (mono1, mono2), not shared))
+                hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared))
             else:
-                dctx.append(DeviceContext(False, up(x), up(y), up(m)))
-        xt_d, yt_d, aux_d = up(xt), up(yt), up(aux_t)
-        return DeviceBatch(dctx, xt_d, yt_d, aux_d, grid, B, int(xt_d.shape[-1]), nbytes)
+                hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))
+        return HostBatch(hctx, cpu(xt), cpu(yt), cpu(aux_t), grid, B)
+
+    def upload(self, hb: "HostBatch") -> DeviceBatch:
+        """Asynchronous H2D of a staged batch on the current stream."""
+        self._require_cuda()
+        dev = self.device
+        nbytes = 0
+
+        def up(t):
+            nonlocal nbytes
+            if t is None:
+                return None
+            if t.device.type == "cuda":
+                return t
+            nbytes += t.numel() * t.element_size()
+            return t.to(dev, non_blocking=True)
+
+        dctx = []
+        for c in hb.contexts:
+            x = tuple(up(v) for v in c.x) if c.gridded else up(c.x)
+            dctx.append(DeviceContext(c.gridded, x, up(c.y), up(c.mask), c.mono, c.x_batched))
+        xt = up(hb.xt)
+        return DeviceBatch(dctx, xt, up(hb.yt), up(hb.aux_t), hb.grid, hb.B, int(xt.shape[-1]), nbytes)
+
+    def prepare(self, contexts, xt, yt, aux_t, pinned: bool = False) -> DeviceBatch:
+        return self.upload(self.stage_host(contexts, xt, yt, aux_t, pinned=pinned))
 
     # ------------------------------------------------------------------------------------------
     # (1) encoder
@@ -212,14 +267,16 @@ class Engine:
                 raise ValueError(f"context set {k}: expected {Ck} channels, got {c.y.shape[1]}")
             if c.gridded:
                 x1, x2 = c.x
+                by = 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) + B * (Ck + 1) * g.n1 * g.n2)
                 self._call("cnp_setconv_enc_grid_fwd", _ptr(x1), _ptr(x2), int(c.x_batched), _ptr(c.y), _ptr(c.mask),
                            B, Ck, int(x1.shape[-1]), int(x2.shape[-1]), c.mono[0], c.mono[1],
                            g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
-                           _stream())
+                           _stream(), work=(0.0, by))
             else:
+                by = 4.0 * (c.x.numel() + c.y.numel() + B * (Ck + 1) * g.n1 * g.n2)
                 self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
                            int(c.x.shape[-1]), g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch,
-                           cfg.in_channels, _stream())
+                           cfg.in_channels, _stream(), work=(0.0, by))
             ch += Ck + 1
         return enc
 
@@ -362,7 +419,18 @@ class Engine:
         return buf
 
     def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0):
-        self._call("cnp_conv_tc", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, C.byref(out), B, _stream())
+        K = _cabi
+        if kind in (K.KIND_K5S1, K.KIND_K5S1_DGRAD):
+            kdim = n_chunks * 8 * 25
+        elif kind in (K.KIND_K1, K.KIND_K1_DGRAD):
+            kdim = n_chunks * 8
+        elif kind == K.KIND_K5S2:
+            kdim = 64 * 25
+        else:
+            kdim = 64 * (3 if py == 0 else 2) * (3 if px == 0 else 2)
+        fl = 2.0 * B * x.H * x.W * 64 * kdim
+        self._call("cnp_conv_tc", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, C.byref(out), B, _stream(),
+                   work=(fl, 0.0))
 
     @staticmethod
     def _out_blk(blk: CnpBlk, bias=None, relu=False, mask: Optional[CnpBlk] = None, accumulate=False,
@@ -454,8 +522,9 @@ class Engine:
                        stride, S)
 
         def wgrad_tc(x: CnpBlk, n_chunks, dy: CnpBlk, kind, name, Cin):
+            kk = 1 if kind == K.WG_K1 else 25
             self._call("cnp_conv_tc_wgrad", C.byref(x), n_chunks, C.byref(dy), kind, _ptr(grads[name + ".weight"]),
-                       Cin, B, S)
+                       Cin, B, S, work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
             self._call("cnp_blk_channel_sum", C.byref(dy), 8, B, _ptr(grads[name + ".bias"]), S)
 
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
@@ -580,7 +649,7 @@ class Engine:
         dz = self._buf("dz", z.shape)
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
         self._call("cnp_setconv_dec_offgrid_bwd", _ptr(df), Cz, _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1, g.start2,
-                   g.n2, g.res, s2, _ptr(dz), dz.stride(0), _stream())
+                   g.n2, g.res, s2, _ptr(dz), dz.stride(0), _stream(), work=(0.0, 4.0 * (dz.numel() + df.numel())))
         if self.precision == "fp32":
             self._unet_bwd_f32(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2)
         else:
