@@ -69,8 +69,9 @@ _SIGS = {
     "cnp_check_device": (C.c_int, []),
     # (1) SetConv encoder
     "cnp_setconv_enc_offgrid_fwd": (C.c_int, [c_fp, c_fp, c_fp, _i, _i, _i] + _GRID + [_f, _f, c_fp, _i, _i, c_stream]),
+    "cnp_setconv_enc_grid_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "cnp_setconv_enc_grid_fwd": (C.c_int, [c_fp, c_fp, _i, c_fp, c_fp, _i, _i, _i, _i, _i, _i] + _GRID +
-                                 [_f, _f, c_fp, _i, _i, c_stream]),
+                                 [_f, _f, c_fp, _i, _i, _i, c_fp, _ll, c_stream]),
     # (3) SetConv decoder
     "cnp_setconv_dec_offgrid_fwd": (C.c_int, [c_fp, _ll, c_fp, _i, _i, _i] + _GRID + [_f, c_fp, _i, c_stream]),
     "cnp_setconv_dec_offgrid_bwd": (C.c_int, [c_fp, _i, c_fp, _i, _i, _i] + _GRID + [_f, c_fp, _ll, c_stream]),
@@ -97,6 +98,7 @@ _SIGS = {
     "cnp_blk_upsample2x_bwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, _i, c_stream]),
     "cnp_blk_space_to_depth": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
     "cnp_conv_tc_wgrad": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_fp, _i, _i, c_stream]),
+    "cnp_conv1x1_in_wgrad": (C.c_int, [c_fp, _ll, _i, C.POINTER(CnpBlk), _i, c_fp, c_fp, c_stream]),
     "cnp_blk_channel_sum": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, c_stream]),
 }
 

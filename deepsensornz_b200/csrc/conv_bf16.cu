@@ -362,15 +362,6 @@ conv1x1_in_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, i
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// bilinear x2 (align_corners=False) on blocked tensors; backward optionally masks by (act > 0)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void up2_src(int Y, int H, int* y0, int* y1, float* lam) {
-  float src = ((float)Y + 0.5f) * 0.5f - 0.5f;
-  src = fmaxf(src, 0.f);
-  int i0 = (int)src;
-  *y0 = i0; *y1 = min(i0 + 1, H - 1); *lam = src - (float)i0;
-}
 __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* v) {
   const uint4 pk = __ldg(reinterpret_cast<const uint4*>(p));
   const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
@@ -385,6 +376,84 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = pk;
 }
 
+// ---------------------------------------------------------------------------------------------
+// weight/bias gradient of the initial 1x1 conv: dw[co][ci] += sum_px dy[co,px] * x[ci,px]
+//   x fp32 NCHW (encoder output, Cin <= 48), dy blocked bf16 (64 channels).  Memory-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int IW_PX = 128;
+constexpr int IW_MAXCI = 48;
+
+__global__ void __launch_bounds__(256)
+conv1x1_in_wgrad_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, int W,
+                        const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int B,
+                        float* __restrict__ dw, float* __restrict__ dbias) {
+  extern __shared__ __align__(16) float sm[];
+  float* dy_s = sm;                      // [IW_PX][68]
+  float* x_s = sm + IW_PX * 68;          // [Cin][IW_PX]
+  const int cg = threadIdx.x & 15, cis = threadIdx.x >> 4;  // 16 groups of 4 co; ci slots cis, cis+16, cis+32
+  const int HW = H * W, Hp = H + 4, Wp = W + 4;
+  const int tiles_per_img = (HW + IW_PX - 1) / IW_PX;
+  float acc[3][4], bsum[4];
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) bsum[c] = 0.f;
+  for (int t = blockIdx.x; t < B * tiles_per_img; t += gridDim.x) {
+    const int b = t / tiles_per_img, e0 = (t % tiles_per_img) * IW_PX;
+    __syncthreads();
+    for (int e = threadIdx.x; e < IW_PX * 8; e += 256) {
+      const int px = e >> 3, chunk = e & 7, pe = e0 + px;
+      float v[8];
+      if (pe < HW) {
+        const int yy = pe / W, xx = pe % W;
+        ld8(dy + (size_t)b * dy_bs + (((size_t)(dy_cb + chunk) * Hp + yy + 2) * Wp + xx + 2) * 8, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dy_s[px * 68 + chunk * 8 + i] = v[i];
+    }
+    for (int e = threadIdx.x; e < Cin * IW_PX; e += 256) {
+      const int ci = e / IW_PX, px = e % IW_PX, pe = e0 + px;
+      x_s[e] = pe < HW ? __ldg(x + (size_t)b * x_bs + (size_t)ci * HW + pe) : 0.f;
+    }
+    __syncthreads();
+    for (int px = 0; px < IW_PX; ++px) {
+      const float4 g = *reinterpret_cast<const float4*>(dy_s + px * 68 + cg * 4);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int ci = cis + 16 * m;
+        const float xv = ci < Cin ? x_s[ci * IW_PX + px] : 0.f;
+        acc[m][0] = fmaf(xv, g.x, acc[m][0]); acc[m][1] = fmaf(xv, g.y, acc[m][1]);
+        acc[m][2] = fmaf(xv, g.z, acc[m][2]); acc[m][3] = fmaf(xv, g.w, acc[m][3]);
+      }
+      if (cis == 0) { bsum[0] += g.x; bsum[1] += g.y; bsum[2] += g.z; bsum[3] += g.w; }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const int ci = cis + 16 * m;
+    if (ci < Cin)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(dw + (size_t)(cg * 4 + c) * Cin + ci, acc[m][c]);
+  }
+  if (cis == 0 && dbias)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) atomicAdd(dbias + cg * 4 + c, bsum[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear x2 (align_corners=False) on blocked tensors; backward optionally masks by (act > 0)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_src(int Y, int H, int* y0, int* y1, float* lam) {
+  float src = ((float)Y + 0.5f) * 0.5f - 0.5f;
+  src = fmaxf(src, 0.f);
+  int i0 = (int)src;
+  *y0 = i0; *y1 = min(i0 + 1, H - 1); *lam = src - (float)i0;
+}
 __global__ void __launch_bounds__(256)
 blk_upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, int x_cb, int H, int W,
                           __nv_bfloat16* __restrict__ y, long long y_bs, int y_cb) {
@@ -715,5 +784,23 @@ CNP_API int cnp_blk_space_to_depth(const cnp_blk* x, int n_chunks, const cnp_blk
                                                   n_chunks, x->H, x->W, reinterpret_cast<__nv_bfloat16*>(y->base),
                                                   y->bstride);
   CNP_LAUNCH_CHECK("blk_space_to_depth_kernel");
+  return 0;
+}
+
+CNP_API int cnp_conv1x1_in_wgrad(const float* x, long long x_bstride, int Cin, const cnp_blk* dy, int B, float* dw,
+                                 float* dbias, cudaStream_t st) {
+  CNP_REQUIRE(x && dy && dw && B > 0 && Cin >= 1 && Cin <= IW_MAXCI, "conv1x1_in_wgrad: need Cin <= %d", IW_MAXCI);
+  const size_t smem = (size_t)(IW_PX * 68 + Cin * IW_PX) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(conv1x1_in_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  const int tiles = B * cnp_cdiv(dy->H * dy->W, IW_PX);
+  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+  conv1x1_in_wgrad_kernel<<<grid, 256, smem, st>>>(x, x_bstride, Cin, dy->H, dy->W,
+                                                   reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride,
+                                                   dy->cb_off, B, dw, dbias);
+  CNP_LAUNCH_CHECK("conv1x1_in_wgrad_kernel");
   return 0;
 }

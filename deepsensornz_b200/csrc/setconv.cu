@@ -256,6 +256,111 @@ enc_grid_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int 
 }
 
 // =============================================================================================
+// (1c) gridded context set, fast path: precomputed band tables + two separable passes.
+//   band table (per output index j of one dimension): first contributing input index q0[j] and the
+//   weights w[k][j], k < KB, of inputs q0[j]+k (exact zeros beyond the band).
+//   pass 1: T[b,c,p,j] = sum_k y~[b,c,p,q0[j]+k] * w2[k][j]        (y~ = [valid ; y*valid])
+//   pass 2: out[b,c,i,j] = sum_k w1[k][i] * T[b,c,p0[i]+k,j], then density normalisation.
+// =============================================================================================
+constexpr int KB_MAX = 32;
+
+__global__ void __launch_bounds__(128)
+band_table_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int xb1, int xb2, int N1, int N2,
+                  int mono1, int mono2, double start1, int n1, double start2, int n2, double res, float scale2,
+                  int KB, int* __restrict__ tab_i, float* __restrict__ tab_w) {
+  // layout per batch-of-coordinates bx: tab_i = [q0_1 (n1) | len_1 (n1) | q0_2 (n2) | len_2 (n2)],
+  //                                      tab_w = [w1 (KB x n1) | w2 (KB x n2)]
+  const int bx = blockIdx.y;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= n1 + n2) return;
+  const bool dim2 = e >= n1;
+  const int j = dim2 ? e - n1 : e, n = dim2 ? n2 : n1, N = dim2 ? N2 : N1;
+  const float* x = dim2 ? x2 + (size_t)bx * xb2 : x1 + (size_t)bx * xb1;
+  const float g = cnp_grid_pt(dim2 ? start2 : start1, res, j);
+  const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+  int lo, hi;
+  window_of(x, N, g, g, R, dim2 ? mono2 : mono1, &lo, &hi);
+  const int len = min(hi - lo, KB);
+  int* ti = tab_i + (size_t)bx * 2 * (n1 + n2) + (dim2 ? 2 * n1 : 0);
+  float* tw = tab_w + (size_t)bx * KB * (n1 + n2) + (dim2 ? (size_t)KB * n1 : 0);
+  ti[j] = lo; ti[n + j] = len;
+  for (int k = 0; k < KB; ++k) tw[(size_t)k * n + j] = (k < len) ? cnp_rbf(x[lo + k], g, scale2) : 0.f;
+}
+
+constexpr int P1_ROWS = 4;
+
+__global__ void __launch_bounds__(256)
+enc_grid_pass1_kernel(const float* __restrict__ y, const float* __restrict__ mask, int C, int N1, int N2, int n1,
+                      int n2, int KB, int tab_bstride_i, int tab_bstride_w, const int* __restrict__ tab_i,
+                      const float* __restrict__ tab_w, float* __restrict__ T) {
+  extern __shared__ float ys[];  // [C+1][N2]
+  const int b = blockIdx.y;
+  const int* q0 = tab_i + (size_t)b * tab_bstride_i + 2 * n1;
+  const int* qlen = q0 + n2;
+  const float* w2 = tab_w + (size_t)b * tab_bstride_w + (size_t)KB * n1;
+  const float* yb = y + (size_t)b * C * N1 * N2;
+  const float* mb = mask ? mask + (size_t)b * N1 * N2 : nullptr;
+  for (int r = 0; r < P1_ROWS; ++r) {
+    const int p = blockIdx.x * P1_ROWS + r;
+    if (p >= N1) break;
+    __syncthreads();
+    for (int q = threadIdx.x; q < N2; q += 256) {
+      float valid = mb ? mb[(size_t)p * N2 + q] : 1.f;
+      bool nan_any = false;
+      for (int c = 0; c < C; ++c) nan_any |= isnan(yb[((size_t)c * N1 + p) * N2 + q]);
+      if (nan_any) valid = 0.f;
+      ys[q] = valid;
+      for (int c = 0; c < C; ++c) ys[(c + 1) * N2 + q] = nan_any ? 0.f : yb[((size_t)c * N1 + p) * N2 + q] * valid;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n2; j += 256) {
+      const int s = q0[j], len = qlen[j];
+      float acc[MAXC1];
+#pragma unroll
+      for (int c = 0; c < MAXC1; ++c) acc[c] = 0.f;
+      for (int k = 0; k < len; ++k) {
+        const float w = __ldg(w2 + (size_t)k * n2 + j);
+#pragma unroll
+        for (int c = 0; c < MAXC1; ++c)
+          if (c <= C) acc[c] = fmaf(ys[c * N2 + s + k], w, acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC1; ++c)
+        if (c <= C) T[(((size_t)b * (C + 1) + c) * N1 + p) * n2 + j] = acc[c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+enc_grid_pass2_kernel(const float* __restrict__ T, int C, int N1, int n1, int n2, int KB, int tab_bstride_i,
+                      int tab_bstride_w, const int* __restrict__ tab_i, const float* __restrict__ tab_w, float eps,
+                      float* __restrict__ out, int ch_off, int c_total) {
+  const int tx = threadIdx.x, ty = threadIdx.y, b = blockIdx.z;
+  const int i = blockIdx.y * TI + ty, j = blockIdx.x * TJ + tx;
+  if (i >= n1 || j >= n2) return;
+  const int* p0 = tab_i + (size_t)b * tab_bstride_i;
+  const int s = p0[i], len = p0[n1 + i];
+  const float* w1 = tab_w + (size_t)b * tab_bstride_w;
+  float acc[MAXC1];
+#pragma unroll
+  for (int c = 0; c < MAXC1; ++c) acc[c] = 0.f;
+  for (int k = 0; k < len; ++k) {
+    const float w = __ldg(w1 + (size_t)k * n1 + i);
+    const float* Tr = T + ((size_t)b * (C + 1) * N1 + s + k) * n2 + j;
+#pragma unroll
+    for (int c = 0; c < MAXC1; ++c)
+      if (c <= C) acc[c] = fmaf(w, __ldg(Tr + (size_t)c * N1 * n2), acc[c]);
+  }
+  float* ob = out + ((size_t)b * c_total + ch_off) * n1 * n2 + (size_t)i * n2 + j;
+  const float dens = acc[0];
+  ob[0] = dens;
+  const float den = dens + eps;
+#pragma unroll
+  for (int c = 1; c < MAXC1; ++c)
+    if (c <= C) ob[(size_t)c * n1 * n2] = acc[c] / den;
+}
+
+// =============================================================================================
 // (3) decoder: grid -> off-grid targets, forward.  One block per (target, batch).
 //     z is NCHW fp32 [B, C, n1, n2] with batch stride z_bstride (elements).
 // =============================================================================================
@@ -402,17 +507,57 @@ CNP_API int cnp_setconv_enc_offgrid_fwd(const float* x, const float* y, const fl
   return 0;
 }
 
+// Workspace (bytes) of the banded fast path of cnp_setconv_enc_grid_fwd.
+CNP_API long long cnp_setconv_enc_grid_workspace_bytes(int B, int C, int N1, int n1, int n2, int band) {
+  if (band < 1 || band > KB_MAX) return 0;
+  long long tabs = (long long)B * (2LL * (n1 + n2) * sizeof(int) + (long long)band * (n1 + n2) * sizeof(float));
+  long long T = (long long)B * (C + 1) * N1 * n2 * sizeof(float);
+  return ((tabs + 255) / 256) * 256 + T;
+}
+
+// band: upper bound on the number of inputs within the truncation radius of any grid point along
+// either dimension (host-computed from the coordinates); 1..32 with monotone coordinates and a
+// workspace selects the two-pass banded path, anything else the generic single-kernel path.
 CNP_API int cnp_setconv_enc_grid_fwd(const float* x1, const float* x2, int x_batched, const float* y,
                                      const float* mask, int B, int C, int N1, int N2, int mono1, int mono2,
                                      double start1, int n1, double start2, int n2, double res, float scale2,
-                                     float eps, float* out, int ch_off, int c_total, cudaStream_t stream) {
+                                     float eps, float* out, int ch_off, int c_total, int band, void* workspace,
+                                     long long workspace_bytes, cudaStream_t stream) {
   CNP_REQUIRE(B > 0 && C >= 1 && C + 1 <= MAXC1, "enc_grid: need 1 <= C <= %d (got %d)", MAXC1 - 1, C);
   CNP_REQUIRE(N1 > 0 && N2 > 0 && n1 > 0 && n2 > 0, "enc_grid: bad sizes");
   CNP_REQUIRE(ch_off >= 0 && ch_off + C + 1 <= c_total, "enc_grid: channel window out of range");
+  const size_t p1_smem = (size_t)(C + 1) * N2 * sizeof(float);
+  if (band >= 1 && band <= KB_MAX && mono1 != 0 && mono2 != 0 && workspace && p1_smem <= 200 * 1024) {
+    const long long need = cnp_setconv_enc_grid_workspace_bytes(B, C, N1, n1, n2, band);
+    CNP_REQUIRE(workspace_bytes >= need, "enc_grid: workspace too small (%lld < %lld)", workspace_bytes, need);
+    const int Bx = x_batched ? B : 1;
+    int* tab_i = reinterpret_cast<int*>(workspace);
+    float* tab_w = reinterpret_cast<float*>(tab_i + (size_t)B * 2 * (n1 + n2));
+    const long long tabs = (long long)B * (2LL * (n1 + n2) * sizeof(int) + (long long)band * (n1 + n2) * sizeof(float));
+    float* T = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((tabs + 255) / 256) * 256);
+    dim3 gb(cnp_cdiv(n1 + n2, 128), Bx);
+    band_table_kernel<<<gb, 128, 0, stream>>>(x1, x2, x_batched ? N1 : 0, x_batched ? N2 : 0, N1, N2, mono1, mono2,
+                                              start1, n1, start2, n2, res, scale2, band, tab_i, tab_w);
+    CNP_LAUNCH_CHECK("band_table_kernel");
+    const int tbi = x_batched ? 2 * (n1 + n2) : 0, tbw = x_batched ? band * (n1 + n2) : 0;
+    static size_t attr = 0;
+    if (p1_smem > attr && p1_smem > 48 * 1024) {
+      cudaFuncSetAttribute(enc_grid_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem);
+      attr = p1_smem;
+    }
+    dim3 g1(cnp_cdiv(N1, P1_ROWS), B);
+    enc_grid_pass1_kernel<<<g1, 256, p1_smem, stream>>>(y, mask, C, N1, N2, n1, n2, band, tbi, tbw, tab_i, tab_w, T);
+    CNP_LAUNCH_CHECK("enc_grid_pass1_kernel");
+    dim3 g2(cnp_cdiv(n2, TJ), cnp_cdiv(n1, TI), B), block(TJ, TI);
+    enc_grid_pass2_kernel<<<g2, block, 0, stream>>>(T, C, N1, n1, n2, band, tbi, tbw, tab_i, tab_w, eps, out, ch_off,
+                                                    c_total);
+    CNP_LAUNCH_CHECK("enc_grid_pass2_kernel");
+    return 0;
+  }
   dim3 grid(cnp_cdiv(n2, TJ), cnp_cdiv(n1, TI), B), block(TJ, TI);
   enc_grid_kernel<<<grid, block, 0, stream>>>(x1, x2, x_batched ? N1 : 0, x_batched ? N2 : 0, y, mask, C, N1, N2,
-                                              mono1, mono2, start1, n1, start2, n2, res, scale2, eps, out,
-                                              ch_off, c_total);
+                                              mono1, mono2, start1, n1, start2, n2, res, scale2, eps, out, ch_off,
+                                              c_total);
   CNP_LAUNCH_CHECK("enc_grid_kernel");
   return 0;
 }

@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -44,6 +44,8 @@ class DeviceContext:
     mask: Optional[torch.Tensor]                                # [B,1,N] | [B,1,N1,N2] | None
     mono: Tuple[int, int] = (0, 0)
     x_batched: bool = False
+    x_host: Optional[Tuple[np.ndarray, np.ndarray]] = None   # gridded: host copy of the coordinates
+    band_cache: dict = field(default_factory=dict)           # (grid, scale) -> band hint, shared with uploads
 
 
 @dataclass
@@ -223,7 +225,7 @@ class Engine:
                 mono = (_mono_rows(x1h), _mono_rows(x2h))
                 if shared:
                     x1h, x2h = x1h[:1], x2h[:1]
-                hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared))
+                hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h)))
             else:
                 hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))
         return HostBatch(hctx, cpu(xt), cpu(yt), cpu(aux_t), grid, B)
@@ -246,7 +248,7 @@ class Engine:
         dctx = []
         for c in hb.contexts:
             x = tuple(up(v) for v in c.x) if c.gridded else up(c.x)
-            dctx.append(DeviceContext(c.gridded, x, up(c.y), up(c.mask), c.mono, c.x_batched))
+            dctx.append(DeviceContext(c.gridded, x, up(c.y), up(c.mask), c.mono, c.x_batched, c.x_host, c.band_cache))
         xt = up(hb.xt)
         return DeviceBatch(dctx, xt, up(hb.yt), up(hb.aux_t), hb.grid, hb.B, int(xt.shape[-1]), nbytes)
 
@@ -268,10 +270,16 @@ class Engine:
             if c.gridded:
                 x1, x2 = c.x
                 by = 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) + B * (Ck + 1) * g.n1 * g.n2)
+                N1, N2 = int(x1.shape[-1]), int(x2.shape[-1])
+                band = self._band_hint(c, g, s2)
+                ws, ws_bytes = None, 0
+                if band:
+                    ws_bytes = _cabi.lib().cnp_setconv_enc_grid_workspace_bytes(B, Ck, N1, g.n1, g.n2, band)
+                    ws = self._buf("enc_ws", ((ws_bytes + 3) // 4,))
                 self._call("cnp_setconv_enc_grid_fwd", _ptr(x1), _ptr(x2), int(c.x_batched), _ptr(c.y), _ptr(c.mask),
-                           B, Ck, int(x1.shape[-1]), int(x2.shape[-1]), c.mono[0], c.mono[1],
+                           B, Ck, N1, N2, c.mono[0], c.mono[1],
                            g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
-                           _stream(), work=(0.0, by))
+                           band, _ptr(ws), ws_bytes, _stream(), work=(0.0, by))
             else:
                 by = 4.0 * (c.x.numel() + c.y.numel() + B * (Ck + 1) * g.n1 * g.n2)
                 self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
@@ -279,6 +287,27 @@ class Engine:
                            cfg.in_channels, _stream(), work=(0.0, by))
             ch += Ck + 1
         return enc
+
+    @staticmethod
+    def _band_hint(c: DeviceContext, g: GridSpec, scale2: float) -> int:
+        """Max number of inputs inside the truncation radius of any internal-grid point (both dims),
+        computed on the host from the coordinates; 0 = use the generic kernel."""
+        if c.x_host is None or c.mono[0] == 0 or c.mono[1] == 0:
+            return 0
+        key = (g, scale2)
+        if key in c.band_cache:
+            return c.band_cache[key]
+        R = float(np.sqrt(np.float32(2.0 * 104.0) * np.float32(scale2))) * (1.0 + 1e-6)
+        best = 0
+        for d, xs in enumerate(c.x_host):
+            gp = g.points(d).astype(np.float64)
+            for row in xs:
+                r = np.sort(row.astype(np.float64))
+                cnt = np.searchsorted(r, gp + R, side="right") - np.searchsorted(r, gp - R, side="left")
+                best = max(best, int(cnt.max()))
+        best += 1
+        c.band_cache[key] = best if best <= 32 else 0
+        return c.band_cache[key]
 
     # ------------------------------------------------------------------------------------------
     # (2) UNet, fp32 path
@@ -582,7 +611,8 @@ class Engine:
                 if st[i] == 2:
                     raise NotImplementedError("first UNet level with stride 2")
                 dgrad_tc(d_cat[0].view(0), lyr.weight, "before0", K.KIND_K5S1_DGRAD, 64, d_init, 0, None, 0)
-                wgrad_f32(enc, to_f32(d_init, 0, 64, "w_dy_init"), P + "initial_linear", 1, 1)
+                self._call("cnp_conv1x1_in_wgrad", _ptr(enc), enc.stride(0), cfg.in_channels, C.byref(d_init.view(0)), B,
+                           _ptr(grads[P + "initial_linear.weight"]), _ptr(grads[P + "initial_linear.bias"]), S)
 
     # ------------------------------------------------------------------------------------------
     # (3)+(4) decoder, head

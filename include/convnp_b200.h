@@ -1,0 +1,154 @@
+/* convnp_b200.h -- C ABI of libconvnp_b200.so (sm_100a only).
+ *
+ * The reference (oriordanemily/deepsensorNZ) has no FFI layer: its hot path is reached through the
+ * DeepSensor Python API and executed by torch ops inside
+ * deepsensor==0.3.6 / neuralprocesses==0.2.6.  Each entry point below replaces the torch ops of one
+ * stage of that path; the "replaces" line cites the reference call site that reaches the stage and
+ * the upstream module that implements it today.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  All pointers are DEVICE pointers unless
+ *     stated otherwise; the caller owns every buffer, the callee never allocates, frees or synchronises.
+ *   - every function returns int: 0 = ok, <0 = bad argument (see cnp_last_error()), >0 = cudaError_t.
+ *   - work is enqueued on the cudaStream_t passed as the last argument.
+ *   - fp32 activations are NCHW with an explicit batch stride (in elements) so that channel windows of a
+ *     larger buffer (skip concatenations) can be addressed without copies.
+ *   - bf16 activations use the "blocked" layout [B][C/8][H+4][W+4][8]: channel chunks of 8 (16 B per
+ *     pixel-chunk), each plane physically zero-padded by 2 pixels; described by cnp_blk.  The pad must be
+ *     zero and is never written by the library.  Allocate (16*(W+4)+512)*8 elements of zeroed slack after
+ *     the last plane (tile over-reads).
+ *   - the internal grid is (start1, n1, start2, n2, res): point i along a dimension is
+ *     (float)(start + i*res), computed in double.
+ */
+#ifndef CONVNP_B200_H
+#define CONVNP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* cnp_stream_t; /* == cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+int cnp_version(void);
+const char* cnp_last_error(void);          /* thread-local message of the last failing call */
+int cnp_check_device(void);                /* 0 iff the current device is compute capability 10.x */
+
+/* ---- (1) SetConv encoder -------------------------------------------------------------------
+ * replaces: neuralprocesses PrependDensityChannel + SetConv + DivideByFirstChannel (coders/setconv/*.py),
+ * reached from ConvNP.loss_fn / __call__ / predict -- nzdownscale/downscaler/train.py:370,:388-394,
+ * validate_ERA.py:88-92.  Writes channels [ch_off, ch_off+1+C) of out [B,c_total,n1,n2] (fp32 NCHW):
+ * density first, then data/(density+eps).  y may contain NaN: a point/cell with any NaN channel is
+ * treated as missing (mask 0), exactly like Task.mask_nans_numpy/mask_nans_nps on the host.
+ * scale2 = exp(2*log_scale). */
+int cnp_setconv_enc_offgrid_fwd(const float* x /*[B,2,N]*/, const float* y /*[B,C,N]*/,
+                                const float* mask /*[B,1,N] or NULL*/, int B, int C, int N,
+                                double start1, int n1, double start2, int n2, double res,
+                                float scale2, float eps, float* out, int ch_off, int c_total, cnp_stream_t s);
+long long cnp_setconv_enc_grid_workspace_bytes(int B, int C, int N1, int n1, int n2, int band);
+int cnp_setconv_enc_grid_fwd(const float* x1 /*[B or 1,N1]*/, const float* x2 /*[B or 1,N2]*/, int x_batched,
+                             const float* y /*[B,C,N1,N2]*/, const float* mask /*[B,1,N1,N2] or NULL*/,
+                             int B, int C, int N1, int N2, int mono1 /*+1 asc,-1 desc,0 unsorted*/, int mono2,
+                             double start1, int n1, double start2, int n2, double res,
+                             float scale2, float eps, float* out, int ch_off, int c_total,
+                             int band /*0 = generic kernel*/, void* workspace, long long workspace_bytes,
+                             cnp_stream_t s);
+
+/* ---- (2) UNet, fp32 parity path ------------------------------------------------------------
+ * replaces: torch Conv2d / Upsample(bilinear) / ReLU and their autograd inside neuralprocesses
+ * coders/nn.py UNet, reached from train_epoch (train.py:388-394).  Weights are torch layout
+ * [Cout][Cin][k][k]; supported (k,stride): (5,1) (5,2) (1,1); padding k/2. */
+int cnp_conv2d_fwd_f32(const float* x, long long x_bstride, const float* w, const float* bias, float* y,
+                       long long y_bstride, int B, int Cin, int Hin, int Win, int Cout, int k, int stride,
+                       int relu, cnp_stream_t s);
+int cnp_conv2d_dgrad_f32(const float* dy, long long dy_bstride, const float* w, float* dx, long long dx_bstride,
+                         int B, int Cin, int Hin, int Win, int Cout, int k, int stride, int accumulate,
+                         cnp_stream_t s);
+int cnp_conv2d_wgrad_f32(const float* x, long long x_bstride, const float* dy, long long dy_bstride,
+                         float* dw /*+=*/, float* dbias /*+= or NULL*/, int B, int Cin, int Hin, int Win, int Cout,
+                         int k, int stride, cnp_stream_t s);
+int cnp_relu_bwd_f32(float* dy /*in place*/, long long dy_bstride, const float* y, long long y_bstride, int B,
+                     long long per_batch, cnp_stream_t s);
+int cnp_upsample2x_fwd_f32(const float* x, long long x_bstride, float* y, long long y_bstride, int B, int C, int H,
+                           int W, cnp_stream_t s);
+int cnp_upsample2x_bwd_f32(const float* dy, long long dy_bstride, float* dx, long long dx_bstride, int B, int C,
+                           int H, int W, int accumulate, cnp_stream_t s);
+
+/* ---- (2) UNet, bf16 tensor-core path (tcgen05, TMEM accumulators, bulk-copy staging) ------------- */
+typedef struct cnp_blk {
+  void* base;          /* first element of batch 0, chunk 0 */
+  long long bstride;   /* elements between batches */
+  int cb_off;          /* first channel chunk of the view */
+  int H, W;            /* interior size; planes are (H+4) x (W+4) */
+} cnp_blk;
+
+typedef struct cnp_conv_out {
+  int mode;            /* 0: blocked bf16 (blk), 1: fp32 NCHW (f32, f32_bstride, f32_ch_off) */
+  cnp_blk blk;
+  float* f32; long long f32_bstride; int f32_ch_off;
+  int sy, ay, sx, ax;  /* output pixel = (y*sy+ay, x*sx+ax); 1,0,1,0 for a plain conv */
+  const float* bias;   /* [64] or NULL */
+  int relu;
+  const cnp_blk* mask; /* zero the result where mask <= 0 (ReLU backward), or NULL */
+  int accumulate;      /* out += result */
+} cnp_conv_out;
+
+enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5 };
+enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2 };
+
+long long cnp_conv_tc_packed_bytes(int kind, int n_chunks);
+int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px, int co_off,
+                     void* wpk, cnp_stream_t s);
+/* 64 output channels per call; x chunks [x->cb_off, +n_chunks) are the reduction dimension.
+ * CNP_K5S2 reads the 32-chunk space-to-depth tensor; CNP_K5S2_DGRAD produces output phase (py,px). */
+int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, const cnp_conv_out* out,
+                int B, cnp_stream_t s);
+int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw /*+= [64][Cin][k][k]*/,
+                      int Cin, int B, cnp_stream_t s);
+int cnp_blk_channel_sum(const cnp_blk* v, int n_chunks, int B, float* out /*+=*/, cnp_stream_t s);
+int cnp_conv1x1_in_bf16(const float* x /*fp32 NCHW*/, long long x_bstride, const float* w, const float* bias, int B,
+                        int Cin, int Cout, const cnp_blk* out, cnp_stream_t s);
+int cnp_conv1x1_in_wgrad(const float* x, long long x_bstride, int Cin, const cnp_blk* dy, int B, float* dw,
+                         float* dbias, cnp_stream_t s);
+int cnp_blk_upsample2x_fwd(const cnp_blk* x, int n_chunks, const cnp_blk* y, int B, cnp_stream_t s);
+int cnp_blk_upsample2x_bwd(const cnp_blk* dy, int n_chunks, const cnp_blk* dx, const cnp_blk* act /*or NULL*/,
+                           int accumulate, int B, cnp_stream_t s);
+int cnp_blk_space_to_depth(const cnp_blk* x, int n_chunks, const cnp_blk* y /*32 chunks, half size*/, int B,
+                           cnp_stream_t s);
+int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B, int C, int H, int W, const cnp_blk* dst,
+                          cnp_stream_t s);
+int cnp_blk_to_nchw_f32(const cnp_blk* src, int B, int C, float* dst, long long dst_bstride, cnp_stream_t s);
+
+/* ---- (3) SetConv decoder, grid -> off-grid targets -------------------------------------------
+ * replaces: neuralprocesses SetConv(scale=1/ppu) in the decoder chain + its autograd (A.5). */
+int cnp_setconv_dec_offgrid_fwd(const float* z /*[B,C,n1,n2]*/, long long z_bstride, const float* xt /*[B,2,Nt]*/,
+                                int B, int C, int Nt, double start1, int n1, double start2, int n2, double res,
+                                float scale2, float* f /*[B,f_ctotal,Nt]*/, int f_ctotal, cnp_stream_t s);
+int cnp_setconv_dec_offgrid_bwd(const float* df, int f_ctotal, const float* xt, int B, int C, int Nt,
+                                double start1, int n1, double start2, int n2, double res, float scale2,
+                                float* dz, long long dz_bstride, cnp_stream_t s);
+
+/* ---- (4) aux-at-target MLP + heteroscedastic Gaussian head + normalised NLL -----------------------
+ * replaces: neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood -> MultiOutputNormal.logpdf
+ * -> nps.loglik (A.6, A.7) reached from ConvNP.loss_fn (train.py:370).  logp is float64. */
+#define CNP_MLP_MAX_LAYERS 6
+typedef struct cnp_mlp_params {
+  const float* W[CNP_MLP_MAX_LAYERS];  /* [out,in] row-major */
+  const float* b[CNP_MLP_MAX_LAYERS];
+  float* dW[CNP_MLP_MAX_LAYERS];       /* += (backward only) */
+  float* db[CNP_MLP_MAX_LAYERS];
+  int dims[CNP_MLP_MAX_LAYERS + 1];    /* dims[0] = Cf + Ca, dims[n_layers] = 2 */
+  int n_layers;
+} cnp_mlp_params;                      /* HOST struct holding DEVICE pointers */
+int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
+                     const float* yt /*or NULL*/, int B, int Nt, float* mean, float* var,
+                     double* logp /*[B] += or NULL*/, int* count /*[B] +=*/, cnp_stream_t s);
+int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
+                     const float* yt, int B, int Nt, const float* dlogp /*[B]*/, float* df, cnp_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONVNP_B200_H */

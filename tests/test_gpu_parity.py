@@ -329,3 +329,63 @@ def test_conv_tc_wgrad(cin, stride, k, h, w):
     db = torch.zeros(64, device="cuda")
     _cabi.call("cnp_blk_channel_sum", C.byref(dyb.view()), 8, B, db.data_ptr(), _S())
     assert rel_err(db, dy.double().sum(dim=(0, 2, 3))) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# committed golden vectors (tests/golden/*.npz, generated by tests/golden/make_golden.py from the oracle)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["g1_single", "g2_batch3", "g3_multivar"])
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_cuda_path_matches_golden(name, precision, tol):
+    import importlib.util
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gdir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    m, task = mg.build(name)
+    gold = np.load(os.path.join(gdir, name + ".npz"))
+    m2 = small_model(precision, ppu=m.config.points_per_unit, dim_yc=m.config.dim_yc, seed=1234)
+    g = m2._to_device(task).grid
+    assert [g.start1, g.n1, g.start2, g.n2, g.res] == list(gold["grid"])
+    pred = m2(task)
+    assert rel_err(pred["mean"], gold["mean"]) < tol
+    assert rel_err(pred["std"], np.sqrt(gold["var"])) < tol
+    loss = m2.loss_fn(task, normalise=True)
+    assert abs(float(loss) - float(gold["loss"])) < tol * abs(float(gold["loss"]))
+    loss.backward()
+    gtol = 1e-4 if precision == "fp32" else 0.15
+    assert rel_err(m2.model.decoder.unet.final_linear.bias.grad, gold["d_final_bias"]) < gtol
+    assert rel_err(m2.model.decoder.mlp.layers[0].weight.grad, gold["d_mlp0"]) < gtol
+
+
+def test_nan_loss_surfaces_as_nan(static):
+    """train.py:371,395 filter NaN losses: a poisoned task must give NaN, not crash."""
+    m = small_model("fp32")
+    t = make_task(static, 77)
+    t["Y_t_aux"][0, 3] = np.inf
+    loss = m.loss_fn(t, normalise=True)
+    assert not np.isfinite(float(loss))
+
+
+def test_encoder_frozen_and_requires_grad_honoured(static):
+    m = small_model("fp32")
+    for p in m.model.decoder.unet.before_turn_layers[0].parameters():
+        p.requires_grad = False
+    loss = m.loss_fn(make_task(static, 78), normalise=True)
+    loss.backward()
+    assert m.model.decoder.unet.before_turn_layers[0].weight.grad is None
+    assert m.model.decoder.unet.before_turn_layers[1].weight.grad is not None
+    assert all(p.grad is None for p in m.model.encoder.parameters())
+
+
+def test_train_epoch_decreases_loss(static):
+    from deepsensornz_b200 import train_epoch
+    np.random.seed(0)
+    m = small_model("bf16")
+    tasks = [make_task(static, 500 + i) for i in range(8)]
+    opt = torch.optim.AdamW(m.model.parameters(), lr=2e-3)
+    first = np.mean(train_epoch(m, tasks, batch_size=4, opt=opt))
+    for _ in range(5):
+        last = np.mean(train_epoch(m, tasks, batch_size=4, opt=opt))
+    assert np.isfinite(first) and last < first
