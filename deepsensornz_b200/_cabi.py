@@ -82,6 +82,11 @@ _SIGS = {
     "cnp_relu_bwd_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, _i, _ll, c_stream]),
     "cnp_upsample2x_fwd_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, _i, _i, _i, _i, c_stream]),
     "cnp_upsample2x_bwd_f32": (C.c_int, [c_fp, _ll, c_fp, _ll, _i, _i, _i, _i, _i, c_stream]),
+    "cnp_setconv_dec_grid_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
+    "cnp_setconv_dec_grid_fwd": (C.c_int, [c_fp, _ll, c_fp, c_fp, _i, _i, _i, _i] + _GRID + [_f, c_fp, _ll, c_fp, _ll,
+                                           c_stream]),
+    "cnp_mlp_head_points_fwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _ll, _i, c_fp, _ll, _i, _i, _ll, c_fp, c_fp,
+                                          c_stream]),
     # (4) MLP + Gaussian head + NLL
     "cnp_mlp_head_fwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp,
                                    c_fp, c_stream]),
@@ -97,7 +102,7 @@ _SIGS = {
     "cnp_blk_upsample2x_fwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
     "cnp_blk_upsample2x_bwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, _i, c_stream]),
     "cnp_blk_space_to_depth": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
-    "cnp_conv_tc_wgrad": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_fp, _i, _i, c_stream]),
+    "cnp_conv_tc_wgrad": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_fp, c_fp, _i, _i, c_stream]),
     "cnp_conv1x1_in_wgrad": (C.c_int, [c_fp, _ll, _i, C.POINTER(CnpBlk), _i, c_fp, c_fp, c_stream]),
     "cnp_blk_channel_sum": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, c_stream]),
 }

@@ -222,6 +222,9 @@ class ConvNP:
         batch = self._to_device(task)
         with torch.no_grad():
             out = self.engine.forward(batch, with_loss=False)
+        if out["var"] is None:  # on-grid targets: [B,1,P,Q]
+            mean, std = out["mean"].unsqueeze(1), out["std"].unsqueeze(1)
+            return GaussianPrediction(mean=mean, var=std * std, std=std)
         mean, var = out["mean"].unsqueeze(1), out["var"].unsqueeze(1)
         return GaussianPrediction(mean=mean, var=var, std=var.sqrt())
 

@@ -191,38 +191,47 @@ conv_tc_kernel(const __grid_constant__ cnp_conv_args a) {
         const bool valid = (ty < a.TH) && (tx < a.TW) && (y < a.H) && (x < a.W);
         const int oy = y * a.sy + a.ay, ox = x * a.sx + a.ax;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * (TMEM_COLS / ACC_STAGES) + r * N_OUT;
+        if (a.out_mode == 0) {
+          const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
+                                 ((long long)a.out_c_off * oplane + pix) * 8;
+          // issue every mask / read-modify-write load of this pixel up front (independent 16 B loads in
+          // flight) so the epilogue is bandwidth- rather than latency-bound
+          uint4 mk[8], old[8];
+          if (a.mask && valid) {
+            const __nv_bfloat16* mbase = a.mask + (long long)b * a.mask_bs + ((long long)a.mask_cb_off * oplane + pix) * 8;
 #pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
-          float v[32];
-          tc::tmem_ld32(taddr + hc * 32, v);
-          tc::tmem_ld_wait();
-          if (a.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + hc * 32 + i);
+            for (int c = 0; c < 8; ++c) mk[c] = __ldg(reinterpret_cast<const uint4*>(mbase + (long long)c * oplane * 8));
           }
-          if (a.relu) {
+          if (a.accumulate && valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            for (int c = 0; c < 8; ++c) old[c] = *reinterpret_cast<const uint4*>(obase + (long long)c * oplane * 8);
           }
-          if (valid) {
-            if (a.out_mode == 0) {
-              const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            float v[32];
+            tc::tmem_ld32(taddr + hc * 32, v);
+            tc::tmem_ld_wait();
+            if (a.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + hc * 32 + i);
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] < 0.f ? 0.f : v[i];
+            }
+            if (valid) {
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int chunk = hc * 4 + c8;
                 float* vv = v + c8 * 8;
                 if (a.mask) {
-                  const uint4 mk = __ldg(reinterpret_cast<const uint4*>(
-                      a.mask + (long long)b * a.mask_bs + ((long long)(a.mask_cb_off + chunk) * oplane + pix) * 8));
-                  const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk);
+                  const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mk[chunk]);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) if (!(__bfloat162float(mb[i]) > 0.f)) vv[i] = 0.f;
                 }
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
-                                     ((long long)(a.out_c_off + chunk) * oplane + pix) * 8;
                 if (a.accumulate) {
-                  const uint4 old = *reinterpret_cast<const uint4*>(dst);
-                  const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(&old);
+                  const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(&old[chunk]);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) vv[i] += __bfloat162float(ob[i]);
                 }
@@ -230,9 +239,25 @@ conv_tc_kernel(const __grid_constant__ cnp_conv_args a) {
                 __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(vv[2 * i], vv[2 * i + 1]);
-                *reinterpret_cast<uint4*>(dst) = pk;
+                *reinterpret_cast<uint4*>(obase + (long long)chunk * oplane * 8) = pk;
               }
-            } else {
+            }
+          }
+        } else {
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            float v[32];
+            tc::tmem_ld32(taddr + hc * 32, v);
+            tc::tmem_ld_wait();
+            if (a.bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + hc * 32 + i);
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] < 0.f ? 0.f : v[i];
+            }
+            if (valid) {
               float* dst = reinterpret_cast<float*>(a.out) + (long long)b * a.out_bs +
                            ((long long)(a.out_c_off + hc * 32) * a.out_Hp + oy) * a.out_Wp + ox;
               const long long cs = (long long)a.out_Hp * a.out_Wp;
@@ -404,7 +429,7 @@ conv1x1_in_wgrad_kernel(const float* __restrict__ x, long long x_bs, int Cin, in
     const int b = t / tiles_per_img, e0 = (t % tiles_per_img) * IW_PX;
     __syncthreads();
     for (int e = threadIdx.x; e < IW_PX * 8; e += 256) {
-      const int px = e >> 3, chunk = e & 7, pe = e0 + px;
+      const int px = e & (IW_PX - 1), chunk = e >> 7, pe = e0 + px;
       float v[8];
       if (pe < HW) {
         const int yy = pe / W, xx = pe % W;

@@ -100,7 +100,7 @@ conv_fwd_kernel(const float* __restrict__ x, long long x_bs, int Cin, int Hin, i
     for (int c = 0; c < CO_T; ++c) {
       if (co0 + c < Cout) {
         float v = acc[p][c] + (bias ? __ldg(bias + co0 + c) : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
+        if (relu && v < 0.f) v = 0.f;  // NaN propagates like torch.relu
         float* dst = yb + ((size_t)(co0 + c) * Hout + oy) * Wout + ox;
         if (accumulate) v += *dst;
         *dst = v;

@@ -1,0 +1,225 @@
+// Inference decoder: SetConv from the internal grid onto an ON-GRID target (x1t x x2t, e.g. the
+// 1400x1400 NZ grid) and the aux-at-target MLP + Gaussian head over every target pixel.
+//
+// Replaces, for ConvNP.predict(tasks, X_t=ds_elev) (nzdownscale/downscaler/validate_ERA.py:88-92,
+// validate_WRF.py:227-231, validate.py:1106), the dense upstream einsum 'bcij,bip,bjq->bcpq'
+// (98.6 GFLOP per task untruncated) and the cuBLAS MLP over 1.96 M rows (a6).
+// The set-conv is separable and truncated at the fp32-exact radius (see common.cuh):
+//   pass A: T[b,c,i,q] = sum_j z[b,c,i,j] w2[j,q]     (band of <= 32 grid columns per target column)
+//   pass B: f[b,c,p,q] = sum_i w1[i,p] T[b,c,i,q]
+// Band tables are analytic (the internal grid is uniform), so arbitrary target coordinates work.
+#include "common.cuh"
+#include <math.h>
+
+#include "mlp_params.cuh"
+
+namespace {
+
+constexpr int DKB = 40;  // max band (grid points within the truncation radius of one target coordinate)
+
+// per target coordinate t: first grid index j0[t], count len[t], weights w[k][t]
+__global__ void __launch_bounds__(128)
+dec_band_kernel(const float* __restrict__ xt, int T, double start, int n, double res, float scale2,
+                int* __restrict__ j0, int* __restrict__ len, float* __restrict__ w) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= T) return;
+  const float x = xt[t];
+  const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+  int lo = (int)floor(((double)x - R - start) / res) - 1;
+  int hi = (int)ceil(((double)x + R - start) / res) + 1;
+  lo = max(lo, 0); hi = min(hi, n - 1);
+  // shrink to the exact non-zero support so that the band fits DKB
+  while (lo <= hi && cnp_rbf(x, cnp_grid_pt(start, res, lo), scale2) == 0.f) ++lo;
+  while (hi >= lo && cnp_rbf(x, cnp_grid_pt(start, res, hi), scale2) == 0.f) --hi;
+  const int L = min(max(hi - lo + 1, 0), DKB);
+  j0[t] = lo; len[t] = L;
+  for (int k = 0; k < DKB; ++k) w[(size_t)k * T + t] = (k < L) ? cnp_rbf(x, cnp_grid_pt(start, res, lo + k), scale2) : 0.f;
+}
+
+// pass A: one block per (grid row i, channel c, batch b): stage z row, produce Q outputs
+__global__ void __launch_bounds__(256)
+dec_grid_passA_kernel(const float* __restrict__ z, long long z_bs, int C, int n1, int n2, int Q,
+                      const int* __restrict__ j0, const int* __restrict__ len, const float* __restrict__ w2,
+                      float* __restrict__ T) {
+  extern __shared__ float zr[];  // [n2]
+  const int i = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+  const float* src = z + (size_t)b * z_bs + ((size_t)c * n1 + i) * n2;
+  for (int j = threadIdx.x; j < n2; j += 256) zr[j] = src[j];
+  __syncthreads();
+  float* dst = T + (((size_t)b * C + c) * n1 + i) * Q;
+  for (int q = threadIdx.x; q < Q; q += 256) {
+    const int s = j0[q], L = len[q];
+    float acc = 0.f;
+    for (int k = 0; k < L; ++k) acc = fmaf(zr[s + k], __ldg(w2 + (size_t)k * Q + q), acc);
+    dst[q] = acc;
+  }
+}
+
+// pass B: f[b,c,p,q] = sum_k w1[k][p] T[b,c,i0[p]+k,q]; block = 8 rows p x 32 cols q, loops channels
+__global__ void __launch_bounds__(256)
+dec_grid_passB_kernel(const float* __restrict__ T, int C, int n1, int P, int Q, const int* __restrict__ i0,
+                      const int* __restrict__ len, const float* __restrict__ w1, float* __restrict__ f,
+                      long long f_bs) {
+  const int q = blockIdx.x * 32 + (threadIdx.x & 31), p = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+  if (p >= P || q >= Q) return;
+  const int s = i0[p], L = len[p];
+  float wv[DKB];
+#pragma unroll
+  for (int k = 0; k < DKB; ++k) wv[k] = (k < L) ? __ldg(w1 + (size_t)k * P + p) : 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* Tc = T + (((size_t)b * C + c) * n1 + s) * Q + q;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < DKB; ++k)
+      if (k < L) acc = fmaf(wv[k], __ldg(Tc + (size_t)k * Q), acc);
+    f[(size_t)b * f_bs + ((size_t)c * P + p) * Q + q] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-point MLP + Gaussian head, one THREAD per target point (hidden width 64, input <= 72).
+// Inputs of a layer live in registers, weights are broadcast float4 reads from shared memory,
+// layer outputs go through a conflict-free [64][256] shared buffer.
+// ---------------------------------------------------------------------------------------------
+constexpr int GP_IN = 72;   // padded input width of layer 0
+constexpr int GP_H = 64;
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+template <int IN>
+__device__ __forceinline__ void gp_layer(const float* __restrict__ wl, const float* __restrict__ bl, int nout,
+                                         const float (&a)[IN], float* __restrict__ hbuf, int tid) {
+  for (int o = 0; o < nout; ++o) {
+    const float4* wr = reinterpret_cast<const float4*>(wl + (size_t)o * IN);
+    float s0 = bl[o], s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < IN / 4; ++i) {
+      const float4 w = wr[i];
+      s0 = fmaf(w.x, a[4 * i + 0], s0); s1 = fmaf(w.y, a[4 * i + 1], s1);
+      s0 = fmaf(w.z, a[4 * i + 2], s0); s1 = fmaf(w.w, a[4 * i + 3], s1);
+    }
+    hbuf[o * 256 + tid] = s0 + s1;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+mlp_head_points_kernel(cnp_mlp_params p, const float* __restrict__ f, long long f_bs, int Cf,
+                       const float* __restrict__ aux, long long aux_bs, int Ca, long long npts,
+                       float* __restrict__ mean, float* __restrict__ stdv) {
+  extern __shared__ __align__(16) float sm[];
+  const int L = p.n_layers;
+  // weights: layer 0 [64][GP_IN], hidden [64][64], last [2][64]; biases after each
+  float* w0 = sm;
+  float* b0 = w0 + GP_H * GP_IN;
+  float* wh = b0 + GP_H;                         // (L-2) x ([64][64] + [64])
+  float* wl = wh + (size_t)(L - 2) * (GP_H * GP_H + GP_H);
+  float* bl = wl + 2 * GP_H;
+  float* hbuf = bl + 4;                          // [64][256]
+  const int in0 = p.dims[0];
+  for (int e = threadIdx.x; e < GP_H * GP_IN; e += 256) {
+    const int o = e / GP_IN, i = e % GP_IN;
+    w0[e] = i < in0 ? p.W[0][(size_t)o * in0 + i] : 0.f;
+  }
+  for (int e = threadIdx.x; e < GP_H; e += 256) b0[e] = p.b[0][e];
+  for (int l = 1; l < L - 1; ++l) {
+    float* wd = wh + (size_t)(l - 1) * (GP_H * GP_H + GP_H);
+    for (int e = threadIdx.x; e < GP_H * GP_H; e += 256) wd[e] = p.W[l][e];
+    for (int e = threadIdx.x; e < GP_H; e += 256) wd[GP_H * GP_H + e] = p.b[l][e];
+  }
+  for (int e = threadIdx.x; e < 2 * GP_H; e += 256) wl[e] = p.W[L - 1][e];
+  if (threadIdx.x < 2) bl[threadIdx.x] = p.b[L - 1][threadIdx.x];
+  __syncthreads();
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const float* fb = f + (size_t)b * f_bs;
+  const float* ab = aux + (size_t)b * aux_bs;
+  for (long long pt = (long long)blockIdx.x * 256 + tid; pt < npts; pt += (long long)gridDim.x * 256) {
+    float a0[GP_IN];
+#pragma unroll
+    for (int i = 0; i < GP_IN; ++i) {
+      float v = 0.f;
+      if (i < Cf) v = __ldg(fb + (size_t)i * npts + pt);
+      else if (i < Cf + Ca) v = __ldg(ab + (size_t)(i - Cf) * npts + pt);
+      a0[i] = v;
+    }
+    gp_layer<GP_IN>(w0, b0, GP_H, a0, hbuf, tid);
+    float a[GP_H];
+    for (int l = 1; l < L - 1; ++l) {
+#pragma unroll
+      for (int i = 0; i < GP_H; ++i) { const float v = hbuf[i * 256 + tid]; a[i] = v < 0.f ? 0.f : v; }
+      const float* wd = wh + (size_t)(l - 1) * (GP_H * GP_H + GP_H);
+      gp_layer<GP_H>(wd, wd + GP_H * GP_H, GP_H, a, hbuf, tid);
+    }
+#pragma unroll
+    for (int i = 0; i < GP_H; ++i) { const float v = hbuf[i * 256 + tid]; a[i] = v < 0.f ? 0.f : v; }
+    float o0 = bl[0], o1 = bl[1];
+#pragma unroll
+    for (int i = 0; i < GP_H; ++i) { o0 = fmaf(wl[i], a[i], o0); o1 = fmaf(wl[GP_H + i], a[i], o1); }
+    mean[(size_t)b * npts + pt] = o0;
+    stdv[(size_t)b * npts + pt] = sqrtf(1e-6f + softplus_t(o1));
+  }
+}
+
+}  // namespace
+
+CNP_API long long cnp_setconv_dec_grid_workspace_bytes(int B, int C, int n1, int P, int Q) {
+  long long tabs = (long long)(P + Q) * (2 * sizeof(int) + DKB * sizeof(float));
+  long long T = (long long)B * C * n1 * Q * sizeof(float);
+  return ((tabs + 255) / 256) * 256 + T;
+}
+
+// f [B,C,P,Q] (batch stride f_bstride) = SetConv of z [B,C,n1,n2] onto the target grid x1t[P] x x2t[Q].
+CNP_API int cnp_setconv_dec_grid_fwd(const float* z, long long z_bstride, const float* x1t, const float* x2t, int B,
+                                     int C, int P, int Q, double start1, int n1, double start2, int n2, double res,
+                                     float scale2, float* f, long long f_bstride, void* workspace,
+                                     long long workspace_bytes, cudaStream_t st) {
+  CNP_REQUIRE(z && x1t && x2t && f && workspace && B > 0 && C > 0 && P > 0 && Q > 0, "dec_grid: bad arguments");
+  CNP_REQUIRE(workspace_bytes >= cnp_setconv_dec_grid_workspace_bytes(B, C, n1, P, Q), "dec_grid: workspace too small");
+  const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+  CNP_REQUIRE(2.0 * R / res + 3 <= DKB, "dec_grid: decoder scale too large for the banded kernel (band > %d)", DKB);
+  int* i0 = reinterpret_cast<int*>(workspace);
+  int* len1 = i0 + P;
+  int* j0 = len1 + P;
+  int* len2 = j0 + Q;
+  float* w1 = reinterpret_cast<float*>(len2 + Q);
+  float* w2 = w1 + (size_t)DKB * P;
+  const long long tabs = (long long)(P + Q) * (2 * sizeof(int) + DKB * sizeof(float));
+  float* T = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((tabs + 255) / 256) * 256);
+  dec_band_kernel<<<cnp_cdiv(P, 128), 128, 0, st>>>(x1t, P, start1, n1, res, scale2, i0, len1, w1);
+  dec_band_kernel<<<cnp_cdiv(Q, 128), 128, 0, st>>>(x2t, Q, start2, n2, res, scale2, j0, len2, w2);
+  CNP_LAUNCH_CHECK("dec_band_kernel");
+  dim3 ga(n1, C, B);
+  dec_grid_passA_kernel<<<ga, 256, n2 * sizeof(float), st>>>(z, z_bstride, C, n1, n2, Q, j0, len2, w2, T);
+  CNP_LAUNCH_CHECK("dec_grid_passA_kernel");
+  dim3 gb(cnp_cdiv(Q, 32), cnp_cdiv(P, 8), B);
+  dec_grid_passB_kernel<<<gb, 256, 0, st>>>(T, C, n1, P, Q, i0, len1, w1, f, f_bstride);
+  CNP_LAUNCH_CHECK("dec_grid_passB_kernel");
+  return 0;
+}
+
+// mean / std over npts target points per batch element; f [B,Cf,npts], aux [B or 1,Ca,npts].
+// Specialised for hidden width 64 and Cf+Ca <= 72 (the configuration DeepSensor builds); returns -1 otherwise.
+CNP_API int cnp_mlp_head_points_fwd(const cnp_mlp_params* p, const float* f, long long f_bstride, int Cf,
+                                    const float* aux, long long aux_bstride, int Ca, int B, long long npts,
+                                    float* mean, float* stdv, cudaStream_t st) {
+  CNP_REQUIRE(p && f && aux && mean && stdv && B > 0 && npts > 0, "mlp_head_points: bad arguments");
+  CNP_REQUIRE(p->n_layers >= 3 && p->n_layers <= CNP_MLP_MAX_LAYERS, "mlp_head_points: need >= 2 hidden layers");
+  CNP_REQUIRE(p->dims[0] == Cf + Ca && p->dims[0] <= GP_IN, "mlp_head_points: input width %d > %d", p->dims[0], GP_IN);
+  for (int l = 1; l < p->n_layers; ++l)
+    CNP_REQUIRE(p->dims[l] == GP_H, "mlp_head_points: hidden width must be %d (got %d)", GP_H, p->dims[l]);
+  CNP_REQUIRE(p->dims[p->n_layers] == 2, "mlp_head_points: last layer must have 2 outputs");
+  const int L = p->n_layers;
+  const size_t smem = (size_t)(GP_H * GP_IN + GP_H + (L - 2) * (GP_H * GP_H + GP_H) + 2 * GP_H + 4 + GP_H * 256) *
+                      sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(mlp_head_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  long long nb = (npts + 255) / 256;
+  dim3 grid((unsigned)(nb < 2 * sms ? nb : 2 * sms), B);
+  mlp_head_points_kernel<<<grid, 256, smem, st>>>(*p, f, f_bstride, Cf, aux, aux_bstride, Ca, npts, mean, stdv);
+  CNP_LAUNCH_CHECK("mlp_head_points_kernel");
+  return 0;
+}

@@ -9,16 +9,7 @@
 #include "common.cuh"
 #include <math.h>
 
-#define CNP_MLP_MAX_LAYERS 6
-
-struct cnp_mlp_params {
-  const float* W[CNP_MLP_MAX_LAYERS];   // [out,in] row-major (torch Linear.weight)
-  const float* b[CNP_MLP_MAX_LAYERS];   // [out]
-  float* dW[CNP_MLP_MAX_LAYERS];        // (+=) gradients, backward only
-  float* db[CNP_MLP_MAX_LAYERS];
-  int dims[CNP_MLP_MAX_LAYERS + 1];     // dims[0] = Cf + Ca, dims[n_layers] = 2
-  int n_layers;
-};
+#include "mlp_params.cuh"
 
 namespace {
 
@@ -60,7 +51,7 @@ __device__ __forceinline__ void layer_fwd(const float* ws, const Offsets& o, con
     const float* wr = ws + o.w[l] + oo * (in + 1);
     float s = ws[o.b[l] + oo];
     for (int i = 0; i < in; ++i) s = fmaf(wr[i], hin[i], s);
-    hout[oo] = relu ? fmaxf(s, 0.f) : s;
+    hout[oo] = (relu && s < 0.f) ? 0.f : s;  // NaN propagates like torch.relu
   }
 }
 

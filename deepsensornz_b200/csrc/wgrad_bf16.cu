@@ -39,7 +39,7 @@ struct cnp_wg_pass {
 struct cnp_wg_args {
   const __nv_bfloat16* x; long long x_bs; long long x_plane;   // elements
   const __nv_bfloat16* dy; long long dy_bs; long long dy_plane;
-  float* dw; int Cin, KK;
+  float* dw; float* dbias; int Cin, KK;
   int B, P, p_start, tiles_per_img, ksplit, n_pass;
   cnp_wg_pass pass[CNP_WG_MAX_PASS];
 };
@@ -67,7 +67,8 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   const int total_tiles = a.B * a.tiles_per_img;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    const bool bias_cta0 = (a.dbias != nullptr);
+    for (int i = 0; i < WG_STAGES; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, bias_cta0 ? 5 : 1); }
     tc::mbar_init(done, 1);
     tc::mbar_fence_init();
   }
@@ -125,6 +126,39 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
     // epilogue warps 2..5 -> TMEM lane quadrant (warp & 3)
     const int q = warp & 3;
     const bool has_work = blockIdx.x < total_tiles;
+    if (a.dbias != nullptr) {
+      // bias gradient: these warps idle in the K loop, so they sum the dY tiles streamed anyway; every tile
+      // is seen by all passes (blockIdx.y), tile #it is summed by pass it % n_pass to spread the LDS traffic
+      const int et = (warp - 2) * 32 + lane;  // 0..127
+      float bs[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) bs[i] = 0.f;
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
+        const int s = it % WG_STAGES;
+        tc::mbar_wait(full + s, (it / WG_STAGES) & 1);
+        const uint8_t* ds = smem + s * stage_b + x_tile_b;
+        if ((int)(it % (uint32_t)a.n_pass) == (int)blockIdx.y)
+        for (int px = et; px < P; px += 128) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(ds + c * dy_plane_b + px * 16);
+            const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bs[c * 8 + i] += __bfloat162float(pb[i]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(empty + s);
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float v = bs[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && has_work) atomicAdd(a.dbias + i, v);
+      }
+    }
     if (has_work) {
       tc::mbar_wait(done, 0);
       tc::fence_after_sync();
@@ -193,10 +227,10 @@ blk_channel_sum_kernel(const __nv_bfloat16* __restrict__ v, long long bs, int cb
 
 enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2 };
 
-// dw (+=) torch layout [64][Cin][k][k] fp32.  x: source view (n_chunks = 8 or 16; 32 = phase tensor for
+// dw (+=) torch layout [64][Cin][k][k] fp32; dbias (+=) [64] fp32 or NULL (sum of dy over batch and pixels).  x: source view (n_chunks = 8 or 16; 32 = phase tensor for
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
-CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, int Cin,
-                              int B, cudaStream_t st) {
+CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dbias,
+                              int Cin, int B, cudaStream_t st) {
   CNP_REQUIRE(x && dy && dw && B > 0, "conv_tc_wgrad: bad arguments");
   CNP_REQUIRE(x->H == dy->H && x->W == dy->W, "conv_tc_wgrad: x and dy must share the accumulator geometry");
   cnp_wg_args a;
@@ -205,7 +239,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   a.x_plane = (long long)Hp * Wp * 8; a.dy_plane = a.x_plane;
   a.x = reinterpret_cast<const __nv_bfloat16*>(x->base) + (long long)x->cb_off * a.x_plane; a.x_bs = x->bstride;
   a.dy = reinterpret_cast<const __nv_bfloat16*>(dy->base) + (long long)dy->cb_off * a.dy_plane; a.dy_bs = dy->bstride;
-  a.dw = dw; a.Cin = Cin; a.B = B;
+  a.dw = dw; a.dbias = dbias; a.Cin = Cin; a.B = B;
   // reduction tile: the zero pad after the last interior pixel (2*Wp+2 pixels) must cover the overshoot
   a.P = (2 * Wp + 2 >= 128) ? 128 : (2 * Wp + 2 >= 64 ? 64 : (2 * Wp + 2 >= 32 ? 32 : 16));
   CNP_REQUIRE(2 * Wp + 2 >= a.P, "conv_tc_wgrad: image too narrow");

@@ -195,9 +195,6 @@ class Engine:
         """contexts: list of (x, y, mask|None) numpy/torch CPU arrays with a leading batch axis.
         NaNs may stay in ``y`` (the kernels derive validity on the fly).  Returns float32 contiguous
         CPU tensors (page-locked when ``pinned``) plus the host-side discretisation."""
-        if isinstance(xt, tuple):
-            raise NotImplementedError("on-grid targets go through ConvNP.predict")
-
         def host(a):
             return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
 
@@ -213,7 +210,15 @@ class Engine:
         xs = [c[0] for c in contexts] + [xt]
         xs = [tuple(host(v) for v in x) if isinstance(x, tuple) else host(x) for x in xs]
         grid = discretise(xs, self.cfg.points_per_unit, self.cfg.margin, self.cfg.grid_multiple)
-        B = int(xs[-1].shape[0])
+        B = int((xs[-1][0] if isinstance(xs[-1], tuple) else xs[-1]).shape[0])
+        if isinstance(xt, tuple):
+            x1t, x2t = (v.reshape(v.shape[0], -1) for v in xs[-1])
+            if not (np.all(x1t == x1t[:1]) and np.all(x2t == x2t[:1])):
+                raise NotImplementedError("on-grid targets must share coordinates across the batch")
+            B = int(np.asarray(contexts[0][1].y if hasattr(contexts[0][1], "y") else contexts[0][1]).shape[0])
+            xt_h = (cpu(x1t[0]), cpu(x2t[0]))
+        else:
+            xt_h = None
         hctx = []
         for (x, y, m), xh in zip(contexts, xs[:-1]):
             if isinstance(x, tuple):
@@ -228,7 +233,7 @@ class Engine:
                 hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h)))
             else:
                 hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))
-        return HostBatch(hctx, cpu(xt), cpu(yt), cpu(aux_t), grid, B)
+        return HostBatch(hctx, xt_h if xt_h is not None else cpu(xt), cpu(yt), cpu(aux_t), grid, B)
 
     def upload(self, hb: "HostBatch") -> DeviceBatch:
         """Asynchronous H2D of a staged batch on the current stream."""
@@ -249,8 +254,14 @@ class Engine:
         for c in hb.contexts:
             x = tuple(up(v) for v in c.x) if c.gridded else up(c.x)
             dctx.append(DeviceContext(c.gridded, x, up(c.y), up(c.mask), c.mono, c.x_batched, c.x_host, c.band_cache))
-        xt = up(hb.xt)
-        return DeviceBatch(dctx, xt, up(hb.yt), up(hb.aux_t), hb.grid, hb.B, int(xt.shape[-1]), nbytes)
+        if isinstance(hb.xt, tuple):
+            xt = tuple(up(v) for v in hb.xt)
+            nt = int(xt[0].shape[-1]) * int(xt[1].shape[-1])
+        else:
+            xt = up(hb.xt)
+            nt = int(xt.shape[-1])
+        yt, aux = up(hb.yt), up(hb.aux_t)
+        return DeviceBatch(dctx, xt, yt, aux, hb.grid, hb.B, nt, nbytes)
 
     def prepare(self, contexts, xt, yt, aux_t, pinned: bool = False) -> DeviceBatch:
         return self.upload(self.stage_host(contexts, xt, yt, aux_t, pinned=pinned))
@@ -553,8 +564,7 @@ class Engine:
         def wgrad_tc(x: CnpBlk, n_chunks, dy: CnpBlk, kind, name, Cin):
             kk = 1 if kind == K.WG_K1 else 25
             self._call("cnp_conv_tc_wgrad", C.byref(x), n_chunks, C.byref(dy), kind, _ptr(grads[name + ".weight"]),
-                       Cin, B, S, work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
-            self._call("cnp_blk_channel_sum", C.byref(dy), 8, B, _ptr(grads[name + ".bias"]), S)
+                       _ptr(grads[name + ".bias"]), Cin, B, S, work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
 
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
                      accumulate=False, phase=None):
@@ -641,8 +651,10 @@ class Engine:
         else:
             z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2)
         Cz = z.shape[1]
-        f = self._buf("f", (B, Cz, Nt))
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
+        if isinstance(batch.xt, tuple):
+            return self._decode_grid(batch, z, s2)
+        f = self._buf("f", (B, Cz, Nt))
         self._call("cnp_setconv_dec_offgrid_fwd", _ptr(z), z.stride(0), _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1,
                    g.start2, g.n2, g.res, s2, _ptr(f), Cz, _stream())
         mean = torch.empty((B, Nt), dtype=torch.float32, device=self.device)
@@ -659,6 +671,30 @@ class Engine:
                    _ptr(batch.yt) if with_loss else None, B, Nt, _ptr(mean), _ptr(var), _ptr(logp), _ptr(count),
                    _stream())
         return dict(mean=mean, var=var, logp=logp, count=count, ctx=dict(enc=enc, z=z, A=A, f=f))
+
+    def _decode_grid(self, batch: DeviceBatch, z: torch.Tensor, s2: float):
+        """On-grid targets (predict): separable truncated SetConv + per-point MLP head -> mean/std [B,P,Q]."""
+        cfg, g, B = self.cfg, batch.grid, batch.B
+        x1t, x2t = batch.xt
+        P, Q, Cz, Ca = int(x1t.shape[-1]), int(x2t.shape[-1]), z.shape[1], cfg.dim_aux_t
+        aux = batch.aux_t
+        if aux is None or aux.shape[-3] != Ca or tuple(aux.shape[-2:]) != (P, Q):
+            raise ValueError(f"on-grid prediction needs Y_t_aux of shape [{Ca},{P},{Q}]")
+        aux = aux.reshape(-1, Ca, P, Q)
+        aux_bs = 0 if aux.shape[0] == 1 else aux.stride(0)
+        wsb = _cabi.lib().cnp_setconv_dec_grid_workspace_bytes(B, Cz, g.n1, P, Q)
+        ws = self._buf("dec_grid_ws", ((wsb + 3) // 4,))
+        f = self._buf("f_grid", (B, Cz, P, Q))
+        self._call("cnp_setconv_dec_grid_fwd", _ptr(z), z.stride(0), _ptr(x1t), _ptr(x2t), B, Cz, P, Q, g.start1, g.n1,
+                   g.start2, g.n2, g.res, s2, _ptr(f), f.stride(0), _ptr(ws), wsb, _stream(),
+                   work=(0.0, 4.0 * (z.numel() + f.numel())))
+        mean = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
+        std = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
+        p = self._mlp_params()
+        self._call("cnp_mlp_head_points_fwd", C.byref(p), _ptr(f), f.stride(0), Cz, _ptr(aux), aux_bs, Ca, B, P * Q,
+                   _ptr(mean), _ptr(std), _stream(), work=(2.0 * B * P * Q * sum(
+                       a * b for a, b in zip(self.module.mlp_dims()[:-1], self.module.mlp_dims()[1:])), 0.0))
+        return dict(mean=mean, std=std, var=None, logp=None, count=None, ctx=None)
 
     def backward(self, batch: DeviceBatch, ctx: dict, dlogp: torch.Tensor) -> Dict[str, torch.Tensor]:
         """dlogp [B] fp32 = d loss / d logp_b.  Returns {param name: grad} (views of one flat buffer)."""

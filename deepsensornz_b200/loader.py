@@ -1,0 +1,247 @@
+"""``TaskLoader`` -- host-side mirror of ``deepsensor.data.loader.TaskLoader`` for the surface nzdownscale uses.
+
+Reference call sites: construction ``TaskLoader(context=[...], target=station_df,
+aux_at_targets=highres_aux_ds)`` train.py:160-166; ``task_loader(date, context_sampling=..., target_sampling=...)``
+train.py:315, validate_ERA.py:79; ``load_dask()`` train.py:205; pickling train.py:174-177; sub-classing with
+``sample_df`` / ``task_generation`` overrides that call ``time_slice_variable`` / ``sample_da`` /
+``sample_offgrid_aux`` train.py:525-637; attribute swaps ``context`` / ``target`` validate_ERA.py:117-127.
+
+Gridded variables may be xarray ``Dataset`` / ``DataArray`` objects (when xarray is importable) or
+``deepsensornz_b200.data.GridVar``; off-grid variables are pandas objects indexed by (time, x1, x2).
+Everything here is host numpy/pandas: the layout it produces is what the kernels consume.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import pandas as pd
+
+from .data import GridVar
+from .task import Task
+
+try:  # pragma: no cover - xarray is not installed in the build container
+    import xarray as xr
+except Exception:  # noqa: BLE001
+    xr = None
+
+
+def _is_xr(v) -> bool:
+    return xr is not None and isinstance(v, (xr.Dataset, xr.DataArray))
+
+
+def _is_grid(v) -> bool:
+    return isinstance(v, GridVar) or _is_xr(v)
+
+
+def _is_df(v) -> bool:
+    return isinstance(v, (pd.DataFrame, pd.Series))
+
+
+class InvalidSamplingStrategyError(ValueError):
+    pass
+
+
+class TaskLoader:
+    def __init__(self, context=None, target=None, aux_at_contexts=None, aux_at_targets=None, links=None,
+                 context_delta_t=0, target_delta_t=0, time_freq: str = "D", dtype="float32", task_loader_ID=None):
+        if task_loader_ID is not None:
+            raise NotImplementedError("loading a TaskLoader from a folder: pickle the loader instead (train.py:174-177)")
+        as_list = lambda v: list(v) if isinstance(v, (list, tuple)) else [v]
+        self.context = as_list(context) if context is not None else []
+        self.target = as_list(target) if target is not None else []
+        self.aux_at_contexts = aux_at_contexts
+        self.aux_at_targets = aux_at_targets
+        self.links = links
+        self.time_freq = time_freq
+        self.dtype = np.dtype(dtype).type
+        bc = lambda v, n: tuple(v) if isinstance(v, (list, tuple)) else tuple([v] * n)
+        self.context_delta_t = bc(context_delta_t, len(self.context))
+        self.target_delta_t = bc(target_delta_t, len(self.target))
+
+    # ---- metadata ------------------------------------------------------------------------------
+    @staticmethod
+    def _var_IDs(v):
+        if isinstance(v, GridVar):
+            return tuple(v.var_IDs)
+        if xr is not None and isinstance(v, xr.Dataset):
+            return tuple(v.data_vars)
+        if xr is not None and isinstance(v, xr.DataArray):
+            return (v.name,)
+        if isinstance(v, pd.DataFrame):
+            return tuple(v.columns)
+        if isinstance(v, pd.Series):
+            return (v.name,)
+        raise TypeError(f"unsupported variable type {type(v)}")
+
+    @property
+    def context_var_IDs(self):
+        return tuple(self._var_IDs(v) for v in self.context)
+
+    @property
+    def target_var_IDs(self):
+        return tuple(self._var_IDs(v) for v in self.target)
+
+    @property
+    def context_dims(self):
+        return tuple(len(ids) for ids in self.context_var_IDs)
+
+    @property
+    def target_dims(self):
+        return tuple(len(ids) for ids in self.target_var_IDs)
+
+    @property
+    def aux_at_target_dims(self) -> int:
+        return 0 if self.aux_at_targets is None else len(self._var_IDs(self.aux_at_targets))
+
+    @property
+    def aux_at_target_var_IDs(self):
+        return None if self.aux_at_targets is None else self._var_IDs(self.aux_at_targets)
+
+    def __str__(self):
+        return (f"TaskLoader({len(self.context)} context sets, {len(self.target)} target sets)\n"
+                f"Context variable IDs: {self.context_var_IDs}\nTarget variable IDs: {self.target_var_IDs}\n"
+                f"Auxiliary-at-target variable IDs: {self.aux_at_target_var_IDs}")
+
+    def load_dask(self) -> None:
+        """Materialise lazy arrays (no-op for numpy/pandas; ``.load()`` for xarray)."""
+        if xr is not None:
+            self.context = [v.load() if _is_xr(v) else v for v in self.context]
+            self.target = [v.load() if _is_xr(v) else v for v in self.target]
+            if _is_xr(self.aux_at_targets):
+                self.aux_at_targets = self.aux_at_targets.load()
+
+    # ---- defaults used by ConvNP (deepsensor.model.defaults) -----------------------------------------
+    @staticmethod
+    def _coords(v, name):
+        if isinstance(v, GridVar):
+            return np.asarray(getattr(v, name), dtype=np.float64)
+        return np.asarray(v.coords[name].values, dtype=np.float64)
+
+    def _grid_res(self, v) -> float:
+        r1 = np.abs(np.diff(self._coords(v, "x1"))).mean()
+        r2 = np.abs(np.diff(self._coords(v, "x2"))).mean()
+        return float((r1 + r2) / 2.0)
+
+    def gen_ppu(self) -> int:
+        """Internal density from the finest gridded variable (upstream ``gen_ppu``)."""
+        res = [self._grid_res(v) for v in self.context + self.target if _is_grid(v)]
+        if not res:
+            raise ValueError("cannot infer internal_density without a gridded variable; pass internal_density=")
+        return int(np.ceil(1.0 / min(res)))
+
+    def gen_encoder_scales(self, ppu: float) -> List[float]:
+        """0.5 x grid spacing for gridded context sets, 0.5/ppu for off-grid ones (upstream ``gen_encoder_scales``;
+        numbers confirmed by validation_precip.ipynb:185)."""
+        return [0.5 * self._grid_res(v) if _is_grid(v) else 0.5 / ppu for v in self.context]
+
+    # ---- slicing / sampling ---------------------------------------------------------------------------
+    def time_slice_variable(self, var, date, delta_t: int = 0):
+        date = pd.Timestamp(date) + pd.Timedelta(delta_t, unit=self.time_freq)
+        if isinstance(var, GridVar):
+            return var.sel_time(date)
+        if _is_xr(var):
+            return var.sel(time=date) if "time" in var.dims else var
+        if _is_df(var):
+            if "time" in var.index.names:
+                return var.xs(date, level="time") if isinstance(var.index, pd.MultiIndex) else var.loc[[date]]
+            return var
+        raise TypeError(f"unsupported variable type {type(var)}")
+
+    def sample_da(self, da, sampling_strat, seed: Optional[int] = None):
+        """Gridded context: 'all' -> ((x1[1,N1], x2[1,N2]), Y [C,N1,N2]); int / float -> random off-grid subset."""
+        if isinstance(da, GridVar):
+            x1, x2, arr = da.x1, da.x2, da.stack()
+        else:
+            if xr is not None and isinstance(da, xr.Dataset):
+                da = da.to_array()
+            elif da.ndim == 2:
+                da = da.expand_dims("variable")
+            x1, x2, arr = da.coords["x1"].values, da.coords["x2"].values, da.data
+        if isinstance(sampling_strat, float):
+            sampling_strat = int(sampling_strat * arr.shape[-1] * arr.shape[-2])
+        if isinstance(sampling_strat, str) and sampling_strat == "all":
+            X_c = (x1[np.newaxis, :].astype(self.dtype), x2[np.newaxis, :].astype(self.dtype))
+            return X_c, np.asarray(arr)
+        if isinstance(sampling_strat, (int, np.integer)):
+            rng = np.random.default_rng(seed)
+            i = rng.integers(0, len(x1), sampling_strat)
+            j = rng.integers(0, len(x2), sampling_strat)
+            X_c = np.stack([x1[i], x2[j]], axis=0).astype(self.dtype)
+            return X_c, np.asarray(arr)[:, i, j]
+        raise InvalidSamplingStrategyError(f"Unknown sampling strategy {sampling_strat}")
+
+    def sample_df(self, df, sampling_strat, seed: Optional[int] = None):
+        """Off-grid variable -> (X [2,N], Y [C,N]) (upstream ``sample_df``)."""
+        df = df.dropna(how="any")
+        if isinstance(df, pd.Series):
+            df = df.to_frame()
+        if isinstance(sampling_strat, float):
+            sampling_strat = int(sampling_strat * df.shape[0])
+        if isinstance(sampling_strat, (int, np.integer)):
+            rng = np.random.default_rng(seed)
+            idx = rng.choice(df.index, sampling_strat, replace=False)
+            sub = df.loc[idx]
+        elif isinstance(sampling_strat, str) and sampling_strat in ("all", "split"):
+            sub = df
+        else:
+            raise InvalidSamplingStrategyError(f"Unknown sampling strategy {sampling_strat}")
+        X = sub.reset_index()[["x1", "x2"]].values.T.astype(self.dtype)
+        return X, sub.values.T
+
+    def sample_offgrid_aux(self, X_t, offgrid_aux):
+        """Nearest-neighbour lookup of the aux variable at targets: [C,N] for off-grid X_t, [C,N1,N2] for a tuple."""
+        if isinstance(X_t, tuple):
+            x1, x2, grid = np.asarray(X_t[0]).reshape(-1), np.asarray(X_t[1]).reshape(-1), True
+        else:
+            x1, x2, grid = X_t[0], X_t[1], False
+        if isinstance(offgrid_aux, GridVar):
+            out = offgrid_aux.sel_nearest(x1, x2, grid)
+        else:  # xarray
+            if grid:
+                sel = offgrid_aux.sel(x1=x1, x2=x2, method="nearest")
+            else:
+                sel = offgrid_aux.sel(x1=xr.DataArray(x1, dims="pt"), x2=xr.DataArray(x2, dims="pt"), method="nearest")
+            if isinstance(sel, xr.Dataset):
+                sel = sel.to_array()
+            out = np.asarray(sel.data)
+            if out.ndim == (2 if grid else 1):
+                out = out[np.newaxis]
+        return out.astype(self.dtype)
+
+    # ---- task generation --------------------------------------------------------------------------------
+    def task_generation(self, date, context_sampling="all", target_sampling=None, split_frac: float = 0.5,
+                        datewise_deterministic: bool = False, seed_override: Optional[int] = None) -> Task:
+        def norm(strat, sets):
+            if strat is None:
+                return None
+            return tuple(strat) if isinstance(strat, (list, tuple)) else tuple([strat] * len(sets))
+
+        context_sampling, target_sampling = norm(context_sampling, self.context), norm(target_sampling, self.target)
+        date = pd.Timestamp(date)
+        seed = seed_override if seed_override is not None else (
+            int(date.strftime("%Y%m%d")) if datewise_deterministic else None)
+        task = {"time": date, "ops": [], "X_c": [], "Y_c": [], "X_t": [], "Y_t": []}
+        for i, (var, dt, strat) in enumerate(zip(self.context, self.context_delta_t, context_sampling)):
+            v = self.time_slice_variable(var, date, dt)
+            s = seed + i if seed is not None else None
+            X, Y = self.sample_df(v, strat, s) if _is_df(v) else self.sample_da(v, strat, s)
+            task["X_c"].append(X)
+            task["Y_c"].append(Y)
+        if target_sampling is not None:
+            for j, (var, dt, strat) in enumerate(zip(self.target, self.target_delta_t, target_sampling)):
+                v = self.time_slice_variable(var, date, dt)
+                s = seed + len(self.context) + j if seed is not None else None
+                X, Y = self.sample_df(v, strat, s) if _is_df(v) else self.sample_da(v, strat, s)
+                task["X_t"].append(X)
+                task["Y_t"].append(Y)
+        if self.aux_at_targets is not None and task["X_t"]:
+            if len(task["X_t"]) > 1:
+                raise ValueError("Cannot add auxiliary variable to target set when there are multiple target variables")
+            task["Y_t_aux"] = self.sample_offgrid_aux(task["X_t"][0], self.time_slice_variable(self.aux_at_targets, date))
+        return Task(task)
+
+    def __call__(self, date, *args, **kwargs) -> Union[Task, List[Task]]:
+        if isinstance(date, (list, tuple, pd.DatetimeIndex, np.ndarray)):
+            return [self.task_generation(d, *args, **kwargs) for d in date]
+        return self.task_generation(date, *args, **kwargs)

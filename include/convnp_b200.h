@@ -106,7 +106,7 @@ int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_c
 int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, const cnp_conv_out* out,
                 int B, cnp_stream_t s);
 int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw /*+= [64][Cin][k][k]*/,
-                      int Cin, int B, cnp_stream_t s);
+                      float* dbias /*+= [64] or NULL*/, int Cin, int B, cnp_stream_t s);
 int cnp_blk_channel_sum(const cnp_blk* v, int n_chunks, int B, float* out /*+=*/, cnp_stream_t s);
 int cnp_conv1x1_in_bf16(const float* x /*fp32 NCHW*/, long long x_bstride, const float* w, const float* bias, int B,
                         int Cin, int Cout, const cnp_blk* out, cnp_stream_t s);
@@ -130,6 +130,13 @@ int cnp_setconv_dec_offgrid_bwd(const float* df, int f_ctotal, const float* xt, 
                                 double start1, int n1, double start2, int n2, double res, float scale2,
                                 float* dz, long long dz_bstride, cnp_stream_t s);
 
+/* on-grid targets (ConvNP.predict onto the 1400x1400 NZ grid, validate_ERA.py:88-92): separable, truncated */
+long long cnp_setconv_dec_grid_workspace_bytes(int B, int C, int n1, int P, int Q);
+int cnp_setconv_dec_grid_fwd(const float* z, long long z_bstride, const float* x1t /*[P]*/, const float* x2t /*[Q]*/,
+                             int B, int C, int P, int Q, double start1, int n1, double start2, int n2, double res,
+                             float scale2, float* f /*[B,C,P,Q]*/, long long f_bstride, void* workspace,
+                             long long workspace_bytes, cnp_stream_t s);
+
 /* ---- (4) aux-at-target MLP + heteroscedastic Gaussian head + normalised NLL -----------------------
  * replaces: neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood -> MultiOutputNormal.logpdf
  * -> nps.loglik (A.6, A.7) reached from ConvNP.loss_fn (train.py:370).  logp is float64. */
@@ -145,6 +152,10 @@ typedef struct cnp_mlp_params {
 int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
                      const float* yt /*or NULL*/, int B, int Nt, float* mean, float* var,
                      double* logp /*[B] += or NULL*/, int* count /*[B] +=*/, cnp_stream_t s);
+/* inference head over npts points per batch element (mean, std = sqrt(var)); aux_bstride = 0 shares aux */
+int cnp_mlp_head_points_fwd(const cnp_mlp_params* p, const float* f, long long f_bstride, int Cf, const float* aux,
+                            long long aux_bstride, int Ca, int B, long long npts, float* mean, float* stdv,
+                            cnp_stream_t s);
 int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
                      const float* yt, int B, int Nt, const float* dlogp /*[B]*/, float* df, cnp_stream_t s);
 

@@ -318,14 +318,18 @@ def test_conv_tc_wgrad(cin, stride, k, h, w):
     F.conv2d(x.double(), wd, None, stride=stride, padding=k // 2).backward(dy.double())
     xb, dyb = _to_blk(x), _to_blk(dy)
     dw = torch.zeros(64, cin, k, k, device="cuda")
+    dbf = torch.zeros(64, device="cuda")
     if stride == 2:
         ph = _Blk(B, 32, ho, wo, x.device)
         _cabi.call("cnp_blk_space_to_depth", C.byref(xb.view()), 8, C.byref(ph.view()), B, _S())
-        _cabi.call("cnp_conv_tc_wgrad", C.byref(ph.view()), 32, C.byref(dyb.view()), _cabi.WG_K5S2, dw.data_ptr(), cin, B, _S())
+        _cabi.call("cnp_conv_tc_wgrad", C.byref(ph.view()), 32, C.byref(dyb.view()), _cabi.WG_K5S2, dw.data_ptr(),
+                   dbf.data_ptr(), cin, B, _S())
     else:
         kind = _cabi.WG_K5S1 if k == 5 else _cabi.WG_K1
-        _cabi.call("cnp_conv_tc_wgrad", C.byref(xb.view()), cin // 8, C.byref(dyb.view()), kind, dw.data_ptr(), cin, B, _S())
+        _cabi.call("cnp_conv_tc_wgrad", C.byref(xb.view()), cin // 8, C.byref(dyb.view()), kind, dw.data_ptr(),
+                   dbf.data_ptr(), cin, B, _S())
     assert rel_err(dw, wd.grad) < 1e-4   # exact bf16 products, fp32 accumulation
+    assert rel_err(dbf, dy.double().sum(dim=(0, 2, 3))) < 1e-5   # bias gradient fused into the wgrad kernel
     db = torch.zeros(64, device="cuda")
     _cabi.call("cnp_blk_channel_sum", C.byref(dyb.view()), 8, B, db.data_ptr(), _S())
     assert rel_err(db, dy.double().sum(dim=(0, 2, 3))) < 1e-5
