@@ -256,11 +256,11 @@ def run_ours(args):
     prof = eng.profile_stop()
     pk = peaks()
     roof = None
-    if "cnp_conv_tc" in prof:
-        d = prof["cnp_conv_tc"]
+    if "cnp_conv_tc2" in prof:
+        d = prof["cnp_conv_tc2"]
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
         tot_ms = sum(v["ms"] for v in prof.values())
-        roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM fwd+dgrad)", "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "conv_tc2_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor", "achieved": ach,
                 "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
                 "peak_source": f"{pk['source']} bf16_tflops_sustained", "share_of_step": d["ms"] / tot_ms,
                 "avg_launch_ms": d["ms"] / d["launches"], "flops_per_launch": d["flops"] / d["launches"]}

@@ -96,6 +96,10 @@ _SIGS = {
     "cnp_conv_tc_packed_bytes": (_ll, [_i, _i]),
     "cnp_conv_tc_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_conv_tc": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
+    "cnp_conv_tc2_debug": (C.c_int, [c_fp, _i]),
+    "cnp_conv_tc2_packed_bytes": (_ll, [_i, _i, _i]),
+    "cnp_conv_tc2_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
+    "cnp_conv_tc2": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
     "cnp_blk_from_nchw_f32": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
     "cnp_blk_to_nchw_f32": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, _ll, c_stream]),
     "cnp_conv1x1_in_bf16": (C.c_int, [c_fp, _ll, c_fp, c_fp, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),

@@ -1,0 +1,667 @@
+// bf16 UNet convolutions on tcgen05, second formulation: WEIGHTS are the M operand, PIXELS the N operand.
+//
+// Replaces the torch Conv2d stack (forward and input-gradient) of upstream neuralprocesses' UNet
+// (reached from ConvNP.loss_fn nzdownscale/downscaler/train.py:370 and
+// train_epoch train.py:388-394).
+//
+// Why this shape.  tools/mma_rate.cu (profiles/r01_mma_rate.txt) measures 48 cycles per M128xN64xK16
+// tcgen05.mma with both operands in shared memory -- the 6 KB of operand reads per MMA exceed the
+// 128 B/clk shared-memory port, capping a pixels-as-M / 64-channels-as-N kernel at 2/3 of the tensor
+// peak -- while N >= 128 runs at the floor (N/2 cycles).  A UNet layer only has 64 output channels, so
+// here the roles are swapped:
+//   D[m, n]  m = 128 TMEM lanes = 2 groups x 64 output channels, n = up to 256 consecutive pixels of a row
+//   A (M operand) = packed weights  [128 x 16 input channels]  (4 KB, K-major, SWIZZLE_NONE)
+//   B (N operand) = the activation window in shared memory, [chunk][pixel][8 ch]: K-major with 16 B pixel
+//                   rows, so a conv tap (dy,dx) is again just a +(dy*pitch+dx)*16 B shift of the descriptor.
+// The two lane groups are
+//   PAIR mode (64 output channels): group 0 = output row r, group 1 = output row r+1.  The window row
+//        r+i feeds tap ky=i of group 0 and tap ky=i-1 of group 1, so A = [W(i,kx) ; W(i-1,kx)] and a 5x5
+//        conv takes 6x5 MMAs per 16 input channels for 2 output rows (5/6 of the MMA slots useful);
+//   WIDE mode (128 output channels, the dgrad of the 128->64 layers): group g = channels 64g..64g+63.
+// One accumulator = one output row (WIDE) or row pair (PAIR) x N pixels = N TMEM columns; a tile keeps
+// floor(512/N) accumulators and streams K in blocks of 16 channels: window blocks (2 chunks x (TH+4) rows)
+// double-buffered, weights through a 3-deep ring of 20 KB stages (5 positions x 4 KB), all by cp.async.bulk.
+// Warps: 0 = window producer, 1 = weight producer, 2 = MMA issuer, 3 = TMEM allocator, 4..15 = epilogue
+// (tcgen05.ld 32 pixels of one channel per thread -> bias/ReLU -> transpose through shared memory ->
+// 16 B blocked stores, optional ReLU-mask / accumulate; or direct fp32 NCHW stores).
+#include "tc_common.cuh"
+
+#define C2_MAX_KB 16
+#define C2_MAX_TYPES 4
+#define C2_MAX_POS 30
+
+struct cnp_c2_plan {
+  int n_kb;
+  int regular;                  // every stage = 5 consecutive pixels of window row <stage index> (5x5 stride-1 kinds)
+  int kb_chunk0[C2_MAX_KB];     // first of the 2 source chunks of this 16-channel K block
+  int kb_wci0[C2_MAX_KB];       // weight input-channel base (packing)
+  int kb_type[C2_MAX_KB];       // position list used by this K block
+  int t_npos[C2_MAX_TYPES];
+  short t_boff[C2_MAX_TYPES][C2_MAX_POS];          // B start, in window pixels (row*pitch + col)
+  signed char t_tap[C2_MAX_TYPES][C2_MAX_POS][4];  // (ky0,kx0) of group 0, (ky1,kx1) of group 1; -1 = zero block
+};
+
+struct cnp_c2_args {
+  const __nv_bfloat16* x; long long x_bs; int x_Hp, x_Wp;
+  const uint8_t* w;
+  int B, H, W;
+  int TW, TH, pitch, N, nacc, rpa, plane_sm, tiles_x, tiles_y;
+  int wide;
+  int out_mode;                  // 0: blocked bf16, 1: NCHW fp32
+  void* out; long long out_bs; int out_c_off; int out_Hp, out_Wp;
+  int sy, ay, sx, ax;
+  const float* bias; int relu;
+  const __nv_bfloat16* mask; long long mask_bs; int mask_cb_off;
+  int accumulate;
+  int dbg_flags;                 // profiling only: 1 = epilogue stops after the TMEM load, 2 = skips the global stores
+  long long* dbg;                // optional [grid][8] cycle counters (cnp_conv_tc2_debug), else NULL
+  cnp_c2_plan plan;
+};
+
+static long long* g_c2_dbg = nullptr;
+static int g_c2_dbg_flags = 0;
+
+namespace {
+
+constexpr int C2_POS_BYTES = 4096;                       // 2 k-chunks x 128 rows x 16 B
+constexpr int C2_STAGE_POS = 5;
+constexpr int C2_STAGE_BYTES = C2_STAGE_POS * C2_POS_BYTES;
+constexpr int C2_WSTAGES = 3;
+constexpr int C2_ABUFS = 2;
+constexpr int C2_EPI_WARPS = 12;
+constexpr int C2_THREADS = 32 * (4 + C2_EPI_WARPS);
+constexpr int C2_STG_WORDS_BF16 = 32 * 17;               // per-warp transpose buffer [32 px][17 words]
+constexpr int C2_STG_WORDS_F32 = 32 * 36;                // fp32 output: [32 ch][36 floats]
+
+// positions [P0, P1) of a regular stage (consecutive window pixels of one row) x NACC accumulators, fully unrolled
+template <int NACC, int P0, int P1>
+__device__ __forceinline__ void issue_row(uint32_t tmem, uint32_t w_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                          uint32_t N, uint32_t acc_step16, uint32_t first) {
+#pragma unroll
+  for (int p = P0; p < P1; ++p) {
+#pragma unroll
+    for (int j = 0; j < NACC; ++j)
+      tc::mma_bf16_ss_lohi(tmem + j * N, w_lo + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + p + j * acc_step16, desc_hi, idesc,
+                           p > 0 ? 1u : first);
+  }
+}
+template <int P0, int P1>
+__device__ __forceinline__ void issue_row_n(int nacc, uint32_t tmem, uint32_t w_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t N, uint32_t acc_step16, uint32_t first) {
+#pragma unroll
+  for (int p = P0; p < P1; ++p)
+    for (int j = 0; j < nacc; ++j)
+      tc::mma_bf16_ss_lohi(tmem + j * N, w_lo + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + p + j * acc_step16, desc_hi, idesc,
+                           p > 0 ? 1u : first);
+}
+
+__global__ void __launch_bounds__(C2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int plane_bytes = a.plane_sm * 16;
+  const int abuf_bytes = 2 * plane_bytes;
+  uint8_t* a_smem = smem;
+  uint8_t* w_smem = smem + C2_ABUFS * abuf_bytes;
+  uint32_t* stg = reinterpret_cast<uint32_t*>(w_smem + C2_WSTAGES * C2_STAGE_BYTES);
+  const int stg_words = a.out_mode == 1 ? C2_STG_WORDS_F32 : C2_STG_WORDS_BF16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C2_EPI_WARPS * stg_words);
+  uint64_t* a_full = bars;             // [2]
+  uint64_t* a_empty = bars + 2;        // [2]
+  uint64_t* w_full = bars + 4;         // [3]
+  uint64_t* w_empty = bars + 7;        // [3]
+  uint64_t* acc_full = bars + 10;      // [1]
+  uint64_t* acc_empty = bars + 11;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C2_ABUFS; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < C2_WSTAGES; ++i) { tc::mbar_init(w_full + i, 1); tc::mbar_init(w_empty + i, 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(acc_empty, C2_EPI_WARPS);
+    tc::mbar_fence_init();
+  }
+  if (warp == 3) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int rows = a.TH + 4;
+  const uint32_t row_bytes = (uint32_t)a.pitch * 16u;
+  const long long plane_g = (long long)a.x_Hp * a.x_Wp * 8;
+
+  if (warp == 0) {
+    // ===================== window producer ======================================================
+    if (tc::elect_one()) {
+      uint32_t a_it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / (a.tiles_x * a.tiles_y), tr = tile % (a.tiles_x * a.tiles_y);
+        const int y0 = (tr / a.tiles_x) * a.TH, x0 = (tr % a.tiles_x) * a.TW;
+        const __nv_bfloat16* xb = a.x + (long long)b * a.x_bs + ((long long)y0 * a.x_Wp + x0) * 8;
+        for (int kb = 0; kb < a.plan.n_kb; ++kb, ++a_it) {
+          const int buf = a_it & 1;
+          tc::mbar_wait(a_empty + buf, ((a_it >> 1) & 1) ^ 1);
+          tc::mbar_expect_tx(a_full + buf, 2u * rows * row_bytes);
+          uint8_t* dst = a_smem + buf * abuf_bytes;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const __nv_bfloat16* src = xb + (long long)(a.plan.kb_chunk0[kb] + c) * plane_g;
+            for (int r = 0; r < rows; ++r)
+              tc::bulk_g2s(dst + c * plane_bytes + r * row_bytes, src + (long long)r * a.x_Wp * 8, row_bytes,
+                           a_full + buf);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== weight producer ======================================================
+    if (tc::elect_one()) {
+      uint32_t w_it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint8_t* wsrc = a.w;
+        for (int kb = 0; kb < a.plan.n_kb; ++kb) {
+          const int npos = a.plan.t_npos[a.plan.kb_type[kb]];
+          for (int s0 = 0; s0 < npos; s0 += C2_STAGE_POS, ++w_it) {
+            const int ws = w_it % C2_WSTAGES;
+            const int np = min(C2_STAGE_POS, npos - s0);
+            tc::mbar_wait(w_empty + ws, ((w_it / C2_WSTAGES) & 1) ^ 1);
+            tc::mbar_expect_tx(w_full + ws, (uint32_t)np * C2_POS_BYTES);
+            tc::bulk_g2s(w_smem + ws * C2_STAGE_BYTES, wsrc, (uint32_t)np * C2_POS_BYTES, w_full + ws);
+            wsrc += (size_t)np * C2_POS_BYTES;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer ===========================================================
+    // One flat loop over (tile, K block, stage).  The barrier waits for stage s+1 are issued BEFORE the last
+    // position of stage s: the tensor pipe queues only a few MMAs, so a wait placed between two stages would
+    // leave it idle for the wait's latency (measured: ~60 cycles per stage, fully exposed).
+    if (tc::elect_one() && (int)blockIdx.x < ntiles) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, a.N, 0, 0);
+      const uint32_t acc_step16 = (uint32_t)(a.rpa * a.pitch);        // accumulator-to-accumulator B shift, 16 B units
+      const uint32_t b_lbo = ((uint32_t)plane_bytes >> 4) << 16;      // LBO field of the B descriptor (chunk plane stride)
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);              // SBO = 128 B, descriptor version 1
+      const uint32_t w_lbo = 128u << 16;                              // LBO 2048 B of the packed weights
+      const uint32_t Ncols = (uint32_t)a.N;
+      const int tiles_per_img = a.tiles_x * a.tiles_y;
+      long long c_acc = 0, c_a = 0, c_w = 0, t0 = 0;
+      const long long t_begin = clock64();
+
+      auto wait_stage = [&](int s0, uint32_t a_it, uint32_t w_it) {
+        if (a.dbg) t0 = clock64();
+        if (s0 == 0) tc::mbar_wait(a_full + (a_it & 1), (a_it >> 1) & 1);
+        if (a.dbg) { const long long t1 = clock64(); c_a += t1 - t0; t0 = t1; }
+        tc::mbar_wait(w_full + w_it % C2_WSTAGES, (w_it / C2_WSTAGES) & 1);
+        if (a.dbg) c_w += clock64() - t0;
+        tc::fence_after_sync();
+      };
+      auto tile_nacc = [&](int tile) {
+        const int y0 = ((tile % tiles_per_img) / a.tiles_x) * a.TH;
+        const int need = (a.H - y0 + a.rpa - 1) / a.rpa;
+        return need < a.nacc ? need : a.nacc;
+      };
+
+      int tile = blockIdx.x, kb = 0, s0 = 0;
+      uint32_t a_it = 0, w_it = 0, t_it = 0;
+      int nacc = tile_nacc(tile);
+      wait_stage(0, 0, 0);
+      for (;;) {
+        const int type = a.plan.kb_type[kb];
+        const int npos = a.plan.t_npos[type];
+        const int np = min(C2_STAGE_POS, npos - s0);
+        const int ws = w_it % C2_WSTAGES, buf = a_it & 1;
+        int n_s0 = s0 + C2_STAGE_POS, n_kb = kb, n_tile = tile;
+        uint32_t n_a_it = a_it;
+        if (n_s0 >= npos) {
+          n_s0 = 0; ++n_kb; ++n_a_it;
+          if (n_kb == a.plan.n_kb) { n_kb = 0; n_tile += gridDim.x; }
+        }
+        const bool kb_end = n_s0 == 0, tile_end = n_tile != tile;
+        const uint32_t w_base = tc::smem_u32(w_smem + ws * C2_STAGE_BYTES);
+        const uint32_t a16 = tc::smem_u32(a_smem + buf * abuf_bytes) >> 4;
+        const uint32_t first = (kb > 0 || s0 > 0) ? 1u : 0u;
+        if (a.plan.regular) {
+          // stage = window row s0/5, positions = 5 consecutive pixels: only 32-bit adds between MMAs
+          const uint32_t w_lo = ((w_base >> 4) & 0x3FFFu) | w_lbo;
+          const uint32_t b_lo = ((a16 + (uint32_t)(s0 / C2_STAGE_POS) * (uint32_t)a.pitch) & 0x3FFFu) | b_lbo;
+          if (nacc == 3) issue_row<3, 0, 4>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
+          else if (nacc == 2) issue_row<2, 0, 4>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
+          else issue_row_n<0, 4>(nacc, tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
+          if (!tile_end) wait_stage(n_s0, n_a_it, w_it + 1);
+          if (nacc == 3) issue_row<3, 4, 5>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
+          else if (nacc == 2) issue_row<2, 4, 5>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
+          else issue_row_n<4, 5>(nacc, tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
+        } else {
+          for (int p = 0; p < np; ++p) {
+            if (p == np - 1 && !tile_end) wait_stage(n_s0, n_a_it, w_it + 1);
+            const uint32_t w_lo = (((w_base + p * C2_POS_BYTES) >> 4) & 0x3FFFu) | w_lbo;
+            const uint32_t b_lo = ((a16 + (uint32_t)a.plan.t_boff[type][s0 + p]) & 0x3FFFu) | b_lbo;
+            const uint32_t accf = (p > 0) ? 1u : first;
+            for (int j = 0; j < nacc; ++j)
+              tc::mma_bf16_ss_lohi(tmem_base + j * Ncols, w_lo, desc_hi, b_lo + j * acc_step16, desc_hi, idesc, accf);
+          }
+        }
+        tc::mma_commit(w_empty + ws);
+        if (kb_end) tc::mma_commit(a_empty + buf);
+        ++w_it;
+        if (tile_end) {
+          tc::mma_commit(acc_full);
+          ++t_it;
+          if (n_tile >= ntiles) break;
+          nacc = tile_nacc(n_tile);
+          if (a.dbg) t0 = clock64();
+          tc::mbar_wait(acc_empty, (t_it & 1) ^ 1);     // the epilogue has drained the accumulators
+          if (a.dbg) c_acc += clock64() - t0;
+          wait_stage(0, n_a_it, w_it);
+        }
+        tile = n_tile; kb = n_kb; s0 = n_s0; a_it = n_a_it;
+      }
+      if (a.dbg) {
+        long long* d = a.dbg + blockIdx.x * 8;
+        d[0] = clock64() - t_begin; d[1] = c_acc; d[2] = c_a; d[3] = c_w; d[4] = t_it;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue ==============================================================
+    const int ew = warp - 4;
+    const int q = warp & 3;           // TMEM lane quadrant this warp may read
+    const int h = ew >> 2;            // this quadrant's (accumulator, column block) items are dealt round-robin to its warps
+    const int m = q * 32 + lane;
+    const int g = m >> 6;
+    const int ch = a.wide ? m : (m & 63);                    // output channel of this thread (TMEM lane)
+    const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (q & 1) * 4);   // first of this warp's 4 output chunks
+    const float bias_v = a.bias ? __ldg(a.bias + ch) : 0.f;
+    uint32_t* my_stg = stg + ew * stg_words;
+    const long long oplane = (long long)a.out_Hp * a.out_Wp;
+    const int ncb = a.N >> 5;
+    uint32_t t_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_it) {
+      const int b = tile / (a.tiles_x * a.tiles_y), tr = tile % (a.tiles_x * a.tiles_y);
+      const int y0 = (tr / a.tiles_x) * a.TH, x0 = (tr % a.tiles_x) * a.TW;
+      tc::mbar_wait(acc_full, t_it & 1);
+      const long long te0 = a.dbg ? clock64() : 0;
+      tc::fence_after_sync();
+      const int n_items = a.nacc * ncb;
+      for (int item = h; item < n_items; item += C2_EPI_WARPS / 4) {
+        const int j = item / ncb, cb = item - j * ncb;
+        const int ty = j * a.rpa + (a.wide ? 0 : g);
+        const int y = y0 + ty;
+        if (ty >= a.TH || y >= a.H) continue;                // warp-uniform
+        const int oy = y * a.sy + a.ay;
+        {
+          const int xs = cb * 32;
+          if (xs >= a.TW || x0 + xs >= a.W) continue;        // warp-uniform
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs), v);
+          tc::tmem_ld_wait();
+          if (a.dbg_flags & 1) { float sacc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sacc += v[i];
+            if (sacc == 1.2345e-30f) a.dbg[0] = 1;
+            continue; }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] += bias_v;
+            if (a.relu) v[i] = v[i] < 0.f ? 0.f : v[i];
+          }
+          const int nvalid = min(min(a.TW - xs, a.W - x0 - xs), 32);   // valid pixels of this block
+          if (a.out_mode == 1) {
+            // fp32 NCHW: stage [channel = lane][32 px] (row stride 36 floats), re-read as 4 channels x 8 groups of
+            // 4 pixels so every warp store writes four full 128 B lines
+            float* stf = reinterpret_cast<float*>(my_stg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(stf + lane * 36 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            __syncwarp();
+            const int px4 = (lane & 7) * 4;
+            float* dst0 = reinterpret_cast<float*>(a.out) + (long long)b * a.out_bs +
+                          ((long long)(a.out_c_off + ch - lane) * a.out_Hp + oy) * a.out_Wp + (x0 + xs + px4);
+            const long long cstride = (long long)a.out_Hp * a.out_Wp;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = k * 4 + (lane >> 3);
+              const float4 val = *reinterpret_cast<const float4*>(stf + c * 36 + px4);
+              float* dst = dst0 + c * cstride;
+              if (px4 + 3 < nvalid && !a.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                *reinterpret_cast<float4*>(dst) = val;
+              } else {
+                const float vv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (px4 + i < nvalid) dst[i] = a.accumulate ? dst[i] + vv[i] : vv[i];
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+          // ---- blocked bf16: transpose [channel = lane][pixel] -> [pixel = lane][32 channels] ----
+          __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(my_stg);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) st16[i * 34 + lane] = __float2bfloat16_rn(v[i]);
+          __syncwarp();
+          uint32_t wv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wv[i] = my_stg[lane * 17 + i];
+          __syncwarp();
+          if (a.dbg_flags & 2) { uint32_t xacc = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xacc ^= wv[i];
+            if (xacc == 0x12345678u) a.dbg[0] = 1;
+            continue; }
+          if (lane < nvalid) {
+            const int ox = (x0 + xs + lane) * a.sx + a.ax;
+            const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
+                                   ((long long)chunk0 * oplane + pix) * 8;
+            if (a.mask) {
+              const __nv_bfloat16* mbase = a.mask + (long long)b * a.mask_bs +
+                                           ((long long)(a.mask_cb_off + chunk0 - a.out_c_off) * oplane + pix) * 8;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 mk = __ldg(reinterpret_cast<const uint4*>(mbase + (long long)c * oplane * 8));
+                const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 mf = __bfloat1622float2(m2[i]);
+                  uint32_t keep = 0;
+                  if (mf.x > 0.f) keep |= 0x0000ffffu;
+                  if (mf.y > 0.f) keep |= 0xffff0000u;
+                  wv[c * 4 + i] &= keep;
+                }
+              }
+            }
+            if (a.accumulate) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 old = *reinterpret_cast<const uint4*>(obase + (long long)c * oplane * 8);
+                const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 of = __bfloat1622float2(o2[i]);
+                  const float2 nf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[c * 4 + i]));
+                  const __nv_bfloat162 r = __floats2bfloat162_rn(of.x + nf.x, of.y + nf.y);
+                  wv[c * 4 + i] = *reinterpret_cast<const uint32_t*>(&r);
+                }
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(obase + (long long)c * oplane * 8) =
+                  make_uint4(wv[c * 4], wv[c * 4 + 1], wv[c * 4 + 2], wv[c * 4 + 3]);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(acc_empty);
+      if (a.dbg && ew == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] += clock64() - te0;
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 3) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: torch fp32 [Cout][Cin][k][k] -> bf16 [K block][position][k8 (2)][m (128)][8]
+//   m = 64*g + n.  PAIR: group g uses tap g of the position, output channel co_off + n.
+//                  WIDE: both groups use tap 0, output channel co_off + 64*g + n.
+//   transposed (dgrad): "output channel" indexes the conv's INPUT channels and k its OUTPUT channels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transposed, int wide, int co_off,
+             __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_c2_plan plan, int total_pos) {
+  const long long total = (long long)total_pos * 2048;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const int c = (int)(e & 7), m = (int)((e >> 3) & 127), k8 = (int)((e >> 10) & 1);
+    int gp = (int)(e >> 11);   // global position index
+    int kb = 0;
+    while (gp >= plan.t_npos[plan.kb_type[kb]]) { gp -= plan.t_npos[plan.kb_type[kb]]; ++kb; }
+    const int type = plan.kb_type[kb];
+    const int g = m >> 6, n = m & 63;
+    const int ky = plan.t_tap[type][gp][wide ? 0 : 2 * g], kx = plan.t_tap[type][gp][wide ? 1 : 2 * g + 1];
+    float v = 0.f;
+    if (ky >= 0) {
+      const int kc = plan.kb_wci0[kb] + k8 * 8 + c;
+      const int nn = co_off + (wide ? m : n);
+      if (!transposed) {
+        if (nn < Cout && kc < Cin) v = w[(((size_t)nn * Cin + kc) * k + ky) * k + kx];
+      } else {
+        if (kc < Cout && nn < Cin) v = w[(((size_t)kc * Cin + nn) * k + ky) * k + kx];
+      }
+    }
+    wpk[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side plan construction
+// ---------------------------------------------------------------------------------------------
+enum { KIND_K5S1 = 0, KIND_K1 = 1, KIND_K5S2 = 2, KIND_K5S1_DGRAD = 3, KIND_K1_DGRAD = 4, KIND_K5S2_DGRAD = 5 };
+
+struct Tap { int roff, coff, wky, wkx; };
+
+// positions of one K-block type from the tap list of group 0 (window offsets relative to the output pixel's
+// padded origin); PAIR adds the row-shifted copies for group 1
+int add_type(cnp_c2_plan* p, int type, const Tap* taps, int ntaps, int pitch, int wide) {
+  int np = 0;
+  for (int r = 0; r < 8; ++r)
+    for (int c = 0; c < 8; ++c) {
+      int t0 = -1, t1 = -1;
+      for (int t = 0; t < ntaps; ++t) {
+        if (taps[t].roff == r && taps[t].coff == c) t0 = t;
+        if (!wide && taps[t].roff + 1 == r && taps[t].coff == c) t1 = t;
+      }
+      if (t0 < 0 && t1 < 0) continue;
+      CNP_REQUIRE(np < C2_MAX_POS, "conv plan: too many positions");
+      p->t_boff[type][np] = (short)(r * pitch + c);
+      p->t_tap[type][np][0] = t0 >= 0 ? (signed char)taps[t0].wky : -1;
+      p->t_tap[type][np][1] = t0 >= 0 ? (signed char)taps[t0].wkx : -1;
+      p->t_tap[type][np][2] = t1 >= 0 ? (signed char)taps[t1].wky : -1;
+      p->t_tap[type][np][3] = t1 >= 0 ? (signed char)taps[t1].wkx : -1;
+      ++np;
+    }
+  p->t_npos[type] = np;
+  return 0;
+}
+
+int build_plan2(int kind, int n_chunks, int pitch, int py, int px, int wide, cnp_c2_plan* p) {
+  memset(p, 0, sizeof(*p));
+  Tap taps[25];
+  auto add_kb = [&](int chunk0, int wci0, int type) {
+    p->kb_chunk0[p->n_kb] = chunk0; p->kb_wci0[p->n_kb] = wci0; p->kb_type[p->n_kb] = type; ++p->n_kb;
+  };
+  if (kind == KIND_K5S1 || kind == KIND_K5S1_DGRAD) {
+    CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv plan: 5x5 needs 8 or 16 source chunks");
+    int nt = 0;
+    for (int ky = 0; ky < 5; ++ky)
+      for (int kx = 0; kx < 5; ++kx)
+        taps[nt++] = Tap{ky, kx, kind == KIND_K5S1 ? ky : 4 - ky, kind == KIND_K5S1 ? kx : 4 - kx};
+    if (int e = add_type(p, 0, taps, nt, pitch, wide)) return e;
+    for (int g = 0; g < n_chunks / 2; ++g) add_kb(2 * g, 16 * g, 0);
+    p->regular = 1;
+  } else if (kind == KIND_K1 || kind == KIND_K1_DGRAD) {
+    CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv plan: 1x1 needs 8 or 16 source chunks");
+    taps[0] = Tap{2, 2, 0, 0};
+    if (int e = add_type(p, 0, taps, 1, pitch, wide)) return e;
+    for (int g = 0; g < n_chunks / 2; ++g) add_kb(2 * g, 16 * g, 0);
+  } else if (kind == KIND_K5S2) {
+    CNP_REQUIRE(n_chunks == 32, "conv plan: stride-2 forward reads the 4x8-chunk phase tensor");
+    for (int ph = 0; ph < 4; ++ph) {
+      const int qy = ph >> 1, qx = ph & 1;
+      int nt = 0;
+      for (int ky = qy; ky < 5; ky += 2)
+        for (int kx = qx; kx < 5; kx += 2)
+          taps[nt++] = Tap{2 + (ky - 2 - qy) / 2, 2 + (kx - 2 - qx) / 2, ky, kx};
+      if (int e = add_type(p, ph, taps, nt, pitch, wide)) return e;
+      for (int g = 0; g < 4; ++g) add_kb(ph * 8 + 2 * g, 16 * g, ph);
+    }
+  } else if (kind == KIND_K5S2_DGRAD) {
+    CNP_REQUIRE(n_chunks == 8, "conv plan: stride-2 dgrad reads the 8-chunk dy tensor");
+    int nt = 0;
+    for (int ky = py; ky < 5; ky += 2)
+      for (int kx = px; kx < 5; kx += 2)
+        taps[nt++] = Tap{2 + (py + 2 - ky) / 2, 2 + (px + 2 - kx) / 2, ky, kx};
+    if (int e = add_type(p, 0, taps, nt, pitch, wide)) return e;
+    for (int g = 0; g < 4; ++g) add_kb(2 * g, 16 * g, 0);
+  } else {
+    CNP_REQUIRE(false, "conv plan: unknown kind %d", kind);
+  }
+  return 0;
+}
+
+int plan_total_pos(const cnp_c2_plan& p) {
+  int t = 0;
+  for (int kb = 0; kb < p.n_kb; ++kb) t += p.t_npos[p.kb_type[kb]];
+  return t;
+}
+
+int g2_num_sms = 0;
+int num_sms2() {
+  if (g2_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g2_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g2_num_sms <= 0) g2_num_sms = 148;
+  }
+  return g2_num_sms;
+}
+
+size_t c2_smem_bytes(int plane_sm, int out_mode) {
+  const size_t stg = (size_t)C2_EPI_WARPS * (out_mode == 1 ? C2_STG_WORDS_F32 : C2_STG_WORDS_BF16) * 4;
+  return (size_t)C2_ABUFS * 2 * plane_sm * 16 + (size_t)C2_WSTAGES * C2_STAGE_BYTES + stg + 16 * 8;
+}
+
+// tile geometry: N (pixels per MMA, multiple of 32, <= 256), nacc = floor(512/N) accumulators of rpa rows.
+// Cost model (cycles per tile), calibrated with cnp_conv_tc2_debug on B200:
+//   MMA   : an M128 x N x K16 MMA takes max(N/2, (4096 + 32 N)/128) cycles -- tensor floor vs the 128 B/clk
+//           shared-memory operand port (tools/mma_rate.cu) -- and a tile issues mma_per_acc per accumulator;
+//   L2    : weights (mma_per_acc x 4 KB) + windows are re-read per tile; ~30 B/clk/SM when all SMs stream;
+//   epilogue (not overlapped with the MMAs): ~18 cycles per accumulator column.
+// Minimise waves x (max(MMA, L2) + epilogue).
+void choose_geometry(cnp_c2_args* a, int mma_per_acc) {
+  const int rpa = a->wide ? 1 : 2;
+  double best = 1e300;
+  for (int N = 32; N <= 256; N += 32) {
+    const int tw_max = N < a->W ? N : a->W;
+    const int tiles_x = cnp_cdiv(a->W, tw_max);
+    const int TW = cnp_cdiv(a->W, tiles_x);              // balanced tile width
+    if (cnp_cdiv(TW, 32) * 32 != N) continue;            // a smaller N serves this width
+    const double cyc = (N / 2.0 > 32.0 + N / 4.0) ? N / 2.0 : 32.0 + N / 4.0;
+    int nacc = 512 / N;
+    const int max_rows = cnp_cdiv(a->H, rpa);
+    if (nacc > max_rows) nacc = max_rows;
+    for (; nacc >= 1; --nacc) {
+      const int TH = nacc * rpa;
+      const int pitch = TW + 4;
+      const int plane_sm = (TH + 4) * pitch + (N > pitch ? N - pitch : 0) + 8;
+      if (c2_smem_bytes(plane_sm, a->out_mode) > 225 * 1024) continue;
+      const int tiles_y = cnp_cdiv(a->H, TH);
+      const long long tiles = (long long)a->B * tiles_x * tiles_y;
+      const long long waves = (tiles + num_sms2() - 1) / num_sms2();
+      const int n_kb = mma_per_acc / (a->plan.t_npos[0] > 0 ? a->plan.t_npos[0] : 1);
+      const double mma_c = (double)mma_per_acc * nacc * cyc;
+      const double l2_c = ((double)mma_per_acc * 4096.0 + (double)n_kb * 2.0 * (TH + 4) * pitch * 16.0) / 30.0;
+      const double cost = (double)waves * ((mma_c > l2_c ? mma_c : l2_c) + 18.0 * nacc * N + 1500.0);
+      if (cost < best) {
+        best = cost;
+        a->N = N; a->nacc = nacc; a->rpa = rpa; a->TW = TW; a->TH = TH; a->pitch = pitch; a->plane_sm = plane_sm;
+        a->tiles_x = tiles_x; a->tiles_y = tiles_y;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+struct cnp_conv_out {
+  int mode;
+  cnp_blk blk;
+  float* f32; long long f32_bstride; int f32_ch_off;
+  int sy, ay, sx, ax;
+  const float* bias;
+  int relu;
+  const cnp_blk* mask;
+  int accumulate;
+};
+
+// Debug aid: when buf != NULL every later cnp_conv_tc2 launch writes, per CTA, 8 int64 counters
+// {MMA-thread cycles, waiting on the epilogue, on windows, on weights, tiles, epilogue cycles, -, -}.
+CNP_API int cnp_conv_tc2_debug(long long* buf, int flags) { g_c2_dbg = buf; g_c2_dbg_flags = flags; return 0; }
+
+CNP_API long long cnp_conv_tc2_packed_bytes(int kind, int n_chunks, int n_out) {
+  cnp_c2_plan p;
+  if (build_plan2(kind, n_chunks, 8, 0, 0, n_out == 128, &p)) return -1;
+  return (long long)plan_total_pos(p) * C2_POS_BYTES;
+}
+
+// Pack torch-layout fp32 weights [Cout][Cin][k][k] for cnp_conv_tc2 (n_out = 64: PAIR, 128: WIDE).
+CNP_API int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px,
+                              int co_off, int n_out, void* wpk, cudaStream_t st) {
+  CNP_REQUIRE(n_out == 64 || n_out == 128, "conv_tc2_pack: n_out must be 64 or 128");
+  cnp_c2_plan p;
+  if (int e = build_plan2(kind, n_chunks, 8, py, px, n_out == 128, &p)) return e;
+  const int transposed = (kind >= KIND_K5S1_DGRAD) ? 1 : 0;
+  const int total_pos = plan_total_pos(p);
+  pack2_kernel<<<128, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, co_off,
+                                    reinterpret_cast<__nv_bfloat16*>(wpk), p, total_pos);
+  CNP_LAUNCH_CHECK("pack2_kernel");
+  return 0;
+}
+
+// Tensor-core convolution producing n_out (64 or 128) output channels at chunks [out.cb_off, +n_out/8).
+// x: blocked source whose chunks [x->cb_off, x->cb_off + n_chunks) are the reduction dimension;
+// (x->H, x->W) is the accumulator grid.
+CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, int n_out,
+                         const cnp_conv_out* o, int B, cudaStream_t st) {
+  CNP_REQUIRE(x && o && wpk && B > 0, "conv_tc2: bad arguments");
+  CNP_REQUIRE(n_out == 64 || n_out == 128, "conv_tc2: n_out must be 64 or 128");
+  cnp_c2_args a;
+  memset(&a, 0, sizeof(a));
+  a.H = x->H; a.W = x->W; a.B = B;
+  a.x_Hp = x->H + 4; a.x_Wp = x->W + 4;
+  a.x = reinterpret_cast<const __nv_bfloat16*>(x->base) + (long long)x->cb_off * a.x_Hp * a.x_Wp * 8;
+  a.x_bs = x->bstride;
+  a.w = reinterpret_cast<const uint8_t*>(wpk);
+  a.wide = n_out == 128;
+  a.out_mode = o->mode;
+  if (int e = build_plan2(kind, n_chunks, 8, py, px, a.wide, &a.plan)) return e;   // position count only
+  choose_geometry(&a, plan_total_pos(a.plan));
+  CNP_REQUIRE(a.N > 0, "conv_tc2: no tile geometry for %d x %d", a.H, a.W);
+  if (int e = build_plan2(kind, n_chunks, a.pitch, py, px, a.wide, &a.plan)) return e;
+  a.out_mode = o->mode;
+  a.sy = o->sy; a.ay = o->ay; a.sx = o->sx; a.ax = o->ax;
+  CNP_REQUIRE(a.sy >= 1 && a.sx >= 1, "conv_tc2: output scale must be >= 1");
+  if (o->mode == 0) {
+    CNP_REQUIRE(o->blk.H == x->H * o->sy && o->blk.W == x->W * o->sx, "conv_tc2: output geometry mismatch");
+    a.out = o->blk.base; a.out_bs = o->blk.bstride; a.out_c_off = o->blk.cb_off;
+    a.out_Hp = o->blk.H + 4; a.out_Wp = o->blk.W + 4;
+    if (o->mask) {
+      CNP_REQUIRE(o->mask->H == o->blk.H && o->mask->W == o->blk.W, "conv_tc2: mask geometry mismatch");
+      a.mask = reinterpret_cast<const __nv_bfloat16*>(o->mask->base);
+      a.mask_bs = o->mask->bstride; a.mask_cb_off = o->mask->cb_off;
+    }
+  } else {
+    CNP_REQUIRE(o->f32 && o->sy == 1 && o->sx == 1 && !o->mask, "conv_tc2: fp32 NCHW output is plain only");
+    a.out = o->f32; a.out_bs = o->f32_bstride; a.out_c_off = o->f32_ch_off;
+    a.out_Hp = x->H; a.out_Wp = x->W;
+  }
+  a.bias = o->bias; a.relu = o->relu; a.accumulate = o->accumulate;
+  a.dbg = g_c2_dbg; a.dbg_flags = g_c2_dbg_flags;
+  const size_t smem = c2_smem_bytes(a.plane_sm, a.out_mode);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cnp_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr = smem;
+  }
+  const int ntiles = B * a.tiles_x * a.tiles_y;
+  const int grid = ntiles < num_sms2() ? ntiles : num_sms2();
+  conv_tc2_kernel<<<grid, C2_THREADS, smem, st>>>(a);
+  CNP_LAUNCH_CHECK("conv_tc2_kernel");
+  return 0;
+}

@@ -49,6 +49,26 @@ namespace {
 constexpr int WG_STAGES = 3;
 constexpr int XPAD = 8;  // extra pixels per X plane in shared memory (max tap offset 4, keeps 128 B alignment)
 
+// K steps [K0, K1) x NACC taps of one stage, fully unrolled (tap j = +j pixels on the X operand)
+template <int NACC, int K0, int K1>
+__device__ __forceinline__ void wg_issue(uint32_t tmem, uint32_t xs16, uint32_t ds16, uint32_t lbo, uint32_t a_hi,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int ks = K0; ks < K1; ++ks) {
+#pragma unroll
+    for (int j = 0; j < NACC; ++j)
+      tc::mma_bf16_ss_lohi(tmem + j * 64, ((xs16 + ks * 16 + j) & 0x3FFFu) | lbo, a_hi, ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi,
+                           idesc, ks > K0 ? 1u : acc0);
+  }
+}
+__device__ __forceinline__ void wg_issue_n(int nacc, int k0, int k1, uint32_t tmem, uint32_t xs16, uint32_t ds16,
+                                           uint32_t lbo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
+  for (int ks = k0; ks < k1; ++ks)
+    for (int j = 0; j < nacc; ++j)
+      tc::mma_bf16_ss_lohi(tmem + j * 64, ((xs16 + ks * 16 + j) & 0x3FFFu) | lbo, a_hi, ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi,
+                           idesc, ks > k0 ? 1u : acc0);
+}
+
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -102,22 +122,37 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       }
     }
   } else if (warp == 1) {
-    if (tc::elect_one()) {
+    if (tc::elect_one() && (int)blockIdx.x < total_tiles) {
+      // MN-major operands: LBO = 128 B between the two 8-pixel K groups, SBO = plane stride between 8-channel groups.
+      // Only the low descriptor word changes between MMAs (+1 per tap pixel, +16 per 16-pixel K step), and the wait
+      // for the next stage is issued before the last K step so its latency overlaps queued MMAs.
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t a_hi = ((uint32_t)x_plane_b >> 4) | (1u << 14);
+      const uint32_t b_hi = ((uint32_t)dy_plane_b >> 4) | (1u << 14);
+      const uint32_t lbo = (128u >> 4) << 16;
+      const int nks = P / 16;
+      const int a0 = ps.a_off[0];
       uint32_t it = 0;
+      tc::mbar_wait(full, 0);
+      tc::fence_after_sync();
       for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
         const int s = it % WG_STAGES;
-        tc::mbar_wait(full + s, (it / WG_STAGES) & 1);
-        tc::fence_after_sync();
-        const uint32_t xs = tc::smem_u32(smem + s * stage_b);
-        const uint32_t ds = xs + x_tile_b;
-        for (int ks = 0; ks < P / 16; ++ks) {
-          const uint64_t bdesc = tc::make_smem_desc(ds + ks * 256, 128, dy_plane_b);
-          for (int j = 0; j < ps.n_acc; ++j) {
-            const uint64_t adesc = tc::make_smem_desc(xs + (ps.a_off[j] + ks * 16) * 16, 128, x_plane_b);
-            tc::mma_bf16_ss(tmem_base + j * 64, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          }
+        const uint32_t xs16 = (tc::smem_u32(smem + s * stage_b) >> 4) + (uint32_t)a0;
+        const uint32_t ds16 = tc::smem_u32(smem + s * stage_b + x_tile_b) >> 4;
+        const bool has_next = t + a.ksplit < total_tiles;
+        const uint32_t acc0 = it > 0 ? 1u : 0u;
+        if (nks == 8 && ps.n_acc == 5) wg_issue<5, 0, 7>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        else if (nks == 8 && ps.n_acc == 3) wg_issue<3, 0, 7>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        else wg_issue_n(ps.n_acc, 0, nks - 1, tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        if (has_next) {
+          const uint32_t n = it + 1;
+          tc::mbar_wait(full + n % WG_STAGES, (n / WG_STAGES) & 1);
+          tc::fence_after_sync();
         }
+        const uint32_t acc1 = (it > 0 || nks > 1) ? 1u : 0u;
+        if (nks == 8 && ps.n_acc == 5) wg_issue<5, 7, 8>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        else if (nks == 8 && ps.n_acc == 3) wg_issue<3, 7, 8>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        else wg_issue_n(ps.n_acc, nks - 1, nks, tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc1);
         tc::mma_commit(empty + s);
       }
       tc::mma_commit(done);

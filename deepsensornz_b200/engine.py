@@ -446,19 +446,21 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # (2) UNet, bf16 tensor-core path
     # ------------------------------------------------------------------------------------------
-    def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0) -> torch.Tensor:
+    def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0,
+                        n_out=64) -> torch.Tensor:
         ent = self._packed.get(key)
         ver = w._version
         if ent is not None and ent[0] == ver and ent[1].device == w.device:
             return ent[1]
-        nbytes = _cabi.lib().cnp_conv_tc_packed_bytes(kind, n_chunks)
+        nbytes = _cabi.lib().cnp_conv_tc2_packed_bytes(kind, n_chunks, n_out)
         buf = ent[1] if ent is not None else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
         Cout, Cin, k, _ = w.shape
-        self._call("cnp_conv_tc_pack", _ptr(w), Cout, Cin, k, kind, n_chunks, py, px, co_off, _ptr(buf), _stream())
+        self._call("cnp_conv_tc2_pack", _ptr(w), Cout, Cin, k, kind, n_chunks, py, px, co_off, n_out, _ptr(buf),
+                   _stream())
         self._packed[key] = (ver, buf)
         return buf
 
-    def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0):
+    def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0, n_out=64):
         K = _cabi
         if kind in (K.KIND_K5S1, K.KIND_K5S1_DGRAD):
             kdim = n_chunks * 8 * 25
@@ -468,8 +470,8 @@ class Engine:
             kdim = 64 * 25
         else:
             kdim = 64 * (3 if py == 0 else 2) * (3 if px == 0 else 2)
-        fl = 2.0 * B * x.H * x.W * 64 * kdim
-        self._call("cnp_conv_tc", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, C.byref(out), B, _stream(),
+        fl = 2.0 * B * x.H * x.W * n_out * kdim
+        self._call("cnp_conv_tc2", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, n_out, C.byref(out), B, _stream(),
                    work=(fl, 0.0))
 
     @staticmethod
@@ -568,13 +570,13 @@ class Engine:
 
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
                      accumulate=False, phase=None):
-            for g in range(n_out_ch // 64):
-                py, px = phase if phase is not None else (0, 0)
-                wpk = self._packed_weights(f"{key}.dg{g}.{py}{px}", w, kind, 8, py, px, 64 * g)
-                mk = mask.view(mask_cb + 8 * g) if mask is not None else None
-                sc = (2, py, 2, px) if phase is not None else (1, 0, 1, 0)
-                o = self._out_blk(dst.view(dst_cb + 8 * g), mask=mk, accumulate=accumulate, scatter=sc)
-                self._conv_tc(dy, 8, wpk, kind, o, B, py, px)
+            # 128 input channels (the skip concatenations): one WIDE launch; 64: one PAIR launch
+            py, px = phase if phase is not None else (0, 0)
+            wpk = self._packed_weights(f"{key}.dg.{py}{px}", w, kind, 8, py, px, 0, n_out_ch)
+            mk = mask.view(mask_cb) if mask is not None else None
+            sc = (2, py, 2, px) if phase is not None else (1, 0, 1, 0)
+            o = self._out_blk(dst.view(dst_cb), mask=mk, accumulate=accumulate, scatter=sc)
+            self._conv_tc(dy, 8, wpk, kind, o, B, py, px, n_out_ch)
 
         # final 1x1
         dz_blk = self._blk("dz_blk", B, 8, n1, n2)

@@ -105,6 +105,15 @@ int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_c
  * CNP_K5S2 reads the 32-chunk space-to-depth tensor; CNP_K5S2_DGRAD produces output phase (py,px). */
 int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, const cnp_conv_out* out,
                 int B, cnp_stream_t s);
+/* Second formulation (weights = M operand, pixels = N operand; runs at the tcgen05 floor, see conv_tc2.cu).
+ * n_out = 64: two output rows share one MMA (PAIR); n_out = 128: 128 output channels per call (WIDE, used for
+ * the input gradient of the 128->64 layers). */
+int cnp_conv_tc2_debug(long long* device_buf /*[148][8] or NULL*/, int flags);   /* per-CTA stall counters, profiling aid */
+long long cnp_conv_tc2_packed_bytes(int kind, int n_chunks, int n_out);
+int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px, int co_off,
+                      int n_out, void* wpk, cnp_stream_t s);
+int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, int n_out,
+                 const cnp_conv_out* out, int B, cnp_stream_t s);
 int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw /*+= [64][Cin][k][k]*/,
                       float* dbias /*+= [64] or NULL*/, int Cin, int B, cnp_stream_t s);
 int cnp_blk_channel_sum(const cnp_blk* v, int n_chunks, int B, float* out /*+=*/, cnp_stream_t s);

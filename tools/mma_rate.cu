@@ -9,7 +9,7 @@
 void cnp_set_error(const char*, ...) {}
 
 template <int N, int NACC, int SAME_A>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long* cycles, int b_mis, int b_lbo, int acc_stride) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
@@ -28,12 +28,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long* cycl
 #pragma unroll
     for (int i = 0; i < 8; ++i) ad[i] = tc::make_smem_desc(a0 + (SAME_A ? 0 : i * 8192), 4096, 128);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) bd[i] = tc::make_smem_desc(b0 + i * 2 * N * 16, N * 16, 128);
+    for (int i = 0; i < 4; ++i) bd[i] = tc::make_smem_desc(b0 + b_mis + (b_lbo ? i * 64 : i * 2 * N * 16), b_lbo ? b_lbo : N * 16, 128);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        tc::mma_bf16_ss(tm + (j % NACC) * N, ad[j % 8], bd[(j / NACC) % 4], idesc, 1u);
+        tc::mma_bf16_ss(tm + (j % NACC) * (acc_stride ? acc_stride : N), ad[j % 8], bd[(j / NACC) % 4], idesc, 1u);
     }
     tc::mma_commit(&bar);
     tc::mbar_wait(&bar, 0);
@@ -46,17 +46,17 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long* cycl
 }
 
 template <int N, int NACC, int SAME_A>
-void run(const char* name, int iters) {
+void run(const char* name, int iters, int b_mis = 0, int b_lbo = 0, int acc_stride = 0) {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
   auto k = rate_kernel<N, NACC, SAME_A>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  k<<<148, 128, 200 * 1024>>>(iters, d);
+  k<<<148, 128, 200 * 1024>>>(iters, d, b_mis, b_lbo, acc_stride);
   cudaDeviceSynchronize();
   cudaEventRecord(e0);
-  k<<<148, 128, 200 * 1024>>>(iters, d);
+  k<<<148, 128, 200 * 1024>>>(iters, d, b_mis, b_lbo, acc_stride);
   cudaEventRecord(e1);
   cudaError_t err = cudaDeviceSynchronize();
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -80,5 +80,16 @@ int main() {
   run<256, 2, 0>("M128 N256 distinct A", iters);
   run<256, 2, 1>("M128 N256 same A", iters);
   run<256, 1, 0>("M128 N256 one accumulator", iters);
+  run<160, 3, 0>("M128 N160 aligned dense", iters);
+  run<160, 3, 0>("M128 N160 B +16B", iters, 16);
+  run<160, 3, 0>("M128 N160 B +48B", iters, 48);
+  run<160, 3, 0>("M128 N160 B +64B", iters, 64);
+  run<160, 3, 0>("M128 N160 LBO 25152", iters, 0, 25152);
+  run<160, 3, 0>("M128 N160 LBO 25152 +16B", iters, 16, 25152);
+  run<160, 3, 0>("M128 N160 LBO 25600 (x1024)", iters, 0, 25600);
+  run<160, 3, 0>("M128 N160 acc stride 128?", iters, 0, 0, 170);
+  run<128, 3, 0>("M128 N128 B +16B", iters, 16);
+  run<256, 2, 0>("M128 N256 B +16B", iters, 16);
+  run<64, 4, 0>("M128 N64 B +16B", iters, 16);
   return 0;
 }
