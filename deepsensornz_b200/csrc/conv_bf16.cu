@@ -356,8 +356,8 @@ __global__ void __launch_bounds__(256)
 conv1x1_in_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, int W,
                   const float* __restrict__ w, const float* __restrict__ bias, int Cout,
                   __nv_bfloat16* __restrict__ out, long long out_bs, int cb_off) {
-  __shared__ float w_s[IC_MAX_CIN][64];
-  __shared__ float b_s[64];
+  __shared__ __align__(16) float w_s[IC_MAX_CIN][64];
+  __shared__ __align__(16) float b_s[64];
   const int b = blockIdx.y;
   for (int e = threadIdx.x; e < Cin * 64; e += 256) {
     int ci = e / 64, co = e % 64;
@@ -370,11 +370,28 @@ conv1x1_in_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, i
     const int y = e / W, xx = e % W;
     float acc[64];
 #pragma unroll
-    for (int co = 0; co < 64; ++co) acc[co] = b_s[co];
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float v = __ldg(x + (size_t)b * x_bs + (size_t)ci * H * W + e);
+    for (int q = 0; q < 16; ++q) {
+      const float4 bq = reinterpret_cast<const float4*>(b_s)[q];
+      acc[4 * q] = bq.x; acc[4 * q + 1] = bq.y; acc[4 * q + 2] = bq.z; acc[4 * q + 3] = bq.w;
+    }
+    for (int c0 = 0; c0 < Cin; c0 += 8) {
+      float xv[8];   // 8 independent loads in flight before the FMAs
 #pragma unroll
-      for (int co = 0; co < 64; ++co) acc[co] = fmaf(v, w_s[ci][co], acc[co]);
+      for (int k = 0; k < 8; ++k)
+        xv[k] = (c0 + k < Cin) ? __ldg(x + (size_t)b * x_bs + (size_t)(c0 + k) * H * W + e) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (c0 + k < Cin) {
+          const float v = xv[k];
+          const float4* wr = reinterpret_cast<const float4*>(w_s[c0 + k]);   // broadcast 16 B reads
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 wq = wr[q];
+            acc[4 * q] = fmaf(v, wq.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, wq.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, wq.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, wq.w, acc[4 * q + 3]);
+          }
+        }
+      }
     }
 #pragma unroll
     for (int chunk = 0; chunk < 8; ++chunk) {
@@ -403,71 +420,91 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
 
 // ---------------------------------------------------------------------------------------------
 // weight/bias gradient of the initial 1x1 conv: dw[co][ci] += sum_px dy[co,px] * x[ci,px]
-//   x fp32 NCHW (encoder output, Cin <= 48), dy blocked bf16 (64 channels).  Memory-bound.
+//   x fp32 NCHW (encoder output, Cin <= 16), dy blocked bf16 (64 channels).
+//   Tile = 256 pixels staged in shared memory (dy as raw bf16 [px][64], x as fp32 [px][16]); warp w reduces
+//   pixels w, w+8, ...; lane = (8 output channels, 4 input channels): 3 LDS.128 per 32 FMA, so the kernel is
+//   FMA / HBM bound instead of LDS bound.  Partial sums meet in shared memory, one atomic per output per CTA.
 // ---------------------------------------------------------------------------------------------
-constexpr int IW_PX = 128;
-constexpr int IW_MAXCI = 48;
+constexpr int IW_PX = 256;
+constexpr int IW_MAXCI = 32;   // input channels incl. the constant-1 slot that carries the bias gradient
 
+template <int NH>   // NH = number of 16-channel halves of x in use
 __global__ void __launch_bounds__(256)
 conv1x1_in_wgrad_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, int W,
                         const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int B,
                         float* __restrict__ dw, float* __restrict__ dbias) {
-  extern __shared__ __align__(16) float sm[];
-  float* dy_s = sm;                      // [IW_PX][68]
-  float* x_s = sm + IW_PX * 68;          // [Cin][IW_PX]
-  const int cg = threadIdx.x & 15, cis = threadIdx.x >> 4;  // 16 groups of 4 co; ci slots cis, cis+16, cis+32
+  extern __shared__ __align__(16) uint8_t iw_smem[];
+  __nv_bfloat16 (*dy_s)[64] = reinterpret_cast<__nv_bfloat16 (*)[64]>(iw_smem);                       // [IW_PX][64], 32 KB
+  float (*x_s)[16 * NH] = reinterpret_cast<float (*)[16 * NH]>(iw_smem + IW_PX * 64 * 2);            // [IW_PX][16 NH]
+  constexpr int NCI = 16 * NH;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co8 = lane >> 2, ci4 = lane & 3;
   const int HW = H * W, Hp = H + 4, Wp = W + 4;
   const int tiles_per_img = (HW + IW_PX - 1) / IW_PX;
-  float acc[3][4], bsum[4];
+  const int one_slot = NCI - 1;                 // x channel holding the constant 1 (Cin < NCI is guaranteed)
+  float acc[NH][8][4];
 #pragma unroll
-  for (int m = 0; m < 3; ++m)
+  for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[m][c] = 0.f;
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-  for (int c = 0; c < 4; ++c) bsum[c] = 0.f;
+      for (int c = 0; c < 4; ++c) acc[hh][a][c] = 0.f;
   for (int t = blockIdx.x; t < B * tiles_per_img; t += gridDim.x) {
     const int b = t / tiles_per_img, e0 = (t % tiles_per_img) * IW_PX;
     __syncthreads();
     for (int e = threadIdx.x; e < IW_PX * 8; e += 256) {
-      const int px = e & (IW_PX - 1), chunk = e >> 7, pe = e0 + px;
-      float v[8];
+      const int px = e & (IW_PX - 1), chunk = e >> 8, pe = e0 + px;
+      uint4 v = make_uint4(0, 0, 0, 0);
       if (pe < HW) {
-        const int yy = pe / W, xx = pe % W;
-        ld8(dy + (size_t)b * dy_bs + (((size_t)(dy_cb + chunk) * Hp + yy + 2) * Wp + xx + 2) * 8, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        const int yy = pe / W, xx = pe - yy * W;
+        v = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)b * dy_bs + (((size_t)(dy_cb + chunk) * Hp + yy + 2) * Wp + xx + 2) * 8));
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dy_s[px * 68 + chunk * 8 + i] = v[i];
+      *reinterpret_cast<uint4*>(&dy_s[px][chunk * 8]) = v;
     }
-    for (int e = threadIdx.x; e < Cin * IW_PX; e += 256) {
-      const int ci = e / IW_PX, px = e % IW_PX, pe = e0 + px;
-      x_s[e] = pe < HW ? __ldg(x + (size_t)b * x_bs + (size_t)ci * HW + pe) : 0.f;
+    for (int e = threadIdx.x; e < NCI * IW_PX; e += 256) {
+      const int ci = e >> 8, px = e & (IW_PX - 1), pe = e0 + px;
+      float v = 0.f;
+      if (pe < HW) v = ci < Cin ? __ldg(x + (size_t)b * x_bs + (size_t)ci * HW + pe) : (ci == one_slot ? 1.f : 0.f);
+      x_s[px][ci] = v;
     }
     __syncthreads();
-    for (int px = 0; px < IW_PX; ++px) {
-      const float4 g = *reinterpret_cast<const float4*>(dy_s + px * 68 + cg * 4);
+#pragma unroll 2
+    for (int px = warp; px < IW_PX; px += 8) {
+      const uint4 g = *reinterpret_cast<const uint4*>(&dy_s[px][co8 * 8]);
+      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g);
+      float gf[8];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        const int ci = cis + 16 * m;
-        const float xv = ci < Cin ? x_s[ci * IW_PX + px] : 0.f;
-        acc[m][0] = fmaf(xv, g.x, acc[m][0]); acc[m][1] = fmaf(xv, g.y, acc[m][1]);
-        acc[m][2] = fmaf(xv, g.z, acc[m][2]); acc[m][3] = fmaf(xv, g.w, acc[m][3]);
+      for (int i = 0; i < 4; ++i) { const float2 f2 = __bfloat1622float2(g2[i]); gf[2 * i] = f2.x; gf[2 * i + 1] = f2.y; }
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        const float4 xv = *reinterpret_cast<const float4*>(&x_s[px][hh * 16 + ci4 * 4]);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          acc[hh][a][0] = fmaf(gf[a], xv.x, acc[hh][a][0]); acc[hh][a][1] = fmaf(gf[a], xv.y, acc[hh][a][1]);
+          acc[hh][a][2] = fmaf(gf[a], xv.z, acc[hh][a][2]); acc[hh][a][3] = fmaf(gf[a], xv.w, acc[hh][a][3]);
+        }
       }
-      if (cis == 0) { bsum[0] += g.x; bsum[1] += g.y; bsum[2] += g.z; bsum[3] += g.w; }
     }
   }
+  // reduce the 8 warps through shared memory ([8][64][16] floats = 32 KB per half, aliasing dy_s), one atomic per output
+  float* red = reinterpret_cast<float*>(iw_smem);
 #pragma unroll
-  for (int m = 0; m < 3; ++m) {
-    const int ci = cis + 16 * m;
-    if (ci < Cin)
+  for (int hh = 0; hh < NH; ++hh) {
+    __syncthreads();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) atomicAdd(dw + (size_t)(cg * 4 + c) * Cin + ci, acc[m][c]);
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[(warp * 64 + co8 * 8 + a) * 16 + ci4 * 4 + c] = acc[hh][a][c];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 1024 + e];
+      const int co = e >> 4, ci = hh * 16 + (e & 15);
+      if (ci < Cin) atomicAdd(dw + (size_t)co * Cin + ci, s);
+      else if (ci == one_slot && dbias) atomicAdd(dbias + co, s);
+    }
   }
-  if (cis == 0 && dbias)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) atomicAdd(dbias + cg * 4 + c, bsum[c]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -479,34 +516,58 @@ __device__ __forceinline__ void up2_src(int Y, int H, int* y0, int* y1, float* l
   int i0 = (int)src;
   *y0 = i0; *y1 = min(i0 + 1, H - 1); *lam = src - (float)i0;
 }
+// forward: one thread per LOW-res pixel (u,v) and chunk: 3x3 source neighbourhood -> the 2x2 output block.
+//   Y = 2u   : 0.25 x[u-1] + 0.75 x[u]   (u-1 clamped: at u = 0 the source coordinate clamps to 0 -> x[0])
+//   Y = 2u+1 : 0.75 x[u]   + 0.25 x[u+1] (u+1 clamped)
+// evaluated exactly like up2_src (lambda = 0.75 / 0.25, or 0 at the clamped border).
 __global__ void __launch_bounds__(256)
 blk_upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, int x_cb, int H, int W,
                           __nv_bfloat16* __restrict__ y, long long y_bs, int y_cb) {
   const int b = blockIdx.z, chunk = blockIdx.y;
-  const int Wp = W + 4, Hp = H + 4, H2 = 2 * H, W2 = 2 * W, W2p = W2 + 4, H2p = H2 + 4;
+  const int Wp = W + 4, Hp = H + 4, W2p = 2 * W + 4, H2p = 2 * H + 4;
   const __nv_bfloat16* xc = x + (size_t)b * x_bs + (size_t)(x_cb + chunk) * Hp * Wp * 8;
   __nv_bfloat16* yc = y + (size_t)b * y_bs + (size_t)(y_cb + chunk) * H2p * W2p * 8;
-  for (int e = blockIdx.x * 256 + threadIdx.x; e < H2 * W2; e += gridDim.x * 256) {
-    const int Y = e / W2, X = e % W2;
-    int y0, y1, x0, x1; float ly, lx;
-    up2_src(Y, H, &y0, &y1, &ly);
-    up2_src(X, W, &x0, &x1, &lx);
-    float a00[8], a01[8], a10[8], a11[8], o[8];
-    ld8(xc + ((size_t)(y0 + 2) * Wp + x0 + 2) * 8, a00);
-    ld8(xc + ((size_t)(y0 + 2) * Wp + x1 + 2) * 8, a01);
-    ld8(xc + ((size_t)(y1 + 2) * Wp + x0 + 2) * 8, a10);
-    ld8(xc + ((size_t)(y1 + 2) * Wp + x1 + 2) * 8, a11);
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
+    const int u = e / W, v = e - u * W;
+    const int um = max(u - 1, 0), up = min(u + 1, H - 1), vm = max(v - 1, 0), vp = min(v + 1, W - 1);
+    float a[3][3][8];
+    const int rr[3] = {um, u, up}, cc[3] = {vm, v, vp};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float r0 = (1.f - lx) * a00[i] + lx * a01[i];
-      const float r1 = (1.f - lx) * a10[i] + lx * a11[i];
-      o[i] = (1.f - ly) * r0 + ly * r1;
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) ld8(xc + ((size_t)(rr[i] + 2) * Wp + cc[j] + 2) * 8, a[i][j]);
+    // lambda of the even output (towards index u from u-1) and of the odd one (towards u+1 from u)
+    const float ly0 = u > 0 ? 0.75f : 0.f, ly1 = 0.25f, lx0 = v > 0 ? 0.75f : 0.f, lx1 = 0.25f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int r0 = dy == 0 ? 0 : 1, r1 = dy == 0 ? 1 : 2;     // source rows (y0, y1) of this output row
+      const float ly = dy == 0 ? ly0 : ly1;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int c0 = dx == 0 ? 0 : 1, c1 = dx == 0 ? 1 : 2;
+        const float lx = dx == 0 ? lx0 : lx1;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t0 = (1.f - lx) * a[r0][c0][i] + lx * a[r0][c1][i];
+          const float t1 = (1.f - lx) * a[r1][c0][i] + lx * a[r1][c1][i];
+          o[i] = (1.f - ly) * t0 + ly * t1;
+        }
+        st8(yc + ((size_t)(2 * u + dy + 2) * W2p + (2 * v + dx) + 2) * 8, o);
+      }
     }
-    st8(yc + ((size_t)(Y + 2) * W2p + X + 2) * 8, o);
   }
 }
 
 // dx[u,v] = sum over the <=4x4 hi-res pixels that reference (u,v); optional ReLU mask by act>0.
+// One thread per low-res pixel and chunk; the 4 tap weights per dimension are (0.25, 0.75, 0.75, 0.25) away from
+// the borders and follow up2_src at them.  Rows are combined horizontally first (4 loads per hi-res row).
+__device__ __forceinline__ float up2_wgt(int Y, int H, int u) {
+  if (Y < 0 || Y >= 2 * H) return 0.f;
+  int y0, y1; float l;
+  up2_src(Y, H, &y0, &y1, &l);
+  return (y0 == u ? (1.f - l) : 0.f) + (y1 == u ? l : 0.f);
+}
 __global__ void __launch_bounds__(256)
 blk_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int H, int W,
                           __nv_bfloat16* __restrict__ dx, long long dx_bs, int dx_cb,
@@ -518,23 +579,23 @@ blk_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs,
   const __nv_bfloat16* ac = act ? act + (size_t)b * act_bs + (size_t)(act_cb + chunk) * Hp * Wp * 8 : nullptr;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
     const int u = e / W, v = e % W;
+    float wx[4], wy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { wx[k] = up2_wgt(2 * v - 1 + k, W, v); wy[k] = up2_wgt(2 * u - 1 + k, H, u); }
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
-    for (int Y = max(2 * u - 1, 0); Y <= min(2 * u + 2, H2 - 1); ++Y) {
-      int y0, y1; float ly;
-      up2_src(Y, H, &y0, &y1, &ly);
-      const float wy = (y0 == u ? (1.f - ly) : 0.f) + (y1 == u ? ly : 0.f);
-      if (wy == 0.f) continue;
-      for (int X = max(2 * v - 1, 0); X <= min(2 * v + 2, W2 - 1); ++X) {
-        int x0, x1; float lx;
-        up2_src(X, W, &x0, &x1, &lx);
-        const float wx = (x0 == v ? (1.f - lx) : 0.f) + (x1 == v ? lx : 0.f);
-        if (wx == 0.f) continue;
-        float g[8];
-        ld8(dyc + ((size_t)(Y + 2) * W2p + X + 2) * 8, g);
+    // the zero pad of dy (2 pixels) makes the out-of-range taps (weight 0) safe to read
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[i] = fmaf(wy * wx, g[i], s[i]);
+    for (int ky = 0; ky < 4; ++ky) {
+      const int Y = 2 * u - 1 + ky;
+      float g[4][8];
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) ld8(dyc + ((size_t)(Y + 2) * W2p + (2 * v - 1 + kx) + 2) * 8, g[kx]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float hsum = wx[0] * g[0][i] + wx[1] * g[1][i] + wx[2] * g[2][i] + wx[3] * g[3][i];
+        s[i] = fmaf(wy[ky], hsum, s[i]);
       }
     }
     const size_t pix = ((size_t)(u + 2) * Wp + v + 2) * 8;
@@ -770,7 +831,7 @@ CNP_API int cnp_blk_to_nchw_f32(const cnp_blk* src, int B, int C, float* dst, lo
 CNP_API int cnp_conv1x1_in_bf16(const float* x, long long x_bstride, const float* w, const float* bias, int B, int Cin,
                                 int Cout, const cnp_blk* out, cudaStream_t st) {
   CNP_REQUIRE(out && Cin >= 1 && Cin <= IC_MAX_CIN && Cout >= 1 && Cout <= 64, "conv1x1_in: need Cin<=%d, Cout<=64", IC_MAX_CIN);
-  dim3 grid(min(cnp_cdiv(out->H * out->W, 256), 256), B);
+  dim3 grid(cnp_cdiv(out->H * out->W, 256), B);
   conv1x1_in_kernel<<<grid, 256, 0, st>>>(x, x_bstride, Cin, out->H, out->W, w, bias, Cout,
                                           reinterpret_cast<__nv_bfloat16*>(out->base), out->bstride, out->cb_off);
   CNP_LAUNCH_CHECK("conv1x1_in_kernel");
@@ -779,7 +840,7 @@ CNP_API int cnp_conv1x1_in_bf16(const float* x, long long x_bstride, const float
 
 CNP_API int cnp_blk_upsample2x_fwd(const cnp_blk* x, int n_chunks, const cnp_blk* y, int B, cudaStream_t st) {
   CNP_REQUIRE(x && y && y->H == 2 * x->H && y->W == 2 * x->W, "blk_upsample2x_fwd: geometry mismatch");
-  dim3 grid(min(cnp_cdiv(4 * x->H * x->W, 256), 128), n_chunks, B);
+  dim3 grid(cnp_cdiv(x->H * x->W, 256), n_chunks, B);
   blk_upsample2x_fwd_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x->base), x->bstride, x->cb_off,
                                                   x->H, x->W, reinterpret_cast<__nv_bfloat16*>(y->base), y->bstride,
                                                   y->cb_off);
@@ -791,7 +852,7 @@ CNP_API int cnp_blk_upsample2x_bwd(const cnp_blk* dy, int n_chunks, const cnp_bl
                                    int B, cudaStream_t st) {
   CNP_REQUIRE(dy && dx && dy->H == 2 * dx->H && dy->W == 2 * dx->W, "blk_upsample2x_bwd: geometry mismatch");
   CNP_REQUIRE(!act || (act->H == dx->H && act->W == dx->W), "blk_upsample2x_bwd: mask geometry mismatch");
-  dim3 grid(min(cnp_cdiv(dx->H * dx->W, 256), 128), n_chunks, B);
+  dim3 grid(cnp_cdiv(dx->H * dx->W, 256), n_chunks, B);
   blk_upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride, dy->cb_off, dx->H, dx->W,
       reinterpret_cast<__nv_bfloat16*>(dx->base), dx->bstride, dx->cb_off,
@@ -814,18 +875,21 @@ CNP_API int cnp_blk_space_to_depth(const cnp_blk* x, int n_chunks, const cnp_blk
 
 CNP_API int cnp_conv1x1_in_wgrad(const float* x, long long x_bstride, int Cin, const cnp_blk* dy, int B, float* dw,
                                  float* dbias, cudaStream_t st) {
-  CNP_REQUIRE(x && dy && dw && B > 0 && Cin >= 1 && Cin <= IW_MAXCI, "conv1x1_in_wgrad: need Cin <= %d", IW_MAXCI);
-  const size_t smem = (size_t)(IW_PX * 68 + Cin * IW_PX) * sizeof(float);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaFuncSetAttribute(conv1x1_in_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
+  CNP_REQUIRE(x && dy && dw && B > 0 && Cin >= 1 && Cin < IW_MAXCI, "conv1x1_in_wgrad: need Cin < %d", IW_MAXCI);
+  const int nh = Cin < 16 ? 1 : 2;
+  const size_t smem = (size_t)IW_PX * 64 * 2 + (size_t)IW_PX * 16 * nh * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv1x1_in_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IW_PX * 64 * 2 + IW_PX * 32 * 4);
+    attr = true;
   }
   const int tiles = B * cnp_cdiv(dy->H * dy->W, IW_PX);
-  const int grid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
-  conv1x1_in_wgrad_kernel<<<grid, 256, smem, st>>>(x, x_bstride, Cin, dy->H, dy->W,
-                                                   reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride,
-                                                   dy->cb_off, B, dw, dbias);
+  const int grid = tiles < 3 * num_sms() ? tiles : 3 * num_sms();
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy->base);
+  if (nh == 1)
+    conv1x1_in_wgrad_kernel<1><<<grid, 256, smem, st>>>(x, x_bstride, Cin, dy->H, dy->W, dyp, dy->bstride, dy->cb_off, B, dw, dbias);
+  else
+    conv1x1_in_wgrad_kernel<2><<<grid, 256, smem, st>>>(x, x_bstride, Cin, dy->H, dy->W, dyp, dy->bstride, dy->cb_off, B, dw, dbias);
   CNP_LAUNCH_CHECK("conv1x1_in_wgrad_kernel");
   return 0;
 }

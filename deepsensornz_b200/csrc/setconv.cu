@@ -360,6 +360,161 @@ enc_grid_pass2_kernel(const float* __restrict__ T, int C, int N1, int n1, int n2
     if (c <= C) ob[(size_t)c * n1 * n2] = acc[c] / den;
 }
 
+
+// =============================================================================================
+// (1d) gridded context set, fused banded path (used when the band tables exist): one block owns FR_I output rows
+//   and up to FR_J output columns (one per thread) and streams the input rows of its band through shared memory:
+//     row p:  Trow[c]   = sum_k y~[c, p, q0[j]+k] w2[k][j]            (horizontal band, <= KB taps)
+//             acc[i][c] += w1[p - p0[i]][i] * Trow[c]                  (the <= FR_I output rows that row p touches)
+//   Same summation order as the two-pass path (bit-identical results) but no intermediate T tensor: the input is
+//   read ~1.3x (row halo between neighbouring blocks) and the output written once.  Rows are staged FR_RS at a time,
+//   double-buffered, so the next rows' loads are in flight while the current ones are consumed.
+// =============================================================================================
+constexpr int FR_I = 8;       // output rows per block
+constexpr int FR_J = 320;     // output columns per block = threads
+constexpr int FR_MAXROWS = 160;  // max input rows in the band of FR_I output rows
+
+// LPT = loads per thread per staged row segment (seg_max <= LPT * FR_J), FR_RS = input rows staged per step,
+// KBT = compile-time bound of the horizontal band (taps kept in registers)
+template <int C, int LPT, int FR_RS, int KBT>
+__global__ void __launch_bounds__(FR_J)
+enc_grid_fused_kernel(const float* __restrict__ y, const float* __restrict__ mask, int N1, int N2, int n1, int n2, int KB,
+                      int tab_bstride_i, int tab_bstride_w, const int* __restrict__ tab_i,
+                      const float* __restrict__ tab_w, float eps, float* __restrict__ out, int ch_off, int c_total,
+                      int seg_max) {
+  extern __shared__ float fr_smem[];
+  float* ys = fr_smem;                                     // [2][FR_RS][C+1][seg_max]
+  float* w1blk = fr_smem + 2 * FR_RS * (C + 1) * seg_max;  // [FR_MAXROWS][FR_I]
+  __shared__ int sh[4];
+  const int tid = threadIdx.x, b = blockIdx.z;
+  const int i0 = blockIdx.y * FR_I, j0 = blockIdx.x * FR_J;
+  const int ni = min(FR_I, n1 - i0), nj = min(FR_J, n2 - j0);
+  const int* t1 = tab_i + (size_t)b * tab_bstride_i;       // p0 (n1) | len1 (n1) | q0 (n2) | len2 (n2)
+  const int* t2 = t1 + 2 * n1;
+  const float* w1 = tab_w + (size_t)b * tab_bstride_w;
+  const float* w2 = w1 + (size_t)KB * n1;
+  if (tid == 0) {
+    int plo = N1, phi = 0, qlo = N2, qhi = 0;
+    for (int i = 0; i < ni; ++i) { const int s = t1[i0 + i], l = t1[n1 + i0 + i]; if (l > 0) { plo = min(plo, s); phi = max(phi, s + l); } }
+    for (int j = 0; j < nj; ++j) { const int s = t2[j0 + j], l = t2[n2 + j0 + j]; if (l > 0) { qlo = min(qlo, s); qhi = max(qhi, s + l); } }
+    sh[0] = plo; sh[1] = max(phi, plo); sh[2] = qlo; sh[3] = max(qhi, qlo);
+  }
+  __syncthreads();
+  const int plo = sh[0], phi = min(sh[1], sh[0] + FR_MAXROWS), qlo = sh[2], nseg = min(sh[3] - sh[2], seg_max);
+  // vertical weights of this block: w1blk[p - plo][i]
+  for (int e = tid; e < (phi - plo) * FR_I; e += FR_J) {
+    const int pp = e / FR_I, i = e - pp * FR_I;
+    float w = 0.f;
+    if (i < ni) {
+      const int s = t1[i0 + i], l = t1[n1 + i0 + i], k = plo + pp - s;
+      if (k >= 0 && k < l) w = w1[(size_t)k * n1 + i0 + i];
+    }
+    w1blk[e] = w;
+  }
+  const bool active = tid < nj;
+  const int j = j0 + tid;
+  const int myq = active ? t2[j] - qlo : 0, mylen = active ? min(t2[n2 + j], KBT) : 0;
+  float w2r[KBT];
+#pragma unroll
+  for (int k = 0; k < KBT; ++k) w2r[k] = (k < mylen) ? __ldg(w2 + (size_t)k * n2 + j) : 0.f;
+  float acc[FR_I][C + 1];
+#pragma unroll
+  for (int i = 0; i < FR_I; ++i)
+#pragma unroll
+    for (int c = 0; c <= C; ++c) acc[i][c] = 0.f;
+  const float* yb = y + (size_t)b * C * N1 * N2;
+  const float* mb = mask ? mask + (size_t)b * N1 * N2 : nullptr;
+  float pre[FR_RS][C + 1][LPT];
+  auto prefetch = [&](int p) {
+#pragma unroll
+    for (int r = 0; r < FR_RS; ++r)
+#pragma unroll
+      for (int l = 0; l < LPT; ++l) {
+        const int q = tid + l * FR_J;
+        const bool ok = (p + r < phi) && (q < nseg);
+        const size_t off = (size_t)(p + r) * N2 + qlo + q;
+        pre[r][0][l] = ok ? (mb ? __ldg(mb + off) : 1.f) : 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) pre[r][1 + c][l] = ok ? __ldg(yb + (size_t)c * N1 * N2 + off) : 0.f;
+      }
+  };
+  prefetch(plo);
+  int buf = 0;
+  for (int p = plo; p < phi; p += FR_RS, buf ^= 1) {
+    float* yd = ys + (size_t)buf * FR_RS * (C + 1) * seg_max;
+#pragma unroll
+    for (int r = 0; r < FR_RS; ++r)
+#pragma unroll
+      for (int l = 0; l < LPT; ++l) {
+        const int q = tid + l * FR_J;
+        if (q < nseg) {
+          float valid = pre[r][0][l];
+          bool nan_any = false;
+#pragma unroll
+          for (int c = 0; c < C; ++c) nan_any |= isnan(pre[r][1 + c][l]);
+          if (nan_any) valid = 0.f;
+          yd[(r * (C + 1)) * seg_max + q] = valid;
+#pragma unroll
+          for (int c = 0; c < C; ++c) yd[(r * (C + 1) + 1 + c) * seg_max + q] = nan_any ? 0.f : pre[r][1 + c][l] * valid;
+        }
+      }
+    __syncthreads();
+    if (p + FR_RS < phi) prefetch(p + FR_RS);
+#pragma unroll
+    for (int r = 0; r < FR_RS; ++r) {
+      if (p + r >= phi) break;
+      float Tr[C + 1];
+#pragma unroll
+      for (int c = 0; c <= C; ++c) Tr[c] = 0.f;
+      const float* yr = yd + (r * (C + 1)) * seg_max + myq;
+#pragma unroll
+      for (int k = 0; k < KBT; ++k) {
+        if (k < mylen) {
+#pragma unroll
+          for (int c = 0; c <= C; ++c) Tr[c] = fmaf(yr[c * seg_max + k], w2r[k], Tr[c]);
+        }
+      }
+      const float* wv = w1blk + (p + r - plo) * FR_I;
+#pragma unroll
+      for (int i = 0; i < FR_I; ++i) {
+        const float w = wv[i];
+        if (w != 0.f) {
+#pragma unroll
+          for (int c = 0; c <= C; ++c) acc[i][c] = fmaf(w, Tr[c], acc[i][c]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < FR_I; ++i) {
+    if (i < ni) {
+      float* ob = out + ((size_t)b * c_total + ch_off) * n1 * n2 + (size_t)(i0 + i) * n2 + j;
+      const float dens = acc[i][0];
+      ob[0] = dens;
+      const float den = dens + eps;
+#pragma unroll
+      for (int c = 1; c <= C; ++c) ob[(size_t)c * n1 * n2] = acc[i][c] / den;
+    }
+  }
+}
+
+template <int C, int LPT, int FR_RS, int KBT>
+int launch_enc_fused(const float* y, const float* mask, int B, int N1, int N2, int n1, int n2, int KB, int tbi, int tbw,
+                     const int* tab_i, const float* tab_w, float eps, float* out, int ch_off, int c_total, int seg_max,
+                     cudaStream_t stream) {
+  const size_t smem = ((size_t)2 * FR_RS * (C + 1) * seg_max + (size_t)FR_MAXROWS * FR_I) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute((enc_grid_fused_kernel<C, LPT, FR_RS, KBT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  dim3 grid(cnp_cdiv(n2, FR_J), cnp_cdiv(n1, FR_I), B);
+  enc_grid_fused_kernel<C, LPT, FR_RS, KBT><<<grid, FR_J, smem, stream>>>(y, mask, N1, N2, n1, n2, KB, tbi, tbw, tab_i, tab_w, eps, out, ch_off,
+                                                         c_total, seg_max);
+  return 0;
+}
+
 // =============================================================================================
 // (3) decoder: grid -> off-grid targets, forward.  One block per (target, batch).
 //     z is NCHW fp32 [B, C, n1, n2] with batch stride z_bstride (elements).
@@ -540,6 +695,42 @@ CNP_API int cnp_setconv_enc_grid_fwd(const float* x1, const float* x2, int x_bat
                                               start1, n1, start2, n2, res, scale2, band, tab_i, tab_w);
     CNP_LAUNCH_CHECK("band_table_kernel");
     const int tbi = x_batched ? 2 * (n1 + n2) : 0, tbw = x_batched ? band * (n1 + n2) : 0;
+    // fused single pass when the staged row segment and the row band fit (input no finer than ~20x the grid)
+    {
+      const int seg_max = ((N2 < 6 * FR_J ? N2 : 6 * FR_J) + 3) & ~3;
+      // one column block sees the whole input row; only worth it when the input is finer than the grid (the
+      // streamed rows are then the dominant traffic); coarse inputs keep the two-pass path
+      const bool seg_ok = (n2 <= FR_J) && (N2 <= 6 * FR_J) && (N1 >= 2 * n1);
+      const bool rows_ok = (double)N1 / n1 * FR_I + band + 10 <= FR_MAXROWS;
+      const int lpt = cnp_cdiv(seg_max, FR_J);
+      // (LPT, rows per step): narrow inputs stage 8 rows per step, wide ones 2; register budget limits C
+      const int rs = lpt == 1 ? 8 : 2;
+      const size_t fsmem = ((size_t)2 * rs * (C + 1) * seg_max + (size_t)FR_MAXROWS * FR_I) * sizeof(float);
+      if (seg_ok && rows_ok && fsmem <= 200 * 1024 && C <= 8) {
+        int rc = -1;
+#define CNP_ENC_FUSED(CC, LL, RR)                                                                                        \
+  rc = band <= 16 ? launch_enc_fused<CC, LL, RR, 16>(y, mask, B, N1, N2, n1, n2, band, tbi, tbw, tab_i, tab_w, eps, out,    \
+                                                     ch_off, c_total, seg_max, stream)                                    \
+                  : launch_enc_fused<CC, LL, RR, 32>(y, mask, B, N1, N2, n1, n2, band, tbi, tbw, tab_i, tab_w, eps, out,    \
+                                                     ch_off, c_total, seg_max, stream)
+        if (lpt == 1) {
+          switch (C) {
+            case 1: CNP_ENC_FUSED(1, 1, 8); break; case 2: CNP_ENC_FUSED(2, 1, 8); break; case 3: CNP_ENC_FUSED(3, 1, 8); break;
+            case 4: CNP_ENC_FUSED(4, 1, 8); break; case 5: CNP_ENC_FUSED(5, 1, 8); break; case 6: CNP_ENC_FUSED(6, 1, 8); break;
+            case 7: CNP_ENC_FUSED(7, 1, 8); break; case 8: CNP_ENC_FUSED(8, 1, 8); break;
+          }
+        } else if (lpt <= 3 && C <= 4) {
+          switch (C) {
+            case 1: CNP_ENC_FUSED(1, 3, 2); break; case 2: CNP_ENC_FUSED(2, 3, 2); break; case 3: CNP_ENC_FUSED(3, 3, 2); break;
+            case 4: CNP_ENC_FUSED(4, 3, 2); break;
+          }
+        } else if (lpt <= 6 && C <= 2) {
+          switch (C) { case 1: CNP_ENC_FUSED(1, 6, 2); break; case 2: CNP_ENC_FUSED(2, 6, 2); break; }
+        }
+#undef CNP_ENC_FUSED
+        if (rc == 0) { CNP_LAUNCH_CHECK("enc_grid_fused_kernel"); return 0; }
+      }
+    }
     static size_t attr = 0;
     if (p1_smem > attr && p1_smem > 48 * 1024) {
       cudaFuncSetAttribute(enc_grid_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem);

@@ -488,7 +488,8 @@ class Engine:
         o._keep = (bias, mask)
         return o
 
-    def _unet_fwd_bf16(self, enc: torch.Tensor, B: int, n1: int, n2: int) -> Tuple[torch.Tensor, dict]:
+    def _unet_fwd_bf16(self, enc: torch.Tensor, B: int, n1: int, n2: int, need_z: bool = True
+                       ) -> Tuple[Optional[torch.Tensor], dict]:
         K = _cabi
         cfg, u = self.cfg, self.module.decoder.unet
         st = cfg.unet_strides
@@ -531,6 +532,8 @@ class Engine:
             wpk = self._packed_weights(f"after{i}", lyr.weight, K.KIND_K5S1, ncb)
             self._conv_tc(inp.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(dst, bias=lyr.bias, relu=True), B)
         A["ups"], A["h_last"] = ups, h_last
+        if not need_z:   # training: the decoder runs on h_last and the final 1x1 moves behind it (dec_blk.cu)
+            return None, A
         z = self._buf("z", (B, 64, n1, n2))
         o = CnpConvOut()
         o.mode = 1
@@ -578,12 +581,15 @@ class Engine:
             o = self._out_blk(dst.view(dst_cb), mask=mk, accumulate=accumulate, scatter=sc)
             self._conv_tc(dy, 8, wpk, kind, o, B, py, px, n_out_ch)
 
-        # final 1x1
-        dz_blk = self._blk("dz_blk", B, 8, n1, n2)
-        self._call("cnp_blk_from_nchw_f32", _ptr(dz), dz.stride(0), B, 64, n1, n2, C.byref(dz_blk.view()), S)
-        wgrad_tc(h_last.view(0), 8, dz_blk.view(0), K.WG_K1, P + "final_linear", 64)
-        d_hl = self._blk("d_h_last", B, 8, n1, n2)
-        dgrad_tc(dz_blk.view(0), u.final_linear.weight, "final", K.KIND_K1_DGRAD, 64, d_hl, 0, h_last, 0)
+        # final 1x1 (already folded into the decoder when dz is the blocked d_h_last)
+        if isinstance(dz, _Blk):
+            d_hl = dz
+        else:
+            dz_blk = self._blk("dz_blk", B, 8, n1, n2)
+            self._call("cnp_blk_from_nchw_f32", _ptr(dz), dz.stride(0), B, 64, n1, n2, C.byref(dz_blk.view()), S)
+            wgrad_tc(h_last.view(0), 8, dz_blk.view(0), K.WG_K1, P + "final_linear", 64)
+            d_hl = self._blk("d_h_last", B, 8, n1, n2)
+            dgrad_tc(dz_blk.view(0), u.final_linear.weight, "final", K.KIND_K1_DGRAD, 64, d_hl, 0, h_last, 0)
         d_cat = [self._blk(f"d_cat{i}", B, cat[i].CB, res[i][0], res[i][1]) for i in range(L)]
         dy_blk, dy_cb = d_hl, 0
         for i in range(0, L):
@@ -648,17 +654,25 @@ class Engine:
         self._require_cuda()
         cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
         enc = self.encode(batch)
+        on_grid = isinstance(batch.xt, tuple)
         if self.precision == "fp32":
             z, A = self._unet_fwd_f32(enc, B, g.n1, g.n2)
         else:
-            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2)
-        Cz = z.shape[1]
+            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=on_grid)
+        Cz = cfg.unet_out_channels
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
-        if isinstance(batch.xt, tuple):
+        if on_grid:
             return self._decode_grid(batch, z, s2)
         f = self._buf("f", (B, Cz, Nt))
-        self._call("cnp_setconv_dec_offgrid_fwd", _ptr(z), z.stride(0), _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1,
-                   g.start2, g.n2, g.res, s2, _ptr(f), Cz, _stream())
+        if z is None:
+            fin = self.module.decoder.unet.final_linear
+            gbuf, swbuf = self._buf("dec_g", (B, Nt, 64)), self._buf("dec_sw", (B, Nt))
+            A["dec_g"], A["dec_sw"] = gbuf, swbuf
+            self._call("cnp_dec_blk_fwd", C.byref(A["h_last"].view(0)), _ptr(batch.xt), B, Nt, g.start1, g.start2, g.res,
+                       s2, _ptr(fin.weight), _ptr(fin.bias), Cz, _ptr(gbuf), _ptr(swbuf), _ptr(f), _stream())
+        else:
+            self._call("cnp_setconv_dec_offgrid_fwd", _ptr(z), z.stride(0), _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1,
+                       g.start2, g.n2, g.res, s2, _ptr(f), Cz, _stream())
         mean = torch.empty((B, Nt), dtype=torch.float32, device=self.device)
         var = torch.empty((B, Nt), dtype=torch.float32, device=self.device)
         logp = count = None
@@ -709,15 +723,27 @@ class Engine:
             grads[n] = flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         f, z = ctx["f"], ctx["z"]
-        Cz = z.shape[1]
+        Cz = cfg.unet_out_channels
         df = self._buf("df", (B, Cz, Nt))
         p = self._mlp_params(grads)
         self._call("cnp_mlp_head_bwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(batch.aux_t), cfg.dim_aux_t, _ptr(batch.yt), B,
                    Nt, _ptr(dlogp), _ptr(df), _stream())
-        dz = self._buf("dz", z.shape)
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
-        self._call("cnp_setconv_dec_offgrid_bwd", _ptr(df), Cz, _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1, g.start2,
-                   g.n2, g.res, s2, _ptr(dz), dz.stride(0), _stream(), work=(0.0, 4.0 * (dz.numel() + df.numel())))
+        if z is None:
+            A = ctx["A"]
+            fin = "decoder.unet.final_linear"
+            dg = self._buf("dec_dg", (B, Nt, 64))
+            self._call("cnp_dec_blk_bwd_params", _ptr(df), _ptr(A["dec_g"]), _ptr(A["dec_sw"]),
+                       _ptr(self.module.decoder.unet.final_linear.weight), B, Nt, Cz, _ptr(dg),
+                       _ptr(grads[fin + ".weight"]), _ptr(grads[fin + ".bias"]), _stream())
+            dz = self._blk("d_h_last", B, 8, g.n1, g.n2)
+            self._call("cnp_dec_blk_bwd_data", _ptr(dg), _ptr(batch.xt), B, Nt, g.start1, g.start2, g.res, s2,
+                       C.byref(A["h_last"].view(0)), C.byref(dz.view(0)), _stream(),
+                       work=(0.0, 2.0 * B * 64 * g.n1 * g.n2))
+        else:
+            dz = self._buf("dz", z.shape)
+            self._call("cnp_setconv_dec_offgrid_bwd", _ptr(df), Cz, _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1, g.start2,
+                       g.n2, g.res, s2, _ptr(dz), dz.stride(0), _stream(), work=(0.0, 4.0 * (dz.numel() + df.numel())))
         if self.precision == "fp32":
             self._unet_bwd_f32(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2)
         else:

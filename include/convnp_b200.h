@@ -139,6 +139,17 @@ int cnp_setconv_dec_offgrid_bwd(const float* df, int f_ctotal, const float* xt, 
                                 double start1, int n1, double start2, int n2, double res, float scale2,
                                 float* dz, long long dz_bstride, cnp_stream_t s);
 
+/* Training path on the blocked bf16 activations (dec_blk.cu): the SetConv decoder is applied to the last hidden
+ * activation h (64 ch) and the final 1x1 convolution (Wf [Cz][64], bf [Cz]) is applied to the Nt target vectors
+ * afterwards -- both are linear, f = Wf g + bf sw with g = SetConv(h), sw = SetConv(1).  g [B,Nt,64], sw [B,Nt]. */
+int cnp_dec_blk_fwd(const cnp_blk* h, const float* xt /*[B,2,Nt]*/, int B, int Nt, double start1, double start2,
+                    double res, float scale2, const float* Wf, const float* bf, int Cz, float* g, float* sw,
+                    float* f /*[B,Cz,Nt]*/, cnp_stream_t s);
+int cnp_dec_blk_bwd_params(const float* df /*[B,Cz,Nt]*/, const float* g, const float* sw, const float* Wf, int B, int Nt,
+                           int Cz, float* dg /*[B,Nt,64]*/, float* dWf /*+=*/, float* dbf /*+= or NULL*/, cnp_stream_t s);
+int cnp_dec_blk_bwd_data(const float* dg, const float* xt, int B, int Nt, double start1, double start2, double res,
+                         float scale2, const cnp_blk* h /*ReLU mask*/, const cnp_blk* dh /*out, dense*/, cnp_stream_t s);
+
 /* on-grid targets (ConvNP.predict onto the 1400x1400 NZ grid, validate_ERA.py:88-92): separable, truncated */
 long long cnp_setconv_dec_grid_workspace_bytes(int B, int C, int n1, int P, int Q);
 int cnp_setconv_dec_grid_fwd(const float* z, long long z_bstride, const float* x1t /*[P]*/, const float* x2t /*[Q]*/,
