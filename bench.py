@@ -172,7 +172,9 @@ def workload_config(n_gpus: int, precision: str, grid=None):
                        "(ERA5-shaped 140x140 + 6-ch aux + 1400x1400 land mask + 160 context / 40 target stations)",
            "global_batch": BATCH * max(n_gpus, 1), "per_gpu_batch": BATCH, "internal_density": PPU,
            "unet_channels": [64, 64, 64, 64], "precision": precision,
-           "parallelism": f"dp{max(n_gpus, 1)}", "l2": "per-step working set (>3 GB) exceeds the 126 MB L2"}
+           "parallelism": f"dp{max(n_gpus, 1)}", "l2": "per-step working set (>3 GB) exceeds the 126 MB L2",
+           "static_context_dedup": "context sets that are bit-identical across the 16 tasks of a batch (topography aux, "
+                                   "land mask) are staged, uploaded and encoded once per step and broadcast"}
     if grid is not None:
         cfg["internal_grid"] = [grid.n1, grid.n2]
     return cfg
@@ -203,6 +205,7 @@ def run_ours(args):
     host = [model.stage_task(t, pinned=True) for t in tasks]
     dev = [eng.upload(h) for h in host]
     h2d_bytes = dev[0].h2d_bytes
+    static_shared = [not c.y_batched for c in host[0].contexts]
     torch.cuda.synchronize()
 
     def step(batch):
@@ -241,10 +244,17 @@ def run_ours(args):
     clocks = clk.summary()
     value = world * BATCH * args.steps / (ms * 1e-3)
     # ---- end to end through the public API with host buffers ----
+    # every step: pinned-host -> device copy of that step's batch (on a copy stream, overlapping the previous step,
+    # as train_epoch does), forward, backward, optimiser step and the D2H read of the loss
     last = {}
+    copy_stream = torch.cuda.Stream()
+    pending = {"b": eng.upload(host[0], stream=copy_stream)}
 
     def e2e_step(i):
-        last["loss"] = float(step(host[i % 2]).detach().cpu())  # D2H of the loss every step
+        cur = pending["b"]
+        loss = step(cur)
+        pending["b"] = eng.upload(host[(i + 1) % 2], stream=copy_stream)   # next step's inputs
+        last["loss"] = float(loss.detach().cpu())  # D2H of the loss every step
 
     e2e_step(0)
     ms_e2e = timed(e2e_step, args.steps)

@@ -46,6 +46,8 @@ class DeviceContext:
     x_batched: bool = False
     x_host: Optional[Tuple[np.ndarray, np.ndarray]] = None   # gridded: host copy of the coordinates
     band_cache: dict = field(default_factory=dict)           # (grid, scale) -> band hint, shared with uploads
+    y_batched: bool = True    # False: every task of the batch carries the same field (static topography / land mask):
+    #                           one slice is staged, uploaded and encoded, the encoder output is broadcast
 
 
 @dataclass
@@ -59,6 +61,7 @@ class DeviceBatch:
     B: int
     Nt: int
     h2d_bytes: int = 0
+    ready: Optional[torch.cuda.Event] = None   # set when the upload ran on a side stream (Engine.upload(stream=...))
 
 
 @dataclass
@@ -230,13 +233,29 @@ class Engine:
                 mono = (_mono_rows(x1h), _mono_rows(x2h))
                 if shared:
                     x1h, x2h = x1h[:1], x2h[:1]
-                hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h)))
+                # static fields (topography aux, land mask) are identical in every task of a batch: keep one slice
+                yh = host(y)
+                mh = None if m is None else host(m)
+                y_shared = shared and yh.shape[0] > 1 and all(
+                    np.array_equal(yh[0], yh[i], equal_nan=True) for i in range(1, yh.shape[0])) and (
+                    mh is None or all(np.array_equal(mh[0], mh[i]) for i in range(1, mh.shape[0])))
+                if y_shared:
+                    y, m = yh[:1], (None if mh is None else mh[:1])
+                hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h),
+                                          y_batched=not y_shared))
             else:
                 hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))
         return HostBatch(hctx, xt_h if xt_h is not None else cpu(xt), cpu(yt), cpu(aux_t), grid, B)
 
-    def upload(self, hb: "HostBatch") -> DeviceBatch:
-        """Asynchronous H2D of a staged batch on the current stream."""
+    def upload(self, hb: "HostBatch", stream: Optional[torch.cuda.Stream] = None) -> DeviceBatch:
+        """Asynchronous H2D of a staged batch on the current stream, or on ``stream`` (a copy stream: the batch
+        then carries a ``ready`` event that ``forward`` waits on, so the copy of step i+1 overlaps step i)."""
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                db = self.upload(hb)
+                db.ready = torch.cuda.Event()
+                db.ready.record(stream)
+            return db
         self._require_cuda()
         dev = self.device
         nbytes = 0
@@ -253,7 +272,8 @@ class Engine:
         dctx = []
         for c in hb.contexts:
             x = tuple(up(v) for v in c.x) if c.gridded else up(c.x)
-            dctx.append(DeviceContext(c.gridded, x, up(c.y), up(c.mask), c.mono, c.x_batched, c.x_host, c.band_cache))
+            dctx.append(DeviceContext(c.gridded, x, up(c.y), up(c.mask), c.mono, c.x_batched, c.x_host, c.band_cache,
+                                      c.y_batched))
         if isinstance(hb.xt, tuple):
             xt = tuple(up(v) for v in hb.xt)
             nt = int(xt[0].shape[-1]) * int(xt[1].shape[-1])
@@ -262,6 +282,16 @@ class Engine:
             nt = int(xt.shape[-1])
         yt, aux = up(hb.yt), up(hb.aux_t)
         return DeviceBatch(dctx, xt, yt, aux, hb.grid, hb.B, nt, nbytes)
+
+    @staticmethod
+    def _batch_tensors(batch: DeviceBatch):
+        for c in batch.contexts:
+            for t in (c.x if isinstance(c.x, tuple) else (c.x,)) + (c.y, c.mask):
+                if t is not None:
+                    yield t
+        for t in (batch.xt if isinstance(batch.xt, tuple) else (batch.xt,)) + (batch.yt, batch.aux_t):
+            if t is not None:
+                yield t
 
     def prepare(self, contexts, xt, yt, aux_t, pinned: bool = False) -> DeviceBatch:
         return self.upload(self.stage_host(contexts, xt, yt, aux_t, pinned=pinned))
@@ -280,17 +310,20 @@ class Engine:
                 raise ValueError(f"context set {k}: expected {Ck} channels, got {c.y.shape[1]}")
             if c.gridded:
                 x1, x2 = c.x
-                by = 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) + B * (Ck + 1) * g.n1 * g.n2)
+                Be = B if c.y_batched else 1     # a field shared by the whole batch is encoded once ...
+                by = 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) + Be * (Ck + 1) * g.n1 * g.n2)
                 N1, N2 = int(x1.shape[-1]), int(x2.shape[-1])
                 band = self._band_hint(c, g, s2)
                 ws, ws_bytes = None, 0
                 if band:
-                    ws_bytes = _cabi.lib().cnp_setconv_enc_grid_workspace_bytes(B, Ck, N1, g.n1, g.n2, band)
+                    ws_bytes = _cabi.lib().cnp_setconv_enc_grid_workspace_bytes(Be, Ck, N1, g.n1, g.n2, band)
                     ws = self._buf("enc_ws", ((ws_bytes + 3) // 4,))
                 self._call("cnp_setconv_enc_grid_fwd", _ptr(x1), _ptr(x2), int(c.x_batched), _ptr(c.y), _ptr(c.mask),
-                           B, Ck, N1, N2, c.mono[0], c.mono[1],
+                           Be, Ck, N1, N2, c.mono[0], c.mono[1],
                            g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
                            band, _ptr(ws), ws_bytes, _stream(), work=(0.0, by))
+                if Be < B:                        # ... and its channels broadcast to the other tasks (plain D2D copy)
+                    enc[1:, ch:ch + Ck + 1].copy_(enc[:1, ch:ch + Ck + 1].expand(B - 1, -1, -1, -1))
             else:
                 by = 4.0 * (c.x.numel() + c.y.numel() + B * (Ck + 1) * g.n1 * g.n2)
                 self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
@@ -653,6 +686,12 @@ class Engine:
         """Returns dict(mean [B,Nt], var [B,Nt], logp [B] f64, count [B] i32, ctx)."""
         self._require_cuda()
         cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
+        if batch.ready is not None:   # uploaded on a copy stream: order after the copy, keep the allocator informed
+            cur = torch.cuda.current_stream()
+            cur.wait_event(batch.ready)
+            for t in self._batch_tensors(batch):
+                t.record_stream(cur)
+            batch.ready = None
         enc = self.encode(batch)
         on_grid = isinstance(batch.xt, tuple)
         if self.precision == "fp32":
