@@ -112,6 +112,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   uint64_t* acc_full = bars + 10;      // [1]
   uint64_t* acc_empty = bars + 11;     // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  __shared__ uint32_t pos_tbl[C2_MAX_TYPES][C2_MAX_POS + 2];   // B offsets (16 B units) of the generic plans
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = a.B * a.tiles_x * a.tiles_y;
@@ -124,6 +125,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     tc::mbar_fence_init();
   }
   if (warp == 3) tc::tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + C2_MAX_TYPES * C2_MAX_POS) {
+    const int e = threadIdx.x - 128;
+    pos_tbl[e / C2_MAX_POS][e % C2_MAX_POS] = (uint32_t)a.plan.t_boff[e / C2_MAX_POS][e % C2_MAX_POS];
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -236,13 +241,29 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
           else if (nacc == 2) issue_row<2, 4, 5>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
           else issue_row_n<4, 5>(nacc, tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
         } else {
-          for (int p = 0; p < np; ++p) {
-            if (p == np - 1 && !tile_end) wait_stage(n_s0, n_a_it, w_it + 1);
-            const uint32_t w_lo = (((w_base + p * C2_POS_BYTES) >> 4) & 0x3FFFu) | w_lbo;
-            const uint32_t b_lo = ((a16 + (uint32_t)a.plan.t_boff[type][s0 + p]) & 0x3FFFu) | b_lbo;
-            const uint32_t accf = (p > 0) ? 1u : first;
-            for (int j = 0; j < nacc; ++j)
-              tc::mma_bf16_ss_lohi(tmem_base + j * Ncols, w_lo, desc_hi, b_lo + j * acc_step16, desc_hi, idesc, accf);
+          // generic plans (stride-2, 1x1): offsets of the stage's <= 5 positions come from shared memory, loaded
+          // together up front so the MMAs are separated only by 32-bit adds
+          uint32_t boff[C2_STAGE_POS];
+#pragma unroll
+          for (int p = 0; p < C2_STAGE_POS; ++p) boff[p] = pos_tbl[type][min(s0 + p, C2_MAX_POS - 1)];
+          const uint32_t w_lo0 = ((w_base >> 4) & 0x3FFFu) | w_lbo;
+#pragma unroll
+          for (int p = 0; p < C2_STAGE_POS; ++p) {
+            if (p < np) {
+              if (p == np - 1 && !tile_end) wait_stage(n_s0, n_a_it, w_it + 1);
+              const uint32_t b_lo = ((a16 + boff[p]) & 0x3FFFu) | b_lbo;
+              const uint32_t accf = (p > 0) ? 1u : first;
+              if (nacc == 3) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  tc::mma_bf16_ss_lohi(tmem_base + j * Ncols, w_lo0 + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + j * acc_step16,
+                                       desc_hi, idesc, accf);
+              } else {
+                for (int j = 0; j < nacc; ++j)
+                  tc::mma_bf16_ss_lohi(tmem_base + j * Ncols, w_lo0 + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + j * acc_step16,
+                                       desc_hi, idesc, accf);
+              }
+            }
           }
         }
         tc::mma_commit(w_empty + ws);

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -120,6 +121,10 @@ class Engine:
             raise NotImplementedError("bf16 tensor-core path is specialised for unet_channels=(64,)*L")
         self._ws: Dict[tuple, object] = {}
         self._packed: Dict[str, Tuple[int, torch.Tensor]] = {}
+        self._pack_reqs: Dict[str, tuple] = {}     # every packing seen so far -> re-issued up front on a side stream
+        self._pack_stream = None
+        self._pack_event = None
+        self._side_streams: List[torch.cuda.Stream] = []
         self.allreduce_group = None   # set by dist.enable_data_parallel
         self.world_size = 1
         self.launches = 0
@@ -187,6 +192,7 @@ class Engine:
     def release_workspaces(self):
         self._ws.clear()
         self._packed.clear()
+        self._pack_reqs.clear()
 
     def _scale2(self, log_scale: torch.Tensor) -> float:
         return float(np.float32(math.exp(2.0 * float(log_scale))))
@@ -479,8 +485,35 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # (2) UNet, bf16 tensor-core path
     # ------------------------------------------------------------------------------------------
+    def _prepack_all(self):
+        """Re-pack every weight whose version changed (optimiser step) on a side stream at the start of the step, so
+        the ~25 small packing launches overlap the encoder instead of sitting between the convolutions."""
+        if os.environ.get("CNP_NO_PREPACK"):
+            return
+        stale = [(k, r) for k, r in self._pack_reqs.items()
+                 if self._packed.get(k) is not None and self._packed[k][0] != r[0]._version]
+        if not stale:
+            return
+        if self._pack_stream is None:
+            self._pack_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._pack_stream.wait_stream(main)
+        with torch.cuda.stream(self._pack_stream):
+            for k, (w, kind, n_chunks, py, px, co_off, n_out) in stale:
+                buf = self._packed[k][1]
+                Cout, Cin, kk, _ = w.shape
+                self._call("cnp_conv_tc2_pack", _ptr(w), Cout, Cin, kk, kind, n_chunks, py, px, co_off, n_out, _ptr(buf),
+                           _stream())
+                self._packed[k] = (w._version, buf)
+            self._pack_event = torch.cuda.Event()
+            self._pack_event.record(self._pack_stream)
+
     def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0,
                         n_out=64) -> torch.Tensor:
+        self._pack_reqs[key] = (w, kind, n_chunks, py, px, co_off, n_out)
+        if self._pack_event is not None:          # first consumer of the step: order after the side-stream packing
+            torch.cuda.current_stream().wait_event(self._pack_event)
+            self._pack_event = None
         ent = self._packed.get(key)
         ver = w._version
         if ent is not None and ent[0] == ver and ent[1].device == w.device:
@@ -649,11 +682,26 @@ class Engine:
             else:
                 wgrad_tc(x_src.view(0), 8, d_cat[i].view(0), K.WG_K5S1, name, 64)
             if i > 0:
-                if st[i] == 2:
+                if st[i] == 2 and os.environ.get("CNP_NO_MULTISTREAM"):
                     for py in (0, 1):
                         for px in (0, 1):
                             dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S2_DGRAD, 64, d_cat[i - 1], 0,
                                      cat[i - 1], 0, accumulate=True, phase=(py, px))
+                elif st[i] == 2:
+                    # the four output phases write disjoint pixels: run them on four streams so the small launches
+                    # share the SMs instead of queueing behind each other
+                    if len(self._side_streams) < 4:
+                        self._side_streams = [torch.cuda.Stream() for _ in range(4)]
+                    main = torch.cuda.current_stream()
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    for si, (py, px) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                        ss = self._side_streams[si]
+                        ss.wait_event(fork)
+                        with torch.cuda.stream(ss):
+                            dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S2_DGRAD, 64, d_cat[i - 1], 0,
+                                     cat[i - 1], 0, accumulate=True, phase=(py, px))
+                        main.wait_stream(ss)
                 else:
                     dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S1_DGRAD, 64, d_cat[i - 1], 0,
                              cat[i - 1], 0, accumulate=True)
@@ -686,6 +734,8 @@ class Engine:
         """Returns dict(mean [B,Nt], var [B,Nt], logp [B] f64, count [B] i32, ctx)."""
         self._require_cuda()
         cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
+        if self.precision == "bf16":
+            self._prepack_all()
         if batch.ready is not None:   # uploaded on a copy stream: order after the copy, keep the allocator informed
             cur = torch.cuda.current_stream()
             cur.wait_event(batch.ready)
