@@ -1,0 +1,113 @@
+"""-m gpu: the inference path (on-grid targets, ``ConvNP.__call__`` / ``ConvNP.predict`` as nzdownscale's
+validate_ERA.py:88-92 drives it) against the oracle, and the blocked-decoder kernels (dec_blk.cu) against the
+materialised ``final 1x1 conv -> SetConv`` path they replace."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from deepsensornz_b200 import _cabi, Task
+from deepsensornz_b200.engine import _Blk
+from deepsensornz_b200.synthetic import make_static, make_task
+from oracle import convnp_oracle as O
+from tests.util import cpu_params, oracle_inputs, rel_err, small_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.fixture(scope="module")
+def static():
+    return make_static(seed=7, n_hi=200, with_aux_hi=True)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_on_grid_forward_matches_oracle(static, precision, tol):
+    """mean / std on a gridded target (the decoder-bound path of configs[2]) vs the dense oracle einsum."""
+    task = make_task(static, 4242, grid_targets=True)
+    m = small_model(precision)
+    pred = m(task)
+    ctx, xt, _, aux = oracle_inputs(task)
+    mean_o, var_o = O.forward(cpu_params(m), ctx, xt, aux, m.config.points_per_unit)
+    assert pred["mean"].shape == mean_o.shape
+    assert rel_err(pred["mean"], mean_o) < tol
+    assert rel_err(pred["std"], var_o.sqrt()) < tol
+
+
+def test_predict_matches_forward_and_handles_many_tasks(static):
+    """``predict(tasks, X_t=(x1, x2))`` = per-task forward on the target grid, aux-at-targets uploaded once."""
+    tasks = [make_task(static, 900 + i, all_context=True) for i in range(3)]
+    m = small_model("fp32")
+    x1 = np.linspace(0.05, 0.95, 57).astype(np.float32)
+    x2 = np.linspace(0.10, 0.90, 43).astype(np.float32)
+    aux = np.random.default_rng(3).uniform(-1, 1, (5, 57, 43)).astype(np.float32)
+    pred = m.predict(tasks, X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
+    key = list(pred.keys())[0]
+    mean, std = np.asarray(pred[key]["mean"]), np.asarray(pred[key]["std"])
+    assert mean.shape == (3, 57, 43) and std.shape == (3, 57, 43)
+    assert np.all(std > 0) and np.all(np.isfinite(mean))
+    # oracle on the second task
+    t = Task({k: v for k, v in tasks[1].items()})
+    t["X_t"] = [(x1[None], x2[None])]
+    t["Y_t"] = []
+    t["Y_t_aux"] = aux
+    ctx, xt, _, aux_t = oracle_inputs(t)
+    mean_o, var_o = O.forward(cpu_params(m), ctx, xt, aux_t, m.config.points_per_unit)
+    assert rel_err(mean[1], mean_o[0, 0]) < 1e-5
+    assert rel_err(std[1], var_o[0, 0].sqrt()) < 1e-5
+    # .where(mask) as validate_ERA.py:94-96 uses it
+    mask = np.zeros((57, 43), dtype=bool)
+    mask[:10] = True
+    masked = np.asarray(pred[key]["mean"].where(mask))
+    assert np.isnan(masked[:, 10:]).all() and np.isfinite(masked[:, :10]).all()
+
+
+def test_dec_blk_kernels_match_materialised_path():
+    """f, dWf, dbf and d_h from (SetConv on h, then the 1x1) == torch autograd of (1x1 conv, then dense SetConv)."""
+    torch.manual_seed(11)
+    B, H, W, Nt, Cz = 2, 40, 56, 9, 64
+    start1, start2, res = -0.1, -0.05, 0.02
+    scale2 = float(np.float32(res * res))
+    h = torch.relu(torch.randn(B, 64, H, W, device="cuda")).bfloat16().float()
+    Wf = (torch.randn(Cz, 64, device="cuda") * 0.1).requires_grad_(True)
+    bf = torch.randn(Cz, device="cuda").requires_grad_(True)
+    xt = torch.stack([torch.rand(B, Nt, device="cuda") * 0.7, torch.rand(B, Nt, device="cuda") * 1.0], dim=1).contiguous()
+    df = torch.randn(B, Cz, Nt, device="cuda")
+    # reference: z = conv1x1(h); f = einsum with dense fp64 weights
+    hd = h.double().requires_grad_(True)
+    g1 = torch.tensor([np.float32(start1 + i * res) for i in range(H)], device="cuda").double()
+    g2 = torch.tensor([np.float32(start2 + j * res) for j in range(W)], device="cuda").double()
+    w1 = torch.exp(-0.5 * (xt[:, 0, :, None].double() - g1[None, None]) ** 2 / scale2)
+    w2 = torch.exp(-0.5 * (xt[:, 1, :, None].double() - g2[None, None]) ** 2 / scale2)
+    z = torch.einsum("ck,bkij->bcij", Wf.double(), hd) + bf.double()[None, :, None, None]
+    f_ref = torch.einsum("bcij,bti,btj->bct", z, w1, w2)
+    f_ref.backward(df.double())
+    # kernels
+    hb = _Blk(B, 8, H, W, h.device)
+    _cabi.call("cnp_blk_from_nchw_f32", h.data_ptr(), h.stride(0), B, 64, H, W, C.byref(hb.view()), _S())
+    g = torch.empty(B, Nt, 64, device="cuda")
+    sw = torch.empty(B, Nt, device="cuda")
+    f = torch.empty(B, Cz, Nt, device="cuda")
+    Wd, bd = Wf.detach().contiguous(), bf.detach().contiguous()
+    _cabi.call("cnp_dec_blk_fwd", C.byref(hb.view()), xt.data_ptr(), B, Nt, start1, start2, res, scale2, Wd.data_ptr(),
+               bd.data_ptr(), Cz, g.data_ptr(), sw.data_ptr(), f.data_ptr(), _S())
+    assert rel_err(f, f_ref) < 1e-5
+    dg = torch.empty(B, Nt, 64, device="cuda")
+    dW, db = torch.zeros(Cz, 64, device="cuda"), torch.zeros(Cz, device="cuda")
+    _cabi.call("cnp_dec_blk_bwd_params", df.data_ptr(), g.data_ptr(), sw.data_ptr(), Wd.data_ptr(), B, Nt, Cz, dg.data_ptr(),
+               dW.data_ptr(), db.data_ptr(), _S())
+    assert rel_err(dW, Wf.grad) < 1e-4
+    assert rel_err(db, bf.grad) < 1e-4
+    dh = _Blk(B, 8, H, W, h.device)
+    dh.t.fill_(7.0)   # the kernel must overwrite every interior pixel (dense write)
+    dh.t.view(-1)[:] = 0  # ... but pads are the caller's zeros
+    _cabi.call("cnp_dec_blk_bwd_data", dg.data_ptr(), xt.data_ptr(), B, Nt, start1, start2, res, scale2, C.byref(hb.view()),
+               C.byref(dh.view()), _S())
+    out = torch.empty(B, 64, H, W, device="cuda")
+    _cabi.call("cnp_blk_to_nchw_f32", C.byref(dh.view()), B, 64, out.data_ptr(), out.stride(0), _S())
+    ref = hd.grad * (h > 0)          # ReLU mask of the producing layer fused into the kernel
+    assert rel_err(out, ref) < 1e-2   # bf16 output rounding
