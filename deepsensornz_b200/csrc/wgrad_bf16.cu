@@ -40,6 +40,7 @@ struct cnp_wg_args {
   const __nv_bfloat16* x; long long x_bs; long long x_plane;   // elements
   const __nv_bfloat16* dy; long long dy_bs; long long dy_plane;
   float* dw; float* dbias; int Cin, KK;
+  float* ws;                     // optional partial-sum workspace [pass][ksplit][acc][128][64]; NULL = atomics into dw
   int B, P, p_start, tiles_per_img, ksplit, n_pass;
   cnp_wg_pass pass[CNP_WG_MAX_PASS];
 };
@@ -186,12 +187,20 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(empty + s);
       }
+      // fold the 4 epilogue warps in shared memory: ONE atomic per channel per CTA (64 hot addresses shared by
+      // every CTA of the launch -- per-warp atomics cost ~35 us of serialised L2 traffic per launch)
+      float* bred = reinterpret_cast<float*>(smem + WG_STAGES * stage_b + (2 * WG_STAGES + 1) * 8 + 16);   // [4][64]
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
         float v = bs[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && has_work) atomicAdd(a.dbias + i, v);
+        if (lane == 0) bred[(warp - 2) * 64 + i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && has_work) {
+        for (int i = lane; i < 64; i += 32)
+          atomicAdd(a.dbias + i, bred[i] + bred[64 + i] + bred[128 + i] + bred[192 + i]);
       }
     }
     if (has_work) {
@@ -202,12 +211,19 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
       for (int j = 0; j < ps.n_acc; ++j) {
         const int slot = half ? ps.slot1[j] : ps.slot0[j];
+        float* wsp = a.ws ? a.ws + ((((size_t)blockIdx.y * a.ksplit + blockIdx.x) * CNP_WG_MAX_ACC + j) * 128 + m) * 64
+                          : nullptr;
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {
           float v[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 64 + hc * 32, v);
           tc::tmem_ld_wait();
-          if (slot >= 0 && ci < a.Cin) {
+          if (wsp) {
+            // partial sums go to the workspace with plain 16 B stores; wgrad_reduce_kernel folds the K split
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(wsp + hc * 32)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (slot >= 0 && ci < a.Cin) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int co = hc * 32 + i;
@@ -221,6 +237,28 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
+  const int total = a.n_pass * CNP_WG_MAX_ACC * 128 * 64;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int co = e & 63, m = (e >> 6) & 127, j = (e >> 13) % CNP_WG_MAX_ACC, pass = (e >> 13) / CNP_WG_MAX_ACC;
+    const cnp_wg_pass& ps = a.pass[pass];
+    if (j >= ps.n_acc) continue;
+    const int half = m >> 6;
+    const int slot = half ? ps.slot1[j] : ps.slot0[j];
+    const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
+    if (slot < 0 || ci >= a.Cin) continue;
+    const float* src = a.ws + (((size_t)pass * a.ksplit * CNP_WG_MAX_ACC + j) * 128 + m) * 64 + co;
+    const size_t stride = (size_t)CNP_WG_MAX_ACC * 128 * 64;
+    float s0 = 0.f, s1 = 0.f;
+    int k = 0;
+    for (; k + 1 < a.ksplit; k += 2) { s0 += __ldg(src + (size_t)k * stride); s1 += __ldg(src + (size_t)(k + 1) * stride); }
+    if (k < a.ksplit) s0 += __ldg(src + (size_t)k * stride);
+    a.dw[((size_t)co * a.Cin + ci) * a.KK + slot] += s0 + s1;
+  }
 }
 
 // per-channel sum of a blocked tensor: out[c] += sum_{b,y,x} v[b,c,y,x]   (bias gradients)
@@ -264,8 +302,13 @@ enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2 };
 
 // dw (+=) torch layout [64][Cin][k][k] fp32; dbias (+=) [64] fp32 or NULL (sum of dy over batch and pixels).  x: source view (n_chunks = 8 or 16; 32 = phase tensor for
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
+// Bytes of the optional partial-sum workspace (max over kinds: 5 passes x <=148 CTAs x 5 accumulators x 32 KB).
+CNP_API long long cnp_conv_tc_wgrad_workspace_bytes(void) {
+  return (long long)148 * CNP_WG_MAX_ACC * 128 * 64 * sizeof(float);
+}
+
 CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dbias,
-                              int Cin, int B, cudaStream_t st) {
+                              int Cin, int B, void* workspace, long long workspace_bytes, cudaStream_t st) {
   CNP_REQUIRE(x && dy && dw && B > 0, "conv_tc_wgrad: bad arguments");
   CNP_REQUIRE(x->H == dy->H && x->W == dy->W, "conv_tc_wgrad: x and dy must share the accumulator geometry");
   cnp_wg_args a;
@@ -327,16 +370,25 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   if (a.ksplit > total_tiles) a.ksplit = total_tiles;
   if (a.ksplit < 1) a.ksplit = 1;
   const size_t stage_b = (size_t)16 * (a.P + XPAD) * 16 + (size_t)8 * a.P * 16;
-  const size_t smem = WG_STAGES * stage_b + (2 * WG_STAGES + 1) * 8 + 16;
+  const size_t smem = WG_STAGES * stage_b + (2 * WG_STAGES + 1) * 8 + 16 + 4 * 64 * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cnp_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr = smem;
   }
+  a.ws = nullptr;
+  // the two-kernel reduction only pays for long K loops; short ones keep the atomics
+  if (workspace && total_tiles >= 4096 &&
+      workspace_bytes >= (long long)np * a.ksplit * CNP_WG_MAX_ACC * 128 * 64 * (long long)sizeof(float))
+    a.ws = reinterpret_cast<float*>(workspace);
   dim3 grid(a.ksplit, np);
   wgrad_tc_kernel<<<grid, 192, smem, st>>>(a);
   CNP_LAUNCH_CHECK("wgrad_tc_kernel");
+  if (a.ws) {
+    wgrad_reduce_kernel<<<2 * sms, 256, 0, st>>>(a);
+    CNP_LAUNCH_CHECK("wgrad_reduce_kernel");
+  }
   return 0;
 }
 

@@ -634,8 +634,11 @@ class Engine:
 
         def wgrad_tc(x: CnpBlk, n_chunks, dy: CnpBlk, kind, name, Cin):
             kk = 1 if kind == K.WG_K1 else 25
+            wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
+            ws = self._buf("wgrad_ws", (wsb // 4,))
             self._call("cnp_conv_tc_wgrad", C.byref(x), n_chunks, C.byref(dy), kind, _ptr(grads[name + ".weight"]),
-                       _ptr(grads[name + ".bias"]), Cin, B, S, work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
+                       _ptr(grads[name + ".bias"]), Cin, B, _ptr(ws), wsb, S,
+                       work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
 
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
                      accumulate=False, phase=None):

@@ -114,8 +114,12 @@ int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind, int n_
                       int n_out, void* wpk, cnp_stream_t s);
 int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, int n_out,
                  const cnp_conv_out* out, int B, cnp_stream_t s);
+/* workspace (optional, cnp_conv_tc_wgrad_workspace_bytes()): the K-split partial sums are written there and folded
+ * by a second kernel; without it they are reduced with fp32 atomics straight into dw. */
+long long cnp_conv_tc_wgrad_workspace_bytes(void);
 int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw /*+= [64][Cin][k][k]*/,
-                      float* dbias /*+= [64] or NULL*/, int Cin, int B, cnp_stream_t s);
+                      float* dbias /*+= [64] or NULL*/, int Cin, int B, void* workspace, long long workspace_bytes,
+                      cnp_stream_t s);
 int cnp_blk_channel_sum(const cnp_blk* v, int n_chunks, int B, float* out /*+=*/, cnp_stream_t s);
 int cnp_conv1x1_in_bf16(const float* x /*fp32 NCHW*/, long long x_bstride, const float* w, const float* bias, int B,
                         int Cin, int Cout, const cnp_blk* out, cnp_stream_t s);

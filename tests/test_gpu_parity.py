@@ -306,10 +306,14 @@ def test_conv_tc_dgrad_s2():
     assert rel_err(_from_blk(dxb, 64), xd.grad) < 1e-2
 
 
+@pytest.mark.parametrize("use_ws", [False, True])
 @pytest.mark.parametrize("cin,stride,k,h,w", [(128, 1, 5, 38, 44), (64, 1, 5, 76, 76), (64, 2, 5, 48, 40), (64, 1, 1, 33, 70),
                                               (64, 1, 5, 20, 24)])
-def test_conv_tc_wgrad(cin, stride, k, h, w):
+def test_conv_tc_wgrad(cin, stride, k, h, w, use_ws):
     torch.manual_seed(8)
+    ws_bytes = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes() if use_ws else 0
+    ws = torch.empty(max(ws_bytes // 4, 1), device="cuda")
+    ws_ptr = ws.data_ptr() if use_ws else None
     B = 3
     x = torch.randn(B, cin, h, w, device="cuda").bfloat16().float()
     ho, wo = h // stride, w // stride
@@ -323,11 +327,11 @@ def test_conv_tc_wgrad(cin, stride, k, h, w):
         ph = _Blk(B, 32, ho, wo, x.device)
         _cabi.call("cnp_blk_space_to_depth", C.byref(xb.view()), 8, C.byref(ph.view()), B, _S())
         _cabi.call("cnp_conv_tc_wgrad", C.byref(ph.view()), 32, C.byref(dyb.view()), _cabi.WG_K5S2, dw.data_ptr(),
-                   dbf.data_ptr(), cin, B, _S())
+                   dbf.data_ptr(), cin, B, ws_ptr, ws_bytes, _S())
     else:
         kind = _cabi.WG_K5S1 if k == 5 else _cabi.WG_K1
         _cabi.call("cnp_conv_tc_wgrad", C.byref(xb.view()), cin // 8, C.byref(dyb.view()), kind, dw.data_ptr(),
-                   dbf.data_ptr(), cin, B, _S())
+                   dbf.data_ptr(), cin, B, ws_ptr, ws_bytes, _S())
     assert rel_err(dw, wd.grad) < 1e-4   # exact bf16 products, fp32 accumulation
     assert rel_err(dbf, dy.double().sum(dim=(0, 2, 3))) < 1e-5   # bias gradient fused into the wgrad kernel
     db = torch.zeros(64, device="cuda")
