@@ -58,7 +58,7 @@ __device__ __forceinline__ void layer_fwd(const float* ws, const Offsets& o, con
 // ---------------------------------------------------------------------------------------------
 // forward: grid (chunks, B), 8 warps, PTS points per block
 // ---------------------------------------------------------------------------------------------
-constexpr int FW_PTS = 64;
+constexpr int FW_PTS = 8;    // one target per warp per block: Nt ~ 40-200 targets x B tasks must fill 148 SMs
 
 __global__ void __launch_bounds__(256)
 mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
@@ -121,7 +121,7 @@ mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
 //   dlogp[b] = d loss / d logp_b (already includes -1/(B*N_b)); outputs df (first Cf channels),
 //   dW_l, db_l (+= via atomics once per block)
 // ---------------------------------------------------------------------------------------------
-constexpr int BW_PTS = 32;
+constexpr int BW_PTS = 8;
 
 __global__ void __launch_bounds__(256)
 mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
@@ -232,7 +232,8 @@ CNP_API int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctot
   const Offsets o = make_offsets(*p);
   const size_t smem = (size_t)(o.total + 8 * 2 * MAXW) * sizeof(float);
   CNP_REQUIRE(smem <= 200 * 1024, "mlp_head_fwd: MLP too large for shared memory (%zu B)", smem);
-  cudaFuncSetAttribute(mlp_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t attr_f = 0;
+  if (smem > attr_f) { cudaFuncSetAttribute(mlp_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_f = smem; }
   dim3 grid(cnp_cdiv(Nt, FW_PTS), B);
   mlp_head_fwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, mean, var, logp, count);
   CNP_LAUNCH_CHECK("mlp_head_fwd_kernel");
@@ -250,7 +251,8 @@ CNP_API int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctot
   for (int l = 0; l < p->n_layers; ++l) { asum += p->dims[l]; gsum += p->dims[l + 1]; }
   const size_t smem = (size_t)(o.total + (asum + gsum) * BW_PTS + 8 * MAXW) * sizeof(float);
   CNP_REQUIRE(smem <= 220 * 1024, "mlp_head_bwd: MLP too large for shared memory (%zu B)", smem);
-  cudaFuncSetAttribute(mlp_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t attr_b = 0;
+  if (smem > attr_b) { cudaFuncSetAttribute(mlp_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_b = smem; }
   dim3 grid(cnp_cdiv(Nt, BW_PTS), B);
   mlp_head_bwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, dlogp, df);
   CNP_LAUNCH_CHECK("mlp_head_bwd_kernel");
