@@ -393,12 +393,18 @@ enc_grid_fused_kernel(const float* __restrict__ y, const float* __restrict__ mas
   const int* t2 = t1 + 2 * n1;
   const float* w1 = tab_w + (size_t)b * tab_bstride_w;
   const float* w2 = w1 + (size_t)KB * n1;
-  if (tid == 0) {
-    int plo = N1, phi = 0, qlo = N2, qhi = 0;
-    for (int i = 0; i < ni; ++i) { const int s = t1[i0 + i], l = t1[n1 + i0 + i]; if (l > 0) { plo = min(plo, s); phi = max(phi, s + l); } }
-    for (int j = 0; j < nj; ++j) { const int s = t2[j0 + j], l = t2[n2 + j0 + j]; if (l > 0) { qlo = min(qlo, s); qhi = max(qhi, s + l); } }
-    sh[0] = plo; sh[1] = max(phi, plo); sh[2] = qlo; sh[3] = max(qhi, qlo);
+  if (tid == 0) { sh[0] = N1; sh[1] = 0; sh[2] = N2; sh[3] = 0; }
+  __syncthreads();
+  if (tid < ni) {
+    const int s = t1[i0 + tid], l = t1[n1 + i0 + tid];
+    if (l > 0) { atomicMin(&sh[0], s); atomicMax(&sh[1], s + l); }
   }
+  if (tid < nj) {
+    const int s = t2[j0 + tid], l = t2[n2 + j0 + tid];
+    if (l > 0) { atomicMin(&sh[2], s); atomicMax(&sh[3], s + l); }
+  }
+  __syncthreads();
+  if (tid == 0) { sh[1] = max(sh[1], sh[0]); sh[3] = max(sh[3], sh[2]); }
   __syncthreads();
   const int plo = sh[0], phi = min(sh[1], sh[0] + FR_MAXROWS), qlo = sh[2], nseg = min(sh[3] - sh[2], seg_max);
   // vertical weights of this block: w1blk[p - plo][i]
@@ -513,6 +519,102 @@ int launch_enc_fused(const float* y, const float* mask, int B, int N1, int N2, i
   enc_grid_fused_kernel<C, LPT, FR_RS, KBT><<<grid, FR_J, smem, stream>>>(y, mask, N1, N2, n1, n2, KB, tbi, tbw, tab_i, tab_w, eps, out, ch_off,
                                                          c_total, seg_max);
   return 0;
+}
+
+// =============================================================================================
+// (1e) gridded context set, output-tile path for inputs no finer than the internal grid (ERA5 / aux fields):
+//   one block = ET_I x ET_J output pixels.  The input window of the tile (band union, ~(ET*dx_in/dx_out + band)^2
+//   cells) is staged in shared memory once, the horizontal band pass writes T[c][row][j] to shared memory and the
+//   vertical pass finishes the tile -- no global intermediate, one launch, same summation order as the two-pass
+//   path (bit-identical results).
+// =============================================================================================
+constexpr int ET_I = 16, ET_J = 32;
+
+template <int KBT>
+__global__ void __launch_bounds__(256)
+enc_grid_tile_kernel(const float* __restrict__ y, const float* __restrict__ mask, int C, int N1, int N2, int n1, int n2,
+                     int KB, int tab_bstride_i, int tab_bstride_w, const int* __restrict__ tab_i,
+                     const float* __restrict__ tab_w, float eps, float* __restrict__ out, int ch_off, int c_total,
+                     int max_rows, int max_cols) {
+  extern __shared__ float et_smem[];
+  float* yw = et_smem;                                        // [C+1][max_rows][max_cols]
+  float* T = et_smem + (size_t)(C + 1) * max_rows * max_cols; // [C+1][max_rows][ET_J]
+  __shared__ int sh[4];
+  const int tid = threadIdx.x, b = blockIdx.z;
+  const int i0 = blockIdx.y * ET_I, j0 = blockIdx.x * ET_J;
+  const int ni = min(ET_I, n1 - i0), nj = min(ET_J, n2 - j0);
+  const int* t1 = tab_i + (size_t)b * tab_bstride_i;
+  const int* t2 = t1 + 2 * n1;
+  const float* w1 = tab_w + (size_t)b * tab_bstride_w;
+  const float* w2 = w1 + (size_t)KB * n1;
+  // band union of the tile, in parallel (a serial scan by one thread costs ~1 us of L2 latency per table entry)
+  if (tid == 0) { sh[0] = N1; sh[1] = 0; sh[2] = N2; sh[3] = 0; }
+  __syncthreads();
+  if (tid < ni) {
+    const int s = t1[i0 + tid], l = t1[n1 + i0 + tid];
+    if (l > 0) { atomicMin(&sh[0], s); atomicMax(&sh[1], s + l); }
+  } else if (tid >= 64 && tid < 64 + nj) {
+    const int s = t2[j0 + tid - 64], l = t2[n2 + j0 + tid - 64];
+    if (l > 0) { atomicMin(&sh[2], s); atomicMax(&sh[3], s + l); }
+  }
+  __syncthreads();
+  const int plo = sh[0], nr = max(min(sh[1] - sh[0], max_rows), 0), qlo = sh[2], nc = max(min(sh[3] - sh[2], max_cols), 0);
+  const float* yb = y + (size_t)b * C * N1 * N2;
+  const float* mb = mask ? mask + (size_t)b * N1 * N2 : nullptr;
+  // 1. stage y~ = [valid ; y * valid] of the window
+  for (int e = tid; e < nr * nc; e += 256) {
+    const int r = e / nc, q = e - r * nc;
+    const size_t off = (size_t)(plo + r) * N2 + qlo + q;
+    float valid = mb ? __ldg(mb + off) : 1.f;
+    bool nan_any = false;
+    for (int c = 0; c < C; ++c) nan_any |= isnan(__ldg(yb + (size_t)c * N1 * N2 + off));
+    if (nan_any) valid = 0.f;
+    yw[(size_t)r * max_cols + q] = valid;
+    for (int c = 0; c < C; ++c)
+      yw[((size_t)(1 + c) * max_rows + r) * max_cols + q] = nan_any ? 0.f : __ldg(yb + (size_t)c * N1 * N2 + off) * valid;
+  }
+  __syncthreads();
+  // 2. horizontal band pass: thread = (tile column j, rows r = tid/32, +8, ...)
+  const int tj = tid & 31, tr = tid >> 5;
+  const bool colok = tj < nj;
+  const int jg = j0 + tj;
+  const int myq = colok ? t2[jg] - qlo : 0, mylen = colok ? min(t2[n2 + jg], KBT) : 0;
+  float w2r[KBT];
+#pragma unroll
+  for (int k = 0; k < KBT; ++k) w2r[k] = (k < mylen) ? __ldg(w2 + (size_t)k * n2 + jg) : 0.f;
+  for (int c = 0; c <= C; ++c)
+    for (int r = tr; r < nr; r += 8) {
+      const float* src = yw + ((size_t)c * max_rows + r) * max_cols + myq;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < KBT; ++k)
+        if (k < mylen) acc = fmaf(src[k], w2r[k], acc);
+      T[((size_t)c * max_rows + r) * ET_J + tj] = acc;
+    }
+  __syncthreads();
+  // 3. vertical band pass + density normalisation: thread = (column j, output rows i = tid/32 and +8)
+#pragma unroll
+  for (int m = 0; m < ET_I / 8; ++m) {
+    const int i = tr + 8 * m;
+    if (i < ni && colok) {
+      const int ig = i0 + i;
+      const int s = t1[ig] - plo, len = min(t1[n1 + ig], KBT);
+      float w1r[KBT];
+#pragma unroll
+      for (int k = 0; k < KBT; ++k) w1r[k] = (k < len) ? __ldg(w1 + (size_t)k * n1 + ig) : 0.f;
+      float* ob = out + ((size_t)b * c_total + ch_off) * n1 * n2 + (size_t)ig * n2 + jg;
+      float dens = 0.f;
+      for (int c = 0; c <= C; ++c) {
+        const float* src = T + ((size_t)c * max_rows + s) * ET_J + tj;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < KBT; ++k)
+          if (k < len) acc = fmaf(w1r[k], src[(size_t)k * ET_J], acc);
+        if (c == 0) { dens = acc; ob[0] = acc; }
+        else ob[(size_t)c * n1 * n2] = acc / (dens + eps);
+      }
+    }
+  }
 }
 
 // =============================================================================================
@@ -695,6 +797,26 @@ CNP_API int cnp_setconv_enc_grid_fwd(const float* x1, const float* x2, int x_bat
                                               start1, n1, start2, n2, res, scale2, band, tab_i, tab_w);
     CNP_LAUNCH_CHECK("band_table_kernel");
     const int tbi = x_batched ? 2 * (n1 + n2) : 0, tbw = x_batched ? band * (n1 + n2) : 0;
+    // inputs no finer than ~2x the grid: output-tile kernel (window + T in shared memory, one launch)
+    if (N1 < 2 * n1 && N2 < 2 * n2) {
+      const int max_rows = (int)((double)N1 / n1 * ET_I) + band + 4, max_cols = (int)((double)N2 / n2 * ET_J) + band + 4;
+      const size_t tsmem = ((size_t)(C + 1) * max_rows * max_cols + (size_t)(C + 1) * max_rows * ET_J) * sizeof(float);
+      if (tsmem <= 96 * 1024) {
+        dim3 gt(cnp_cdiv(n2, ET_J), cnp_cdiv(n1, ET_I), B);
+        static size_t attr16 = 0, attr32 = 0;
+        if (band <= 16) {
+          if (tsmem > attr16 && tsmem > 48 * 1024) { cudaFuncSetAttribute(enc_grid_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem); attr16 = tsmem; }
+          enc_grid_tile_kernel<16><<<gt, 256, tsmem, stream>>>(y, mask, C, N1, N2, n1, n2, band, tbi, tbw, tab_i, tab_w, eps, out,
+                                                              ch_off, c_total, max_rows, max_cols);
+        } else {
+          if (tsmem > attr32 && tsmem > 48 * 1024) { cudaFuncSetAttribute(enc_grid_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem); attr32 = tsmem; }
+          enc_grid_tile_kernel<32><<<gt, 256, tsmem, stream>>>(y, mask, C, N1, N2, n1, n2, band, tbi, tbw, tab_i, tab_w, eps, out,
+                                                              ch_off, c_total, max_rows, max_cols);
+        }
+        CNP_LAUNCH_CHECK("enc_grid_tile_kernel");
+        return 0;
+      }
+    }
     // fused single pass when the staged row segment and the row band fit (input no finer than ~20x the grid)
     {
       const int seg_max = ((N2 < 6 * FR_J ? N2 : 6 * FR_J) + 3) & ~3;
