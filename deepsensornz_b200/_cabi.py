@@ -52,6 +52,7 @@ class CnpConvOut(C.Structure):
         ("relu", C.c_int),
         ("mask", C.POINTER(CnpBlk)),
         ("accumulate", C.c_int),
+        ("s2d", C.POINTER(CnpBlk)),
     ]
 
 
@@ -102,6 +103,7 @@ _SIGS = {
     "cnp_conv_tc_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_conv_tc": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
     "cnp_conv_tc2_debug": (C.c_int, [c_fp, _i]),
+    "cnp_conv_tc2_set_cluster": (C.c_int, [_i]),
     "cnp_conv_tc2_packed_bytes": (_ll, [_i, _i, _i]),
     "cnp_conv_tc2_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_conv_tc2": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),

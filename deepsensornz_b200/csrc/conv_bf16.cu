@@ -742,6 +742,7 @@ struct cnp_conv_out {
   int relu;
   const cnp_blk* mask;    // zero the result where mask <= 0 (same geometry as the output) or NULL
   int accumulate;
+  const cnp_blk* s2d;     // (conv_tc2 only) optional space-to-depth copy of the output
 };
 
 // Bytes of packed weights for (kind, n_chunks): stages x 20480.

@@ -570,18 +570,24 @@ class Engine:
         A["h_init"], A["cat"] = h_init, cat
         phases = [None] * L
         x = h_init
+        # layer i's epilogue also writes the space-to-depth copy that the stride-2 layer i+1 reads
         for i in range(L):
+            if st[i] == 2 and phases[i] is None:     # producer could not fuse it (first level): separate kernel
+                ph = self._blk(f"phase{i}", B, 32, res[i][0], res[i][1])
+                self._call("cnp_blk_space_to_depth", C.byref(x.view(0)), 8, C.byref(ph.view()), B, S)
+                phases[i] = ph
             lyr = u.before_turn_layers[i]
             out = self._out_blk(cat[i].view(0), bias=lyr.bias, relu=True)
+            if i + 1 < L and st[i + 1] == 2 and res[i][0] % 2 == 0 and res[i][1] % 2 == 0:
+                phases[i + 1] = self._blk(f"phase{i + 1}", B, 32, res[i + 1][0], res[i + 1][1])
+                out._s2d_view = phases[i + 1].view()
+                out.s2d = C.pointer(out._s2d_view)
             if st[i] == 1:
                 wpk = self._packed_weights(f"before{i}", lyr.weight, K.KIND_K5S1, 8)
                 self._conv_tc(x.view(0), 8, wpk, K.KIND_K5S1, out, B)
             else:
-                ph = self._blk(f"phase{i}", B, 32, res[i][0], res[i][1])
-                self._call("cnp_blk_space_to_depth", C.byref(x.view(0)), 8, C.byref(ph.view()), B, S)
-                phases[i] = ph
                 wpk = self._packed_weights(f"before{i}", lyr.weight, K.KIND_K5S2, 32)
-                self._conv_tc(ph.view(0), 32, wpk, K.KIND_K5S2, out, B)
+                self._conv_tc(phases[i].view(0), 32, wpk, K.KIND_K5S2, out, B)
             x = cat[i]
         A["phases"] = phases
         ups = [None] * L

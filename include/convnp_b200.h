@@ -93,6 +93,7 @@ typedef struct cnp_conv_out {
   int relu;
   const cnp_blk* mask; /* zero the result where mask <= 0 (ReLU backward), or NULL */
   int accumulate;      /* out += result */
+  const cnp_blk* s2d;  /* cnp_conv_tc2 only: also write the space-to-depth copy (32 chunks, half size) or NULL */
 } cnp_conv_out;
 
 enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5 };
@@ -109,6 +110,7 @@ int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int p
  * n_out = 64: two output rows share one MMA (PAIR); n_out = 128: 128 output channels per call (WIDE, used for
  * the input gradient of the 128->64 layers). */
 int cnp_conv_tc2_debug(long long* device_buf /*[148][8] or NULL*/, int flags);   /* per-CTA stall counters, profiling aid */
+int cnp_conv_tc2_set_cluster(int cluster /*1 | 2: CTA pairs multicast the weight stream*/);
 long long cnp_conv_tc2_packed_bytes(int kind, int n_chunks, int n_out);
 int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px, int co_off,
                       int n_out, void* wpk, cnp_stream_t s);

@@ -164,3 +164,29 @@ def test_conv_tc2_dgrad_s2_and_1x1():
     _cabi.call("cnp_conv_tc2", C.byref(dzb.view()), 8, _pack(w1, _cabi.KIND_K1_DGRAD, 8).data_ptr(),
                _cabi.KIND_K1_DGRAD, 0, 0, 64, C.byref(o), B, _S())
     assert rel_err(_from_blk(d1, 64), xd1.grad) < 1e-2
+
+
+def test_conv_tc2_cluster_multicast_matches_plain():
+    """Clusters of two CTAs sharing the weight stream by multicast give bit-identical outputs (also with an odd number
+    of tiles, where one CTA of a pair only streams weights in the last round)."""
+    torch.manual_seed(9)
+    B, cin, h, w = 3, 128, 70, 300
+    x = torch.randn(B, cin, h, w, device="cuda").bfloat16().float()
+    wt = (torch.randn(64, cin, 5, 5, device="cuda") * 0.05).bfloat16().float()
+    b = torch.randn(64, device="cuda")
+    xb = _to_blk(x)
+    wpk = _pack(wt, _cabi.KIND_K5S1, cin // 8)
+    outs = []
+    try:
+        for cluster in (1, 2):
+            _cabi.call("cnp_conv_tc2_set_cluster", cluster)
+            yb = _Blk(B, 8, h, w, x.device)
+            o = _out(yb.view(), bias=b, relu=1)
+            _cabi.call("cnp_conv_tc2", C.byref(xb.view()), cin // 8, wpk.data_ptr(), _cabi.KIND_K5S1, 0, 0, 64, C.byref(o), B, _S())
+            outs.append(_from_blk(yb, 64))
+    finally:
+        _cabi.call("cnp_conv_tc2_set_cluster", 1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=2))
+    assert rel_err(outs[0], ref) < 1e-2
