@@ -159,7 +159,7 @@ def run_reference(args):
         "impl": "reference", "metric": "convnp_train_tasks_per_s", "value": rate, "unit": "tasks/s", "n_gpus": 0,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, "fp32"),
+        "config": {k: v for k, v in workload_config(1, "fp32").items() if k != "static_context_dedup"},
         "cpu_baseline": {"value": rate, "unit": "tasks/s", "cores": cores, "kind": "port",
                          "sample": f"{n_tasks} task per step (fwd+NLL+bwd), torch CPU oracle, all host threads"},
         "e2e": {"value": rate, "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,7 +199,8 @@ def run_ours(args):
         from deepsensornz_b200.dist import enable_data_parallel
         enable_data_parallel(model)
     # the reference's optimiser (train.py:354); fused=True is torch's single-kernel implementation of the same update
-    opt = torch.optim.AdamW(model.model.parameters(), lr=5e-5, weight_decay=1e-5, fused=True)
+    opt = torch.optim.AdamW(model.model.parameters(), lr=5e-5, weight_decay=1e-5, fused=True,
+                            capturable=(world == 1 and not args.no_graph))
     eng = model.engine
 
     tasks = make_batches(2, rank)
@@ -237,11 +238,23 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step(dev[i % 2])
+    # One-GPU runs replay the whole step (forward, NLL, backward, AdamW) as a CUDA graph (deepsensornz_b200/graph.py);
+    # the data-parallel step keeps eager launches around the NCCL all-reduce.
+    gs = None
+    if world == 1 and not args.no_graph:
+        from deepsensornz_b200.graph import GraphedTrainStep
+        l0 = eng.launches
+        gs = GraphedTrainStep(model, opt, dev[0], warmup=1)
+        graph_launches = (eng.launches - l0) // 2      # one warm-up step + the captured step
+        run = lambda batch: gs.step(batch)
+    else:
+        run = step
+    run(dev[0])
     # ---- device-resident throughput ----
     launches0 = eng.launches
     with ClockSampler(local) as clk:
-        ms = timed(lambda i: step(dev[i % 2]), args.steps)
-    launches = eng.launches - launches0
+        ms = timed(lambda i: run(dev[i % 2]), args.steps)
+    launches = (eng.launches - launches0) if gs is None else graph_launches * args.steps
     clocks = clk.summary()
     value = world * BATCH * args.steps / (ms * 1e-3)
     # ---- end to end through the public API with host buffers ----
@@ -253,7 +266,7 @@ def run_ours(args):
 
     def e2e_step(i):
         cur = pending["b"]
-        loss = step(cur)
+        loss = run(cur)
         pending["b"] = eng.upload(host[(i + 1) % 2], stream=copy_stream)   # next step's inputs
         last["loss"] = float(loss.detach().cpu())  # D2H of the loss every step
 
@@ -291,7 +304,7 @@ def run_ours(args):
         "config": workload_config(world, args.precision, dev[0].grid),
         "e2e": {"value": e2e, "unit": "tasks/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
+        "gpu_launches": launches, "cuda_graph": gs is not None, "clocks": clocks, "roofline": roof, "kernels": kernels,
         "loss": last.get("loss"),
     }
     if rank == 0:
@@ -313,6 +326,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

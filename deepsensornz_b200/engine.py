@@ -121,6 +121,7 @@ class Engine:
             raise NotImplementedError("bf16 tensor-core path is specialised for unet_channels=(64,)*L")
         self._ws: Dict[tuple, object] = {}
         self._packed: Dict[str, Tuple[int, torch.Tensor]] = {}
+        self._scale_cache: Dict[int, Tuple[int, float]] = {}
         self._pack_reqs: Dict[str, tuple] = {}     # every packing seen so far -> re-issued up front on a side stream
         self._pack_stream = None
         self._pack_event = None
@@ -195,7 +196,13 @@ class Engine:
         self._pack_reqs.clear()
 
     def _scale2(self, log_scale: torch.Tensor) -> float:
-        return float(np.float32(math.exp(2.0 * float(log_scale))))
+        """exp(2 log_scale) as an fp32-rounded host float.  The length scales are fixed (not learnable), so the value
+        is read back from the device once per parameter version -- never inside a step (CUDA-graph capture)."""
+        ent = self._scale_cache.get(id(log_scale))
+        if ent is None or ent[0] != log_scale._version:
+            ent = (log_scale._version, float(np.float32(math.exp(2.0 * float(log_scale)))))
+            self._scale_cache[id(log_scale)] = ent
+        return ent[1]
 
     # ------------------------------------------------------------------------------------------
     # host -> device

@@ -21,9 +21,15 @@ def set_gpu_default_device() -> None:
 
 
 def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional[int] = None, opt=None,
-                progress_bar: bool = False, tqdm_notebook: bool = False) -> List[float]:
+                progress_bar: bool = False, tqdm_notebook: bool = False, use_graph: Optional[bool] = None) -> List[float]:
     """One pass over ``tasks``.  ``batch_size=None``: one optimiser step per task; otherwise
-    ``len(tasks)//batch_size`` steps on concatenated batches (the remainder is dropped, as upstream)."""
+    ``len(tasks)//batch_size`` steps on concatenated batches (the remainder is dropped, as upstream).
+
+    ``use_graph`` (default: env ``CONVNP_B200_GRAPH=1``): replay forward + backward (+ the optimiser step when it is
+    ``capturable``) as a CUDA graph from the second batch with the same shape signature on (graph.py)."""
+    import os
+    if use_graph is None:
+        use_graph = os.environ.get("CONVNP_B200_GRAPH", "0") == "1"
     if opt is None:
         opt = torch.optim.Adam(model.model.parameters(), lr=lr)
 
@@ -62,11 +68,25 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
             it = tqdm(it)
         except Exception:
             pass
+    use_graph = bool(use_graph) and can_stage and getattr(model.engine, "world_size", 1) == 1
+    graphs = model.__dict__.setdefault("_train_graphs", {}) if use_graph else None
     losses = []
     nxt = make(0) if n_batches > 0 else None
     for bi in it:
         cur = nxt
-        loss_t = launch_step(cur)
+        if use_graph and not isinstance(cur, list):
+            from .graph import GraphedTrainStep, batch_signature
+            key = (id(opt), batch_signature(cur))
+            gs = graphs.get(key)
+            if gs is None:            # first batch of this shape: eager (it is also the warm-up of the capture)
+                loss_t = launch_step(cur)
+                graphs[key] = False
+            else:
+                if gs is False:
+                    gs = graphs[key] = GraphedTrainStep(model, opt, cur, warm=True)
+                loss_t = gs.step(cur)
+        else:
+            loss_t = launch_step(cur)
         nxt = make(bi + 1) if bi + 1 < n_batches else None
         losses.append(float(loss_t.cpu().numpy()))
     return losses

@@ -397,3 +397,48 @@ def test_train_epoch_decreases_loss(static):
     for _ in range(5):
         last = np.mean(train_epoch(m, tasks, batch_size=4, opt=opt))
     assert np.isfinite(first) and last < first
+
+
+def test_graphed_train_step_matches_eager(static):
+    """The CUDA-graph replay of (forward, NLL, backward, AdamW) follows the eager step bit for bit in its losses."""
+    from deepsensornz_b200.graph import GraphedTrainStep
+    tasks = [concat_tasks([make_task(static, 700 + 4 * k + i) for i in range(4)]) for k in range(3)]
+    losses = {}
+    for mode in ("eager", "graph"):
+        m = small_model("bf16", seed=3)
+        opt = torch.optim.AdamW(m.model.parameters(), lr=1e-3, fused=True, capturable=True)
+        dev = [m._to_device(t) for t in tasks]
+        out = []
+        if mode == "graph":
+            gs = GraphedTrainStep(m, opt, dev[0], warmup=1)      # = one eager step on dev[0] before the capture
+            assert all(gs.matches(d) for d in dev)
+            for k in range(6):
+                out.append(float(gs.step(dev[k % 3])))
+        else:
+            for k in [0] + list(range(6)):
+                opt.zero_grad(set_to_none=True)
+                loss = m.loss_fn(dev[k % 3], normalise=True)
+                loss.backward()
+                opt.step()
+                out.append(float(loss))
+        losses[mode] = out
+    assert losses["graph"][-1] < losses["graph"][0]          # it trains
+    for a, b in zip(losses["eager"][1:], losses["graph"]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses["eager"], losses["graph"])   # atomics reorder fp32 sums
+
+
+def test_train_epoch_with_graph_decreases_loss(static):
+    from deepsensornz_b200 import train_epoch
+    import numpy as np
+    np.random.seed(0)
+    tasks = [make_task(static, 500 + i) for i in range(8)]
+    m = small_model("bf16", seed=5)
+    opt = torch.optim.AdamW(m.model.parameters(), lr=2e-3)      # not capturable: the optimiser step stays eager
+    first = last = None
+    for ep in range(6):
+        losses = train_epoch(m, tasks, batch_size=4, opt=opt, use_graph=True)
+        assert len(losses) == 2 and all(np.isfinite(losses))
+        first = first if first is not None else float(np.mean(losses))
+        last = float(np.mean(losses))
+    assert last < first
+    assert any(g not in (None, False) for g in m._train_graphs.values())   # a graph was captured and replayed
