@@ -170,12 +170,12 @@ class ConvNP:
             task = task.mask_nans_nps()
         return task
 
-    def stage_task(self, task: Task, pinned: bool = True) -> HostBatch:
+    def stage_task(self, task: Task, pinned: bool = True, ctx_cache: Optional[dict] = None) -> HostBatch:
         """Stage a task once in page-locked host memory; ``loss_fn`` / ``__call__`` accept the result and
         then only pay the asynchronous H2D copy per call."""
-        return self._to_device(task, pinned=pinned, upload=False)
+        return self._to_device(task, pinned=pinned, upload=False, ctx_cache=ctx_cache)
 
-    def _to_device(self, task, pinned: bool = False, upload: bool = True):
+    def _to_device(self, task, pinned: bool = False, upload: bool = True, ctx_cache: Optional[dict] = None):
         """Upload a task.  Raw tasks skip the host NaN scans: NaNs travel to the GPU and the encoder
         kernels derive the masks there (identical result to the Masked path, see tests)."""
         if isinstance(task, DeviceBatch):
@@ -200,7 +200,7 @@ class ConvNP:
                 contexts.append((x, y, None))
         if isinstance(yt, np.ma.MaskedArray):
             yt = yt.filled(np.nan)
-        hb = self.engine.stage_host(contexts, xt, yt, kw.get("aux_t"), pinned=pinned)
+        hb = self.engine.stage_host(contexts, xt, yt, kw.get("aux_t"), pinned=pinned, ctx_cache=ctx_cache)
         return self.engine.upload(hb) if upload else hb
 
     # ------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@
 //   pass A: T[b,c,i,q] = sum_j z[b,c,i,j] w2[j,q]     (band of <= 32 grid columns per target column)
 //   pass B: f[b,c,p,q] = sum_i w1[i,p] T[b,c,i,q]
 // Band tables are analytic (the internal grid is uniform), so arbitrary target coordinates work.
-#include "common.cuh"
+#include "tc_common.cuh"   // cnp_blk
 #include <math.h>
 
 #include "mlp_params.cuh"
@@ -221,5 +221,226 @@ CNP_API int cnp_mlp_head_points_fwd(const cnp_mlp_params* p, const float* f, lon
   dim3 grid((unsigned)(nb < 2 * sms ? nb : 2 * sms), B);
   mlp_head_points_kernel<<<grid, 256, smem, st>>>(*p, f, f_bstride, Cf, aux, aux_bstride, Ca, npts, mean, stdv);
   CNP_LAUNCH_CHECK("mlp_head_points_kernel");
+  return 0;
+}
+
+// =============================================================================================
+// Fused on-grid inference decoder on the blocked bf16 hidden activation (bf16 mode):
+//   column pass   T[c,i,q]   = sum_j h[c,i,j] w2[j,q]                       (blocked bf16 in, blocked bf16 out)
+//   fused tail    g[c,p,q]   = sum_i w1[i,p] T[c,i,q]                        (registers, never written)
+//                 o          = MLP([Wf g + bf sw ; aux]) with the final 1x1 (Wf, bf) folded into MLP layer 0:
+//                              W0'' = [W0f Wf | W0a | W0f bf],  input = [g ; aux ; sw],  sw = SetConv(1) = sw1[p] sw2[q]
+//                 mean = o0, std = sqrt(1e-6 + softplus(o1))
+// The 64 x P x Q decoder output (502 MB per 1400^2 task) and the full-grid 1x1 convolution are never materialised.
+// Replaces, for ConvNP.predict (validate_ERA.py:88-92), final Conv1x1 + SetConv + Augment + MLP + likelihood.
+// =============================================================================================
+namespace {
+
+constexpr int FZ_IN = 72;   // padded layer-0 input: 64 (g) + Ca (<= 6) + 1 (sw) <= 72
+
+// per target coordinate: band start, length, weights and their sum (SetConv of ones)
+__global__ void __launch_bounds__(128)
+dec_band_sw_kernel(const float* __restrict__ xt, int T, double start, int n, double res, float scale2,
+                   int* __restrict__ j0, int* __restrict__ len, float* __restrict__ w, float* __restrict__ sw) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= T) return;
+  const float x = xt[t];
+  const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+  int lo = (int)floor(((double)x - R - start) / res) - 1;
+  int hi = (int)ceil(((double)x + R - start) / res) + 1;
+  lo = max(lo, 0); hi = min(hi, n - 1);
+  while (lo <= hi && cnp_rbf(x, cnp_grid_pt(start, res, lo), scale2) == 0.f) ++lo;
+  while (hi >= lo && cnp_rbf(x, cnp_grid_pt(start, res, hi), scale2) == 0.f) --hi;
+  const int L = min(max(hi - lo + 1, 0), DKB);
+  j0[t] = lo; len[t] = L;
+  float s = 0.f;
+  for (int k = 0; k < DKB; ++k) {
+    const float v = (k < L) ? cnp_rbf(x, cnp_grid_pt(start, res, lo + k), scale2) : 0.f;
+    w[(size_t)k * T + t] = v;
+    s += v;
+  }
+  sw[t] = s;
+}
+
+// W0'' [64][FZ_IN] and b0 from (W0 [64][64+Ca], Wf [64][64], bf [64])
+__global__ void __launch_bounds__(FZ_IN)
+fold_final_kernel(const float* __restrict__ W0, const float* __restrict__ Wf, const float* __restrict__ bfin, int Ca,
+                  float* __restrict__ Wout) {
+  const int o = blockIdx.x, i = threadIdx.x, in0 = 64 + Ca;
+  float v = 0.f;
+  if (i < 64) {
+    for (int c = 0; c < 64; ++c) v = fmaf(W0[(size_t)o * in0 + c], Wf[(size_t)c * 64 + i], v);
+  } else if (i < 64 + Ca) {
+    v = W0[(size_t)o * in0 + i];
+  } else if (i == 64 + Ca) {
+    for (int c = 0; c < 64; ++c) v = fmaf(W0[(size_t)o * in0 + c], bfin[c], v);
+  }
+  Wout[(size_t)o * FZ_IN + i] = v;
+}
+
+// column pass on the blocked layout; block = 32 target columns x 8 chunks, one grid row per blockIdx.y
+__global__ void __launch_bounds__(256)
+dec_cols_blk_kernel(const __nv_bfloat16* __restrict__ h, long long h_bs, int H, int W, int Q,
+                    const int* __restrict__ j0, const int* __restrict__ len, const float* __restrict__ w2,
+                    __nv_bfloat16* __restrict__ T) {
+  const int q = blockIdx.x * 32 + (threadIdx.x & 31), chunk = threadIdx.x >> 5, i = blockIdx.y, b = blockIdx.z;
+  if (q >= Q) return;
+  const int Wp = W + 4;
+  const __nv_bfloat16* src = h + (size_t)b * h_bs + (((size_t)chunk * (H + 4) + i + 2) * Wp + 2) * 8;
+  const int s = j0[q], L = len[q];
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int k = 0; k < L; ++k) {
+    const float wv = __ldg(w2 + (size_t)k * Q + q);
+    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(s + k) * 8));
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float2 f2 = __bfloat1622float2(p2[c]);
+      acc[2 * c] = fmaf(wv, f2.x, acc[2 * c]); acc[2 * c + 1] = fmaf(wv, f2.y, acc[2 * c + 1]);
+    }
+  }
+  uint4 o;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) o2[c] = __floats2bfloat162_rn(acc[2 * c], acc[2 * c + 1]);
+  *reinterpret_cast<uint4*>(T + ((((size_t)b * 8 + chunk) * H + i) * Q + q) * 8) = o;
+}
+
+// row pass + folded MLP + head; one thread per target pixel
+__global__ void __launch_bounds__(256, 1)
+dec_grid_mlp_fused_kernel(cnp_mlp_params p, const float* __restrict__ W0f /*[64][FZ_IN]*/, const __nv_bfloat16* __restrict__ T,
+                          int H, int P, int Q, const int* __restrict__ i0, const int* __restrict__ len1,
+                          const float* __restrict__ w1, const float* __restrict__ sw1, const float* __restrict__ sw2,
+                          const float* __restrict__ aux, long long aux_bs, int Ca, float* __restrict__ mean,
+                          float* __restrict__ stdv) {
+  extern __shared__ __align__(16) float sm[];
+  const int L = p.n_layers;
+  float* w0 = sm;                                   // [64][FZ_IN]
+  float* b0 = w0 + GP_H * FZ_IN;
+  float* wh = b0 + GP_H;                            // (L-2) x ([64][64] + [64])
+  float* wl = wh + (size_t)(L - 2) * (GP_H * GP_H + GP_H);
+  float* bl = wl + 2 * GP_H;
+  float* hbuf = bl + 4;                             // [64][256]
+  for (int e = threadIdx.x; e < GP_H * FZ_IN; e += 256) w0[e] = W0f[e];
+  for (int e = threadIdx.x; e < GP_H; e += 256) b0[e] = p.b[0][e];
+  for (int l = 1; l < L - 1; ++l) {
+    float* wd = wh + (size_t)(l - 1) * (GP_H * GP_H + GP_H);
+    for (int e = threadIdx.x; e < GP_H * GP_H; e += 256) wd[e] = p.W[l][e];
+    for (int e = threadIdx.x; e < GP_H; e += 256) wd[GP_H * GP_H + e] = p.b[l][e];
+  }
+  for (int e = threadIdx.x; e < 2 * GP_H; e += 256) wl[e] = p.W[L - 1][e];
+  if (threadIdx.x < 2) bl[threadIdx.x] = p.b[L - 1][threadIdx.x];
+  __syncthreads();
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const long long npts = (long long)P * Q;
+  const float* ab = aux + (size_t)b * aux_bs;
+  const __nv_bfloat16* Tb = T + (size_t)b * 8 * H * Q * 8;
+  for (long long pt = (long long)blockIdx.x * 256 + tid; pt < npts; pt += (long long)gridDim.x * 256) {
+    const int pp = (int)(pt / Q), q = (int)(pt - (long long)pp * Q);
+    const int s = i0[pp], Ln = len1[pp];
+    float a0[FZ_IN];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) a0[i] = 0.f;
+    for (int k = 0; k < Ln; ++k) {
+      const float wv = __ldg(w1 + (size_t)k * P + pp);
+      const __nv_bfloat16* row = Tb + ((size_t)(s + k) * Q + q) * 8;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 pk = __ldg(reinterpret_cast<const uint4*>(row + (size_t)c * H * Q * 8));
+        const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f2 = __bfloat1622float2(p2[e]);
+          a0[c * 8 + 2 * e] = fmaf(wv, f2.x, a0[c * 8 + 2 * e]);
+          a0[c * 8 + 2 * e + 1] = fmaf(wv, f2.y, a0[c * 8 + 2 * e + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 64; i < FZ_IN; ++i) {
+      float v = 0.f;
+      if (i < 64 + Ca) v = __ldg(ab + (size_t)(i - 64) * npts + pt);
+      else if (i == 64 + Ca) v = sw1[pp] * sw2[q];
+      a0[i] = v;
+    }
+    gp_layer<FZ_IN>(w0, b0, GP_H, a0, hbuf, tid);
+    float a[GP_H];
+    for (int l = 1; l < L - 1; ++l) {
+#pragma unroll
+      for (int i = 0; i < GP_H; ++i) { const float v = hbuf[i * 256 + tid]; a[i] = v < 0.f ? 0.f : v; }
+      const float* wd = wh + (size_t)(l - 1) * (GP_H * GP_H + GP_H);
+      gp_layer<GP_H>(wd, wd + GP_H * GP_H, GP_H, a, hbuf, tid);
+    }
+#pragma unroll
+    for (int i = 0; i < GP_H; ++i) { const float v = hbuf[i * 256 + tid]; a[i] = v < 0.f ? 0.f : v; }
+    float o0 = bl[0], o1 = bl[1];
+#pragma unroll
+    for (int i = 0; i < GP_H; ++i) { o0 = fmaf(wl[i], a[i], o0); o1 = fmaf(wl[GP_H + i], a[i], o1); }
+    mean[(size_t)b * npts + pt] = o0;
+    stdv[(size_t)b * npts + pt] = sqrtf(1e-6f + softplus_t(o1));
+  }
+}
+
+}  // namespace
+
+CNP_API long long cnp_decode_grid_fused_workspace_bytes(int B, int n1, int P, int Q) {
+  long long tabs = (long long)(P + Q) * (2 * sizeof(int) + (DKB + 1) * sizeof(float)) + (long long)64 * FZ_IN * sizeof(float);
+  long long T = (long long)B * 64 * n1 * Q * 2;
+  return ((tabs + 255) / 256) * 256 + T;
+}
+
+// mean / std [B,P,Q] on the target grid x1t[P] x x2t[Q] from the blocked 64-channel hidden activation h, the final 1x1
+// (Wf [64][64], bf [64]) and the aux MLP (p: dims[0] = 64 + Ca, hidden width 64, >= 2 hidden layers).
+CNP_API int cnp_decode_grid_fused_fwd(const cnp_blk* h, const float* x1t, const float* x2t, int B, int P, int Q,
+                                      double start1, double start2, double res, float scale2, const float* Wf,
+                                      const float* bfin, const cnp_mlp_params* p, const float* aux, long long aux_bstride,
+                                      int Ca, float* mean, float* stdv, void* workspace, long long workspace_bytes,
+                                      cudaStream_t st) {
+  CNP_REQUIRE(h && x1t && x2t && Wf && bfin && p && aux && mean && stdv && workspace && B > 0 && P > 0 && Q > 0,
+              "decode_grid_fused: bad arguments");
+  const int n1 = h->H, n2 = h->W;
+  CNP_REQUIRE(workspace_bytes >= cnp_decode_grid_fused_workspace_bytes(B, n1, P, Q), "decode_grid_fused: workspace too small");
+  CNP_REQUIRE(p->n_layers >= 3 && p->n_layers <= CNP_MLP_MAX_LAYERS, "decode_grid_fused: need >= 2 hidden layers");
+  CNP_REQUIRE(p->dims[0] == 64 + Ca && 64 + Ca + 1 <= FZ_IN, "decode_grid_fused: layer-0 width %d unsupported", p->dims[0]);
+  for (int l = 1; l < p->n_layers; ++l)
+    CNP_REQUIRE(p->dims[l] == GP_H, "decode_grid_fused: hidden width must be %d (got %d)", GP_H, p->dims[l]);
+  CNP_REQUIRE(p->dims[p->n_layers] == 2, "decode_grid_fused: last layer must have 2 outputs");
+  const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+  CNP_REQUIRE(2.0 * R / res + 3 <= DKB, "decode_grid_fused: decoder scale too large for the banded kernel (band > %d)", DKB);
+  int* i0 = reinterpret_cast<int*>(workspace);
+  int* len1 = i0 + P;
+  int* j0 = len1 + P;
+  int* len2 = j0 + Q;
+  float* w1 = reinterpret_cast<float*>(len2 + Q);
+  float* w2 = w1 + (size_t)DKB * P;
+  float* sw1 = w2 + (size_t)DKB * Q;
+  float* sw2 = sw1 + P;
+  float* W0f = sw2 + Q;
+  const long long tabs = (long long)(P + Q) * (2 * sizeof(int) + (DKB + 1) * sizeof(float)) + (long long)64 * FZ_IN * sizeof(float);
+  __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + ((tabs + 255) / 256) * 256);
+  dec_band_sw_kernel<<<cnp_cdiv(P, 128), 128, 0, st>>>(x1t, P, start1, n1, res, scale2, i0, len1, w1, sw1);
+  dec_band_sw_kernel<<<cnp_cdiv(Q, 128), 128, 0, st>>>(x2t, Q, start2, n2, res, scale2, j0, len2, w2, sw2);
+  fold_final_kernel<<<64, FZ_IN, 0, st>>>(p->W[0], Wf, bfin, Ca, W0f);
+  CNP_LAUNCH_CHECK("dec_band_sw_kernel");
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h->base) + (size_t)h->cb_off * (n1 + 4) * (n2 + 4) * 8;
+  dim3 gc(cnp_cdiv(Q, 32), n1, B);
+  dec_cols_blk_kernel<<<gc, 256, 0, st>>>(hp, h->bstride, n1, n2, Q, j0, len2, w2, T);
+  CNP_LAUNCH_CHECK("dec_cols_blk_kernel");
+  const int L = p->n_layers;
+  const size_t smem = (size_t)(GP_H * FZ_IN + GP_H + (L - 2) * (GP_H * GP_H + GP_H) + 2 * GP_H + 4 + GP_H * 256) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(dec_grid_mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const long long nb = ((long long)P * Q + 255) / 256;
+  dim3 grid((unsigned)(nb < 2 * sms ? nb : 2 * sms), B);
+  dec_grid_mlp_fused_kernel<<<grid, 256, smem, st>>>(*p, W0f, T, n1, P, Q, i0, len1, w1, sw1, sw2, aux, aux_bstride, Ca,
+                                                     mean, stdv);
+  CNP_LAUNCH_CHECK("dec_grid_mlp_fused_kernel");
   return 0;
 }

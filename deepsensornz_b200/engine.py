@@ -207,10 +207,19 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # host -> device
     # ------------------------------------------------------------------------------------------
-    def stage_host(self, contexts, xt, yt, aux_t, pinned: bool = False) -> "HostBatch":
+    def stage_host(self, contexts, xt, yt, aux_t, pinned: bool = False, ctx_cache: Optional[dict] = None) -> "HostBatch":
         """contexts: list of (x, y, mask|None) numpy/torch CPU arrays with a leading batch axis.
         NaNs may stay in ``y`` (the kernels derive validity on the fly).  Returns float32 contiguous
-        CPU tensors (page-locked when ``pinned``) plus the host-side discretisation."""
+        CPU tensors (page-locked when ``pinned``) plus the host-side discretisation.
+
+        ``ctx_cache`` (predict over many tasks): gridded context sets whose arrays are the same host buffers as in an
+        earlier task (static topography / land mask) are uploaded once and their device copy -- with its band tables
+        hint -- is reused; keyed on (data pointer, shape) of x, y and mask."""
+        def bufkey(a):
+            if a is None:
+                return None
+            a = np.asarray(a)
+            return (a.__array_interface__["data"][0], a.shape, a.strides, str(a.dtype))
         def host(a):
             return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
 
@@ -237,6 +246,12 @@ class Engine:
             xt_h = None
         hctx = []
         for (x, y, m), xh in zip(contexts, xs[:-1]):
+            key = None
+            if ctx_cache is not None and isinstance(x, tuple) and not isinstance(y, torch.Tensor):
+                key = (bufkey(x[0]), bufkey(x[1]), bufkey(y), bufkey(m))
+                if key in ctx_cache:
+                    hctx.append(ctx_cache[key])
+                    continue
             if isinstance(x, tuple):
                 x1h, x2h = xh
                 x1h = x1h.reshape(x1h.shape[0], -1)
@@ -254,8 +269,16 @@ class Engine:
                     mh is None or all(np.array_equal(mh[0], mh[i]) for i in range(1, mh.shape[0])))
                 if y_shared:
                     y, m = yh[:1], (None if mh is None else mh[:1])
-                hctx.append(DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h),
-                                          y_batched=not y_shared))
+                hc = DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h),
+                                   y_batched=not y_shared)
+                if key is not None:       # keep the DEVICE copy: later tasks skip staging and H2D of this set
+                    self._require_cuda()
+                    dev = self.device
+                    up1 = lambda t: None if t is None else t.to(dev, non_blocking=True)
+                    hc = DeviceContext(True, tuple(up1(v) for v in hc.x), up1(hc.y), up1(hc.mask), hc.mono, hc.x_batched,
+                                       hc.x_host, hc.band_cache, hc.y_batched)
+                    ctx_cache[key] = hc
+                hctx.append(hc)
             else:
                 hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))
         return HostBatch(hctx, xt_h if xt_h is not None else cpu(xt), cpu(yt), cpu(aux_t), grid, B)
@@ -763,10 +786,12 @@ class Engine:
         if self.precision == "fp32":
             z, A = self._unet_fwd_f32(enc, B, g.n1, g.n2)
         else:
-            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=on_grid)
+            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=False)
         Cz = cfg.unet_out_channels
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
         if on_grid:
+            if z is None:
+                return self._decode_grid_fused(batch, A["h_last"], s2)
             return self._decode_grid(batch, z, s2)
         f = self._buf("f", (B, Cz, Nt))
         if z is None:
@@ -815,6 +840,30 @@ class Engine:
         self._call("cnp_mlp_head_points_fwd", C.byref(p), _ptr(f), f.stride(0), Cz, _ptr(aux), aux_bs, Ca, B, P * Q,
                    _ptr(mean), _ptr(std), _stream(), work=(2.0 * B * P * Q * sum(
                        a * b for a, b in zip(self.module.mlp_dims()[:-1], self.module.mlp_dims()[1:])), 0.0))
+        return dict(mean=mean, std=std, var=None, logp=None, count=None, ctx=None)
+
+    def _decode_grid_fused(self, batch: DeviceBatch, h_last: _Blk, s2: float):
+        """bf16 mode, on-grid targets: SetConv of the last hidden activation + final 1x1 folded into the MLP + head in
+        two kernels (decode_grid.cu); the 64 x P x Q decoder output is never materialised."""
+        cfg, g, B = self.cfg, batch.grid, batch.B
+        x1t, x2t = batch.xt
+        P, Q, Ca = int(x1t.shape[-1]), int(x2t.shape[-1]), cfg.dim_aux_t
+        aux = batch.aux_t
+        if aux is None or aux.shape[-3] != Ca or tuple(aux.shape[-2:]) != (P, Q):
+            raise ValueError(f"on-grid prediction needs Y_t_aux of shape [{Ca},{P},{Q}]")
+        aux = aux.reshape(-1, Ca, P, Q)
+        aux_bs = 0 if aux.shape[0] == 1 else aux.stride(0)
+        wsb = _cabi.lib().cnp_decode_grid_fused_workspace_bytes(B, g.n1, P, Q)
+        ws = self._buf("dec_fused_ws", ((wsb + 3) // 4,))
+        mean = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
+        std = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
+        fin = self.module.decoder.unet.final_linear
+        p = self._mlp_params()
+        dims = self.module.mlp_dims()
+        flops = 2.0 * B * P * Q * (sum(a * b for a, b in zip(dims[:-1], dims[1:])) + 64 * 30)
+        self._call("cnp_decode_grid_fused_fwd", C.byref(h_last.view(0)), _ptr(x1t), _ptr(x2t), B, P, Q, g.start1, g.start2,
+                   g.res, s2, _ptr(fin.weight), _ptr(fin.bias), C.byref(p), _ptr(aux), aux_bs, Ca, _ptr(mean), _ptr(std),
+                   _ptr(ws), wsb, _stream(), work=(flops, 4.0 * B * P * Q * (Ca + 2) + 2.0 * B * 64 * g.n1 * g.n2))
         return dict(mean=mean, std=std, var=None, logp=None, count=None, ctx=None)
 
     def backward(self, batch: DeviceBatch, ctx: dict, dlogp: torch.Tensor) -> Dict[str, torch.Tensor]:

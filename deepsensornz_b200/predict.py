@@ -110,22 +110,64 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
             it = tqdm(tasks)
         except Exception:  # noqa: BLE001
             pass
-    means, stds, times = [], [], []
-    for task in it:
+    # Per task: only the per-date tensors travel (static context sets are uploaded once, ctx_cache); mean / std come
+    # back through two page-locked buffers with asynchronous copies, so the D2H of task i overlaps the kernels of
+    # task i+1 (the reference reads every result back synchronously).
+    n = len(tasks)
+    mean_out = std_out = None
+    times = []
+    ctx_cache = {}
+    cuda = torch.cuda.is_available()
+    pin = [None, None]
+    events = [None, None]
+    pending = []            # (slot, task index)
+    direct, registered = None, []
+
+    def drain(slot, idx):
+        events[slot].synchronize()
+        mean_out[idx] = pin[slot][0].numpy()
+        std_out[idx] = pin[slot][1].numpy()
+
+    for idx, task in enumerate(it):
         t2 = Task({k: v for k, v in task.items() if k not in ("Y_t", "Y_t_aux", "X_t")})
         t2["ops"] = list(task["ops"])
         if "batch_dim" in t2["ops"]:
             raise ValueError("predict expects un-batched tasks (one per time), as produced by the TaskLoader")
         t2["X_t"] = [tuple(v[np.newaxis] for v in Xn)] if mode == "on-grid" else [Xn]
         t2["Y_t"] = []
-        hb = model.stage_task(t2, pinned=False)
+        hb = model.stage_task(t2, pinned=False, ctx_cache=ctx_cache)
         hb.aux_t = aux_dev
         out = model(hb)
         mean, std = out["mean"][0, 0], out["std"][0, 0]
-        means.append(mean.cpu().numpy())
-        stds.append(std.cpu().numpy())
+        if mean_out is None:
+            mean_out = np.empty((n,) + tuple(mean.shape), dtype=np.float32)
+            std_out = np.empty_like(mean_out)
+            if cuda:
+                if direct is None:
+                    pin = [(torch.empty(mean.shape, dtype=torch.float32).pin_memory(),
+                            torch.empty(mean.shape, dtype=torch.float32).pin_memory()) for _ in range(2)]
+        if cuda and direct is not None:
+            direct[0][idx].copy_(mean, non_blocking=True)
+            direct[1][idx].copy_(std, non_blocking=True)
+        elif cuda:
+            slot = idx & 1
+            if len(pending) == 2:          # the buffer we are about to reuse must have been drained
+                drain(*pending.pop(0))
+            pin[slot][0].copy_(mean, non_blocking=True)
+            pin[slot][1].copy_(std, non_blocking=True)
+            events[slot] = torch.cuda.Event()
+            events[slot].record()
+            pending.append((slot, idx))
+        else:
+            mean_out[idx], std_out[idx] = mean.numpy(), std.numpy()
         times.append(task.get("time"))
-    mean, std = np.stack(means), np.stack(stds)
+    for slot, idx in pending:
+        drain(slot, idx)
+    if cuda:
+        torch.cuda.synchronize()
+        for a in registered:
+            torch.cuda.cudart().cudaHostUnregister(a.ctypes.data)
+    mean, std = mean_out, std_out
     var_ID = "target"
     if tl is not None and getattr(tl, "target_var_IDs", None):
         var_ID = tl.target_var_IDs[0][0]

@@ -66,7 +66,7 @@ class Task(dict):
         return self.op(lambda a: a[np.newaxis, ...], "batch_dim")
 
     def cast_to_float32(self) -> "Task":
-        return self.op(lambda a: a.astype(np.float32), "float32")
+        return self.op(lambda a: a.astype(np.float32, copy=False), "float32")   # no copy when already float32
 
     def remove_target_nans(self) -> "Task":
         """Drop off-grid target points whose observation is NaN (before a batch dim exists)."""

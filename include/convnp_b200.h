@@ -163,6 +163,17 @@ int cnp_setconv_dec_grid_fwd(const float* z, long long z_bstride, const float* x
                              float scale2, float* f /*[B,C,P,Q]*/, long long f_bstride, void* workspace,
                              long long workspace_bytes, cnp_stream_t s);
 
+/* Fused on-grid inference decoder on the blocked bf16 hidden activation h (64 ch): SetConv of h (column pass to a
+ * bf16 workspace, row pass in registers), final 1x1 (Wf [64][64], bf) folded into MLP layer 0, MLP, Gaussian head.
+ * The 64 x P x Q decoder output is never materialised.  p: dims[0] = 64 + Ca, hidden width 64, >= 2 hidden layers. */
+long long cnp_decode_grid_fused_workspace_bytes(int B, int n1, int P, int Q);
+struct cnp_mlp_params;
+int cnp_decode_grid_fused_fwd(const cnp_blk* h, const float* x1t /*[P]*/, const float* x2t /*[Q]*/, int B, int P, int Q,
+                              double start1, double start2, double res, float scale2, const float* Wf, const float* bf,
+                              const struct cnp_mlp_params* p, const float* aux /*[B or 1,Ca,P,Q]*/, long long aux_bstride,
+                              int Ca, float* mean /*[B,P,Q]*/, float* stdv, void* workspace, long long workspace_bytes,
+                              cnp_stream_t s);
+
 /* ---- (4) aux-at-target MLP + heteroscedastic Gaussian head + normalised NLL -----------------------
  * replaces: neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood -> MultiOutputNormal.logpdf
  * -> nps.loglik (A.6, A.7) reached from ConvNP.loss_fn (train.py:370).  logp is float64. */
