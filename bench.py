@@ -39,11 +39,12 @@ DIM_YC = (3, 6, 1, 1)
 N_STATIONS, CTX_FRAC = 200, 0.8
 
 
-def model_kwargs():
+def model_kwargs(ppu=None):
+    ppu = ppu or PPU
     n_lo = 140
     s_lo = 0.5 * (0.99643 - 0.00357) / (n_lo - 1)
-    return dict(dim_yc=DIM_YC, dim_yt=1, dim_aux_t=5, internal_density=PPU,
-                encoder_scales=(s_lo, s_lo, 0.5 / 1399.0, 0.5 / PPU), decoder_scale=1.0 / PPU,
+    return dict(dim_yc=DIM_YC, dim_yt=1, dim_aux_t=5, internal_density=ppu,
+                encoder_scales=(s_lo, s_lo, 0.5 / 1399.0, 0.5 / ppu), decoder_scale=1.0 / ppu,
                 unet_channels=(64,) * 4, verbose=False)
 
 
@@ -172,7 +173,8 @@ def run_reference(args):
 def workload_config(n_gpus: int, precision: str, grid=None):
     cfg = {"workload": "configs[1]: ConvNP training step, batch of 16 synthetic daily NZ tasks "
                        "(ERA5-shaped 140x140 + 6-ch aux + 1400x1400 land mask + 160 context / 40 target stations)",
-           "global_batch": BATCH * max(n_gpus, 1), "per_gpu_batch": BATCH, "internal_density": PPU,
+           "global_batch": BATCH * max(n_gpus, 1), "per_gpu_batch": BATCH,
+           "internal_density": int(round(1.0 / grid.res)) if grid is not None else PPU,
            "unet_channels": [64, 64, 64, 64], "precision": precision,
            "parallelism": f"dp{max(n_gpus, 1)}", "l2": "per-step working set (>3 GB) exceeds the 126 MB L2",
            "static_context_dedup": "context sets that are bit-identical across the 16 tasks of a batch (topography aux, "
@@ -196,7 +198,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.manual_seed(0)
-    model = ConvNP(precision=args.precision, **model_kwargs())
+    model = ConvNP(precision=args.precision, **model_kwargs(args.internal_density))
     if world > 1:
         from deepsensornz_b200.dist import enable_data_parallel
         enable_data_parallel(model)
@@ -328,6 +330,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--internal-density", type=int, default=PPU,
+                    help="points per unit of the internal grid: 250 (saved models, 304^2 grid) or 500 (repo default, 608^2)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

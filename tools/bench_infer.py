@@ -32,6 +32,16 @@ def main():
     dt = time.perf_counter() - t0
     key = list(pred.keys())[0]
     mean = np.asarray(pred[key]["mean"])
+    if os.environ.get("CNP_PROFILE_HOST"):
+        import cProfile, pstats, io
+        pr = cProfile.Profile()
+        pr.enable()
+        model.predict(tasks, X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
+        torch.cuda.synchronize()
+        pr.disable()
+        st = io.StringIO()
+        pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(28)
+        print(st.getvalue()[:6000])
     # per-kernel profile of one task
     eng.profile_start()
     model.predict(tasks[:1], X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
