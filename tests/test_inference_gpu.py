@@ -111,3 +111,47 @@ def test_dec_blk_kernels_match_materialised_path():
     _cabi.call("cnp_blk_to_nchw_f32", C.byref(dh.view()), B, 64, out.data_ptr(), out.stride(0), _S())
     ref = hd.grad * (h > 0)          # ReLU mask of the producing layer fused into the kernel
     assert rel_err(out, ref) < 1e-2   # bf16 output rounding
+
+
+def test_predict_off_grid_targets(static):
+    """predict onto station locations (validate.py-style off-grid X_t): [2,N] normalised coordinates."""
+    tasks = [make_task(static, 950 + i, all_context=True) for i in range(2)]
+    m = small_model("fp32")
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0.1, 0.9, (2, 23)).astype(np.float32)
+    aux = rng.uniform(-1, 1, (5, 23)).astype(np.float32)
+    pred = m.predict(tasks, X_t=X, X_t_is_normalised=True, aux_at_targets_override=aux)
+    df = pred[list(pred.keys())[0]]
+    assert len(df) == 2 * 23 and np.isfinite(df["mean"].values).all() and (df["std"].values > 0).all()
+    t = Task({k: v for k, v in tasks[0].items()})
+    t["X_t"], t["Y_t"], t["Y_t_aux"] = [X], [], aux
+    ctx, xt, _, aux_t = oracle_inputs(t)
+    mean_o, var_o = O.forward(cpu_params(m), ctx, xt, aux_t, m.config.points_per_unit)
+    assert rel_err(df["mean"].values[:23], mean_o[0, 0]) < 1e-5
+    assert rel_err(df["std"].values[:23], var_o[0, 0].sqrt()) < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_multivariable_ragged_batch_matches_oracle(static, precision, tol):
+    """configs[3] shape: 8-channel base context (Cin = 20), tasks with different numbers of context stations padded by
+    concat_tasks (masks), loss and gradients vs the oracle."""
+    from deepsensornz_b200 import concat_tasks
+    tasks = []
+    for i, nst in enumerate((60, 52, 57)):
+        t = make_task(static, 1200 + i, n_stations=nst, context_frac=1.0 - 12.0 / nst, c0_channels=8)
+        tasks.append(t)
+    assert len({t["X_t"][0].shape[-1] for t in tasks}) == 1          # equal targets, ragged contexts
+    task = concat_tasks(tasks)
+    m = small_model(precision, dim_yc=(8, 6, 1, 1))
+    loss = m.loss_fn(task, normalise=True)
+    loss.backward()
+    ctx, xt, yt, aux = oracle_inputs(task)
+    P = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in cpu_params(m).items()}
+    ref = O.loss_fn(P, ctx, xt, yt, aux, m.config.points_per_unit)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < tol
+    for n, p in m.model.named_parameters():
+        if p.requires_grad and P[n].grad is not None:
+            g, r = p.grad.detach().cpu().double().flatten(), P[n].grad.double().flatten()
+            cos = float((g @ r) / (g.norm() * r.norm()).clamp(min=1e-300))
+            assert cos > (0.9999 if precision == "fp32" else 0.99), (n, cos)
