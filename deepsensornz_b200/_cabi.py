@@ -96,6 +96,9 @@ _SIGS = {
     "cnp_decode_grid_fused_workspace_bytes": (_ll, [_i, _i, _i, _i]),
     "cnp_decode_grid_fused_fwd": (C.c_int, [C.POINTER(CnpBlk), c_fp, c_fp, _i, _i, _i, _d, _d, _d, _f, c_fp, c_fp,
                                             C.POINTER(CnpMlpParams), c_fp, _ll, _i, c_fp, c_fp, c_fp, _ll, c_stream]),
+    "cnp_decode_grid_tc_workspace_bytes": (_ll, [_i, _i, _i, _i]),
+    "cnp_decode_grid_tc_fwd": (C.c_int, [C.POINTER(CnpBlk), c_fp, c_fp, _i, _i, _i, _d, _d, _d, _f, c_fp, c_fp,
+                                         C.POINTER(CnpMlpParams), c_fp, _ll, _i, c_fp, c_fp, c_fp, _ll, c_stream]),
     # (4) MLP + Gaussian head + NLL
     "cnp_mlp_head_fwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp,
                                    c_fp, c_stream]),

@@ -428,19 +428,33 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
 constexpr int IW_PX = 256;
 constexpr int IW_MAXCI = 32;   // input channels incl. the constant-1 slot that carries the bias gradient
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;   // src-size 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int NH>   // NH = number of 16-channel halves of x in use
 __global__ void __launch_bounds__(256)
 conv1x1_in_wgrad_kernel(const float* __restrict__ x, long long x_bs, int Cin, int H, int W,
                         const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int B,
                         float* __restrict__ dw, float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t iw_smem[];
-  __nv_bfloat16 (*dy_s)[64] = reinterpret_cast<__nv_bfloat16 (*)[64]>(iw_smem);                       // [IW_PX][64], 32 KB
-  float (*x_s)[16 * NH] = reinterpret_cast<float (*)[16 * NH]>(iw_smem + IW_PX * 64 * 2);            // [IW_PX][16 NH]
   constexpr int NCI = 16 * NH;
+  constexpr int STAGE_B = IW_PX * 64 * 2 + IW_PX * NCI * 4;     // dy tile (bf16) + x tile (fp32), two stages (LDGSTS)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int co8 = lane >> 2, ci4 = lane & 3;
   const int HW = H * W, Hp = H + 4, Wp = W + 4;
   const int tiles_per_img = (HW + IW_PX - 1) / IW_PX;
+  const int ntiles = B * tiles_per_img;
   const int one_slot = NCI - 1;                 // x channel holding the constant 1 (Cin < NCI is guaranteed)
   float acc[NH][8][4];
 #pragma unroll
@@ -449,25 +463,33 @@ conv1x1_in_wgrad_kernel(const float* __restrict__ x, long long x_bs, int Cin, in
     for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[hh][a][c] = 0.f;
-  for (int t = blockIdx.x; t < B * tiles_per_img; t += gridDim.x) {
+
+  auto issue = [&](int t, int stage) {
+    __nv_bfloat16 (*dy_s)[64] = reinterpret_cast<__nv_bfloat16 (*)[64]>(iw_smem + stage * STAGE_B);
+    float (*x_s)[NCI] = reinterpret_cast<float (*)[NCI]>(iw_smem + stage * STAGE_B + IW_PX * 64 * 2);
     const int b = t / tiles_per_img, e0 = (t % tiles_per_img) * IW_PX;
-    __syncthreads();
     for (int e = threadIdx.x; e < IW_PX * 8; e += 256) {
       const int px = e & (IW_PX - 1), chunk = e >> 8, pe = e0 + px;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (pe < HW) {
-        const int yy = pe / W, xx = pe - yy * W;
-        v = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)b * dy_bs + (((size_t)(dy_cb + chunk) * Hp + yy + 2) * Wp + xx + 2) * 8));
-      }
-      *reinterpret_cast<uint4*>(&dy_s[px][chunk * 8]) = v;
+      const bool ok = pe < HW;
+      const int yy = ok ? pe / W : 0, xx = ok ? pe - yy * W : 0;
+      cp_async16(&dy_s[px][chunk * 8], dy + (size_t)b * dy_bs + (((size_t)(dy_cb + chunk) * Hp + yy + 2) * Wp + xx + 2) * 8, ok);
     }
     for (int e = threadIdx.x; e < NCI * IW_PX; e += 256) {
       const int ci = e >> 8, px = e & (IW_PX - 1), pe = e0 + px;
-      float v = 0.f;
-      if (pe < HW) v = ci < Cin ? __ldg(x + (size_t)b * x_bs + (size_t)ci * HW + pe) : (ci == one_slot ? 1.f : 0.f);
-      x_s[px][ci] = v;
+      if (ci < Cin) cp_async4(&x_s[px][ci], x + (size_t)b * x_bs + (size_t)ci * HW + (pe < HW ? pe : 0), pe < HW);
+      else x_s[px][ci] = (ci == one_slot && pe < HW) ? 1.f : 0.f;
     }
+    cp_async_commit();
+  };
+
+  int stage = 0;
+  if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, stage ^= 1) {
+    const int tn = t + gridDim.x;
+    if (tn < ntiles) { issue(tn, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
+    const __nv_bfloat16 (*dy_s)[64] = reinterpret_cast<const __nv_bfloat16 (*)[64]>(iw_smem + stage * STAGE_B);
+    const float (*x_s)[NCI] = reinterpret_cast<const float (*)[NCI]>(iw_smem + stage * STAGE_B + IW_PX * 64 * 2);
 #pragma unroll 2
     for (int px = warp; px < IW_PX; px += 8) {
       const uint4 g = *reinterpret_cast<const uint4*>(&dy_s[px][co8 * 8]);
@@ -485,8 +507,9 @@ conv1x1_in_wgrad_kernel(const float* __restrict__ x, long long x_bs, int Cin, in
         }
       }
     }
+    __syncthreads();   // the stage just consumed is refilled by the next iteration's issue()
   }
-  // reduce the 8 warps through shared memory ([8][64][16] floats = 32 KB per half, aliasing dy_s), one atomic per output
+  // reduce the 8 warps through shared memory ([8][64][16] floats = 32 KB per half), one atomic per output
   float* red = reinterpret_cast<float*>(iw_smem);
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh) {
@@ -585,17 +608,27 @@ blk_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs,
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
-    // the zero pad of dy (2 pixels) makes the out-of-range taps (weight 0) safe to read
+    // the zero pad of dy (2 pixels) makes the out-of-range taps (weight 0) safe to read.  All 16 loads are issued
+    // before any arithmetic (16 independent 16 B loads in flight per thread).
+    uint4 raw[4][4];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx)
+        raw[ky][kx] = __ldg(reinterpret_cast<const uint4*>(dyc + ((size_t)(2 * u - 1 + ky + 2) * W2p + (2 * v - 1 + kx) + 2) * 8));
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
-      const int Y = 2 * u - 1 + ky;
-      float g[4][8];
 #pragma unroll
-      for (int kx = 0; kx < 4; ++kx) ld8(dyc + ((size_t)(Y + 2) * W2p + (2 * v - 1 + kx) + 2) * 8, g[kx]);
+      for (int h2 = 0; h2 < 4; ++h2) {   // 4 bf16 pairs = 8 channels
+        float hx = 0.f, hy = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float hsum = wx[0] * g[0][i] + wx[1] * g[1][i] + wx[2] * g[2][i] + wx[3] * g[3][i];
-        s[i] = fmaf(wy[ky], hsum, s[i]);
+        for (int kx = 0; kx < 4; ++kx) {
+          const __nv_bfloat162 pr = reinterpret_cast<const __nv_bfloat162*>(&raw[ky][kx])[h2];
+          const float2 f2 = __bfloat1622float2(pr);
+          hx = fmaf(wx[kx], f2.x, hx); hy = fmaf(wx[kx], f2.y, hy);
+        }
+        s[2 * h2] = fmaf(wy[ky], hx, s[2 * h2]);
+        s[2 * h2 + 1] = fmaf(wy[ky], hy, s[2 * h2 + 1]);
       }
     }
     const size_t pix = ((size_t)(u + 2) * Wp + v + 2) * 8;
@@ -878,10 +911,11 @@ CNP_API int cnp_conv1x1_in_wgrad(const float* x, long long x_bstride, int Cin, c
                                  float* dbias, cudaStream_t st) {
   CNP_REQUIRE(x && dy && dw && B > 0 && Cin >= 1 && Cin < IW_MAXCI, "conv1x1_in_wgrad: need Cin < %d", IW_MAXCI);
   const int nh = Cin < 16 ? 1 : 2;
-  const size_t smem = (size_t)IW_PX * 64 * 2 + (size_t)IW_PX * 16 * nh * 4;
+  const size_t smem = 2 * ((size_t)IW_PX * 64 * 2 + (size_t)IW_PX * 16 * nh * 4);   // two stages
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(conv1x1_in_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, IW_PX * 64 * 2 + IW_PX * 32 * 4);
+    cudaFuncSetAttribute(conv1x1_in_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (IW_PX * 64 * 2 + IW_PX * 16 * 4));
+    cudaFuncSetAttribute(conv1x1_in_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (IW_PX * 64 * 2 + IW_PX * 32 * 4));
     attr = true;
   }
   const int tiles = B * cnp_cdiv(dy->H * dy->W, IW_PX);

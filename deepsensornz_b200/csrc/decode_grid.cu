@@ -444,3 +444,308 @@ CNP_API int cnp_decode_grid_fused_fwd(const cnp_blk* h, const float* x1t, const 
   CNP_LAUNCH_CHECK("dec_grid_mlp_fused_kernel");
   return 0;
 }
+
+// =============================================================================================
+// Tensor-core inference decoder tail (bf16 mode).  For a tile of 128 consecutive target columns q of one target
+// row p everything after the row pass is a chain of small GEMMs with the 128 pixels as M:
+//     g   [128 x 64]  = W2band [128 q x 64 j]  x  T'[p] [64 j x 64 c]        SetConv column pass (W2 split hi + lo bf16)
+//     a1  = relu(W0'' [g ; aux ; sw] + b0)    a2 = relu(W1 a1 + b1)    a3 = relu(W2 a2 + b2)      tcgen05, K = 80 / 64
+//     mean, std from the 64 -> 2 head in registers
+// where T'[b][p][chunk][j][8] (bf16) is the ROW pass of the hidden activation (dec_rows_blk_kernel).  A CTA owns one
+// q tile (its W2band and the MLP weights stay in shared memory) and a segment of target rows; its 16 warps form 4
+// independent "lanes" of 4 warps (one TMEM lane quadrant each, thread = pixel) that walk the rows p = lane, lane+4, ...:
+// each lane issues its own MMAs (one elected thread), waits for them on its own mbarrier, reads the accumulator with
+// tcgen05.ld, applies bias / ReLU, writes the next bf16 A operand back to its shared-memory buffer and repeats -- the
+// tensor pipe is shared by the 4 lanes, so while one lane is in an epilogue the others' MMAs run.
+// =============================================================================================
+namespace {
+
+constexpr int TCD_LANES = 4;
+constexpr int TCD_KIN = 80;                 // layer-0 K: 64 (g) + 8 (aux, sw, pad) + 8 (pad)
+constexpr int TCD_ABUF = 10 * 2048;         // [k8 (10)][px (128)][8] bf16
+constexpr int TCD_TT = 8 * 1024;            // [chunk (8)][j (64)][8] bf16
+// shared-memory map (bytes)
+constexpr int TCD_OFF_WG = 0;                                   // hi, lo: 2 x [k8 (8)][q (128)][8] bf16
+constexpr int TCD_OFF_W0 = TCD_OFF_WG + 2 * 16384;              // [k8 (10)][n (64)][8] bf16
+constexpr int TCD_OFF_W1 = TCD_OFF_W0 + 10 * 1024;
+constexpr int TCD_OFF_W2 = TCD_OFF_W1 + 8 * 1024;
+constexpr int TCD_OFF_F32 = TCD_OFF_W2 + 8 * 1024;              // b0,b1,b2 [64] each, wl [2][64], bl [2] (+pad) fp32
+constexpr int TCD_OFF_LANE = TCD_OFF_F32 + (3 * 64 + 128 + 8) * 4;
+constexpr int TCD_LANE_BYTES = TCD_ABUF + 2 * TCD_TT;
+constexpr int TCD_OFF_BAR = TCD_OFF_LANE + TCD_LANES * TCD_LANE_BYTES;
+constexpr int TCD_SMEM = TCD_OFF_BAR + TCD_LANES * 3 * 8 + 16;
+
+// row pass on the blocked layout: T'[b][p][chunk][j][8] = sum_k w1[k][p] h[b][chunk][i0[p]+k][j][8]
+__global__ void __launch_bounds__(256)
+dec_rows_blk_kernel(const __nv_bfloat16* __restrict__ h, long long h_bs, int H, int W, int P,
+                    const int* __restrict__ i0, const int* __restrict__ len, const float* __restrict__ w1,
+                    __nv_bfloat16* __restrict__ T) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31), chunk = threadIdx.x >> 5, p = blockIdx.y, b = blockIdx.z;
+  if (j >= W) return;
+  const int Wp = W + 4;
+  const int s = i0[p], L = len[p];
+  const __nv_bfloat16* src = h + (size_t)b * h_bs + (((size_t)chunk * (H + 4) + s + 2) * Wp + j + 2) * 8;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int k = 0; k < L; ++k) {
+    const float wv = __ldg(w1 + (size_t)k * P + p);
+    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(src + (size_t)k * Wp * 8));
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float2 f2 = __bfloat1622float2(p2[c]);
+      acc[2 * c] = fmaf(wv, f2.x, acc[2 * c]); acc[2 * c + 1] = fmaf(wv, f2.y, acc[2 * c + 1]);
+    }
+  }
+  uint4 o;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) o2[c] = __floats2bfloat162_rn(acc[2 * c], acc[2 * c + 1]);
+  *reinterpret_cast<uint4*>(T + ((((size_t)b * P + p) * 8 + chunk) * W + j) * 8) = o;
+}
+
+__device__ __forceinline__ void tcd_lane_bar(int lane_id) {   // named barrier of the 128 threads of one lane
+  asm volatile("bar.sync %0, 128;" ::"r"(lane_id + 1) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// store 64 fp32 values of one pixel as bf16 into chunks 0..7 of a K-major A buffer
+__device__ __forceinline__ void tcd_store_act(uint8_t* abuf, int px, const float* v) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 pk;
+    __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(v[c * 8 + 2 * i], v[c * 8 + 2 * i + 1]);
+    *reinterpret_cast<uint4*>(abuf + c * 2048 + px * 16) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(128 * TCD_LANES, 1)
+dec_tc_kernel(cnp_mlp_params mp, const float* __restrict__ W0f /*[64][FZ_IN] folded*/, const __nv_bfloat16* __restrict__ T,
+              int n2, int P, int Q, const float* __restrict__ x2t, double start2, double res, float scale2,
+              const int* __restrict__ j0tab, const float* __restrict__ sw1, const float* __restrict__ sw2,
+              const float* __restrict__ aux, long long aux_bs, int Ca, float* __restrict__ mean, float* __restrict__ stdv,
+              int rows_per_cta) {
+  extern __shared__ __align__(128) uint8_t tsm[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ln = warp >> 2;                    // lane (group of 4 warps)
+  const int px = tid & 127;                    // pixel of this thread inside the q tile = TMEM lane
+  const int q0 = blockIdx.x * 128, b = blockIdx.z;
+  const int p_begin = blockIdx.y * rows_per_cta, p_end = min(P, p_begin + rows_per_cta);
+  float* f32 = reinterpret_cast<float*>(tsm + TCD_OFF_F32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tsm + TCD_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tsm + TCD_OFF_BAR + TCD_LANES * 3 * 8);
+  // band start of this q tile (all 128 columns must fit in 64 grid columns; checked by the host wrapper's caller)
+  int jlo = min(j0tab[min(q0, Q - 1)], j0tab[min(q0 + 127, Q - 1)]);   // ascending or descending target coordinates
+  jlo = max(0, min(jlo, n2 - 64));
+  // ---- one-time setup: W2 band (hi/lo), MLP weights as bf16 B operands, biases ----
+  for (int e = tid; e < 128 * 64; e += 128 * TCD_LANES) {
+    const int q = e >> 6, j = e & 63;
+    const float xq = x2t[min(q0 + q, Q - 1)];
+    const float w = (q0 + q < Q) ? cnp_rbf(xq, cnp_grid_pt(start2, res, jlo + j), scale2) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    const int off = (j >> 3) * 2048 + q * 16 + (j & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(tsm + TCD_OFF_WG + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(tsm + TCD_OFF_WG + 16384 + off) = lo;
+  }
+  for (int e = tid; e < 64 * TCD_KIN; e += 128 * TCD_LANES) {
+    const int n = e / TCD_KIN, k = e % TCD_KIN;
+    const float v = k < FZ_IN ? W0f[(size_t)n * FZ_IN + k] : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(tsm + TCD_OFF_W0 + (k >> 3) * 1024 + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  for (int e = tid; e < 64 * 64; e += 128 * TCD_LANES) {
+    const int n = e >> 6, k = e & 63;
+    *reinterpret_cast<__nv_bfloat16*>(tsm + TCD_OFF_W1 + (k >> 3) * 1024 + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(mp.W[1][e]);
+    *reinterpret_cast<__nv_bfloat16*>(tsm + TCD_OFF_W2 + (k >> 3) * 1024 + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(mp.W[2][e]);
+  }
+  if (tid < 64) { f32[tid] = mp.b[0][tid]; f32[64 + tid] = mp.b[1][tid]; f32[128 + tid] = mp.b[2][tid]; }
+  if (tid < 128) f32[192 + tid] = mp.W[3][tid];
+  if (tid < 2) f32[320 + tid] = mp.b[3][tid];
+  uint8_t* lane_base = tsm + TCD_OFF_LANE + ln * TCD_LANE_BYTES;
+  uint8_t* abuf = lane_base;
+  uint8_t* tt = lane_base + TCD_ABUF;          // two T' tile buffers
+  // chunks 8 and 9 of the A buffer (aux / sw / zero pad): zero once, chunk 8 is rewritten per tile
+  *reinterpret_cast<uint4*>(abuf + 8 * 2048 + px * 16) = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<uint4*>(abuf + 9 * 2048 + px * 16) = make_uint4(0, 0, 0, 0);
+  uint64_t* tile_full = bars + ln * 3;         // [2]
+  uint64_t* mma_done = bars + ln * 3 + 2;
+  if ((tid & 127) == 0) { tc::mbar_init(tile_full, 1); tc::mbar_init(tile_full + 1, 1); tc::mbar_init(mma_done, 1); tc::mbar_fence_init(); }
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot + ln * 128;                         // two 64-column accumulators per lane
+  const uint32_t tl = ((uint32_t)((warp & 3) * 32)) << 16;             // this warp's TMEM lane quadrant
+  const bool leader = (tid & 127) == 0;
+  const uint32_t idesc_g = tc::make_idesc_bf16(128, 64, 0, 1);         // A K-major (W2 band), B MN-major (T' tile)
+  const uint32_t idesc_m = tc::make_idesc_bf16(128, 64, 0, 0);         // A K-major (activations), B K-major (weights)
+  const uint32_t hiA = (128u >> 4) | (1u << 14);                       // A: SBO 128 B
+  const uint32_t lboA = (2048u >> 4) << 16;                            // A: LBO 2048 B (k8 planes)
+  const uint32_t hiW = (128u >> 4) | (1u << 14), lboW = (1024u >> 4) << 16;   // weights: LBO 1024, SBO 128
+  const uint32_t hiT = (1024u >> 4) | (1u << 14), lboT = (128u >> 4) << 16;   // T' tile (MN-major): SBO 1024 (chunk), LBO 128
+  const size_t npts = (size_t)P * Q;
+  const float* ab = aux + (size_t)b * aux_bs;
+  const __nv_bfloat16* Tb = T + (size_t)b * P * 8 * n2 * 8;
+  const int q = q0 + px;
+  const bool q_ok = q < Q;
+  const float swq = q_ok ? sw2[q] : 0.f;
+  uint32_t mma_phase = 0;
+
+  auto load_tile = [&](int p, int buf) {       // leader only: 8 chunk rows of 64 grid columns (1 KB each)
+    tc::mbar_expect_tx(tile_full + buf, 8u * 1024u);
+    const __nv_bfloat16* src = Tb + (((size_t)p * 8) * n2 + jlo) * 8;
+    for (int c = 0; c < 8; ++c)
+      tc::bulk_g2s(tt + buf * TCD_TT + c * 1024, src + (size_t)c * n2 * 8, 1024u, tile_full + buf);
+  };
+  auto wait_mma = [&]() {
+    tc::mbar_wait(mma_done, mma_phase & 1);
+    ++mma_phase;
+    tc::fence_after_sync();
+  };
+
+  int it = 0;
+  if (leader && p_begin + ln < p_end) load_tile(p_begin + ln, 0);
+  for (int p = p_begin + ln; p < p_end; p += TCD_LANES, ++it) {
+    const int buf = it & 1;
+    // aux / sw for this pixel (global loads in flight during the column-pass MMAs)
+    float av[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) av[c] = (c < Ca && q_ok) ? __ldg(ab + (size_t)c * npts + (size_t)p * Q + q) : 0.f;
+    if (leader) {
+      tc::mbar_wait(tile_full + buf, (it >> 1) & 1);
+      tc::fence_after_sync();
+      const uint32_t t16 = tc::smem_u32(tt + buf * TCD_TT) >> 4, w16 = tc::smem_u32(tsm + TCD_OFF_WG) >> 4;
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)            // K = 16 grid columns per MMA: 2 k8 planes of A, 2 K groups of B
+          tc::mma_bf16_ss_lohi(tmem, ((w16 + hl * 1024 + k * 256) & 0x3FFFu) | lboA, hiA, ((t16 + k * 16) & 0x3FFFu) | lboT, hiT,
+                               idesc_g, (hl | k) ? 1u : 0u);
+      tc::mma_commit(mma_done);
+      if (p + TCD_LANES < p_end) load_tile(p + TCD_LANES, buf ^ 1);
+    }
+    wait_mma();
+    float v[64];
+    tc::tmem_ld32(tmem + tl, v);
+    tc::tmem_ld32(tmem + tl + 32, v + 32);
+    tc::tmem_ld_wait();
+    // ---- A0 = [g ; aux ; sw ; 0] ----
+    tcd_store_act(abuf, px, v);
+    {
+      uint4 pk;
+      __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+      float ex[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ex[c] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) if (c < Ca) ex[c] = av[c];
+      ex[Ca] = sw1[p] * swq;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(ex[2 * i], ex[2 * i + 1]);
+      *reinterpret_cast<uint4*>(abuf + 8 * 2048 + px * 16) = pk;
+    }
+    // ---- three hidden layers on the tensor cores ----
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      fence_proxy_async();
+      tc::fence_before_sync();
+      tcd_lane_bar(ln);
+      if (leader) {
+        tc::fence_after_sync();
+        const uint32_t a16 = tc::smem_u32(abuf) >> 4;
+        const uint32_t w16 = tc::smem_u32(tsm + (l == 0 ? TCD_OFF_W0 : (l == 1 ? TCD_OFF_W1 : TCD_OFF_W2))) >> 4;
+        const int nk = l == 0 ? TCD_KIN / 16 : 4;
+        const uint32_t d = tmem + ((l & 1) ? 0u : 64u);
+        for (int k = 0; k < nk; ++k)
+          tc::mma_bf16_ss_lohi(d, ((a16 + k * 256) & 0x3FFFu) | lboA, hiA, ((w16 + k * 128) & 0x3FFFu) | lboW, hiW, idesc_m,
+                               k ? 1u : 0u);
+        tc::mma_commit(mma_done);
+      }
+      wait_mma();
+      const uint32_t d = tmem + ((l & 1) ? 0u : 64u);
+      tc::tmem_ld32(d + tl, v);
+      tc::tmem_ld32(d + tl + 32, v + 32);
+      tc::tmem_ld_wait();
+      const float* bias = f32 + 64 * l;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { const float t = v[i] + bias[i]; v[i] = t < 0.f ? 0.f : t; }
+      if (l < 2) tcd_store_act(abuf, px, v);
+    }
+    // ---- head ----
+    float o0 = f32[320], o1 = f32[321];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { o0 = fmaf(f32[192 + i], v[i], o0); o1 = fmaf(f32[256 + i], v[i], o1); }
+    if (q_ok) {
+      mean[(size_t)b * npts + (size_t)p * Q + q] = o0;
+      stdv[(size_t)b * npts + (size_t)p * Q + q] = sqrtf(1e-6f + softplus_t(o1));
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tc::fence_after_sync(); tc::tmem_dealloc(*tmem_slot, 512); }
+}
+
+}  // namespace
+
+CNP_API long long cnp_decode_grid_tc_workspace_bytes(int B, int n2, int P, int Q) {
+  long long tabs = (long long)(P + Q) * (2 * sizeof(int) + (DKB + 1) * sizeof(float)) + (long long)64 * FZ_IN * sizeof(float);
+  long long T = (long long)B * P * 64 * n2 * 2;
+  return ((tabs + 255) / 256) * 256 + T;
+}
+
+// Tensor-core variant of cnp_decode_grid_fused_fwd (same arguments).  Requirements checked here: 3 hidden layers of
+// width 64, 64 + Ca + 1 <= 72, n2 >= 64.  The caller guarantees that any 128 consecutive target columns x2t span at
+// most 64 - band internal-grid columns (true whenever the target grid is at least ~4x finer than the internal grid).
+CNP_API int cnp_decode_grid_tc_fwd(const cnp_blk* h, const float* x1t, const float* x2t, int B, int P, int Q,
+                                   double start1, double start2, double res, float scale2, const float* Wf,
+                                   const float* bfin, const cnp_mlp_params* p, const float* aux, long long aux_bstride,
+                                   int Ca, float* mean, float* stdv, void* workspace, long long workspace_bytes,
+                                   cudaStream_t st) {
+  CNP_REQUIRE(h && x1t && x2t && Wf && bfin && p && aux && mean && stdv && workspace && B > 0 && P > 0 && Q > 0,
+              "decode_grid_tc: bad arguments");
+  const int n1 = h->H, n2 = h->W;
+  CNP_REQUIRE(n2 >= 64, "decode_grid_tc: internal grid too narrow");
+  CNP_REQUIRE(workspace_bytes >= cnp_decode_grid_tc_workspace_bytes(B, n2, P, Q), "decode_grid_tc: workspace too small");
+  CNP_REQUIRE(p->n_layers == 4 && p->dims[0] == 64 + Ca && 64 + Ca + 1 <= FZ_IN && Ca <= 6, "decode_grid_tc: MLP shape unsupported");
+  for (int l = 1; l < 4; ++l) CNP_REQUIRE(p->dims[l] == 64, "decode_grid_tc: hidden width must be 64");
+  CNP_REQUIRE(p->dims[4] == 2, "decode_grid_tc: last layer must have 2 outputs");
+  const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+  CNP_REQUIRE(2.0 * R / res + 3 <= DKB, "decode_grid_tc: decoder scale too large (band > %d)", DKB);
+  int* i0 = reinterpret_cast<int*>(workspace);
+  int* len1 = i0 + P;
+  int* j0 = len1 + P;
+  int* len2 = j0 + Q;
+  float* w1 = reinterpret_cast<float*>(len2 + Q);
+  float* w2 = w1 + (size_t)DKB * P;
+  float* sw1 = w2 + (size_t)DKB * Q;
+  float* sw2 = sw1 + P;
+  float* W0f = sw2 + Q;
+  const long long tabs = (long long)(P + Q) * (2 * sizeof(int) + (DKB + 1) * sizeof(float)) + (long long)64 * FZ_IN * sizeof(float);
+  __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(workspace) + ((tabs + 255) / 256) * 256);
+  dec_band_sw_kernel<<<cnp_cdiv(P, 128), 128, 0, st>>>(x1t, P, start1, n1, res, scale2, i0, len1, w1, sw1);
+  dec_band_sw_kernel<<<cnp_cdiv(Q, 128), 128, 0, st>>>(x2t, Q, start2, n2, res, scale2, j0, len2, w2, sw2);
+  fold_final_kernel<<<64, FZ_IN, 0, st>>>(p->W[0], Wf, bfin, Ca, W0f);
+  CNP_LAUNCH_CHECK("dec_band_sw_kernel");
+  const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(h->base) + (size_t)h->cb_off * (n1 + 4) * (n2 + 4) * 8;
+  dim3 gr(cnp_cdiv(n2, 32), P, B);
+  dec_rows_blk_kernel<<<gr, 256, 0, st>>>(hp, h->bstride, n1, n2, P, i0, len1, w1, T);
+  CNP_LAUNCH_CHECK("dec_rows_blk_kernel");
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(dec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCD_SMEM); attr = true; }
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int nqt = cnp_cdiv(Q, 128);
+  int nseg = sms / (nqt * B);
+  if (nseg < 1) nseg = 1;
+  int rows_per_cta = cnp_cdiv(P, nseg);
+  rows_per_cta = cnp_cdiv(rows_per_cta, TCD_LANES) * TCD_LANES;
+  dim3 grid(nqt, cnp_cdiv(P, rows_per_cta), B);
+  dec_tc_kernel<<<grid, 128 * TCD_LANES, TCD_SMEM, st>>>(*p, W0f, T, n2, P, Q, x2t, start2, res, scale2, j0, sw1, sw2, aux,
+                                                        aux_bstride, Ca, mean, stdv, rows_per_cta);
+  CNP_LAUNCH_CHECK("dec_tc_kernel");
+  return 0;
+}

@@ -63,6 +63,7 @@ class DeviceBatch:
     Nt: int
     h2d_bytes: int = 0
     ready: Optional[torch.cuda.Event] = None   # set when the upload ran on a side stream (Engine.upload(stream=...))
+    xt_host: Optional[Tuple[np.ndarray, np.ndarray]] = None   # on-grid targets: host copy of the coordinates
 
 
 @dataclass
@@ -74,6 +75,7 @@ class HostBatch:
     aux_t: Optional[torch.Tensor]
     grid: GridSpec
     B: int
+    xt_host: Optional[Tuple[np.ndarray, np.ndarray]] = None
 
 
 def _monotone(v: np.ndarray) -> int:
@@ -242,8 +244,9 @@ class Engine:
                 raise NotImplementedError("on-grid targets must share coordinates across the batch")
             B = int(np.asarray(contexts[0][1].y if hasattr(contexts[0][1], "y") else contexts[0][1]).shape[0])
             xt_h = (cpu(x1t[0]), cpu(x2t[0]))
+            xt_np = (np.array(x1t[0], dtype=np.float32), np.array(x2t[0], dtype=np.float32))
         else:
-            xt_h = None
+            xt_h = xt_np = None
         hctx = []
         for (x, y, m), xh in zip(contexts, xs[:-1]):
             key = None
@@ -281,7 +284,7 @@ class Engine:
                 hctx.append(hc)
             else:
                 hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))
-        return HostBatch(hctx, xt_h if xt_h is not None else cpu(xt), cpu(yt), cpu(aux_t), grid, B)
+        return HostBatch(hctx, xt_h if xt_h is not None else cpu(xt), cpu(yt), cpu(aux_t), grid, B, xt_np)
 
     def upload(self, hb: "HostBatch", stream: Optional[torch.cuda.Stream] = None) -> DeviceBatch:
         """Asynchronous H2D of a staged batch on the current stream, or on ``stream`` (a copy stream: the batch
@@ -317,7 +320,7 @@ class Engine:
             xt = up(hb.xt)
             nt = int(xt.shape[-1])
         yt, aux = up(hb.yt), up(hb.aux_t)
-        return DeviceBatch(dctx, xt, yt, aux, hb.grid, hb.B, nt, nbytes)
+        return DeviceBatch(dctx, xt, yt, aux, hb.grid, hb.B, nt, nbytes, xt_host=hb.xt_host)
 
     @staticmethod
     def _batch_tensors(batch: DeviceBatch):
@@ -853,17 +856,28 @@ class Engine:
             raise ValueError(f"on-grid prediction needs Y_t_aux of shape [{Ca},{P},{Q}]")
         aux = aux.reshape(-1, Ca, P, Q)
         aux_bs = 0 if aux.shape[0] == 1 else aux.stride(0)
-        wsb = _cabi.lib().cnp_decode_grid_fused_workspace_bytes(B, g.n1, P, Q)
-        ws = self._buf("dec_fused_ws", ((wsb + 3) // 4,))
         mean = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
         std = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
         fin = self.module.decoder.unet.final_linear
         p = self._mlp_params()
         dims = self.module.mlp_dims()
         flops = 2.0 * B * P * Q * (sum(a * b for a, b in zip(dims[:-1], dims[1:])) + 64 * 30)
-        self._call("cnp_decode_grid_fused_fwd", C.byref(h_last.view(0)), _ptr(x1t), _ptr(x2t), B, P, Q, g.start1, g.start2,
+        work = (flops, 4.0 * B * P * Q * (Ca + 2) + 2.0 * B * 64 * g.n1 * g.n2)
+        # tensor-core tail when the MLP is the standard 3 x 64 one and the target grid is fine enough that any 128
+        # consecutive target columns (plus the SetConv band) fit in 64 internal-grid columns
+        use_tc = (os.environ.get("CNP_DECODE_TC", "1") != "0" and len(dims) == 5 and all(d == 64 for d in dims[1:4])
+                  and Ca <= 6 and g.n2 >= 64 and batch.xt_host is not None)
+        if use_tc:
+            x2 = batch.xt_host[1].astype(np.float64)
+            band = 2.0 * math.sqrt(2.0 * 104.0 * s2) / g.res + 4.0
+            span = max((abs(x2[min(i + 127, Q - 1)] - x2[i]) for i in range(0, Q, 128)), default=0.0) / g.res
+            use_tc = span + band <= 64.0
+        name = "cnp_decode_grid_tc" if use_tc else "cnp_decode_grid_fused"
+        wsb = getattr(_cabi.lib(), name + "_workspace_bytes")(B, g.n2 if use_tc else g.n1, P, Q)
+        ws = self._buf("dec_fused_ws", ((wsb + 3) // 4,))
+        self._call(name + "_fwd", C.byref(h_last.view(0)), _ptr(x1t), _ptr(x2t), B, P, Q, g.start1, g.start2,
                    g.res, s2, _ptr(fin.weight), _ptr(fin.bias), C.byref(p), _ptr(aux), aux_bs, Ca, _ptr(mean), _ptr(std),
-                   _ptr(ws), wsb, _stream(), work=(flops, 4.0 * B * P * Q * (Ca + 2) + 2.0 * B * 64 * g.n1 * g.n2))
+                   _ptr(ws), wsb, _stream(), work=work)
         return dict(mean=mean, std=std, var=None, logp=None, count=None, ctx=None)
 
     def backward(self, batch: DeviceBatch, ctx: dict, dlogp: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -174,6 +174,15 @@ int cnp_decode_grid_fused_fwd(const cnp_blk* h, const float* x1t /*[P]*/, const 
                               int Ca, float* mean /*[B,P,Q]*/, float* stdv, void* workspace, long long workspace_bytes,
                               cnp_stream_t s);
 
+/* Tensor-core variant (same arguments): row pass to a bf16 workspace, then per 128-pixel tile the column pass and the
+ * three hidden MLP layers as chained tcgen05 GEMMs (pixels = M), head in registers.  Needs 3 hidden layers of width
+ * 64 and a target grid fine enough that 128 consecutive x2t span <= 64 - band internal-grid columns. */
+long long cnp_decode_grid_tc_workspace_bytes(int B, int n2, int P, int Q);
+int cnp_decode_grid_tc_fwd(const cnp_blk* h, const float* x1t, const float* x2t, int B, int P, int Q, double start1,
+                           double start2, double res, float scale2, const float* Wf, const float* bf,
+                           const struct cnp_mlp_params* p, const float* aux, long long aux_bstride, int Ca, float* mean,
+                           float* stdv, void* workspace, long long workspace_bytes, cnp_stream_t s);
+
 /* ---- (4) aux-at-target MLP + heteroscedastic Gaussian head + normalised NLL -----------------------
  * replaces: neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood -> MultiOutputNormal.logpdf
  * -> nps.loglik (A.6, A.7) reached from ConvNP.loss_fn (train.py:370).  logp is float64. */

@@ -155,3 +155,25 @@ def test_multivariable_ragged_batch_matches_oracle(static, precision, tol):
             g, r = p.grad.detach().cpu().double().flatten(), P[n].grad.double().flatten()
             cos = float((g @ r) / (g.norm() * r.norm()).clamp(min=1e-300))
             assert cos > (0.9999 if precision == "fp32" else 0.99), (n, cos)
+
+
+def test_tensor_core_decoder_tail_matches_fused_and_oracle(monkeypatch):
+    """On a target grid fine enough for the tcgen05 tail (128 target columns + band within 64 internal columns) the
+    tensor-core decoder agrees with the CUDA-core fused decoder (same inputs, fp32 MLP) and with the oracle."""
+    static = make_static(seed=11, n_hi=520, with_aux_hi=True)
+    task = make_task(static, 777, grid_targets=True)
+    m = small_model("bf16")
+    monkeypatch.setenv("CNP_DECODE_TC", "0")
+    ref = m(task)
+    calls = []
+    orig = m.engine._call
+    monkeypatch.setattr(m.engine, "_call", lambda name, *a, **k: (calls.append(name), orig(name, *a, **k))[1])
+    monkeypatch.setenv("CNP_DECODE_TC", "1")
+    out = m(task)
+    assert "cnp_decode_grid_tc_fwd" in calls          # the tensor-core path really ran
+    assert rel_err(out["mean"], ref["mean"]) < 1e-2    # bf16 hidden activations / weights in the MLP
+    assert rel_err(out["std"], ref["std"]) < 1e-2
+    ctx, xt, _, aux = oracle_inputs(task)
+    mean_o, var_o = O.forward(cpu_params(m), ctx, xt, aux, m.config.points_per_unit)
+    assert rel_err(out["mean"], mean_o) < 2e-2
+    assert rel_err(out["std"], var_o.sqrt()) < 2e-2
