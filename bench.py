@@ -293,8 +293,13 @@ def run_ours(args):
         d = prof["cnp_conv_tc2"]
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
         tot_ms = sum(v["ms"] for v in prof.values())
+        traffic = None     # DRAM bytes per launch from the committed ncu pass (profiles/r01_traffic.json), same command
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and args.internal_density == PPU:
+            with open(tpath) as f:
+                traffic = json.load(f).get("conv_tc2_kernel", {}).get("dram_bytes_per_launch")
         roof = {"kernel": "conv_tc2_kernel (tcgen05 implicit-GEMM conv, fwd + dgrad launches)", "bound": "tensor", "achieved": ach,
-                "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
+                "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": traffic,
                 "peak_source": f"{pk['source']} bf16_tflops_sustained", "share_of_step": d["ms"] / tot_ms,
                 "avg_launch_ms": d["ms"] / d["launches"], "flops_per_launch": d["flops"] / d["launches"]}
     kernels = {k: {"launches": v["launches"] // 2, "ms_per_step": v["ms"] / 2,
