@@ -18,8 +18,15 @@
 //     taps kx and kx+3 (3 accumulators);
 //   * stride-2 layers   : M = [phase (py,0) ; phase (py,1)] of the space-to-depth tensor.
 // K is split across CTAs; partial sums are reduced with fp32 atomics straight into the torch-layout
-// gradient.
+// gradient (or through a workspace + reduce kernel for long K loops).
+//
+// N = 128 ("dup") variant, used for the 5x5 kinds: the M128 x N64 MMA is shared-memory bound (48 cycles against a
+// 32-cycle floor, profiles/r01_mma_rate.txt) while N = 128 runs at its floor (64 cycles).  The dY tile is therefore
+// loaded twice, the second copy shifted by one pixel, and used as ONE N = 128 operand [dY(p) ; dY(p-1)]: an MMA with
+// the X operand at offset a then yields tap a (columns 0..63) and tap a+1 (columns 64..127).  A 128-channel layer
+// needs 3 MMAs of 64 cycles per 16-pixel K step (taps {0,1},{2,3},{4,5}; 5 is discarded) instead of 5 of 48.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 #define CNP_WG_MAX_PASS 5
 #define CNP_WG_MAX_ACC 5
@@ -30,10 +37,9 @@ struct cnp_wg_pass {
   int shift_px;      // >=0: planes 8..15 = chunks chunk0..chunk0+7 shifted by shift_px pixels; -1: real chunks 8..15
   int base_off;      // linear pixel offset of the X tile relative to the dY tile
   int n_acc;
-  int a_off[CNP_WG_MAX_ACC];
-  int slot0[CNP_WG_MAX_ACC];   // tap index (ky*k+kx) of rows 0..63, -1 = discard
-  int slot1[CNP_WG_MAX_ACC];   // tap index of rows 64..127
-  int ci0, ci1;                // input-channel base of the two halves
+  int a0, astep;               // accumulator j uses the X operand at pixel offset a0 + j*astep
+  int slot[CNP_WG_MAX_ACC][2][2];   // tap index (ky*k+kx) of [accumulator][row half][column half], -1 = discard
+  int ci0, ci1;                // input-channel base of the two row halves
 };
 
 struct cnp_wg_args {
@@ -42,6 +48,8 @@ struct cnp_wg_args {
   float* dw; float* dbias; int Cin, KK;
   float* ws;                     // optional partial-sum workspace [pass][ksplit][acc][128][64]; NULL = atomics into dw
   int B, P, p_start, tiles_per_img, ksplit, n_pass;
+  int dup;                       // 1: N = 128 operand [dY(p) ; dY(p-1)] (column half 1 = tap a+1)
+  int ws_acc;                    // accumulators per CTA in the workspace layout
   cnp_wg_pass pass[CNP_WG_MAX_PASS];
 };
 
@@ -50,24 +58,25 @@ namespace {
 constexpr int WG_STAGES = 3;
 constexpr int XPAD = 8;  // extra pixels per X plane in shared memory (max tap offset 4, keeps 128 B alignment)
 
-// K steps [K0, K1) x NACC taps of one stage, fully unrolled (tap j = +j pixels on the X operand)
+// K steps [K0, K1) x NACC accumulators of one stage, fully unrolled (accumulator j: X operand at +a_j pixels)
 template <int NACC, int K0, int K1>
-__device__ __forceinline__ void wg_issue(uint32_t tmem, uint32_t xs16, uint32_t ds16, uint32_t lbo, uint32_t a_hi,
-                                         uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
+__device__ __forceinline__ void wg_issue(uint32_t tmem, uint32_t ncols, uint32_t xs16, uint32_t astep, uint32_t ds16,
+                                         uint32_t lbo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
 #pragma unroll
   for (int ks = K0; ks < K1; ++ks) {
 #pragma unroll
     for (int j = 0; j < NACC; ++j)
-      tc::mma_bf16_ss_lohi(tmem + j * 64, ((xs16 + ks * 16 + j) & 0x3FFFu) | lbo, a_hi, ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi,
-                           idesc, ks > K0 ? 1u : acc0);
+      tc::mma_bf16_ss_lohi(tmem + j * ncols, ((xs16 + ks * 16 + j * astep) & 0x3FFFu) | lbo, a_hi,
+                           ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi, idesc, ks > K0 ? 1u : acc0);
   }
 }
-__device__ __forceinline__ void wg_issue_n(int nacc, int k0, int k1, uint32_t tmem, uint32_t xs16, uint32_t ds16,
-                                           uint32_t lbo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc, uint32_t acc0) {
+__device__ __forceinline__ void wg_issue_n(int nacc, int k0, int k1, uint32_t tmem, uint32_t ncols, uint32_t xs16,
+                                           uint32_t astep, uint32_t ds16, uint32_t lbo, uint32_t a_hi, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t acc0) {
   for (int ks = k0; ks < k1; ++ks)
     for (int j = 0; j < nacc; ++j)
-      tc::mma_bf16_ss_lohi(tmem + j * 64, ((xs16 + ks * 16 + j) & 0x3FFFu) | lbo, a_hi, ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi,
-                           idesc, ks > k0 ? 1u : acc0);
+      tc::mma_bf16_ss_lohi(tmem + j * ncols, ((xs16 + ks * 16 + j * astep) & 0x3FFFu) | lbo, a_hi,
+                           ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi, idesc, ks > k0 ? 1u : acc0);
 }
 
 __global__ void __launch_bounds__(192, 1)
@@ -75,7 +84,8 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int P = a.P;
   const int x_plane_b = (P + XPAD) * 16, dy_plane_b = P * 16;
-  const int x_tile_b = 16 * x_plane_b, dy_tile_b = 8 * dy_plane_b;
+  const int ndy = a.dup ? 16 : 8;              // dY planes per stage (dup: second copy shifted by one pixel)
+  const int x_tile_b = 16 * x_plane_b, dy_tile_b = ndy * dy_plane_b;
   const int stage_b = x_tile_b + dy_tile_b;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * stage_b);
   uint64_t* full = bars;                 // [WG_STAGES]
@@ -109,17 +119,17 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         const long long p0 = a.p_start + (long long)ti * P;
         uint8_t* xs = smem + s * stage_b;
         uint8_t* ds = xs + x_tile_b;
-        tc::mbar_expect_tx(full + s, 16u * (uint32_t)(P + 4) * 16u + 8u * (uint32_t)P * 16u);
+        tc::mbar_expect_tx(full + s, 16u * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u);
         const __nv_bfloat16* xb = a.x + (long long)b * a.x_bs + (p0 + ps.base_off) * 8;
         for (int c = 0; c < 16; ++c) {
           const __nv_bfloat16* src;
           if (c < 8 || ps.shift_px < 0) src = xb + (long long)(ps.chunk0 + c) * a.x_plane;
           else src = xb + (long long)(ps.chunk0 + c - 8) * a.x_plane + (long long)ps.shift_px * 8;
-          tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + 4) * 16u, full + s);
+          tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + XPAD) * 16u, full + s);
         }
         const __nv_bfloat16* db = a.dy + (long long)b * a.dy_bs + p0 * 8;
-        for (int c = 0; c < 8; ++c)
-          tc::bulk_g2s(ds + c * dy_plane_b, db + (long long)c * a.dy_plane, (uint32_t)P * 16u, full + s);
+        for (int c = 0; c < ndy; ++c)   // planes 8..15 (dup): the same chunks one pixel earlier
+          tc::bulk_g2s(ds + c * dy_plane_b, db + (long long)(c & 7) * a.dy_plane - (c >> 3) * 8, (uint32_t)P * 16u, full + s);
       }
     }
   } else if (warp == 1) {
@@ -127,33 +137,37 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       // MN-major operands: LBO = 128 B between the two 8-pixel K groups, SBO = plane stride between 8-channel groups.
       // Only the low descriptor word changes between MMAs (+1 per tap pixel, +16 per 16-pixel K step), and the wait
       // for the next stage is issued before the last K step so its latency overlaps queued MMAs.
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc = a.dup ? tc::make_idesc_bf16(128, 128, 1, 1) : tc::make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t ncols = a.dup ? 128u : 64u;
       const uint32_t a_hi = ((uint32_t)x_plane_b >> 4) | (1u << 14);
       const uint32_t b_hi = ((uint32_t)dy_plane_b >> 4) | (1u << 14);
       const uint32_t lbo = (128u >> 4) << 16;
       const int nks = P / 16;
-      const int a0 = ps.a_off[0];
+      const uint32_t astep = (uint32_t)ps.astep;
       uint32_t it = 0;
       tc::mbar_wait(full, 0);
       tc::fence_after_sync();
       for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
         const int s = it % WG_STAGES;
-        const uint32_t xs16 = (tc::smem_u32(smem + s * stage_b) >> 4) + (uint32_t)a0;
+        const uint32_t xs16 = (tc::smem_u32(smem + s * stage_b) >> 4) + (uint32_t)ps.a0;
         const uint32_t ds16 = tc::smem_u32(smem + s * stage_b + x_tile_b) >> 4;
         const bool has_next = t + a.ksplit < total_tiles;
         const uint32_t acc0 = it > 0 ? 1u : 0u;
-        if (nks == 8 && ps.n_acc == 5) wg_issue<5, 0, 7>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc0);
-        else if (nks == 8 && ps.n_acc == 3) wg_issue<3, 0, 7>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc0);
-        else wg_issue_n(ps.n_acc, 0, nks - 1, tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        const bool fast = nks == 8;
+        if (fast && ps.n_acc == 3) wg_issue<3, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        else if (fast && ps.n_acc == 2) wg_issue<2, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        else if (fast && ps.n_acc == 5) wg_issue<5, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        else wg_issue_n(ps.n_acc, 0, nks - 1, tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
         if (has_next) {
           const uint32_t n = it + 1;
           tc::mbar_wait(full + n % WG_STAGES, (n / WG_STAGES) & 1);
           tc::fence_after_sync();
         }
         const uint32_t acc1 = (it > 0 || nks > 1) ? 1u : 0u;
-        if (nks == 8 && ps.n_acc == 5) wg_issue<5, 7, 8>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc1);
-        else if (nks == 8 && ps.n_acc == 3) wg_issue<3, 7, 8>(tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc1);
-        else wg_issue_n(ps.n_acc, nks - 1, nks, tmem_base, xs16, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        if (fast && ps.n_acc == 3) wg_issue<3, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        else if (fast && ps.n_acc == 2) wg_issue<2, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        else if (fast && ps.n_acc == 5) wg_issue<5, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        else wg_issue_n(ps.n_acc, nks - 1, nks, tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
         tc::mma_commit(empty + s);
       }
       tc::mma_commit(done);
@@ -209,14 +223,13 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       const int m = q * 32 + lane;
       const int half = m >> 6;
       const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
+      const int ncols = a.dup ? 128 : 64;
       for (int j = 0; j < ps.n_acc; ++j) {
-        const int slot = half ? ps.slot1[j] : ps.slot0[j];
-        float* wsp = a.ws ? a.ws + ((((size_t)blockIdx.y * a.ksplit + blockIdx.x) * CNP_WG_MAX_ACC + j) * 128 + m) * 64
-                          : nullptr;
-#pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
+        float* wsp = a.ws ? a.ws + ((((size_t)blockIdx.y * a.ksplit + blockIdx.x) * a.ws_acc + j) * 128 + m) * 128 : nullptr;
+        for (int hc = 0; hc < ncols / 32; ++hc) {
+          const int slot = ps.slot[j][half][hc >> 1];
           float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 64 + hc * 32, v);
+          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * ncols + hc * 32, v);
           tc::tmem_ld_wait();
           if (wsp) {
             // partial sums go to the workspace with plain 16 B stores; wgrad_reduce_kernel folds the K split
@@ -226,7 +239,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
           } else if (slot >= 0 && ci < a.Cin) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int co = hc * 32 + i;
+              const int co = (hc & 1) * 32 + i;
               atomicAdd(a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot, v[i]);
             }
           }
@@ -242,17 +255,18 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
 // dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
-  const int total = a.n_pass * CNP_WG_MAX_ACC * 128 * 64;
+  const int ncols = a.dup ? 128 : 64;
+  const int total = a.n_pass * a.ws_acc * 128 * ncols;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
-    const int co = e & 63, m = (e >> 6) & 127, j = (e >> 13) % CNP_WG_MAX_ACC, pass = (e >> 13) / CNP_WG_MAX_ACC;
+    const int col = e % ncols, m = (e / ncols) & 127, jj = e / (ncols * 128), j = jj % a.ws_acc, pass = jj / a.ws_acc;
     const cnp_wg_pass& ps = a.pass[pass];
     if (j >= ps.n_acc) continue;
-    const int half = m >> 6;
-    const int slot = half ? ps.slot1[j] : ps.slot0[j];
+    const int half = m >> 6, co = col & 63;
+    const int slot = ps.slot[j][half][col >> 6];
     const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
     if (slot < 0 || ci >= a.Cin) continue;
-    const float* src = a.ws + (((size_t)pass * a.ksplit * CNP_WG_MAX_ACC + j) * 128 + m) * 64 + co;
-    const size_t stride = (size_t)CNP_WG_MAX_ACC * 128 * 64;
+    const float* src = a.ws + (((size_t)pass * a.ksplit * a.ws_acc + j) * 128 + m) * 128 + col;
+    const size_t stride = (size_t)a.ws_acc * 128 * 128;
     float s0 = 0.f, s1 = 0.f;
     int k = 0;
     for (; k + 1 < a.ksplit; k += 2) { s0 += __ldg(src + (size_t)k * stride); s1 += __ldg(src + (size_t)(k + 1) * stride); }
@@ -304,7 +318,7 @@ enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2 };
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
 // Bytes of the optional partial-sum workspace (max over kinds: 5 passes x <=148 CTAs x 5 accumulators x 32 KB).
 CNP_API long long cnp_conv_tc_wgrad_workspace_bytes(void) {
-  return (long long)148 * CNP_WG_MAX_ACC * 128 * 64 * sizeof(float);
+  return (long long)148 * 3 * 128 * 128 * sizeof(float);   // <= 148 CTAs x <= 3 accumulators x [128][128] floats
 }
 
 CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dbias,
@@ -325,20 +339,42 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   const int p_end = (H + 1) * Wp + W + 2;
   a.tiles_per_img = cnp_cdiv(p_end - a.p_start, a.P);
   int np = 0;
+  static const bool no_dup = getenv("CNP_WGRAD_NO_DUP") != nullptr;
+  // only where it pays: 128-channel inputs (3 MMAs of 64 cycles instead of 5 of 48 per K step).  With 64-channel
+  // inputs the second dY copy makes the stage L2-bound (measured 18 % slower), so those keep N = 64.
+  a.dup = (!no_dup && kind == WG_K5S1 && n_chunks == 16) ? 1 : 0;
+  auto clear_slots = [](cnp_wg_pass& p) {
+    for (int j = 0; j < CNP_WG_MAX_ACC; ++j)
+      for (int h = 0; h < 2; ++h) p.slot[j][h][0] = p.slot[j][h][1] = -1;
+  };
+  auto tap = [](int ky, int kx) { return (kx >= 0 && kx < 5) ? ky * 5 + kx : -1; };
   if (kind == WG_K5S1) {
     CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv_tc_wgrad: 5x5 needs 8 or 16 source chunks");
     CNP_REQUIRE(Cin == n_chunks * 8, "conv_tc_wgrad: Cin mismatch");
     a.KK = 25;
     for (int ky = 0; ky < 5; ++ky, ++np) {
       cnp_wg_pass& p = a.pass[np];
+      clear_slots(p);
       p.chunk0 = 0; p.base_off = (ky - 2) * Wp - 2; p.ci0 = 0;
-      if (n_chunks == 16) {
-        p.shift_px = -1; p.ci1 = 64; p.n_acc = 5;
-        for (int kx = 0; kx < 5; ++kx) { p.a_off[kx] = kx; p.slot0[kx] = ky * 5 + kx; p.slot1[kx] = ky * 5 + kx; }
-      } else {
-        p.shift_px = 3; p.ci1 = 0; p.n_acc = 3;
-        for (int kx = 0; kx < 3; ++kx) {
-          p.a_off[kx] = kx; p.slot0[kx] = ky * 5 + kx; p.slot1[kx] = (kx + 3 < 5) ? ky * 5 + kx + 3 : -1;
+      if (n_chunks == 16) {                 // rows = 128 input channels
+        p.shift_px = -1; p.ci1 = 64;
+        if (a.dup) {                        // X offsets 0,2,4: taps (a, a+1)
+          p.n_acc = 3; p.a0 = 0; p.astep = 2;
+          for (int j = 0; j < 3; ++j)
+            for (int h = 0; h < 2; ++h) { p.slot[j][h][0] = tap(ky, 2 * j); p.slot[j][h][1] = tap(ky, 2 * j + 1); }
+        } else {
+          p.n_acc = 5; p.a0 = 0; p.astep = 1;
+          for (int kx = 0; kx < 5; ++kx) p.slot[kx][0][0] = p.slot[kx][1][0] = tap(ky, kx);
+        }
+      } else {                              // rows = [64 channels ; the same 64 channels 3 pixels further]
+        p.shift_px = 3; p.ci1 = 0;
+        if (a.dup) {                        // offsets 0,1: row half 0 taps (a, a+1), row half 1 taps (a+3, a+4)
+          p.n_acc = 2; p.a0 = 0; p.astep = 1;
+          p.slot[0][0][0] = tap(ky, 0); p.slot[0][0][1] = tap(ky, 1); p.slot[0][1][0] = tap(ky, 3); p.slot[0][1][1] = tap(ky, 4);
+          p.slot[1][0][1] = tap(ky, 2);     // (1, 4, 5 are already covered or out of range)
+        } else {
+          p.n_acc = 3; p.a0 = 0; p.astep = 1;
+          for (int kx = 0; kx < 3; ++kx) { p.slot[kx][0][0] = tap(ky, kx); p.slot[kx][1][0] = tap(ky, kx + 3); }
         }
       }
     }
@@ -346,22 +382,36 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
     CNP_REQUIRE(n_chunks == 8 && Cin == 64, "conv_tc_wgrad: 1x1 needs an 8-chunk source");
     a.KK = 1;
     cnp_wg_pass& p = a.pass[np++];
-    p.chunk0 = 0; p.shift_px = 0; p.base_off = 0; p.n_acc = 1; p.a_off[0] = 0; p.slot0[0] = 0; p.slot1[0] = -1;
+    clear_slots(p);
+    p.chunk0 = 0; p.shift_px = 0; p.base_off = 0; p.n_acc = 1; p.a0 = 0; p.astep = 1; p.slot[0][0][0] = 0;
   } else if (kind == WG_K5S2) {
     CNP_REQUIRE(n_chunks == 32 && Cin == 64, "conv_tc_wgrad: stride-2 reads the 32-chunk phase tensor");
     a.KK = 25;
     for (int py = 0; py < 2; ++py)
       for (int ky = py; ky < 5; ky += 2, ++np) {
         cnp_wg_pass& p = a.pass[np];
+        clear_slots(p);
         const int dyy = (ky - 2 - py) / 2;
-        p.chunk0 = 16 * py; p.shift_px = -1; p.base_off = dyy * Wp - 1; p.ci0 = 0; p.ci1 = 0; p.n_acc = 3;
-        for (int j = 0; j < 3; ++j) {
-          p.a_off[j] = j; p.slot0[j] = ky * 5 + 2 * j; p.slot1[j] = (2 * j + 1 < 5) ? ky * 5 + 2 * j + 1 : -1;
+        // rows = [x-phase 0 ; x-phase 1] of the space-to-depth tensor: offset j <-> taps kx = 2j (half 0), 2j+1 (half 1)
+        p.chunk0 = 16 * py; p.shift_px = -1; p.base_off = dyy * Wp - 1; p.ci0 = 0; p.ci1 = 0;
+        if (a.dup) {                        // offset j: taps (2j, 2j+2) for x-phase 0, (2j+1, 2j+3) for x-phase 1
+          p.n_acc = 2; p.a0 = 0; p.astep = 1;
+          p.slot[0][0][0] = tap(ky, 0); p.slot[0][0][1] = tap(ky, 2); p.slot[0][1][0] = tap(ky, 1); p.slot[0][1][1] = tap(ky, 3);
+          p.slot[1][0][1] = tap(ky, 4);
+        } else {
+          p.n_acc = 3; p.a0 = 0; p.astep = 1;
+          for (int j = 0; j < 3; ++j) { p.slot[j][0][0] = tap(ky, 2 * j); p.slot[j][1][0] = tap(ky, 2 * j + 1); }
         }
       }
   } else {
     CNP_REQUIRE(false, "conv_tc_wgrad: unknown kind %d", kind);
   }
+  if (a.dup) {
+    // the shifted dY copy sums dY[p-1]: run one pixel further so that it still covers the last interior pixel
+    a.tiles_per_img = cnp_cdiv(p_end - a.p_start + 1, a.P);
+  }
+  a.ws_acc = 1;
+  for (int i = 0; i < np; ++i) a.ws_acc = a.pass[i].n_acc > a.ws_acc ? a.pass[i].n_acc : a.ws_acc;
   a.n_pass = np;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
@@ -369,7 +419,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   a.ksplit = sms / np;
   if (a.ksplit > total_tiles) a.ksplit = total_tiles;
   if (a.ksplit < 1) a.ksplit = 1;
-  const size_t stage_b = (size_t)16 * (a.P + XPAD) * 16 + (size_t)8 * a.P * 16;
+  const size_t stage_b = (size_t)16 * (a.P + XPAD) * 16 + (size_t)(a.dup ? 16 : 8) * a.P * 16;
   const size_t smem = WG_STAGES * stage_b + (2 * WG_STAGES + 1) * 8 + 16 + 4 * 64 * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
@@ -380,7 +430,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   a.ws = nullptr;
   // the two-kernel reduction only pays for long K loops; short ones keep the atomics
   if (workspace && total_tiles >= 4096 &&
-      workspace_bytes >= (long long)np * a.ksplit * CNP_WG_MAX_ACC * 128 * 64 * (long long)sizeof(float))
+      workspace_bytes >= (long long)np * a.ksplit * a.ws_acc * 128 * 128 * (long long)sizeof(float))
     a.ws = reinterpret_cast<float*>(workspace);
   dim3 grid(a.ksplit, np);
   wgrad_tc_kernel<<<grid, 192, smem, st>>>(a);
