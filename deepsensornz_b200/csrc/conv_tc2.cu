@@ -118,8 +118,12 @@ __device__ __forceinline__ void issue_row_n(int nacc, uint32_t tmem, uint32_t w_
                            p > 0 ? 1u : first);
 }
 
+// CL = true: instantiation with the cluster / multicast code.  A kernel that contains cluster instructions is scheduled
+// differently even in a plain launch (measured ~15 % slower on the wgrad kernel), hence two instantiations.
+template <bool CL>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
+  const int a_cluster = CL ? a.cluster : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const int plane_bytes = a.plane_sm * 16;
   const int abuf_bytes = 2 * plane_bytes;
@@ -142,7 +146,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C2_ABUFS; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < C2_WSTAGES; ++i) { tc::mbar_init(w_full + i, 1); tc::mbar_init(w_empty + i, (uint32_t)a.cluster); }
+    for (int i = 0; i < C2_WSTAGES; ++i) { tc::mbar_init(w_full + i, 1); tc::mbar_init(w_empty + i, (uint32_t)a_cluster); }
     tc::mbar_init(acc_full, 1);
     tc::mbar_init(acc_empty, C2_EPI_WARPS);
     tc::mbar_fence_init();
@@ -154,12 +158,12 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (a.cluster > 1) tc::cluster_sync();   // the partner's barriers are initialised before anything is multicast to them
+  if ((CL && a_cluster > 1)) tc::cluster_sync();   // the partner's barriers are initialised before anything is multicast to them
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const int n_iter = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;   // a CTA without a tile in the last round still
-  const bool ghost = a.cluster > 1 && (int)blockIdx.x + (n_iter - 1) * (int)gridDim.x >= ntiles;   // streams weights
-  const uint32_t crank = a.cluster > 1 ? tc::cluster_ctarank() : 0u;
+  const bool ghost = (CL && a_cluster > 1) && (int)blockIdx.x + (n_iter - 1) * (int)gridDim.x >= ntiles;   // streams weights
+  const uint32_t crank = (CL && a_cluster > 1) ? tc::cluster_ctarank() : 0u;
 
   const uint32_t row_bytes = (uint32_t)a.pitch * 16u;
   const long long plane_g = (long long)a.x_Hp * a.x_Wp * 8;
@@ -193,7 +197,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     if (tc::elect_one()) {
       uint32_t w_it = 0;
       for (int it = 0; it < n_iter; ++it) {
-        if (a.cluster == 1 && (int)blockIdx.x + it * (int)gridDim.x >= ntiles) break;
+        if (a_cluster == 1 && (int)blockIdx.x + it * (int)gridDim.x >= ntiles) break;
         const uint8_t* wsrc = a.w;
         for (int kb = 0; kb < a.plan.n_kb; ++kb) {
           const int npos = a.plan.t_npos[a.plan.kb_type[kb]];
@@ -203,7 +207,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             const uint32_t bytes = (uint32_t)np * C2_POS_BYTES;
             tc::mbar_wait(w_empty + ws, ((w_it / C2_WSTAGES) & 1) ^ 1);   // cluster: BOTH CTAs released the slot
             tc::mbar_expect_tx(w_full + ws, bytes);
-            if (a.cluster > 1) {
+            if ((CL && a_cluster > 1)) {
               // my half of the stage, delivered to both CTAs of the pair (one L2 read instead of two)
               const uint32_t half = bytes >> 1;
               tc::bulk_g2s_mc(w_smem + ws * C2_STAGE_BYTES + crank * half, wsrc + crank * half, half, w_full + ws, 0x3);
@@ -296,7 +300,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             }
           }
         }
-        if (a.cluster > 1) tc::mma_commit_mc(w_empty + ws, 0x3); else tc::mma_commit(w_empty + ws);
+        if ((CL && a_cluster > 1)) tc::mma_commit_mc(w_empty + ws, 0x3); else tc::mma_commit(w_empty + ws);
         if (kb_end) tc::mma_commit(a_empty + buf);
         ++w_it;
         if (tile_end) {
@@ -477,7 +481,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (a.cluster > 1) tc::cluster_sync();   // nobody exits while the partner may still multicast into its shared memory
+  if ((CL && a_cluster > 1)) tc::cluster_sync();   // nobody exits while the partner may still multicast into its shared memory
   if (warp == 3) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
@@ -748,7 +752,8 @@ CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int ki
   const size_t smem = c2_smem_bytes(a.plane_sm, a.out_mode);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cnp_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr = smem;
   }
@@ -774,8 +779,12 @@ CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int ki
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = a.cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, a);
-  if (le != cudaSuccess) { cnp_set_error("conv_tc2_kernel: %s", cudaGetErrorString(le)); return (int)le; }
+  if (a.cluster > 1) {
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, a);
+    if (le != cudaSuccess) { cnp_set_error("conv_tc2_kernel: %s", cudaGetErrorString(le)); return (int)le; }
+  } else {   // plain launch when no cluster is requested (cluster-attribute launches place CTAs differently)
+    conv_tc2_kernel<false><<<grid, C2_THREADS, smem, st>>>(a);
+  }
   CNP_LAUNCH_CHECK("conv_tc2_kernel");
   return 0;
 }

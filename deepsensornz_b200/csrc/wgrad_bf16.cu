@@ -50,6 +50,7 @@ struct cnp_wg_args {
   int B, P, p_start, tiles_per_img, ksplit, n_pass;
   int dup;                       // 1: N = 128 operand [dY(p) ; dY(p-1)] (column half 1 = tap a+1)
   int ws_acc;                    // accumulators per CTA in the workspace layout
+  int cluster;                   // 5: the five ky passes of a K-split slice form a cluster and share the dY stream
   cnp_wg_pass pass[CNP_WG_MAX_PASS];
 };
 
@@ -79,8 +80,12 @@ __device__ __forceinline__ void wg_issue_n(int nacc, int k0, int k1, uint32_t tm
                            ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi, idesc, ks > k0 ? 1u : acc0);
 }
 
+// CL = true: instantiation with the cluster / multicast code (a kernel that contains cluster instructions is scheduled
+// differently even when launched without a cluster, which costs ~15 % here, hence two instantiations)
+template <bool CL>
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
+  const int a_cluster = CL ? a.cluster : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const int P = a.P;
   const int x_plane_b = (P + XPAD) * 16, dy_plane_b = P * 16;
@@ -99,15 +104,21 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
 
   if (threadIdx.x == 0) {
     const bool bias_cta0 = (a.dbias != nullptr);
-    for (int i = 0; i < WG_STAGES; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, bias_cta0 ? 5 : 1); }
+    // a stage is free when every reader is done with it: the MMAs (of all CTAs of the cluster, whose dY copies this
+    // CTA's producer overwrites by multicast) and, with a bias gradient, the 4 summing warps (of every CTA)
+    const uint32_t ncta = (CL && a_cluster > 1) ? (uint32_t)a_cluster : 1u;
+    for (int i = 0; i < WG_STAGES; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, ncta * (bias_cta0 ? 5u : 1u)); }
     tc::mbar_init(done, 1);
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_sync();
   __syncthreads();
+  if ((CL && a_cluster > 1)) tc::cluster_sync();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CL && a_cluster > 1) ? tc::cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << a_cluster) - 1u);
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -128,8 +139,15 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
           tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + XPAD) * 16u, full + s);
         }
         const __nv_bfloat16* db = a.dy + (long long)b * a.dy_bs + p0 * 8;
-        for (int c = 0; c < ndy; ++c)   // planes 8..15 (dup): the same chunks one pixel earlier
-          tc::bulk_g2s(ds + c * dy_plane_b, db + (long long)(c & 7) * a.dy_plane - (c >> 3) * 8, (uint32_t)P * 16u, full + s);
+        for (int c = 0; c < ndy; ++c) {   // planes 8..15 (dup): the same chunks one pixel earlier
+          const __nv_bfloat16* src = db + (long long)(c & 7) * a.dy_plane - (c >> 3) * 8;
+          if ((CL && a_cluster > 1)) {            // every CTA of the cluster needs the same dY tile: load a fifth, multicast it
+            if ((uint32_t)c % (uint32_t)a_cluster == crank)
+              tc::bulk_g2s_mc(ds + c * dy_plane_b, src, (uint32_t)P * 16u, full + s, cmask);
+          } else {
+            tc::bulk_g2s(ds + c * dy_plane_b, src, (uint32_t)P * 16u, full + s);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -168,7 +186,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         else if (fast && ps.n_acc == 2) wg_issue<2, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
         else if (fast && ps.n_acc == 5) wg_issue<5, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
         else wg_issue_n(ps.n_acc, nks - 1, nks, tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
-        tc::mma_commit(empty + s);
+        if ((CL && a_cluster > 1)) tc::mma_commit_mc(empty + s, cmask); else tc::mma_commit(empty + s);
       }
       tc::mma_commit(done);
     }
@@ -199,7 +217,8 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
           }
         }
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(empty + s);
+        if ((CL && a_cluster > 1)) { if (lane < a_cluster) tc::mbar_arrive_cluster(empty + s, (uint32_t)lane); }
+        else if (lane == 0) tc::mbar_arrive(empty + s);
       }
       // fold the 4 epilogue warps in shared memory: ONE atomic per channel per CTA (64 hot addresses shared by
       // every CTA of the launch -- per-warp atomics cost ~35 us of serialised L2 traffic per launch)
@@ -249,6 +268,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   }
   tc::fence_before_sync();
   __syncthreads();
+  if ((CL && a_cluster > 1)) tc::cluster_sync();   // no CTA exits while a partner may still signal its barriers
   if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
@@ -423,17 +443,49 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   const size_t smem = WG_STAGES * stage_b + (2 * WG_STAGES + 1) * 8 + 16 + 4 * 64 * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cnp_set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr = smem;
+  }
+  // cluster of the five ky passes sharing the dY stream (dup path only: its stage is otherwise L2-bound); the K split
+  // is limited to the number of clusters that can be resident at once
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 1; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attrs; cfg.numAttrs = 1;
+  a.cluster = 1;
+  // Measured on B200: the 5-CTA cluster halves the L2 traffic of the dup path but runs 2.2x SLOWER (only 26 clusters
+  // fit, the five passes advance in lock-step, and cluster launches place CTAs differently), so it stays opt-in.
+  static const bool use_cluster = getenv("CNP_WGRAD_CLUSTER") != nullptr;
+  if (a.dup && np == 5 && use_cluster) {
+    attrs[0].val.clusterDim.y = 5;
+    cfg.gridDim = dim3(a.ksplit, np);
+    int max_clusters = 0;
+    const cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, wgrad_tc_kernel<true>, &cfg);
+    if (getenv("CNP_WGRAD_VERBOSE")) fprintf(stderr, "wgrad: max active clusters of 5 = %d (%s), ksplit %d\n", max_clusters, cudaGetErrorString(oe), a.ksplit);
+    if (oe == cudaSuccess && max_clusters >= 16) {
+      a.cluster = 5;
+      if (a.ksplit > max_clusters) a.ksplit = max_clusters;
+    } else {
+      cudaGetLastError();
+      attrs[0].val.clusterDim.y = 1;
+    }
   }
   a.ws = nullptr;
   // the two-kernel reduction only pays for long K loops; short ones keep the atomics
   if (workspace && total_tiles >= 4096 &&
       workspace_bytes >= (long long)np * a.ksplit * a.ws_acc * 128 * 128 * (long long)sizeof(float))
     a.ws = reinterpret_cast<float*>(workspace);
-  dim3 grid(a.ksplit, np);
-  wgrad_tc_kernel<<<grid, 192, smem, st>>>(a);
+  cfg.gridDim = dim3(a.ksplit, np);
+  if (a.cluster > 1) {
+    cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, a);
+    if (le != cudaSuccess) { cnp_set_error("wgrad_tc_kernel: %s", cudaGetErrorString(le)); return (int)le; }
+  } else {   // plain launch: a launch carrying a cluster attribute (even 1x1x1) was measured ~15 % slower here
+    wgrad_tc_kernel<false><<<cfg.gridDim, 192, smem, st>>>(a);
+  }
   CNP_LAUNCH_CHECK("wgrad_tc_kernel");
   if (a.ws) {
     wgrad_reduce_kernel<<<2 * sms, 256, 0, st>>>(a);
