@@ -130,6 +130,7 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
 
     # the pinned -> result-array memcpy (2 x 7.8 MB per 1400^2 task) runs on a worker thread (numpy releases the GIL),
     # so it overlaps the launches of the following tasks
+    copy_stream = torch.cuda.Stream() if cuda else None
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=1)
     futures = [None, None, None]
@@ -143,7 +144,9 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
         t2["Y_t"] = []
         hb = model.stage_task(t2, pinned=False, ctx_cache=ctx_cache)
         hb.aux_t = aux_dev
-        out = model(hb)
+        # upload on a copy stream: a pageable H2D copy on the compute stream would block the host until the previous
+        # task's kernels have drained
+        out = model(eng.upload(hb, stream=copy_stream) if copy_stream is not None else hb)
         mean, std = out["mean"][0, 0], out["std"][0, 0]
         if mean_out is None:
             mean_out = np.empty((n,) + tuple(mean.shape), dtype=np.float32)
