@@ -11,7 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from deepsensornz_b200 import _cabi, concat_tasks
+from deepsensornz_b200 import _cabi, concat_tasks, Task
 from deepsensornz_b200.engine import _Blk
 from deepsensornz_b200.synthetic import make_static, make_task
 from oracle import convnp_oracle as O
@@ -442,3 +442,30 @@ def test_train_epoch_with_graph_decreases_loss(static):
         last = float(np.mean(losses))
     assert last < first
     assert any(g not in (None, False) for g in m._train_graphs.values())   # a graph was captured and replayed
+
+
+@pytest.mark.parametrize("case", ["no_context_stations", "one_target", "all_sea"])
+def test_edge_cases_match_oracle(static, case):
+    """Empty / degenerate inputs the domain produces: an hour with no reporting context station, a single target
+    station, and a base grid that is entirely masked (all NaN)."""
+    t = make_task(static, 3100, n_stations=30, context_frac=0.6)
+    t = Task({k: (list(v) if isinstance(v, list) else v) for k, v in t.items()})
+    if case == "no_context_stations":
+        t["X_c"][3] = t["X_c"][3][:, :0]
+        t["Y_c"][3] = t["Y_c"][3][:, :0]
+    elif case == "one_target":
+        t["X_t"][0] = t["X_t"][0][:, :1]
+        t["Y_t"][0] = t["Y_t"][0][:, :1]
+        t["Y_t_aux"] = t["Y_t_aux"][:, :1]
+    else:
+        y = t["Y_c"][0].copy()
+        y[:] = np.nan
+        t["Y_c"][0] = y
+    m = small_model("fp32")
+    loss = m.loss_fn(t, normalise=True)
+    loss.backward()
+    ctx, xt, yt, aux = oracle_inputs(t)
+    ref = O.loss_fn(cpu_params(m), ctx, xt, yt, aux, m.config.points_per_unit)
+    assert np.isfinite(float(loss))
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < FP32_TOL
+    assert all(torch.isfinite(p.grad).all() for p in m.model.parameters() if p.requires_grad)
