@@ -235,6 +235,12 @@ class TaskLoader:
                 X, Y = self.sample_df(v, strat, s) if _is_df(v) else self.sample_da(v, strat, s)
                 task["X_t"].append(X)
                 task["Y_t"].append(Y)
+        if self.aux_at_contexts is not None:
+            # one extra off-grid context set: the aux variable sampled at every off-grid context location
+            off = [X for X in task["X_c"] if not isinstance(X, tuple)]
+            X_all = np.concatenate(off, axis=1) if off else np.empty((2, 0), dtype=self.dtype)
+            task["X_c"].append(X_all)
+            task["Y_c"].append(self.sample_offgrid_aux(X_all, self.time_slice_variable(self.aux_at_contexts, date)))
         if self.aux_at_targets is not None and task["X_t"]:
             if len(task["X_t"]) > 1:
                 raise ValueError("Cannot add auxiliary variable to target set when there are multiple target variables")

@@ -221,3 +221,13 @@ def test_tasks_feed_the_host_staging(loader):
     batch = concat_tasks(tasks)
     assert batch["Y_c"][0].shape == (2, 1, 12, 15) and batch["X_t"][0].shape == (2, 2, 20)
     assert batch["Y_t_aux"].shape == (2, 3, 20)
+
+
+def test_aux_at_contexts_appends_an_offgrid_set(loader):
+    """train.py:614-626: the aux variable sampled at all off-grid context locations becomes one more context set."""
+    ld = TaskLoader(context=loader.context, target=loader.target, aux_at_contexts=loader.aux_at_targets)
+    t = ld(DATES[0], "all", "all")
+    assert len(t["X_c"]) == 4 and t["X_c"][3].shape == (2, 20) and t["Y_c"][3].shape == (3, 20)
+    assert np.array_equal(t["X_c"][3], t["X_c"][2])
+    grid_only = TaskLoader(context=loader.context[:2], aux_at_contexts=loader.aux_at_targets)(DATES[0], "all")
+    assert grid_only["X_c"][2].shape == (2, 0) and grid_only["Y_c"][2].shape == (3, 0)
