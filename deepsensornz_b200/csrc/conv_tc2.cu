@@ -555,7 +555,7 @@ int build_plan2(int kind, int n_chunks, int pitch, int py, int px, int wide, cnp
     p->kb_chunk0[p->n_kb] = chunk0; p->kb_wci0[p->n_kb] = wci0; p->kb_type[p->n_kb] = type; ++p->n_kb;
   };
   if (kind == KIND_K5S1 || kind == KIND_K5S1_DGRAD) {
-    CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv plan: 5x5 needs 8 or 16 source chunks");
+    CNP_REQUIRE(n_chunks >= 2 && n_chunks <= 16 && n_chunks % 2 == 0, "conv plan: 5x5 needs 2, 4, .. 16 source chunks");
     int nt = 0;
     for (int ky = 0; ky < 5; ++ky)
       for (int kx = 0; kx < 5; ++kx)

@@ -40,6 +40,7 @@ struct cnp_wg_pass {
   int a0, astep;               // accumulator j uses the X operand at pixel offset a0 + j*astep
   int slot[CNP_WG_MAX_ACC][2][2];   // tap index (ky*k+kx) of [accumulator][row half][column half], -1 = discard
   int ci0, ci1;                // input-channel base of the two row halves
+  int ky0, n_grp;              // narrow inputs: the pass covers kernel rows ky0 .. ky0 + n_grp - 1 (one row group each)
 };
 
 struct cnp_wg_args {
@@ -51,6 +52,8 @@ struct cnp_wg_args {
   int dup;                       // 1: N = 128 operand [dY(p) ; dY(p-1)] (column half 1 = tap a+1)
   int ws_acc;                    // accumulators per CTA in the workspace layout
   int cluster;                   // 5: the five ky passes of a K-split slice form a cluster and share the dY stream
+  int narrow;                    // >0: chunks per row group -- the 16 X planes are [kernel row][chunk] (few input channels)
+  int grp_shift;                 // narrow: pixel shift between consecutive row groups (= padded row pitch)
   cnp_wg_pass pass[CNP_WG_MAX_PASS];
 };
 
@@ -78,6 +81,18 @@ __device__ __forceinline__ void wg_issue_n(int nacc, int k0, int k1, uint32_t tm
     for (int j = 0; j < nacc; ++j)
       tc::mma_bf16_ss_lohi(tmem + j * ncols, ((xs16 + ks * 16 + j * astep) & 0x3FFFu) | lbo, a_hi,
                            ((ds16 + ks * 16) & 0x3FFFu) | lbo, b_hi, idesc, ks > k0 ? 1u : acc0);
+}
+
+// accumulator j, TMEM lane m, column half -> (tap index or -1, input channel)
+__device__ __forceinline__ int wg_slot(const cnp_wg_args& a, const cnp_wg_pass& ps, int m, int j, int colhalf, int* ci) {
+  if (a.narrow) {
+    const int rows = a.narrow * 8, g = m / rows, kx = ps.a0 + j * ps.astep + colhalf;
+    *ci = m - g * rows;
+    return (g < ps.n_grp && kx < 5) ? (ps.ky0 + g) * 5 + kx : -1;
+  }
+  const int half = m >> 6;
+  *ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
+  return ps.slot[j][half][colhalf];
 }
 
 // CL = true: instantiation with the cluster / multicast code (a kernel that contains cluster instructions is scheduled
@@ -130,13 +145,27 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         const long long p0 = a.p_start + (long long)ti * P;
         uint8_t* xs = smem + s * stage_b;
         uint8_t* ds = xs + x_tile_b;
-        tc::mbar_expect_tx(full + s, 16u * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u);
         const __nv_bfloat16* xb = a.x + (long long)b * a.x_bs + (p0 + ps.base_off) * 8;
-        for (int c = 0; c < 16; ++c) {
-          const __nv_bfloat16* src;
-          if (c < 8 || ps.shift_px < 0) src = xb + (long long)(ps.chunk0 + c) * a.x_plane;
-          else src = xb + (long long)(ps.chunk0 + c - 8) * a.x_plane + (long long)ps.shift_px * 8;
-          tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + XPAD) * 16u, full + s);
+        if (a.narrow) {
+          // few input channels: plane c = (row group c / narrow, chunk c % narrow); unused planes are never read back
+          const int nxp = ps.n_grp * a.narrow;
+          tc::mbar_expect_tx(full + s, (uint32_t)nxp * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u);
+          int c = 0;
+          for (int g = 0; g < ps.n_grp; ++g)
+            for (int k = 0; k < a.narrow; ++k, ++c)
+              tc::bulk_g2s(xs + c * x_plane_b, xb + (long long)k * a.x_plane + (long long)g * a.grp_shift * 8,
+                           (uint32_t)(P + XPAD) * 16u, full + s);
+        } else {
+          // (keep this loop's trip count constant: with a run-time bound it is not unrolled and the single producer
+          // thread becomes the bottleneck of the whole kernel -- measured 830 us instead of 446 us on the 128-ch layer)
+          tc::mbar_expect_tx(full + s, 16u * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const __nv_bfloat16* src;
+            if (c < 8 || ps.shift_px < 0) src = xb + (long long)(ps.chunk0 + c) * a.x_plane;
+            else src = xb + (long long)(ps.chunk0 + c - 8) * a.x_plane + (long long)ps.shift_px * 8;
+            tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + XPAD) * 16u, full + s);
+          }
         }
         const __nv_bfloat16* db = a.dy + (long long)b * a.dy_bs + p0 * 8;
         for (int c = 0; c < ndy; ++c) {   // planes 8..15 (dup): the same chunks one pixel earlier
@@ -240,13 +269,12 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       tc::mbar_wait(done, 0);
       tc::fence_after_sync();
       const int m = q * 32 + lane;
-      const int half = m >> 6;
-      const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
       const int ncols = a.dup ? 128 : 64;
       for (int j = 0; j < ps.n_acc; ++j) {
         float* wsp = a.ws ? a.ws + ((((size_t)blockIdx.y * a.ksplit + blockIdx.x) * a.ws_acc + j) * 128 + m) * 128 : nullptr;
         for (int hc = 0; hc < ncols / 32; ++hc) {
-          const int slot = ps.slot[j][half][hc >> 1];
+          int ci;
+          const int slot = wg_slot(a, ps, m, j, hc >> 1, &ci);
           float v[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * ncols + hc * 32, v);
           tc::tmem_ld_wait();
@@ -272,26 +300,37 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
-// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel
+// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel.
+// Thread = 4 consecutive columns (one 16 B load per partial) x one slice of WG_RED_KS partials (blockIdx.y), all loads
+// of the slice in flight together; slices meet in dw with one atomic per value (the workspace is ~30 MB per launch:
+// the first version, one thread per element looping over all partials, ran at a quarter of the HBM rate).
+constexpr int WG_RED_KS = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
   const int ncols = a.dup ? 128 : 64;
-  const int total = a.n_pass * a.ws_acc * 128 * ncols;
-  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
-    const int col = e % ncols, m = (e / ncols) & 127, jj = e / (ncols * 128), j = jj % a.ws_acc, pass = jj / a.ws_acc;
+  const int total4 = a.n_pass * a.ws_acc * 128 * (ncols / 4);
+  const int k0 = blockIdx.y * WG_RED_KS, k1 = min(k0 + WG_RED_KS, a.ksplit);
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total4; e += gridDim.x * 256) {
+    const int col = (e % (ncols / 4)) * 4, m = (e / (ncols / 4)) & 127, jj = e / ((ncols / 4) * 128);
+    const int j = jj % a.ws_acc, pass = jj / a.ws_acc;
     const cnp_wg_pass& ps = a.pass[pass];
     if (j >= ps.n_acc) continue;
-    const int half = m >> 6, co = col & 63;
-    const int slot = ps.slot[j][half][col >> 6];
-    const int ci = (half ? ps.ci1 : ps.ci0) + (m & 63);
+    int ci;
+    const int slot = wg_slot(a, ps, m, j, col >> 6, &ci);
     if (slot < 0 || ci >= a.Cin) continue;
     const float* src = a.ws + (((size_t)pass * a.ksplit * a.ws_acc + j) * 128 + m) * 128 + col;
     const size_t stride = (size_t)a.ws_acc * 128 * 128;
-    float s0 = 0.f, s1 = 0.f;
-    int k = 0;
-    for (; k + 1 < a.ksplit; k += 2) { s0 += __ldg(src + (size_t)k * stride); s1 += __ldg(src + (size_t)(k + 1) * stride); }
-    if (k < a.ksplit) s0 += __ldg(src + (size_t)k * stride);
-    a.dw[((size_t)co * a.Cin + ci) * a.KK + slot] += s0 + s1;
+    float4 v[WG_RED_KS];
+#pragma unroll
+    for (int k = 0; k < WG_RED_KS; ++k)
+      v[k] = (k0 + k < k1) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(k0 + k) * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 sum = v[0];
+#pragma unroll
+    for (int k = 1; k < WG_RED_KS; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+    const int co = col & 63;
+    float* dst = a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot;
+    const size_t cs = (size_t)a.Cin * a.KK;
+    atomicAdd(dst, sum.x); atomicAdd(dst + cs, sum.y); atomicAdd(dst + 2 * cs, sum.z); atomicAdd(dst + 3 * cs, sum.w);
   }
 }
 
@@ -332,7 +371,7 @@ blk_channel_sum_kernel(const __nv_bfloat16* __restrict__ v, long long bs, int cb
 
 }  // namespace
 
-enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2 };
+enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2, WG_K5S1_NARROW = 3 };
 
 // dw (+=) torch layout [64][Cin][k][k] fp32; dbias (+=) [64] fp32 or NULL (sum of dy over batch and pixels).  x: source view (n_chunks = 8 or 16; 32 = phase tensor for
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
@@ -362,7 +401,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   static const bool no_dup = getenv("CNP_WGRAD_NO_DUP") != nullptr;
   // only where it pays: 128-channel inputs (3 MMAs of 64 cycles instead of 5 of 48 per K step).  With 64-channel
   // inputs the second dY copy makes the stage L2-bound (measured 18 % slower), so those keep N = 64.
-  a.dup = (!no_dup && kind == WG_K5S1 && n_chunks == 16) ? 1 : 0;
+  a.dup = ((!no_dup && kind == WG_K5S1 && n_chunks == 16) || kind == WG_K5S1_NARROW) ? 1 : 0;
   auto clear_slots = [](cnp_wg_pass& p) {
     for (int j = 0; j < CNP_WG_MAX_ACC; ++j)
       for (int h = 0; h < 2; ++h) p.slot[j][h][0] = p.slot[j][h][1] = -1;
@@ -397,6 +436,21 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
           for (int kx = 0; kx < 3; ++kx) { p.slot[kx][0][0] = tap(ky, kx); p.slot[kx][1][0] = tap(ky, kx + 3); }
         }
       }
+    }
+  } else if (kind == WG_K5S1_NARROW) {
+    // few input channels (the folded first layer, fold_in.cu): the 128 M rows hold G = 16 / n_chunks kernel ROWS of
+    // the same n_chunks source chunks (row group g = the source shifted by g image rows), and the N = 128 operand
+    // [dY(p) ; dY(p-1)] adds the column pairs: 3 MMAs per 16-pixel K step cover G x 5 taps.
+    CNP_REQUIRE(n_chunks >= 1 && n_chunks <= 8 && Cin == n_chunks * 8, "conv_tc_wgrad: narrow 5x5 needs 1..8 source chunks");
+    a.KK = 25;
+    a.narrow = n_chunks; a.grp_shift = Wp;
+    const int G = 16 / n_chunks;
+    for (int ky0 = 0; ky0 < 5; ky0 += G, ++np) {
+      cnp_wg_pass& p = a.pass[np];
+      clear_slots(p);
+      p.chunk0 = 0; p.shift_px = -1; p.base_off = (ky0 - 2) * Wp - 2; p.ci0 = p.ci1 = 0;
+      p.ky0 = ky0; p.n_grp = (5 - ky0 < G) ? 5 - ky0 : G;
+      p.n_acc = 3; p.a0 = 0; p.astep = 2;
     }
   } else if (kind == WG_K1) {
     CNP_REQUIRE(n_chunks == 8 && Cin == 64, "conv_tc_wgrad: 1x1 needs an 8-chunk source");
@@ -488,7 +542,8 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   }
   CNP_LAUNCH_CHECK("wgrad_tc_kernel");
   if (a.ws) {
-    wgrad_reduce_kernel<<<2 * sms, 256, 0, st>>>(a);
+    const int total4 = np * a.ws_acc * 128 * ((a.dup ? 128 : 64) / 4);
+    wgrad_reduce_kernel<<<dim3(cnp_cdiv(total4, 256), cnp_cdiv(a.ksplit, WG_RED_KS)), 256, 0, st>>>(a);
     CNP_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   return 0;

@@ -524,7 +524,7 @@ class Engine:
         if os.environ.get("CNP_NO_PREPACK"):
             return
         stale = [(k, r) for k, r in self._pack_reqs.items()
-                 if self._packed.get(k) is not None and self._packed[k][0] != r[0]._version]
+                 if self._packed.get(k) is not None and self._packed[k][0] != self._pack_version(r)]
         if not stale:
             return
         if self._pack_stream is None:
@@ -532,31 +532,46 @@ class Engine:
         main = torch.cuda.current_stream()
         self._pack_stream.wait_stream(main)
         with torch.cuda.stream(self._pack_stream):
-            for k, (w, kind, n_chunks, py, px, co_off, n_out) in stale:
-                buf = self._packed[k][1]
-                Cout, Cin, kk, _ = w.shape
-                self._call("cnp_conv_tc2_pack", _ptr(w), Cout, Cin, kk, kind, n_chunks, py, px, co_off, n_out, _ptr(buf),
-                           _stream())
-                self._packed[k] = (w._version, buf)
+            for k, r in stale:
+                self._do_pack(k, r, self._packed[k][1])
             self._pack_event = torch.cuda.Event()
             self._pack_event.record(self._pack_stream)
 
+    @staticmethod
+    def _pack_version(req) -> tuple:
+        w, fold = req[0], req[7]
+        return (w._version,) if fold is None else (w._version, fold[0]._version, fold[1]._version)
+
+    def _do_pack(self, key: str, req, buf: torch.Tensor) -> None:
+        """Pack (and, for the first layer, fold the initial 1x1 into) one weight tensor on the current stream."""
+        w, kind, n_chunks, py, px, co_off, n_out, fold = req
+        ver = self._pack_version(req)
+        Cout, Cin, k, _ = w.shape
+        src = w
+        if fold is not None:
+            w1, b1 = fold
+            Cp = n_chunks * 8
+            src = self._buf(f"fold.{key}", (Cout, Cp, k, k))
+            self._call("cnp_fold_in_fwd", _ptr(w), _ptr(w1), _ptr(b1), Cout, Cin, w1.shape[1], Cp, k, _ptr(src), _stream())
+            Cin = Cp
+        self._call("cnp_conv_tc2_pack", _ptr(src), Cout, Cin, k, kind, n_chunks, py, px, co_off, n_out, _ptr(buf),
+                   _stream())
+        self._packed[key] = (ver, buf)
+
     def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0,
-                        n_out=64) -> torch.Tensor:
-        self._pack_reqs[key] = (w, kind, n_chunks, py, px, co_off, n_out)
+                        n_out=64, fold=None) -> torch.Tensor:
+        """``fold=(W1, b1)``: ``w`` is the first 5x5 and the packed tensor is the folded 5x5 over [x ; 1] (fold_in.cu)."""
+        req = (w, kind, n_chunks, py, px, co_off, n_out, fold)
+        self._pack_reqs[key] = req
         if self._pack_event is not None:          # first consumer of the step: order after the side-stream packing
             torch.cuda.current_stream().wait_event(self._pack_event)
             self._pack_event = None
         ent = self._packed.get(key)
-        ver = w._version
-        if ent is not None and ent[0] == ver and ent[1].device == w.device:
+        if ent is not None and ent[0] == self._pack_version(req) and ent[1].device == w.device:
             return ent[1]
         nbytes = _cabi.lib().cnp_conv_tc2_packed_bytes(kind, n_chunks, n_out)
         buf = ent[1] if ent is not None else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-        Cout, Cin, k, _ = w.shape
-        self._call("cnp_conv_tc2_pack", _ptr(w), Cout, Cin, k, kind, n_chunks, py, px, co_off, n_out, _ptr(buf),
-                   _stream())
-        self._packed[key] = (ver, buf)
+        self._do_pack(key, req, buf)
         return buf
 
     def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0, n_out=64):
@@ -596,11 +611,21 @@ class Engine:
         res = self._levels(n1, n2)
         S = _stream()
         A = {}
-        h_init = self._blk("h_init", B, 8, n1, n2)
-        self._call("cnp_conv1x1_in_bf16", _ptr(enc), enc.stride(0), _ptr(u.initial_linear.weight),
-                   _ptr(u.initial_linear.bias), B, cfg.in_channels, 64, C.byref(h_init.view()), S)
+        # the initial 1x1 is folded into the first 5x5 (fold_in.cu) when that layer has stride 1: its input is then
+        # the encoder output itself, in 2 (4, 6) bf16 chunks with a constant-1 channel carrying the 1x1's bias
+        fold_in = st[0] == 1 and cfg.in_channels + 1 <= 64 and not os.environ.get("CNP_NO_FOLD_IN")
+        if fold_in:
+            cb0 = 2 * ((cfg.in_channels + 1 + 15) // 16)
+            h_init = self._blk("x_aug", B, cb0, n1, n2)
+            self._call("cnp_blk_from_nchw_f32_ones", _ptr(enc), enc.stride(0), B, cfg.in_channels, n1, n2,
+                       C.byref(h_init.view()), cb0, S)
+        else:
+            cb0 = 8
+            h_init = self._blk("h_init", B, 8, n1, n2)
+            self._call("cnp_conv1x1_in_bf16", _ptr(enc), enc.stride(0), _ptr(u.initial_linear.weight),
+                       _ptr(u.initial_linear.bias), B, cfg.in_channels, 64, C.byref(h_init.view()), S)
         cat = [self._blk(f"cat{i}", B, 8 if i == L - 1 else 16, res[i][0], res[i][1]) for i in range(L)]
-        A["h_init"], A["cat"] = h_init, cat
+        A["h_init"], A["cat"], A["fold_in"] = h_init, cat, fold_in
         phases = [None] * L
         x = h_init
         # layer i's epilogue also writes the space-to-depth copy that the stride-2 layer i+1 reads
@@ -615,7 +640,11 @@ class Engine:
                 phases[i + 1] = self._blk(f"phase{i + 1}", B, 32, res[i + 1][0], res[i + 1][1])
                 out._s2d_view = phases[i + 1].view()
                 out.s2d = C.pointer(out._s2d_view)
-            if st[i] == 1:
+            if st[i] == 1 and i == 0 and fold_in:
+                wpk = self._packed_weights("before0.folded", lyr.weight, K.KIND_K5S1, cb0,
+                                           fold=(u.initial_linear.weight, u.initial_linear.bias))
+                self._conv_tc(x.view(0), cb0, wpk, K.KIND_K5S1, out, B)
+            elif st[i] == 1:
                 wpk = self._packed_weights(f"before{i}", lyr.weight, K.KIND_K5S1, 8)
                 self._conv_tc(x.view(0), 8, wpk, K.KIND_K5S1, out, B)
             else:
@@ -719,6 +748,22 @@ class Engine:
             name = P + f"before_turn_layers.{i}"
             lyr = u.before_turn_layers[i]
             x_src = cat[i - 1] if i > 0 else h_init
+            if i == 0 and A["fold_in"]:
+                # folded first layer: tensor-core wgrad w.r.t. the folded weights (few input channels: the M rows
+                # hold kernel rows instead), then the chain rule to W5 / W1 / b1; no dgrad (the encoder is not trained)
+                il = u.initial_linear
+                cp = x_src.CB * 8
+                dwf = self._buf("dwf0", (64, cp, 5, 5))
+                dwf.zero_()
+                wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
+                ws = self._buf("wgrad_ws", (wsb // 4,))
+                self._call("cnp_conv_tc_wgrad", C.byref(x_src.view(0)), x_src.CB, C.byref(d_cat[0].view(0)),
+                           K.WG_K5S1_NARROW, _ptr(dwf), _ptr(grads[name + ".bias"]), cp, B, _ptr(ws), wsb, S,
+                           work=(2.0 * B * n1 * n2 * 64 * cp * 25, 0.0))
+                self._call("cnp_fold_in_bwd", _ptr(dwf), _ptr(lyr.weight), _ptr(il.weight), _ptr(il.bias), 64, 64,
+                           cfg.in_channels, cp, 5, _ptr(grads[name + ".weight"]),
+                           _ptr(grads[P + "initial_linear.weight"]), _ptr(grads[P + "initial_linear.bias"]), S)
+                continue
             if st[i] == 2:
                 wgrad_tc(A["phases"][i].view(0), 32, d_cat[i].view(0), K.WG_K5S2, name, 64)
             else:

@@ -97,7 +97,7 @@ typedef struct cnp_conv_out {
 } cnp_conv_out;
 
 enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5 };
-enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2 };
+enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2, CNP_WG_K5S1_NARROW = 3 /* 1..8 source chunks */ };
 
 long long cnp_conv_tc_packed_bytes(int kind, int n_chunks);
 int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px, int co_off,
@@ -135,6 +135,15 @@ int cnp_blk_space_to_depth(const cnp_blk* x, int n_chunks, const cnp_blk* y /*32
 int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B, int C, int H, int W, const cnp_blk* dst,
                           cnp_stream_t s);
 int cnp_blk_to_nchw_f32(const cnp_blk* src, int B, int C, float* dst, long long dst_bstride, cnp_stream_t s);
+/* conversion into n_chunks chunks with channel C := 1 inside the image (input of the folded first layer) */
+int cnp_blk_from_nchw_f32_ones(const float* src, long long src_bstride, int B, int C, int H, int W, const cnp_blk* dst,
+                               int n_chunks, cnp_stream_t s);
+/* initial 1x1 (neuralprocesses UNet.initial_linear) folded into the first 5x5 (before_turn_layers[0]):
+ * wf [Cout][Cp][k*k] = W5 . [W1 | b1] (channels Cin+1..Cp-1 zero); bwd maps the folded gradient dwf back (+=). */
+int cnp_fold_in_fwd(const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin, int Cp, int k,
+                    float* wf, cnp_stream_t s);
+int cnp_fold_in_bwd(const float* dwf, const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin,
+                    int Cp, int k, float* dw5, float* dw1, float* db1 /*or NULL*/, cnp_stream_t s);
 
 /* ---- (3) SetConv decoder, grid -> off-grid targets -------------------------------------------
  * replaces: neuralprocesses SetConv(scale=1/ppu) in the decoder chain + its autograd (A.5). */

@@ -51,5 +51,26 @@ def main():
         print(f"wgrad {cin:3d}ch {H}^2 | " + " | ".join(res), flush=True)
 
 
+def narrow():
+    """the folded first layer: 16-channel [x ; 1] input, WG_K5S1_NARROW"""
+    B, H, dev = 16, 304, torch.device("cuda")
+    wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
+    ws = torch.empty(wsb // 4, device=dev)
+    for nch in (2, 4):
+        x = _Blk(B, nch, H, H, dev)
+        x.t.normal_()
+        dy = _Blk(B, 8, H, H, dev)
+        dy.t.normal_()
+        for blk, cb in ((x, nch), (dy, 8)):
+            v = blk.t[:B * blk.bstride].view(B, cb, H + 4, H + 4, 8)
+            v[:, :, :2] = 0; v[:, :, -2:] = 0; v[:, :, :, :2] = 0; v[:, :, :, -2:] = 0
+        dw = torch.zeros(64, nch * 8, 5, 5, device=dev)
+        db = torch.zeros(64, device=dev)
+        t = timeit(lambda: _cabi.call("cnp_conv_tc_wgrad", C.byref(x.view()), nch, C.byref(dy.view()), _cabi.WG_K5S1_NARROW,
+                                      dw.data_ptr(), db.data_ptr(), nch * 8, B, ws.data_ptr(), wsb, S()))
+        print(f"narrow wgrad {nch * 8:3d}ch {H}^2: {t * 1e3:7.1f} us", flush=True)
+
+
 if __name__ == "__main__":
+    narrow()
     main()
