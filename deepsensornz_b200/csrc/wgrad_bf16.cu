@@ -98,7 +98,7 @@ __device__ __forceinline__ int wg_slot(const cnp_wg_args& a, const cnp_wg_pass& 
 // CL = true: instantiation with the cluster / multicast code (a kernel that contains cluster instructions is scheduled
 // differently even when launched without a cluster, which costs ~15 % here, hence two instantiations)
 template <bool CL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(224, 1)
 wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   const int a_cluster = CL ? a.cluster : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -137,6 +137,18 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
 
   if (warp == 0) {
     if (tc::elect_one()) {
+      // per-plane source offsets are fixed for the whole CTA: computed once, so that the per-stage work of this single
+      // producer thread is 32 straight-line copy instructions (with the offsets recomputed per copy, or a loop with a
+      // run-time bound, the producer becomes the bottleneck: 830 us instead of 446 us on the 128-channel layer)
+      const int nxp = a.narrow ? ps.n_grp * a.narrow : 16;   // X planes really loaded (the rest is never read back)
+      long long xoff[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (a.narrow) xoff[c] = (long long)(c % a.narrow) * a.x_plane + (long long)(c / a.narrow) * a.grp_shift * 8;
+        else if (c < 8 || ps.shift_px < 0) xoff[c] = (long long)(ps.chunk0 + c) * a.x_plane;
+        else xoff[c] = (long long)(ps.chunk0 + c - 8) * a.x_plane + (long long)ps.shift_px * 8;
+      }
+      const uint32_t tx = (uint32_t)nxp * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u;
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
         const int s = it % WG_STAGES;
@@ -144,37 +156,38 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         const int b = t / a.tiles_per_img, ti = t % a.tiles_per_img;
         const long long p0 = a.p_start + (long long)ti * P;
         uint8_t* xs = smem + s * stage_b;
-        uint8_t* ds = xs + x_tile_b;
+        tc::mbar_expect_tx(full + s, tx);       // the whole stage (X planes from here, dY planes from warp 6)
         const __nv_bfloat16* xb = a.x + (long long)b * a.x_bs + (p0 + ps.base_off) * 8;
-        if (a.narrow) {
-          // few input channels: plane c = (row group c / narrow, chunk c % narrow); unused planes are never read back
-          const int nxp = ps.n_grp * a.narrow;
-          tc::mbar_expect_tx(full + s, (uint32_t)nxp * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u);
-          int c = 0;
-          for (int g = 0; g < ps.n_grp; ++g)
-            for (int k = 0; k < a.narrow; ++k, ++c)
-              tc::bulk_g2s(xs + c * x_plane_b, xb + (long long)k * a.x_plane + (long long)g * a.grp_shift * 8,
-                           (uint32_t)(P + XPAD) * 16u, full + s);
-        } else {
-          // (keep this loop's trip count constant: with a run-time bound it is not unrolled and the single producer
-          // thread becomes the bottleneck of the whole kernel -- measured 830 us instead of 446 us on the 128-ch layer)
-          tc::mbar_expect_tx(full + s, 16u * (uint32_t)(P + XPAD) * 16u + (uint32_t)ndy * (uint32_t)P * 16u);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const __nv_bfloat16* src;
-            if (c < 8 || ps.shift_px < 0) src = xb + (long long)(ps.chunk0 + c) * a.x_plane;
-            else src = xb + (long long)(ps.chunk0 + c - 8) * a.x_plane + (long long)ps.shift_px * 8;
-            tc::bulk_g2s(xs + c * x_plane_b, src, (uint32_t)(P + XPAD) * 16u, full + s);
-          }
-        }
+        for (int c = 0; c < 16; ++c)
+          if (c < nxp) tc::bulk_g2s(xs + c * x_plane_b, xb + xoff[c], (uint32_t)(P + XPAD) * 16u, full + s);
+      }
+    }
+  } else if (warp == 6) {
+    // second producer thread: the dY planes of every stage (one thread issuing all ~32 copies of a stage limits the
+    // kernel; the barrier's transaction count is armed by warp 0 -- completions may arrive first, the phase cannot
+    // complete before warp 0's arrive.expect_tx)
+    if (tc::elect_one()) {
+      long long doff[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) doff[c] = (long long)(c & 7) * a.dy_plane - (c >> 3) * 8;   // 8..15 (dup): one pixel earlier
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
+        const int s = it % WG_STAGES;
+        tc::mbar_wait(empty + s, ((it / WG_STAGES) & 1) ^ 1);
+        const int b = t / a.tiles_per_img, ti = t % a.tiles_per_img;
+        const long long p0 = a.p_start + (long long)ti * P;
+        uint8_t* ds = smem + s * stage_b + x_tile_b;
         const __nv_bfloat16* db = a.dy + (long long)b * a.dy_bs + p0 * 8;
-        for (int c = 0; c < ndy; ++c) {   // planes 8..15 (dup): the same chunks one pixel earlier
-          const __nv_bfloat16* src = db + (long long)(c & 7) * a.dy_plane - (c >> 3) * 8;
-          if ((CL && a_cluster > 1)) {            // every CTA of the cluster needs the same dY tile: load a fifth, multicast it
-            if ((uint32_t)c % (uint32_t)a_cluster == crank)
-              tc::bulk_g2s_mc(ds + c * dy_plane_b, src, (uint32_t)P * 16u, full + s, cmask);
-          } else {
-            tc::bulk_g2s(ds + c * dy_plane_b, src, (uint32_t)P * 16u, full + s);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if (c < ndy) {
+            if ((CL && a_cluster > 1)) {            // every CTA of the cluster needs the same dY tile: load a fifth, multicast it
+              if ((uint32_t)c % (uint32_t)a_cluster == crank)
+                tc::bulk_g2s_mc(ds + c * dy_plane_b, db + doff[c], (uint32_t)P * 16u, full + s, cmask);
+            } else {
+              tc::bulk_g2s(ds + c * dy_plane_b, db + doff[c], (uint32_t)P * 16u, full + s);
+            }
           }
         }
       }
@@ -219,7 +232,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       }
       tc::mma_commit(done);
     }
-  } else {
+  } else if (warp < 6) {
     // epilogue warps 2..5 -> TMEM lane quadrant (warp & 3)
     const int q = warp & 3;
     const bool has_work = blockIdx.x < total_tiles;
@@ -377,7 +390,7 @@ enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2, WG_K5S1_NARROW = 3 };
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
 // Bytes of the optional partial-sum workspace (max over kinds: 5 passes x <=148 CTAs x 5 accumulators x 32 KB).
 CNP_API long long cnp_conv_tc_wgrad_workspace_bytes(void) {
-  return (long long)148 * 3 * 128 * 128 * sizeof(float);   // <= 148 CTAs x <= 3 accumulators x [128][128] floats
+  return (long long)148 * 5 * 128 * 128 * sizeof(float);   // <= 148 CTAs x <= 5 accumulators x [128][128] floats
 }
 
 CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dbias,
@@ -401,7 +414,8 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   static const bool no_dup = getenv("CNP_WGRAD_NO_DUP") != nullptr;
   // only where it pays: 128-channel inputs (3 MMAs of 64 cycles instead of 5 of 48 per K step).  With 64-channel
   // inputs the second dY copy makes the stage L2-bound (measured 18 % slower), so those keep N = 64.
-  a.dup = ((!no_dup && kind == WG_K5S1 && n_chunks == 16) || kind == WG_K5S1_NARROW) ? 1 : 0;
+  static const bool narrow_dup = getenv("CNP_WGRAD_NARROW_DUP") != nullptr;
+  a.dup = ((!no_dup && kind == WG_K5S1 && n_chunks == 16) || (kind == WG_K5S1_NARROW && narrow_dup)) ? 1 : 0;
   auto clear_slots = [](cnp_wg_pass& p) {
     for (int j = 0; j < CNP_WG_MAX_ACC; ++j)
       for (int h = 0; h < 2; ++h) p.slot[j][h][0] = p.slot[j][h][1] = -1;
@@ -450,7 +464,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
       clear_slots(p);
       p.chunk0 = 0; p.shift_px = -1; p.base_off = (ky0 - 2) * Wp - 2; p.ci0 = p.ci1 = 0;
       p.ky0 = ky0; p.n_grp = (5 - ky0 < G) ? 5 - ky0 : G;
-      p.n_acc = 3; p.a0 = 0; p.astep = 2;
+      if (a.dup) { p.n_acc = 3; p.a0 = 0; p.astep = 2; } else { p.n_acc = 5; p.a0 = 0; p.astep = 1; }
     }
   } else if (kind == WG_K1) {
     CNP_REQUIRE(n_chunks == 8 && Cin == 64, "conv_tc_wgrad: 1x1 needs an 8-chunk source");
@@ -509,7 +523,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = 1; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attrs; cfg.numAttrs = 1;
+  cfg.blockDim = dim3(224); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attrs; cfg.numAttrs = 1;
   a.cluster = 1;
   // Measured on B200: the 5-CTA cluster halves the L2 traffic of the dup path but runs 2.2x SLOWER (only 26 clusters
   // fit, the five passes advance in lock-step, and cluster launches place CTAs differently), so it stays opt-in.
@@ -538,7 +552,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
     cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, a);
     if (le != cudaSuccess) { cnp_set_error("wgrad_tc_kernel: %s", cudaGetErrorString(le)); return (int)le; }
   } else {   // plain launch: a launch carrying a cluster attribute (even 1x1x1) was measured ~15 % slower here
-    wgrad_tc_kernel<false><<<cfg.gridDim, 192, smem, st>>>(a);
+    wgrad_tc_kernel<false><<<cfg.gridDim, 224, smem, st>>>(a);
   }
   CNP_LAUNCH_CHECK("wgrad_tc_kernel");
   if (a.ws) {
