@@ -539,10 +539,33 @@ __device__ __forceinline__ void up2_src(int Y, int H, int* y0, int* y1, float* l
   int i0 = (int)src;
   *y0 = i0; *y1 = min(i0 + 1, H - 1); *lam = src - (float)i0;
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): two adjacent 8-channel pixels of a blocked row per instruction,
+// so that a warp's access covers whole 32 B sectors (two 16 B accesses at a 32 B stride each touch half a sector)
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint32_t* r, float* v) {   // 4 words = 8 bf16 -> fp32 (exact)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(r[i] << 16); v[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void pack8(const float* v, uint32_t* r) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    r[i] = *reinterpret_cast<const uint32_t*>(&t);
+  }
+}
+
 // forward: one thread per LOW-res pixel (u,v) and chunk: 3x3 source neighbourhood -> the 2x2 output block.
 //   Y = 2u   : 0.25 x[u-1] + 0.75 x[u]   (u-1 clamped: at u = 0 the source coordinate clamps to 0 -> x[0])
 //   Y = 2u+1 : 0.75 x[u]   + 0.25 x[u+1] (u+1 clamped)
-// evaluated exactly like up2_src (lambda = 0.75 / 0.25, or 0 at the clamped border).
+// evaluated exactly like up2_src (lambda = 0.75 / 0.25, or 0 at the clamped border): horizontally once per source
+// row (even / odd output column), then vertically; each output row leaves as one 32 B store.
 __global__ void __launch_bounds__(256)
 blk_upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, int x_cb, int H, int W,
                           __nv_bfloat16* __restrict__ y, long long y_bs, int y_cb) {
@@ -553,44 +576,131 @@ blk_upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_bs, i
   for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
     const int u = e / W, v = e - u * W;
     const int um = max(u - 1, 0), up = min(u + 1, H - 1), vm = max(v - 1, 0), vp = min(v + 1, W - 1);
-    float a[3][3][8];
     const int rr[3] = {um, u, up}, cc[3] = {vm, v, vp};
+    uint4 raw[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) ld8(xc + ((size_t)(rr[i] + 2) * Wp + cc[j] + 2) * 8, a[i][j]);
+      for (int j = 0; j < 3; ++j)
+        raw[i][j] = __ldg(reinterpret_cast<const uint4*>(xc + ((size_t)(rr[i] + 2) * Wp + cc[j] + 2) * 8));
     // lambda of the even output (towards index u from u-1) and of the odd one (towards u+1 from u)
     const float ly0 = u > 0 ? 0.75f : 0.f, ly1 = 0.25f, lx0 = v > 0 ? 0.75f : 0.f, lx1 = 0.25f;
+    float ev[3][8], od[3][8];   // per source row: even / odd output column
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      float a0[8], a1[8], a2[8];
+      unpack8(reinterpret_cast<const uint32_t*>(&raw[i][0]), a0);
+      unpack8(reinterpret_cast<const uint32_t*>(&raw[i][1]), a1);
+      unpack8(reinterpret_cast<const uint32_t*>(&raw[i][2]), a2);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        ev[i][k] = (1.f - lx0) * a0[k] + lx0 * a1[k];
+        od[i][k] = (1.f - lx1) * a1[k] + lx1 * a2[k];
+      }
+    }
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-      const int r0 = dy == 0 ? 0 : 1, r1 = dy == 0 ? 1 : 2;     // source rows (y0, y1) of this output row
+      const int r0 = dy, r1 = dy + 1;                        // source rows (y0, y1) of this output row
       const float ly = dy == 0 ? ly0 : ly1;
+      float o0[8], o1[8];
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int c0 = dx == 0 ? 0 : 1, c1 = dx == 0 ? 1 : 2;
-        const float lx = dx == 0 ? lx0 : lx1;
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t0 = (1.f - lx) * a[r0][c0][i] + lx * a[r0][c1][i];
-          const float t1 = (1.f - lx) * a[r1][c0][i] + lx * a[r1][c1][i];
-          o[i] = (1.f - ly) * t0 + ly * t1;
-        }
-        st8(yc + ((size_t)(2 * u + dy + 2) * W2p + (2 * v + dx) + 2) * 8, o);
+      for (int k = 0; k < 8; ++k) {
+        o0[k] = (1.f - ly) * ev[r0][k] + ly * ev[r1][k];
+        o1[k] = (1.f - ly) * od[r0][k] + ly * od[r1][k];
       }
+      uint32_t pk[8];
+      pack8(o0, pk);
+      pack8(o1, pk + 4);
+      stg256(yc + ((size_t)(2 * u + dy + 2) * W2p + 2 * v + 2) * 8, pk);
     }
   }
 }
 
-// dx[u,v] = sum over the <=4x4 hi-res pixels that reference (u,v); optional ReLU mask by act>0.
-// One thread per low-res pixel and chunk; the 4 tap weights per dimension are (0.25, 0.75, 0.75, 0.25) away from
-// the borders and follow up2_src at them.  Rows are combined horizontally first (4 loads per hi-res row).
+// dx[u,v] = sum over the <=4x4 hi-res pixels that reference (u,v); optional ReLU mask by act>0.  The 4 tap weights
+// per dimension are (0.25, 0.75, 0.75, 0.25) away from the borders and follow up2_src at them.
 __device__ __forceinline__ float up2_wgt(int Y, int H, int u) {
   if (Y < 0 || Y >= 2 * H) return 0.f;
   int y0, y1; float l;
   up2_src(Y, H, &y0, &y1, &l);
   return (y0 == u ? (1.f - l) : 0.f) + (y1 == u ? l : 0.f);
 }
+
+// Row kernel (W <= 1024): one block per low-res row u and chunk, thread v = low-res column.  Each thread loads only
+// ITS two hi-res columns (2v, 2v+1) of the four rows -- one 32 B load per row -- and combines them vertically
+// (V0, V1); the horizontal taps of the neighbours (V1 of v-1, V0 of v+1) come through shared memory.  Per thread:
+// 4 loads and 64 conversions instead of 16 and 128 (the per-pixel kernel below was issue-bound at 1.75 TB/s).
+__global__ void __launch_bounds__(1024)
+blk_upsample2x_bwd_row_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int H, int W,
+                              __nv_bfloat16* __restrict__ dx, long long dx_bs, int dx_cb,
+                              const __nv_bfloat16* __restrict__ act, long long act_bs, int act_cb, int accumulate) {
+  extern __shared__ __align__(16) float4 up_sm[];          // [4][blockDim.x]: V0 lo, V0 hi, V1 lo, V1 hi
+  const int u = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z, v = threadIdx.x, T = blockDim.x;
+  const int Wp = W + 4, Hp = H + 4, W2p = 2 * W + 4, H2p = 2 * H + 4;
+  const __nv_bfloat16* dyc = dy + (size_t)b * dy_bs + (size_t)(dy_cb + chunk) * H2p * W2p * 8;
+  float wy[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wy[k] = up2_wgt(2 * u - 1 + k, H, u);
+  float V0[8], V1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) V0[i] = V1[i] = 0.f;
+  if (v < W) {
+    // rows 2u-1 .. 2u+2 (the zero pad of dy makes the out-of-range rows, weight 0, safe to read)
+    uint32_t raw[4][8];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) ldg256(dyc + ((size_t)(2 * u - 1 + ky + 2) * W2p + 2 * v + 2) * 8, raw[ky]);
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      float a0[8], a1[8];
+      unpack8(raw[ky], a0);
+      unpack8(raw[ky] + 4, a1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { V0[i] = fmaf(wy[ky], a0[i], V0[i]); V1[i] = fmaf(wy[ky], a1[i], V1[i]); }
+    }
+  }
+  up_sm[v] = make_float4(V0[0], V0[1], V0[2], V0[3]);
+  up_sm[T + v] = make_float4(V0[4], V0[5], V0[6], V0[7]);
+  up_sm[2 * T + v] = make_float4(V1[0], V1[1], V1[2], V1[3]);
+  up_sm[3 * T + v] = make_float4(V1[4], V1[5], V1[6], V1[7]);
+  __syncthreads();
+  if (v >= W) return;
+  float wx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wx[k] = up2_wgt(2 * v - 1 + k, W, v);
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = wx[1] * V0[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[2], V1[i], s[i]);
+  if (v > 0) {           // hi-res column 2v-1 = V1 of the left neighbour
+    const float4 l0 = up_sm[2 * T + v - 1], l1 = up_sm[3 * T + v - 1];
+    const float L[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[0], L[i], s[i]);
+  }
+  if (v < W - 1) {       // hi-res column 2v+2 = V0 of the right neighbour
+    const float4 r0 = up_sm[v + 1], r1 = up_sm[T + v + 1];
+    const float R[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[3], R[i], s[i]);
+  }
+  const size_t pix = ((size_t)(u + 2) * Wp + v + 2) * 8;
+  __nv_bfloat16* dxc = dx + (size_t)b * dx_bs + (size_t)(dx_cb + chunk) * Hp * Wp * 8;
+  if (act) {
+    float av[8];
+    ld8(act + (size_t)b * act_bs + (size_t)(act_cb + chunk) * Hp * Wp * 8 + pix, av);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (!(av[i] > 0.f)) s[i] = 0.f;
+  }
+  if (accumulate) {
+    float old[8];
+    ld8(dxc + pix, old);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += old[i];
+  }
+  st8(dxc + pix, s);
+}
+
+// Per-pixel kernel (any width): one thread per low-res pixel and chunk, all 16 loads issued before the arithmetic.
 __global__ void __launch_bounds__(256)
 blk_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int H, int W,
                           __nv_bfloat16* __restrict__ dx, long long dx_bs, int dx_cb,
@@ -608,8 +718,6 @@ blk_upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs,
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
-    // the zero pad of dy (2 pixels) makes the out-of-range taps (weight 0) safe to read.  All 16 loads are issued
-    // before any arithmetic (16 independent 16 B loads in flight per thread).
     uint4 raw[4][4];
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky)
@@ -888,6 +996,8 @@ CNP_API int cnp_conv1x1_in_bf16(const float* x, long long x_bstride, const float
 
 CNP_API int cnp_blk_upsample2x_fwd(const cnp_blk* x, int n_chunks, const cnp_blk* y, int B, cudaStream_t st) {
   CNP_REQUIRE(x && y && y->H == 2 * x->H && y->W == 2 * x->W, "blk_upsample2x_fwd: geometry mismatch");
+  CNP_REQUIRE((reinterpret_cast<uintptr_t>(y->base) & 31) == 0 && (y->bstride & 15) == 0,
+              "blk_upsample2x_fwd: output must be 32-byte aligned (256-bit stores)");
   dim3 grid(cnp_cdiv(x->H * x->W, 256), n_chunks, B);
   blk_upsample2x_fwd_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x->base), x->bstride, x->cb_off,
                                                   x->H, x->W, reinterpret_cast<__nv_bfloat16*>(y->base), y->bstride,
@@ -900,12 +1010,21 @@ CNP_API int cnp_blk_upsample2x_bwd(const cnp_blk* dy, int n_chunks, const cnp_bl
                                    int B, cudaStream_t st) {
   CNP_REQUIRE(dy && dx && dy->H == 2 * dx->H && dy->W == 2 * dx->W, "blk_upsample2x_bwd: geometry mismatch");
   CNP_REQUIRE(!act || (act->H == dx->H && act->W == dx->W), "blk_upsample2x_bwd: mask geometry mismatch");
+  const __nv_bfloat16* ap = act ? reinterpret_cast<const __nv_bfloat16*>(act->base) : nullptr;
+  if (dx->W <= 1024 && (reinterpret_cast<uintptr_t>(dy->base) & 31) == 0 && (dy->bstride & 15) == 0) {
+    const int T = cnp_cdiv(dx->W, 32) * 32;
+    blk_upsample2x_bwd_row_kernel<<<dim3(dx->H, n_chunks, B), T, (size_t)4 * T * sizeof(float4), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride, dy->cb_off, dx->H, dx->W,
+        reinterpret_cast<__nv_bfloat16*>(dx->base), dx->bstride, dx->cb_off, ap, act ? act->bstride : 0,
+        act ? act->cb_off : 0, accumulate);
+    CNP_LAUNCH_CHECK("blk_upsample2x_bwd_row_kernel");
+    return 0;
+  }
   dim3 grid(cnp_cdiv(dx->H * dx->W, 256), n_chunks, B);
   blk_upsample2x_bwd_kernel<<<grid, 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride, dy->cb_off, dx->H, dx->W,
-      reinterpret_cast<__nv_bfloat16*>(dx->base), dx->bstride, dx->cb_off,
-      act ? reinterpret_cast<const __nv_bfloat16*>(act->base) : nullptr, act ? act->bstride : 0, act ? act->cb_off : 0,
-      accumulate);
+      reinterpret_cast<__nv_bfloat16*>(dx->base), dx->bstride, dx->cb_off, ap, act ? act->bstride : 0,
+      act ? act->cb_off : 0, accumulate);
   CNP_LAUNCH_CHECK("blk_upsample2x_bwd_kernel");
   return 0;
 }
