@@ -159,8 +159,8 @@ def run_reference(args):
     n_tasks = 1
     rate, sec, cores = cpu_reference_rate(n_tasks, max(1, args.steps), max(0, min(args.warmup, 1)))
     line = {
-        "impl": "reference", "metric": "convnp_train_tasks_per_s", "value": rate, "unit": "tasks/s", "n_gpus": 0,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": "convnp_train_tasks_per_s", "value": rate, "unit": "tasks/s",
+        "n_gpus": int(args.gpus), "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {k: v for k, v in workload_config(1, "fp32").items() if k != "static_context_dedup"},
         "cpu_baseline": {"value": rate, "unit": "tasks/s", "cores": cores, "kind": "port",
@@ -196,6 +196,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a GPU (the hot path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION, ahead of the one JSON line the driver reads
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.manual_seed(0)
     model = ConvNP(precision=args.precision, **model_kwargs(args.internal_density))
