@@ -339,37 +339,61 @@ class Engine:
     # (1) encoder
     # ------------------------------------------------------------------------------------------
     def encode(self, batch: DeviceBatch) -> torch.Tensor:
+        """SetConv encoders of all context sets into disjoint channel ranges of one [B, Cin, n1, n2] tensor.  The sets
+        are independent and individually too small to fill the GPU (a static field is encoded once, B = 1), so each
+        runs on its own side stream (fork / join on events; serial when profiling or with CNP_NO_MULTISTREAM)."""
         cfg, g, B = self.cfg, batch.grid, batch.B
         enc = self._buf("enc", (B, cfg.in_channels, g.n1, g.n2))
+        multi = len(batch.contexts) > 1 and self._prof is None and not os.environ.get("CNP_NO_MULTISTREAM")
+        main = torch.cuda.current_stream()
+        if multi:
+            if len(self._side_streams) < 4:
+                self._side_streams = [torch.cuda.Stream() for _ in range(4)]
+            fork = torch.cuda.Event()
+            fork.record(main)
         ch = 0
         for k, c in enumerate(batch.contexts):
-            s2 = self._scale2(self.module.encoder.set_convs[k].log_scale)
             Ck = cfg.dim_yc[k]
             if c.y.shape[1] != Ck:
                 raise ValueError(f"context set {k}: expected {Ck} channels, got {c.y.shape[1]}")
-            if c.gridded:
-                x1, x2 = c.x
-                Be = B if c.y_batched else 1     # a field shared by the whole batch is encoded once ...
-                by = 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) + Be * (Ck + 1) * g.n1 * g.n2)
-                N1, N2 = int(x1.shape[-1]), int(x2.shape[-1])
-                band = self._band_hint(c, g, s2)
-                ws, ws_bytes = None, 0
-                if band:
-                    ws_bytes = _cabi.lib().cnp_setconv_enc_grid_workspace_bytes(Be, Ck, N1, g.n1, g.n2, band)
-                    ws = self._buf("enc_ws", ((ws_bytes + 3) // 4,))
-                self._call("cnp_setconv_enc_grid_fwd", _ptr(x1), _ptr(x2), int(c.x_batched), _ptr(c.y), _ptr(c.mask),
-                           Be, Ck, N1, N2, c.mono[0], c.mono[1],
-                           g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
-                           band, _ptr(ws), ws_bytes, _stream(), work=(0.0, by))
-                if Be < B:                        # ... and its channels broadcast to the other tasks (plain D2D copy)
-                    enc[1:, ch:ch + Ck + 1].copy_(enc[:1, ch:ch + Ck + 1].expand(B - 1, -1, -1, -1))
+            if multi:
+                ss = self._side_streams[k % 4]
+                ss.wait_event(fork)
+                with torch.cuda.stream(ss):
+                    self._encode_set(batch, k, c, enc, ch)
             else:
-                by = 4.0 * (c.x.numel() + c.y.numel() + B * (Ck + 1) * g.n1 * g.n2)
-                self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
-                           int(c.x.shape[-1]), g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch,
-                           cfg.in_channels, _stream(), work=(0.0, by))
+                self._encode_set(batch, k, c, enc, ch)
             ch += Ck + 1
+        if multi:
+            for ss in self._side_streams[:min(4, len(batch.contexts))]:
+                main.wait_stream(ss)
         return enc
+
+    def _encode_set(self, batch: DeviceBatch, k: int, c: DeviceContext, enc: torch.Tensor, ch: int) -> None:
+        cfg, g, B = self.cfg, batch.grid, batch.B
+        s2 = self._scale2(self.module.encoder.set_convs[k].log_scale)
+        Ck = cfg.dim_yc[k]
+        if c.gridded:
+            x1, x2 = c.x
+            Be = B if c.y_batched else 1     # a field shared by the whole batch is encoded once ...
+            by = 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) + Be * (Ck + 1) * g.n1 * g.n2)
+            N1, N2 = int(x1.shape[-1]), int(x2.shape[-1])
+            band = self._band_hint(c, g, s2)
+            ws, ws_bytes = None, 0
+            if band:
+                ws_bytes = _cabi.lib().cnp_setconv_enc_grid_workspace_bytes(Be, Ck, N1, g.n1, g.n2, band)
+                ws = self._buf(f"enc_ws{k}", ((ws_bytes + 3) // 4,))
+            self._call("cnp_setconv_enc_grid_fwd", _ptr(x1), _ptr(x2), int(c.x_batched), _ptr(c.y), _ptr(c.mask),
+                       Be, Ck, N1, N2, c.mono[0], c.mono[1],
+                       g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
+                       band, _ptr(ws), ws_bytes, _stream(), work=(0.0, by))
+            if Be < B:                        # ... and its channels broadcast to the other tasks (plain D2D copy)
+                enc[1:, ch:ch + Ck + 1].copy_(enc[:1, ch:ch + Ck + 1].expand(B - 1, -1, -1, -1))
+        else:
+            by = 4.0 * (c.x.numel() + c.y.numel() + B * (Ck + 1) * g.n1 * g.n2)
+            self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
+                       int(c.x.shape[-1]), g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch,
+                       cfg.in_channels, _stream(), work=(0.0, by))
 
     @staticmethod
     def _band_hint(c: DeviceContext, g: GridSpec, scale2: float) -> int:
