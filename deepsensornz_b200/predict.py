@@ -15,6 +15,7 @@ over (time, x1, x2) when xarray is importable and X_t was an xarray object, else
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -53,6 +54,88 @@ class GridResult(dict):
 
 class Prediction(dict):
     pass
+
+
+def _inference_signature(b) -> tuple:
+    """Everything a captured forward bakes in: tensor shapes, internal grid, and -- because the banded encoder's
+    band width is derived on the host from them -- the coordinates of the gridded context sets."""
+    from .graph import batch_signature
+    coords = []
+    for c in b.contexts:
+        if c.gridded and c.x_host is not None:
+            coords.append(tuple(hash(np.ascontiguousarray(v).tobytes()) for v in c.x_host))
+    return batch_signature(b) + (tuple(coords),)
+
+
+def _pad_offgrid(hb, multiple: int = 16):
+    """Pad the off-grid context sets of a staged (host) batch to a multiple of ``multiple`` points with masked-out
+    entries (x = 0, y = 0, mask = 0): dates with slightly different station counts then share one captured graph.
+    Masked points add exactly 0 to every density / data sum, so the result is bit-identical to the unpadded call."""
+    from .engine import DeviceContext
+    out = []
+    for c in hb.contexts:
+        if c.gridded or c.x.device.type != "cpu":
+            out.append(c)
+            continue
+        B, _, N = c.x.shape
+        Np = max(multiple, -(-N // multiple) * multiple)
+        x = torch.zeros(B, 2, Np, dtype=torch.float32)
+        y = torch.zeros(B, c.y.shape[1], Np, dtype=torch.float32)
+        m = torch.zeros(B, 1, Np, dtype=torch.float32)
+        x[:, :, :N], y[:, :, :N] = c.x, torch.nan_to_num(c.y, nan=0.0)
+        valid = (~torch.isnan(c.y).any(dim=1, keepdim=True)).to(torch.float32)
+        m[:, :, :N] = valid if c.mask is None else c.mask.reshape(B, 1, N) * valid
+        out.append(DeviceContext(False, x, y, m))
+    hb.contexts = out
+    return hb
+
+
+class _GraphedForward:
+    """One captured inference forward (encoder -> UNet -> on-grid decoder -> head) for one batch signature.
+    ``predict`` over many dates is launch-bound when run eagerly (~35 launches and ~1.7 ms of Python / ctypes work
+    per task for ~1 ms of GPU work): the forward of the first task with a given signature runs eagerly (allocating
+    every workspace), is then captured, and the following tasks only copy their inputs into the static tensors and
+    replay.  Inputs travel through three rings of page-locked mirrors owned by the graph (allocating pinned memory per
+    task costs more than the forward itself)."""
+
+    SLOTS = 3
+
+    def __init__(self, model, static):
+        self.static = static                       # DeviceBatch whose tensors are the graph's inputs
+        self.graph = torch.cuda.CUDAGraph()
+        self.mirrors = [dict() for _ in range(self.SLOTS)]
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
+        # raw capture API: torch.cuda.graph() also empties the (device and pinned-host) allocator caches, ~20 ms
+        with torch.no_grad(), torch.cuda.stream(side):
+            self.graph.capture_begin()
+            out = model.engine.forward(static, with_loss=False)
+            self.graph.capture_end()
+        main.wait_stream(side)
+        self.mean, self.std = out["mean"], out["std"]
+
+    def load(self, hb, slot: int) -> None:
+        """H2D of a staged batch with the same signature into the static inputs (tensors that are the same device
+        objects -- the cached static context sets, the aux-at-targets field -- are skipped).  ``slot``: ring index of
+        the pinned mirrors; the caller guarantees the copies issued from this slot three tasks ago have completed."""
+        from .graph import _tensors
+        mir = self.mirrors[slot]
+        for i, (dst, src) in enumerate(zip(_tensors(self.static), _tensors(hb))):
+            if dst is None or dst is src:
+                continue
+            if src.device.type != "cpu":
+                dst.copy_(src, non_blocking=True)
+                continue
+            m = mir.get(i)
+            if m is None:
+                m = mir[i] = torch.empty(dst.shape, dtype=dst.dtype, pin_memory=True)
+            m.copy_(src)
+            dst.copy_(m, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        return self.mean, self.std
 
 
 def _target_coords(model, X_t, X_t_is_normalised: bool):
@@ -132,8 +215,16 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
     # so it overlaps the launches of the following tasks
     copy_stream = torch.cuda.Stream() if cuda else None
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=1)
+    pool = ThreadPoolExecutor(max_workers=int(os.environ.get('CONVNP_B200_DRAIN_THREADS', '3')))
     futures = [None, None, None]
+    # CUDA-graph replay of the forward for tasks sharing a batch signature (CONVNP_B200_PREDICT_GRAPH=0: eager)
+    # (capture + instantiation cost ~40 ms per signature: only for calls with enough tasks to win that back)
+    use_graph = (cuda and mode == "on-grid" and os.environ.get("CONVNP_B200_PREDICT_GRAPH", "1") != "0"
+                 and (len(tasks) >= 12 or os.environ.get("CONVNP_B200_PREDICT_GRAPH") == "1")
+                 and model.engine._prof is None)          # per-launch profiling needs eager launches
+    graphs = {}
+    seen = {}
+    dslots = [None, None, None]      # device copies of the graph's static outputs, one per in-flight D2H
 
     for idx, task in enumerate(it):
         t2 = Task({k: v for k, v in task.items() if k not in ("Y_t", "Y_t_aux", "X_t")})
@@ -144,10 +235,37 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
         t2["Y_t"] = []
         hb = model.stage_task(t2, pinned=False, ctx_cache=ctx_cache)
         hb.aux_t = aux_dev
-        # upload on a copy stream: a pageable H2D copy on the compute stream would block the host until the previous
-        # task's kernels have drained
-        out = model(eng.upload(hb, stream=copy_stream) if copy_stream is not None else hb)
-        mean, std = out["mean"][0, 0], out["std"][0, 0]
+        gf = None
+        if use_graph:
+            hb = _pad_offgrid(hb)
+            sig = _inference_signature(hb)
+            gf = graphs.get(sig)
+        if gf is not None:
+            slot = idx % 3
+            if futures[slot] is not None:      # everything issued from this slot three tasks ago has completed
+                futures[slot].result()
+                futures[slot] = None
+            gf.load(hb, slot)
+            gmean, gstd = gf.replay()
+            # the static outputs are overwritten by the next replay: hand a device copy (15.7 MB, ~5 us) to the D2H
+            if dslots[slot] is None or dslots[slot][0].shape != gmean.shape:
+                dslots[slot] = (torch.empty_like(gmean), torch.empty_like(gstd))
+            dslots[slot][0].copy_(gmean)
+            dslots[slot][1].copy_(gstd)
+            mean, std = dslots[slot][0][0], dslots[slot][1][0]
+        else:
+            # upload on a copy stream: a pageable H2D copy on the compute stream would block the host until the
+            # previous task's kernels have drained
+            db = eng.upload(hb, stream=copy_stream) if copy_stream is not None else hb
+            out = model(db)
+            mean, std = out["mean"][0, 0], out["std"][0, 0]
+            if use_graph and len(graphs) < 8:
+                # second task with this signature: capture (the eager forward above has allocated every workspace)
+                seen[sig] = seen.get(sig, 0) + 1
+                if seen[sig] >= 1:
+                    torch.cuda.current_stream().wait_stream(copy_stream)
+                    db.ready = None
+                    graphs[sig] = _GraphedForward(model, db)
         if mean_out is None:
             mean_out = np.empty((n,) + tuple(mean.shape), dtype=np.float32)
             std_out = np.empty_like(mean_out)
@@ -159,10 +277,21 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
             slot = idx % 3
             if futures[slot] is not None:  # the buffer we are about to reuse must have been drained
                 futures[slot].result()
-            pin[slot][0].copy_(mean, non_blocking=True)
-            pin[slot][1].copy_(std, non_blocking=True)
-            events[slot] = torch.cuda.Event()
-            events[slot].record()
+            if gf is not None:
+                # D2H on the copy stream, so that it overlaps the next task's replay
+                ev = torch.cuda.Event()
+                ev.record()
+                copy_stream.wait_event(ev)
+                with torch.cuda.stream(copy_stream):
+                    pin[slot][0].copy_(mean, non_blocking=True)
+                    pin[slot][1].copy_(std, non_blocking=True)
+                    events[slot] = torch.cuda.Event()
+                    events[slot].record()
+            else:
+                pin[slot][0].copy_(mean, non_blocking=True)
+                pin[slot][1].copy_(std, non_blocking=True)
+                events[slot] = torch.cuda.Event()
+                events[slot].record()
             futures[slot] = pool.submit(drain, slot, idx)
         else:
             mean_out[idx], std_out[idx] = mean.numpy(), std.numpy()

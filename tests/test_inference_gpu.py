@@ -177,3 +177,29 @@ def test_tensor_core_decoder_tail_matches_fused_and_oracle(monkeypatch):
     mean_o, var_o = O.forward(cpu_params(m), ctx, xt, aux, m.config.points_per_unit)
     assert rel_err(out["mean"], mean_o) < 2e-2
     assert rel_err(out["std"], var_o.sqrt()) < 2e-2
+
+
+def test_predict_graph_replay_matches_eager(static, monkeypatch):
+    """predict replays a captured forward for tasks that share a batch signature (station counts padded to a multiple of
+    16 with masked points); results are bit-identical to the eager path, also when the signature changes mid-call."""
+    counts = (60, 60, 57, 60, 41, 41, 60)          # 57 pads to 64 like 60; 41 -> 48 is a second signature
+    tasks = [make_task(static, 3000 + i, all_context=True, n_stations=n) for i, n in enumerate(counts)]
+    m = small_model("bf16")
+    x1 = np.linspace(0.05, 0.95, 150).astype(np.float32)
+    x2 = np.linspace(0.10, 0.90, 170).astype(np.float32)
+    aux = np.random.default_rng(3).uniform(-1, 1, (5, 150, 170)).astype(np.float32)
+    calls = []
+    orig = m.engine._call
+    monkeypatch.setattr(m.engine, "_call", lambda name, *a, **k: (calls.append(name), orig(name, *a, **k))[1])
+    monkeypatch.setenv("CONVNP_B200_PREDICT_GRAPH", "1")
+    pg = m.predict(tasks, X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
+    n_graph = sum(1 for c in calls if c.startswith("cnp_decode_grid"))
+    calls.clear()
+    monkeypatch.setenv("CONVNP_B200_PREDICT_GRAPH", "0")
+    pe = m.predict(tasks, X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
+    n_eager = sum(1 for c in calls if c.startswith("cnp_decode_grid"))
+    # eager: one decoder launch per task; graph: one eager + one captured launch per signature, the rest are replays
+    assert n_eager == len(tasks) and n_graph == 2 * 2
+    key = list(pg.keys())[0]
+    assert np.array_equal(np.asarray(pg[key]["mean"]), np.asarray(pe[key]["mean"]))
+    assert np.array_equal(np.asarray(pg[key]["std"]), np.asarray(pe[key]["std"]))
