@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -215,13 +216,20 @@ class Engine:
         CPU tensors (page-locked when ``pinned``) plus the host-side discretisation.
 
         ``ctx_cache`` (predict over many tasks): gridded context sets whose arrays are the same host buffers as in an
-        earlier task (static topography / land mask) are uploaded once and their device copy -- with its band tables
-        hint -- is reused; keyed on (data pointer, shape) of x, y and mask."""
+        earlier task (static topography / land mask) are uploaded once (on their second sighting: per-date fields
+        never enter the cache) and their device copy -- with its band hint -- is reused; keyed on (data pointer,
+        shape) of x, y and mask."""
         def bufkey(a):
             if a is None:
                 return None
             a = np.asarray(a)
             return (a.__array_interface__["data"][0], a.shape, a.strides, str(a.dtype))
+        def owner(a):
+            a = np.asarray(a)
+            while isinstance(a.base, np.ndarray):
+                a = a.base
+            return a
+
         def host(a):
             return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
 
@@ -252,9 +260,20 @@ class Engine:
             key = None
             if ctx_cache is not None and isinstance(x, tuple) and not isinstance(y, torch.Tensor):
                 key = (bufkey(x[0]), bufkey(x[1]), bufkey(y), bufkey(m))
-                if key in ctx_cache:
-                    hctx.append(ctx_cache[key])
+                bases = tuple(owner(a) for a in (x[0], x[1], y, m) if a is not None)
+                ent = ctx_cache.get(key)
+                # an entry only counts while the arrays that own its buffers are still the same live objects: a freed
+                # temporary (e.g. the float32 copy of a float64 field) can hand its address to the next task's data
+                alive = ent is not None and len(ent[0]) == len(bases) and all(r() is b for r, b in zip(ent[0], bases))
+                if alive and ent[1] is not None:
+                    hctx.append(ent[1])
                     continue
+                if not alive:              # first sighting: a per-date field until the same buffers come back
+                    try:
+                        ctx_cache[key] = (tuple(weakref.ref(b) for b in bases), None)
+                    except TypeError:
+                        ctx_cache.pop(key, None)
+                    key = None
             if isinstance(x, tuple):
                 x1h, x2h = xh
                 x1h = x1h.reshape(x1h.shape[0], -1)
@@ -280,7 +299,7 @@ class Engine:
                     up1 = lambda t: None if t is None else t.to(dev, non_blocking=True)
                     hc = DeviceContext(True, tuple(up1(v) for v in hc.x), up1(hc.y), up1(hc.mask), hc.mono, hc.x_batched,
                                        hc.x_host, hc.band_cache, hc.y_batched)
-                    ctx_cache[key] = hc
+                    ctx_cache[key] = (ctx_cache[key][0], hc)
                 hctx.append(hc)
             else:
                 hctx.append(DeviceContext(False, cpu(x), cpu(y), cpu(m)))

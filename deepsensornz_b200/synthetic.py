@@ -85,9 +85,11 @@ def make_task(static: StaticFields, seed: int, n_stations: int = 200, context_fr
     task = {
         "time": seed,
         "ops": [],
+        # static fields hand over the SAME coordinate / value arrays for every date (as TaskLoader does for variables
+        # without a time axis): predict then uploads and encodes them once
         "X_c": [(x1_desc[None], static.x_lo[None].copy()),
-                (static.x_lo[None].copy(), static.x_lo[None].copy()),
-                (static.x_hi[None].copy(), static.x_hi[None].copy()),
+                (static.x_lo[None], static.x_lo[None]),
+                (static.x_hi[None], static.x_hi[None]),
                 xs[:, ci]],
         "Y_c": [c0, static.c1, static.c2, ys[:, ci]],
     }

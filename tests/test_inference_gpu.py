@@ -182,7 +182,7 @@ def test_tensor_core_decoder_tail_matches_fused_and_oracle(monkeypatch):
 def test_predict_graph_replay_matches_eager(static, monkeypatch):
     """predict replays a captured forward for tasks that share a batch signature (station counts padded to a multiple of
     16 with masked points); results are bit-identical to the eager path, also when the signature changes mid-call."""
-    counts = (60, 60, 57, 60, 41, 41, 60)          # 57 pads to 64 like 60; 41 -> 48 is a second signature
+    counts = (60, 60, 57, 60, 41, 41, 60, 41, 60)  # 57 pads to 64 like 60; 41 -> 48 is a second signature
     tasks = [make_task(static, 3000 + i, all_context=True, n_stations=n) for i, n in enumerate(counts)]
     m = small_model("bf16")
     x1 = np.linspace(0.05, 0.95, 150).astype(np.float32)
@@ -198,8 +198,31 @@ def test_predict_graph_replay_matches_eager(static, monkeypatch):
     monkeypatch.setenv("CONVNP_B200_PREDICT_GRAPH", "0")
     pe = m.predict(tasks, X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
     n_eager = sum(1 for c in calls if c.startswith("cnp_decode_grid"))
-    # eager: one decoder launch per task; graph: one eager + one captured launch per signature, the rest are replays
-    assert n_eager == len(tasks) and n_graph == 2 * 2
+    # eager: one decoder launch per task; graph: two eager + one captured launch per signature, the rest are replays
+    assert n_eager == len(tasks) and n_graph == 2 * 3
     key = list(pg.keys())[0]
     assert np.array_equal(np.asarray(pg[key]["mean"]), np.asarray(pe[key]["mean"]))
     assert np.array_equal(np.asarray(pg[key]["std"]), np.asarray(pe[key]["std"]))
+
+
+def test_predict_context_cache_is_not_fooled_by_recycled_buffers(static):
+    """float64 tasks (what xarray hands over) are cast per task into temporaries whose addresses get recycled; the
+    static-context cache must never serve one date's field for another: every task equals its own single-task call."""
+    tasks = []
+    for i in range(6):
+        t = make_task(static, 5000 + i, all_context=True)
+        t["Y_c"] = [np.asarray(y, dtype=np.float64) for y in t["Y_c"]]
+        t["X_c"] = [tuple(np.asarray(v, dtype=np.float64) for v in x) if isinstance(x, tuple) else np.asarray(x, dtype=np.float64)
+                    for x in t["X_c"]]
+        tasks.append(t)
+    m = small_model("fp32")
+    x1 = np.linspace(0.05, 0.95, 40).astype(np.float32)
+    x2 = np.linspace(0.10, 0.90, 36).astype(np.float32)
+    aux = np.random.default_rng(3).uniform(-1, 1, (5, 40, 36)).astype(np.float32)
+    pred = m.predict(tasks, X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
+    key = list(pred.keys())[0]
+    mean = np.asarray(pred[key]["mean"])
+    for i, t in enumerate(tasks):
+        single = m.predict([t], X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
+        assert np.array_equal(np.asarray(single[key]["mean"])[0], mean[i]), i
+    assert not np.array_equal(mean[0], mean[1])

@@ -231,3 +231,18 @@ def test_aux_at_contexts_appends_an_offgrid_set(loader):
     assert np.array_equal(t["X_c"][3], t["X_c"][2])
     grid_only = TaskLoader(context=loader.context[:2], aux_at_contexts=loader.aux_at_targets)(DATES[0], "all")
     assert grid_only["X_c"][2].shape == (2, 0) and grid_only["Y_c"][2].shape == (3, 0)
+
+
+def test_static_variables_return_identical_arrays(loader):
+    """A context variable without a time axis is the same field on every date: "all" sampling hands back the same array
+    objects (ConvNP.predict keys its upload-once cache on identity); dated variables and sub-sampled draws do not."""
+    a, b = loader(DATES[0], "all", "all"), loader(DATES[1], "all", "all")
+    assert a["Y_c"][1] is b["Y_c"][1] and a["X_c"][1][0] is b["X_c"][1][0]       # static elevation set
+    assert a["Y_c"][0] is not b["Y_c"][0] and not np.array_equal(a["Y_c"][0], b["Y_c"][0])   # dated ERA field
+    s1 = loader(DATES[0], [5, 5, "all"], seed_override=1)
+    s2 = loader(DATES[0], [5, 5, "all"], seed_override=2)
+    assert s1["Y_c"][1] is not s2["Y_c"][1]
+    loader.context = [loader.context[0], _grid(30, 40, ["elevation", "tpi"], 99, timed=False), loader.context[2]]
+    c = loader(DATES[0], "all", "all")
+    assert c["Y_c"][1] is not a["Y_c"][1] and not np.array_equal(c["Y_c"][1], a["Y_c"][1])   # swapped variable: new field
+    assert "_static_cache" not in pickle.loads(pickle.dumps(loader)).__dict__
