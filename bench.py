@@ -196,9 +196,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a GPU (the hot path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION, ahead of the one JSON line the driver reads
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL logs (the version banner at NCCL_DEBUG=VERSION/WARN, everything at INFO) go to stdout by default, ahead
+        # of the one JSON line the driver reads: send them to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.manual_seed(0)
     model = ConvNP(precision=args.precision, **model_kwargs(args.internal_density))
