@@ -71,6 +71,17 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
     use_graph = bool(use_graph) and can_stage and getattr(model.engine, "world_size", 1) == 1
     graphs = model.__dict__.setdefault("_train_graphs", {}) if use_graph else None
     losses = []
+    # The loss of batch i is copied to page-locked memory asynchronously and READ while batch i+1 is already queued:
+    # every batch's loss still reaches the host (as upstream's train_epoch returns it), but the GPU never waits for the
+    # host to come back from a synchronising read between two steps.
+    on_gpu = torch.cuda.is_available() and can_stage
+    slots = [torch.empty((), dtype=torch.float64).pin_memory() for _ in range(2)] if on_gpu else None
+    events = [None, None]
+
+    def read_back(j):
+        events[j % 2].synchronize()
+        losses.append(float(slots[j % 2]))
+
     nxt = make(0) if n_batches > 0 else None
     for bi in it:
         cur = nxt
@@ -87,6 +98,16 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
                 loss_t = gs.step(cur)
         else:
             loss_t = launch_step(cur)
+        if on_gpu and loss_t.is_cuda:
+            slots[bi % 2].copy_(loss_t.to(torch.float64), non_blocking=True)
+            events[bi % 2] = torch.cuda.Event()
+            events[bi % 2].record()
         nxt = make(bi + 1) if bi + 1 < n_batches else None
-        losses.append(float(loss_t.cpu().numpy()))
+        if on_gpu and loss_t.is_cuda:
+            if bi > 0:
+                read_back(bi - 1)
+        else:
+            losses.append(float(loss_t.cpu().numpy()))
+    if on_gpu and n_batches > 0 and len(losses) < n_batches:
+        read_back(n_batches - 1)
     return losses
