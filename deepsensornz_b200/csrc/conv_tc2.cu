@@ -76,7 +76,7 @@ constexpr int C2_WSTAGES = 3;
 constexpr int C2_ABUFS = 2;
 constexpr int C2_EPI_WARPS = 12;
 constexpr int C2_THREADS = 32 * (4 + C2_EPI_WARPS);
-constexpr int C2_STG_WORDS_BF16 = 32 * 17;               // per-warp transpose buffer [32 px][17 words]
+constexpr int C2_STG_WORDS_BF16 = 32 * 20;               // per-warp transpose buffer [32 px][64 B of channels + 16 B pad]
 constexpr int C2_STG_WORDS_F32 = 32 * 36;                // fp32 output: [32 ch][36 floats]
 
 struct c2_work { int b, y0, x0, nacc; };
@@ -342,6 +342,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     const int ch = a.wide ? m : (m & 63);                    // output channel of this thread (TMEM lane)
     const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (q & 1) * 4);   // first of this warp's 4 output chunks
     const float bias_v = a.bias ? __ldg(a.bias + ch) : 0.f;
+    // bias of the four channels this thread holds in the fragment distribution: warp channel base + lane/4 + {0,8,16,24}
+    float bias4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bias4[i] = a.bias ? __ldg(a.bias + (ch - lane) + (lane >> 2) + 8 * i) : 0.f;
     uint32_t* my_stg = stg + ew * stg_words;
     const long long oplane = (long long)a.out_Hp * a.out_Wp;
     const int ncb = a.N >> 5;
@@ -384,6 +388,53 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
         {
           const int xs = cb * 32;
           if (xs >= a.TW || x0 + xs >= a.W) continue;        // warp-uniform
+          const int nvalid = min(min(a.TW - xs, a.W - x0 - xs), 32);   // valid pixels of this block
+          uint32_t wv[16];
+          if (a.out_mode == 0) {
+            // ---- blocked bf16: [channel = TMEM lane][pixel] -> [pixel = thread][32 channels] ----
+            // The accumulator block is read in the mma-fragment distribution (two 16-lane halves), bias / ReLU are
+            // applied, pairs are packed to bf16 and four stmatrix.x4.trans write the block transposed into shared
+            // memory as [pixel][8 channels] rows; every thread then reads its pixel's 64 B back with four 16 B loads.
+            // (The first version -- thread = channel, 32 two-byte stores + 16 word loads per block -- kept the
+            // shared-memory instruction pipe busy for half of the epilogue: tools/bench_conv.py stall counters.)
+            uint32_t ra[16], rb[16];
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs);
+            tc::tmem_ld_16x256b_x4(t0, ra);
+            tc::tmem_ld_16x256b_x4(t0 + (16u << 16), rb);
+            tc::tmem_ld_wait();
+            if (a.dbg_flags & 1) { uint32_t xacc = 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xacc ^= ra[i] ^ rb[i];
+              if (xacc == 0x12345678u) a.dbg[0] = 1;
+              continue; }
+            const uint32_t srow = tc::smem_u32(my_stg) + (uint32_t)(lane & 7) * 80u + (uint32_t)(lane >> 3) * 16u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float f[8];
+              f[0] = __uint_as_float(ra[4 * k]) + bias4[0];     f[1] = __uint_as_float(ra[4 * k + 1]) + bias4[0];
+              f[2] = __uint_as_float(ra[4 * k + 2]) + bias4[1]; f[3] = __uint_as_float(ra[4 * k + 3]) + bias4[1];
+              f[4] = __uint_as_float(rb[4 * k]) + bias4[2];     f[5] = __uint_as_float(rb[4 * k + 1]) + bias4[2];
+              f[6] = __uint_as_float(rb[4 * k + 2]) + bias4[3]; f[7] = __uint_as_float(rb[4 * k + 3]) + bias4[3];
+              if (a.relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+              uint32_t m[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 pr = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                m[i] = *reinterpret_cast<const uint32_t*>(&pr);
+              }
+              tc::stmatrix_x4_trans(srow + (uint32_t)k * 8u * 80u, m[0], m[1], m[2], m[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 t4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(my_stg) + lane * 80 + c * 16);
+              wv[4 * c] = t4.x; wv[4 * c + 1] = t4.y; wv[4 * c + 2] = t4.z; wv[4 * c + 3] = t4.w;
+            }
+            __syncwarp();
+          } else {
           float v[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs), v);
           tc::tmem_ld_wait();
@@ -397,8 +448,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             v[i] += bias_v;
             if (a.relu) v[i] = v[i] < 0.f ? 0.f : v[i];
           }
-          const int nvalid = min(min(a.TW - xs, a.W - x0 - xs), 32);   // valid pixels of this block
-          if (a.out_mode == 1) {
+          {
             // fp32 NCHW: stage [channel = lane][32 px] (row stride 36 floats), re-read as 4 channels x 8 groups of
             // 4 pixels so every warp store writes four full 128 B lines
             float* stf = reinterpret_cast<float*>(my_stg);
@@ -427,15 +477,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             __syncwarp();
             continue;
           }
-          // ---- blocked bf16: transpose [channel = lane][pixel] -> [pixel = lane][32 channels] ----
-          __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(my_stg);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) st16[i * 34 + lane] = __float2bfloat16_rn(v[i]);
-          __syncwarp();
-          uint32_t wv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) wv[i] = my_stg[lane * 17 + i];
-          __syncwarp();
+          }
           if (a.dbg_flags & 2) { uint32_t xacc = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) xacc ^= wv[i];

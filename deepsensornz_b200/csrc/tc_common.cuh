@@ -145,6 +145,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 16 TMEM lanes x 32 columns in the mma-fragment distribution (probed with tools/tmem_probe.cu): thread t holds, for
+// column block k = 0..3, r[4k] / r[4k+1] = (lane base + t/4, columns 8k + 2(t%4), +1) and r[4k+2] / r[4k+3] = the same
+// columns of lane base + t/4 + 8.  Packed to bf16 pairs these are stmatrix fragments.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// four 8x8 b16 matrices, each stored TRANSPOSED: thread t supplies the shared address of row t%8 of matrix t/8
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(m0), "r"(m1),
+               "r"(m2), "r"(m3) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ------------------------------------------------------------------------------------
