@@ -114,7 +114,7 @@ _SIGS = {
     "cnp_conv_tc2_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_conv_tc2": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
     "cnp_blk_from_nchw_f32": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
-    "cnp_blk_from_nchw_f32_ones": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), _i, c_stream]),
+    "cnp_blk_from_nchw_f32_ones": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), _i, C.c_ulonglong, c_stream]),
     "cnp_fold_in_fwd": (C.c_int, [c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_fold_in_bwd": (C.c_int, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_stream]),
     "cnp_blk_to_nchw_f32": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, _ll, c_stream]),

@@ -310,7 +310,8 @@ pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int t
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 nchw_to_blk_kernel(const float* __restrict__ src, long long src_bs, int C, int H, int W,
-                   __nv_bfloat16* __restrict__ dst, long long dst_bs, int cb_off, int ones_ch) {
+                   __nv_bfloat16* __restrict__ dst, long long dst_bs, int cb_off, int ones_ch,
+                   unsigned long long shared_mask) {
   const int b = blockIdx.z, chunk = blockIdx.y;
   const int Hp = H + 4, Wp = W + 4;
   for (int e = blockIdx.x * 256 + threadIdx.x; e < H * W; e += gridDim.x * 256) {
@@ -321,7 +322,9 @@ nchw_to_blk_kernel(const float* __restrict__ src, long long src_bs, int C, int H
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = chunk * 8 + i;
-      v[i] = c < C ? src[(size_t)b * src_bs + ((size_t)c * H + y) * W + x] : (c == ones_ch ? 1.f : 0.f);
+      // channels flagged in shared_mask hold one field for the whole batch: read batch 0 (broadcast on the fly)
+      const size_t bb = ((shared_mask >> (c & 63)) & 1ull) ? 0 : (size_t)b;
+      v[i] = c < C ? src[bb * src_bs + ((size_t)c * H + y) * W + x] : (c == ones_ch ? 1.f : 0.f);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) p2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -956,7 +959,7 @@ CNP_API int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B
   CNP_REQUIRE(dst && dst->H == H && dst->W == W, "blk_from_nchw: geometry mismatch");
   dim3 grid(min(cnp_cdiv(H * W, 256), 128), cnp_cdiv(C, 8), B);
   nchw_to_blk_kernel<<<grid, 256, 0, st>>>(src, src_bstride, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst->base),
-                                           dst->bstride, dst->cb_off, -1);
+                                           dst->bstride, dst->cb_off, -1, 0ull);
   CNP_LAUNCH_CHECK("nchw_to_blk_kernel");
   return 0;
 }
@@ -964,13 +967,15 @@ CNP_API int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B
 // Same conversion into n_chunks chunks, with channel C set to 1 inside the image (the pad stays 0) and channels
 // C+1.. zero: the input of the first UNet convolution once the initial 1x1 is folded into it (fold_in.cu) -- the
 // constant channel carries the 1x1's bias through the zero-padded 5x5 window exactly.
+// shared_mask: bit c set = channel c of `src` is only valid in batch 0 (a context set shared by all tasks, encoded once)
+// and is broadcast to every task here instead of by a separate copy.
 CNP_API int cnp_blk_from_nchw_f32_ones(const float* src, long long src_bstride, int B, int C, int H, int W,
-                                       const cnp_blk* dst, int n_chunks, cudaStream_t st) {
+                                       const cnp_blk* dst, int n_chunks, unsigned long long shared_mask, cudaStream_t st) {
   CNP_REQUIRE(dst && dst->H == H && dst->W == W, "blk_from_nchw_ones: geometry mismatch");
-  CNP_REQUIRE(C + 1 <= n_chunks * 8, "blk_from_nchw_ones: need C + 1 <= 8 * n_chunks");
+  CNP_REQUIRE(C + 1 <= n_chunks * 8 && C < 64, "blk_from_nchw_ones: need C + 1 <= 8 * n_chunks and C < 64");
   dim3 grid(min(cnp_cdiv(H * W, 256), 128), n_chunks, B);
   nchw_to_blk_kernel<<<grid, 256, 0, st>>>(src, src_bstride, C, H, W, reinterpret_cast<__nv_bfloat16*>(dst->base),
-                                           dst->bstride, dst->cb_off, C);
+                                           dst->bstride, dst->cb_off, C, shared_mask);
   CNP_LAUNCH_CHECK("nchw_to_blk_kernel(ones)");
   return 0;
 }

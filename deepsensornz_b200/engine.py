@@ -357,12 +357,16 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # (1) encoder
     # ------------------------------------------------------------------------------------------
-    def encode(self, batch: DeviceBatch) -> torch.Tensor:
+    def encode(self, batch: DeviceBatch, broadcast: bool = True) -> torch.Tensor:
         """SetConv encoders of all context sets into disjoint channel ranges of one [B, Cin, n1, n2] tensor.  The sets
         are independent and individually too small to fill the GPU (a static field is encoded once, B = 1), so each
         runs on its own side stream (fork / join on events; serial when profiling or with CNP_NO_MULTISTREAM)."""
         cfg, g, B = self.cfg, batch.grid, batch.B
         enc = self._buf("enc", (B, cfg.in_channels, g.n1, g.n2))
+        # broadcast=False: channels of context sets shared by the whole batch are written for task 0 only and flagged in
+        # self._enc_shared_mask; the consumer (the blocked conversion of the folded first layer) broadcasts on the fly
+        self._enc_shared_mask = 0
+        self._enc_broadcast = broadcast
         multi = len(batch.contexts) > 1 and self._prof is None and not os.environ.get("CNP_NO_MULTISTREAM")
         main = torch.cuda.current_stream()
         if multi:
@@ -406,8 +410,11 @@ class Engine:
                        Be, Ck, N1, N2, c.mono[0], c.mono[1],
                        g.start1, g.n1, g.start2, g.n2, g.res, s2, cfg.epsilon, _ptr(enc), ch, cfg.in_channels,
                        band, _ptr(ws), ws_bytes, _stream(), work=(0.0, by))
-            if Be < B:                        # ... and its channels broadcast to the other tasks (plain D2D copy)
-                enc[1:, ch:ch + Ck + 1].copy_(enc[:1, ch:ch + Ck + 1].expand(B - 1, -1, -1, -1))
+            if Be < B:                        # ... and its channels broadcast to the other tasks
+                if self._enc_broadcast:       # (plain D2D copy, or on the fly by the consumer)
+                    enc[1:, ch:ch + Ck + 1].copy_(enc[:1, ch:ch + Ck + 1].expand(B - 1, -1, -1, -1))
+                else:
+                    self._enc_shared_mask |= ((1 << (Ck + 1)) - 1) << ch
         else:
             by = 4.0 * (c.x.numel() + c.y.numel() + B * (Ck + 1) * g.n1 * g.n2)
             self._call("cnp_setconv_enc_offgrid_fwd", _ptr(c.x), _ptr(c.y), _ptr(c.mask), B, Ck,
@@ -661,7 +668,7 @@ class Engine:
             cb0 = 2 * ((cfg.in_channels + 1 + 15) // 16)
             h_init = self._blk("x_aug", B, cb0, n1, n2)
             self._call("cnp_blk_from_nchw_f32_ones", _ptr(enc), enc.stride(0), B, cfg.in_channels, n1, n2,
-                       C.byref(h_init.view()), cb0, S)
+                       C.byref(h_init.view()), cb0, int(getattr(self, "_enc_shared_mask", 0)), S)
         else:
             cb0 = 8
             h_init = self._blk("h_init", B, 8, n1, n2)
@@ -872,7 +879,11 @@ class Engine:
             for t in self._batch_tensors(batch):
                 t.record_stream(cur)
             batch.ready = None
-        enc = self.encode(batch)
+        # with the folded first layer the only reader of the encoder output is the blocked conversion, which broadcasts
+        # the channels of batch-shared context sets itself
+        folded = (self.precision != "fp32" and cfg.unet_strides[0] == 1 and cfg.in_channels + 1 <= 64
+                  and not os.environ.get("CNP_NO_FOLD_IN"))
+        enc = self.encode(batch, broadcast=not folded)
         on_grid = isinstance(batch.xt, tuple)
         if self.precision == "fp32":
             z, A = self._unet_fwd_f32(enc, B, g.n1, g.n2)

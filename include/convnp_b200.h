@@ -137,7 +137,8 @@ int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B, int C,
 int cnp_blk_to_nchw_f32(const cnp_blk* src, int B, int C, float* dst, long long dst_bstride, cnp_stream_t s);
 /* conversion into n_chunks chunks with channel C := 1 inside the image (input of the folded first layer) */
 int cnp_blk_from_nchw_f32_ones(const float* src, long long src_bstride, int B, int C, int H, int W, const cnp_blk* dst,
-                               int n_chunks, cnp_stream_t s);
+                               int n_chunks, unsigned long long shared_mask /* bit c: channel c is read from batch 0 */,
+                               cnp_stream_t s);
 /* initial 1x1 (neuralprocesses UNet.initial_linear) folded into the first 5x5 (before_turn_layers[0]):
  * wf [Cout][Cp][k*k] = W5 . [W1 | b1] (channels Cin+1..Cp-1 zero); bwd maps the folded gradient dwf back (+=). */
 int cnp_fold_in_fwd(const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin, int Cp, int k,

@@ -20,8 +20,23 @@ pytestmark = pytest.mark.gpu
 def _aug(x, n_chunks):
     B, Cc, H, W = x.shape
     blk = _Blk(B, n_chunks, H, W, x.device)
-    _cabi.call("cnp_blk_from_nchw_f32_ones", x.data_ptr(), x.stride(0), B, Cc, H, W, C.byref(blk.view()), n_chunks, _S())
+    _cabi.call("cnp_blk_from_nchw_f32_ones", x.data_ptr(), x.stride(0), B, Cc, H, W, C.byref(blk.view()), n_chunks, 0, _S())
     return blk
+
+
+def test_conversion_broadcasts_shared_channels():
+    """Channels flagged in shared_mask are read from batch 0 for every task (a context set encoded once per batch)."""
+    torch.manual_seed(4)
+    B, Cc, H, W = 3, 13, 9, 11
+    x = torch.randn(B, Cc, H, W, device="cuda").bfloat16().float()
+    mask = (0b1111 << 2) | (1 << 12)                     # channels 2..5 and 12 are shared
+    blk = _Blk(B, 2, H, W, x.device)
+    _cabi.call("cnp_blk_from_nchw_f32_ones", x.data_ptr(), x.stride(0), B, Cc, H, W, C.byref(blk.view()), 2, mask, _S())
+    got = _from_blk(blk, 16)
+    want = x.clone()
+    for c in (2, 3, 4, 5, 12):
+        want[:, c] = x[0, c]
+    assert torch.equal(got[:, :Cc], want) and float((got[:, Cc] - 1).abs().max()) == 0 and float(got[:, Cc + 1:].abs().max()) == 0
 
 
 def _params(cin, seed):
