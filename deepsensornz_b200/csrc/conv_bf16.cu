@@ -632,75 +632,97 @@ __device__ __forceinline__ float up2_wgt(int Y, int H, int u) {
 // ITS two hi-res columns (2v, 2v+1) of the four rows -- one 32 B load per row -- and combines them vertically
 // (V0, V1); the horizontal taps of the neighbours (V1 of v-1, V0 of v+1) come through shared memory.  Per thread:
 // 4 loads and 64 conversions instead of 16 and 128 (the per-pixel kernel below was issue-bound at 1.75 TB/s).
-__global__ void __launch_bounds__(1024)
+// rows_per_block low-res rows per block: hi-res rows 2u+1, 2u+2 of one row are rows 2u'-1, 2u' of the next
+__global__ void __launch_bounds__(512)
 blk_upsample2x_bwd_row_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_bs, int dy_cb, int H, int W,
                               __nv_bfloat16* __restrict__ dx, long long dx_bs, int dx_cb,
-                              const __nv_bfloat16* __restrict__ act, long long act_bs, int act_cb, int accumulate) {
+                              const __nv_bfloat16* __restrict__ act, long long act_bs, int act_cb, int accumulate,
+                              int rows_per_block) {
   extern __shared__ __align__(16) float4 up_sm[];          // [4][blockDim.x]: V0 lo, V0 hi, V1 lo, V1 hi
-  const int u = blockIdx.x, chunk = blockIdx.y, b = blockIdx.z, v = threadIdx.x, T = blockDim.x;
+  const int chunk = blockIdx.y, b = blockIdx.z, v = threadIdx.x, T = blockDim.x;
+  const int u0 = blockIdx.x * rows_per_block, u1 = min(u0 + rows_per_block, H);
   const int Wp = W + 4, Hp = H + 4, W2p = 2 * W + 4, H2p = 2 * H + 4;
   const __nv_bfloat16* dyc = dy + (size_t)b * dy_bs + (size_t)(dy_cb + chunk) * H2p * W2p * 8;
-  float wy[4];
+  __nv_bfloat16* dxc = dx + (size_t)b * dx_bs + (size_t)(dx_cb + chunk) * Hp * Wp * 8;
+  const __nv_bfloat16* ac = act ? act + (size_t)b * act_bs + (size_t)(act_cb + chunk) * Hp * Wp * 8 : nullptr;
+  const bool in = v < W;
+  float wx[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) wy[k] = up2_wgt(2 * u - 1 + k, H, u);
-  float V0[8], V1[8];
+  for (int k = 0; k < 4; ++k) wx[k] = in ? up2_wgt(2 * v - 1 + k, W, v) : 0.f;
+  // this thread's two hi-res columns (2v, 2v+1) of the rows 2u-1 and 2u, carried from one low-res row to the next so
+  // that every hi-res row is loaded once per block (rows outside the image are the zero pad of dy: weight 0, safe)
+  uint32_t ra[8], rb[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) V0[i] = V1[i] = 0.f;
-  if (v < W) {
-    // rows 2u-1 .. 2u+2 (the zero pad of dy makes the out-of-range rows, weight 0, safe to read)
-    uint32_t raw[4][8];
+  for (int i = 0; i < 8; ++i) ra[i] = rb[i] = 0;
+  if (in) {
+    ldg256(dyc + ((size_t)(2 * u0 - 1 + 2) * W2p + 2 * v + 2) * 8, ra);
+    ldg256(dyc + ((size_t)(2 * u0 + 2) * W2p + 2 * v + 2) * 8, rb);
+  }
+  for (int u = u0; u < u1; ++u) {
+    uint32_t rc[8], rd[8];
 #pragma unroll
-    for (int ky = 0; ky < 4; ++ky) ldg256(dyc + ((size_t)(2 * u - 1 + ky + 2) * W2p + 2 * v + 2) * 8, raw[ky]);
+    for (int i = 0; i < 8; ++i) rc[i] = rd[i] = 0;
+    if (in) {
+      ldg256(dyc + ((size_t)(2 * u + 1 + 2) * W2p + 2 * v + 2) * 8, rc);
+      ldg256(dyc + ((size_t)(2 * u + 2 + 2) * W2p + 2 * v + 2) * 8, rd);
+    }
+    float wy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wy[k] = up2_wgt(2 * u - 1 + k, H, u);
+    float V0[8], V1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) V0[i] = V1[i] = 0.f;
+    const uint32_t* rows[4] = {ra, rb, rc, rd};
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
       float a0[8], a1[8];
-      unpack8(raw[ky], a0);
-      unpack8(raw[ky] + 4, a1);
+      unpack8(rows[ky], a0);
+      unpack8(rows[ky] + 4, a1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { V0[i] = fmaf(wy[ky], a0[i], V0[i]); V1[i] = fmaf(wy[ky], a1[i], V1[i]); }
     }
+    up_sm[v] = make_float4(V0[0], V0[1], V0[2], V0[3]);
+    up_sm[T + v] = make_float4(V0[4], V0[5], V0[6], V0[7]);
+    up_sm[2 * T + v] = make_float4(V1[0], V1[1], V1[2], V1[3]);
+    up_sm[3 * T + v] = make_float4(V1[4], V1[5], V1[6], V1[7]);
+    __syncthreads();
+    if (in) {
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = wx[1] * V0[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[2], V1[i], s[i]);
+      if (v > 0) {           // hi-res column 2v-1 = V1 of the left neighbour
+        const float4 l0 = up_sm[2 * T + v - 1], l1 = up_sm[3 * T + v - 1];
+        const float L[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[0], L[i], s[i]);
+      }
+      if (v < W - 1) {       // hi-res column 2v+2 = V0 of the right neighbour
+        const float4 r0 = up_sm[v + 1], r1 = up_sm[T + v + 1];
+        const float R[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[3], R[i], s[i]);
+      }
+      const size_t pix = ((size_t)(u + 2) * Wp + v + 2) * 8;
+      if (ac) {
+        float av[8];
+        ld8(ac + pix, av);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (!(av[i] > 0.f)) s[i] = 0.f;
+      }
+      if (accumulate) {
+        float old[8];
+        ld8(dxc + pix, old);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += old[i];
+      }
+      st8(dxc + pix, s);
+    }
+    __syncthreads();        // the exchange buffer is rewritten by the next row
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ra[i] = rc[i]; rb[i] = rd[i]; }
   }
-  up_sm[v] = make_float4(V0[0], V0[1], V0[2], V0[3]);
-  up_sm[T + v] = make_float4(V0[4], V0[5], V0[6], V0[7]);
-  up_sm[2 * T + v] = make_float4(V1[0], V1[1], V1[2], V1[3]);
-  up_sm[3 * T + v] = make_float4(V1[4], V1[5], V1[6], V1[7]);
-  __syncthreads();
-  if (v >= W) return;
-  float wx[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) wx[k] = up2_wgt(2 * v - 1 + k, W, v);
-  float s[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = wx[1] * V0[i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[2], V1[i], s[i]);
-  if (v > 0) {           // hi-res column 2v-1 = V1 of the left neighbour
-    const float4 l0 = up_sm[2 * T + v - 1], l1 = up_sm[3 * T + v - 1];
-    const float L[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[0], L[i], s[i]);
-  }
-  if (v < W - 1) {       // hi-res column 2v+2 = V0 of the right neighbour
-    const float4 r0 = up_sm[v + 1], r1 = up_sm[T + v + 1];
-    const float R[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = fmaf(wx[3], R[i], s[i]);
-  }
-  const size_t pix = ((size_t)(u + 2) * Wp + v + 2) * 8;
-  __nv_bfloat16* dxc = dx + (size_t)b * dx_bs + (size_t)(dx_cb + chunk) * Hp * Wp * 8;
-  if (act) {
-    float av[8];
-    ld8(act + (size_t)b * act_bs + (size_t)(act_cb + chunk) * Hp * Wp * 8 + pix, av);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) if (!(av[i] > 0.f)) s[i] = 0.f;
-  }
-  if (accumulate) {
-    float old[8];
-    ld8(dxc + pix, old);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] += old[i];
-  }
-  st8(dxc + pix, s);
 }
 
 // Per-pixel kernel (any width): one thread per low-res pixel and chunk, all 16 loads issued before the arithmetic.
@@ -1016,12 +1038,13 @@ CNP_API int cnp_blk_upsample2x_bwd(const cnp_blk* dy, int n_chunks, const cnp_bl
   CNP_REQUIRE(dy && dx && dy->H == 2 * dx->H && dy->W == 2 * dx->W, "blk_upsample2x_bwd: geometry mismatch");
   CNP_REQUIRE(!act || (act->H == dx->H && act->W == dx->W), "blk_upsample2x_bwd: mask geometry mismatch");
   const __nv_bfloat16* ap = act ? reinterpret_cast<const __nv_bfloat16*>(act->base) : nullptr;
-  if (dx->W <= 1024 && (reinterpret_cast<uintptr_t>(dy->base) & 31) == 0 && (dy->bstride & 15) == 0) {
+  if (dx->W <= 512 && (reinterpret_cast<uintptr_t>(dy->base) & 31) == 0 && (dy->bstride & 15) == 0) {
     const int T = cnp_cdiv(dx->W, 32) * 32;
-    blk_upsample2x_bwd_row_kernel<<<dim3(dx->H, n_chunks, B), T, (size_t)4 * T * sizeof(float4), st>>>(
+    const int rpb = dx->H >= 100 ? 8 : (dx->H >= 50 ? 4 : 1);     // small images need the blocks more than the reuse
+    blk_upsample2x_bwd_row_kernel<<<dim3(cnp_cdiv(dx->H, rpb), n_chunks, B), T, (size_t)4 * T * sizeof(float4), st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy->base), dy->bstride, dy->cb_off, dx->H, dx->W,
         reinterpret_cast<__nv_bfloat16*>(dx->base), dx->bstride, dx->cb_off, ap, act ? act->bstride : 0,
-        act ? act->cb_off : 0, accumulate);
+        act ? act->cb_off : 0, accumulate, rpb);
     CNP_LAUNCH_CHECK("blk_upsample2x_bwd_row_kernel");
     return 0;
   }

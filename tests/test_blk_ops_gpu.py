@@ -29,9 +29,9 @@ def test_blk_upsample_fwd(c, h, w):
 
 
 @pytest.mark.parametrize("mask,accumulate", [(False, False), (True, False), (True, True)])
-@pytest.mark.parametrize("c,h,w", [(16, 19, 23), (128, 38, 38), (64, 5, 152), (8, 1, 1), (8, 3, 2), (8, 2, 1030)])
+@pytest.mark.parametrize("c,h,w", [(16, 19, 23), (128, 38, 38), (64, 5, 152), (8, 1, 1), (8, 3, 2), (8, 2, 1030), (8, 19, 300), (16, 17, 9), (8, 61, 40), (8, 103, 24)])
 def test_blk_upsample_bwd(c, h, w, mask, accumulate):
-    """dx = J^T dy (* (act > 0)) (+ dx_old).  W = 1030 takes the per-pixel kernel, the others the row kernel."""
+    """dx = J^T dy (* (act > 0)) (+ dx_old).  W = 1030 takes the per-pixel kernel, the others the row kernel (8 rows per block, partial last block)."""
     torch.manual_seed(2)
     B = 2
     dy = torch.randn(B, c, 2 * h, 2 * w, device="cuda").bfloat16().float()
