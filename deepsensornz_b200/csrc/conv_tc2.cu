@@ -48,6 +48,7 @@ struct cnp_c2_args {
   int B, H, W;
   int TW, TH, pitch, N, nacc, rpa, plane_sm, tiles_x, tiles_y;
   int wide;
+  int pxpair;                   // stride-2 dgrad: lane group g = output x-phase g (both phases of a row in one launch)
   int n_work, split_from, split;  // work items: tiles [0, split_from) whole, the leftover tiles of the last round
                                   // split into `split` single-accumulator items (finer tail, see cnp_conv_tc2)
   int cluster;                   // 1, or 2: CTA pairs share the weight stream (each loads half a stage and multicasts it)
@@ -360,10 +361,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
         const int n_it = wk.nacc * ncb;
         for (int item = h; item < n_it; item += C2_EPI_WARPS / 4) {
           const int j = item / ncb, xs = (item - j * ncb) * 32;
-          const int y = y0 + j * a.rpa + (a.wide ? 0 : g);
+          const int y = y0 + j * a.rpa + ((a.wide || a.pxpair) ? 0 : g);
           if (y >= a.H || xs >= a.TW || x0 + xs >= a.W) continue;
           const int xx = min(x0 + xs + lane, a.W - 1);
-          const long long pix = (long long)(y * a.sy + a.ay + 2) * a.out_Wp + (xx * a.sx + a.ax + 2);
+          const long long pix = (long long)(y * a.sy + a.ay + 2) * a.out_Wp + (xx * a.sx + a.ax + (a.pxpair ? g : 0) + 2);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (a.mask)
@@ -381,7 +382,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       const int n_items = wk.nacc * ncb;
       for (int item = h; item < n_items; item += C2_EPI_WARPS / 4) {
         const int j = item / ncb, cb = item - j * ncb;
-        const int ty = j * a.rpa + (a.wide ? 0 : g);
+        const int ty = j * a.rpa + ((a.wide || a.pxpair) ? 0 : g);
         const int y = y0 + ty;
         if (y >= a.H) continue;                              // warp-uniform
         const int oy = y * a.sy + a.ay;
@@ -484,7 +485,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             if (xacc == 0x12345678u) a.dbg[0] = 1;
             continue; }
           if (lane < nvalid) {
-            const int ox = (x0 + xs + lane) * a.sx + a.ax;
+            const int ox = (x0 + xs + lane) * a.sx + a.ax + (a.pxpair ? g : 0);
             const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
                                    ((long long)chunk0 * oplane + pix) * 8;
@@ -590,22 +591,27 @@ struct Tap { int roff, coff, wky, wkx; };
 
 // positions of one K-block type from the tap list of group 0 (window offsets relative to the output pixel's
 // padded origin); PAIR adds the row-shifted copies for group 1
-int add_type(cnp_c2_plan* p, int type, const Tap* taps, int ntaps, int pitch, int wide) {
+// (taps1 != NULL: group 1 has its own tap list at the SAME window offsets -- the second x-phase of a stride-2 dgrad)
+int add_type(cnp_c2_plan* p, int type, const Tap* taps, int ntaps, int pitch, int wide, const Tap* taps1 = nullptr,
+             int ntaps1 = 0) {
   int np = 0;
   for (int r = 0; r < 8; ++r)
     for (int c = 0; c < 8; ++c) {
       int t0 = -1, t1 = -1;
       for (int t = 0; t < ntaps; ++t) {
         if (taps[t].roff == r && taps[t].coff == c) t0 = t;
-        if (!wide && taps[t].roff + 1 == r && taps[t].coff == c) t1 = t;
+        if (!wide && !taps1 && taps[t].roff + 1 == r && taps[t].coff == c) t1 = t;
       }
+      for (int t = 0; t < ntaps1; ++t)
+        if (taps1[t].roff == r && taps1[t].coff == c) t1 = t;
       if (t0 < 0 && t1 < 0) continue;
       CNP_REQUIRE(np < C2_MAX_POS, "conv plan: too many positions");
+      const Tap* g1 = taps1 ? taps1 : taps;
       p->t_boff[type][np] = (short)(r * pitch + c);
       p->t_tap[type][np][0] = t0 >= 0 ? (signed char)taps[t0].wky : -1;
       p->t_tap[type][np][1] = t0 >= 0 ? (signed char)taps[t0].wkx : -1;
-      p->t_tap[type][np][2] = t1 >= 0 ? (signed char)taps[t1].wky : -1;
-      p->t_tap[type][np][3] = t1 >= 0 ? (signed char)taps[t1].wkx : -1;
+      p->t_tap[type][np][2] = t1 >= 0 ? (signed char)g1[t1].wky : -1;
+      p->t_tap[type][np][3] = t1 >= 0 ? (signed char)g1[t1].wkx : -1;
       ++np;
     }
   p->t_npos[type] = np;
@@ -646,10 +652,23 @@ int build_plan2(int kind, int n_chunks, int pitch, int py, int px, int wide, cnp
   } else if (kind == KIND_K5S2_DGRAD) {
     CNP_REQUIRE(n_chunks == 8, "conv plan: stride-2 dgrad reads the 8-chunk dy tensor");
     int nt = 0;
-    for (int ky = py; ky < 5; ky += 2)
-      for (int kx = px; kx < 5; kx += 2)
-        taps[nt++] = Tap{2 + (py + 2 - ky) / 2, 2 + (px + 2 - kx) / 2, ky, kx};
-    if (int e = add_type(p, 0, taps, nt, pitch, wide)) return e;
+    if (px == 2) {
+      // both x-phases of output row phase py in one launch: lane group 0 = phase px 0, group 1 = phase px 1, each with
+      // its own taps at the shared window offsets (3 x 3 resp. 2 x 3 positions; x-phase 1 has no tap at column offset 1)
+      CNP_REQUIRE(!wide, "conv plan: the x-phase pair produces 64 channels per phase");
+      Tap taps1[25];
+      int nt1 = 0;
+      for (int ky = py; ky < 5; ky += 2) {
+        for (int kx = 0; kx < 5; kx += 2) taps[nt++] = Tap{2 + (py + 2 - ky) / 2, 2 + (0 + 2 - kx) / 2, ky, kx};
+        for (int kx = 1; kx < 5; kx += 2) taps1[nt1++] = Tap{2 + (py + 2 - ky) / 2, 2 + (1 + 2 - kx) / 2, ky, kx};
+      }
+      if (int e = add_type(p, 0, taps, nt, pitch, 0, taps1, nt1)) return e;
+    } else {
+      for (int ky = py; ky < 5; ky += 2)
+        for (int kx = px; kx < 5; kx += 2)
+          taps[nt++] = Tap{2 + (py + 2 - ky) / 2, 2 + (px + 2 - kx) / 2, ky, kx};
+      if (int e = add_type(p, 0, taps, nt, pitch, wide)) return e;
+    }
     for (int g = 0; g < 4; ++g) add_kb(2 * g, 16 * g, 0);
   } else {
     CNP_REQUIRE(false, "conv plan: unknown kind %d", kind);
@@ -687,7 +706,7 @@ size_t c2_smem_bytes(int plane_sm, int out_mode) {
 //   epilogue (not overlapped with the MMAs): ~18 cycles per accumulator column.
 // Minimise waves x (max(MMA, L2) + epilogue).
 void choose_geometry(cnp_c2_args* a, int mma_per_acc) {
-  const int rpa = a->wide ? 1 : 2;
+  const int rpa = (a->wide || a->pxpair) ? 1 : 2;
   double best = 1e300;
   for (int N = 32; N <= 256; N += 32) {
     const int tw_max = N < a->W ? N : a->W;
@@ -782,6 +801,9 @@ CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int ki
   a.x_bs = x->bstride;
   a.w = reinterpret_cast<const uint8_t*>(wpk);
   a.wide = n_out == 128;
+  a.pxpair = (kind == KIND_K5S2_DGRAD && px == 2) ? 1 : 0;
+  CNP_REQUIRE(!a.pxpair || (o->mode == 0 && o->sx == 2 && o->ax == 0 && !o->s2d),
+              "conv_tc2: the x-phase pair writes a blocked output with sx = 2, ax = 0");
   a.out_mode = o->mode;
   a.cluster = g_c2_cluster;
   if (int e = build_plan2(kind, n_chunks, 8, py, px, a.wide, &a.plan)) return e;   // position count only

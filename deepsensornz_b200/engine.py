@@ -633,7 +633,7 @@ class Engine:
         elif kind == K.KIND_K5S2:
             kdim = 64 * 25
         else:
-            kdim = 64 * (3 if py == 0 else 2) * (3 if px == 0 else 2)
+            kdim = 64 * (3 if py == 0 else 2) * (5 if px == 2 else (3 if px == 0 else 2))   # px = 2: both x-phases
         fl = 2.0 * B * x.H * x.W * n_out * kdim
         self._call("cnp_conv_tc2", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, n_out, C.byref(out), B, _stream(),
                    work=(fl, 0.0))
@@ -764,7 +764,7 @@ class Engine:
             py, px = phase if phase is not None else (0, 0)
             wpk = self._packed_weights(f"{key}.dg.{py}{px}", w, kind, 8, py, px, 0, n_out_ch)
             mk = mask.view(mask_cb) if mask is not None else None
-            sc = (2, py, 2, px) if phase is not None else (1, 0, 1, 0)
+            sc = (2, py, 2, px if px < 2 else 0) if phase is not None else (1, 0, 1, 0)
             o = self._out_blk(dst.view(dst_cb), mask=mk, accumulate=accumulate, scatter=sc)
             self._conv_tc(dy, 8, wpk, kind, o, B, py, px, n_out_ch)
 
@@ -819,20 +819,27 @@ class Engine:
             else:
                 wgrad_tc(x_src.view(0), 8, d_cat[i].view(0), K.WG_K5S1, name, 64)
             if i > 0:
+                # Stride-2 input gradient by output phases.  Default: TWO launches (one per row phase), each producing both
+                # x-phases in its two lane groups, so that the scattered read-modify-write of the epilogue touches whole
+                # 32 B sectors (four single-phase launches each moved ~300 MB for 47 MB of output);
+                # CNP_S2_DGRAD_4PHASE=1 keeps the four-launch form.
+                if st[i] == 2 and os.environ.get("CNP_S2_DGRAD_4PHASE"):
+                    phases = ((0, 0), (0, 1), (1, 0), (1, 1))
+                else:
+                    phases = ((0, 2), (1, 2))
                 if st[i] == 2 and os.environ.get("CNP_NO_MULTISTREAM"):
-                    for py in (0, 1):
-                        for px in (0, 1):
-                            dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S2_DGRAD, 64, d_cat[i - 1], 0,
-                                     cat[i - 1], 0, accumulate=True, phase=(py, px))
+                    for py, px in phases:
+                        dgrad_tc(d_cat[i].view(0), lyr.weight, f"before{i}", K.KIND_K5S2_DGRAD, 64, d_cat[i - 1], 0,
+                                 cat[i - 1], 0, accumulate=True, phase=(py, px))
                 elif st[i] == 2:
-                    # the four output phases write disjoint pixels: run them on four streams so the small launches
+                    # the phases write disjoint pixels: run them on separate streams so the small launches
                     # share the SMs instead of queueing behind each other
                     if len(self._side_streams) < 4:
                         self._side_streams = [torch.cuda.Stream() for _ in range(4)]
                     main = torch.cuda.current_stream()
                     fork = torch.cuda.Event()
                     fork.record(main)
-                    for si, (py, px) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                    for si, (py, px) in enumerate(phases):
                         ss = self._side_streams[si]
                         ss.wait_event(fork)
                         with torch.cuda.stream(ss):

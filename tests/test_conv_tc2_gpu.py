@@ -190,3 +190,39 @@ def test_conv_tc2_cluster_multicast_matches_plain():
     assert torch.equal(outs[0], outs[1])
     ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=2))
     assert rel_err(outs[0], ref) < 1e-2
+
+
+@pytest.mark.parametrize("h,w", [(40, 48), (76, 152), (22, 310)])
+def test_conv_tc2_dgrad_s2_x_phase_pair(h, w):
+    """Both x-phases of an output row phase in ONE launch (px = 2: lane group g = x-phase g, adjacent output pixels):
+    two launches give the full stride-2 input gradient, with ReLU mask and accumulation, equal to the four-launch form."""
+    torch.manual_seed(9)
+    B = 2
+    dy = torch.randn(B, 64, h // 2, w // 2, device="cuda").bfloat16().float()
+    wt = (torch.randn(64, 64, 5, 5, device="cuda") * 0.05).bfloat16().float()
+    act = torch.randn(B, 64, h, w, device="cuda").bfloat16().float()
+    old = torch.randn(B, 64, h, w, device="cuda").bfloat16().float()
+    xd = torch.zeros(B, 64, h, w, device="cuda", dtype=torch.double, requires_grad=True)
+    F.conv2d(xd, wt.double(), None, stride=2, padding=2).backward(dy.double())
+    dyb, actb = _to_blk(dy), _to_blk(act)
+    plain = _Blk(B, 8, h, w, dy.device)
+    for py in (0, 1):
+        o = _out(plain.view(0), scatter=(2, py, 2, 0))
+        _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S2_DGRAD, 8, py, 2).data_ptr(),
+                   _cabi.KIND_K5S2_DGRAD, py, 2, 64, C.byref(o), B, _S())
+    assert rel_err(_from_blk(plain, 64), xd.grad) < 1e-2
+    assert _pad_is_zero(plain, B, 8, h, w)
+    # mask + accumulate: identical (bit for bit) to the four single-phase launches
+    a4, a2 = _to_blk(old), _to_blk(old)
+    mview = actb.view(0)
+    for py in (0, 1):
+        for px in (0, 1):
+            o = _out(a4.view(0), scatter=(2, py, 2, px), accumulate=1, mask=mview)
+            _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S2_DGRAD, 8, py, px).data_ptr(),
+                       _cabi.KIND_K5S2_DGRAD, py, px, 64, C.byref(o), B, _S())
+        o = _out(a2.view(0), scatter=(2, py, 2, 0), accumulate=1, mask=mview)
+        _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S2_DGRAD, 8, py, 2).data_ptr(),
+                   _cabi.KIND_K5S2_DGRAD, py, 2, 64, C.byref(o), B, _S())
+    assert torch.equal(_from_blk(a4, 64), _from_blk(a2, 64))
+    ref = xd.grad * (act > 0) + old.double()
+    assert rel_err(_from_blk(a2, 64), ref) < 1e-2
