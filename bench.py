@@ -196,10 +196,21 @@ def run_ours(args):
         raise SystemExit("bench.py needs a GPU (the hot path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL logs (the version banner at NCCL_DEBUG=VERSION/WARN, everything at INFO) go to stdout by default, ahead
-        # of the one JSON line the driver reads: send them to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner (and, at NCCL_DEBUG=INFO, its whole log) on stdout while the communicator is
+        # created, ahead of the one JSON line the driver reads: stdout is pointed at stderr for the duration of the
+        # initialisation (file-descriptor level, the banner comes from C code)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)                     # forces the (possibly lazy) communicator creation now
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     torch.manual_seed(0)
     model = ConvNP(precision=args.precision, **model_kwargs(args.internal_density))
     if world > 1:
