@@ -544,8 +544,11 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
     }
   }
   a.ws = nullptr;
-  // the two-kernel reduction only pays for long K loops; short ones keep the atomics
-  if (workspace && total_tiles >= 4096 &&
+  // partial sums through the workspace + reduce kernel; only very short K loops keep the atomics
+  // (with the 16 B / 8-partial reduce kernel the workspace wins down to small layers: 152^2 142.6 -> 130.6 us,
+  // 38^2 41.8 -> 34.3 us against the atomics epilogue)
+  static const int ws_min_tiles = getenv("CNP_WGRAD_WS_MIN_TILES") ? atoi(getenv("CNP_WGRAD_WS_MIN_TILES")) : 128;
+  if (workspace && total_tiles >= ws_min_tiles &&
       workspace_bytes >= (long long)np * a.ksplit * a.ws_acc * 128 * 128 * (long long)sizeof(float))
     a.ws = reinterpret_cast<float*>(workspace);
   cfg.gridDim = dim3(a.ksplit, np);
