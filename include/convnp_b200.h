@@ -108,7 +108,10 @@ int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int p
                 int B, cnp_stream_t s);
 /* Second formulation (weights = M operand, pixels = N operand; runs at the tcgen05 floor, see conv_tc2.cu).
  * n_out = 64: two output rows share one MMA (PAIR); n_out = 128: 128 output channels per call (WIDE, used for
- * the input gradient of the 128->64 layers). */
+ * the input gradient of the 128->64 layers).  n_chunks: 2, 4, .. 16 source chunks for the 5x5 kinds (2 = the folded
+ * first layer).  CNP_K5S2_DGRAD computes one output phase (py, px) of the stride-2 input gradient per call
+ * (output sy = sx = 2, ay = py, ax = px); px = 2 computes BOTH x-phases of row phase py in one call (lane group =
+ * x-phase, adjacent output pixels: output ax = 0), which is what the engine uses. */
 int cnp_conv_tc2_debug(long long* device_buf /*[148][8] or NULL*/, int flags);   /* per-CTA stall counters, profiling aid */
 int cnp_conv_tc2_set_cluster(int cluster /*1 | 2: CTA pairs multicast the weight stream*/);
 long long cnp_conv_tc2_packed_bytes(int kind, int n_chunks, int n_out);
