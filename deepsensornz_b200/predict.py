@@ -141,6 +141,22 @@ class _GraphedForward:
         return self.mean, self.std
 
 
+def _affine_of(dp, var_ID, add_offset: bool):
+    """(a, b) with ``dp.map_array(x, var_ID, unnorm=True, add_offset=add_offset) == a * x + b``, found by probing the
+    data processor (DeepSensor's mean/std and min/max normalisations are affine); None if it is not affine or fails."""
+    try:
+        probe = np.array([0.0, 1.0, 2.0], dtype=np.float32)
+        out = np.asarray(dp.map_array(probe, var_ID, unnorm=True, add_offset=add_offset), dtype=np.float64)
+    except Exception:  # noqa: BLE001
+        return None
+    if out.shape != (3,) or not np.all(np.isfinite(out)):
+        return None
+    a, b = out[1] - out[0], out[0]
+    if not np.isclose(out[2] - out[1], a, rtol=1e-6, atol=1e-12):
+        return None
+    return float(a), float(b)
+
+
 def _target_coords(model, X_t, X_t_is_normalised: bool):
     """-> (mode, X_t_norm, raw coords for the output).  mode 'on-grid' gives a tuple (x1[N1], x2[N2])."""
     dp = model.data_processor
@@ -200,6 +216,17 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
     # back through two page-locked buffers with asynchronous copies, so the D2H of task i overlaps the kernels of
     # task i+1 (the reference reads every result back synchronously).
     n = len(tasks)
+    var_ID = "target"
+    if tl is not None and getattr(tl, "target_var_IDs", None):
+        var_ID = tl.target_var_IDs[0][0]
+    # un-normalisation: when the data processor's map is affine it is applied on the GPU before the
+    # read-back (two tiny elementwise launches per task) instead of as two host passes over the [T, N1, N2] results
+    dpr = model.data_processor
+    aff_mean = aff_std = None
+    if unnormalise and dpr is not None and torch.cuda.is_available():
+        aff_mean, aff_std = _affine_of(dpr, var_ID, True), _affine_of(dpr, var_ID, False)
+        if aff_mean is None or aff_std is None:
+            aff_mean = aff_std = None
     mean_out = std_out = None
     times = []
     ctx_cache = {}
@@ -271,6 +298,12 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
                     torch.cuda.current_stream().wait_stream(copy_stream)
                     db.ready = None
                     graphs[sig] = _GraphedForward(model, db)
+        if aff_mean is not None:
+            mean = mean * aff_mean[0] + aff_mean[1]
+            std = std * aff_std[0] + aff_std[1]
+            if gf is not None:          # read back on the copy stream: keep the temporaries alive for it
+                mean.record_stream(copy_stream)
+                std.record_stream(copy_stream)
         if mean_out is None:
             mean_out = np.empty((n,) + tuple(mean.shape), dtype=np.float32)
             std_out = np.empty_like(mean_out)
@@ -306,11 +339,8 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
             f.result()
     pool.shutdown()
     mean, std = mean_out, std_out
-    var_ID = "target"
-    if tl is not None and getattr(tl, "target_var_IDs", None):
-        var_ID = tl.target_var_IDs[0][0]
     dp = model.data_processor
-    if unnormalise and dp is not None:
+    if unnormalise and dp is not None and aff_mean is None:
         mean = dp.map_array(mean, var_ID, unnorm=True)
         std = dp.map_array(std, var_ID, unnorm=True, add_offset=False)
     pred = Prediction()

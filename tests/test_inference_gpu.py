@@ -226,3 +226,49 @@ def test_predict_context_cache_is_not_fooled_by_recycled_buffers(static):
         single = m.predict([t], X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
         assert np.array_equal(np.asarray(single[key]["mean"])[0], mean[i]), i
     assert not np.array_equal(mean[0], mean[1])
+
+
+class _FakeProcessor:
+    """Stand-in for deepsensor's DataProcessor: mean/std normalisation of the target variable (affine), or a
+    non-affine map to exercise the host fallback."""
+
+    def __init__(self, mean=281.5, std=7.25, affine=True):
+        self.mean, self.std, self.affine, self.calls = mean, std, affine, 0
+
+    def map_array(self, data, var_ID, method=None, unnorm=False, add_offset=True):
+        self.calls += 1
+        data = np.asarray(data)
+        assert unnorm
+        if not self.affine:
+            return np.exp(data * 0.1).astype(data.dtype)
+        out = data * self.std
+        return out + self.mean if add_offset else out
+
+
+def test_predict_unnormalises_on_the_device(static):
+    """An affine data-processor map is applied on the GPU before the read-back (no host pass over the [T,N1,N2]
+    results); a non-affine one falls back to ``map_array`` on the host.  Both equal the normalised prediction mapped
+    by hand."""
+    tasks = [make_task(static, 7000 + i, all_context=True) for i in range(3)]
+    m = small_model("fp32")
+    x1 = np.linspace(0.05, 0.95, 41).astype(np.float32)
+    x2 = np.linspace(0.10, 0.90, 37).astype(np.float32)
+    aux = np.random.default_rng(3).uniform(-1, 1, (5, 41, 37)).astype(np.float32)
+    kw = dict(X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
+    raw = m.predict(tasks, **kw)
+    key = list(raw.keys())[0]
+    mean_n, std_n = np.asarray(raw[key]["mean"]), np.asarray(raw[key]["std"])
+    dp = _FakeProcessor()
+    m.data_processor = dp
+    out = m.predict(tasks, **kw)
+    assert dp.calls == 2                                  # only the two 3-point probes, no full-array call
+    assert np.allclose(np.asarray(out[key]["mean"]), mean_n * np.float32(dp.std) + np.float32(dp.mean), rtol=1e-6, atol=1e-5)
+    assert np.allclose(np.asarray(out[key]["std"]), std_n * np.float32(dp.std), rtol=1e-6)
+    dp2 = _FakeProcessor(affine=False)
+    m.data_processor = dp2
+    out2 = m.predict(tasks, **kw)
+    assert dp2.calls == 4                                 # probes rejected, then the host fallback for mean and std
+    assert np.allclose(np.asarray(out2[key]["mean"]), np.exp(mean_n * 0.1), rtol=1e-6)
+    unn = m.predict(tasks, unnormalise=False, **kw)
+    assert np.array_equal(np.asarray(unn[key]["mean"]), mean_n)
+    m.data_processor = None
