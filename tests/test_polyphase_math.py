@@ -1,0 +1,22 @@
+"""CPU check of the identity behind the planned polyphase resize-convolution (tools/polyphase_check.py):
+conv5x5(zero_pad(bilinear_up2x(x))) == four 4x4 phase convolutions of the replicate-padded input minus the 5x5
+convolution of a two-pixel frame -- exact in float64, and the frame term only reaches outputs within 2 pixels of the border."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import polyphase_check as P  # noqa: E402
+
+
+@pytest.mark.parametrize("h,w", [(7, 9), (8, 8), (1, 5), (2, 2), (19, 38)])
+def test_polyphase_identity(h, w):
+    err_interior, err_total, border_only = P.check(H=h, W=w, seed=h * 100 + w)
+    assert err_interior < 1e-12 and err_total < 1e-12 and border_only
+
+
+def test_phase_weights_cut_the_tap_count():
+    import torch
+    wp = P.phase_weights(torch.randn(4, 3, 5, 5, dtype=torch.float64))
+    assert wp.shape == (2, 2, 4, 3, 4, 4)          # 4 phases x 16 taps = 64 tap-GEMMs per low-res pixel (vs 4 x 25)

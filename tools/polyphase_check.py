@@ -1,0 +1,85 @@
+"""Groundwork for the next structural step: the resize-convolution of upstream's UNet decoder levels,
+
+    y = conv5x5(zero_pad_2(bilinear_up2x(x)))          (torch.nn.Upsample(scale_factor=2, mode="bilinear") + Conv2d(k=5, padding=2))
+
+computed WITHOUT materialising the upsampled tensor:
+
+    y = polyphase(x~) - conv5x5(E)
+
+* x~ = x replicate-padded by 2 low-res pixels.  Interpolating x~ with the interior formula
+  (U'(2m) = 0.25 x~[m-1] + 0.75 x~[m],  U'(2m+1) = 0.75 x~[m] + 0.25 x~[m+1]) reproduces the clamped bilinear upsampling
+  exactly on the image and extends it onto the 2-pixel frame where the reference has ZEROS.
+* polyphase: output phase (a, b) in {0,1}^2 of y is a 4 x 4-tap convolution of x~ with weights folded from W5 and the
+  interpolation weights: 4 x 16 = 64 tap-GEMMs per low-res pixel instead of 4 x 25 = 100.
+* E = U' on the frame (rows / columns -2, -1, 2H, 2H+1), zero inside: the part of U' the reference does not have.  It
+  only reaches the outputs within 2 pixels of the border, and E(-1, X) = E(-2, X) = U'(0, X) etc., so conv5x5(E) is a
+  handful of 1-D convolutions of the border rows / columns with row-summed weights.
+
+This script checks the identity in float64 (max abs error ~1e-15) for odd / even sizes; it is pure torch on the CPU.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def phase_weights(w5: torch.Tensor) -> torch.Tensor:
+    """w5 [Co,Ci,5,5] -> wp [2,2,Co,Ci,4,4]: phase (a,b) taps over low-res offsets d in {-2+a .. 1+a} (index d + 2 - a)."""
+    co, ci = w5.shape[:2]
+    # 1-D folding matrix: for output phase a and kernel tap k the hi-res row is R = 2i + a + k - 2 = 2m + r;
+    # r = 0 reads 0.25 x[m-1] + 0.75 x[m], r = 1 reads 0.75 x[m] + 0.25 x[m+1]; m - i = floor((a + k - 2) / 2)
+    fold = torch.zeros(2, 5, 4, dtype=w5.dtype)        # [phase][tap k][low-res offset index]
+    for a in range(2):
+        for k in range(5):
+            s = a + k - 2
+            m, r = s // 2, s % 2
+            for dm, wgt in (((-1, 0.25), (0, 0.75)) if r == 0 else ((0, 0.75), (1, 0.25))):
+                fold[a, k, m + dm + 2 - a] += wgt       # offsets m + dm in {-2+a .. 1+a}
+    # separable in the two dimensions
+    return torch.einsum("oikl,akp,blq->aboipq", w5, fold, fold)
+
+
+def upconv_polyphase(x: torch.Tensor, w5: torch.Tensor) -> torch.Tensor:
+    """conv5x5(U') where U' is the interior interpolation of the replicate-padded x, as four 4x4 phase convolutions."""
+    B, C, H, W = x.shape
+    xt = F.pad(x, (2, 2, 2, 2), mode="replicate")
+    wp = phase_weights(w5)
+    y = x.new_zeros(B, w5.shape[0], 2 * H, 2 * W)
+    for a in range(2):
+        for b in range(2):
+            # low-res window rows i - 2 + a .. i + 1 + a  ->  padded rows i + a .. i + a + 3
+            win = xt[:, :, a:a + H + 3, b:b + W + 3]
+            y[:, :, a::2, b::2] = F.conv2d(win, wp[a, b])
+    return y
+
+
+def frame_of_extended_upsampling(x: torch.Tensor) -> torch.Tensor:
+    """E on the (2H+4) x (2W+4) canvas: U' on the 2-pixel frame, zero inside."""
+    B, C, H, W = x.shape
+    up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    ext = F.pad(up, (2, 2, 2, 2), mode="replicate")      # U' on the frame = the nearest border value of U (see docstring)
+    ext[:, :, 2:-2, 2:-2] = 0
+    return ext
+
+
+def upconv_reference(x, w5):
+    return F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), w5, padding=2)
+
+
+def check(B=2, C=3, Co=4, H=7, W=9, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, dtype=torch.float64, generator=g)
+    w5 = torch.randn(Co, C, 5, 5, dtype=torch.float64, generator=g)
+    ref = upconv_reference(x, w5)
+    poly = upconv_polyphase(x, w5)
+    corr = F.conv2d(frame_of_extended_upsampling(x), w5)  # canvas already carries the 2-pixel frame: no padding
+    inner = (poly - ref)[:, :, 2:-2, 2:-2]
+    err_interior = float(inner.abs().max()) if inner.numel() else 0.0
+    err_total = float((poly - corr - ref).abs().max())
+    touched = (corr.abs() > 0).any(dim=1).any(dim=0)
+    border_only = not bool(touched[2:-2, 2:-2].any())
+    return err_interior, err_total, border_only
+
+
+if __name__ == "__main__":
+    for shape in ((7, 9), (8, 8), (1, 5), (38, 38)):
+        ei, et, bo = check(H=shape[0], W=shape[1])
+        print(f"H x W = {shape}: interior error {ei:.2e}, with frame correction {et:.2e}, correction confined to the border: {bo}")
