@@ -20,3 +20,12 @@ def test_phase_weights_cut_the_tap_count():
     import torch
     wp = P.phase_weights(torch.randn(4, 3, 5, 5, dtype=torch.float64))
     assert wp.shape == (2, 2, 4, 3, 4, 4)          # 4 phases x 16 taps = 64 tap-GEMMs per low-res pixel (vs 4 x 25)
+
+
+@pytest.mark.parametrize("h,w", [(7, 9), (8, 8), (1, 5), (13, 4)])
+def test_polyphase_backward_formulas(h, w):
+    """Input and weight gradients in the form the kernels would compute them (phase-wise low-resolution weight gradient
+    folded back through the interpolation matrix, phase-wise transposed convolutions, replicate-pad folding, frame term)
+    equal autograd of upsample + conv."""
+    err_dx, err_dw = P.check_backward(H=h, W=w, seed=h * 10 + w)
+    assert err_dx < 1e-11 and err_dw < 1e-11

@@ -79,7 +79,80 @@ def check(B=2, C=3, Co=4, H=7, W=9, seed=0):
     return err_interior, err_total, border_only
 
 
+def fold_matrix(dtype=torch.float64) -> torch.Tensor:
+    """[phase a][5x5 tap k][low-res offset index p]: the 1-D map from kernel taps to phase taps used by phase_weights."""
+    fold = torch.zeros(2, 5, 4, dtype=dtype)
+    for a in range(2):
+        for k in range(5):
+            s = a + k - 2
+            m, r = s // 2, s % 2
+            for dm, wgt in (((-1, 0.25), (0, 0.75)) if r == 0 else ((0, 0.75), (1, 0.25))):
+                fold[a, k, m + dm + 2 - a] += wgt
+    return fold
+
+
+def upconv_backward_explicit(x: torch.Tensor, w5: torch.Tensor, dy: torch.Tensor):
+    """The gradients in the form the kernels will compute them (no autograd):
+
+    * dWp[a,b] = correlation of the replicate-padded low-res input with the phase (a,b) sub-image of dY (a weight gradient
+      at LOW resolution, 16 taps), folded back to the 5x5 weights with the same interpolation matrix:
+      dW5[o,i,k,l] = sum_{a,b,p,q} dWp[a,b,o,i,p,q] fold[a,k,p] fold[b,l,q];  minus the frame term  dY (*) E.
+    * dx~ = sum over phases of the transposed 4x4 convolution of the phase sub-image of dY; the replicate padding folds
+      the gradient of the padded border back onto the edge pixels; minus the gradient through the frame term.
+    Returns (dx, dw5) for y = upconv_reference(x, w5), dL/dy = dy."""
+    B, C, H, W = x.shape
+    Co = w5.shape[0]
+    fold = fold_matrix(x.dtype)
+    wp = phase_weights(w5)
+    xt = F.pad(x, (2, 2, 2, 2), mode="replicate")
+    dxt = torch.zeros_like(xt)
+    dwp = torch.zeros_like(wp)
+    for a in range(2):
+        for b in range(2):
+            dyp = dy[:, :, a::2, b::2]                                     # [B,Co,H,W] phase sub-image
+            win = xt[:, :, a:a + H + 3, b:b + W + 3]
+            # weight gradient of a 4x4 correlation: dwp[o,i,p,q] = sum_{n,y,x} dyp[n,o,y,x] win[n,i,y+p,x+q]
+            dwp[a, b] = F.conv2d(win.transpose(0, 1), dyp.transpose(0, 1)).transpose(0, 1)
+            # input gradient: full correlation with the flipped kernel
+            dxt[:, :, a:a + H + 3, b:b + W + 3] += F.conv_transpose2d(dyp, wp[a, b])
+    dw5 = torch.einsum("aboipq,akp,blq->oikl", dwp, fold, fold)
+    # replicate padding backward: border strips accumulate onto the edge rows / columns
+    dx = dxt[:, :, 2:-2, 2:-2].clone()
+    dx[:, :, 0] += dxt[:, :, :2, 2:-2].sum(2); dx[:, :, -1] += dxt[:, :, -2:, 2:-2].sum(2)
+    dx[:, :, :, 0] += dxt[:, :, 2:-2, :2].sum(3); dx[:, :, :, -1] += dxt[:, :, 2:-2, -2:].sum(3)
+    dx[:, :, 0, 0] += dxt[:, :, :2, :2].sum((2, 3)); dx[:, :, 0, -1] += dxt[:, :, :2, -2:].sum((2, 3))
+    dx[:, :, -1, 0] += dxt[:, :, -2:, :2].sum((2, 3)); dx[:, :, -1, -1] += dxt[:, :, -2:, -2:].sum((2, 3))
+    # frame term  - conv5x5(E(x)):  E is linear in x (upsample, replicate-extend, zero the interior)
+    E = frame_of_extended_upsampling(x)
+    dw5 = dw5 - F.conv2d(E.transpose(0, 1), dy.transpose(0, 1)).transpose(0, 1)
+    dE = F.conv_transpose2d(dy, w5)                                        # gradient w.r.t. the (2H+4) x (2W+4) canvas
+    dE[:, :, 2:-2, 2:-2] = 0
+    # back through the replicate extension of U (frame -> nearest border pixel of U) ...
+    dU = torch.zeros(B, C, 2 * H, 2 * W, dtype=x.dtype)
+    dU[:, :, 0] += dE[:, :, :2, 2:-2].sum(2); dU[:, :, -1] += dE[:, :, -2:, 2:-2].sum(2)
+    dU[:, :, :, 0] += dE[:, :, 2:-2, :2].sum(3); dU[:, :, :, -1] += dE[:, :, 2:-2, -2:].sum(3)
+    dU[:, :, 0, 0] += dE[:, :, :2, :2].sum((2, 3)); dU[:, :, 0, -1] += dE[:, :, :2, -2:].sum((2, 3))
+    dU[:, :, -1, 0] += dE[:, :, -2:, :2].sum((2, 3)); dU[:, :, -1, -1] += dE[:, :, -2:, -2:].sum((2, 3))
+    # ... and through the bilinear upsampling (only the border rows / columns of dU are non-zero)
+    xg = x.detach().clone().requires_grad_(True)
+    F.interpolate(xg, scale_factor=2, mode="bilinear", align_corners=False).backward(dU)
+    dx = dx - xg.grad
+    return dx, dw5
+
+
+def check_backward(B=2, C=3, Co=4, H=7, W=9, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, dtype=torch.float64, generator=g, requires_grad=True)
+    w5 = torch.randn(Co, C, 5, 5, dtype=torch.float64, generator=g, requires_grad=True)
+    dy = torch.randn(B, Co, 2 * H, 2 * W, dtype=torch.float64, generator=g)
+    upconv_reference(x, w5).backward(dy)
+    dx, dw5 = upconv_backward_explicit(x.detach(), w5.detach(), dy)
+    return float((dx - x.grad).abs().max()), float((dw5 - w5.grad).abs().max())
+
+
 if __name__ == "__main__":
     for shape in ((7, 9), (8, 8), (1, 5), (38, 38)):
         ei, et, bo = check(H=shape[0], W=shape[1])
         print(f"H x W = {shape}: interior error {ei:.2e}, with frame correction {et:.2e}, correction confined to the border: {bo}")
+        ex, ew = check_backward(H=shape[0], W=shape[1])
+        print(f"             backward (explicit phase formulas vs autograd of the reference): dx {ex:.2e}, dW5 {ew:.2e}")
