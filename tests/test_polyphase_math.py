@@ -29,3 +29,15 @@ def test_polyphase_backward_formulas(h, w):
     equal autograd of upsample + conv."""
     err_dx, err_dw = P.check_backward(H=h, W=w, seed=h * 10 + w)
     assert err_dx < 1e-11 and err_dw < 1e-11
+
+
+def test_polyphase_position_plan_matches_phase_convolutions():
+    """The per-position accumulation a conv_tc2 phase kind would run (20 window offsets per K block and row phase, the
+    two x-phases as lane groups) reproduces the four phase convolutions."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 6, 11, dtype=torch.float64, generator=g)
+    w = torch.randn(3, 5, 5, 5, dtype=torch.float64, generator=g)
+    y, n_pos = P.upconv_by_plan(x, w)
+    assert n_pos == 20
+    assert float((y - P.upconv_polyphase(x, w)).abs().max()) < 1e-12

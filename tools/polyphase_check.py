@@ -150,9 +150,52 @@ def check_backward(B=2, C=3, Co=4, H=7, W=9, seed=0):
     return float((dx - x.grad).abs().max()), float((dw5 - w5.grad).abs().max())
 
 
+def phase_pair_plan(a: int):
+    """Positions of a conv_tc2-style plan for output row phase ``a`` with the two x-phases as the two lane groups
+    (the layout the stride-2 dgrad already uses): a position is a window offset (r, c) in the replicate-padded low-res
+    tensor relative to the low-res pixel (i, j) -- padded index (i + r, j + c) -- and carries, per x-phase b, the index
+    (p, q) of the 4x4 phase tap it multiplies, or None.  Row taps: padded rows i + a + p (p = 0..3); column taps of
+    x-phase b: padded columns j + b + q (q = 0..3).  Union over b: 4 rows x 5 columns = 20 positions per 16-channel K
+    block (x-phase 0 has no tap at column offset 4, x-phase 1 none at offset 0)."""
+    plan = []
+    for p in range(4):
+        for c in range(5):
+            taps = []
+            for b in range(2):
+                q = c - b
+                taps.append((p, q) if 0 <= q < 4 else None)
+            plan.append(((a + p, c), taps))
+    return plan
+
+
+def upconv_by_plan(x: torch.Tensor, w5: torch.Tensor) -> torch.Tensor:
+    """The polyphase forward evaluated position by position exactly as the tensor-core kernel would accumulate it
+    (one 'MMA' per position: all pixels of a row x all input channels x both x-phases)."""
+    B, C, H, W = x.shape
+    xt = F.pad(x, (2, 2, 2, 2), mode="replicate")
+    wp = phase_weights(w5)
+    y = x.new_zeros(B, w5.shape[0], 2 * H, 2 * W)
+    n_pos = 0
+    for a in range(2):
+        plan = phase_pair_plan(a)
+        n_pos = len(plan)
+        for (r, c), taps in plan:
+            win = xt[:, :, r:r + H, c:c + W]                      # the shifted window: one pixel per low-res output pixel
+            for b, t in enumerate(taps):
+                if t is not None:
+                    y[:, :, a::2, b::2] += torch.einsum("nchw,oc->nohw", win, wp[a, b][:, :, t[0], t[1]])
+    return y, n_pos
+
+
 if __name__ == "__main__":
     for shape in ((7, 9), (8, 8), (1, 5), (38, 38)):
         ei, et, bo = check(H=shape[0], W=shape[1])
         print(f"H x W = {shape}: interior error {ei:.2e}, with frame correction {et:.2e}, correction confined to the border: {bo}")
+        g = torch.Generator().manual_seed(1)
+        xx = torch.randn(2, 3, shape[0], shape[1], dtype=torch.float64, generator=g)
+        ww = torch.randn(4, 3, 5, 5, dtype=torch.float64, generator=g)
+        yp, n_pos = upconv_by_plan(xx, ww)
+        print(f"             position plan ({n_pos} positions per K block and row phase): "
+              f"{float((yp - upconv_polyphase(xx, ww)).abs().max()):.2e} vs the phase convolutions")
         ex, ew = check_backward(H=shape[0], W=shape[1])
         print(f"             backward (explicit phase formulas vs autograd of the reference): dx {ex:.2e}, dW5 {ew:.2e}")
