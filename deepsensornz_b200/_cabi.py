@@ -57,7 +57,7 @@ class CnpConvOut(C.Structure):
 
 
 # conv_tc kinds (must match conv_bf16.cu)
-KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD = range(6)
+KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD, KIND_UP_PHASE = range(7)
 # conv_tc_wgrad kinds (must match wgrad_bf16.cu)
 WG_K5S1, WG_K1, WG_K5S2, WG_K5S1_NARROW = range(4)
 
@@ -115,6 +115,7 @@ _SIGS = {
     "cnp_conv_tc2": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
     "cnp_blk_from_nchw_f32": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
     "cnp_blk_from_nchw_f32_ones": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), _i, C.c_ulonglong, c_stream]),
+    "cnp_up_phase_weights": (C.c_int, [c_fp, _i, _i, c_fp, c_stream]),
     "cnp_fold_in_fwd": (C.c_int, [c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_fold_in_bwd": (C.c_int, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_stream]),
     "cnp_blk_to_nchw_f32": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, _ll, c_stream]),

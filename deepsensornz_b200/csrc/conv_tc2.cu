@@ -558,7 +558,8 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transposed, int wide, int co_off,
-             __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_c2_plan plan, int total_pos) {
+             __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_c2_plan plan, int total_pos,
+             long long group_stride /* elements between the weight tensors of lane groups 0 and 1 (0: the same tensor) */) {
   const long long total = (long long)total_pos * 2048;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     const int c = (int)(e & 7), m = (int)((e >> 3) & 127), k8 = (int)((e >> 10) & 1);
@@ -573,7 +574,7 @@ pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transpos
       const int kc = plan.kb_wci0[kb] + k8 * 8 + c;
       const int nn = co_off + (wide ? m : n);
       if (!transposed) {
-        if (nn < Cout && kc < Cin) v = w[(((size_t)nn * Cin + kc) * k + ky) * k + kx];
+        if (nn < Cout && kc < Cin) v = w[(size_t)g * group_stride + (((size_t)nn * Cin + kc) * k + ky) * k + kx];
       } else {
         if (kc < Cout && nn < Cin) v = w[(((size_t)kc * Cin + nn) * k + ky) * k + kx];
       }
@@ -585,7 +586,8 @@ pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transpos
 // ---------------------------------------------------------------------------------------------
 // host-side plan construction
 // ---------------------------------------------------------------------------------------------
-enum { KIND_K5S1 = 0, KIND_K1 = 1, KIND_K5S2 = 2, KIND_K5S1_DGRAD = 3, KIND_K1_DGRAD = 4, KIND_K5S2_DGRAD = 5 };
+enum { KIND_K5S1 = 0, KIND_K1 = 1, KIND_K5S2 = 2, KIND_K5S1_DGRAD = 3, KIND_K1_DGRAD = 4, KIND_K5S2_DGRAD = 5,
+       KIND_UP_PHASE = 6 };
 
 struct Tap { int roff, coff, wky, wkx; };
 
@@ -670,6 +672,23 @@ int build_plan2(int kind, int n_chunks, int pitch, int py, int px, int wide, cnp
       if (int e = add_type(p, 0, taps, nt, pitch, wide)) return e;
     }
     for (int g = 0; g < 4; ++g) add_kb(2 * g, 16 * g, 0);
+  } else if (kind == KIND_UP_PHASE) {
+    // Polyphase form of conv5x5(bilinear_up2x(x)) (tools/polyphase_check.py): output row phase py of the high-resolution
+    // result as a 4x4-tap convolution of the REPLICATE-padded low-resolution input; lane group g = output x-phase g.
+    // Window offset of phase tap (p, q) of x-phase b: (py + p, b + q) -- 4 rows x 5 column offsets = 20 positions per
+    // 16-channel K block (x-phase 0 has no tap at column offset 4, x-phase 1 none at 0).  The weights are the 4x4 phase
+    // weights [b][Cout][Cin][4][4] of row phase py (cnp_up_phase_weights).
+    CNP_REQUIRE(n_chunks >= 2 && n_chunks <= 16 && n_chunks % 2 == 0 && !wide && (py == 0 || py == 1),
+                "conv plan: the up-phase kind needs 2..16 source chunks, 64 outputs per x-phase, py in {0,1}");
+    Tap taps1[25];
+    int nt = 0, nt1 = 0;
+    for (int pp = 0; pp < 4; ++pp)
+      for (int qq = 0; qq < 4; ++qq) {
+        taps[nt++] = Tap{py + pp, qq, pp, qq};
+        taps1[nt1++] = Tap{py + pp, 1 + qq, pp, qq};
+      }
+    if (int e = add_type(p, 0, taps, nt, pitch, 0, taps1, nt1)) return e;
+    for (int g = 0; g < n_chunks / 2; ++g) add_kb(2 * g, 16 * g, 0);
   } else {
     CNP_REQUIRE(false, "conv plan: unknown kind %d", kind);
   }
@@ -778,10 +797,12 @@ CNP_API int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind
   CNP_REQUIRE(n_out == 64 || n_out == 128, "conv_tc2_pack: n_out must be 64 or 128");
   cnp_c2_plan p;
   if (int e = build_plan2(kind, n_chunks, 8, py, px, n_out == 128, &p)) return e;
-  const int transposed = (kind >= KIND_K5S1_DGRAD) ? 1 : 0;
   const int total_pos = plan_total_pos(p);
+  CNP_REQUIRE(kind != KIND_UP_PHASE || k == 4, "conv_tc2_pack: the up-phase kind packs 4x4 phase weights [2][Cout][Cin][4][4]");
+  const int transposed = (kind >= KIND_K5S1_DGRAD && kind <= KIND_K5S2_DGRAD) ? 1 : 0;
   pack2_kernel<<<128, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, co_off,
-                                    reinterpret_cast<__nv_bfloat16*>(wpk), p, total_pos);
+                                    reinterpret_cast<__nv_bfloat16*>(wpk), p, total_pos,
+                                    kind == KIND_UP_PHASE ? (long long)Cout * Cin * 16 : 0ll);
   CNP_LAUNCH_CHECK("pack2_kernel");
   return 0;
 }
@@ -801,7 +822,7 @@ CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int ki
   a.x_bs = x->bstride;
   a.w = reinterpret_cast<const uint8_t*>(wpk);
   a.wide = n_out == 128;
-  a.pxpair = (kind == KIND_K5S2_DGRAD && px == 2) ? 1 : 0;
+  a.pxpair = ((kind == KIND_K5S2_DGRAD && px == 2) || kind == KIND_UP_PHASE) ? 1 : 0;
   CNP_REQUIRE(!a.pxpair || (o->mode == 0 && o->sx == 2 && o->ax == 0 && !o->s2d),
               "conv_tc2: the x-phase pair writes a blocked output with sx = 2, ax = 0");
   a.out_mode = o->mode;

@@ -72,7 +72,49 @@ fold_in_bwd_w1_kernel(const float* __restrict__ dwf, const float* __restrict__ w
   }
 }
 
+// 1-D map from the 5 kernel taps to the 4 low-resolution taps of output phase a of a x2 bilinear upsampling
+// (align_corners = False, interior formula): hi-res row 2i + a + k - 2 = 2m + r reads 0.25 x[m-1] + 0.75 x[m] (r = 0)
+// or 0.75 x[m] + 0.25 x[m+1] (r = 1); low-res offset index = m + dm + 2 - a - i.  (tools/polyphase_check.py)
+__device__ __forceinline__ float up_fold(int a, int k, int p) {
+  const int s = a + k - 2;
+  const int m = (s >= 0) ? s / 2 : -((-s + 1) / 2), r = s - 2 * m;
+  const int p0 = m + (r == 0 ? -1 : 0) + 2 - a, p1 = p0 + 1;
+  const float w0 = r == 0 ? 0.25f : 0.75f, w1 = r == 0 ? 0.75f : 0.25f;
+  return (p == p0 ? w0 : 0.f) + (p == p1 ? w1 : 0.f);
+}
+
+// wp[a][b][co][ci][p][q] = sum_{k,l} w5[co][ci][k][l] fold(a,k,p) fold(b,l,q)
+__global__ void __launch_bounds__(256)
+up_phase_weights_kernel(const float* __restrict__ w5, int Cout, int Cin, float* __restrict__ wp) {
+  const int total = 4 * Cout * Cin * 16;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int q = e & 3, p = (e >> 2) & 3, rest = e >> 4;
+    const int ci = rest % Cin, co = (rest / Cin) % Cout, ab = rest / (Cin * Cout);
+    const int a = ab >> 1, b = ab & 1;
+    const float* w = w5 + ((size_t)co * Cin + ci) * 25;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float fk = up_fold(a, k, p);
+      if (fk != 0.f) {
+#pragma unroll
+        for (int l = 0; l < 5; ++l) s = fmaf(__ldg(w + k * 5 + l) * fk, up_fold(b, l, q), s);
+      }
+    }
+    wp[e] = s;
+  }
+}
+
 }  // namespace
+
+// Phase weights of the polyphase resize-convolution (groundwork for replacing Upsample + Conv 5x5 of the UNet decoder
+// levels): wp [2 (row phase)][2 (x-phase)][Cout][Cin][4][4] fp32 from w5 [Cout][Cin][5][5].
+CNP_API int cnp_up_phase_weights(const float* w5, int Cout, int Cin, float* wp, cudaStream_t st) {
+  CNP_REQUIRE(w5 && wp && Cout > 0 && Cin > 0, "up_phase_weights: bad arguments");
+  up_phase_weights_kernel<<<cnp_cdiv(4 * Cout * Cin * 16, 256), 256, 0, st>>>(w5, Cout, Cin, wp);
+  CNP_LAUNCH_CHECK("up_phase_weights_kernel");
+  return 0;
+}
 
 // wf [Cout][Cp][k*k] fp32 <- W5 [Cout][Cmid][k][k], W1 [Cmid][Cin], b1 [Cmid]; channels Cin+1 .. Cp-1 are zero.
 CNP_API int cnp_fold_in_fwd(const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin, int Cp, int k,

@@ -96,7 +96,10 @@ typedef struct cnp_conv_out {
   const cnp_blk* s2d;  /* cnp_conv_tc2 only: also write the space-to-depth copy (32 chunks, half size) or NULL */
 } cnp_conv_out;
 
-enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5 };
+enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5,
+       CNP_UP_PHASE = 6 /* building block, not yet used by the engine: row phase py of conv5x5(bilinear_up2x(x)) as a 4x4
+                           convolution of the REPLICATE-padded low-res x; both x-phases per call; weights from
+                           cnp_up_phase_weights()[py], packed with k = 4; output sy = sx = 2, ay = py, ax = 0 */ };
 enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2, CNP_WG_K5S1_NARROW = 3 /* 1..8 source chunks */ };
 
 long long cnp_conv_tc_packed_bytes(int kind, int n_chunks);
@@ -144,6 +147,8 @@ int cnp_blk_from_nchw_f32_ones(const float* src, long long src_bstride, int B, i
                                cnp_stream_t s);
 /* initial 1x1 (neuralprocesses UNet.initial_linear) folded into the first 5x5 (before_turn_layers[0]):
  * wf [Cout][Cp][k*k] = W5 . [W1 | b1] (channels Cin+1..Cp-1 zero); bwd maps the folded gradient dwf back (+=). */
+/* wp [2 row phase][2 x-phase][Cout][Cin][4][4] <- w5 [Cout][Cin][5][5]: polyphase weights of Upsample(x2, bilinear) + Conv 5x5 */
+int cnp_up_phase_weights(const float* w5, int Cout, int Cin, float* wp, cnp_stream_t s);
 int cnp_fold_in_fwd(const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin, int Cp, int k,
                     float* wf, cnp_stream_t s);
 int cnp_fold_in_bwd(const float* dwf, const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin,

@@ -226,3 +226,53 @@ def test_conv_tc2_dgrad_s2_x_phase_pair(h, w):
     assert torch.equal(_from_blk(a4, 64), _from_blk(a2, 64))
     ref = xd.grad * (act > 0) + old.double()
     assert rel_err(_from_blk(a2, 64), ref) < 1e-2
+
+
+@pytest.mark.parametrize("cin,h,w", [(128, 19, 23), (64, 38, 152), (16, 8, 40)])
+def test_conv_tc2_up_phase_kind_matches_polyphase_reference(cin, h, w):
+    """Building block for the polyphase resize-convolution (tools/polyphase_check.py): the up-phase kind
+    computes one row phase (both x-phases) of conv5x5(bilinear_up2x(x)) as a 4x4 convolution of the replicate-padded
+    low-resolution input.  Two launches == four phase convolutions in float64 (same bf16-rounded phase weights), and, away
+    from the border, == Upsample + Conv2d itself."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import polyphase_check as P
+    torch.manual_seed(13)
+    B = 2
+    x = torch.randn(B, cin, h, w, device="cuda").bfloat16().float()
+    w5 = (torch.randn(64, cin, 5, 5, device="cuda") * 0.05)
+    bias = torch.randn(64, device="cuda") * 0.1
+    wp = torch.empty(2, 2, 64, cin, 4, 4, device="cuda")
+    _cabi.call("cnp_up_phase_weights", w5.data_ptr(), 64, cin, wp.data_ptr(), _S())
+    assert rel_err(wp, P.phase_weights(w5.double().cpu())) < 1e-6
+    # blocked input whose 2-pixel pad holds the REPLICATED border
+    xb = _Blk(B, cin // 8, h, w, x.device)
+    xt = F.pad(x, (2, 2, 2, 2), mode="replicate")                                  # [B,C,h+4,w+4]
+    xb.t[:B * xb.bstride].view(B, cin // 8, h + 4, w + 4, 8).copy_(
+        xt.view(B, cin // 8, 8, h + 4, w + 4).permute(0, 1, 3, 4, 2).bfloat16())
+    y = _Blk(B, 8, 2 * h, 2 * w, x.device)
+    for a in (0, 1):
+        nbytes = _cabi.lib().cnp_conv_tc2_packed_bytes(_cabi.KIND_UP_PHASE, cin // 8, 64)
+        wpk = torch.empty(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+        wa = wp[a].contiguous()
+        _cabi.call("cnp_conv_tc2_pack", wa.data_ptr(), 64, cin, 4, _cabi.KIND_UP_PHASE, cin // 8, a, 0, 0, 64,
+                   wpk.data_ptr(), _S())
+        o = _out(y.view(0), bias=bias, relu=1, scatter=(2, a, 2, 0))
+        _cabi.call("cnp_conv_tc2", C.byref(xb.view()), cin // 8, wpk.data_ptr(), _cabi.KIND_UP_PHASE, a, 0, 64,
+                   C.byref(o), B, _S())
+    got = _from_blk(y, 64)
+    # same arithmetic in float64: bf16-rounded phase weights, replicate-padded input, four 4x4 phase convolutions
+    wpb = wp.bfloat16().double()
+    ref = torch.zeros(B, 64, 2 * h, 2 * w, device="cuda", dtype=torch.double)
+    xt64 = xt.double()
+    for a in (0, 1):
+        for b in (0, 1):
+            ref[:, :, a::2, b::2] = F.conv2d(xt64[:, :, a:a + h + 3, b:b + w + 3], wpb[a, b])
+    ref = torch.relu(ref + bias.double()[None, :, None, None])
+    assert rel_err(got, ref) < 4e-3                     # bf16 rounding of the stored output only
+    assert _pad_is_zero(y, B, 8, 2 * h, 2 * w)
+    # and it IS the resize-convolution away from the border (where the reference zero-pads the upsampled tensor)
+    true = torch.relu(F.conv2d(F.interpolate(x.double(), scale_factor=2, mode="bilinear", align_corners=False),
+                               w5.double(), bias.double(), padding=2))
+    assert rel_err(got[:, :, 2:-2, 2:-2], true[:, :, 2:-2, 2:-2]) < 1e-2
