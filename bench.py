@@ -108,16 +108,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_batches(n_batches: int, rank: int):
-    from deepsensornz_b200 import concat_tasks
+def make_task_lists(n_batches: int, rank: int, dim_yc=DIM_YC):
+    """``n_batches`` lists of BATCH raw (numpy, un-batched) tasks -- what ``train_epoch`` receives."""
     from deepsensornz_b200.synthetic import make_static, make_task
     static = make_static(seed=7)
-    out = []
-    for k in range(n_batches):
-        tasks = [make_task(static, 20160101 + rank * 10000 + k * BATCH + i, n_stations=N_STATIONS,
-                           context_frac=CTX_FRAC) for i in range(BATCH)]
-        out.append(concat_tasks(tasks))
-    return out
+    return [[make_task(static, 20160101 + rank * 10000 + k * BATCH + i, n_stations=N_STATIONS, context_frac=CTX_FRAC,
+                       c0_channels=dim_yc[0]) for i in range(BATCH)] for k in range(n_batches)]
+
+
+def make_batches(n_batches: int, rank: int):
+    from deepsensornz_b200 import concat_tasks
+    return [concat_tasks(tasks) for tasks in make_task_lists(n_batches, rank)]
 
 
 # ------------------------------------------------------------------------------------------------

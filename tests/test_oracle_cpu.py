@@ -150,3 +150,73 @@ def test_oracle_gradients_finite_difference():
         Pp[key] = P[key] - d
         lm = O.loss_fn(Pp, ctx, xt, yt, aux, 30)
     assert abs(float((lp - lm) / (2 * eps)) - float(g[3])) < 1e-6 * max(1.0, abs(float(g[3])))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE shapes (tests/golden/s*.npz, tests/golden/make_golden_baseline.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _mgb():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_baseline", os.path.join(GOLD, "make_golden_baseline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_reproduces_baseline_shape_golden():
+    """S1 (one task, 304 x 304 internal grid, 1400 x 1400 land-mask context): the oracle still gives the committed
+    numbers -- inputs regenerated from the seeds, through oracle/task_tensors.py."""
+    from oracle.task_tensors import task_tensors
+    from tests.util import cpu_params
+    mg = _mgb()
+    gold = np.load(os.path.join(GOLD, "s1_single.npz"))
+    m = mg.build_model("s1_single")
+    ctx, xt, yt, aux = task_tensors(mg.build_tasks("s1_single"))
+    with torch.no_grad():
+        mean, var, info = O.forward(cpu_params(m), ctx, xt, aux, mg.PPU, return_internal=True)
+        loss = -O.loglik(mean, var, yt, True).mean()
+    assert info["grid"][0][1] == 304 and info["grid"][1][1] == 304
+    assert np.allclose(mean.numpy(), gold["mean"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(info["z"][mg.Z_SAMPLE].numpy(), gold["z_sample"], rtol=1e-4, atol=1e-5)
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
+
+
+@pytest.mark.parametrize("name", ["s1_single", "s2_batch4", "s4_multivar8"])
+def test_sensitive_weights_make_the_unet_matter(name):
+    """The golden weights are scaled so that the loss depends on the convolutions: zeroing after_turn_layers.0 moves
+    the oracle's loss by far more than 1 % (with torch's default init it moves by 1e-3, VERDICT r01 weak #2)."""
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    assert abs(float(gold["loss_after0_zeroed"]) - float(gold["loss"])) > 0.05 * abs(float(gold["loss"]))
+    assert float(gold["z_abs_mean"]) > 0.1
+
+
+def test_task_tensors_restatement_equals_product_batching():
+    """oracle/task_tensors.py (independent restatement of modify_task + concat_tasks, SURVEY A.1 / A.8) and the
+    product's concat_tasks -> modify_task -> convert_task_to_nps_args agree bit for bit, ragged context sets included."""
+    from deepsensornz_b200 import concat_tasks
+    from deepsensornz_b200.synthetic import make_static, make_task
+    from oracle.task_tensors import task_tensors
+    from tests.util import oracle_inputs
+    static = make_static(seed=7, n_hi=200)
+    tasks = [make_task(static, 900 + i, n_stations=200 - 10 * i) for i in range(3)]
+    nt = min(t["X_t"][0].shape[-1] for t in tasks)
+    for t in tasks:
+        t["X_t"][0], t["Y_t"][0], t["Y_t_aux"] = t["X_t"][0][:, :nt], t["Y_t"][0][:, :nt], t["Y_t_aux"][:, :nt]
+
+    def eq(u, v):
+        if u is None or v is None:
+            return u is None and v is None
+        if isinstance(u, tuple):
+            return all(eq(a, b) for a, b in zip(u, v))
+        return u.shape == v.shape and u.dtype == v.dtype and torch.equal(u, v)
+
+    for group in (tasks, tasks[:1]):
+        a = oracle_inputs(concat_tasks(group) if len(group) > 1 else group[0])
+        b = task_tensors(group)
+        assert len(a[0]) == len(b[0])
+        for (x, y, m), (x2, y2, m2) in zip(a[0], b[0]):
+            assert eq(x, x2) and eq(y, y2) and eq(m, m2)
+        assert eq(a[1], b[1]) and eq(a[2], b[2]) and eq(a[3], b[3])
+    # the ragged set really was padded and masked
+    m3 = task_tensors(tasks)[0][3][2]
+    assert m3 is not None and float(m3[0].sum()) == 160 and float(m3[2].sum()) == 144
