@@ -28,6 +28,7 @@ from . import _cabi
 from ._cabi import CnpBlk, CnpConvOut, CnpMlpParams
 from .discretisation import GridSpec, discretise
 from .model import ConvNPConfig, ConvNPModule
+from .task import is_batch_broadcast
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -133,6 +134,9 @@ class Engine:
         self.world_size = 1
         self.launches = 0
         self._prof = None
+        self.force_pack = False       # graph capture: re-pack every bf16 weight inside the captured region
+        self.packs_recorded = 0
+        self.generation = 0           # forward counter: a backward whose activations were overwritten must not run
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -286,9 +290,16 @@ class Engine:
                 # static fields (topography aux, land mask) are identical in every task of a batch: keep one slice
                 yh = host(y)
                 mh = None if m is None else host(m)
-                y_shared = shared and yh.shape[0] > 1 and all(
-                    np.array_equal(yh[0], yh[i], equal_nan=True) for i in range(1, yh.shape[0])) and (
-                    mh is None or all(np.array_equal(mh[0], mh[i]) for i in range(1, mh.shape[0])))
+                if is_batch_broadcast(yh) and (mh is None or is_batch_broadcast(mh)):
+                    y_shared = shared            # concat_tasks stacked ONE buffer (zero-stride view): nothing to compare
+                else:
+                    # separate copies of the same field: a strided sample rules out per-date fields before the full compare
+                    def same(a):
+                        flat = a.reshape(a.shape[0], -1)
+                        smp = flat[:, ::max(1, flat.shape[1] // 4096)]
+                        return all(np.array_equal(smp[0], smp[i], equal_nan=True) for i in range(1, a.shape[0])) and \
+                            all(np.array_equal(a[0], a[i], equal_nan=True) for i in range(1, a.shape[0]))
+                    y_shared = shared and yh.shape[0] > 1 and same(yh) and (mh is None or same(mh))
                 if y_shared:
                     y, m = yh[:1], (None if mh is None else mh[:1])
                 hc = DeviceContext(True, (cpu(x1h), cpu(x2h)), cpu(y), cpu(m), mono, not shared, (x1h, x2h),
@@ -571,10 +582,15 @@ class Engine:
     def _prepack_all(self):
         """Re-pack every weight whose version changed (optimiser step) on a side stream at the start of the step, so
         the ~25 small packing launches overlap the encoder instead of sitting between the convolutions."""
+        if self.force_pack:
+            self.packs_recorded = 0
+            self._forced = set()
         if os.environ.get("CNP_NO_PREPACK"):
             return
         stale = [(k, r) for k, r in self._pack_reqs.items()
-                 if self._packed.get(k) is not None and self._packed[k][0] != self._pack_version(r)]
+                 if self._packed.get(k) is not None and (self.force_pack or self._packed[k][0] != self._pack_version(r))]
+        if self.force_pack:
+            self._forced = set(k for k, _ in stale)
         if not stale:
             return
         if self._pack_stream is None:
@@ -606,6 +622,7 @@ class Engine:
             Cin = Cp
         self._call("cnp_conv_tc2_pack", _ptr(src), Cout, Cin, k, kind, n_chunks, py, px, co_off, n_out, _ptr(buf),
                    _stream())
+        self.packs_recorded += 1
         self._packed[key] = (ver, buf)
 
     def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0,
@@ -617,8 +634,11 @@ class Engine:
             torch.cuda.current_stream().wait_event(self._pack_event)
             self._pack_event = None
         ent = self._packed.get(key)
-        if ent is not None and ent[0] == self._pack_version(req) and ent[1].device == w.device:
+        fresh = not self.force_pack or key in getattr(self, "_forced", ())      # forced: already re-packed this step
+        if ent is not None and ent[0] == self._pack_version(req) and ent[1].device == w.device and fresh:
             return ent[1]
+        if self.force_pack:
+            self._forced.add(key)
         nbytes = _cabi.lib().cnp_conv_tc2_packed_bytes(kind, n_chunks, n_out)
         buf = ent[1] if ent is not None else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
         self._do_pack(key, req, buf)
@@ -878,6 +898,7 @@ class Engine:
         """Returns dict(mean [B,Nt], var [B,Nt], logp [B] f64, count [B] i32, ctx)."""
         self._require_cuda()
         cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
+        self.generation += 1
         if self.precision == "bf16":
             self._prepack_all()
         if batch.ready is not None:   # uploaded on a copy stream: order after the copy, keep the allocator informed
@@ -925,7 +946,7 @@ class Engine:
         self._call("cnp_mlp_head_fwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(batch.aux_t), Ca,
                    _ptr(batch.yt) if with_loss else None, B, Nt, _ptr(mean), _ptr(var), _ptr(logp), _ptr(count),
                    _stream())
-        return dict(mean=mean, var=var, logp=logp, count=count, ctx=dict(enc=enc, z=z, A=A, f=f))
+        return dict(mean=mean, var=var, logp=logp, count=count, ctx=dict(enc=enc, z=z, A=A, f=f, generation=self.generation))
 
     def _decode_grid(self, batch: DeviceBatch, z: torch.Tensor, s2: float):
         """On-grid targets (predict): separable truncated SetConv + per-point MLP head -> mean/std [B,P,Q]."""
@@ -989,6 +1010,11 @@ class Engine:
     def backward(self, batch: DeviceBatch, ctx: dict, dlogp: torch.Tensor) -> Dict[str, torch.Tensor]:
         """dlogp [B] fp32 = d loss / d logp_b.  Returns {param name: grad} (views of one flat buffer)."""
         cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
+        if ctx.get("generation") != self.generation:
+            # the activations a backward needs live in engine-wide workspaces keyed by shape: a later forward
+            # (a second loss_fn before .backward(), a validation pass with grad enabled) has overwritten them
+            raise _cabi.CnpError("backward() of a loss whose forward is no longer the engine's latest one: call "
+                                 ".backward() before the next loss_fn / model(task) (one loss in flight per model)")
         named = [(n, p) for n, p in self.module.named_parameters() if n.startswith("decoder.") and p.dim() > 0]
         total = sum(p.numel() for _, p in named)
         flat = torch.zeros(total, dtype=torch.float32, device=self.device)

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 from typing import Optional
 
+import numpy as np
 import torch
 
 from .engine import DeviceBatch, DeviceContext, HostBatch
@@ -26,8 +27,13 @@ def batch_signature(b) -> tuple:
     ctx = []
     for c in b.contexts:
         xs = c.x if isinstance(c.x, tuple) else (c.x,)
+        # the banded encoder's band width and workspace size are derived on the host from the gridded coordinates and
+        # baked into the captured launch: the coordinates themselves are part of the signature
+        coords = None
+        if c.gridded and c.x_host is not None:
+            coords = tuple(hash(np.ascontiguousarray(v).tobytes()) for v in c.x_host)
         ctx.append((c.gridded, tuple(tuple(v.shape) for v in xs), tuple(c.y.shape), None if c.mask is None else
-                    tuple(c.mask.shape), c.mono, c.x_batched, c.y_batched))
+                    tuple(c.mask.shape), c.mono, c.x_batched, c.y_batched, coords))
     xt = b.xt if isinstance(b.xt, tuple) else (b.xt,)
     g = b.grid
     return (tuple(ctx), tuple(tuple(v.shape) for v in xt), None if b.yt is None else tuple(b.yt.shape),
@@ -74,10 +80,27 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.loss = self._fwd_bwd()
-            if self.capture_optimizer:
-                self.opt.step()
+        # the bf16 weight packing must be IN the graph: an eager forward just before the capture (validation loss_fn)
+        # leaves the packed copies current, and a capture that then records no pack kernels would replay with the
+        # weights frozen at capture time while the fp32 masters keep moving
+        eng.force_pack = True
+        l0 = eng.launches
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+                if self.capture_optimizer:
+                    self.opt.step()
+        finally:
+            eng.force_pack = False
+        self.launches = eng.launches - l0
+        if eng.precision == "bf16" and not eng.packs_recorded:
+            raise RuntimeError("graph capture recorded no weight-packing kernels")
+        # the captured backward writes into THESE gradient tensors (they live in the graph's private pool); an eager
+        # step on another batch signature rebinds p.grad to fresh tensors, so step() binds them back before an eager
+        # optimiser step reads them
+        self._params = [p for p in model.model.parameters() if p.grad is not None]
+        self._grads = [p.grad for p in self._params]
+        self._loaded = {}
 
     def _fwd_bwd(self):
         loss = self.model.loss_fn(self.static, normalise=True)
@@ -95,9 +118,19 @@ class GraphedTrainStep:
 
     def load(self, batch) -> None:
         """Copy a batch (DeviceBatch, or HostBatch in pinned memory) into the static input buffers."""
-        for dst, src in zip(_tensors(self.static), _tensors(batch)):
-            if dst is not None:
-                dst.copy_(src, non_blocking=True)
+        static_ids = set()
+        for c in batch.contexts:
+            if not c.y_batched:       # device-resident static field (staging.BatchStager): copied only when it changes
+                static_ids.update(id(t) for t in (c.x if isinstance(c.x, tuple) else (c.x,)) + (c.y, c.mask)
+                                  if t is not None)
+        for i, (dst, src) in enumerate(zip(_tensors(self.static), _tensors(batch))):
+            if dst is None:
+                continue
+            if id(src) in static_ids and src.device.type == "cuda":
+                if self._loaded.get(i) is src:
+                    continue
+                self._loaded[i] = src
+            dst.copy_(src, non_blocking=True)
 
     def step(self, batch=None) -> torch.Tensor:
         if batch is not None:
@@ -107,5 +140,7 @@ class GraphedTrainStep:
             self.load(batch)
         self.graph.replay()
         if not self.capture_optimizer:
+            for p, g in zip(self._params, self._grads):
+                p.grad = g
             self.opt.step()
         return self.loss

@@ -79,9 +79,10 @@ def _pad_offgrid(hb, multiple: int = 16):
             continue
         B, _, N = c.x.shape
         Np = max(multiple, -(-N // multiple) * multiple)
-        x = torch.zeros(B, 2, Np, dtype=torch.float32)
-        y = torch.zeros(B, c.y.shape[1], Np, dtype=torch.float32)
-        m = torch.zeros(B, 1, Np, dtype=torch.float32)
+        # device="cpu" everywhere on the host side: the reference calls set_gpu_default_device() first (train.py:48)
+        x = torch.zeros(B, 2, Np, dtype=torch.float32, device="cpu")
+        y = torch.zeros(B, c.y.shape[1], Np, dtype=torch.float32, device="cpu")
+        m = torch.zeros(B, 1, Np, dtype=torch.float32, device="cpu")
         x[:, :, :N], y[:, :, :N] = c.x, torch.nan_to_num(c.y, nan=0.0)
         valid = (~torch.isnan(c.y).any(dim=1, keepdim=True)).to(torch.float32)
         m[:, :, :N] = valid if c.mask is None else c.mask.reshape(B, 1, N) * valid
@@ -130,7 +131,7 @@ class _GraphedForward:
                 continue
             m = mir.get(i)
             if m is None:
-                m = mir[i] = torch.empty(dst.shape, dtype=dst.dtype, pin_memory=True)
+                m = mir[i] = torch.empty(dst.shape, dtype=dst.dtype, device="cpu", pin_memory=True)
             # plain memcpy: torch's CPU copy_ goes parallel above 32 K elements and its OpenMP team then fights the
             # drain threads for cores (measured 2.5 ms for a 235 KB field)
             np.copyto(m.numpy(), src.numpy())
@@ -309,8 +310,8 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
             std_out = np.empty_like(mean_out)
             if cuda:
                 if direct is None:
-                    pin = [(torch.empty(mean.shape, dtype=torch.float32).pin_memory(),
-                            torch.empty(mean.shape, dtype=torch.float32).pin_memory()) for _ in range(3)]
+                    pin = [(torch.empty(mean.shape, dtype=torch.float32, device="cpu", pin_memory=True),
+                            torch.empty(mean.shape, dtype=torch.float32, device="cpu", pin_memory=True)) for _ in range(3)]
         if cuda:
             slot = idx % 3
             if futures[slot] is not None:  # the buffer we are about to reuse must have been drained

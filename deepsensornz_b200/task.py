@@ -88,6 +88,11 @@ class Task(dict):
         def f(a):
             if isinstance(a, np.ma.MaskedArray):
                 return a
+            if is_batch_broadcast(a):                 # one shared slice: scan it once
+                one = a[:1]
+                if np.issubdtype(a.dtype, np.floating) and np.isnan(one).any():
+                    return np.ma.MaskedArray(a, mask=np.broadcast_to(np.isnan(one), a.shape), fill_value=np.nan)
+                return a
             if np.issubdtype(a.dtype, np.floating) and np.isnan(a).any():
                 return np.ma.MaskedArray(a, mask=np.isnan(a), fill_value=np.nan)
             return a
@@ -101,6 +106,11 @@ class Task(dict):
 
         def f(a):
             if isinstance(a, np.ma.MaskedArray):
+                if is_batch_broadcast(a.data):        # one shared slice: mask it once, hand out zero-stride views
+                    one = f(np.ma.MaskedArray(a.data[:1], mask=np.ma.getmaskarray(a)[:1]))
+                    B = a.shape[0]
+                    return Masked(np.broadcast_to(one.y, (B,) + one.y.shape[1:]),
+                                  np.broadcast_to(one.mask, (B,) + one.mask.shape[1:]))
                 m = np.ma.getmaskarray(a)
                 mask = (~np.any(m, axis=1, keepdims=True)).astype(a.dtype)
                 y = np.array(a.data, copy=True)
@@ -129,6 +139,38 @@ def _pad_last(a: np.ndarray, n: int, value: float) -> np.ndarray:
     return np.concatenate([a, pad], axis=-1)
 
 
+def same_buffer(arrays) -> bool:
+    """True when every array is the SAME memory (pointer, shape, strides, dtype): a static field -- topography aux,
+    land mask -- that the TaskLoader hands to every date without copying (variables without a time axis)."""
+    a0 = arrays[0]
+    if not isinstance(a0, np.ndarray) or isinstance(a0, np.ma.MaskedArray):
+        return False
+    k0 = (a0.__array_interface__["data"][0], a0.shape, a0.strides, a0.dtype)
+    for a in arrays[1:]:
+        if a is a0:
+            continue
+        if not isinstance(a, np.ndarray) or isinstance(a, np.ma.MaskedArray):
+            return False
+        if (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype) != k0:
+            return False
+    return True
+
+
+def is_batch_broadcast(a) -> bool:
+    """A stacked array whose batch axis has stride 0: ``concat_tasks`` made it from one shared buffer."""
+    return isinstance(a, np.ndarray) and a.ndim >= 1 and a.shape[0] > 1 and a.strides[0] == 0
+
+
+def _stack(arrays):
+    """Concatenate along the batch axis; arrays that are all the same buffer become a zero-stride view of it (same
+    shape and values as the copy, none of its 16 x 7.8 MB of traffic for a 1400 x 1400 land mask)."""
+    if len(arrays) > 1 and same_buffer(arrays):
+        a = arrays[0]
+        return np.broadcast_to(a[:1], (len(arrays) * a.shape[0],) + a.shape[1:]) if a.shape[0] == 1 else \
+            np.concatenate(arrays, axis=0)
+    return np.concatenate(arrays, axis=0)
+
+
 def merge_contexts(contexts: List[Tuple], multiple: int = 1):
     """Merge one context set across tasks (mirror of ``neuralprocesses.mask.merge_contexts``).
 
@@ -137,8 +179,8 @@ def merge_contexts(contexts: List[Tuple], multiple: int = 1):
     """
     xs, ys = [c[0] for c in contexts], [c[1] for c in contexts]
     if isinstance(xs[0], tuple):
-        x = tuple(np.concatenate([xi[d] for xi in xs], axis=0) for d in range(len(xs[0])))
-        return x, np.concatenate(ys, axis=0)
+        x = tuple(_stack([xi[d] for xi in xs]) for d in range(len(xs[0])))
+        return x, _stack(ys)
     n = max(xi.shape[-1] for xi in xs)
     n = ((n + multiple - 1) // multiple) * multiple
     x = np.concatenate([_pad_last(xi, n, 0.0) for xi in xs], axis=0)

@@ -36,9 +36,7 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
     def launch_step(task) -> torch.Tensor:
         """Queue forward + backward + optimiser step; returns the (device) loss without synchronising."""
         opt.zero_grad()
-        items = task if isinstance(task, list) else [task]
-        losses = [model.loss_fn(t, normalise=True) for t in items]
-        mean_loss = torch.stack(losses).mean()
+        mean_loss = model.loss_fn(task, normalise=True)
         mean_loss.backward()
         opt.step()
         return mean_loss.detach()
@@ -47,18 +45,31 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
     tasks = [tasks[i] for i in order]
     n_batches = len(tasks) // batch_size if batch_size is not None else len(tasks)
 
-    # Batch i+1 is concatenated, staged in pinned memory and copied on a side stream while the GPU runs step i
-    # (the reference re-uploads every task synchronously inside loss_fn).
+    # Batch i+1 is built (straight into persistent page-locked buffers, static context sets resident on the device:
+    # staging.BatchStager) and copied on a side stream by a worker thread while the GPU runs step i; the reference
+    # re-concatenates and re-uploads every task synchronously inside loss_fn.
     can_stage = hasattr(model, "stage_task") and torch.cuda.is_available()
-    copy_stream = torch.cuda.Stream() if can_stage else None
+    copy_stream = None
+    stager = None
+    if can_stage:
+        from .staging import BatchStager
+        copy_stream = model.__dict__.get("_copy_stream")
+        if copy_stream is None:
+            copy_stream = model.__dict__["_copy_stream"] = torch.cuda.Stream()
+        stager = model.__dict__.get("_stager")
+        if stager is None:
+            stager = model.__dict__["_stager"] = BatchStager(model.engine)
+        dev_index = model.engine.device.index
 
     def make(bi):
-        if batch_size is not None:
-            task = concat_tasks(tasks[bi * batch_size:(bi + 1) * batch_size])
-        else:
-            task = tasks[bi]
+        group = tasks[bi * batch_size:(bi + 1) * batch_size] if batch_size is not None else [tasks[bi]]
         if not can_stage:
-            return task
+            return concat_tasks(group) if len(group) > 1 else group[0]
+        if dev_index is not None:
+            torch.cuda.set_device(dev_index)          # worker thread: the current device is per thread
+        if stager.fast_path_ok(group):
+            return stager.upload(stager.build(group), stream=copy_stream)
+        task = concat_tasks(group) if len(group) > 1 else group[0]
         return model.engine.upload(model.stage_task(task, pinned=True), stream=copy_stream)
 
     it = range(n_batches)
@@ -68,46 +79,59 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
             it = tqdm(it)
         except Exception:
             pass
-    use_graph = bool(use_graph) and can_stage and getattr(model.engine, "world_size", 1) == 1
+    dp = getattr(model.engine, "world_size", 1) > 1
+    use_graph = bool(use_graph) and can_stage and not dp      # the data-parallel step launches eagerly around NCCL
     graphs = model.__dict__.setdefault("_train_graphs", {}) if use_graph else None
     losses = []
     # The loss of batch i is copied to page-locked memory asynchronously and READ while batch i+1 is already queued:
     # every batch's loss still reaches the host (as upstream's train_epoch returns it), but the GPU never waits for the
     # host to come back from a synchronising read between two steps.
     on_gpu = torch.cuda.is_available() and can_stage
-    slots = [torch.empty((), dtype=torch.float64).pin_memory() for _ in range(2)] if on_gpu else None
+    slots = [torch.empty((), dtype=torch.float64, device="cpu", pin_memory=True) for _ in range(2)] if on_gpu else None
     events = [None, None]
 
     def read_back(j):
         events[j % 2].synchronize()
         losses.append(float(slots[j % 2]))
 
-    nxt = make(0) if n_batches > 0 else None
-    for bi in it:
-        cur = nxt
-        if use_graph and not isinstance(cur, list):
-            from .graph import GraphedTrainStep, batch_signature
-            key = (id(opt), batch_signature(cur))
-            gs = graphs.get(key)
-            if gs is None:            # first batch of this shape: eager (it is also the warm-up of the capture)
-                loss_t = launch_step(cur)
-                graphs[key] = False
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=1) if can_stage and n_batches > 1 else None
+    try:
+        nxt = make(0) if n_batches > 0 else None
+        for bi in it:
+            cur = nxt
+            fut = pool.submit(make, bi + 1) if (pool is not None and bi + 1 < n_batches) else None
+            if use_graph and not isinstance(cur, list):
+                from .graph import GraphedTrainStep, batch_signature
+                key = (id(opt), batch_signature(cur))
+                gs = graphs.get(key)
+                if gs is None:            # first batch of this shape: eager (it is also the warm-up of the capture)
+                    loss_t = launch_step(cur)
+                    graphs[key] = False
+                else:
+                    if gs is False:
+                        gs = graphs[key] = GraphedTrainStep(model, opt, cur, warm=True)
+                    loss_t = gs.step(cur)
             else:
-                if gs is False:
-                    gs = graphs[key] = GraphedTrainStep(model, opt, cur, warm=True)
-                loss_t = gs.step(cur)
-        else:
-            loss_t = launch_step(cur)
-        if on_gpu and loss_t.is_cuda:
-            slots[bi % 2].copy_(loss_t.to(torch.float64), non_blocking=True)
-            events[bi % 2] = torch.cuda.Event()
-            events[bi % 2].record()
-        nxt = make(bi + 1) if bi + 1 < n_batches else None
-        if on_gpu and loss_t.is_cuda:
-            if bi > 0:
-                read_back(bi - 1)
-        else:
-            losses.append(float(loss_t.cpu().numpy()))
-    if on_gpu and n_batches > 0 and len(losses) < n_batches:
-        read_back(n_batches - 1)
+                loss_t = launch_step(cur)
+            if on_gpu and loss_t.is_cuda:
+                slots[bi % 2].copy_(loss_t.to(torch.float64), non_blocking=True)
+                events[bi % 2] = torch.cuda.Event()
+                events[bi % 2].record()
+            if fut is not None:
+                nxt = fut.result()
+            elif bi + 1 < n_batches:
+                nxt = make(bi + 1)
+            else:
+                nxt = None
+            if on_gpu and loss_t.is_cuda:
+                if bi > 0:
+                    read_back(bi - 1)
+            else:
+                losses.append(float(loss_t.cpu().numpy()))
+        if on_gpu and n_batches > 0 and len(losses) < n_batches:
+            read_back(n_batches - 1)
+    finally:
+        if pool is not None:
+            pool.shutdown(wait=True)
     return losses

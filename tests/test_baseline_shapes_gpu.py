@@ -218,8 +218,9 @@ def test_bench_launch_wide_dgrad_masked_accumulating_at_304():
     _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S1_DGRAD, 8, n_out=128).data_ptr(),
                _cabi.KIND_K5S1_DGRAD, 0, 0, 128, C.byref(o), B16, _S())
     got = _from_blk(dxb, 128)
-    assert rel_err(got, ref) < 4e-3 and _pad_is_zero(dxb, B16, 16, G, G)
-    assert rel_err(got[15, 64:, 300:], ref[15, 64:, 300:]) < 4e-3
+    # the accumulating epilogue rounds twice (gradient to bf16, then the bf16 sum): 2^-8 of the largest value
+    assert rel_err(got, ref) < 8e-3 and _pad_is_zero(dxb, B16, 16, G, G)
+    assert rel_err(got[15, 64:, 300:], ref[15, 64:, 300:]) < 8e-3
 
 
 @pytest.mark.parametrize("py", [0, 1])
@@ -234,7 +235,7 @@ def test_bench_launch_stride2_dgrad_x_phase_pair_at_304(py):
     o = _out(dxb.view(0), scatter=(2, py, 2, 0), accumulate=1, mask=actb.view(0))
     _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S2_DGRAD, 8, py, 2).data_ptr(),
                _cabi.KIND_K5S2_DGRAD, py, 2, 64, C.byref(o), B16, _S())
-    assert rel_err(_from_blk(dxb, 64), ref) < 4e-3 and _pad_is_zero(dxb, B16, 8, G, G)
+    assert rel_err(_from_blk(dxb, 64), ref) < 8e-3 and _pad_is_zero(dxb, B16, 8, G, G)
 
 
 @pytest.mark.parametrize("cin", [64, 128])
