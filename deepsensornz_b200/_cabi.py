@@ -56,6 +56,17 @@ class CnpConvOut(C.Structure):
     ]
 
 
+class CnpEncSet(C.Structure):
+    _fields_ = [("kind", C.c_int), ("C", C.c_int), ("ch_off", C.c_int), ("batched", C.c_int),
+                ("x1", C.c_void_p), ("x2", C.c_void_p), ("y", C.c_void_p), ("mask", C.c_void_p),
+                ("N1", C.c_int), ("N2", C.c_int), ("mono1", C.c_int), ("mono2", C.c_int),
+                ("scale2", C.c_float), ("pad_", C.c_int)]
+
+
+class CnpEncSets(C.Structure):
+    _fields_ = [("n_sets", C.c_int), ("pad_", C.c_int), ("s", CnpEncSet * 8)]
+
+
 # conv_tc kinds (must match conv_bf16.cu)
 KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD, KIND_UP_PHASE = range(7)
 # conv_tc_wgrad kinds (must match wgrad_bf16.cu)
@@ -73,6 +84,9 @@ _SIGS = {
     "cnp_setconv_enc_grid_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "cnp_setconv_enc_grid_fwd": (C.c_int, [c_fp, c_fp, _i, c_fp, c_fp, _i, _i, _i, _i, _i, _i] + _GRID +
                                  [_f, _f, c_fp, _i, _i, _i, c_fp, _ll, c_stream]),
+    "cnp_encode_fused_smem_bytes": (_ll, [_i, _i, _i]),
+    "cnp_encode_fused": (C.c_int, [C.POINTER(CnpEncSets), _i] + _GRID + [_f, _i, c_fp, _ll, _i, C.POINTER(CnpBlk), _i, _i,
+                                   c_stream]),
     # (3) SetConv decoder
     "cnp_setconv_dec_offgrid_fwd": (C.c_int, [c_fp, _ll, c_fp, _i, _i, _i] + _GRID + [_f, c_fp, _i, c_stream]),
     "cnp_setconv_dec_offgrid_bwd": (C.c_int, [c_fp, _i, c_fp, _i, _i, _i] + _GRID + [_f, c_fp, _ll, c_stream]),

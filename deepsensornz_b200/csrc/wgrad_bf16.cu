@@ -48,6 +48,7 @@ struct cnp_wg_args {
   const __nv_bfloat16* dy; long long dy_bs; long long dy_plane;
   float* dw; float* dbias; int Cin, KK;
   float* ws;                     // optional partial-sum workspace [pass][ksplit][acc][128][64]; NULL = atomics into dw
+  float* ws_bias;                // with ws: per-CTA bias partials [pass][ksplit][64]
   int B, P, p_start, tiles_per_img, ksplit, n_pass;
   int dup;                       // 1: N = 128 operand [dY(p) ; dY(p-1)] (column half 1 = tap a+1)
   int ws_acc;                    // accumulators per CTA in the workspace layout
@@ -274,8 +275,13 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 2 && has_work) {
-        for (int i = lane; i < 64; i += 32)
-          atomicAdd(a.dbias + i, bred[i] + bred[64 + i] + bred[128 + i] + bred[192 + i]);
+        // with a workspace every CTA stores its partial and wgrad_reduce_kernel adds them in a fixed order
+        // (run-to-run identical gradients); without one, one atomic per channel per CTA
+        float* bws = a.ws ? a.ws_bias + ((size_t)blockIdx.y * a.ksplit + blockIdx.x) * 64 : nullptr;
+        for (int i = lane; i < 64; i += 32) {
+          const float v = bred[i] + bred[64 + i] + bred[128 + i] + bred[192 + i];
+          if (bws) bws[i] = v; else atomicAdd(a.dbias + i, v);
+        }
       }
     }
     if (has_work) {
@@ -313,16 +319,22 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
-// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel.
-// Thread = 4 consecutive columns (one 16 B load per partial) x one slice of WG_RED_KS partials (blockIdx.y), all loads
-// of the slice in flight together; slices meet in dw with one atomic per value (the workspace is ~30 MB per launch:
-// the first version, one thread per element looping over all partials, ran at a quarter of the HBM rate).
+// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel, in a FIXED order
+// (k = 0, 1, ...: gradients are run-to-run identical, so a CUDA-graph replay equals the eager step bit for bit).
+// Thread = 4 consecutive columns (one 16 B load per partial), WG_RED_KS loads in flight at a time; every (co, ci, tap)
+// is owned by exactly one thread (wg_slot is one-to-one on the valid slots).  The first 64 threads of block 0 also fold
+// the per-CTA bias partials.
 constexpr int WG_RED_KS = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
   const int ncols = a.dup ? 128 : 64;
   const int total4 = a.n_pass * a.ws_acc * 128 * (ncols / 4);
-  const int k0 = blockIdx.y * WG_RED_KS, k1 = min(k0 + WG_RED_KS, a.ksplit);
+  if (a.dbias != nullptr && blockIdx.x == 0 && threadIdx.x < 64) {
+    float s = 0.f;
+    const int n = a.n_pass * a.ksplit;
+    for (int k = 0; k < n; ++k) s += a.ws_bias[(size_t)k * 64 + threadIdx.x];
+    a.dbias[threadIdx.x] += s;
+  }
   for (int e = blockIdx.x * 256 + threadIdx.x; e < total4; e += gridDim.x * 256) {
     const int col = (e % (ncols / 4)) * 4, m = (e / (ncols / 4)) & 127, jj = e / ((ncols / 4) * 128);
     const int j = jj % a.ws_acc, pass = jj / a.ws_acc;
@@ -333,17 +345,20 @@ wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
     if (slot < 0 || ci >= a.Cin) continue;
     const float* src = a.ws + (((size_t)pass * a.ksplit * a.ws_acc + j) * 128 + m) * 128 + col;
     const size_t stride = (size_t)a.ws_acc * 128 * 128;
-    float4 v[WG_RED_KS];
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < a.ksplit; k0 += WG_RED_KS) {
+      float4 v[WG_RED_KS];
 #pragma unroll
-    for (int k = 0; k < WG_RED_KS; ++k)
-      v[k] = (k0 + k < k1) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(k0 + k) * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 sum = v[0];
+      for (int k = 0; k < WG_RED_KS; ++k)
+        v[k] = (k0 + k < a.ksplit) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(k0 + k) * stride))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 1; k < WG_RED_KS; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+      for (int k = 0; k < WG_RED_KS; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+    }
     const int co = col & 63;
     float* dst = a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot;
     const size_t cs = (size_t)a.Cin * a.KK;
-    atomicAdd(dst, sum.x); atomicAdd(dst + cs, sum.y); atomicAdd(dst + 2 * cs, sum.z); atomicAdd(dst + 3 * cs, sum.w);
+    dst[0] += sum.x; dst[cs] += sum.y; dst[2 * cs] += sum.z; dst[3 * cs] += sum.w;
   }
 }
 
@@ -390,7 +405,8 @@ enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2, WG_K5S1_NARROW = 3 };
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
 // Bytes of the optional partial-sum workspace (max over kinds: 5 passes x <=148 CTAs x 5 accumulators x 32 KB).
 CNP_API long long cnp_conv_tc_wgrad_workspace_bytes(void) {
-  return (long long)148 * 5 * 128 * 128 * sizeof(float);   // <= 148 CTAs x <= 5 accumulators x [128][128] floats
+  // <= 148 CTAs x <= 5 accumulators x [128][128] floats, + the per-CTA bias partials [148][64]
+  return (long long)148 * 5 * 128 * 128 * sizeof(float) + (long long)148 * 64 * sizeof(float);
 }
 
 CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dbias,
@@ -547,10 +563,13 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   // partial sums through the workspace + reduce kernel; only very short K loops keep the atomics
   // (with the 16 B / 8-partial reduce kernel the workspace wins down to small layers: 152^2 142.6 -> 130.6 us,
   // 38^2 41.8 -> 34.3 us against the atomics epilogue)
-  static const int ws_min_tiles = getenv("CNP_WGRAD_WS_MIN_TILES") ? atoi(getenv("CNP_WGRAD_WS_MIN_TILES")) : 128;
-  if (workspace && total_tiles >= ws_min_tiles &&
-      workspace_bytes >= (long long)np * a.ksplit * a.ws_acc * 128 * 128 * (long long)sizeof(float))
+  // (a caller that hands over a workspace gets the ordered reduction for every size: deterministic gradients)
+  static const int ws_min_tiles = getenv("CNP_WGRAD_WS_MIN_TILES") ? atoi(getenv("CNP_WGRAD_WS_MIN_TILES")) : 1;
+  const long long ws_part = (long long)np * a.ksplit * a.ws_acc * 128 * 128 * (long long)sizeof(float);
+  if (workspace && total_tiles >= ws_min_tiles && workspace_bytes >= ws_part + (long long)np * a.ksplit * 64 * (long long)sizeof(float)) {
     a.ws = reinterpret_cast<float*>(workspace);
+    a.ws_bias = a.ws + ws_part / sizeof(float);
+  }
   cfg.gridDim = dim3(a.ksplit, np);
   if (a.cluster > 1) {
     cudaError_t le = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, a);
@@ -561,7 +580,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   CNP_LAUNCH_CHECK("wgrad_tc_kernel");
   if (a.ws) {
     const int total4 = np * a.ws_acc * 128 * ((a.dup ? 128 : 64) / 4);
-    wgrad_reduce_kernel<<<dim3(cnp_cdiv(total4, 256), cnp_cdiv(a.ksplit, WG_RED_KS)), 256, 0, st>>>(a);
+    wgrad_reduce_kernel<<<dim3(cnp_cdiv(total4, 256)), 256, 0, st>>>(a);
     CNP_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   return 0;

@@ -137,6 +137,10 @@ class Engine:
         self.force_pack = False       # graph capture: re-pack every bf16 weight inside the captured region
         self.packs_recorded = 0
         self.generation = 0           # forward counter: a backward whose activations were overwritten must not run
+        # bf16 copies of the weights are re-packed when a master's _version changed -- and, because fused optimisers
+        # and CUDA-graph replays update the masters WITHOUT bumping _version (measured: torch.optim.AdamW(fused=True,
+        # capturable=True) leaves it untouched), whenever a backward has run since the last packing
+        self.weights_dirty = False
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -378,6 +382,9 @@ class Engine:
         # self._enc_shared_mask; the consumer (the blocked conversion of the folded first layer) broadcasts on the fly
         self._enc_shared_mask = 0
         self._enc_broadcast = broadcast
+        plan = self._fused_plan(batch)
+        if plan is not None and self._encode_fused(batch, plan, enc=enc):
+            return enc
         multi = len(batch.contexts) > 1 and self._prof is None and not os.environ.get("CNP_NO_MULTISTREAM")
         main = torch.cuda.current_stream()
         if multi:
@@ -402,6 +409,128 @@ class Engine:
             for ss in self._side_streams[:min(4, len(batch.contexts))]:
                 main.wait_stream(ss)
         return enc
+
+    # ---- fused encoder (enc_fused.cu): all context sets of a task in one launch ----
+    def _fused_cols_hint(self, c: DeviceContext, g: GridSpec, scale2: float) -> int:
+        """Upper bound of the number of input columns inside the band of any 32 consecutive internal-grid columns
+        (shared-memory staging width of the fused encoder), from the host copy of the coordinates."""
+        key = (g, scale2, "cols")
+        if key in c.band_cache:
+            return c.band_cache[key]
+        R = float(np.sqrt(np.float32(2.0 * 104.0) * np.float32(scale2))) * (1.0 + 1e-5)
+        xs = np.sort(c.x_host[1][0].astype(np.float64))
+        gp = g.points(1).astype(np.float64)
+        lo, hi = gp[0::32], gp[np.minimum(np.arange(0, g.n2, 32) + 31, g.n2 - 1)]
+        cnt = np.searchsorted(xs, hi + R, side="right") - np.searchsorted(xs, lo - R, side="left")
+        c.band_cache[key] = int(cnt.max()) + 2
+        return c.band_cache[key]
+
+    def _fused_plan(self, batch: DeviceBatch):
+        """Which context sets the fused encoder takes directly, which are encoded once per batch first (sets every task
+        shares), and the staging width; None when a set needs the generic kernels (unsorted or per-task coordinates,
+        bands wider than 32 inputs, more than 8 channels)."""
+        if os.environ.get("CNP_NO_ENC_FUSED") or len(batch.contexts) > 8:
+            return None
+        cfg, g, B = self.cfg, batch.grid, batch.B
+        per_task, static = [], []
+        cols = {"task": 1, "static": 1}
+        cmax = {"task": 1, "static": 1}
+        ch = 0
+        for k, c in enumerate(batch.contexts):
+            Ck = cfg.dim_yc[k]
+            if c.y.shape[1] != Ck:
+                raise ValueError(f"context set {k}: expected {Ck} channels, got {c.y.shape[1]}")
+            if Ck > 8:
+                return None
+            s2 = self._scale2(self.module.encoder.set_convs[k].log_scale)
+            if c.gridded:
+                if c.x_batched or c.mono[0] == 0 or c.mono[1] == 0 or c.x_host is None or not self._band_hint(c, g, s2):
+                    return None
+                where = "static" if (not c.y_batched and B > 1) else "task"
+                cols[where] = max(cols[where], self._fused_cols_hint(c, g, s2))
+                cmax[where] = max(cmax[where], Ck + 1)
+                (static if where == "static" else per_task).append((k, c, ch, s2))
+            else:
+                per_task.append((k, c, ch, s2))
+            ch += Ck + 1
+        return dict(per_task=per_task, static=static, cols=cols, cmax=cmax)
+
+    def _enc_sets(self, entries, rebase: bool):
+        K = _cabi
+        sets = K.CnpEncSets()
+        keep = []
+        off = 0
+        for n, (k, c, ch, s2) in enumerate(entries):
+            e = sets.s[n]
+            Ck = self.cfg.dim_yc[k]
+            e.kind, e.C, e.ch_off, e.scale2 = (1 if c.gridded else 0), Ck, (off if rebase else ch), s2
+            if c.gridded:
+                e.batched = int(c.y_batched and c.y.shape[0] > 1)
+                e.x1, e.x2 = c.x[0].data_ptr(), c.x[1].data_ptr()
+                e.N1, e.N2 = int(c.x[0].shape[-1]), int(c.x[1].shape[-1])
+                e.mono1, e.mono2 = c.mono
+            else:
+                e.batched = 1
+                e.x1, e.N1 = c.x.data_ptr(), int(c.x.shape[-1])
+            e.y = c.y.data_ptr()
+            e.mask = _ptr(c.mask)
+            off += Ck + 1
+        sets.n_sets = len(entries)
+        return sets, off
+
+    def _encode_fused(self, batch: DeviceBatch, plan: dict, enc: Optional[torch.Tensor] = None,
+                      blk: Optional["_Blk"] = None) -> bool:
+        """Launch the fused encoder into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel).  False when
+        the staging does not fit in shared memory (the caller falls back to the per-set kernels)."""
+        K = _cabi
+        cfg, g, B = self.cfg, batch.grid, batch.B
+        lib = K.lib()
+        Cin = cfg.in_channels
+        CP = blk.CB * 8 if blk is not None else Cin
+        if lib.cnp_encode_fused_smem_bytes(CP, plan["cmax"]["task"], plan["cols"]["task"]) <= 0:
+            return False
+        n_in = lambda c: 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0))
+        entries = list(plan["per_task"])
+        sets, _ = self._enc_sets(entries, rebase=False)
+        if plan["static"]:
+            ssets, Cs = self._enc_sets(plan["static"], rebase=True)
+            if lib.cnp_encode_fused_smem_bytes(Cs, plan["cmax"]["static"], plan["cols"]["static"]) <= 0:
+                return False
+            sbuf = self._buf("enc_static", (1, Cs, g.n1, g.n2))
+            self._call("cnp_encode_fused", C.byref(ssets), 1, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
+                       _ptr(sbuf), sbuf.stride(0), Cs, None, 0, plan["cols"]["static"], _stream(),
+                       work=(0.0, sum(n_in(c) for _, c, _, _ in plan["static"]) + 4.0 * sbuf.numel()))
+            off = 0
+            n = sets.n_sets
+            for (k, c, ch, s2) in plan["static"]:
+                e = sets.s[n]
+                e.kind, e.C, e.ch_off = 2, cfg.dim_yc[k] + 1, ch
+                e.y = sbuf.data_ptr() + 4 * off * g.n1 * g.n2
+                off += cfg.dim_yc[k] + 1
+                n += 1
+            sets.n_sets = n
+        by_in = sum(n_in(c) for _, c, _, _ in plan["per_task"])
+        if blk is not None:
+            bv = blk.view()
+            self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 1, None, 0,
+                       Cin, C.byref(bv), blk.CB, plan["cols"]["task"], _stream(),
+                       work=(0.0, by_in + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
+        else:
+            self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
+                       _ptr(enc), enc.stride(0), Cin, None, 0, plan["cols"]["task"], _stream(),
+                       work=(0.0, by_in + 4.0 * enc.numel()))
+        return True
+
+    def encode_blocked(self, batch: DeviceBatch) -> Optional["_Blk"]:
+        """bf16 UNet with the folded first layer: the encoder writes the UNet's blocked bf16 input (with the constant-1
+        channel) directly.  None when the batch needs the per-set kernels (then ``encode`` + the layout conversion run)."""
+        plan = self._fused_plan(batch)
+        if plan is None:
+            return None
+        cfg, g = self.cfg, batch.grid
+        cb0 = 2 * ((cfg.in_channels + 1 + 15) // 16)
+        blk = self._blk("x_aug", batch.B, cb0, g.n1, g.n2)
+        return blk if self._encode_fused(batch, plan, blk=blk) else None
 
     def _encode_set(self, batch: DeviceBatch, k: int, c: DeviceContext, enc: torch.Tensor, ch: int) -> None:
         cfg, g, B = self.cfg, batch.grid, batch.B
@@ -582,14 +711,15 @@ class Engine:
     def _prepack_all(self):
         """Re-pack every weight whose version changed (optimiser step) on a side stream at the start of the step, so
         the ~25 small packing launches overlap the encoder instead of sitting between the convolutions."""
-        if self.force_pack:
+        if self.force_pack or self.weights_dirty:
             self.packs_recorded = 0
             self._forced = set()
         if os.environ.get("CNP_NO_PREPACK"):
             return
+        force = self.force_pack or self.weights_dirty
         stale = [(k, r) for k, r in self._pack_reqs.items()
-                 if self._packed.get(k) is not None and (self.force_pack or self._packed[k][0] != self._pack_version(r))]
-        if self.force_pack:
+                 if self._packed.get(k) is not None and (force or self._packed[k][0] != self._pack_version(r))]
+        if force:
             self._forced = set(k for k, _ in stale)
         if not stale:
             return
@@ -634,10 +764,11 @@ class Engine:
             torch.cuda.current_stream().wait_event(self._pack_event)
             self._pack_event = None
         ent = self._packed.get(key)
-        fresh = not self.force_pack or key in getattr(self, "_forced", ())      # forced: already re-packed this step
+        force = self.force_pack or self.weights_dirty
+        fresh = not force or key in getattr(self, "_forced", ())      # forced: already re-packed in this forward
         if ent is not None and ent[0] == self._pack_version(req) and ent[1].device == w.device and fresh:
             return ent[1]
-        if self.force_pack:
+        if force:
             self._forced.add(key)
         nbytes = _cabi.lib().cnp_conv_tc2_packed_bytes(kind, n_chunks, n_out)
         buf = ent[1] if ent is not None else torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
@@ -672,8 +803,8 @@ class Engine:
         o._keep = (bias, mask)
         return o
 
-    def _unet_fwd_bf16(self, enc: torch.Tensor, B: int, n1: int, n2: int, need_z: bool = True
-                       ) -> Tuple[Optional[torch.Tensor], dict]:
+    def _unet_fwd_bf16(self, enc: Optional[torch.Tensor], B: int, n1: int, n2: int, need_z: bool = True,
+                       x_aug: Optional["_Blk"] = None) -> Tuple[Optional[torch.Tensor], dict]:
         K = _cabi
         cfg, u = self.cfg, self.module.decoder.unet
         st = cfg.unet_strides
@@ -684,7 +815,9 @@ class Engine:
         # the initial 1x1 is folded into the first 5x5 (fold_in.cu) when that layer has stride 1: its input is then
         # the encoder output itself, in 2 (4, 6) bf16 chunks with a constant-1 channel carrying the 1x1's bias
         fold_in = st[0] == 1 and cfg.in_channels + 1 <= 64 and not os.environ.get("CNP_NO_FOLD_IN")
-        if fold_in:
+        if fold_in and x_aug is not None:        # written by the fused encoder (enc_fused.cu)
+            cb0, h_init = x_aug.CB, x_aug
+        elif fold_in:
             cb0 = 2 * ((cfg.in_channels + 1 + 15) // 16)
             h_init = self._blk("x_aug", B, cb0, n1, n2)
             self._call("cnp_blk_from_nchw_f32_ones", _ptr(enc), enc.stride(0), B, cfg.in_channels, n1, n2,
@@ -911,12 +1044,15 @@ class Engine:
         # the channels of batch-shared context sets itself
         folded = (self.precision != "fp32" and cfg.unet_strides[0] == 1 and cfg.in_channels + 1 <= 64
                   and not os.environ.get("CNP_NO_FOLD_IN"))
-        enc = self.encode(batch, broadcast=not folded)
+        x_aug = self.encode_blocked(batch) if folded else None
+        enc = self.encode(batch, broadcast=not folded) if x_aug is None else None
         on_grid = isinstance(batch.xt, tuple)
         if self.precision == "fp32":
             z, A = self._unet_fwd_f32(enc, B, g.n1, g.n2)
         else:
-            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=False)
+            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=False, x_aug=x_aug)
+            if not os.environ.get("CNP_NO_PREPACK"):
+                self.weights_dirty = False     # every known packing (forward and dgrad) was refreshed by _prepack_all
         Cz = cfg.unet_out_channels
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
         if on_grid:
@@ -1053,4 +1189,5 @@ class Engine:
             dist.all_reduce(flat, group=self.allreduce_group)
             flat.mul_(1.0 / self.world_size)
         self._flat_grad = flat
+        self.weights_dirty = True     # an optimiser step follows a backward: the next forward re-packs the bf16 weights
         return grads

@@ -139,6 +139,7 @@ class GraphedTrainStep:
                 batch.ready = None
             self.load(batch)
         self.graph.replay()
+        self.eng.weights_dirty = True          # the replay moved the masters: a later eager forward must re-pack
         if not self.capture_optimizer:
             for p, g in zip(self._params, self._grads):
                 p.grad = g

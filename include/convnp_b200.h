@@ -84,6 +84,35 @@ typedef struct cnp_blk {
   int H, W;            /* interior size; planes are (H+4) x (W+4) */
 } cnp_blk;
 
+/* ---- (1') fused SetConv encoder: every context set of a task -> the UNet input, one launch -----------
+ * replaces: the whole upstream encoder stack (PrependDensityChannel + SetConv per set + DivideByFirstChannel +
+ * Concatenate, neuralprocesses coders/setconv) as reached from ConvNP.loss_fn / predict --
+ * nzdownscale/downscaler/train.py:370, validate_ERA.py:88-92.  One CTA = one 8 x 32 tile of the internal grid of one
+ * task; gridded sets need monotone coordinates shared by the batch.  kind 2 feeds channels that were encoded once for
+ * the whole batch by a first call (B = 1, mode 0) -- static topography / land-mask sets.
+ * mode 0: fp32 NCHW out_f32 [B][c_total][n1][n2]; mode 1: blocked bf16 out_blk with n_chunks chunks: channels
+ * [0, c_total) = encoder output, channel c_total = 1 inside the image (folded first layer, cnp_fold_in_fwd), rest 0. */
+typedef struct cnp_enc_set {
+  int kind;            /* 0 off-grid, 1 gridded, 2 precomputed fp32 planes [C][n1][n2] */
+  int C;               /* data channels (<= 8); kind 2: number of planes */
+  int ch_off;          /* first output channel (density for kinds 0 / 1) */
+  int batched;         /* gridded: y / mask carry a batch axis (0 = one field for every task) */
+  const float* x1;     /* gridded [N1]; off-grid x [B,2,N] */
+  const float* x2;     /* gridded [N2] */
+  const float* y;      /* gridded [B or 1,C,N1,N2]; off-grid [B,C,N]; may hold NaN (= missing) */
+  const float* mask;   /* gridded [B or 1,1,N1,N2]; off-grid [B,1,N]; or NULL */
+  int N1, N2;          /* off-grid: N1 = N */
+  int mono1, mono2;    /* +1 ascending, -1 descending */
+  float scale2;        /* exp(2 log_scale) */
+  int pad_;
+} cnp_enc_set;
+typedef struct cnp_enc_sets { int n_sets; int pad_; cnp_enc_set s[8]; } cnp_enc_sets;   /* HOST struct, passed by value to the kernel */
+long long cnp_encode_fused_smem_bytes(int channels_staged, int cmax1, int max_cols);   /* -1: does not fit */
+int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
+                     float eps, int mode, float* out_f32, long long out_bstride, int c_total, const cnp_blk* out_blk,
+                     int n_chunks, int max_cols /* bound of input columns inside the band of 32 grid columns */,
+                     cnp_stream_t s);
+
 typedef struct cnp_conv_out {
   int mode;            /* 0: blocked bf16 (blk), 1: fp32 NCHW (f32, f32_bstride, f32_ch_off) */
   cnp_blk blk;
