@@ -86,7 +86,9 @@ class GraphedTrainStep:
         eng.force_pack = True
         l0 = eng.launches
         try:
-            with torch.cuda.graph(self.graph):
+            # thread-local error mode: train_epoch's worker thread may be staging / uploading the next batch (pinned
+            # allocations, event synchronisation) while this thread captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.loss = self._fwd_bwd()
                 if self.capture_optimizer:
                     self.opt.step()

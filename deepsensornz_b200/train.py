@@ -100,19 +100,23 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
         nxt = make(0) if n_batches > 0 else None
         for bi in it:
             cur = nxt
-            fut = pool.submit(make, bi + 1) if (pool is not None and bi + 1 < n_batches) else None
+            fut = None
+            submit = lambda: pool.submit(make, bi + 1) if (pool is not None and bi + 1 < n_batches) else None
             if use_graph and not isinstance(cur, list):
                 from .graph import GraphedTrainStep, batch_signature
                 key = (id(opt), batch_signature(cur))
                 gs = graphs.get(key)
                 if gs is None:            # first batch of this shape: eager (it is also the warm-up of the capture)
+                    fut = submit()
                     loss_t = launch_step(cur)
                     graphs[key] = False
                 else:
-                    if gs is False:
+                    if gs is False:       # second batch: capture (no concurrent staging while the graph is recorded)
                         gs = graphs[key] = GraphedTrainStep(model, opt, cur, warm=True)
+                    fut = submit()
                     loss_t = gs.step(cur)
             else:
+                fut = submit()
                 loss_t = launch_step(cur)
             if on_gpu and loss_t.is_cuda:
                 slots[bi % 2].copy_(loss_t.to(torch.float64), non_blocking=True)
