@@ -126,6 +126,7 @@ class Engine:
         self._ws: Dict[tuple, object] = {}
         self._packed: Dict[str, Tuple[int, torch.Tensor]] = {}
         self._scale_cache: Dict[int, Tuple[int, float]] = {}
+        self._enc_tabs: Dict[tuple, tuple] = {}      # band tables of the fused encoder, per (coordinates, grid, scale)
         self._pack_reqs: Dict[str, tuple] = {}     # every packing seen so far -> re-issued up front on a side stream
         self._pack_stream = None
         self._pack_event = None
@@ -205,6 +206,7 @@ class Engine:
         self._ws.clear()
         self._packed.clear()
         self._pack_reqs.clear()
+        self._enc_tabs.clear()
 
     def _scale2(self, log_scale: torch.Tensor) -> float:
         """exp(2 log_scale) as an fp32-rounded host float.  The length scales are fixed (not learnable), so the value
@@ -455,7 +457,27 @@ class Engine:
             ch += Ck + 1
         return dict(per_task=per_task, static=static, cols=cols, cmax=cmax)
 
-    def _enc_sets(self, entries, rebase: bool):
+    def _enc_tables(self, c: DeviceContext, g: GridSpec, scale2: float):
+        """Band tables of a gridded set (band starts, lengths and SetConv weights per internal-grid row / column).  They
+        depend only on (coordinates, grid, length scale) -- all fixed during training -- so they are built once
+        (cnp_encode_tables) and kept on the device, keyed by the coordinate bytes."""
+        key = (c.x_host[0].tobytes(), c.x_host[1].tobytes(), g, scale2)
+        ent = self._enc_tabs.get(key)
+        if ent is None:
+            if len(self._enc_tabs) > 64:
+                self._enc_tabs.clear()
+            band = self._band_hint(c, g, scale2)
+            ti = torch.empty(2 * (g.n1 + g.n2), dtype=torch.int32, device=self.device)
+            tw = torch.empty(band * (g.n1 + g.n2), dtype=torch.float32, device=self.device)
+            x1, x2 = c.x
+            self._call("cnp_encode_tables", _ptr(x1), _ptr(x2), int(x1.shape[-1]), int(x2.shape[-1]), c.mono[0], c.mono[1],
+                       g.start1, g.n1, g.start2, g.n2, g.res, scale2, band, _ptr(ti), _ptr(tw), _stream())
+            ent = (band, ti, tw)
+            if not torch.cuda.is_current_stream_capturing():     # (tensors made during a capture live in the graph's pool)
+                self._enc_tabs[key] = ent
+        return ent
+
+    def _enc_sets(self, entries, grid: GridSpec, rebase: bool):
         K = _cabi
         sets = K.CnpEncSets()
         keep = []
@@ -469,6 +491,8 @@ class Engine:
                 e.x1, e.x2 = c.x[0].data_ptr(), c.x[1].data_ptr()
                 e.N1, e.N2 = int(c.x[0].shape[-1]), int(c.x[1].shape[-1])
                 e.mono1, e.mono2 = c.mono
+                e.KB, ti, tw = self._enc_tables(c, grid, s2)
+                e.tab_i, e.tab_w = ti.data_ptr(), tw.data_ptr()
             else:
                 e.batched = 1
                 e.x1, e.N1 = c.x.data_ptr(), int(c.x.shape[-1])
@@ -491,9 +515,9 @@ class Engine:
             return False
         n_in = lambda c: 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0))
         entries = list(plan["per_task"])
-        sets, _ = self._enc_sets(entries, rebase=False)
+        sets, _ = self._enc_sets(entries, g, rebase=False)
         if plan["static"]:
-            ssets, Cs = self._enc_sets(plan["static"], rebase=True)
+            ssets, Cs = self._enc_sets(plan["static"], g, rebase=True)
             if lib.cnp_encode_fused_smem_bytes(Cs, plan["cmax"]["static"], plan["cols"]["static"]) <= 0:
                 return False
             sbuf = self._buf("enc_static", (1, Cs, g.n1, g.n2))

@@ -88,7 +88,7 @@ typedef struct cnp_blk {
  * replaces: the whole upstream encoder stack (PrependDensityChannel + SetConv per set + DivideByFirstChannel +
  * Concatenate, neuralprocesses coders/setconv) as reached from ConvNP.loss_fn / predict --
  * nzdownscale/downscaler/train.py:370, validate_ERA.py:88-92.  One CTA = one 8 x 32 tile of the internal grid of one
- * task; gridded sets need monotone coordinates shared by the batch.  kind 2 feeds channels that were encoded once for
+ * task; gridded sets need monotone coordinates shared by the batch and their band tables (cnp_encode_tables).  kind 2 feeds channels that were encoded once for
  * the whole batch by a first call (B = 1, mode 0) -- static topography / land-mask sets.
  * mode 0: fp32 NCHW out_f32 [B][c_total][n1][n2]; mode 1: blocked bf16 out_blk with n_chunks chunks: channels
  * [0, c_total) = encoder output, channel c_total = 1 inside the image (folded first layer, cnp_fold_in_fwd), rest 0. */
@@ -104,10 +104,18 @@ typedef struct cnp_enc_set {
   int N1, N2;          /* off-grid: N1 = N */
   int mono1, mono2;    /* +1 ascending, -1 descending */
   float scale2;        /* exp(2 log_scale) */
-  int pad_;
+  int KB;              /* gridded: band width of the tables (<= 32) */
+  const int* tab_i;    /* gridded: [p0 (n1) | len1 (n1) | q0 (n2) | len2 (n2)], from cnp_encode_tables */
+  const float* tab_w;  /* gridded: [w1 (KB x n1) | w2 (KB x n2)] */
 } cnp_enc_set;
 typedef struct cnp_enc_sets { int n_sets; int pad_; cnp_enc_set s[8]; } cnp_enc_sets;   /* HOST struct, passed by value to the kernel */
 long long cnp_encode_fused_smem_bytes(int channels_staged, int cmax1, int max_cols);   /* -1: does not fit */
+/* band tables of one gridded set: they depend only on (coordinates, internal grid, length scale) -- build once, keep
+ * across steps.  tab_i: 2 * (n1 + n2) ints, tab_w: band * (n1 + n2) floats; band = host-side upper bound (<= 32) of
+ * the number of inputs within the truncation radius of any grid point along either dimension. */
+int cnp_encode_tables(const float* x1 /*[N1]*/, const float* x2 /*[N2]*/, int N1, int N2, int mono1, int mono2,
+                      double start1, int n1, double start2, int n2, double res, float scale2, int band,
+                      int* tab_i, float* tab_w, cnp_stream_t s);
 int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
                      float eps, int mode, float* out_f32, long long out_bstride, int c_total, const cnp_blk* out_blk,
                      int n_chunks, int max_cols /* bound of input columns inside the band of 32 grid columns */,
