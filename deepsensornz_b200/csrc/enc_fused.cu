@@ -8,29 +8,37 @@
 // with NaN observations turned into valid = 0 on the fly (ConvNP.modify_task's host scan) and terms whose exponent
 // exceeds 104 (exactly 0.0f in fp32) left out of the sums.
 //
-// One CTA = one 8 x 32 tile of the internal grid of one task; it walks the task's context sets:
-//   * gridded set: the input rows inside the tile's band are streamed through shared memory 16 / 32 at a time; a
-//     horizontal band pass (<= 32 taps per output column) writes T[c][row][j] to shared memory and the vertical pass
-//     accumulates the thread's pixel.  Band starts and weights come from per-set tables (cnp_encode_tables) that depend
-//     only on (coordinates, internal grid, length scale): the caller builds them once and keeps them across steps, so a
-//     CTA starts with two coalesced table reads instead of binary searches and expf.  Gather form, no atomics.
-//   * off-grid set: points that can touch the tile are compacted in order, their separable weights staged in shared
-//     memory, every thread sums its own pixel.
-//   * precomputed planes: channels of sets that the whole batch shares (topography aux, land mask) are encoded ONCE
-//     per step by a first launch of this same kernel (B = 1, fp32 planes) and copied in here from L2.
-// The tile's channels meet in shared memory and leave as either fp32 NCHW (parity mode) or -- bf16 UNet -- directly
-// as the blocked bf16 tensor [B][chunk][H+4][W+4][8] with the constant-1 channel of the folded first layer
-// (fold_in.cu): no fp32 encoder tensor, no layout-conversion kernel.  Bound: HBM.
+// Two launches per step (three when the batch shares static sets):
+//   1. cnp_encode_hpass: horizontal band pass of EVERY gridded set, T_k[b][c][p][j] = sum_q y~[b][c][p][q] w2[q][j]
+//      (<= 32 taps, one thread per (p, j), all channels) into a workspace that stays in L2.  Band starts and weights
+//      come from per-set tables (cnp_encode_tables) that depend only on (coordinates, internal grid, length scale): the
+//      caller builds them once and keeps them across steps.
+//   2. cnp_encode_fused: one CTA = one 32 x 32 tile of the internal grid of one task, one thread = 4 adjacent rows of one
+//      column.  Per context set:
+//        * gridded: vertical band pass over the T rows in the union band of the thread's rows (each T row is loaded
+//          once for the 4 pixels, coalesced along the columns), weights from a shared-memory copy of the tile's table;
+//        * off-grid: every thread loads one point (coordinates, channels, mask), the points that can touch the tile are
+//          compacted in order, their separable weights staged in shared memory, every thread sums its own pixels;
+//        * precomputed planes: channels of sets the whole batch shares (topography aux, land mask) are encoded ONCE per
+//          step by a first call of this same kernel (B = 1, fp32 planes) and copied in here from L2.
+//      Gather form throughout, no atomics.  The tile's channels meet in shared memory and leave as either fp32 NCHW
+//      (parity mode) or -- bf16 UNet -- directly as the blocked bf16 tensor [B][chunk][H+4][W+4][8] with the constant-1
+//      channel of the folded first layer (fold_in.cu): no fp32 encoder tensor, no layout-conversion kernel.
+// Bound: HBM.  History (B200, B = 16, 304^2): per-set kernels of round 1 240 us; a first fused
+// version that recomputed the horizontal pass per 8 x 32 tile in shared memory 312 us (ncu: 166 M warp instructions,
+// instruction-bound -- every tile redid ~3x the horizontal work and ran 9-channel predicated loops); this version:
+// see profiles/.
 #include "tc_common.cuh"
 #include <math.h>
+#include <type_traits>
 
 struct cnp_enc_set {
   int kind;          // 0 off-grid, 1 gridded, 2 precomputed fp32 planes [C][n1][n2] (already normalised)
   int C;             // data channels (kind 2: number of planes)
   int ch_off;        // first output channel (the density channel for kinds 0 / 1)
-  int batched;       // y (and mask) carry a batch axis; 0: one field shared by every task
-  const float* x1;   // gridded: [N1]; off-grid: x [B,2,N]
-  const float* x2;   // gridded: [N2]
+  int batched;       // y (and mask, T) carry a batch axis; 0: one field shared by every task
+  const float* x1;   // off-grid: x [B,2,N]
+  const float* x2;   // unused by the kernels (gridded coordinates enter through the tables)
   const float* y;    // gridded [B or 1, C, N1, N2]; off-grid [B, C, N]
   const float* mask; // gridded [B or 1, 1, N1, N2] | off-grid [B, 1, N] | NULL
   int N1, N2;        // off-grid: N1 = N
@@ -39,6 +47,7 @@ struct cnp_enc_set {
   int KB;            // gridded: band width of the tables (<= 32)
   const int* tab_i;  // gridded: [p0 (n1) | len1 (n1) | q0 (n2) | len2 (n2)]   (cnp_encode_tables)
   const float* tab_w;// gridded: [w1 (KB x n1) | w2 (KB x n2)]
+  float* T;          // gridded: horizontal-pass workspace [B or 1][C+1][N1][n2]
 };
 struct cnp_enc_sets {
   int n_sets;
@@ -48,7 +57,7 @@ struct cnp_enc_sets {
 
 namespace {
 
-constexpr int TI = 8, TJ = 32, NT = 256;
+constexpr int TI = 32, TJ = 32, NT = 256, RPT = 4;   // tile rows / cols, threads, rows per thread
 constexpr int KBMAX = 32;    // max band (inputs within R of one grid row / column)
 constexpr int OGC = 256;     // off-grid points per chunk (one per thread)
 constexpr int OGS = 64;      // off-grid points whose weights are staged at a time
@@ -81,143 +90,213 @@ __device__ void window_of(const float* __restrict__ x, int n, float a, float b, 
   if (*p1 < *p0) *p1 = *p0;
 }
 
+// =====================================================================================================================
+// launch 1: horizontal band pass of every gridded set
+// =====================================================================================================================
+struct cnp_hpass_args {
+  cnp_enc_sets S;
+  int blk0[9];       // first block of every set (prefix sums); blk0[n_sets] = grid size
+  int nb[8];         // batch entries of every set (B or 1)
+  int n1, n2;
+};
+
+template <int C>
+__device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p, int j, int n1, int n2) {
+  const int N1 = st.N1, N2 = st.N2;
+  const int q0 = __ldg(st.tab_i + 2 * n1 + j), len = __ldg(st.tab_i + 2 * n1 + n2 + j);
+  const float* w2 = st.tab_w + (size_t)st.KB * n1 + j;
+  const size_t plane = (size_t)N1 * N2;
+  const float* yb = st.y + (size_t)b * C * plane + (size_t)p * N2 + q0;
+  const float* mb = st.mask ? st.mask + (size_t)b * plane + (size_t)p * N2 + q0 : nullptr;
+  float acc[C + 1];
+#pragma unroll
+  for (int c = 0; c <= C; ++c) acc[c] = 0.f;
+  for (int k = 0; k < len; ++k) {
+    const float w = __ldg(w2 + (size_t)k * n2);
+    float valid = mb ? __ldg(mb + k) : 1.f;
+    float v[C];
+    bool nan_any = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { v[c] = __ldg(yb + (size_t)c * plane + k); nan_any |= isnan(v[c]); }
+    if (nan_any) valid = 0.f;
+    acc[0] = fmaf(valid, w, acc[0]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[1 + c] = fmaf(nan_any ? 0.f : v[c] * valid, w, acc[1 + c]);
+  }
+  float* T = st.T + (((size_t)b * (C + 1)) * N1 + p) * n2 + j;
+#pragma unroll
+  for (int c = 0; c <= C; ++c) T[(size_t)c * N1 * n2] = acc[c];
+}
+
+__global__ void __launch_bounds__(256)
+enc_hpass_kernel(const __grid_constant__ cnp_hpass_args a) {
+  int k = 0;
+  while (k + 1 < a.S.n_sets && (int)blockIdx.x >= a.blk0[k + 1]) ++k;
+  const cnp_enc_set& st = a.S.s[k];
+  const long long e = (long long)(blockIdx.x - a.blk0[k]) * 256 + threadIdx.x;
+  const long long per_b = (long long)st.N1 * a.n2;
+  if (e >= per_b * a.nb[k]) return;
+  const int b = (int)(e / per_b), r = (int)(e - (long long)b * per_b), p = r / a.n2, j = r - p * a.n2;
+  switch (st.C) {
+    case 1: hpass_elem<1>(st, b, p, j, a.n1, a.n2); break;
+    case 2: hpass_elem<2>(st, b, p, j, a.n1, a.n2); break;
+    case 3: hpass_elem<3>(st, b, p, j, a.n1, a.n2); break;
+    case 4: hpass_elem<4>(st, b, p, j, a.n1, a.n2); break;
+    case 5: hpass_elem<5>(st, b, p, j, a.n1, a.n2); break;
+    case 6: hpass_elem<6>(st, b, p, j, a.n1, a.n2); break;
+    case 7: hpass_elem<7>(st, b, p, j, a.n1, a.n2); break;
+    default: hpass_elem<8>(st, b, p, j, a.n1, a.n2); break;
+  }
+}
+
+// =====================================================================================================================
+// launch 2: vertical pass + off-grid sets + precomputed planes -> the UNet input
+// =====================================================================================================================
+template <typename OT> __device__ __forceinline__ void put(OT* o, float v);
+template <> __device__ __forceinline__ void put<float>(float* o, float v) { *o = v; }
+template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* o, float v) { *o = __float2bfloat16(v); }
+
+// store one set's result for the thread's RPT pixels: density first, data divided by (density + eps)
+template <int C, typename OT>
+__device__ __forceinline__ void store_set(OT* outs, int ch_off, int pix0, const float (&acc)[RPT][MAXC1], float eps) {
+#pragma unroll
+  for (int e = 0; e < RPT; ++e) {
+    const float dens = acc[e][0], den = dens + eps;
+    put<OT>(outs + (size_t)ch_off * (TI * TJ) + pix0 + e * TJ, dens);
+#pragma unroll
+    for (int c = 1; c <= C; ++c) put<OT>(outs + (size_t)(ch_off + c) * (TI * TJ) + pix0 + e * TJ, acc[e][c] / den);
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void vpass(const cnp_enc_set& st, int b, int n1, int n2, int j, bool col_ok, const int (&p0)[RPT],
+                                      const int (&len)[RPT], const float* __restrict__ w1t, int row0,
+                                      float (&acc)[RPT][MAXC1]) {
+  // union band of the thread's rows (monotone coordinates: bands of adjacent rows overlap almost entirely)
+  int lo = 0x7fffffff, hi = 0;
+#pragma unroll
+  for (int e = 0; e < RPT; ++e) if (len[e] > 0) { lo = min(lo, p0[e]); hi = max(hi, p0[e] + len[e]); }
+  if (!col_ok || hi <= lo) return;
+  const int N1 = st.N1, KBs = st.KB;
+  const float* T = st.T + ((size_t)(st.batched ? b : 0) * (C + 1)) * N1 * n2 + j;
+  for (int r = lo; r < hi; ++r) {
+    float t[C + 1];
+#pragma unroll
+    for (int c = 0; c <= C; ++c) t[c] = __ldg(T + ((size_t)c * N1 + r) * n2);
+#pragma unroll
+    for (int e = 0; e < RPT; ++e) {
+      const int kk = r - p0[e];
+      const float w = ((unsigned)kk < (unsigned)len[e]) ? w1t[(row0 + e) * KBs + kk] : 0.f;
+#pragma unroll
+      for (int c = 0; c <= C; ++c) acc[e][c] = fmaf(w, t[c], acc[e][c]);
+    }
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void ogacc(const float* __restrict__ ys, const float* __restrict__ w1s,
+                                      const float* __restrict__ w2s, int m0, int nm, int row0, int tx,
+                                      float (&acc)[RPT][MAXC1]) {
+  for (int m = 0; m < nm; ++m) {
+    const float w2 = w2s[m * (TJ + 1) + tx];
+    float yv[C + 1];
+#pragma unroll
+    for (int c = 0; c <= C; ++c) yv[c] = ys[c * OGC + m0 + m];
+#pragma unroll
+    for (int e = 0; e < RPT; ++e) {
+      const float w = w1s[m * TI + row0 + e] * w2;
+#pragma unroll
+      for (int c = 0; c <= C; ++c) acc[e][c] = fmaf(yv[c], w, acc[e][c]);
+    }
+  }
+}
+
+#define CNP_SWITCH_C(Cv, ...)                     \
+  switch (Cv) {                                   \
+    case 1: { constexpr int CC = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int CC = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int CC = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int CC = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int CC = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int CC = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int CC = 7; __VA_ARGS__; } break; \
+    default: { constexpr int CC = 8; __VA_ARGS__; } break; \
+  }
+
 template <int MODE>   // 0: fp32 NCHW output, 1: blocked bf16 output with the constant-1 channel
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 enc_fused_kernel(const __grid_constant__ cnp_enc_sets S, double start1, int n1, double start2, int n2, double res,
-                 float eps, float* __restrict__ out_f32, long long out_bs, int c_total, cnp_blk ob, int n_chunks,
-                 int max_cols, int cmax1, int CP, int ROWS) {
-  extern __shared__ float sm[];
-  float* outs = sm;                               // [CP][NT]
-  float* scr = sm + (size_t)CP * NT;              // per-set scratch
+                 float eps, float* __restrict__ out_f32, long long out_bs, int c_total, cnp_blk ob, int n_chunks, int CP) {
+  using OT = typename std::conditional<MODE == 0, float, __nv_bfloat16>::type;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  OT* outs = reinterpret_cast<OT*>(sm_raw);                                        // [CP][TI*TJ]
+  float* scr = reinterpret_cast<float*>(sm_raw + (((size_t)CP * TI * TJ * sizeof(OT) + 15) & ~(size_t)15));
   __shared__ float g1s[TI], g2s[TJ];
-  __shared__ int p0s[TI], p1s[TI], q0s[TJ], q1s[TJ], win[4], warp_cnt[8];
+  __shared__ int warp_cnt[8];
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int b = blockIdx.z, i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
-  const int i = i0 + ty, j = j0 + tx;
+  const int row0 = ty * RPT, j = j0 + tx;
+  const bool col_ok = j < n2;
+  const int pix0 = row0 * TJ + tx;                 // tile-local pixel of the thread's first row
   if (tid < TI) g1s[tid] = cnp_grid_pt(start1, res, min(i0 + tid, n1 - 1));
   if (tid >= 32 && tid < 32 + TJ) g2s[tid - 32] = cnp_grid_pt(start2, res, min(j0 + tid - 32, n2 - 1));
-  for (int c = 0; c < CP; ++c) outs[c * NT + tid] = 0.f;
+  for (int c = 0; c < CP; ++c)
+#pragma unroll
+    for (int e = 0; e < RPT; ++e) put<OT>(outs + (size_t)c * (TI * TJ) + pix0 + e * TJ, 0.f);
 
   for (int k = 0; k < S.n_sets; ++k) {
     const cnp_enc_set& st = S.s[k];
     const int C = st.C;
     __syncthreads();                               // scratch of the previous set is free; g1s / g2s are visible
     if (st.kind == 2) {
-      if (i < n1 && j < n2)
+      if (col_ok)
         for (int c = 0; c < C; ++c)
-          outs[(st.ch_off + c) * NT + tid] = __ldg(st.y + ((size_t)c * n1 + i) * n2 + j);
+#pragma unroll
+          for (int e = 0; e < RPT; ++e) {
+            const int i = i0 + row0 + e;
+            if (i < n1) put<OT>(outs + (size_t)(st.ch_off + c) * (TI * TJ) + pix0 + e * TJ,
+                                __ldg(st.y + ((size_t)c * n1 + i) * n2 + j));
+          }
       continue;
     }
-    const float scale2 = st.scale2;
-    const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
-    float acc[MAXC1];
+    float acc[RPT][MAXC1];
 #pragma unroll
-    for (int c = 0; c < MAXC1; ++c) acc[c] = 0.f;
+    for (int e = 0; e < RPT; ++e)
+#pragma unroll
+      for (int c = 0; c < MAXC1; ++c) acc[e][c] = 0.f;
 
     if (st.kind == 1) {
-      // ---------------- gridded set ----------------
-      const int N1 = st.N1, N2 = st.N2, KBs = st.KB;
-      float* yv = scr;                                           // [cmax1][ROWS][max_cols]
-      float* T = yv + (size_t)cmax1 * ROWS * max_cols;           // [cmax1][ROWS][TJ]
-      float* w2b = T + (size_t)cmax1 * ROWS * TJ;                // [KBMAX][TJ]
-      float* w1c = w2b + KBMAX * TJ;                             // [ROWS][TI]
-      const int* ti = st.tab_i;
-      const float* tw1 = st.tab_w;
-      const float* tw2 = st.tab_w + (size_t)KBs * n1;
-      if (ty < 2) {                                  // warp 0: row bands of the tile, warp 1: column bands
-        int lo = 0x7fffffff, hi = 0;
-        if (ty == 0) {
-          if (tx < TI) {
-            const int ii = min(i0 + tx, n1 - 1), s0 = __ldg(ti + ii), l = __ldg(ti + n1 + ii);
-            p0s[tx] = s0; p1s[tx] = s0 + l;
-            if (i0 + tx < n1 && l > 0) { lo = s0; hi = s0 + l; }
-          }
-        } else {
-          const int jj = min(j0 + tx, n2 - 1), s0 = __ldg(ti + 2 * n1 + jj), l = __ldg(ti + 2 * n1 + n2 + jj);
-          q0s[tx] = s0; q1s[tx] = s0 + l;
-          if (j0 + tx < n2 && l > 0) { lo = s0; hi = s0 + l; }
-        }
-        lo = __reduce_min_sync(0xffffffffu, lo);
-        hi = __reduce_max_sync(0xffffffffu, hi);
-        if (tx == 0) { win[2 * ty] = (hi > 0) ? lo : 0; win[2 * ty + 1] = (hi > 0) ? hi : 0; }
+      // ---------------- gridded set: vertical band pass over the horizontal-pass workspace ----------------
+      const int KBs = st.KB;
+      float* w1t = scr;                            // [TI][KBs] weights of the tile's rows
+      for (int e = tid; e < TI * KBs; e += NT) {
+        const int r = e / KBs, kk = e - r * KBs;
+        w1t[e] = __ldg(st.tab_w + (size_t)kk * n1 + min(i0 + r, n1 - 1));
       }
-      for (int e = tid; e < KBMAX * TJ; e += NT) {
-        const int kk = e / TJ, jj = min(j0 + (e - kk * TJ), n2 - 1);
-        w2b[e] = (kk < KBs) ? __ldg(tw2 + (size_t)kk * n2 + jj) : 0.f;      // zero beyond the band (table padding)
+      int p0[RPT], len[RPT];
+#pragma unroll
+      for (int e = 0; e < RPT; ++e) {
+        const int i = i0 + row0 + e;
+        p0[e] = __ldg(st.tab_i + min(i, n1 - 1));
+        len[e] = (i < n1) ? __ldg(st.tab_i + n1 + min(i, n1 - 1)) : 0;
       }
       __syncthreads();
-      const int plo = win[0], phi = win[1], qlo = win[2];
-      const int ncols = min(win[3] - win[2], max_cols);
-      const int myq = q0s[tx] - qlo;
-      const int mylen = max(0, min(min(q1s[tx] - q0s[tx], KBs), ncols - myq));
-      const size_t plane = (size_t)N1 * N2;
-      const float* yb = st.y + (st.batched ? (size_t)b * C * plane : 0);
-      const float* mb = st.mask ? st.mask + (st.batched ? (size_t)b * plane : 0) : nullptr;
-      const size_t cstride = (size_t)ROWS * max_cols;
-      for (int pc = plo; pc < phi; pc += ROWS) {
-        const int np = min(ROWS, phi - pc);
-        if (pc > plo) __syncthreads();             // the previous chunk's T / yv / w1c readers are done
-        for (int e = tid; e < np * ncols; e += NT) {
-          const int r = e / ncols, q = e - r * ncols;
-          const size_t off = (size_t)(pc + r) * N2 + qlo + q;
-          float valid = mb ? __ldg(mb + off) : 1.f;
-          float v[MAXC1 - 1];
-          bool nan_any = false;
-#pragma unroll
-          for (int c = 0; c < MAXC1 - 1; ++c)
-            if (c < C) { v[c] = __ldg(yb + (size_t)c * plane + off); nan_any |= isnan(v[c]); }
-          if (nan_any) valid = 0.f;
-          float* d = yv + (size_t)r * max_cols + q;
-          d[0] = valid;
-#pragma unroll
-          for (int c = 0; c < MAXC1 - 1; ++c)
-            if (c < C) d[(size_t)(1 + c) * cstride] = nan_any ? 0.f : v[c] * valid;
-        }
-        for (int e = tid; e < np * TI; e += NT) {
-          const int r = e / TI, ii = e - r * TI, kk = pc + r - p0s[ii];
-          w1c[e] = (kk >= 0 && kk < p1s[ii] - p0s[ii] && kk < KBs)
-                       ? __ldg(tw1 + (size_t)kk * n1 + min(i0 + ii, n1 - 1)) : 0.f;
-        }
-        __syncthreads();
-        // horizontal band pass: T[c][r][tx] = sum_k yv[c][r][myq + k] w2b[k][tx]
-        for (int r = ty; r < np; r += TI) {
-          float Tr[MAXC1];
-#pragma unroll
-          for (int c = 0; c < MAXC1; ++c) Tr[c] = 0.f;
-          const float* yr = yv + (size_t)r * max_cols + myq;
-          for (int kk = 0; kk < mylen; ++kk) {
-            const float w = w2b[kk * TJ + tx];
-#pragma unroll
-            for (int c = 0; c < MAXC1; ++c)
-              if (c <= C) Tr[c] = fmaf(yr[(size_t)c * cstride + kk], w, Tr[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < MAXC1; ++c)
-            if (c <= C) T[((size_t)c * ROWS + r) * TJ + tx] = Tr[c];
-        }
-        __syncthreads();
-        // vertical pass: this thread's pixel
-        for (int r = 0; r < np; ++r) {
-          const float w = w1c[r * TI + ty];
-          if (w != 0.f) {
-#pragma unroll
-            for (int c = 0; c < MAXC1; ++c)
-              if (c <= C) acc[c] = fmaf(w, T[((size_t)c * ROWS + r) * TJ + tx], acc[c]);
-          }
-        }
-      }
+      CNP_SWITCH_C(C, vpass<CC>(st, b, n1, n2, j, col_ok, p0, len, w1t, row0, acc); store_set<CC, OT>(outs, st.ch_off, pix0, acc, eps))
     } else {
       // ---------------- off-grid set ----------------
       // one global round trip per chunk of 256 points: every thread loads its point (coordinates, all channels, mask),
       // the points that can touch the tile are compacted in order into shared memory, their separable weights are
-      // staged 64 points at a time and every thread sums its own pixel
+      // staged 64 points at a time and every thread sums its own pixels
+      const float scale2 = st.scale2;
+      const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
       const int N = st.N1;
       float* px = scr;                     // [2][OGC] compacted coordinates
       float* ys = px + 2 * OGC;            // [MAXC1][OGC] compacted [valid ; y * valid]
       float* w1s = ys + MAXC1 * OGC;       // [OGS][TI]
       float* w2s = w1s + OGS * TI;         // [OGS][TJ + 1]
       const float a1 = g1s[0], b1 = g1s[TI - 1], a2 = g2s[0], b2 = g2s[TJ - 1];
+      const float lo1 = fminf(a1, b1) - R, hi1 = fmaxf(a1, b1) + R, lo2 = fminf(a2, b2) - R, hi2 = fmaxf(a2, b2) + R;
       const float* xb = st.x1 + (size_t)b * 2 * N;
       const float* yb = st.y + (size_t)b * C * N;
       const float* mb = st.mask ? st.mask + (size_t)b * N : nullptr;
@@ -236,7 +315,7 @@ enc_fused_kernel(const __grid_constant__ cnp_enc_sets S, double start1, int n1, 
 #pragma unroll
           for (int c = 0; c < MAXC1 - 1; ++c)
             if (c < C) v[c] = nan_any ? 0.f : v[c] * valid;
-          keep = (p1 >= a1 - R) && (p1 <= b1 + R) && (p2 >= a2 - R) && (p2 <= b2 + R);
+          keep = (p1 >= lo1) && (p1 <= hi1) && (p2 >= lo2) && (p2 <= hi2);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (c0 > 0) __syncthreads();       // the previous chunk's consumers are done
@@ -258,40 +337,43 @@ enc_fused_kernel(const __grid_constant__ cnp_enc_sets S, double start1, int n1, 
           for (int e = tid; e < nm * TJ; e += NT) {
             const int m = e / TJ, jj = e - m * TJ;
             w2s[m * (TJ + 1) + jj] = cnp_rbf(px[OGC + m0 + m], g2s[jj], scale2);
-            if (jj < TI) w1s[m * TI + jj] = cnp_rbf(px[m0 + m], g1s[jj], scale2);
+            w1s[m * TI + jj] = cnp_rbf(px[m0 + m], g1s[jj], scale2);
           }
           __syncthreads();
-          for (int m = 0; m < nm; ++m) {
-            const float w = w1s[m * TI + ty] * w2s[m * (TJ + 1) + tx];
-#pragma unroll
-            for (int c = 0; c < MAXC1; ++c)
-              if (c <= C) acc[c] = fmaf(ys[c * OGC + m0 + m], w, acc[c]);
-          }
+          CNP_SWITCH_C(C, ogacc<CC>(ys, w1s, w2s, m0, nm, row0, tx, acc))
         }
       }
+      CNP_SWITCH_C(C, store_set<CC, OT>(outs, st.ch_off, pix0, acc, eps))
     }
-    // density first, data divided by (density + eps)
-    const float dens = acc[0], den = dens + eps;
-    outs[st.ch_off * NT + tid] = dens;
-#pragma unroll
-    for (int c = 1; c < MAXC1; ++c)
-      if (c <= C) outs[(st.ch_off + c) * NT + tid] = acc[c] / den;
   }
 
-  if (i >= n1 || j >= n2) return;
+  if (!col_ok) return;
   if (MODE == 0) {
-    float* o = out_f32 + (size_t)b * out_bs + (size_t)i * n2 + j;
-    for (int c = 0; c < c_total; ++c) o[(size_t)c * n1 * n2] = outs[c * NT + tid];
+#pragma unroll
+    for (int e = 0; e < RPT; ++e) {
+      const int i = i0 + row0 + e;
+      if (i >= n1) continue;
+      float* o = out_f32 + (size_t)b * out_bs + (size_t)i * n2 + j;
+      for (int c = 0; c < c_total; ++c) o[(size_t)c * n1 * n2] = (float)outs[(size_t)c * (TI * TJ) + pix0 + e * TJ];
+    }
   } else {
-    outs[c_total * NT + tid] = 1.f;       // constant-1 channel of the folded first layer (0 in the pad, like the image)
     const int Hp = ob.H + 4, Wp = ob.W + 4;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ob.base) + (size_t)b * ob.bstride;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      __align__(16) __nv_bfloat16 pk[8];
+    const __nv_bfloat16 one = __float2bfloat16(1.f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) pk[e] = __float2bfloat16(outs[(ch * 8 + e) * NT + tid]);
-      *reinterpret_cast<uint4*>(base + (((size_t)(ob.cb_off + ch) * Hp + i + 2) * Wp + j + 2) * 8) =
-          *reinterpret_cast<const uint4*>(pk);
+    for (int e = 0; e < RPT; ++e) {
+      const int i = i0 + row0 + e;
+      if (i >= n1) continue;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        __align__(16) __nv_bfloat16 pk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = ch * 8 + q;   // channel c_total: constant 1 of the folded first layer (0 in the pad, like the image)
+          pk[q] = (c == c_total) ? one : reinterpret_cast<const __nv_bfloat16*>(outs)[(size_t)c * (TI * TJ) + pix0 + e * TJ];
+        }
+        *reinterpret_cast<uint4*>(base + (((size_t)(ob.cb_off + ch) * Hp + i + 2) * Wp + j + 2) * 8) =
+            *reinterpret_cast<const uint4*>(pk);
+      }
     }
   }
 }
@@ -333,51 +415,76 @@ CNP_API int cnp_encode_tables(const float* x1, const float* x2, int N1, int N2, 
   return 0;
 }
 
-static long long ef_smem(int channels_staged, int cmax1, int max_cols, int rows) {
-  if (cmax1 < 1) cmax1 = 1;
-  const long long grid_f = (long long)cmax1 * rows * max_cols + (long long)cmax1 * rows * TJ + KBMAX * TJ + rows * TI;
+static long long ef_smem(int mode, int channels_staged) {
   const long long og_f = 2LL * OGC + (long long)MAXC1 * OGC + OGS * TI + OGS * (TJ + 1);
-  return ((long long)channels_staged * NT + (grid_f > og_f ? grid_f : og_f)) * 4;
-}
-// rows staged per step: 32 when the launch then still fits 3 CTAs per SM, else 16
-static int ef_rows(int channels_staged, int cmax1, int max_cols) {
-  return ef_smem(channels_staged, cmax1, max_cols, 32) <= 72 * 1024 ? 32 : 16;
+  const long long grid_f = (long long)TI * KBMAX;
+  const long long outs_b = (((long long)channels_staged * TI * TJ * (mode == 0 ? 4 : 2)) + 15) & ~15LL;
+  return outs_b + (grid_f > og_f ? grid_f : og_f) * 4;
 }
 
-// Shared memory of one launch (bytes) for the given staging geometry; -1 when it cannot fit.
-CNP_API long long cnp_encode_fused_smem_bytes(int channels_staged, int cmax1, int max_cols) {
-  const long long bytes = ef_smem(channels_staged, cmax1, max_cols, ef_rows(channels_staged, cmax1, max_cols));
+// Shared memory of one cnp_encode_fused launch (bytes); -1 when it cannot fit.
+CNP_API long long cnp_encode_fused_smem_bytes(int mode, int channels_staged) {
+  const long long bytes = ef_smem(mode, channels_staged);
   return bytes <= 200 * 1024 ? bytes : -1;
 }
 
-// mode 0: out_f32 [B][c_total][n1][n2] (batch stride out_bstride floats); mode 1: out_blk = blocked bf16 view with
-// n_chunks >= (c_total + 1 + 7) / 8 chunks: channels [0, c_total) = the encoder output, channel c_total = 1, rest 0.
-// max_cols: upper bound of the number of input columns inside the band of any 32 consecutive grid columns, over the
-// gridded sets (host-side, from the coordinates; the kernel clamps to it).
-CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
-                             float eps, int mode, float* out_f32, long long out_bstride, int c_total,
-                             const cnp_blk* out_blk, int n_chunks, int max_cols, cudaStream_t st) {
-  CNP_REQUIRE(sets && sets->n_sets >= 1 && sets->n_sets <= 8 && B > 0 && n1 > 0 && n2 > 0, "encode_fused: bad arguments");
-  CNP_REQUIRE(mode == 0 ? out_f32 != nullptr : (out_blk != nullptr && n_chunks * 8 >= c_total + 1),
-              "encode_fused: output does not match mode %d", mode);
-  int cmax1 = 1;
+static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who) {
+  CNP_REQUIRE(sets && sets->n_sets >= 1 && sets->n_sets <= 8, "%s: need 1..8 context sets", who);
   for (int k = 0; k < sets->n_sets; ++k) {
     const cnp_enc_set& s = sets->s[k];
-    CNP_REQUIRE(s.kind >= 0 && s.kind <= 2 && s.C >= 0 && s.ch_off >= 0, "encode_fused: set %d malformed", k);
-    CNP_REQUIRE(s.ch_off + s.C + (s.kind == 2 ? 0 : 1) <= c_total, "encode_fused: set %d exceeds %d channels", k, c_total);
-    if (s.kind != 2) CNP_REQUIRE(s.C <= MAXC1 - 1, "encode_fused: set %d has more than %d channels", k, MAXC1 - 1);
-    if (s.kind == 1) {
-      CNP_REQUIRE(s.y && s.tab_i && s.tab_w && s.KB >= 1 && s.KB <= KBMAX, "encode_fused: gridded set %d needs band tables", k);
-      if (s.C + 1 > cmax1) cmax1 = s.C + 1;
-    }
-    if (s.kind == 0) CNP_REQUIRE(s.N1 == 0 || (s.x1 && s.y), "encode_fused: off-grid set %d has null inputs", k);
+    CNP_REQUIRE(s.kind >= 0 && s.kind <= 2 && s.C >= 0 && s.ch_off >= 0, "%s: set %d malformed", who, k);
+    CNP_REQUIRE(s.ch_off + s.C + (s.kind == 2 ? 0 : 1) <= c_total, "%s: set %d exceeds %d channels", who, k, c_total);
+    if (s.kind != 2) CNP_REQUIRE(s.C >= 1 && s.C <= MAXC1 - 1, "%s: set %d needs 1..%d channels", who, k, MAXC1 - 1);
+    if (s.kind == 1)
+      CNP_REQUIRE(s.y && s.tab_i && s.tab_w && s.T && s.KB >= 1 && s.KB <= KBMAX && s.N1 > 0 && s.N2 > 0,
+                  "%s: gridded set %d needs band tables and a horizontal-pass workspace", who, k);
+    if (s.kind == 0) CNP_REQUIRE(s.N1 == 0 || (s.x1 && s.y), "%s: off-grid set %d has null inputs", who, k);
+    if (s.kind == 2) CNP_REQUIRE(s.y != nullptr, "%s: plane set %d has no planes", who, k);
   }
+  return 0;
+}
+
+// Launch 1: horizontal band pass of every gridded set of ``sets`` (other kinds are skipped) into their T workspaces
+// ([B or 1][C+1][N1][n2] floats each).
+CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
+  CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_hpass: bad arguments");
+  if (int rc = ef_check_sets(sets, 1 << 30, "encode_hpass")) return rc;
+  cnp_hpass_args a;
+  memset(&a, 0, sizeof(a));
+  a.n1 = n1; a.n2 = n2;
+  int n = 0, blocks = 0;
+  for (int k = 0; k < sets->n_sets; ++k) {
+    const cnp_enc_set& s = sets->s[k];
+    if (s.kind != 1) continue;
+    a.S.s[n] = s;
+    a.nb[n] = s.batched ? B : 1;
+    a.blk0[n] = blocks;
+    const long long elems = (long long)a.nb[n] * s.N1 * n2;
+    blocks += (int)((elems + 255) / 256);
+    ++n;
+  }
+  if (n == 0) return 0;
+  a.S.n_sets = n;
+  a.blk0[n] = blocks;
+  enc_hpass_kernel<<<blocks, 256, 0, st>>>(a);
+  CNP_LAUNCH_CHECK("enc_hpass_kernel");
+  return 0;
+}
+
+// Launch 2.  mode 0: out_f32 [B][c_total][n1][n2] (batch stride out_bstride floats); mode 1: out_blk = blocked bf16 view
+// with n_chunks >= (c_total + 1 + 7) / 8 chunks: channels [0, c_total) = the encoder output, channel c_total = 1, rest 0.
+// Gridded sets read the T workspaces written by cnp_encode_hpass on the same stream.
+CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
+                             float eps, int mode, float* out_f32, long long out_bstride, int c_total,
+                             const cnp_blk* out_blk, int n_chunks, cudaStream_t st) {
+  CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0 && (mode == 0 || mode == 1), "encode_fused: bad arguments");
+  CNP_REQUIRE(mode == 0 ? out_f32 != nullptr : (out_blk != nullptr && n_chunks * 8 >= c_total + 1),
+              "encode_fused: output does not match mode %d", mode);
+  if (int rc = ef_check_sets(sets, c_total, "encode_fused")) return rc;
   if (mode == 1) CNP_REQUIRE(out_blk->H == n1 && out_blk->W == n2, "encode_fused: blocked output geometry mismatch");
-  if (max_cols < 1) max_cols = 1;
   const int CP = mode == 1 ? n_chunks * 8 : c_total;
-  const int rows = ef_rows(CP, cmax1, max_cols);
-  const long long smem = ef_smem(CP, cmax1, max_cols, rows);
-  CNP_REQUIRE(smem <= 200 * 1024, "encode_fused: staging of %d channels x %d columns does not fit in shared memory", cmax1, max_cols);
+  const long long smem = ef_smem(mode, CP);
+  CNP_REQUIRE(smem <= 200 * 1024, "encode_fused: %d staged channels do not fit in shared memory", CP);
   static long long attr[2] = {0, 0};
   if (smem > attr[mode] && smem > 48 * 1024) {
     cudaError_t e = mode == 0
@@ -392,10 +499,10 @@ CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int
   if (out_blk) ob = *out_blk;
   if (mode == 0)
     enc_fused_kernel<0><<<grid, NT, smem, st>>>(*sets, start1, n1, start2, n2, res, eps, out_f32, out_bstride, c_total, ob,
-                                                n_chunks, max_cols, cmax1, CP, rows);
+                                                n_chunks, CP);
   else
     enc_fused_kernel<1><<<grid, NT, smem, st>>>(*sets, start1, n1, start2, n2, res, eps, out_f32, out_bstride, c_total, ob,
-                                                n_chunks, max_cols, cmax1, CP, rows);
+                                                n_chunks, CP);
   CNP_LAUNCH_CHECK("enc_fused_kernel");
   return 0;
 }

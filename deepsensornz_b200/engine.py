@@ -413,49 +413,30 @@ class Engine:
         return enc
 
     # ---- fused encoder (enc_fused.cu): all context sets of a task in one launch ----
-    def _fused_cols_hint(self, c: DeviceContext, g: GridSpec, scale2: float) -> int:
-        """Upper bound of the number of input columns inside the band of any 32 consecutive internal-grid columns
-        (shared-memory staging width of the fused encoder), from the host copy of the coordinates."""
-        key = (g, scale2, "cols")
-        if key in c.band_cache:
-            return c.band_cache[key]
-        R = float(np.sqrt(np.float32(2.0 * 104.0) * np.float32(scale2))) * (1.0 + 1e-5)
-        xs = np.sort(c.x_host[1][0].astype(np.float64))
-        gp = g.points(1).astype(np.float64)
-        lo, hi = gp[0::32], gp[np.minimum(np.arange(0, g.n2, 32) + 31, g.n2 - 1)]
-        cnt = np.searchsorted(xs, hi + R, side="right") - np.searchsorted(xs, lo - R, side="left")
-        c.band_cache[key] = int(cnt.max()) + 2
-        return c.band_cache[key]
-
     def _fused_plan(self, batch: DeviceBatch):
-        """Which context sets the fused encoder takes directly, which are encoded once per batch first (sets every task
-        shares), and the staging width; None when a set needs the generic kernels (unsorted or per-task coordinates,
-        bands wider than 32 inputs, more than 8 channels)."""
+        """Which context sets the fused encoder takes per task and which are encoded once per batch first (sets every
+        task shares); None when a set needs the generic kernels (unsorted or per-task coordinates, bands wider than 32
+        inputs, more than 8 channels)."""
         if os.environ.get("CNP_NO_ENC_FUSED") or len(batch.contexts) > 8:
             return None
         cfg, g, B = self.cfg, batch.grid, batch.B
         per_task, static = [], []
-        cols = {"task": 1, "static": 1}
-        cmax = {"task": 1, "static": 1}
         ch = 0
         for k, c in enumerate(batch.contexts):
             Ck = cfg.dim_yc[k]
             if c.y.shape[1] != Ck:
                 raise ValueError(f"context set {k}: expected {Ck} channels, got {c.y.shape[1]}")
-            if Ck > 8:
+            if Ck > 8 or Ck < 1:
                 return None
             s2 = self._scale2(self.module.encoder.set_convs[k].log_scale)
             if c.gridded:
                 if c.x_batched or c.mono[0] == 0 or c.mono[1] == 0 or c.x_host is None or not self._band_hint(c, g, s2):
                     return None
-                where = "static" if (not c.y_batched and B > 1) else "task"
-                cols[where] = max(cols[where], self._fused_cols_hint(c, g, s2))
-                cmax[where] = max(cmax[where], Ck + 1)
-                (static if where == "static" else per_task).append((k, c, ch, s2))
+                (static if (not c.y_batched and B > 1) else per_task).append((k, c, ch, s2))
             else:
                 per_task.append((k, c, ch, s2))
             ch += Ck + 1
-        return dict(per_task=per_task, static=static, cols=cols, cmax=cmax)
+        return dict(per_task=per_task, static=static)
 
     def _enc_tables(self, c: DeviceContext, g: GridSpec, scale2: float):
         """Band tables of a gridded set (band starts, lengths and SetConv weights per internal-grid row / column).  They
@@ -477,53 +458,60 @@ class Engine:
                 self._enc_tabs[key] = ent
         return ent
 
-    def _enc_sets(self, entries, grid: GridSpec, rebase: bool):
+    def _enc_sets(self, entries, grid: GridSpec, B: int, rebase: bool):
         K = _cabi
         sets = K.CnpEncSets()
-        keep = []
         off = 0
+        t_bytes = 0
         for n, (k, c, ch, s2) in enumerate(entries):
             e = sets.s[n]
             Ck = self.cfg.dim_yc[k]
             e.kind, e.C, e.ch_off, e.scale2 = (1 if c.gridded else 0), Ck, (off if rebase else ch), s2
             if c.gridded:
                 e.batched = int(c.y_batched and c.y.shape[0] > 1)
-                e.x1, e.x2 = c.x[0].data_ptr(), c.x[1].data_ptr()
                 e.N1, e.N2 = int(c.x[0].shape[-1]), int(c.x[1].shape[-1])
                 e.mono1, e.mono2 = c.mono
                 e.KB, ti, tw = self._enc_tables(c, grid, s2)
                 e.tab_i, e.tab_w = ti.data_ptr(), tw.data_ptr()
+                T = self._buf(f"enc_T{k}", (B if e.batched else 1, Ck + 1, e.N1, grid.n2))
+                e.T = T.data_ptr()
+                t_bytes += 4 * T.numel()
             else:
                 e.batched = 1
-                e.x1, e.N1 = c.x.data_ptr(), int(c.x.shape[-1])
-            e.y = c.y.data_ptr()
+                e.x1, e.N1 = _ptr(c.x), int(c.x.shape[-1])
+            e.y = _ptr(c.y)
             e.mask = _ptr(c.mask)
             off += Ck + 1
         sets.n_sets = len(entries)
-        return sets, off
+        return sets, off, t_bytes
 
     def _encode_fused(self, batch: DeviceBatch, plan: dict, enc: Optional[torch.Tensor] = None,
                       blk: Optional["_Blk"] = None) -> bool:
-        """Launch the fused encoder into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel).  False when
+        """Launch the fused encoder into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel): horizontal pass
+        of every gridded set, [sets the whole batch shares -> fp32 planes, once,] then the per-task launch.  False when
         the staging does not fit in shared memory (the caller falls back to the per-set kernels)."""
         K = _cabi
         cfg, g, B = self.cfg, batch.grid, batch.B
         lib = K.lib()
         Cin = cfg.in_channels
-        CP = blk.CB * 8 if blk is not None else Cin
-        if lib.cnp_encode_fused_smem_bytes(CP, plan["cmax"]["task"], plan["cols"]["task"]) <= 0:
+        mode = 1 if blk is not None else 0
+        if lib.cnp_encode_fused_smem_bytes(mode, blk.CB * 8 if blk is not None else Cin) <= 0:
             return False
         n_in = lambda c: 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0))
-        entries = list(plan["per_task"])
-        sets, _ = self._enc_sets(entries, g, rebase=False)
+        S = _stream()
+        sets, _, _ = self._enc_sets(plan["per_task"], g, B, rebase=False)
+        gridded = [e for e in plan["per_task"] + plan["static"] if e[1].gridded]
+        if gridded:
+            hsets, _, t_bytes = self._enc_sets(gridded, g, B, rebase=False)
+            self._call("cnp_encode_hpass", C.byref(hsets), B, g.n1, g.n2, S,
+                       work=(0.0, sum(n_in(c) for _, c, _, _ in gridded) + t_bytes))
         if plan["static"]:
-            ssets, Cs = self._enc_sets(plan["static"], g, rebase=True)
-            if lib.cnp_encode_fused_smem_bytes(Cs, plan["cmax"]["static"], plan["cols"]["static"]) <= 0:
+            ssets, Cs, _ = self._enc_sets(plan["static"], g, B, rebase=True)
+            if lib.cnp_encode_fused_smem_bytes(0, Cs) <= 0:
                 return False
             sbuf = self._buf("enc_static", (1, Cs, g.n1, g.n2))
             self._call("cnp_encode_fused", C.byref(ssets), 1, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
-                       _ptr(sbuf), sbuf.stride(0), Cs, None, 0, plan["cols"]["static"], _stream(),
-                       work=(0.0, sum(n_in(c) for _, c, _, _ in plan["static"]) + 4.0 * sbuf.numel()))
+                       _ptr(sbuf), sbuf.stride(0), Cs, None, 0, S, work=(0.0, 4.0 * sbuf.numel()))
             off = 0
             n = sets.n_sets
             for (k, c, ch, s2) in plan["static"]:
@@ -533,16 +521,14 @@ class Engine:
                 off += cfg.dim_yc[k] + 1
                 n += 1
             sets.n_sets = n
-        by_in = sum(n_in(c) for _, c, _, _ in plan["per_task"])
+        by_in = sum(n_in(c) for _, c, _, _ in plan["per_task"] if not c.gridded)
         if blk is not None:
             bv = blk.view()
             self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 1, None, 0,
-                       Cin, C.byref(bv), blk.CB, plan["cols"]["task"], _stream(),
-                       work=(0.0, by_in + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
+                       Cin, C.byref(bv), blk.CB, S, work=(0.0, by_in + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
         else:
             self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
-                       _ptr(enc), enc.stride(0), Cin, None, 0, plan["cols"]["task"], _stream(),
-                       work=(0.0, by_in + 4.0 * enc.numel()))
+                       _ptr(enc), enc.stride(0), Cin, None, 0, S, work=(0.0, by_in + 4.0 * enc.numel()))
         return True
 
     def encode_blocked(self, batch: DeviceBatch) -> Optional["_Blk"]:

@@ -84,22 +84,27 @@ typedef struct cnp_blk {
   int H, W;            /* interior size; planes are (H+4) x (W+4) */
 } cnp_blk;
 
-/* ---- (1') fused SetConv encoder: every context set of a task -> the UNet input, one launch -----------
+/* ---- (1') fused SetConv encoder: every context set of a task -> the UNet input ---------------------------
  * replaces: the whole upstream encoder stack (PrependDensityChannel + SetConv per set + DivideByFirstChannel +
  * Concatenate, neuralprocesses coders/setconv) as reached from ConvNP.loss_fn / predict --
- * nzdownscale/downscaler/train.py:370, validate_ERA.py:88-92.  One CTA = one 8 x 32 tile of the internal grid of one
- * task; gridded sets need monotone coordinates shared by the batch and their band tables (cnp_encode_tables).  kind 2 feeds channels that were encoded once for
- * the whole batch by a first call (B = 1, mode 0) -- static topography / land-mask sets.
+ * nzdownscale/downscaler/train.py:370, validate_ERA.py:88-92.
+ *   cnp_encode_tables : band tables of one gridded set; they depend only on (coordinates, internal grid, length scale)
+ *                       -- build once, keep across steps.
+ *   cnp_encode_hpass  : horizontal band pass of every gridded set of ``sets`` into its T workspace.
+ *   cnp_encode_fused  : one CTA = one 32 x 32 tile of the internal grid of one task: vertical pass of the gridded sets,
+ *                       off-grid sets, precomputed planes (kind 2: channels encoded once for the whole batch by a
+ *                       first call with B = 1, mode 0 -- static topography / land-mask sets), density normalisation.
  * mode 0: fp32 NCHW out_f32 [B][c_total][n1][n2]; mode 1: blocked bf16 out_blk with n_chunks chunks: channels
- * [0, c_total) = encoder output, channel c_total = 1 inside the image (folded first layer, cnp_fold_in_fwd), rest 0. */
+ * [0, c_total) = encoder output, channel c_total = 1 inside the image (folded first layer, cnp_fold_in_fwd), rest 0.
+ * Gridded sets need monotone coordinates shared by the batch. */
 typedef struct cnp_enc_set {
   int kind;            /* 0 off-grid, 1 gridded, 2 precomputed fp32 planes [C][n1][n2] */
-  int C;               /* data channels (<= 8); kind 2: number of planes */
+  int C;               /* data channels (1..8); kind 2: number of planes */
   int ch_off;          /* first output channel (density for kinds 0 / 1) */
-  int batched;         /* gridded: y / mask carry a batch axis (0 = one field for every task) */
-  const float* x1;     /* gridded [N1]; off-grid x [B,2,N] */
-  const float* x2;     /* gridded [N2] */
-  const float* y;      /* gridded [B or 1,C,N1,N2]; off-grid [B,C,N]; may hold NaN (= missing) */
+  int batched;         /* gridded: y / mask / T carry a batch axis (0 = one field for every task) */
+  const float* x1;     /* off-grid x [B,2,N] */
+  const float* x2;     /* unused */
+  const float* y;      /* gridded [B or 1,C,N1,N2]; off-grid [B,C,N]; may hold NaN (= missing); kind 2: the planes */
   const float* mask;   /* gridded [B or 1,1,N1,N2]; off-grid [B,1,N]; or NULL */
   int N1, N2;          /* off-grid: N1 = N */
   int mono1, mono2;    /* +1 ascending, -1 descending */
@@ -107,19 +112,19 @@ typedef struct cnp_enc_set {
   int KB;              /* gridded: band width of the tables (<= 32) */
   const int* tab_i;    /* gridded: [p0 (n1) | len1 (n1) | q0 (n2) | len2 (n2)], from cnp_encode_tables */
   const float* tab_w;  /* gridded: [w1 (KB x n1) | w2 (KB x n2)] */
+  float* T;            /* gridded: horizontal-pass workspace [B or 1][C+1][N1][n2] */
 } cnp_enc_set;
-typedef struct cnp_enc_sets { int n_sets; int pad_; cnp_enc_set s[8]; } cnp_enc_sets;   /* HOST struct, passed by value to the kernel */
-long long cnp_encode_fused_smem_bytes(int channels_staged, int cmax1, int max_cols);   /* -1: does not fit */
-/* band tables of one gridded set: they depend only on (coordinates, internal grid, length scale) -- build once, keep
- * across steps.  tab_i: 2 * (n1 + n2) ints, tab_w: band * (n1 + n2) floats; band = host-side upper bound (<= 32) of
- * the number of inputs within the truncation radius of any grid point along either dimension. */
+typedef struct cnp_enc_sets { int n_sets; int pad_; cnp_enc_set s[8]; } cnp_enc_sets;   /* HOST struct, passed by value to the kernels */
+/* tab_i: 2 * (n1 + n2) ints, tab_w: band * (n1 + n2) floats; band = host-side upper bound (<= 32) of the number of inputs
+ * within the truncation radius of any grid point along either dimension. */
 int cnp_encode_tables(const float* x1 /*[N1]*/, const float* x2 /*[N2]*/, int N1, int N2, int mono1, int mono2,
                       double start1, int n1, double start2, int n2, double res, float scale2, int band,
                       int* tab_i, float* tab_w, cnp_stream_t s);
+long long cnp_encode_fused_smem_bytes(int mode, int channels_staged);   /* -1: does not fit */
+int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cnp_stream_t s);
 int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
                      float eps, int mode, float* out_f32, long long out_bstride, int c_total, const cnp_blk* out_blk,
-                     int n_chunks, int max_cols /* bound of input columns inside the band of 32 grid columns */,
-                     cnp_stream_t s);
+                     int n_chunks, cnp_stream_t s);
 
 typedef struct cnp_conv_out {
   int mode;            /* 0: blocked bf16 (blk), 1: fp32 NCHW (f32, f32_bstride, f32_ch_off) */

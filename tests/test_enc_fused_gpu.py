@@ -43,7 +43,8 @@ def test_fused_encoder_matches_oracle_and_per_set_kernels(static, monkeypatch, n
     calls = _calls(m, monkeypatch)
     batch = m._to_device(task)
     enc = m.engine.encode(batch).clone()
-    assert calls.count("cnp_encode_fused") == (2 if nb > 1 else 1) and "cnp_setconv_enc_grid_fwd" not in calls
+    assert calls.count("cnp_encode_fused") == (2 if nb > 1 else 1) and calls.count("cnp_encode_hpass") == 1
+    assert "cnp_setconv_enc_grid_fwd" not in calls
     ref = _oracle_enc(m, tasks)
     assert enc.shape == ref.shape
     for c in range(ref.shape[1]):               # per channel, so that small channels are held to the same bound
