@@ -33,9 +33,9 @@
 #include <type_traits>
 
 struct cnp_enc_set {
-  int kind;          // 0 off-grid, 1 gridded, 2 precomputed fp32 planes [C][n1][n2] (already normalised)
-  int C;             // data channels (kind 2: number of planes)
-  int ch_off;        // first output channel (the density channel for kinds 0 / 1)
+  int kind;          // 0 off-grid, 1 gridded
+  int C;             // data channels (1..8)
+  int ch_off;        // first output channel (the density channel)
   int batched;       // y (and mask, T) carry a batch axis; 0: one field shared by every task
   const float* x1;   // off-grid: x [B,2,N]
   const float* x2;   // unused by the kernels (gridded coordinates enter through the tables)
@@ -57,9 +57,10 @@ struct cnp_enc_sets {
 
 namespace {
 
-constexpr int TI = 32, TJ = 32, NT = 256, RPT = 4;   // tile rows / cols, threads, rows per thread
+constexpr int TI = 16, TJ = 32, NT = 128, RPT = 4;   // tile rows / cols, threads, rows per thread
+constexpr int NPIX = TI * TJ;
 constexpr int KBMAX = 32;    // max band (inputs within R of one grid row / column)
-constexpr int OGC = 256;     // off-grid points per chunk (one per thread)
+constexpr int OGC = NT;      // off-grid points per chunk (one per thread)
 constexpr int OGS = 64;      // off-grid points whose weights are staged at a time
 constexpr int MAXC1 = 9;     // max channels incl. density of one set
 
@@ -104,28 +105,30 @@ template <int C>
 __device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p, int j, int n1, int n2) {
   const int N1 = st.N1, N2 = st.N2;
   const int q0 = __ldg(st.tab_i + 2 * n1 + j), len = __ldg(st.tab_i + 2 * n1 + n2 + j);
-  const float* w2 = st.tab_w + (size_t)st.KB * n1 + j;
-  const size_t plane = (size_t)N1 * N2;
-  const float* yb = st.y + (size_t)b * C * plane + (size_t)p * N2 + q0;
-  const float* mb = st.mask ? st.mask + (size_t)b * plane + (size_t)p * N2 + q0 : nullptr;
+  const float* w2 = st.tab_w + st.KB * n1 + j;
+  const int plane = N1 * N2;                       // (a context field has far fewer than 2^31 cells)
+  const float* yb = st.y + (size_t)b * C * plane + p * N2 + q0;
+  const float* mb = st.mask ? st.mask + (size_t)b * plane + p * N2 + q0 : nullptr;
   float acc[C + 1];
 #pragma unroll
   for (int c = 0; c <= C; ++c) acc[c] = 0.f;
+#pragma unroll 4
   for (int k = 0; k < len; ++k) {
-    const float w = __ldg(w2 + (size_t)k * n2);
+    const float w = __ldg(w2 + k * n2);
     float valid = mb ? __ldg(mb + k) : 1.f;
     float v[C];
     bool nan_any = false;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { v[c] = __ldg(yb + (size_t)c * plane + k); nan_any |= isnan(v[c]); }
+    for (int c = 0; c < C; ++c) { v[c] = __ldg(yb + c * plane + k); nan_any |= isnan(v[c]); }
     if (nan_any) valid = 0.f;
     acc[0] = fmaf(valid, w, acc[0]);
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[1 + c] = fmaf(nan_any ? 0.f : v[c] * valid, w, acc[1 + c]);
   }
-  float* T = st.T + (((size_t)b * (C + 1)) * N1 + p) * n2 + j;
+  const int tplane = N1 * n2;
+  float* T = st.T + (size_t)b * (C + 1) * tplane + p * n2 + j;
 #pragma unroll
-  for (int c = 0; c <= C; ++c) T[(size_t)c * N1 * n2] = acc[c];
+  for (int c = 0; c <= C; ++c) T[c * tplane] = acc[c];
 }
 
 __global__ void __launch_bounds__(256)
@@ -133,10 +136,10 @@ enc_hpass_kernel(const __grid_constant__ cnp_hpass_args a) {
   int k = 0;
   while (k + 1 < a.S.n_sets && (int)blockIdx.x >= a.blk0[k + 1]) ++k;
   const cnp_enc_set& st = a.S.s[k];
-  const long long e = (long long)(blockIdx.x - a.blk0[k]) * 256 + threadIdx.x;
-  const long long per_b = (long long)st.N1 * a.n2;
+  const int e = (int)(blockIdx.x - a.blk0[k]) * 256 + threadIdx.x;
+  const int per_b = st.N1 * a.n2;
   if (e >= per_b * a.nb[k]) return;
-  const int b = (int)(e / per_b), r = (int)(e - (long long)b * per_b), p = r / a.n2, j = r - p * a.n2;
+  const int b = e / per_b, r = e - b * per_b, p = r / a.n2, j = r - p * a.n2;
   switch (st.C) {
     case 1: hpass_elem<1>(st, b, p, j, a.n1, a.n2); break;
     case 2: hpass_elem<2>(st, b, p, j, a.n1, a.n2); break;
@@ -150,26 +153,24 @@ enc_hpass_kernel(const __grid_constant__ cnp_hpass_args a) {
 }
 
 // =====================================================================================================================
-// launch 2: vertical pass + off-grid sets + precomputed planes -> the UNet input
+// launch 2: vertical pass + off-grid sets -> the UNet input
 // =====================================================================================================================
-template <typename OT> __device__ __forceinline__ void put(OT* o, float v);
-template <> __device__ __forceinline__ void put<float>(float* o, float v) { *o = v; }
-template <> __device__ __forceinline__ void put<__nv_bfloat16>(__nv_bfloat16* o, float v) { *o = __float2bfloat16(v); }
-
-// store one set's result for the thread's RPT pixels: density first, data divided by (density + eps)
-template <int C, typename OT>
-__device__ __forceinline__ void store_set(OT* outs, int ch_off, int pix0, const float (&acc)[RPT][MAXC1], float eps) {
+// store one set's result for the thread's RPT pixels: density first, data times 1 / (density + eps)
+template <int C>
+__device__ __forceinline__ void store_set(float* __restrict__ outs, int ch_off, int pix0, const float (&acc)[RPT][MAXC1],
+                                          float eps) {
+  float* o = outs + ch_off * NPIX + pix0;
 #pragma unroll
   for (int e = 0; e < RPT; ++e) {
-    const float dens = acc[e][0], den = dens + eps;
-    put<OT>(outs + (size_t)ch_off * (TI * TJ) + pix0 + e * TJ, dens);
+    const float dens = acc[e][0], inv = 1.0f / (dens + eps);
+    o[e * TJ] = dens;
 #pragma unroll
-    for (int c = 1; c <= C; ++c) put<OT>(outs + (size_t)(ch_off + c) * (TI * TJ) + pix0 + e * TJ, acc[e][c] / den);
+    for (int c = 1; c <= C; ++c) o[c * NPIX + e * TJ] = acc[e][c] * inv;
   }
 }
 
 template <int C>
-__device__ __forceinline__ void vpass(const cnp_enc_set& st, int b, int n1, int n2, int j, bool col_ok, const int (&p0)[RPT],
+__device__ __forceinline__ void vpass(const cnp_enc_set& st, int b, int n2, int j, bool col_ok, const int (&p0)[RPT],
                                       const int (&len)[RPT], const float* __restrict__ w1t, int row0,
                                       float (&acc)[RPT][MAXC1]) {
   // union band of the thread's rows (monotone coordinates: bands of adjacent rows overlap almost entirely)
@@ -177,16 +178,19 @@ __device__ __forceinline__ void vpass(const cnp_enc_set& st, int b, int n1, int 
 #pragma unroll
   for (int e = 0; e < RPT; ++e) if (len[e] > 0) { lo = min(lo, p0[e]); hi = max(hi, p0[e] + len[e]); }
   if (!col_ok || hi <= lo) return;
-  const int N1 = st.N1, KBs = st.KB;
-  const float* T = st.T + ((size_t)(st.batched ? b : 0) * (C + 1)) * N1 * n2 + j;
-  for (int r = lo; r < hi; ++r) {
+  const int KBs = st.KB, tplane = st.N1 * n2;
+  const float* T = st.T + (size_t)(st.batched ? b : 0) * (C + 1) * tplane + lo * n2 + j;
+  const float* wb[RPT];
+#pragma unroll
+  for (int e = 0; e < RPT; ++e) wb[e] = w1t + (row0 + e) * KBs - p0[e];
+#pragma unroll 2
+  for (int r = lo; r < hi; ++r, T += n2) {
     float t[C + 1];
 #pragma unroll
-    for (int c = 0; c <= C; ++c) t[c] = __ldg(T + ((size_t)c * N1 + r) * n2);
+    for (int c = 0; c <= C; ++c) t[c] = __ldg(T + c * tplane);
 #pragma unroll
     for (int e = 0; e < RPT; ++e) {
-      const int kk = r - p0[e];
-      const float w = ((unsigned)kk < (unsigned)len[e]) ? w1t[(row0 + e) * KBs + kk] : 0.f;
+      const float w = ((unsigned)(r - p0[e]) < (unsigned)len[e]) ? wb[e][r] : 0.f;
 #pragma unroll
       for (int c = 0; c <= C; ++c) acc[e][c] = fmaf(w, t[c], acc[e][c]);
     }
@@ -223,156 +227,155 @@ __device__ __forceinline__ void ogacc(const float* __restrict__ ys, const float*
     default: { constexpr int CC = 8; __VA_ARGS__; } break; \
   }
 
+// One CTA = one 16 x 32 tile of the internal grid and TB consecutive tasks; one thread = 4 adjacent rows of one column.
+// Gridded sets that every task shares (batched = 0) are computed for the first task of the CTA only: their channels stay
+// in the shared-memory staging tile while the per-task sets of the following tasks overwrite theirs.
 template <int MODE>   // 0: fp32 NCHW output, 1: blocked bf16 output with the constant-1 channel
-__global__ void __launch_bounds__(NT, 3)
-enc_fused_kernel(const __grid_constant__ cnp_enc_sets S, double start1, int n1, double start2, int n2, double res,
-                 float eps, float* __restrict__ out_f32, long long out_bs, int c_total, cnp_blk ob, int n_chunks, int CP) {
-  using OT = typename std::conditional<MODE == 0, float, __nv_bfloat16>::type;
-  extern __shared__ __align__(16) unsigned char sm_raw[];
-  OT* outs = reinterpret_cast<OT*>(sm_raw);                                        // [CP][TI*TJ]
-  float* scr = reinterpret_cast<float*>(sm_raw + (((size_t)CP * TI * TJ * sizeof(OT) + 15) & ~(size_t)15));
+__global__ void __launch_bounds__(NT, 4)
+enc_fused_kernel(const __grid_constant__ cnp_enc_sets S, int B, int TB, double start1, int n1, double start2, int n2,
+                 double res, float eps, float* __restrict__ out_f32, long long out_bs, int c_total, cnp_blk ob,
+                 int n_chunks, int CP) {
+  extern __shared__ __align__(16) float sm[];
+  float* outs = sm;                                // [CP][NPIX] fp32 staging of the tile's channels
+  float* scr = sm + CP * NPIX;                     // per-set scratch
   __shared__ float g1s[TI], g2s[TJ];
-  __shared__ int warp_cnt[8];
+  __shared__ int warp_cnt[NT / 32];
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int b = blockIdx.z, i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
   const int row0 = ty * RPT, j = j0 + tx;
   const bool col_ok = j < n2;
   const int pix0 = row0 * TJ + tx;                 // tile-local pixel of the thread's first row
   if (tid < TI) g1s[tid] = cnp_grid_pt(start1, res, min(i0 + tid, n1 - 1));
   if (tid >= 32 && tid < 32 + TJ) g2s[tid - 32] = cnp_grid_pt(start2, res, min(j0 + tid - 32, n2 - 1));
-  for (int c = 0; c < CP; ++c)
+  for (int c = 0; c < CP; ++c) {
+    const float v = (MODE == 1 && c == c_total) ? 1.f : 0.f;   // constant-1 channel of the folded first layer
 #pragma unroll
-    for (int e = 0; e < RPT; ++e) put<OT>(outs + (size_t)c * (TI * TJ) + pix0 + e * TJ, 0.f);
+    for (int e = 0; e < RPT; ++e) outs[c * NPIX + pix0 + e * TJ] = v;
+  }
 
-  for (int k = 0; k < S.n_sets; ++k) {
-    const cnp_enc_set& st = S.s[k];
-    const int C = st.C;
-    __syncthreads();                               // scratch of the previous set is free; g1s / g2s are visible
-    if (st.kind == 2) {
-      if (col_ok)
-        for (int c = 0; c < C; ++c)
+  for (int bl = 0; bl < TB; ++bl) {
+    const int b = blockIdx.z * TB + bl;
+    if (b >= B) break;
+    for (int k = 0; k < S.n_sets; ++k) {
+      const cnp_enc_set& st = S.s[k];
+      const int C = st.C;
+      if (st.kind == 1 && !st.batched && bl > 0) continue;      // shared field: already in the staging tile
+      __syncthreads();                             // scratch of the previous set is free; g1s / g2s are visible
+      float acc[RPT][MAXC1];
 #pragma unroll
-          for (int e = 0; e < RPT; ++e) {
-            const int i = i0 + row0 + e;
-            if (i < n1) put<OT>(outs + (size_t)(st.ch_off + c) * (TI * TJ) + pix0 + e * TJ,
-                                __ldg(st.y + ((size_t)c * n1 + i) * n2 + j));
+      for (int e = 0; e < RPT; ++e)
+#pragma unroll
+        for (int c = 0; c < MAXC1; ++c) acc[e][c] = 0.f;
+
+      if (st.kind == 1) {
+        // ---------------- gridded set: vertical band pass over the horizontal-pass workspace ----------------
+        const int KBs = st.KB;
+        float* w1t = scr;                          // [TI][KBs] weights of the tile's rows
+        for (int e = tid; e < TI * KBs; e += NT) {
+          const int r = e / KBs, kk = e - r * KBs;
+          w1t[e] = __ldg(st.tab_w + kk * n1 + min(i0 + r, n1 - 1));
+        }
+        int p0[RPT], len[RPT];
+#pragma unroll
+        for (int e = 0; e < RPT; ++e) {
+          const int i = i0 + row0 + e;
+          p0[e] = __ldg(st.tab_i + min(i, n1 - 1));
+          len[e] = (i < n1) ? __ldg(st.tab_i + n1 + min(i, n1 - 1)) : 0;
+        }
+        __syncthreads();
+        CNP_SWITCH_C(C, vpass<CC>(st, b, n2, j, col_ok, p0, len, w1t, row0, acc); store_set<CC>(outs, st.ch_off, pix0, acc, eps))
+      } else {
+        // ---------------- off-grid set ----------------
+        // one global round trip per chunk of 128 points: every thread loads its point (coordinates, all channels,
+        // mask), the points that can touch the tile are compacted in order into shared memory, their separable weights
+        // are staged 64 points at a time and every thread sums its own pixels
+        const float scale2 = st.scale2;
+        const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+        const int N = st.N1;
+        float* px = scr;                     // [2][OGC] compacted coordinates
+        float* ys = px + 2 * OGC;            // [MAXC1][OGC] compacted [valid ; y * valid]
+        float* w1s = ys + MAXC1 * OGC;       // [OGS][TI]
+        float* w2s = w1s + OGS * TI;         // [OGS][TJ + 1]
+        const float a1 = g1s[0], b1 = g1s[TI - 1], a2 = g2s[0], b2 = g2s[TJ - 1];
+        const float lo1 = fminf(a1, b1) - R, hi1 = fmaxf(a1, b1) + R, lo2 = fminf(a2, b2) - R, hi2 = fmaxf(a2, b2) + R;
+        const float* xb = st.x1 + (size_t)b * 2 * N;
+        const float* yb = st.y + (size_t)b * C * N;
+        const float* mb = st.mask ? st.mask + (size_t)b * N : nullptr;
+        for (int c0 = 0; c0 < N; c0 += OGC) {
+          const int n = c0 + tid;
+          bool keep = false;
+          float p1 = 0.f, p2 = 0.f, valid = 0.f, v[MAXC1 - 1];
+          if (n < N) {
+            p1 = __ldg(xb + n); p2 = __ldg(xb + N + n);
+            valid = mb ? __ldg(mb + n) : 1.f;
+            bool nan_any = false;
+#pragma unroll
+            for (int c = 0; c < MAXC1 - 1; ++c)
+              if (c < C) { v[c] = __ldg(yb + c * N + n); nan_any |= isnan(v[c]); }
+            if (nan_any) valid = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXC1 - 1; ++c)
+              if (c < C) v[c] = nan_any ? 0.f : v[c] * valid;
+            keep = (p1 >= lo1) && (p1 <= hi1) && (p2 >= lo2) && (p2 <= hi2);
           }
-      continue;
-    }
-    float acc[RPT][MAXC1];
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (c0 > 0) __syncthreads();     // the previous chunk's consumers are done
+          if (tx == 0) warp_cnt[ty] = __popc(bal);
+          __syncthreads();
+          int base = 0, total = 0;
 #pragma unroll
-    for (int e = 0; e < RPT; ++e)
+          for (int w = 0; w < NT / 32; ++w) { if (w < ty) base += warp_cnt[w]; total += warp_cnt[w]; }
+          if (keep) {
+            const int m = base + __popc(bal & ((1u << tx) - 1u));
+            px[m] = p1; px[OGC + m] = p2; ys[m] = valid;
 #pragma unroll
-      for (int c = 0; c < MAXC1; ++c) acc[e][c] = 0.f;
-
-    if (st.kind == 1) {
-      // ---------------- gridded set: vertical band pass over the horizontal-pass workspace ----------------
-      const int KBs = st.KB;
-      float* w1t = scr;                            // [TI][KBs] weights of the tile's rows
-      for (int e = tid; e < TI * KBs; e += NT) {
-        const int r = e / KBs, kk = e - r * KBs;
-        w1t[e] = __ldg(st.tab_w + (size_t)kk * n1 + min(i0 + r, n1 - 1));
+            for (int c = 0; c < MAXC1 - 1; ++c)
+              if (c < C) ys[(1 + c) * OGC + m] = v[c];
+          }
+          for (int m0 = 0; m0 < total; m0 += OGS) {
+            const int nm = min(OGS, total - m0);
+            __syncthreads();               // compacted points visible / previous weights consumed
+            for (int e = tid; e < nm * TJ; e += NT) {
+              const int m = e >> 5, jj = e & 31;
+              w2s[m * (TJ + 1) + jj] = cnp_rbf(px[OGC + m0 + m], g2s[jj], scale2);
+              if (jj < TI) w1s[m * TI + jj] = cnp_rbf(px[m0 + m], g1s[jj], scale2);
+            }
+            __syncthreads();
+            CNP_SWITCH_C(C, ogacc<CC>(ys, w1s, w2s, m0, nm, row0, tx, acc))
+          }
+        }
+        CNP_SWITCH_C(C, store_set<CC>(outs, st.ch_off, pix0, acc, eps))
       }
-      int p0[RPT], len[RPT];
+    }
+    // ---- write the task's tile (every thread reads back only what it wrote itself: no barrier) ----
+    if (!col_ok) continue;
+    if (MODE == 0) {
 #pragma unroll
       for (int e = 0; e < RPT; ++e) {
         const int i = i0 + row0 + e;
-        p0[e] = __ldg(st.tab_i + min(i, n1 - 1));
-        len[e] = (i < n1) ? __ldg(st.tab_i + n1 + min(i, n1 - 1)) : 0;
+        if (i >= n1) continue;
+        float* o = out_f32 + (size_t)b * out_bs + i * n2 + j;
+        const int plane = n1 * n2;
+        for (int c = 0; c < c_total; ++c) o[c * plane] = outs[c * NPIX + pix0 + e * TJ];
       }
-      __syncthreads();
-      CNP_SWITCH_C(C, vpass<CC>(st, b, n1, n2, j, col_ok, p0, len, w1t, row0, acc); store_set<CC, OT>(outs, st.ch_off, pix0, acc, eps))
     } else {
-      // ---------------- off-grid set ----------------
-      // one global round trip per chunk of 256 points: every thread loads its point (coordinates, all channels, mask),
-      // the points that can touch the tile are compacted in order into shared memory, their separable weights are
-      // staged 64 points at a time and every thread sums its own pixels
-      const float scale2 = st.scale2;
-      const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
-      const int N = st.N1;
-      float* px = scr;                     // [2][OGC] compacted coordinates
-      float* ys = px + 2 * OGC;            // [MAXC1][OGC] compacted [valid ; y * valid]
-      float* w1s = ys + MAXC1 * OGC;       // [OGS][TI]
-      float* w2s = w1s + OGS * TI;         // [OGS][TJ + 1]
-      const float a1 = g1s[0], b1 = g1s[TI - 1], a2 = g2s[0], b2 = g2s[TJ - 1];
-      const float lo1 = fminf(a1, b1) - R, hi1 = fmaxf(a1, b1) + R, lo2 = fminf(a2, b2) - R, hi2 = fmaxf(a2, b2) + R;
-      const float* xb = st.x1 + (size_t)b * 2 * N;
-      const float* yb = st.y + (size_t)b * C * N;
-      const float* mb = st.mask ? st.mask + (size_t)b * N : nullptr;
-      for (int c0 = 0; c0 < N; c0 += OGC) {
-        const int n = c0 + tid;
-        bool keep = false;
-        float p1 = 0.f, p2 = 0.f, valid = 0.f, v[MAXC1 - 1];
-        if (n < N) {
-          p1 = __ldg(xb + n); p2 = __ldg(xb + N + n);
-          valid = mb ? __ldg(mb + n) : 1.f;
-          bool nan_any = false;
+      const int Hp = ob.H + 4, Wp = ob.W + 4;
+      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ob.base) + (size_t)b * ob.bstride;
 #pragma unroll
-          for (int c = 0; c < MAXC1 - 1; ++c)
-            if (c < C) { v[c] = __ldg(yb + (size_t)c * N + n); nan_any |= isnan(v[c]); }
-          if (nan_any) valid = 0.f;
-#pragma unroll
-          for (int c = 0; c < MAXC1 - 1; ++c)
-            if (c < C) v[c] = nan_any ? 0.f : v[c] * valid;
-          keep = (p1 >= lo1) && (p1 <= hi1) && (p2 >= lo2) && (p2 <= hi2);
+      for (int e = 0; e < RPT; ++e) {
+        const int i = i0 + row0 + e;
+        if (i >= n1) continue;
+        const float* o = outs + pix0 + e * TJ;
+        for (int ch = 0; ch < n_chunks; ++ch, o += 8 * NPIX) {
+          uint4 pk;
+          __nv_bfloat162 h;
+          h = __floats2bfloat162_rn(o[0], o[NPIX]);             pk.x = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(o[2 * NPIX], o[3 * NPIX]);  pk.y = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(o[4 * NPIX], o[5 * NPIX]);  pk.z = *reinterpret_cast<uint32_t*>(&h);
+          h = __floats2bfloat162_rn(o[6 * NPIX], o[7 * NPIX]);  pk.w = *reinterpret_cast<uint32_t*>(&h);
+          *reinterpret_cast<uint4*>(base + (((size_t)(ob.cb_off + ch) * Hp + i + 2) * Wp + j + 2) * 8) = pk;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (c0 > 0) __syncthreads();       // the previous chunk's consumers are done
-        if (tx == 0) warp_cnt[ty] = __popc(bal);
-        __syncthreads();
-        int base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { if (w < ty) base += warp_cnt[w]; total += warp_cnt[w]; }
-        if (keep) {
-          const int m = base + __popc(bal & ((1u << tx) - 1u));
-          px[m] = p1; px[OGC + m] = p2; ys[m] = valid;
-#pragma unroll
-          for (int c = 0; c < MAXC1 - 1; ++c)
-            if (c < C) ys[(1 + c) * OGC + m] = v[c];
-        }
-        for (int m0 = 0; m0 < total; m0 += OGS) {
-          const int nm = min(OGS, total - m0);
-          __syncthreads();                 // compacted points visible / previous weights consumed
-          for (int e = tid; e < nm * TJ; e += NT) {
-            const int m = e / TJ, jj = e - m * TJ;
-            w2s[m * (TJ + 1) + jj] = cnp_rbf(px[OGC + m0 + m], g2s[jj], scale2);
-            w1s[m * TI + jj] = cnp_rbf(px[m0 + m], g1s[jj], scale2);
-          }
-          __syncthreads();
-          CNP_SWITCH_C(C, ogacc<CC>(ys, w1s, w2s, m0, nm, row0, tx, acc))
-        }
-      }
-      CNP_SWITCH_C(C, store_set<CC, OT>(outs, st.ch_off, pix0, acc, eps))
-    }
-  }
-
-  if (!col_ok) return;
-  if (MODE == 0) {
-#pragma unroll
-    for (int e = 0; e < RPT; ++e) {
-      const int i = i0 + row0 + e;
-      if (i >= n1) continue;
-      float* o = out_f32 + (size_t)b * out_bs + (size_t)i * n2 + j;
-      for (int c = 0; c < c_total; ++c) o[(size_t)c * n1 * n2] = (float)outs[(size_t)c * (TI * TJ) + pix0 + e * TJ];
-    }
-  } else {
-    const int Hp = ob.H + 4, Wp = ob.W + 4;
-    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ob.base) + (size_t)b * ob.bstride;
-    const __nv_bfloat16 one = __float2bfloat16(1.f);
-#pragma unroll
-    for (int e = 0; e < RPT; ++e) {
-      const int i = i0 + row0 + e;
-      if (i >= n1) continue;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        __align__(16) __nv_bfloat16 pk[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int c = ch * 8 + q;   // channel c_total: constant 1 of the folded first layer (0 in the pad, like the image)
-          pk[q] = (c == c_total) ? one : reinterpret_cast<const __nv_bfloat16*>(outs)[(size_t)c * (TI * TJ) + pix0 + e * TJ];
-        }
-        *reinterpret_cast<uint4*>(base + (((size_t)(ob.cb_off + ch) * Hp + i + 2) * Wp + j + 2) * 8) =
-            *reinterpret_cast<const uint4*>(pk);
       }
     }
   }
@@ -415,16 +418,16 @@ CNP_API int cnp_encode_tables(const float* x1, const float* x2, int N1, int N2, 
   return 0;
 }
 
-static long long ef_smem(int mode, int channels_staged) {
+static long long ef_smem(int channels_staged) {
   const long long og_f = 2LL * OGC + (long long)MAXC1 * OGC + OGS * TI + OGS * (TJ + 1);
   const long long grid_f = (long long)TI * KBMAX;
-  const long long outs_b = (((long long)channels_staged * TI * TJ * (mode == 0 ? 4 : 2)) + 15) & ~15LL;
-  return outs_b + (grid_f > og_f ? grid_f : og_f) * 4;
+  return ((long long)channels_staged * NPIX + (grid_f > og_f ? grid_f : og_f)) * 4;
 }
 
 // Shared memory of one cnp_encode_fused launch (bytes); -1 when it cannot fit.
 CNP_API long long cnp_encode_fused_smem_bytes(int mode, int channels_staged) {
-  const long long bytes = ef_smem(mode, channels_staged);
+  (void)mode;
+  const long long bytes = ef_smem(channels_staged);
   return bytes <= 200 * 1024 ? bytes : -1;
 }
 
@@ -432,19 +435,19 @@ static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who)
   CNP_REQUIRE(sets && sets->n_sets >= 1 && sets->n_sets <= 8, "%s: need 1..8 context sets", who);
   for (int k = 0; k < sets->n_sets; ++k) {
     const cnp_enc_set& s = sets->s[k];
-    CNP_REQUIRE(s.kind >= 0 && s.kind <= 2 && s.C >= 0 && s.ch_off >= 0, "%s: set %d malformed", who, k);
-    CNP_REQUIRE(s.ch_off + s.C + (s.kind == 2 ? 0 : 1) <= c_total, "%s: set %d exceeds %d channels", who, k, c_total);
-    if (s.kind != 2) CNP_REQUIRE(s.C >= 1 && s.C <= MAXC1 - 1, "%s: set %d needs 1..%d channels", who, k, MAXC1 - 1);
+    CNP_REQUIRE((s.kind == 0 || s.kind == 1) && s.ch_off >= 0, "%s: set %d malformed", who, k);
+    CNP_REQUIRE(s.C >= 1 && s.C <= MAXC1 - 1, "%s: set %d needs 1..%d channels", who, k, MAXC1 - 1);
+    CNP_REQUIRE(s.ch_off + s.C + 1 <= c_total, "%s: set %d exceeds %d channels", who, k, c_total);
     if (s.kind == 1)
-      CNP_REQUIRE(s.y && s.tab_i && s.tab_w && s.T && s.KB >= 1 && s.KB <= KBMAX && s.N1 > 0 && s.N2 > 0,
+      CNP_REQUIRE(s.y && s.tab_i && s.tab_w && s.T && s.KB >= 1 && s.KB <= KBMAX && s.N1 > 0 && s.N2 > 0 &&
+                      (long long)s.N1 * s.N2 < (1LL << 30),
                   "%s: gridded set %d needs band tables and a horizontal-pass workspace", who, k);
     if (s.kind == 0) CNP_REQUIRE(s.N1 == 0 || (s.x1 && s.y), "%s: off-grid set %d has null inputs", who, k);
-    if (s.kind == 2) CNP_REQUIRE(s.y != nullptr, "%s: plane set %d has no planes", who, k);
   }
   return 0;
 }
 
-// Launch 1: horizontal band pass of every gridded set of ``sets`` (other kinds are skipped) into their T workspaces
+// Launch 1: horizontal band pass of every gridded set of ``sets`` (off-grid sets are skipped) into their T workspaces
 // ([B or 1][C+1][N1][n2] floats each).
 CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_hpass: bad arguments");
@@ -452,21 +455,23 @@ CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cu
   cnp_hpass_args a;
   memset(&a, 0, sizeof(a));
   a.n1 = n1; a.n2 = n2;
-  int n = 0, blocks = 0;
+  int n = 0;
+  long long blocks = 0;
   for (int k = 0; k < sets->n_sets; ++k) {
     const cnp_enc_set& s = sets->s[k];
     if (s.kind != 1) continue;
     a.S.s[n] = s;
     a.nb[n] = s.batched ? B : 1;
-    a.blk0[n] = blocks;
+    a.blk0[n] = (int)blocks;
     const long long elems = (long long)a.nb[n] * s.N1 * n2;
-    blocks += (int)((elems + 255) / 256);
+    CNP_REQUIRE(elems < (1LL << 31), "encode_hpass: set %d is too large", k);
+    blocks += (elems + 255) / 256;
     ++n;
   }
   if (n == 0) return 0;
   a.S.n_sets = n;
-  a.blk0[n] = blocks;
-  enc_hpass_kernel<<<blocks, 256, 0, st>>>(a);
+  a.blk0[n] = (int)blocks;
+  enc_hpass_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
   CNP_LAUNCH_CHECK("enc_hpass_kernel");
   return 0;
 }
@@ -483,7 +488,7 @@ CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int
   if (int rc = ef_check_sets(sets, c_total, "encode_fused")) return rc;
   if (mode == 1) CNP_REQUIRE(out_blk->H == n1 && out_blk->W == n2, "encode_fused: blocked output geometry mismatch");
   const int CP = mode == 1 ? n_chunks * 8 : c_total;
-  const long long smem = ef_smem(mode, CP);
+  const long long smem = ef_smem(CP);
   CNP_REQUIRE(smem <= 200 * 1024, "encode_fused: %d staged channels do not fit in shared memory", CP);
   static long long attr[2] = {0, 0};
   if (smem > attr[mode] && smem > 48 * 1024) {
@@ -493,16 +498,21 @@ CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int
     if (e != cudaSuccess) { cnp_set_error("encode_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr[mode] = smem;
   }
-  dim3 grid(cnp_cdiv(n2, TJ), cnp_cdiv(n1, TI), B);
+  // tasks per CTA: sets that every task shares are encoded once per CTA, so larger batches walk 4 tasks per CTA
+  // (B = 16 at 304^2: 760 CTAs of 128 threads, one wave on 148 SMs)
+  bool shared_sets = false;
+  for (int k = 0; k < sets->n_sets; ++k) shared_sets |= (sets->s[k].kind == 1 && !sets->s[k].batched);
+  const int TB = (shared_sets && B >= 8) ? 4 : (shared_sets && B >= 2 ? 2 : 1);
+  dim3 grid(cnp_cdiv(n2, TJ), cnp_cdiv(n1, TI), cnp_cdiv(B, TB));
   cnp_blk ob;
   memset(&ob, 0, sizeof(ob));
   if (out_blk) ob = *out_blk;
   if (mode == 0)
-    enc_fused_kernel<0><<<grid, NT, smem, st>>>(*sets, start1, n1, start2, n2, res, eps, out_f32, out_bstride, c_total, ob,
-                                                n_chunks, CP);
+    enc_fused_kernel<0><<<grid, NT, smem, st>>>(*sets, B, TB, start1, n1, start2, n2, res, eps, out_f32, out_bstride,
+                                                c_total, ob, n_chunks, CP);
   else
-    enc_fused_kernel<1><<<grid, NT, smem, st>>>(*sets, start1, n1, start2, n2, res, eps, out_f32, out_bstride, c_total, ob,
-                                                n_chunks, CP);
+    enc_fused_kernel<1><<<grid, NT, smem, st>>>(*sets, B, TB, start1, n1, start2, n2, res, eps, out_f32, out_bstride,
+                                                c_total, ob, n_chunks, CP);
   CNP_LAUNCH_CHECK("enc_fused_kernel");
   return 0;
 }

@@ -458,17 +458,16 @@ class Engine:
                 self._enc_tabs[key] = ent
         return ent
 
-    def _enc_sets(self, entries, grid: GridSpec, B: int, rebase: bool):
+    def _enc_sets(self, entries, grid: GridSpec, B: int):
         K = _cabi
         sets = K.CnpEncSets()
-        off = 0
         t_bytes = 0
         for n, (k, c, ch, s2) in enumerate(entries):
             e = sets.s[n]
             Ck = self.cfg.dim_yc[k]
-            e.kind, e.C, e.ch_off, e.scale2 = (1 if c.gridded else 0), Ck, (off if rebase else ch), s2
+            e.kind, e.C, e.ch_off, e.scale2 = (1 if c.gridded else 0), Ck, ch, s2
             if c.gridded:
-                e.batched = int(c.y_batched and c.y.shape[0] > 1)
+                e.batched = int(c.y_batched and B > 1)
                 e.N1, e.N2 = int(c.x[0].shape[-1]), int(c.x[1].shape[-1])
                 e.mono1, e.mono2 = c.mono
                 e.KB, ti, tw = self._enc_tables(c, grid, s2)
@@ -481,15 +480,14 @@ class Engine:
                 e.x1, e.N1 = _ptr(c.x), int(c.x.shape[-1])
             e.y = _ptr(c.y)
             e.mask = _ptr(c.mask)
-            off += Ck + 1
         sets.n_sets = len(entries)
-        return sets, off, t_bytes
+        return sets, t_bytes
 
     def _encode_fused(self, batch: DeviceBatch, plan: dict, enc: Optional[torch.Tensor] = None,
                       blk: Optional["_Blk"] = None) -> bool:
-        """Launch the fused encoder into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel): horizontal pass
-        of every gridded set, [sets the whole batch shares -> fp32 planes, once,] then the per-task launch.  False when
-        the staging does not fit in shared memory (the caller falls back to the per-set kernels)."""
+        """Launch the fused encoder into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel): the horizontal
+        pass of every gridded set, then the per-tile launch.  False when the staging does not fit in shared memory (the
+        caller falls back to the per-set kernels)."""
         K = _cabi
         cfg, g, B = self.cfg, batch.grid, batch.B
         lib = K.lib()
@@ -499,36 +497,19 @@ class Engine:
             return False
         n_in = lambda c: 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0))
         S = _stream()
-        sets, _, _ = self._enc_sets(plan["per_task"], g, B, rebase=False)
-        gridded = [e for e in plan["per_task"] + plan["static"] if e[1].gridded]
-        if gridded:
-            hsets, _, t_bytes = self._enc_sets(gridded, g, B, rebase=False)
-            self._call("cnp_encode_hpass", C.byref(hsets), B, g.n1, g.n2, S,
-                       work=(0.0, sum(n_in(c) for _, c, _, _ in gridded) + t_bytes))
-        if plan["static"]:
-            ssets, Cs, _ = self._enc_sets(plan["static"], g, B, rebase=True)
-            if lib.cnp_encode_fused_smem_bytes(0, Cs) <= 0:
-                return False
-            sbuf = self._buf("enc_static", (1, Cs, g.n1, g.n2))
-            self._call("cnp_encode_fused", C.byref(ssets), 1, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
-                       _ptr(sbuf), sbuf.stride(0), Cs, None, 0, S, work=(0.0, 4.0 * sbuf.numel()))
-            off = 0
-            n = sets.n_sets
-            for (k, c, ch, s2) in plan["static"]:
-                e = sets.s[n]
-                e.kind, e.C, e.ch_off = 2, cfg.dim_yc[k] + 1, ch
-                e.y = sbuf.data_ptr() + 4 * off * g.n1 * g.n2
-                off += cfg.dim_yc[k] + 1
-                n += 1
-            sets.n_sets = n
-        by_in = sum(n_in(c) for _, c, _, _ in plan["per_task"] if not c.gridded)
+        entries = sorted(plan["per_task"] + plan["static"], key=lambda t: t[0])
+        sets, t_bytes = self._enc_sets(entries, g, B)
+        by_grid = sum(n_in(c) for _, c, _, _ in entries if c.gridded)
+        by_off = sum(n_in(c) for _, c, _, _ in entries if not c.gridded)
+        if any(c.gridded for _, c, _, _ in entries):
+            self._call("cnp_encode_hpass", C.byref(sets), B, g.n1, g.n2, S, work=(0.0, by_grid + t_bytes))
         if blk is not None:
             bv = blk.view()
             self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 1, None, 0,
-                       Cin, C.byref(bv), blk.CB, S, work=(0.0, by_in + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
+                       Cin, C.byref(bv), blk.CB, S, work=(0.0, by_off + t_bytes + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
         else:
             self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
-                       _ptr(enc), enc.stride(0), Cin, None, 0, S, work=(0.0, by_in + 4.0 * enc.numel()))
+                       _ptr(enc), enc.stride(0), Cin, None, 0, S, work=(0.0, by_off + t_bytes + 4.0 * enc.numel()))
         return True
 
     def encode_blocked(self, batch: DeviceBatch) -> Optional["_Blk"]:

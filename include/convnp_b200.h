@@ -91,20 +91,20 @@ typedef struct cnp_blk {
  *   cnp_encode_tables : band tables of one gridded set; they depend only on (coordinates, internal grid, length scale)
  *                       -- build once, keep across steps.
  *   cnp_encode_hpass  : horizontal band pass of every gridded set of ``sets`` into its T workspace.
- *   cnp_encode_fused  : one CTA = one 32 x 32 tile of the internal grid of one task: vertical pass of the gridded sets,
- *                       off-grid sets, precomputed planes (kind 2: channels encoded once for the whole batch by a
- *                       first call with B = 1, mode 0 -- static topography / land-mask sets), density normalisation.
+ *   cnp_encode_fused  : one CTA = one 16 x 32 tile of the internal grid and up to 4 consecutive tasks: vertical pass of
+ *                       the gridded sets (fields every task shares -- batched = 0: static topography / land mask --
+ *                       once per CTA), off-grid sets, density normalisation.
  * mode 0: fp32 NCHW out_f32 [B][c_total][n1][n2]; mode 1: blocked bf16 out_blk with n_chunks chunks: channels
  * [0, c_total) = encoder output, channel c_total = 1 inside the image (folded first layer, cnp_fold_in_fwd), rest 0.
  * Gridded sets need monotone coordinates shared by the batch. */
 typedef struct cnp_enc_set {
-  int kind;            /* 0 off-grid, 1 gridded, 2 precomputed fp32 planes [C][n1][n2] */
-  int C;               /* data channels (1..8); kind 2: number of planes */
+  int kind;            /* 0 off-grid, 1 gridded */
+  int C;               /* data channels (1..8) */
   int ch_off;          /* first output channel (density for kinds 0 / 1) */
   int batched;         /* gridded: y / mask / T carry a batch axis (0 = one field for every task) */
   const float* x1;     /* off-grid x [B,2,N] */
   const float* x2;     /* unused */
-  const float* y;      /* gridded [B or 1,C,N1,N2]; off-grid [B,C,N]; may hold NaN (= missing); kind 2: the planes */
+  const float* y;      /* gridded [B or 1,C,N1,N2]; off-grid [B,C,N]; may hold NaN (= missing) */
   const float* mask;   /* gridded [B or 1,1,N1,N2]; off-grid [B,1,N]; or NULL */
   int N1, N2;          /* off-grid: N1 = N */
   int mono1, mono2;    /* +1 ascending, -1 descending */
