@@ -61,7 +61,7 @@ class CnpEncSet(C.Structure):
                 ("x1", C.c_void_p), ("x2", C.c_void_p), ("y", C.c_void_p), ("mask", C.c_void_p),
                 ("N1", C.c_int), ("N2", C.c_int), ("mono1", C.c_int), ("mono2", C.c_int),
                 ("scale2", C.c_float), ("KB", C.c_int), ("tab_i", C.c_void_p), ("tab_w", C.c_void_p),
-                ("T", C.c_void_p)]
+                ("T", C.c_void_p), ("V", C.c_void_p), ("V_bs", C.c_longlong)]
 
 
 class CnpEncSets(C.Structure):
@@ -85,7 +85,7 @@ _SIGS = {
     "cnp_setconv_enc_grid_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "cnp_setconv_enc_grid_fwd": (C.c_int, [c_fp, c_fp, _i, c_fp, c_fp, _i, _i, _i, _i, _i, _i] + _GRID +
                                  [_f, _f, c_fp, _i, _i, _i, c_fp, _ll, c_stream]),
-    "cnp_encode_fused_smem_bytes": (_ll, [_i, _i]),
+    "cnp_encode_vpass": (C.c_int, [C.POINTER(CnpEncSets), _i, _i, _i, _f, c_stream]),
     "cnp_encode_hpass": (C.c_int, [C.POINTER(CnpEncSets), _i, _i, _i, c_stream]),
     "cnp_encode_tables": (C.c_int, [c_fp, c_fp, _i, _i, _i, _i] + _GRID + [_f, _i, c_fp, c_fp, c_stream]),
     "cnp_encode_fused": (C.c_int, [C.POINTER(CnpEncSets), _i] + _GRID + [_f, _i, c_fp, _ll, _i, C.POINTER(CnpBlk), _i,

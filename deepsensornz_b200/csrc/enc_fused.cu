@@ -8,35 +8,32 @@
 // with NaN observations turned into valid = 0 on the fly (ConvNP.modify_task's host scan) and terms whose exponent
 // exceeds 104 (exactly 0.0f in fp32) left out of the sums.
 //
-// Two launches per step (three when the batch shares static sets):
+// Three launches per step, each a flat data-parallel sweep (the work is tiny -- 60 MB of algorithmic traffic per 16-task
+// step -- so what matters is exposing all of it at once and keeping every thread's instruction stream short):
 //   1. cnp_encode_hpass: horizontal band pass of EVERY gridded set, T_k[b][c][p][j] = sum_q y~[b][c][p][q] w2[q][j]
-//      (<= 32 taps, one thread per (p, j), all channels) into a workspace that stays in L2.  Band starts and weights
-//      come from per-set tables (cnp_encode_tables) that depend only on (coordinates, internal grid, length scale): the
-//      caller builds them once and keeps them across steps.
-//   2. cnp_encode_fused: one CTA = one 32 x 32 tile of the internal grid of one task, one thread = 4 adjacent rows of one
-//      column.  Per context set:
-//        * gridded: vertical band pass over the T rows in the union band of the thread's rows (each T row is loaded
-//          once for the 4 pixels, coalesced along the columns), weights from a shared-memory copy of the tile's table;
-//        * off-grid: every thread loads one point (coordinates, channels, mask), the points that can touch the tile are
-//          compacted in order, their separable weights staged in shared memory, every thread sums its own pixels;
-//        * precomputed planes: channels of sets the whole batch shares (topography aux, land mask) are encoded ONCE per
-//          step by a first call of this same kernel (B = 1, fp32 planes) and copied in here from L2.
-//      Gather form throughout, no atomics.  The tile's channels meet in shared memory and leave as either fp32 NCHW
-//      (parity mode) or -- bf16 UNet -- directly as the blocked bf16 tensor [B][chunk][H+4][W+4][8] with the constant-1
-//      channel of the folded first layer (fold_in.cu): no fp32 encoder tensor, no layout-conversion kernel.
-// Bound: HBM.  History (B200, B = 16, 304^2): per-set kernels of round 1 240 us; a first fused
-// version that recomputed the horizontal pass per 8 x 32 tile in shared memory 312 us (ncu: 166 M warp instructions,
-// instruction-bound -- every tile redid ~3x the horizontal work and ran 9-channel predicated loops); this version:
-// see profiles/.
+//      (<= 32 taps, one thread per (b, p, j), all channels) into a workspace that stays in L2.
+//   2. cnp_encode_vpass: vertical band pass + density normalisation, one thread per (b, i, j), all channels:
+//      V_k[b][c][i][j] (fp32 planes; in fp32 mode these ARE the output channels).
+//   3. cnp_encode_fused: one CTA = one 16 x 32 tile of one task: the off-grid sets (every thread loads one point --
+//      coordinates, channels, mask --, the points that can touch the tile are compacted in order, their separable weights
+//      staged in shared memory, every thread sums its own 4 pixels), then -- bf16 UNet -- the tile's channels are
+//      gathered from the V planes (coalesced, L2) and leave directly as the blocked bf16 tensor [B][chunk][H+4][W+4][8]
+//      with the constant-1 channel of the folded first layer (fold_in.cu): no fp32 encoder tensor, no layout-conversion
+//      kernel.
+// Band starts and weights come from per-set tables (cnp_encode_tables) that depend only on (coordinates, internal grid,
+// length scale): the caller builds them once and keeps them across steps.  Gather form throughout, no atomics.
+// Bound: HBM.  History (B200, B = 16, 304^2, ncu): per-set kernels of round 1 240 us; fused per-tile
+// kernel recomputing the horizontal pass in shared memory 312 us (166 M warp instructions, instruction-bound: every
+// 8 x 32 tile redid ~3x the horizontal work in 9-channel predicated loops); horizontal pass split off, 4 rows per
+// thread 158 us; 4 tasks per CTA 119 us (latency-bound at 12 resident warps per SM); this version: profiles/.
 #include "tc_common.cuh"
 #include <math.h>
-#include <type_traits>
 
 struct cnp_enc_set {
   int kind;          // 0 off-grid, 1 gridded
   int C;             // data channels (1..8)
   int ch_off;        // first output channel (the density channel)
-  int batched;       // y (and mask, T) carry a batch axis; 0: one field shared by every task
+  int batched;       // y (and mask, T, V) carry a batch axis; 0: one field shared by every task
   const float* x1;   // off-grid: x [B,2,N]
   const float* x2;   // unused by the kernels (gridded coordinates enter through the tables)
   const float* y;    // gridded [B or 1, C, N1, N2]; off-grid [B, C, N]
@@ -48,6 +45,8 @@ struct cnp_enc_set {
   const int* tab_i;  // gridded: [p0 (n1) | len1 (n1) | q0 (n2) | len2 (n2)]   (cnp_encode_tables)
   const float* tab_w;// gridded: [w1 (KB x n1) | w2 (KB x n2)]
   float* T;          // gridded: horizontal-pass workspace [B or 1][C+1][N1][n2]
+  float* V;          // gridded: normalised output planes, channel stride n1*n2, batch stride V_bs
+  long long V_bs;
 };
 struct cnp_enc_sets {
   int n_sets;
@@ -57,12 +56,14 @@ struct cnp_enc_sets {
 
 namespace {
 
-constexpr int TI = 16, TJ = 32, NT = 128, RPT = 4;   // tile rows / cols, threads, rows per thread
+constexpr int TI = 16, TJ = 32, NT = 128, RPT = 4;   // tile rows / cols, threads, rows per thread (launch 3)
 constexpr int NPIX = TI * TJ;
 constexpr int KBMAX = 32;    // max band (inputs within R of one grid row / column)
 constexpr int OGC = NT;      // off-grid points per chunk (one per thread)
 constexpr int OGS = 64;      // off-grid points whose weights are staged at a time
 constexpr int MAXC1 = 9;     // max channels incl. density of one set
+constexpr int SW = 160;      // threads per block of the sweeps (launches 1, 2): 304 columns = 2 blocks, 95 % of the lanes
+constexpr int MAXCH = 72;    // max output channels (8 sets x 9)
 
 __device__ int lower_bound_f(const float* __restrict__ x, int n, float v, int asc) {
   int lo = 0, hi = n;
@@ -92,38 +93,50 @@ __device__ void window_of(const float* __restrict__ x, int n, float a, float b, 
 }
 
 // =====================================================================================================================
-// launch 1: horizontal band pass of every gridded set
+// launches 1 and 2: one block = SW consecutive columns of one (set, batch entry, row)
 // =====================================================================================================================
-struct cnp_hpass_args {
-  cnp_enc_sets S;
+struct cnp_sweep_args {
+  cnp_enc_sets S;    // gridded sets only
   int blk0[9];       // first block of every set (prefix sums); blk0[n_sets] = grid size
-  int nb[8];         // batch entries of every set (B or 1)
-  int n1, n2;
+  int rows[8];       // rows swept per batch entry: N1 (horizontal pass) or n1 (vertical pass)
+  int n1, n2, bpr;   // bpr = blocks per row
 };
 
-template <int C>
+// block -> (set, batch entry, row, column); block-uniform integer work only
+__device__ __forceinline__ const cnp_enc_set& sweep_decode(const cnp_sweep_args& a, int* b, int* row, int* j) {
+  int k = 0;
+  while (k + 1 < a.S.n_sets && (int)blockIdx.x >= a.blk0[k + 1]) ++k;
+  const int lb = (int)blockIdx.x - a.blk0[k];
+  const int pr = lb / a.bpr;
+  *j = (lb - pr * a.bpr) * SW + threadIdx.x;
+  *b = pr / a.rows[k];
+  *row = pr - *b * a.rows[k];
+  return a.S.s[k];
+}
+
+template <int C, bool MASK>
 __device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p, int j, int n1, int n2) {
   const int N1 = st.N1, N2 = st.N2;
   const int q0 = __ldg(st.tab_i + 2 * n1 + j), len = __ldg(st.tab_i + 2 * n1 + n2 + j);
   const float* w2 = st.tab_w + st.KB * n1 + j;
-  const int plane = N1 * N2;                       // (a context field has far fewer than 2^31 cells)
+  const int plane = N1 * N2;                       // (a context field has far fewer than 2^30 cells)
   const float* yb = st.y + (size_t)b * C * plane + p * N2 + q0;
-  const float* mb = st.mask ? st.mask + (size_t)b * plane + p * N2 + q0 : nullptr;
+  const float* mb = MASK ? st.mask + (size_t)b * plane + p * N2 + q0 : nullptr;
   float acc[C + 1];
 #pragma unroll
   for (int c = 0; c <= C; ++c) acc[c] = 0.f;
 #pragma unroll 4
   for (int k = 0; k < len; ++k) {
     const float w = __ldg(w2 + k * n2);
-    float valid = mb ? __ldg(mb + k) : 1.f;
     float v[C];
     bool nan_any = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) { v[c] = __ldg(yb + c * plane + k); nan_any |= isnan(v[c]); }
+    float valid = MASK ? __ldg(mb + k) : 1.f;
     if (nan_any) valid = 0.f;
     acc[0] = fmaf(valid, w, acc[0]);
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[1 + c] = fmaf(nan_any ? 0.f : v[c] * valid, w, acc[1 + c]);
+    for (int c = 0; c < C; ++c) acc[1 + c] = fmaf(nan_any ? 0.f : (MASK ? v[c] * valid : v[c]), w, acc[1 + c]);
   }
   const int tplane = N1 * n2;
   float* T = st.T + (size_t)b * (C + 1) * tplane + p * n2 + j;
@@ -131,69 +144,79 @@ __device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p, 
   for (int c = 0; c <= C; ++c) T[c * tplane] = acc[c];
 }
 
-__global__ void __launch_bounds__(256)
-enc_hpass_kernel(const __grid_constant__ cnp_hpass_args a) {
-  int k = 0;
-  while (k + 1 < a.S.n_sets && (int)blockIdx.x >= a.blk0[k + 1]) ++k;
-  const cnp_enc_set& st = a.S.s[k];
-  const int e = (int)(blockIdx.x - a.blk0[k]) * 256 + threadIdx.x;
-  const int per_b = st.N1 * a.n2;
-  if (e >= per_b * a.nb[k]) return;
-  const int b = e / per_b, r = e - b * per_b, p = r / a.n2, j = r - p * a.n2;
-  switch (st.C) {
-    case 1: hpass_elem<1>(st, b, p, j, a.n1, a.n2); break;
-    case 2: hpass_elem<2>(st, b, p, j, a.n1, a.n2); break;
-    case 3: hpass_elem<3>(st, b, p, j, a.n1, a.n2); break;
-    case 4: hpass_elem<4>(st, b, p, j, a.n1, a.n2); break;
-    case 5: hpass_elem<5>(st, b, p, j, a.n1, a.n2); break;
-    case 6: hpass_elem<6>(st, b, p, j, a.n1, a.n2); break;
-    case 7: hpass_elem<7>(st, b, p, j, a.n1, a.n2); break;
-    default: hpass_elem<8>(st, b, p, j, a.n1, a.n2); break;
+#define CNP_SWITCH_C(Cv, ...)                     \
+  switch (Cv) {                                   \
+    case 1: { constexpr int CC = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int CC = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int CC = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int CC = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int CC = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int CC = 6; __VA_ARGS__; } break; \
+    case 7: { constexpr int CC = 7; __VA_ARGS__; } break; \
+    default: { constexpr int CC = 8; __VA_ARGS__; } break; \
   }
+
+__global__ void __launch_bounds__(SW)
+enc_hpass_kernel(const __grid_constant__ cnp_sweep_args a) {
+  int b, p, j;
+  const cnp_enc_set& st = sweep_decode(a, &b, &p, &j);
+  if (j >= a.n2) return;
+  if (st.mask) { CNP_SWITCH_C(st.C, hpass_elem<CC, true>(st, b, p, j, a.n1, a.n2)) }
+  else { CNP_SWITCH_C(st.C, hpass_elem<CC, false>(st, b, p, j, a.n1, a.n2)) }
+}
+
+template <int C>
+__device__ __forceinline__ void vpass_elem(const cnp_enc_set& st, int b, int i, int j, int n1, int n2, float eps) {
+  const int p0 = __ldg(st.tab_i + i), len = __ldg(st.tab_i + n1 + i);
+  const float* w1 = st.tab_w + i;
+  const int tplane = st.N1 * n2;
+  const float* T = st.T + (size_t)b * (C + 1) * tplane + p0 * n2 + j;
+  float acc[C + 1];
+#pragma unroll
+  for (int c = 0; c <= C; ++c) acc[c] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < len; ++k) {
+    const float w = __ldg(w1 + k * n1);
+#pragma unroll
+    for (int c = 0; c <= C; ++c) acc[c] = fmaf(w, __ldg(T + c * tplane + k * n2), acc[c]);
+  }
+  // density first, data divided by (density + eps)
+  const int plane = n1 * n2;
+  float* V = st.V + (size_t)b * st.V_bs + i * n2 + j;
+  const float dens = acc[0], inv = 1.0f / (dens + eps);
+  V[0] = dens;
+#pragma unroll
+  for (int c = 1; c <= C; ++c) V[c * plane] = acc[c] * inv;
+}
+
+__global__ void __launch_bounds__(SW)
+enc_vpass_kernel(const __grid_constant__ cnp_sweep_args a, float eps) {
+  int b, i, j;
+  const cnp_enc_set& st = sweep_decode(a, &b, &i, &j);
+  if (j >= a.n2) return;
+  CNP_SWITCH_C(st.C, vpass_elem<CC>(st, b, i, j, a.n1, a.n2, eps))
 }
 
 // =====================================================================================================================
-// launch 2: vertical pass + off-grid sets -> the UNet input
+// launch 3: off-grid sets + assembly of the UNet input
 // =====================================================================================================================
-// store one set's result for the thread's RPT pixels: density first, data times 1 / (density + eps)
+struct cnp_asm_args {
+  cnp_enc_sets S;                 // off-grid sets only; ch_off = REAL output channel, og_off[] = slot in the staging tile
+  int og_off[8];
+  int n_og_ch;                    // staged off-grid channels
+  const float* cptr[MAXCH];       // per output channel: V plane of a gridded set, or NULL
+  long long cbs[MAXCH];           // its batch stride (0: shared by every task)
+  short og_map[MAXCH];            // per output channel: slot in the off-grid staging tile, or -1
+};
+
 template <int C>
-__device__ __forceinline__ void store_set(float* __restrict__ outs, int ch_off, int pix0, const float (&acc)[RPT][MAXC1],
-                                          float eps) {
-  float* o = outs + ch_off * NPIX + pix0;
+__device__ __forceinline__ void store_set(float* __restrict__ o, const float (&acc)[RPT][MAXC1], float eps) {
 #pragma unroll
   for (int e = 0; e < RPT; ++e) {
     const float dens = acc[e][0], inv = 1.0f / (dens + eps);
     o[e * TJ] = dens;
 #pragma unroll
     for (int c = 1; c <= C; ++c) o[c * NPIX + e * TJ] = acc[e][c] * inv;
-  }
-}
-
-template <int C>
-__device__ __forceinline__ void vpass(const cnp_enc_set& st, int b, int n2, int j, bool col_ok, const int (&p0)[RPT],
-                                      const int (&len)[RPT], const float* __restrict__ w1t, int row0,
-                                      float (&acc)[RPT][MAXC1]) {
-  // union band of the thread's rows (monotone coordinates: bands of adjacent rows overlap almost entirely)
-  int lo = 0x7fffffff, hi = 0;
-#pragma unroll
-  for (int e = 0; e < RPT; ++e) if (len[e] > 0) { lo = min(lo, p0[e]); hi = max(hi, p0[e] + len[e]); }
-  if (!col_ok || hi <= lo) return;
-  const int KBs = st.KB, tplane = st.N1 * n2;
-  const float* T = st.T + (size_t)(st.batched ? b : 0) * (C + 1) * tplane + lo * n2 + j;
-  const float* wb[RPT];
-#pragma unroll
-  for (int e = 0; e < RPT; ++e) wb[e] = w1t + (row0 + e) * KBs - p0[e];
-#pragma unroll 2
-  for (int r = lo; r < hi; ++r, T += n2) {
-    float t[C + 1];
-#pragma unroll
-    for (int c = 0; c <= C; ++c) t[c] = __ldg(T + c * tplane);
-#pragma unroll
-    for (int e = 0; e < RPT; ++e) {
-      const float w = ((unsigned)(r - p0[e]) < (unsigned)len[e]) ? wb[e][r] : 0.f;
-#pragma unroll
-      for (int c = 0; c <= C; ++c) acc[e][c] = fmaf(w, t[c], acc[e][c]);
-    }
   }
 }
 
@@ -215,167 +238,138 @@ __device__ __forceinline__ void ogacc(const float* __restrict__ ys, const float*
   }
 }
 
-#define CNP_SWITCH_C(Cv, ...)                     \
-  switch (Cv) {                                   \
-    case 1: { constexpr int CC = 1; __VA_ARGS__; } break; \
-    case 2: { constexpr int CC = 2; __VA_ARGS__; } break; \
-    case 3: { constexpr int CC = 3; __VA_ARGS__; } break; \
-    case 4: { constexpr int CC = 4; __VA_ARGS__; } break; \
-    case 5: { constexpr int CC = 5; __VA_ARGS__; } break; \
-    case 6: { constexpr int CC = 6; __VA_ARGS__; } break; \
-    case 7: { constexpr int CC = 7; __VA_ARGS__; } break; \
-    default: { constexpr int CC = 8; __VA_ARGS__; } break; \
-  }
-
-// One CTA = one 16 x 32 tile of the internal grid and TB consecutive tasks; one thread = 4 adjacent rows of one column.
-// Gridded sets that every task shares (batched = 0) are computed for the first task of the CTA only: their channels stay
-// in the shared-memory staging tile while the per-task sets of the following tasks overwrite theirs.
-template <int MODE>   // 0: fp32 NCHW output, 1: blocked bf16 output with the constant-1 channel
-__global__ void __launch_bounds__(NT, 4)
-enc_fused_kernel(const __grid_constant__ cnp_enc_sets S, int B, int TB, double start1, int n1, double start2, int n2,
-                 double res, float eps, float* __restrict__ out_f32, long long out_bs, int c_total, cnp_blk ob,
-                 int n_chunks, int CP) {
+template <int MODE>   // 0: fp32 NCHW output (off-grid channels only; launch 2 wrote the rest), 1: blocked bf16 output
+__global__ void __launch_bounds__(NT, 6)
+enc_fused_kernel(const __grid_constant__ cnp_asm_args A, double start1, int n1, double start2, int n2, double res,
+                 float eps, float* __restrict__ out_f32, long long out_bs, int c_total, cnp_blk ob, int n_chunks) {
   extern __shared__ __align__(16) float sm[];
-  float* outs = sm;                                // [CP][NPIX] fp32 staging of the tile's channels
-  float* scr = sm + CP * NPIX;                     // per-set scratch
+  float* og = sm;                                  // [n_og_ch][NPIX] staging of the off-grid channels of the tile
+  float* scr = sm + A.n_og_ch * NPIX;              // per-set scratch
   __shared__ float g1s[TI], g2s[TJ];
   __shared__ int warp_cnt[NT / 32];
 
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+  const int b = blockIdx.z, i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
   const int row0 = ty * RPT, j = j0 + tx;
   const bool col_ok = j < n2;
   const int pix0 = row0 * TJ + tx;                 // tile-local pixel of the thread's first row
   if (tid < TI) g1s[tid] = cnp_grid_pt(start1, res, min(i0 + tid, n1 - 1));
   if (tid >= 32 && tid < 32 + TJ) g2s[tid - 32] = cnp_grid_pt(start2, res, min(j0 + tid - 32, n2 - 1));
-  for (int c = 0; c < CP; ++c) {
-    const float v = (MODE == 1 && c == c_total) ? 1.f : 0.f;   // constant-1 channel of the folded first layer
-#pragma unroll
-    for (int e = 0; e < RPT; ++e) outs[c * NPIX + pix0 + e * TJ] = v;
-  }
 
-  for (int bl = 0; bl < TB; ++bl) {
-    const int b = blockIdx.z * TB + bl;
-    if (b >= B) break;
-    for (int k = 0; k < S.n_sets; ++k) {
-      const cnp_enc_set& st = S.s[k];
-      const int C = st.C;
-      if (st.kind == 1 && !st.batched && bl > 0) continue;      // shared field: already in the staging tile
-      __syncthreads();                             // scratch of the previous set is free; g1s / g2s are visible
-      float acc[RPT][MAXC1];
+  for (int k = 0; k < A.S.n_sets; ++k) {
+    const cnp_enc_set& st = A.S.s[k];
+    const int C = st.C;
+    __syncthreads();                               // scratch of the previous set is free; g1s / g2s are visible
+    float acc[RPT][MAXC1];
 #pragma unroll
-      for (int e = 0; e < RPT; ++e)
+    for (int e = 0; e < RPT; ++e)
 #pragma unroll
-        for (int c = 0; c < MAXC1; ++c) acc[e][c] = 0.f;
-
-      if (st.kind == 1) {
-        // ---------------- gridded set: vertical band pass over the horizontal-pass workspace ----------------
-        const int KBs = st.KB;
-        float* w1t = scr;                          // [TI][KBs] weights of the tile's rows
-        for (int e = tid; e < TI * KBs; e += NT) {
-          const int r = e / KBs, kk = e - r * KBs;
-          w1t[e] = __ldg(st.tab_w + kk * n1 + min(i0 + r, n1 - 1));
-        }
-        int p0[RPT], len[RPT];
+      for (int c = 0; c < MAXC1; ++c) acc[e][c] = 0.f;
+    const float scale2 = st.scale2;
+    const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
+    const int N = st.N1;
+    float* px = scr;                     // [2][OGC] compacted coordinates
+    float* ys = px + 2 * OGC;            // [MAXC1][OGC] compacted [valid ; y * valid]
+    float* w1s = ys + MAXC1 * OGC;       // [OGS][TI]
+    float* w2s = w1s + OGS * TI;         // [OGS][TJ + 1]
+    const float a1 = g1s[0], b1 = g1s[TI - 1], a2 = g2s[0], b2 = g2s[TJ - 1];
+    const float lo1 = fminf(a1, b1) - R, hi1 = fmaxf(a1, b1) + R, lo2 = fminf(a2, b2) - R, hi2 = fmaxf(a2, b2) + R;
+    const float* xb = st.x1 + (size_t)b * 2 * N;
+    const float* yb = st.y + (size_t)b * C * N;
+    const float* mb = st.mask ? st.mask + (size_t)b * N : nullptr;
+    for (int c0 = 0; c0 < N; c0 += OGC) {
+      const int n = c0 + tid;
+      bool keep = false;
+      float p1 = 0.f, p2 = 0.f, valid = 0.f, v[MAXC1 - 1];
+      if (n < N) {
+        p1 = __ldg(xb + n); p2 = __ldg(xb + N + n);
+        valid = mb ? __ldg(mb + n) : 1.f;
+        bool nan_any = false;
 #pragma unroll
-        for (int e = 0; e < RPT; ++e) {
-          const int i = i0 + row0 + e;
-          p0[e] = __ldg(st.tab_i + min(i, n1 - 1));
-          len[e] = (i < n1) ? __ldg(st.tab_i + n1 + min(i, n1 - 1)) : 0;
+        for (int c = 0; c < MAXC1 - 1; ++c)
+          if (c < C) { v[c] = __ldg(yb + c * N + n); nan_any |= isnan(v[c]); }
+        if (nan_any) valid = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC1 - 1; ++c)
+          if (c < C) v[c] = nan_any ? 0.f : v[c] * valid;
+        keep = (p1 >= lo1) && (p1 <= hi1) && (p2 >= lo2) && (p2 <= hi2);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (c0 > 0) __syncthreads();       // the previous chunk's consumers are done
+      if (tx == 0) warp_cnt[ty] = __popc(bal);
+      __syncthreads();
+      int base = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) { if (w < ty) base += warp_cnt[w]; total += warp_cnt[w]; }
+      if (keep) {
+        const int m = base + __popc(bal & ((1u << tx) - 1u));
+        px[m] = p1; px[OGC + m] = p2; ys[m] = valid;
+#pragma unroll
+        for (int c = 0; c < MAXC1 - 1; ++c)
+          if (c < C) ys[(1 + c) * OGC + m] = v[c];
+      }
+      for (int m0 = 0; m0 < total; m0 += OGS) {
+        const int nm = min(OGS, total - m0);
+        __syncthreads();                 // compacted points visible / previous weights consumed
+        for (int e = tid; e < nm * TJ; e += NT) {
+          const int m = e >> 5, jj = e & 31;
+          w2s[m * (TJ + 1) + jj] = cnp_rbf(px[OGC + m0 + m], g2s[jj], scale2);
+          if (jj < TI) w1s[m * TI + jj] = cnp_rbf(px[m0 + m], g1s[jj], scale2);
         }
         __syncthreads();
-        CNP_SWITCH_C(C, vpass<CC>(st, b, n2, j, col_ok, p0, len, w1t, row0, acc); store_set<CC>(outs, st.ch_off, pix0, acc, eps))
-      } else {
-        // ---------------- off-grid set ----------------
-        // one global round trip per chunk of 128 points: every thread loads its point (coordinates, all channels,
-        // mask), the points that can touch the tile are compacted in order into shared memory, their separable weights
-        // are staged 64 points at a time and every thread sums its own pixels
-        const float scale2 = st.scale2;
-        const float R = sqrtf(2.0f * CNP_EXP_CUTOFF * scale2);
-        const int N = st.N1;
-        float* px = scr;                     // [2][OGC] compacted coordinates
-        float* ys = px + 2 * OGC;            // [MAXC1][OGC] compacted [valid ; y * valid]
-        float* w1s = ys + MAXC1 * OGC;       // [OGS][TI]
-        float* w2s = w1s + OGS * TI;         // [OGS][TJ + 1]
-        const float a1 = g1s[0], b1 = g1s[TI - 1], a2 = g2s[0], b2 = g2s[TJ - 1];
-        const float lo1 = fminf(a1, b1) - R, hi1 = fmaxf(a1, b1) + R, lo2 = fminf(a2, b2) - R, hi2 = fmaxf(a2, b2) + R;
-        const float* xb = st.x1 + (size_t)b * 2 * N;
-        const float* yb = st.y + (size_t)b * C * N;
-        const float* mb = st.mask ? st.mask + (size_t)b * N : nullptr;
-        for (int c0 = 0; c0 < N; c0 += OGC) {
-          const int n = c0 + tid;
-          bool keep = false;
-          float p1 = 0.f, p2 = 0.f, valid = 0.f, v[MAXC1 - 1];
-          if (n < N) {
-            p1 = __ldg(xb + n); p2 = __ldg(xb + N + n);
-            valid = mb ? __ldg(mb + n) : 1.f;
-            bool nan_any = false;
-#pragma unroll
-            for (int c = 0; c < MAXC1 - 1; ++c)
-              if (c < C) { v[c] = __ldg(yb + c * N + n); nan_any |= isnan(v[c]); }
-            if (nan_any) valid = 0.f;
-#pragma unroll
-            for (int c = 0; c < MAXC1 - 1; ++c)
-              if (c < C) v[c] = nan_any ? 0.f : v[c] * valid;
-            keep = (p1 >= lo1) && (p1 <= hi1) && (p2 >= lo2) && (p2 <= hi2);
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (c0 > 0) __syncthreads();     // the previous chunk's consumers are done
-          if (tx == 0) warp_cnt[ty] = __popc(bal);
-          __syncthreads();
-          int base = 0, total = 0;
-#pragma unroll
-          for (int w = 0; w < NT / 32; ++w) { if (w < ty) base += warp_cnt[w]; total += warp_cnt[w]; }
-          if (keep) {
-            const int m = base + __popc(bal & ((1u << tx) - 1u));
-            px[m] = p1; px[OGC + m] = p2; ys[m] = valid;
-#pragma unroll
-            for (int c = 0; c < MAXC1 - 1; ++c)
-              if (c < C) ys[(1 + c) * OGC + m] = v[c];
-          }
-          for (int m0 = 0; m0 < total; m0 += OGS) {
-            const int nm = min(OGS, total - m0);
-            __syncthreads();               // compacted points visible / previous weights consumed
-            for (int e = tid; e < nm * TJ; e += NT) {
-              const int m = e >> 5, jj = e & 31;
-              w2s[m * (TJ + 1) + jj] = cnp_rbf(px[OGC + m0 + m], g2s[jj], scale2);
-              if (jj < TI) w1s[m * TI + jj] = cnp_rbf(px[m0 + m], g1s[jj], scale2);
-            }
-            __syncthreads();
-            CNP_SWITCH_C(C, ogacc<CC>(ys, w1s, w2s, m0, nm, row0, tx, acc))
-          }
-        }
-        CNP_SWITCH_C(C, store_set<CC>(outs, st.ch_off, pix0, acc, eps))
+        CNP_SWITCH_C(C, ogacc<CC>(ys, w1s, w2s, m0, nm, row0, tx, acc))
       }
     }
-    // ---- write the task's tile (every thread reads back only what it wrote itself: no barrier) ----
-    if (!col_ok) continue;
-    if (MODE == 0) {
+    CNP_SWITCH_C(C, store_set<CC>(og + A.og_off[k] * NPIX + pix0, acc, eps))
+  }
+  // ---- write the tile (every thread reads back only what it staged itself: no barrier) ----
+  if (!col_ok) return;
+  if (MODE == 0) {
+    const int plane = n1 * n2;
+    for (int k = 0; k < A.S.n_sets; ++k) {
+      const cnp_enc_set& st = A.S.s[k];
 #pragma unroll
       for (int e = 0; e < RPT; ++e) {
         const int i = i0 + row0 + e;
         if (i >= n1) continue;
-        float* o = out_f32 + (size_t)b * out_bs + i * n2 + j;
-        const int plane = n1 * n2;
-        for (int c = 0; c < c_total; ++c) o[c * plane] = outs[c * NPIX + pix0 + e * TJ];
+        float* o = out_f32 + (size_t)b * out_bs + (size_t)st.ch_off * plane + i * n2 + j;
+        for (int c = 0; c <= st.C; ++c) o[c * plane] = og[(A.og_off[k] + c) * NPIX + pix0 + e * TJ];
       }
-    } else {
-      const int Hp = ob.H + 4, Wp = ob.W + 4;
-      __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ob.base) + (size_t)b * ob.bstride;
+    }
+  } else {
+    const int Hp = ob.H + 4, Wp = ob.W + 4;
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ob.base) + (size_t)b * ob.bstride;
+    int poff[RPT];
+#pragma unroll
+    for (int e = 0; e < RPT; ++e) poff[e] = min(i0 + row0 + e, n1 - 1) * n2 + j;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      float v[8][RPT];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int c = ch * 8 + q;
+        const float* p = A.cptr[c];
+        if (p != nullptr) {                        // channel of a gridded set: V plane (coalesced along the row, L2)
+          p += (size_t)b * A.cbs[c];
+#pragma unroll
+          for (int e = 0; e < RPT; ++e) v[q][e] = __ldg(p + poff[e]);
+        } else {
+          const int slot = A.og_map[c];
+          const float cst = (c == c_total) ? 1.f : 0.f;       // constant-1 channel of the folded first layer
+#pragma unroll
+          for (int e = 0; e < RPT; ++e) v[q][e] = slot >= 0 ? og[slot * NPIX + pix0 + e * TJ] : cst;
+        }
+      }
 #pragma unroll
       for (int e = 0; e < RPT; ++e) {
         const int i = i0 + row0 + e;
         if (i >= n1) continue;
-        const float* o = outs + pix0 + e * TJ;
-        for (int ch = 0; ch < n_chunks; ++ch, o += 8 * NPIX) {
-          uint4 pk;
-          __nv_bfloat162 h;
-          h = __floats2bfloat162_rn(o[0], o[NPIX]);             pk.x = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2bfloat162_rn(o[2 * NPIX], o[3 * NPIX]);  pk.y = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2bfloat162_rn(o[4 * NPIX], o[5 * NPIX]);  pk.z = *reinterpret_cast<uint32_t*>(&h);
-          h = __floats2bfloat162_rn(o[6 * NPIX], o[7 * NPIX]);  pk.w = *reinterpret_cast<uint32_t*>(&h);
-          *reinterpret_cast<uint4*>(base + (((size_t)(ob.cb_off + ch) * Hp + i + 2) * Wp + j + 2) * 8) = pk;
-        }
+        uint4 pk;
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(v[0][e], v[1][e]); pk.x = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(v[2][e], v[3][e]); pk.y = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(v[4][e], v[5][e]); pk.z = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(v[6][e], v[7][e]); pk.w = *reinterpret_cast<uint32_t*>(&h);
+        *reinterpret_cast<uint4*>(base + (((size_t)(ob.cb_off + ch) * Hp + i + 2) * Wp + j + 2) * 8) = pk;
       }
     }
   }
@@ -418,17 +412,9 @@ CNP_API int cnp_encode_tables(const float* x1, const float* x2, int N1, int N2, 
   return 0;
 }
 
-static long long ef_smem(int channels_staged) {
+static long long ef_smem(int og_channels) {
   const long long og_f = 2LL * OGC + (long long)MAXC1 * OGC + OGS * TI + OGS * (TJ + 1);
-  const long long grid_f = (long long)TI * KBMAX;
-  return ((long long)channels_staged * NPIX + (grid_f > og_f ? grid_f : og_f)) * 4;
-}
-
-// Shared memory of one cnp_encode_fused launch (bytes); -1 when it cannot fit.
-CNP_API long long cnp_encode_fused_smem_bytes(int mode, int channels_staged) {
-  (void)mode;
-  const long long bytes = ef_smem(channels_staged);
-  return bytes <= 200 * 1024 ? bytes : -1;
+  return ((long long)og_channels * NPIX + og_f) * 4;
 }
 
 static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who) {
@@ -439,11 +425,32 @@ static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who)
     CNP_REQUIRE(s.C >= 1 && s.C <= MAXC1 - 1, "%s: set %d needs 1..%d channels", who, k, MAXC1 - 1);
     CNP_REQUIRE(s.ch_off + s.C + 1 <= c_total, "%s: set %d exceeds %d channels", who, k, c_total);
     if (s.kind == 1)
-      CNP_REQUIRE(s.y && s.tab_i && s.tab_w && s.T && s.KB >= 1 && s.KB <= KBMAX && s.N1 > 0 && s.N2 > 0 &&
+      CNP_REQUIRE(s.y && s.tab_i && s.tab_w && s.T && s.V && s.KB >= 1 && s.KB <= KBMAX && s.N1 > 0 && s.N2 > 0 &&
                       (long long)s.N1 * s.N2 < (1LL << 30),
-                  "%s: gridded set %d needs band tables and a horizontal-pass workspace", who, k);
+                  "%s: gridded set %d needs band tables and the T / V workspaces", who, k);
     if (s.kind == 0) CNP_REQUIRE(s.N1 == 0 || (s.x1 && s.y), "%s: off-grid set %d has null inputs", who, k);
   }
+  return 0;
+}
+
+static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, cnp_sweep_args* a) {
+  memset(a, 0, sizeof(*a));
+  a->n1 = n1; a->n2 = n2; a->bpr = cnp_cdiv(n2, SW);
+  int n = 0;
+  long long blocks = 0;
+  for (int k = 0; k < sets->n_sets; ++k) {
+    const cnp_enc_set& s = sets->s[k];
+    if (s.kind != 1) continue;
+    a->S.s[n] = s;
+    a->rows[n] = vertical ? n1 : s.N1;
+    a->blk0[n] = (int)blocks;
+    blocks += (long long)(s.batched ? B : 1) * a->rows[n] * a->bpr;
+    CNP_REQUIRE(blocks < (1LL << 31) && (long long)(s.batched ? B : 1) * (s.C + 1) * s.N1 * n2 < (1LL << 40),
+                "encode: set %d is too large", k);
+    ++n;
+  }
+  a->S.n_sets = n;
+  a->blk0[n] = (int)blocks;
   return 0;
 }
 
@@ -452,44 +459,64 @@ static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who)
 CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_hpass: bad arguments");
   if (int rc = ef_check_sets(sets, 1 << 30, "encode_hpass")) return rc;
-  cnp_hpass_args a;
-  memset(&a, 0, sizeof(a));
-  a.n1 = n1; a.n2 = n2;
-  int n = 0;
-  long long blocks = 0;
-  for (int k = 0; k < sets->n_sets; ++k) {
-    const cnp_enc_set& s = sets->s[k];
-    if (s.kind != 1) continue;
-    a.S.s[n] = s;
-    a.nb[n] = s.batched ? B : 1;
-    a.blk0[n] = (int)blocks;
-    const long long elems = (long long)a.nb[n] * s.N1 * n2;
-    CNP_REQUIRE(elems < (1LL << 31), "encode_hpass: set %d is too large", k);
-    blocks += (elems + 255) / 256;
-    ++n;
-  }
-  if (n == 0) return 0;
-  a.S.n_sets = n;
-  a.blk0[n] = (int)blocks;
-  enc_hpass_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+  cnp_sweep_args a;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, false, &a)) return rc;
+  if (a.S.n_sets == 0) return 0;
+  enc_hpass_kernel<<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
   CNP_LAUNCH_CHECK("enc_hpass_kernel");
   return 0;
 }
 
-// Launch 2.  mode 0: out_f32 [B][c_total][n1][n2] (batch stride out_bstride floats); mode 1: out_blk = blocked bf16 view
-// with n_chunks >= (c_total + 1 + 7) / 8 chunks: channels [0, c_total) = the encoder output, channel c_total = 1, rest 0.
-// Gridded sets read the T workspaces written by cnp_encode_hpass on the same stream.
+// Launch 2: vertical band pass + density normalisation of every gridded set: T -> V (fp32 planes, channel stride n1*n2,
+// batch stride V_bs; a set every task shares writes one batch entry).
+CNP_API int cnp_encode_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, float eps, cudaStream_t st) {
+  CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_vpass: bad arguments");
+  if (int rc = ef_check_sets(sets, 1 << 30, "encode_vpass")) return rc;
+  cnp_sweep_args a;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, true, &a)) return rc;
+  if (a.S.n_sets == 0) return 0;
+  enc_vpass_kernel<<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a, eps);
+  CNP_LAUNCH_CHECK("enc_vpass_kernel");
+  return 0;
+}
+
+// Launch 3.  mode 0: writes the channels of the OFF-GRID sets into out_f32 [B][c_total][n1][n2] (batch stride out_bstride
+// floats; the gridded sets' V planes point into the same tensor and were written by launch 2).  mode 1: out_blk = blocked
+// bf16 view with n_chunks >= (c_total + 1 + 7) / 8 chunks: channels [0, c_total) = the encoder output (gridded channels
+// gathered from the V planes), channel c_total = 1, rest 0.
 CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
                              float eps, int mode, float* out_f32, long long out_bstride, int c_total,
                              const cnp_blk* out_blk, int n_chunks, cudaStream_t st) {
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0 && (mode == 0 || mode == 1), "encode_fused: bad arguments");
   CNP_REQUIRE(mode == 0 ? out_f32 != nullptr : (out_blk != nullptr && n_chunks * 8 >= c_total + 1),
               "encode_fused: output does not match mode %d", mode);
+  CNP_REQUIRE(c_total + 1 <= MAXCH && n_chunks * 8 <= MAXCH, "encode_fused: more than %d channels", MAXCH);
   if (int rc = ef_check_sets(sets, c_total, "encode_fused")) return rc;
   if (mode == 1) CNP_REQUIRE(out_blk->H == n1 && out_blk->W == n2, "encode_fused: blocked output geometry mismatch");
-  const int CP = mode == 1 ? n_chunks * 8 : c_total;
-  const long long smem = ef_smem(CP);
-  CNP_REQUIRE(smem <= 200 * 1024, "encode_fused: %d staged channels do not fit in shared memory", CP);
+  cnp_asm_args A;
+  memset(&A, 0, sizeof(A));
+  for (int c = 0; c < MAXCH; ++c) A.og_map[c] = -1;
+  int n = 0, slot = 0;
+  for (int k = 0; k < sets->n_sets; ++k) {
+    const cnp_enc_set& s = sets->s[k];
+    if (s.kind == 1) {
+      for (int c = 0; c <= s.C; ++c) {
+        A.cptr[s.ch_off + c] = s.V + (size_t)c * n1 * n2;
+        A.cbs[s.ch_off + c] = s.batched ? s.V_bs : 0;
+      }
+    } else {
+      A.S.s[n] = s;
+      A.og_off[n] = slot;
+      for (int c = 0; c <= s.C; ++c) A.og_map[s.ch_off + c] = (short)(slot + c);
+      slot += s.C + 1;
+      ++n;
+    }
+  }
+  A.S.n_sets = n;
+  A.n_og_ch = slot;
+  if (mode == 0 && n == 0) return 0;               // nothing left to write
+  const long long smem = ef_smem(slot);
+  CNP_REQUIRE(smem <= 200 * 1024, "encode_fused: %d off-grid channels do not fit in shared memory", slot);
   static long long attr[2] = {0, 0};
   if (smem > attr[mode] && smem > 48 * 1024) {
     cudaError_t e = mode == 0
@@ -498,21 +525,16 @@ CNP_API int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int
     if (e != cudaSuccess) { cnp_set_error("encode_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr[mode] = smem;
   }
-  // tasks per CTA: sets that every task shares are encoded once per CTA, so larger batches walk 4 tasks per CTA
-  // (B = 16 at 304^2: 760 CTAs of 128 threads, one wave on 148 SMs)
-  bool shared_sets = false;
-  for (int k = 0; k < sets->n_sets; ++k) shared_sets |= (sets->s[k].kind == 1 && !sets->s[k].batched);
-  const int TB = (shared_sets && B >= 8) ? 4 : (shared_sets && B >= 2 ? 2 : 1);
-  dim3 grid(cnp_cdiv(n2, TJ), cnp_cdiv(n1, TI), cnp_cdiv(B, TB));
+  dim3 grid(cnp_cdiv(n2, TJ), cnp_cdiv(n1, TI), B);
   cnp_blk ob;
   memset(&ob, 0, sizeof(ob));
   if (out_blk) ob = *out_blk;
   if (mode == 0)
-    enc_fused_kernel<0><<<grid, NT, smem, st>>>(*sets, B, TB, start1, n1, start2, n2, res, eps, out_f32, out_bstride,
-                                                c_total, ob, n_chunks, CP);
+    enc_fused_kernel<0><<<grid, NT, smem, st>>>(A, start1, n1, start2, n2, res, eps, out_f32, out_bstride, c_total, ob,
+                                                n_chunks);
   else
-    enc_fused_kernel<1><<<grid, NT, smem, st>>>(*sets, B, TB, start1, n1, start2, n2, res, eps, out_f32, out_bstride,
-                                                c_total, ob, n_chunks, CP);
+    enc_fused_kernel<1><<<grid, NT, smem, st>>>(A, start1, n1, start2, n2, res, eps, out_f32, out_bstride, c_total, ob,
+                                                n_chunks);
   CNP_LAUNCH_CHECK("enc_fused_kernel");
   return 0;
 }

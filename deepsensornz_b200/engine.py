@@ -458,58 +458,67 @@ class Engine:
                 self._enc_tabs[key] = ent
         return ent
 
-    def _enc_sets(self, entries, grid: GridSpec, B: int):
+    def _enc_sets(self, entries, grid: GridSpec, B: int, enc: Optional[torch.Tensor]):
+        """The C-ABI description of the context sets.  ``enc`` given (fp32 mode): the V planes of the gridded sets are the
+        channels of ``enc`` themselves; else they live in a workspace the assembly kernel gathers from."""
         K = _cabi
         sets = K.CnpEncSets()
-        t_bytes = 0
+        t_bytes = v_bytes = 0
+        plane = grid.n1 * grid.n2
         for n, (k, c, ch, s2) in enumerate(entries):
             e = sets.s[n]
             Ck = self.cfg.dim_yc[k]
             e.kind, e.C, e.ch_off, e.scale2 = (1 if c.gridded else 0), Ck, ch, s2
             if c.gridded:
                 e.batched = int(c.y_batched and B > 1)
+                nb = B if e.batched else 1
                 e.N1, e.N2 = int(c.x[0].shape[-1]), int(c.x[1].shape[-1])
                 e.mono1, e.mono2 = c.mono
                 e.KB, ti, tw = self._enc_tables(c, grid, s2)
                 e.tab_i, e.tab_w = ti.data_ptr(), tw.data_ptr()
-                T = self._buf(f"enc_T{k}", (B if e.batched else 1, Ck + 1, e.N1, grid.n2))
+                T = self._buf(f"enc_T{k}", (nb, Ck + 1, e.N1, grid.n2))
                 e.T = T.data_ptr()
+                if enc is not None:
+                    e.V, e.V_bs = enc.data_ptr() + 4 * ch * plane, enc.stride(0)
+                else:
+                    V = self._buf(f"enc_V{k}", (nb, Ck + 1, grid.n1, grid.n2))
+                    e.V, e.V_bs = V.data_ptr(), V.stride(0)
                 t_bytes += 4 * T.numel()
+                v_bytes += 4 * nb * (Ck + 1) * plane
             else:
                 e.batched = 1
                 e.x1, e.N1 = _ptr(c.x), int(c.x.shape[-1])
             e.y = _ptr(c.y)
             e.mask = _ptr(c.mask)
         sets.n_sets = len(entries)
-        return sets, t_bytes
+        return sets, t_bytes, v_bytes
 
     def _encode_fused(self, batch: DeviceBatch, plan: dict, enc: Optional[torch.Tensor] = None,
                       blk: Optional["_Blk"] = None) -> bool:
-        """Launch the fused encoder into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel): the horizontal
-        pass of every gridded set, then the per-tile launch.  False when the staging does not fit in shared memory (the
-        caller falls back to the per-set kernels)."""
-        K = _cabi
+        """Launch the fused encoder (enc_fused.cu) into ``enc`` (fp32 NCHW) or ``blk`` (blocked bf16 + constant-1 channel):
+        horizontal pass and vertical pass of every gridded set, then the off-grid sets + assembly per tile."""
         cfg, g, B = self.cfg, batch.grid, batch.B
-        lib = K.lib()
         Cin = cfg.in_channels
-        mode = 1 if blk is not None else 0
-        if lib.cnp_encode_fused_smem_bytes(mode, blk.CB * 8 if blk is not None else Cin) <= 0:
-            return False
         n_in = lambda c: 4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0))
         S = _stream()
         entries = sorted(plan["per_task"] + plan["static"], key=lambda t: t[0])
-        sets, t_bytes = self._enc_sets(entries, g, B)
+        sets, t_bytes, v_bytes = self._enc_sets(entries, g, B, enc)
         by_grid = sum(n_in(c) for _, c, _, _ in entries if c.gridded)
         by_off = sum(n_in(c) for _, c, _, _ in entries if not c.gridded)
         if any(c.gridded for _, c, _, _ in entries):
             self._call("cnp_encode_hpass", C.byref(sets), B, g.n1, g.n2, S, work=(0.0, by_grid + t_bytes))
+            self._call("cnp_encode_vpass", C.byref(sets), B, g.n1, g.n2, cfg.epsilon, S, work=(0.0, t_bytes + v_bytes))
         if blk is not None:
             bv = blk.view()
             self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 1, None, 0,
-                       Cin, C.byref(bv), blk.CB, S, work=(0.0, by_off + t_bytes + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
+                       Cin, C.byref(bv), blk.CB, S, work=(0.0, by_off + v_bytes + 2.0 * B * blk.CB * 8 * g.n1 * g.n2))
         else:
+            n_og = sum(cfg.dim_yc[k] + 1 for k, c, _, _ in entries if not c.gridded)
             self._call("cnp_encode_fused", C.byref(sets), B, g.start1, g.n1, g.start2, g.n2, g.res, cfg.epsilon, 0,
-                       _ptr(enc), enc.stride(0), Cin, None, 0, S, work=(0.0, by_off + t_bytes + 4.0 * enc.numel()))
+                       _ptr(enc), enc.stride(0), Cin, None, 0, S, work=(0.0, by_off + 4.0 * B * n_og * g.n1 * g.n2))
+            for k, c, ch, _ in plan["static"]:      # a field every task shares was encoded for task 0: broadcast
+                Ck = cfg.dim_yc[k]
+                enc[1:, ch:ch + Ck + 1].copy_(enc[:1, ch:ch + Ck + 1].expand(B - 1, -1, -1, -1))
         return True
 
     def encode_blocked(self, batch: DeviceBatch) -> Optional["_Blk"]:

@@ -90,13 +90,15 @@ typedef struct cnp_blk {
  * nzdownscale/downscaler/train.py:370, validate_ERA.py:88-92.
  *   cnp_encode_tables : band tables of one gridded set; they depend only on (coordinates, internal grid, length scale)
  *                       -- build once, keep across steps.
- *   cnp_encode_hpass  : horizontal band pass of every gridded set of ``sets`` into its T workspace.
- *   cnp_encode_fused  : one CTA = one 16 x 32 tile of the internal grid and up to 4 consecutive tasks: vertical pass of
- *                       the gridded sets (fields every task shares -- batched = 0: static topography / land mask --
- *                       once per CTA), off-grid sets, density normalisation.
- * mode 0: fp32 NCHW out_f32 [B][c_total][n1][n2]; mode 1: blocked bf16 out_blk with n_chunks chunks: channels
- * [0, c_total) = encoder output, channel c_total = 1 inside the image (folded first layer, cnp_fold_in_fwd), rest 0.
- * Gridded sets need monotone coordinates shared by the batch. */
+ *   cnp_encode_hpass  : horizontal band pass of every gridded set of ``sets`` into its T workspace (one thread per
+ *                       (task, input row, grid column), all channels).
+ *   cnp_encode_vpass  : vertical band pass + density normalisation, T -> V fp32 planes (one thread per (task, grid row,
+ *                       grid column)); a field every task shares (batched = 0: static topography / land mask) is done once.
+ *   cnp_encode_fused  : one CTA = one 16 x 32 tile of one task: off-grid sets, then assembly of the output tile.
+ * mode 0: fp32 NCHW out_f32 [B][c_total][n1][n2]: the gridded sets' V planes point INTO out_f32 (vpass writes the final
+ * channels), cnp_encode_fused adds the off-grid channels.  mode 1: blocked bf16 out_blk with n_chunks chunks: channels
+ * [0, c_total) = encoder output (gridded channels gathered from the V planes), channel c_total = 1 inside the image
+ * (folded first layer, cnp_fold_in_fwd), rest 0.  Gridded sets need monotone coordinates shared by the batch. */
 typedef struct cnp_enc_set {
   int kind;            /* 0 off-grid, 1 gridded */
   int C;               /* data channels (1..8) */
@@ -113,6 +115,8 @@ typedef struct cnp_enc_set {
   const int* tab_i;    /* gridded: [p0 (n1) | len1 (n1) | q0 (n2) | len2 (n2)], from cnp_encode_tables */
   const float* tab_w;  /* gridded: [w1 (KB x n1) | w2 (KB x n2)] */
   float* T;            /* gridded: horizontal-pass workspace [B or 1][C+1][N1][n2] */
+  float* V;            /* gridded: normalised output planes, channel stride n1*n2 floats */
+  long long V_bs;      /*          batch stride of V in floats */
 } cnp_enc_set;
 typedef struct cnp_enc_sets { int n_sets; int pad_; cnp_enc_set s[8]; } cnp_enc_sets;   /* HOST struct, passed by value to the kernels */
 /* tab_i: 2 * (n1 + n2) ints, tab_w: band * (n1 + n2) floats; band = host-side upper bound (<= 32) of the number of inputs
@@ -120,8 +124,8 @@ typedef struct cnp_enc_sets { int n_sets; int pad_; cnp_enc_set s[8]; } cnp_enc_
 int cnp_encode_tables(const float* x1 /*[N1]*/, const float* x2 /*[N2]*/, int N1, int N2, int mono1, int mono2,
                       double start1, int n1, double start2, int n2, double res, float scale2, int band,
                       int* tab_i, float* tab_w, cnp_stream_t s);
-long long cnp_encode_fused_smem_bytes(int mode, int channels_staged);   /* -1: does not fit */
 int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cnp_stream_t s);
+int cnp_encode_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, float eps, cnp_stream_t s);
 int cnp_encode_fused(const cnp_enc_sets* sets, int B, double start1, int n1, double start2, int n2, double res,
                      float eps, int mode, float* out_f32, long long out_bstride, int c_total, const cnp_blk* out_blk,
                      int n_chunks, cnp_stream_t s);

@@ -36,11 +36,11 @@ def main():
         torch.cuda.synchronize()
         pk = bench.peaks()
         d = {"launches": 0, "ms": 0.0, "bytes": 0.0}
-        for kname in ("cnp_encode_hpass", "cnp_encode_fused"):
+        for kname in ("cnp_encode_hpass", "cnp_encode_vpass", "cnp_encode_fused"):
             for f in d:
                 d[f] += prof[kname][f]
         out[name] = {"launches_per_call": d["launches"] // reps, "us_per_call_serial": d["ms"] / reps * 1e3,
-                     "us_hpass": prof["cnp_encode_hpass"]["ms"] / reps * 1e3, "us_fused": prof["cnp_encode_fused"]["ms"] / reps * 1e3,
+                     "us_hpass": prof["cnp_encode_hpass"]["ms"] / reps * 1e3, "us_vpass": prof["cnp_encode_vpass"]["ms"] / reps * 1e3, "us_fused": prof["cnp_encode_fused"]["ms"] / reps * 1e3,
                      "us_per_call_back_to_back": e0.elapsed_time(e1) / reps * 1e3,
                      "algorithmic_MB_per_call": d["bytes"] / reps / 1e6,
                      "GBps": d["bytes"] / (d["ms"] * 1e-3) / 1e9, "frac_of_hbm_peak": d["bytes"] / (d["ms"] * 1e-3) / 1e9 / pk["hbm"]}
