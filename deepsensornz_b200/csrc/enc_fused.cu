@@ -108,7 +108,7 @@ __device__ __forceinline__ const cnp_enc_set& sweep_decode(const cnp_sweep_args&
   while (k + 1 < a.S.n_sets && (int)blockIdx.x >= a.blk0[k + 1]) ++k;
   const int lb = (int)blockIdx.x - a.blk0[k];
   const int pr = lb / a.bpr;
-  *j = (lb - pr * a.bpr) * SW + threadIdx.x;
+  *j = (lb - pr * a.bpr) * (int)blockDim.x + threadIdx.x;
   *b = pr / a.rows[k];
   *row = pr - *b * a.rows[k];
   return a.S.s[k];
@@ -165,6 +165,39 @@ enc_hpass_kernel(const __grid_constant__ cnp_sweep_args a) {
   else { CNP_SWITCH_C(st.C, hpass_elem<CC, false>(st, b, p, j, a.n1, a.n2)) }
 }
 
+// one thread = 4 adjacent columns of one (task, grid row): the T rows are read with 16 B loads (n2 % 4 == 0), the
+// weight of a tap is the same for the 4 outputs
+template <int C>
+__device__ __forceinline__ void vpass_elem4(const cnp_enc_set& st, int b, int i, int j, int n1, int n2, float eps) {
+  const int p0 = __ldg(st.tab_i + i), len = __ldg(st.tab_i + n1 + i);
+  const float* w1 = st.tab_w + i;
+  const int tplane = st.N1 * n2;
+  const float* T = st.T + (size_t)b * (C + 1) * tplane + p0 * n2 + j;
+  float4 acc[C + 1];
+#pragma unroll
+  for (int c = 0; c <= C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+  for (int k = 0; k < len; ++k, T += n2) {
+    const float w = __ldg(w1 + k * n1);
+#pragma unroll
+    for (int c = 0; c <= C; ++c) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(T + c * tplane));
+      acc[c].x = fmaf(w, t.x, acc[c].x); acc[c].y = fmaf(w, t.y, acc[c].y);
+      acc[c].z = fmaf(w, t.z, acc[c].z); acc[c].w = fmaf(w, t.w, acc[c].w);
+    }
+  }
+  // density first, data divided by (density + eps)
+  const int plane = n1 * n2;
+  float* V = st.V + (size_t)b * st.V_bs + i * n2 + j;
+  const float4 d = acc[0];
+  const float4 inv = make_float4(1.0f / (d.x + eps), 1.0f / (d.y + eps), 1.0f / (d.z + eps), 1.0f / (d.w + eps));
+  *reinterpret_cast<float4*>(V) = d;
+#pragma unroll
+  for (int c = 1; c <= C; ++c)
+    *reinterpret_cast<float4*>(V + c * plane) =
+        make_float4(acc[c].x * inv.x, acc[c].y * inv.y, acc[c].z * inv.z, acc[c].w * inv.w);
+}
+
 template <int C>
 __device__ __forceinline__ void vpass_elem(const cnp_enc_set& st, int b, int i, int j, int n1, int n2, float eps) {
   const int p0 = __ldg(st.tab_i + i), len = __ldg(st.tab_i + n1 + i);
@@ -180,7 +213,6 @@ __device__ __forceinline__ void vpass_elem(const cnp_enc_set& st, int b, int i, 
 #pragma unroll
     for (int c = 0; c <= C; ++c) acc[c] = fmaf(w, __ldg(T + c * tplane + k * n2), acc[c]);
   }
-  // density first, data divided by (density + eps)
   const int plane = n1 * n2;
   float* V = st.V + (size_t)b * st.V_bs + i * n2 + j;
   const float dens = acc[0], inv = 1.0f / (dens + eps);
@@ -189,12 +221,20 @@ __device__ __forceinline__ void vpass_elem(const cnp_enc_set& st, int b, int i, 
   for (int c = 1; c <= C; ++c) V[c * plane] = acc[c] * inv;
 }
 
-__global__ void __launch_bounds__(SW)
+// VEC: the block sweeps 4 * SW columns, 4 per thread (needs n2 % 4 == 0 and 16 B aligned T / V planes)
+template <bool VEC>
+__global__ void __launch_bounds__(SW, 4)
 enc_vpass_kernel(const __grid_constant__ cnp_sweep_args a, float eps) {
   int b, i, j;
   const cnp_enc_set& st = sweep_decode(a, &b, &i, &j);
-  if (j >= a.n2) return;
-  CNP_SWITCH_C(st.C, vpass_elem<CC>(st, b, i, j, a.n1, a.n2, eps))
+  if (VEC) {
+    j *= 4;
+    if (j >= a.n2) return;
+    CNP_SWITCH_C(st.C, vpass_elem4<CC>(st, b, i, j, a.n1, a.n2, eps))
+  } else {
+    if (j >= a.n2) return;
+    CNP_SWITCH_C(st.C, vpass_elem<CC>(st, b, i, j, a.n1, a.n2, eps))
+  }
 }
 
 // =====================================================================================================================
@@ -433,9 +473,10 @@ static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who)
   return 0;
 }
 
-static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, cnp_sweep_args* a) {
+static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, int cols_per_block,
+                         cnp_sweep_args* a) {
   memset(a, 0, sizeof(*a));
-  a->n1 = n1; a->n2 = n2; a->bpr = cnp_cdiv(n2, SW);
+  a->n1 = n1; a->n2 = n2; a->bpr = cnp_cdiv(n2, cols_per_block);
   int n = 0;
   long long blocks = 0;
   for (int k = 0; k < sets->n_sets; ++k) {
@@ -460,7 +501,7 @@ CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cu
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_hpass: bad arguments");
   if (int rc = ef_check_sets(sets, 1 << 30, "encode_hpass")) return rc;
   cnp_sweep_args a;
-  if (int rc = ef_sweep_args(sets, B, n1, n2, false, &a)) return rc;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, false, SW, &a)) return rc;
   if (a.S.n_sets == 0) return 0;
   enc_hpass_kernel<<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
   CNP_LAUNCH_CHECK("enc_hpass_kernel");
@@ -472,10 +513,21 @@ CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cu
 CNP_API int cnp_encode_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, float eps, cudaStream_t st) {
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_vpass: bad arguments");
   if (int rc = ef_check_sets(sets, 1 << 30, "encode_vpass")) return rc;
+  bool vec = (n2 % 4 == 0);
+  for (int k = 0; k < sets->n_sets; ++k) {
+    const cnp_enc_set& s = sets->s[k];
+    if (s.kind != 1) continue;
+    vec = vec && ((uintptr_t)s.T % 16 == 0) && ((uintptr_t)s.V % 16 == 0) && (s.V_bs % 4 == 0) &&
+          (((long long)s.N1 * n2) % 4 == 0) && (((long long)n1 * n2) % 4 == 0);
+  }
+  // vector form: a block of `threads` lanes covers 4 * threads columns of one row (304 columns: 96 lanes, 79 % active)
+  int threads = SW;
+  if (vec) { threads = ((cnp_cdiv(n2, 4) + 31) / 32) * 32; if (threads > SW) threads = SW; }
   cnp_sweep_args a;
-  if (int rc = ef_sweep_args(sets, B, n1, n2, true, &a)) return rc;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, true, vec ? 4 * threads : threads, &a)) return rc;
   if (a.S.n_sets == 0) return 0;
-  enc_vpass_kernel<<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a, eps);
+  if (vec) enc_vpass_kernel<true><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
+  else enc_vpass_kernel<false><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
   CNP_LAUNCH_CHECK("enc_vpass_kernel");
   return 0;
 }
