@@ -62,22 +62,16 @@ constexpr int FW_PTS = 8;    // one target per warp per block: Nt ~ 40-200 targe
 
 __global__ void __launch_bounds__(256)
 mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
-                    const float* __restrict__ aux, int Ca, const float* __restrict__ yt, int Nt,
-                    float* __restrict__ mean, float* __restrict__ var, double* __restrict__ logp,
-                    int* __restrict__ count) {
+                    const float* __restrict__ aux, int Ca, int Nt, float* __restrict__ mean, float* __restrict__ var) {
   extern __shared__ __align__(16) float smem[];
   const Offsets o = make_offsets(p);
   float* ws = smem;
   float* act = smem + o.total;  // [8 warps][2][MAXW]
-  __shared__ double lp_s[8];
-  __shared__ int cnt_s[8];
   stage_weights(p, o, ws);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
   float* ha = act + warp * 2 * MAXW;
   float* hb = ha + MAXW;
-  double lp = 0.0;
-  int cnt = 0;
   const int t0 = blockIdx.x * FW_PTS;
   for (int t = t0 + warp; t < min(t0 + FW_PTS, Nt); t += 8) {
     for (int c = lane; c < Cf; c += 32) ha[c] = f[((size_t)b * f_ctotal + c) * Nt + t];
@@ -93,27 +87,34 @@ mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
       const float m = hin[0], v = 1e-6f + softplus_t(hin[1]);
       mean[(size_t)b * Nt + t] = m;
       var[(size_t)b * Nt + t] = v;
-      if (yt) {
-        const float yv = yt[(size_t)b * Nt + t];
-        if (!isnan(yv)) {
-          const double dm = (double)yv - (double)m, dv = (double)v;
-          lp += -0.5 * (1.8378770664093453 + log(dv) + dm * dm / dv);
-          cnt += 1;
-        }
-      }
     }
     __syncwarp();
   }
-  if (logp) {
-    if (lane == 0) { lp_s[warp] = lp; cnt_s[warp] = cnt; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0; int c = 0;
-      for (int w = 0; w < 8; ++w) { s += lp_s[w]; c += cnt_s[w]; }
-      atomicAdd(logp + b, s);
-      atomicAdd(count + b, c);
+}
+
+// logp[b] = sum_t log N(y_t; mean_t, var_t) in float64 over the non-NaN targets, count[b] = their number.  One warp per
+// task, a FIXED summation order (lane-strided partial sums, then a shuffle tree): the loss is run-to-run identical
+// (the first version added per-block partial sums with atomics, which reordered the float64 sum from run to run).
+__global__ void __launch_bounds__(32)
+head_logp_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ yt, int Nt,
+                 double* __restrict__ logp, int* __restrict__ count) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  double lp = 0.0;
+  int cnt = 0;
+  for (int t = lane; t < Nt; t += 32) {
+    const float yv = yt[(size_t)b * Nt + t];
+    if (!isnan(yv)) {
+      const double dm = (double)yv - (double)mean[(size_t)b * Nt + t], dv = (double)var[(size_t)b * Nt + t];
+      lp += -0.5 * (1.8378770664093453 + log(dv) + dm * dm / dv);
+      cnt += 1;
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) { logp[b] = lp; count[b] = cnt; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,8 +236,12 @@ CNP_API int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctot
   static size_t attr_f = 0;
   if (smem > attr_f) { cudaFuncSetAttribute(mlp_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_f = smem; }
   dim3 grid(cnp_cdiv(Nt, FW_PTS), B);
-  mlp_head_fwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, mean, var, logp, count);
+  mlp_head_fwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, Nt, mean, var);
   CNP_LAUNCH_CHECK("mlp_head_fwd_kernel");
+  if (logp) {
+    head_logp_kernel<<<B, 32, 0, st>>>(mean, var, yt, Nt, logp, count);
+    CNP_LAUNCH_CHECK("head_logp_kernel");
+  }
   return 0;
 }
 
