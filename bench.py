@@ -311,7 +311,7 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
     if world > 1:
         from deepsensornz_b200.dist import enable_data_parallel
         enable_data_parallel(model)
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("CONVNP_B200_DP_GRAPH", "1") == "1")
     # the reference's optimiser (train.py:354); fused=True is torch's single-kernel implementation of the same update
     opt = torch.optim.AdamW(model.model.parameters(), lr=5e-5, weight_decay=1e-5, fused=True, capturable=use_graph)
     eng = model.engine
@@ -342,8 +342,8 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
 
     for i in range(warmup):
         step(dev[i % 2])
-    # One-GPU runs replay the whole step (forward, NLL, backward, AdamW) as a CUDA graph (deepsensornz_b200/graph.py);
-    # the data-parallel step keeps eager launches around the NCCL all-reduce.
+    # The whole step (forward, NLL, backward, [bucketed NCCL all-reduces,] AdamW) is replayed as a CUDA graph
+    # (deepsensornz_b200/graph.py); CONVNP_B200_DP_GRAPH=0 keeps eager launches around NCCL at N > 1.
     gs = None
     if use_graph:
         from deepsensornz_b200.graph import GraphedTrainStep

@@ -641,7 +641,8 @@ class Engine:
         self._conv_f32(h, u.final_linear.weight, u.final_linear.bias, z, 1, 1, False)
         return z, A
 
-    def _unet_bwd_f32(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads: Dict[str, torch.Tensor], B, n1, n2):
+    def _unet_bwd_f32(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads: Dict[str, torch.Tensor], B, n1, n2,
+                      up_done=None):
         cfg, u = self.cfg, self.module.decoder.unet
         ch, st = cfg.unet_channels, cfg.unet_strides
         L = len(ch)
@@ -687,6 +688,8 @@ class Engine:
             relu_bwd(d_cat[i], cat[i])
             if i < L - 1:
                 dy = d_cat[i][:, ch[i]:]
+        if up_done is not None:
+            up_done()
         # down path, deepest first; gradients accumulate into the skip halves
         for i in range(L - 1, -1, -1):
             name = P + f"before_turn_layers.{i}"
@@ -881,7 +884,7 @@ class Engine:
         self._conv_tc(h_last.view(0), 8, wpk, K.KIND_K1, o, B)
         return z, A
 
-    def _unet_bwd_bf16(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads, B, n1, n2):
+    def _unet_bwd_bf16(self, dz: torch.Tensor, enc: torch.Tensor, A: dict, grads, B, n1, n2, up_done=None):
         """Backward of the bf16 UNet: tcgen05 dgrad and wgrad on the blocked bf16 activations."""
         K = _cabi
         cfg, u = self.cfg, self.module.decoder.unet
@@ -947,6 +950,8 @@ class Engine:
                 dgrad_tc(dy_blk.view(dy_cb), lyr.weight, f"after{i}", K.KIND_K5S1_DGRAD, nch, d_cat[i], 0, cat[i], 0)
             if i < L - 1:
                 dy_blk, dy_cb = d_cat[i], 8
+        if up_done is not None:          # gradients of the head, the final 1x1 and the up path are complete
+            up_done()
         for i in range(L - 1, -1, -1):
             name = P + f"before_turn_layers.{i}"
             lyr = u.before_turn_layers[i]
@@ -1152,12 +1157,30 @@ class Engine:
             raise _cabi.CnpError("backward() of a loss whose forward is no longer the engine's latest one: call "
                                  ".backward() before the next loss_fn / model(task) (one loss in flight per model)")
         named = [(n, p) for n, p in self.module.named_parameters() if n.startswith("decoder.") and p.dim() > 0]
+        # Flat gradient buffer in TWO buckets ordered by when the backward finishes them: [head MLP, final 1x1, up path]
+        # first, [down path, initial 1x1] second.  Data-parallel training all-reduces the first bucket while the
+        # down-path backward still runs (dist.enable_data_parallel; SURVEY 8(e): one 4.58 MB exchange per step).
+        first = lambda n: n.startswith(("decoder.mlp.", "decoder.unet.final_linear.", "decoder.unet.after_turn_layers."))
+        named = [t for t in named if first(t[0])] + [t for t in named if not first(t[0])]
         total = sum(p.numel() for _, p in named)
+        n_first = sum(p.numel() for n, p in named if first(n))
         flat = torch.zeros(total, dtype=torch.float32, device=self.device)
         grads, off = {}, 0
         for n, p in named:
             grads[n] = flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        dp = self.allreduce_group is not None and self.world_size > 1
+        pending = []
+
+        def reduce_bucket(t):
+            import torch.distributed as dist
+            if dist.get_backend(self.allreduce_group) == "nccl":      # mean over ranks inside the collective
+                pending.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.allreduce_group, async_op=True))
+            else:
+                dist.all_reduce(t, group=self.allreduce_group)
+                t.mul_(1.0 / self.world_size)
+
+        up_done = (lambda: reduce_bucket(flat[:n_first])) if dp else None
         f, z = ctx["f"], ctx["z"]
         Cz = cfg.unet_out_channels
         df = self._buf("df", (B, Cz, Nt))
@@ -1181,13 +1204,13 @@ class Engine:
             self._call("cnp_setconv_dec_offgrid_bwd", _ptr(df), Cz, _ptr(batch.xt), B, Cz, Nt, g.start1, g.n1, g.start2,
                        g.n2, g.res, s2, _ptr(dz), dz.stride(0), _stream(), work=(0.0, 4.0 * (dz.numel() + df.numel())))
         if self.precision == "fp32":
-            self._unet_bwd_f32(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2)
+            self._unet_bwd_f32(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2, up_done=up_done)
         else:
-            self._unet_bwd_bf16(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2)
-        if self.allreduce_group is not None and self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(flat, group=self.allreduce_group)
-            flat.mul_(1.0 / self.world_size)
+            self._unet_bwd_bf16(dz, ctx["enc"], ctx["A"], grads, B, g.n1, g.n2, up_done=up_done)
+        if dp:
+            reduce_bucket(flat[n_first:])
+            for w in pending:
+                w.wait()              # orders the current stream after the collectives (no host block with NCCL)
         self._flat_grad = flat
         self.weights_dirty = True     # an optimiser step follows a backward: the next forward re-packs the bf16 weights
         return grads

@@ -5,7 +5,8 @@ kernels and the Python/ctypes launch path cost ~5 % of the step.  All shapes of 
 as the batch signature (tasks per batch, context / target counts, internal grid) does not change -- which is what
 the reference's grouping by station count guarantees (nzdownscale/downscaler/train.py:448-475) -- so the whole
 step is captured once and replayed: inputs are copied into static device buffers, `graph.replay()` re-issues every
-kernel (encoder, weight packing, tcgen05 convolutions, decoder, head, wgrad, gradient all-reduce is NOT captured).
+kernel (encoder, weight packing, tcgen05 convolutions, decoder, head, wgrad, and -- data-parallel -- the two bucketed NCCL
+all-reduces).  Release the graph (``del``) and synchronise before ``destroy_process_group``.
 
 Usage (what ``train_epoch(..., use_graph=True)`` and ``bench.py`` do):
 
@@ -54,8 +55,8 @@ class GraphedTrainStep:
         """``warm=True``: an eager step with this batch signature has already run on this model (workspaces, side
         streams and host caches exist), so no warm-up steps -- and no extra optimiser updates -- are made here."""
         eng = model.engine
-        if eng.allreduce_group is not None and eng.world_size > 1:
-            raise RuntimeError("graph capture of the data-parallel step is not supported (NCCL all-reduce inside backward)")
+        # data-parallel: the two bucketed NCCL all-reduces of Engine.backward are captured with the step (they become
+        # graph nodes on NCCL's stream, so the first still overlaps the down-path backward in every replay)
         self.model, self.opt, self.eng = model, opt, eng
         self.signature = batch_signature(example)
         clone = lambda t: None if t is None else t.clone()

@@ -80,7 +80,7 @@ def train_epoch(model, tasks: List[Task], lr: float = 5e-5, batch_size: Optional
         except Exception:
             pass
     dp = getattr(model.engine, "world_size", 1) > 1
-    use_graph = bool(use_graph) and can_stage and not dp      # the data-parallel step launches eagerly around NCCL
+    use_graph = bool(use_graph) and can_stage
     graphs = model.__dict__.setdefault("_train_graphs", {}) if use_graph else None
     losses = []
     # The loss of batch i is copied to page-locked memory asynchronously and READ while batch i+1 is already queued:
