@@ -26,6 +26,7 @@ class CnpMlpParams(C.Structure):
         ("db", C.c_void_p * 6),
         ("dims", C.c_int * 7),
         ("n_layers", C.c_int),
+        ("likelihood", C.c_int),
     ]
 
 
@@ -67,6 +68,9 @@ class CnpEncSet(C.Structure):
 class CnpEncSets(C.Structure):
     _fields_ = [("n_sets", C.c_int), ("pad_", C.c_int), ("s", CnpEncSet * 8)]
 
+
+LIKELIHOODS = {"cnp": 0, "het": 0, "bernoulli-gamma": 1, "cnp-spikes-beta": 2, "spikes-beta": 2}
+LIK_CHANNELS = {0: 2, 1: 4, 2: 5}      # head inputs per target variable
 
 # conv_tc kinds (must match conv_bf16.cu)
 KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD, KIND_UP_PHASE = range(7)
@@ -117,7 +121,7 @@ _SIGS = {
     "cnp_decode_grid_tc_fwd": (C.c_int, [C.POINTER(CnpBlk), c_fp, c_fp, _i, _i, _i, _d, _d, _d, _f, c_fp, c_fp,
                                          C.POINTER(CnpMlpParams), c_fp, _ll, _i, c_fp, c_fp, c_fp, _ll, c_stream]),
     # (4) MLP + Gaussian head + NLL
-    "cnp_mlp_head_fwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp,
+    "cnp_mlp_head_fwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp, c_fp,
                                    c_fp, c_stream]),
     "cnp_mlp_head_bwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp,
                                    c_stream]),

@@ -1,11 +1,18 @@
-// Fused aux-at-target MLP + heterogeneous Gaussian head + normalised NLL, forward and backward.
+// Fused aux-at-target MLP + likelihood head + normalised NLL, forward and backward.
 //
-// Replaces upstream neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood ->
-// MultiOutputNormal.logpdf -> nps.loglik(normalise=True) (U11) as reached from
-// ConvNP.loss_fn (nzdownscale/downscaler/train.py:370) and train_epoch (train.py:388-394).
-//   o = MLP([f ; aux_t]);  mean = o0;  var = 1e-6 + softplus(o1);
-//   logp_b = -1/2 sum_t [log 2pi + log var + (y-mean)^2/var]   (float64, NaN targets skipped)
-// The backward recomputes the (tiny) forward instead of saving activations.
+// Replaces upstream neuralprocesses Augment -> MLP -> likelihood -> logpdf -> nps.loglik(normalise=True)
+// (U11) as reached from ConvNP.loss_fn (nzdownscale/downscaler/train.py:370) and train_epoch
+// (train.py:388-394), for the likelihoods nzdownscale/dataprocess/config.py:162-169 selects per variable:
+//   Gaussian ('cnp'):            o = MLP([f ; aux_t]);  mean = o0;  var = 1e-6 + softplus(o1);
+//                                logp_b = -1/2 sum_t [log 2pi + log var + (y-mean)^2/var]
+//   Bernoulli-Gamma (precip.):   k = 1e-6 + softplus(o0), scale = 1e-6 + softplus(o1), (l_zero, l_slab) = (o2, o3);
+//                                log p(y) = log_softmax(l)_zero            if y == 0
+//                                         = log_softmax(l)_slab + log Gamma(y; k, scale)   otherwise
+//   spikes-Beta (humidity):      alpha = 1e-6 + softplus(o0), beta = 1e-6 + softplus(o1), (l_0, l_1, l_slab) = o2..4;
+//                                log p(y) = log_softmax(l)_0 | _1          if y == 0 | y == 1
+//                                         = log_softmax(l)_slab + log Beta(clamp(y, eps, 1-eps); alpha, beta)   otherwise
+//   (upstream neuralprocesses SpikesSlab: spikes first, slab last -- [U], SURVEY 8(c): restated from memory)
+// All log-pdfs in float64, NaN targets skipped.  The backward recomputes the (tiny) forward instead of saving activations.
 #include "common.cuh"
 #include <math.h>
 
@@ -35,6 +42,64 @@ __host__ __device__ inline Offsets make_offsets(const cnp_mlp_params& p) {
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_t(float x) { return x > 20.f ? 1.f : 1.f / (1.f + expf(-x)); }
 
+constexpr double LIK_EPS = 1e-6;
+
+// digamma(x), x > 0: recurrence up to x >= 6, then the asymptotic series (|error| < 1e-12)
+__device__ double digamma_d(double x) {
+  double r = 0.0;
+  while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+}
+
+__host__ __device__ inline int lik_channels(int lik) { return lik == CNP_LIK_GAUSS ? 2 : (lik == CNP_LIK_BERNOULLI_GAMMA ? 4 : 5); }
+
+// Parameters of the spikes-and-slab likelihoods from the raw head inputs z: a = 1e-6 + softplus(z0), b = 1e-6 +
+// softplus(z1) in fp32 like the model outputs, log-probabilities normalised in float64.  lp[] = spikes..., slab.
+struct SpikeSlab {
+  double a, b;        // Gamma: (k, scale); Beta: (alpha, beta)
+  double lp[3];
+  int n_spikes;
+};
+__device__ __forceinline__ SpikeSlab spike_slab_of(const float* z, int lik) {
+  SpikeSlab s;
+  s.a = (double)(1e-6f + softplus_t(z[0]));
+  s.b = (double)(1e-6f + softplus_t(z[1]));
+  s.n_spikes = lik == CNP_LIK_BERNOULLI_GAMMA ? 1 : 2;
+  double mx = -INFINITY;
+  for (int i = 0; i <= s.n_spikes; ++i) mx = fmax(mx, (double)z[2 + i]);
+  double se = 0.0;
+  for (int i = 0; i <= s.n_spikes; ++i) se += exp((double)z[2 + i] - mx);
+  const double lse = mx + log(se);
+  for (int i = 0; i <= s.n_spikes; ++i) s.lp[i] = (double)z[2 + i] - lse;
+  return s;
+}
+// category of an observation: spike index, or n_spikes for the slab
+__device__ __forceinline__ int spike_of(float y, int lik) {
+  if (y == 0.f) return 0;
+  if (lik == CNP_LIK_SPIKES_BETA && y == 1.f) return 1;
+  return lik == CNP_LIK_BERNOULLI_GAMMA ? 1 : 2;
+}
+__device__ __forceinline__ double slab_logpdf(const SpikeSlab& s, float y, int lik) {
+  if (lik == CNP_LIK_BERNOULLI_GAMMA) {
+    const double x = (double)y;
+    return (s.a - 1.0) * log(x) - x / s.b - lgamma(s.a) - s.a * log(s.b);
+  }
+  const double x = fmin(fmax((double)y, LIK_EPS), 1.0 - LIK_EPS);
+  return (s.a - 1.0) * log(x) + (s.b - 1.0) * log1p(-x) - (lgamma(s.a) + lgamma(s.b) - lgamma(s.a + s.b));
+}
+// distribution mean and variance (what ConvNP.mean / .std / predict report)
+__device__ __forceinline__ void spike_slab_moments(const SpikeSlab& s, int lik, float* mean, float* var) {
+  double m1, m2;   // slab mean and second moment
+  if (lik == CNP_LIK_BERNOULLI_GAMMA) { m1 = s.a * s.b; m2 = s.a * (s.a + 1.0) * s.b * s.b; }
+  else { const double t = s.a + s.b; m1 = s.a / t; m2 = s.a * s.b / (t * t * (t + 1.0)) + m1 * m1; }
+  const double ps = exp(s.lp[s.n_spikes]);
+  double m = ps * m1, e2 = ps * m2;
+  if (lik == CNP_LIK_SPIKES_BETA) { const double p1 = exp(s.lp[1]); m += p1; e2 += p1; }   // spike at 1 (spike at 0 adds 0)
+  *mean = (float)m;
+  *var = (float)fmax(e2 - m * m, 0.0);
+}
+
 __device__ void stage_weights(const cnp_mlp_params& p, const Offsets& o, float* ws) {
   for (int l = 0; l < p.n_layers; ++l) {
     const int in = p.dims[l], out = p.dims[l + 1];
@@ -62,7 +127,8 @@ constexpr int FW_PTS = 8;    // one target per warp per block: Nt ~ 40-200 targe
 
 __global__ void __launch_bounds__(256)
 mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
-                    const float* __restrict__ aux, int Ca, int Nt, float* __restrict__ mean, float* __restrict__ var) {
+                    const float* __restrict__ aux, int Ca, int Nt, float* __restrict__ mean, float* __restrict__ var,
+                    float* __restrict__ zraw) {
   extern __shared__ __align__(16) float smem[];
   const Offsets o = make_offsets(p);
   float* ws = smem;
@@ -84,9 +150,15 @@ mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
       float* tmp = hin; hin = hout; hout = tmp;
     }
     if (lane == 0) {
-      const float m = hin[0], v = 1e-6f + softplus_t(hin[1]);
-      mean[(size_t)b * Nt + t] = m;
-      var[(size_t)b * Nt + t] = v;
+      if (p.likelihood == CNP_LIK_GAUSS) {
+        mean[(size_t)b * Nt + t] = hin[0];
+        var[(size_t)b * Nt + t] = 1e-6f + softplus_t(hin[1]);
+      } else {
+        const int nz = lik_channels(p.likelihood);
+        for (int c = 0; c < nz; ++c) zraw[((size_t)b * nz + c) * Nt + t] = hin[c];
+        const SpikeSlab ss = spike_slab_of(hin, p.likelihood);
+        spike_slab_moments(ss, p.likelihood, mean + (size_t)b * Nt + t, var + (size_t)b * Nt + t);
+      }
     }
     __syncwarp();
   }
@@ -96,16 +168,25 @@ mlp_head_fwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
 // task, a FIXED summation order (lane-strided partial sums, then a shuffle tree): the loss is run-to-run identical
 // (the first version added per-block partial sums with atomics, which reordered the float64 sum from run to run).
 __global__ void __launch_bounds__(32)
-head_logp_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ yt, int Nt,
-                 double* __restrict__ logp, int* __restrict__ count) {
+head_logp_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ zraw,
+                 int lik, const float* __restrict__ yt, int Nt, double* __restrict__ logp, int* __restrict__ count) {
   const int b = blockIdx.x, lane = threadIdx.x;
   double lp = 0.0;
   int cnt = 0;
   for (int t = lane; t < Nt; t += 32) {
     const float yv = yt[(size_t)b * Nt + t];
     if (!isnan(yv)) {
-      const double dm = (double)yv - (double)mean[(size_t)b * Nt + t], dv = (double)var[(size_t)b * Nt + t];
-      lp += -0.5 * (1.8378770664093453 + log(dv) + dm * dm / dv);
+      if (lik == CNP_LIK_GAUSS) {
+        const double dm = (double)yv - (double)mean[(size_t)b * Nt + t], dv = (double)var[(size_t)b * Nt + t];
+        lp += -0.5 * (1.8378770664093453 + log(dv) + dm * dm / dv);
+      } else {
+        const int nz = lik_channels(lik);
+        float z[5];
+        for (int c = 0; c < nz; ++c) z[c] = zraw[((size_t)b * nz + c) * Nt + t];
+        const SpikeSlab ss = spike_slab_of(z, lik);
+        const int cat = spike_of(yv, lik);
+        lp += ss.lp[cat] + (cat == ss.n_spikes ? slab_logpdf(ss, yv, lik) : 0.0);
+      }
       cnt += 1;
     }
   }
@@ -163,16 +244,41 @@ mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
     // head gradient
     float* gL = dpre + goff[L - 1] * BW_PTS + pt * p.dims[L];
     if (lane == 0) {
-      const float m = tmp[0], z1 = tmp[1], v = 1e-6f + softplus_t(z1);
       const float yv = yt[(size_t)b * Nt + t];
-      float dm = 0.f, dz = 0.f;
-      if (!isnan(yv)) {
-        const float r = yv - m;
-        dm = gl * (r / v);
-        const float dvv = gl * (-0.5f) * (1.f / v - r * r / (v * v));
-        dz = dvv * sigmoid_t(z1);
+      if (p.likelihood == CNP_LIK_GAUSS) {
+        const float m = tmp[0], z1 = tmp[1], v = 1e-6f + softplus_t(z1);
+        float dm = 0.f, dz = 0.f;
+        if (!isnan(yv)) {
+          const float r = yv - m;
+          dm = gl * (r / v);
+          const float dvv = gl * (-0.5f) * (1.f / v - r * r / (v * v));
+          dz = dvv * sigmoid_t(z1);
+        }
+        gL[0] = dm; gL[1] = dz;
+      } else {
+        const int lik = p.likelihood, nz = lik_channels(lik);
+        for (int c = 0; c < nz; ++c) gL[c] = 0.f;
+        if (!isnan(yv)) {
+          const SpikeSlab ss = spike_slab_of(tmp, lik);
+          const int cat = spike_of(yv, lik);
+          // d log p / d l_j = [j == cat] - softmax(l)_j
+          for (int i = 0; i <= ss.n_spikes; ++i) gL[2 + i] = gl * (float)((i == cat ? 1.0 : 0.0) - exp(ss.lp[i]));
+          if (cat == ss.n_spikes) {
+            double da, db;      // d slab_logpdf / d (a, b)
+            if (lik == CNP_LIK_BERNOULLI_GAMMA) {
+              const double x = (double)yv;
+              da = log(x) - digamma_d(ss.a) - log(ss.b);
+              db = x / (ss.b * ss.b) - ss.a / ss.b;
+            } else {
+              const double x = fmin(fmax((double)yv, LIK_EPS), 1.0 - LIK_EPS), dg = digamma_d(ss.a + ss.b);
+              da = log(x) - digamma_d(ss.a) + dg;
+              db = log1p(-x) - digamma_d(ss.b) + dg;
+            }
+            gL[0] = gl * (float)da * sigmoid_t(tmp[0]);
+            gL[1] = gl * (float)db * sigmoid_t(tmp[1]);
+          }
+        }
       }
-      gL[0] = dm; gL[1] = dz;
     }
     __syncwarp();
     // backward through the layers
@@ -215,7 +321,9 @@ mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
 int check_params(const cnp_mlp_params* p, int Cf, int Ca) {
   CNP_REQUIRE(p && p->n_layers >= 1 && p->n_layers <= CNP_MLP_MAX_LAYERS, "mlp_head: 1..%d layers", CNP_MLP_MAX_LAYERS);
   CNP_REQUIRE(p->dims[0] == Cf + Ca, "mlp_head: dims[0]=%d != Cf+Ca=%d", p->dims[0], Cf + Ca);
-  CNP_REQUIRE(p->dims[p->n_layers] == 2, "mlp_head: last layer must have 2 outputs (mean, pre-softplus var)");
+  CNP_REQUIRE(p->likelihood >= 0 && p->likelihood <= 2, "mlp_head: unknown likelihood %d", p->likelihood);
+  CNP_REQUIRE(p->dims[p->n_layers] == lik_channels(p->likelihood), "mlp_head: likelihood %d needs %d head inputs, the MLP has %d",
+              p->likelihood, lik_channels(p->likelihood), p->dims[p->n_layers]);
   for (int l = 0; l <= p->n_layers; ++l)
     CNP_REQUIRE(p->dims[l] >= 1 && p->dims[l] <= MAXW, "mlp_head: layer width %d out of range (<=%d)", p->dims[l], MAXW);
   return 0;
@@ -224,9 +332,10 @@ int check_params(const cnp_mlp_params* p, int Cf, int Ca) {
 }  // namespace
 
 CNP_API int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
-                             const float* yt, int B, int Nt, float* mean, float* var, double* logp, int* count,
+                             const float* yt, int B, int Nt, float* mean, float* var, float* zraw, double* logp, int* count,
                              cudaStream_t st) {
   if (int e = check_params(p, Cf, Ca)) return e;
+  CNP_REQUIRE(p->likelihood == CNP_LIK_GAUSS || zraw != nullptr, "mlp_head_fwd: this likelihood needs the zraw buffer");
   CNP_REQUIRE(B > 0 && Nt >= 0 && f_ctotal >= Cf, "mlp_head_fwd: bad sizes");
   CNP_REQUIRE(logp == nullptr || (yt != nullptr && count != nullptr), "mlp_head_fwd: logp needs yt and count");
   if (Nt == 0) return 0;
@@ -236,10 +345,10 @@ CNP_API int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctot
   static size_t attr_f = 0;
   if (smem > attr_f) { cudaFuncSetAttribute(mlp_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_f = smem; }
   dim3 grid(cnp_cdiv(Nt, FW_PTS), B);
-  mlp_head_fwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, Nt, mean, var);
+  mlp_head_fwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, Nt, mean, var, zraw);
   CNP_LAUNCH_CHECK("mlp_head_fwd_kernel");
   if (logp) {
-    head_logp_kernel<<<B, 32, 0, st>>>(mean, var, yt, Nt, logp, count);
+    head_logp_kernel<<<B, 32, 0, st>>>(mean, var, zraw, p->likelihood, yt, Nt, logp, count);
     CNP_LAUNCH_CHECK("head_logp_kernel");
   }
   return 0;

@@ -6,6 +6,10 @@ struct cnp_mlp_params {
   const float* b[CNP_MLP_MAX_LAYERS];   // [out]
   float* dW[CNP_MLP_MAX_LAYERS];        // (+=) gradients, backward only
   float* db[CNP_MLP_MAX_LAYERS];
-  int dims[CNP_MLP_MAX_LAYERS + 1];     // dims[0] = Cf + Ca, dims[n_layers] = 2
+  int dims[CNP_MLP_MAX_LAYERS + 1];     // dims[0] = Cf + Ca, dims[n_layers] = head inputs (2 | 4 | 5)
   int n_layers;
+  int likelihood;                       // CNP_LIK_*: 0 heteroscedastic Gaussian, 1 Bernoulli-Gamma, 2 spikes-Beta
 };
+#define CNP_LIK_GAUSS 0
+#define CNP_LIK_BERNOULLI_GAMMA 1
+#define CNP_LIK_SPIKES_BETA 2

@@ -1022,6 +1022,7 @@ class Engine:
         p = CnpMlpParams()
         layers = self.module.decoder.mlp.layers
         p.n_layers = len(layers)
+        p.likelihood = _cabi.LIKELIHOODS[self.cfg.likelihood]
         dims = self.module.mlp_dims()
         for i, d in enumerate(dims):
             p.dims[i] = d
@@ -1055,7 +1056,9 @@ class Engine:
         if self.precision == "fp32":
             z, A = self._unet_fwd_f32(enc, B, g.n1, g.n2)
         else:
-            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=False, x_aug=x_aug)
+            # the fused on-grid decoders carry the Gaussian head only: other likelihoods decode from z (unfused)
+            z, A = self._unet_fwd_bf16(enc, B, g.n1, g.n2, need_z=(on_grid and cfg.likelihood not in ("cnp", "het")),
+                                       x_aug=x_aug)
             if not os.environ.get("CNP_NO_PREPACK"):
                 self.weights_dirty = False     # every known packing (forward and dgrad) was refreshed by _prepack_all
         Cz = cfg.unet_out_channels
@@ -1084,9 +1087,10 @@ class Engine:
         Ca = cfg.dim_aux_t
         if batch.aux_t is None or batch.aux_t.shape[1] != Ca:
             raise ValueError(f"task needs Y_t_aux with {Ca} channels")
+        zraw = None if p.likelihood == 0 else self._buf("head_zraw", (B, cfg.likelihood_channels, Nt))
         self._call("cnp_mlp_head_fwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(batch.aux_t), Ca,
-                   _ptr(batch.yt) if with_loss else None, B, Nt, _ptr(mean), _ptr(var), _ptr(logp), _ptr(count),
-                   _stream())
+                   _ptr(batch.yt) if with_loss else None, B, Nt, _ptr(mean), _ptr(var), _ptr(zraw), _ptr(logp),
+                   _ptr(count), _stream())
         return dict(mean=mean, var=var, logp=logp, count=count, ctx=dict(enc=enc, z=z, A=A, f=f, generation=self.generation))
 
     def _decode_grid(self, batch: DeviceBatch, z: torch.Tensor, s2: float):
@@ -1108,6 +1112,15 @@ class Engine:
         mean = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
         std = torch.empty((B, P, Q), dtype=torch.float32, device=self.device)
         p = self._mlp_params()
+        if p.likelihood != 0:
+            # Bernoulli-Gamma / spikes-Beta: the general head kernel over the flattened target grid ([B,C,P,Q] is
+            # [B,C,P*Q]); mean and std of the spikes-and-slab distribution
+            auxb = aux if aux.shape[0] == B else aux.expand(B, -1, -1, -1).contiguous()
+            zraw = self._buf("head_zraw_grid", (B, cfg.likelihood_channels, P * Q))
+            self._call("cnp_mlp_head_fwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(auxb), Ca, None, B, P * Q, _ptr(mean), _ptr(std),
+                       _ptr(zraw), None, None, _stream())
+            std.sqrt_()
+            return dict(mean=mean, std=std, var=None, logp=None, count=None, ctx=None)
         self._call("cnp_mlp_head_points_fwd", C.byref(p), _ptr(f), f.stride(0), Cz, _ptr(aux), aux_bs, Ca, B, P * Q,
                    _ptr(mean), _ptr(std), _stream(), work=(2.0 * B * P * Q * sum(
                        a * b for a, b in zip(self.module.mlp_dims()[:-1], self.module.mlp_dims()[1:])), 0.0))

@@ -19,6 +19,11 @@ import torch
 import torch.nn as nn
 
 
+# head inputs per target variable (upstream neuralprocesses construct_likelihood: mean + pre-softplus variance;
+# k~, scale~, 2 log-probabilities; alpha~, beta~, 3 log-probabilities)
+LIKELIHOOD_CHANNELS = {"cnp": 2, "het": 2, "bernoulli-gamma": 4, "cnp-spikes-beta": 5, "spikes-beta": 5}
+
+
 @dataclass
 class ConvNPConfig:
     dim_yc: Tuple[int, ...]
@@ -49,10 +54,11 @@ class ConvNPConfig:
             raise NotImplementedError("the hot path implements the 5x5 UNet DeepSensor configures")
         if any(s not in (1, 2) for s in self.unet_strides):
             raise NotImplementedError("UNet strides must be 1 or 2")
-        if self.likelihood not in ("cnp", "het"):
+        if self.likelihood not in LIKELIHOOD_CHANNELS:
             raise NotImplementedError(
-                f"likelihood '{self.likelihood}': only the heteroscedastic Gaussian head ('cnp'/'het') is on the "
-                "hot path (SURVEY.md section 8(f) lists the other heads as next)")
+                f"likelihood '{self.likelihood}': the hot path has the heads nzdownscale selects per variable "
+                "(nzdownscale/dataprocess/config.py:162-169): 'cnp' / 'het' (Gaussian), 'bernoulli-gamma', "
+                "'cnp-spikes-beta'; the low-rank 'gnp' head is not built")
         if self.dim_yt != 1:
             raise NotImplementedError("single target variable (dim_yt=1) only")
 
@@ -68,8 +74,13 @@ class ConvNPConfig:
         return m
 
     @property
+    def likelihood_channels(self) -> int:
+        """Inputs of the likelihood per target point: 2 (Gaussian), 4 (Bernoulli-Gamma), 5 (spikes-Beta), times dim_yt."""
+        return LIKELIHOOD_CHANNELS[self.likelihood] * self.dim_yt
+
+    @property
     def unet_out_channels(self) -> int:
-        return self.unet_channels[0] if self.dim_aux_t > 0 else 2 * self.dim_yt
+        return self.unet_channels[0] if self.dim_aux_t > 0 else self.likelihood_channels
 
     def to_json(self) -> dict:
         return asdict(self)
@@ -115,7 +126,7 @@ class Decoder(nn.Module):
         self.unet = UNetParams(cfg)
         self.set_conv = SetConvScale(cfg.decoder_scale)
         if cfg.dim_aux_t > 0:
-            dims = (cfg.unet_channels[0] + cfg.dim_aux_t,) + tuple(cfg.aux_t_mlp_layers) + (2 * cfg.dim_yt,)
+            dims = (cfg.unet_channels[0] + cfg.dim_aux_t,) + tuple(cfg.aux_t_mlp_layers) + (cfg.likelihood_channels,)
             self.mlp = MLPParams(dims)
         else:
             self.mlp = MLPParams(())

@@ -247,21 +247,26 @@ int cnp_decode_grid_tc_fwd(const cnp_blk* h, const float* x1t, const float* x2t,
                            const struct cnp_mlp_params* p, const float* aux, long long aux_bstride, int Ca, float* mean,
                            float* stdv, void* workspace, long long workspace_bytes, cnp_stream_t s);
 
-/* ---- (4) aux-at-target MLP + heteroscedastic Gaussian head + normalised NLL -----------------------
- * replaces: neuralprocesses Augment -> MLP -> HeterogeneousGaussianLikelihood -> MultiOutputNormal.logpdf
- * -> nps.loglik (A.6, A.7) reached from ConvNP.loss_fn (train.py:370).  logp is float64. */
+/* ---- (4) aux-at-target MLP + likelihood head + normalised NLL ---------------------------------------
+ * replaces: neuralprocesses Augment -> MLP -> likelihood -> logpdf -> nps.loglik (A.6, A.7) reached from
+ * ConvNP.loss_fn (train.py:370).  logp is float64.  Likelihoods (the ones nzdownscale/dataprocess/config.py:162-169
+ * selects per variable): 0 heteroscedastic Gaussian ('cnp': mean = o0, var = 1e-6 + softplus(o1)); 1 Bernoulli-Gamma
+ * ('bernoulli-gamma', precipitation: o = (k~, scale~, l_zero, l_slab)); 2 spikes-Beta ('cnp-spikes-beta', humidity:
+ * o = (alpha~, beta~, l_0, l_1, l_slab)).  mean / var are the distribution's mean and variance in every case. */
 #define CNP_MLP_MAX_LAYERS 6
 typedef struct cnp_mlp_params {
   const float* W[CNP_MLP_MAX_LAYERS];  /* [out,in] row-major */
   const float* b[CNP_MLP_MAX_LAYERS];
   float* dW[CNP_MLP_MAX_LAYERS];       /* += (backward only) */
   float* db[CNP_MLP_MAX_LAYERS];
-  int dims[CNP_MLP_MAX_LAYERS + 1];    /* dims[0] = Cf + Ca, dims[n_layers] = 2 */
+  int dims[CNP_MLP_MAX_LAYERS + 1];    /* dims[0] = Cf + Ca, dims[n_layers] = head inputs: 2 | 4 | 5 */
   int n_layers;
+  int likelihood;                      /* 0 Gaussian, 1 Bernoulli-Gamma, 2 spikes-Beta */
 } cnp_mlp_params;                      /* HOST struct holding DEVICE pointers */
 int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
                      const float* yt /*or NULL*/, int B, int Nt, float* mean, float* var,
-                     double* logp /*[B] += or NULL*/, int* count /*[B] +=*/, cnp_stream_t s);
+                     float* zraw /*[B][dims[n_layers]][Nt] raw head inputs; needed for likelihoods 1, 2, else NULL*/,
+                     double* logp /*[B] or NULL*/, int* count /*[B]*/, cnp_stream_t s);
 /* inference head over npts points per batch element (mean, std = sqrt(var)); aux_bstride = 0 shares aux */
 int cnp_mlp_head_points_fwd(const cnp_mlp_params* p, const float* f, long long f_bstride, int Cf, const float* aux,
                             long long aux_bstride, int Ca, int B, long long npts, float* mean, float* stdv,

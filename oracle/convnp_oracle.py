@@ -187,12 +187,76 @@ def n_mlp_layers(params) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# Spikes-and-slab likelihoods (neuralprocesses/likelihood.py BernoulliGammaLikelihood / SpikesBetaLikelihood over
+# dist/spikeslab.py SpikesSlab -- [U], restated from memory like the rest of this file: spikes first, slab last).
+# Selected per variable by /root/reference/nzdownscale/dataprocess/config.py:162-169:
+#   'bernoulli-gamma'  (precipitation): o = (k~, scale~, l_zero, l_slab), spike at 0, slab Gamma(k, scale)
+#   'cnp-spikes-beta'  (humidity):      o = (alpha~, beta~, l_0, l_1, l_slab), spikes at 0 and 1, slab Beta(alpha, beta)
+# with a = 1e-6 + softplus(a~) (fp32, like the Gaussian head's variance), log-probabilities = log_softmax(l) and every
+# log-pdf evaluated in float64.
+# --------------------------------------------------------------------------------------
+LIK_EPS = 1e-6
+SPIKES = {"bernoulli-gamma": (0.0,), "cnp-spikes-beta": (0.0, 1.0), "spikes-beta": (0.0, 1.0)}
+
+
+def spike_slab_params(o: Tensor, kind: str):
+    """o [B, 2 + n_spikes + 1, ...] -> (a, b, log-probabilities [B, n_spikes + 1, ...]) in float64."""
+    a = (LIK_EPS + F.softplus(o[:, 0])).double()
+    b = (LIK_EPS + F.softplus(o[:, 1])).double()
+    lp = torch.log_softmax(o[:, 2:].double(), dim=1)
+    return a, b, lp
+
+
+def slab_logpdf(a: Tensor, b: Tensor, y: Tensor, kind: str) -> Tensor:
+    if kind == "bernoulli-gamma":
+        return (a - 1.0) * torch.log(y) - y / b - torch.lgamma(a) - a * torch.log(b)
+    x = y.clamp(LIK_EPS, 1.0 - LIK_EPS)
+    return (a - 1.0) * torch.log(x) + (b - 1.0) * torch.log1p(-x) - (torch.lgamma(a) + torch.lgamma(b) - torch.lgamma(a + b))
+
+
+def spike_slab_logpdf(o: Tensor, yt: Tensor, kind: str) -> Tensor:
+    """Per-target log-pdf [B, ...] (NaN where the target is NaN)."""
+    a, b, lp = spike_slab_params(o, kind)
+    y = yt[:, 0].double()
+    spikes = SPIKES[kind]
+    ok = ~torch.isnan(y)
+    y0 = torch.where(ok, y, torch.full_like(y, 0.5))
+    is_spike = [y0 == s for s in spikes]
+    any_spike = torch.zeros_like(ok)
+    for m in is_spike:
+        any_spike = any_spike | m
+    y_safe = torch.where(any_spike, torch.full_like(y0, 0.5), y0)       # the slab is only evaluated off the spikes
+    out = lp[:, len(spikes)] + slab_logpdf(a, b, y_safe, kind)
+    for i, m in enumerate(is_spike):
+        out = torch.where(m, lp[:, i], out)
+    return torch.where(ok, out, torch.full_like(out, float("nan")))
+
+
+def spike_slab_moments(o: Tensor, kind: str):
+    """Mean and variance of the spikes-and-slab distribution, [B, 1, ...] float32 each."""
+    a, b, lp = spike_slab_params(o, kind)
+    p = lp.exp()
+    if kind == "bernoulli-gamma":
+        m1, m2 = a * b, a * (a + 1.0) * b * b
+        mean, e2 = p[:, 1] * m1, p[:, 1] * m2
+    else:
+        t = a + b
+        m1 = a / t
+        m2 = a * b / (t * t * (t + 1.0)) + m1 * m1
+        mean, e2 = p[:, 1] + p[:, 2] * m1, p[:, 1] + p[:, 2] * m2
+    var = (e2 - mean * mean).clamp(min=0.0)
+    return mean.float().unsqueeze(1), var.float().unsqueeze(1)
+
+
+# --------------------------------------------------------------------------------------
 # Full forward / loss
 # --------------------------------------------------------------------------------------
 def forward(params: Dict[str, Tensor], contexts, xt, aux_t: Optional[Tensor], ppu: float,
-            margin: float = 0.1, eps: float = 1e-2, strides=(1, 2, 2, 2), return_internal: bool = False):
+            margin: float = 0.1, eps: float = 1e-2, strides=(1, 2, 2, 2), return_internal: bool = False,
+            likelihood: str = "cnp"):
     """contexts: list of (x, y, mask|None); off-grid x [B,2,N] y [B,C,N] mask [B,1,N];
-    gridded x (x1 [B,1,N1], x2 [B,1,N2]) y [B,C,N1,N2] mask [B,1,N1,N2]."""
+    gridded x (x1 [B,1,N1], x2 [B,1,N2]) y [B,C,N1,N2] mask [B,1,N1,N2].  Returns the mean and variance of the
+    predictive distribution (``o`` -- the raw likelihood inputs -- in the internals)."""
     mult = 1
     for s in strides:
         mult *= s
@@ -204,9 +268,12 @@ def forward(params: Dict[str, Tensor], contexts, xt, aux_t: Optional[Tensor], pp
     if aux_t is not None:
         f = torch.cat([f, aux_t], dim=1)
     o = mlp(params, f, n_mlp_layers(params))
-    mean, var = het_gaussian(o)
+    if likelihood in ("cnp", "het"):
+        mean, var = het_gaussian(o)
+    else:
+        mean, var = spike_slab_moments(o, likelihood)
     if return_internal:
-        return mean, var, dict(enc=enc, z=z, f=f, grid=((s1, n1), (s2, n2), res))
+        return mean, var, dict(enc=enc, z=z, f=f, o=o, grid=((s1, n1), (s2, n2), res))
     return mean, var
 
 
@@ -224,6 +291,19 @@ def loglik(mean: Tensor, var: Tensor, yt: Tensor, normalise: bool = True) -> Ten
     return lp
 
 
-def loss_fn(params, contexts, xt, yt, aux_t, ppu, normalise=True, **kw) -> Tensor:
-    mean, var = forward(params, contexts, xt, aux_t, ppu, **kw)
-    return -loglik(mean, var, yt, normalise).mean()
+def loglik_spike_slab(o: Tensor, yt: Tensor, kind: str, normalise: bool = True) -> Tensor:
+    lp = spike_slab_logpdf(o, yt, kind)
+    ok = ~torch.isnan(lp)
+    lp = torch.where(ok, lp, torch.zeros_like(lp))
+    B = lp.shape[0]
+    s = lp.reshape(B, -1).sum(dim=1)
+    if normalise:
+        s = s / ok.reshape(B, -1).sum(dim=1).clamp(min=1).double()
+    return s
+
+
+def loss_fn(params, contexts, xt, yt, aux_t, ppu, normalise=True, likelihood: str = "cnp", **kw) -> Tensor:
+    mean, var, info = forward(params, contexts, xt, aux_t, ppu, return_internal=True, likelihood=likelihood, **kw)
+    if likelihood in ("cnp", "het"):
+        return -loglik(mean, var, yt, normalise).mean()
+    return -loglik_spike_slab(info["o"], yt, likelihood, normalise).mean()

@@ -220,3 +220,51 @@ def test_task_tensors_restatement_equals_product_batching():
     # the ragged set really was padded and masked
     m3 = task_tensors(tasks)[0][3][2]
     assert m3 is not None and float(m3[0].sum()) == 160 and float(m3[2].sum()) == 144
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# spikes-and-slab likelihoods: closed-form known answers
+# ---------------------------------------------------------------------------------------------------------------------
+def _inv_softplus(v):
+    return math.log(math.expm1(v))
+
+
+def test_bernoulli_gamma_known_answers():
+    """k = 1 makes the slab an exponential: log p(y) = log p_slab - y / scale - log scale; y == 0 picks the spike."""
+    scale, l0, l1 = 2.0, 0.3, -0.4
+    o = torch.tensor([_inv_softplus(1.0 - 1e-6), _inv_softplus(scale - 1e-6), l0, l1], dtype=torch.float32).view(1, 4, 1).repeat(1, 1, 3)
+    y = torch.tensor([[[0.0, 1.5, float("nan")]]])
+    lp = O.spike_slab_logpdf(o, y, "bernoulli-gamma")
+    lz = math.log(math.exp(l0) + math.exp(l1))
+    assert abs(float(lp[0, 0]) - (l0 - lz)) < 1e-6
+    assert abs(float(lp[0, 1]) - ((l1 - lz) - 1.5 / scale - math.log(scale))) < 1e-5
+    assert math.isnan(float(lp[0, 2]))
+    ll = O.loglik_spike_slab(o, y, "bernoulli-gamma", normalise=True)
+    assert abs(float(ll) - 0.5 * (float(lp[0, 0]) + float(lp[0, 1]))) < 1e-12          # NaN target skipped, / 2
+    mean, var = O.spike_slab_moments(o, "bernoulli-gamma")
+    p1 = math.exp(l1 - lz)
+    assert abs(float(mean[0, 0, 0]) - p1 * scale) < 1e-5                                  # E = p_slab * k * scale
+    assert abs(float(var[0, 0, 0]) - (p1 * 2 * scale ** 2 - (p1 * scale) ** 2)) < 1e-4    # E[x^2] = p k (k+1) scale^2
+
+
+def test_spikes_beta_known_answers():
+    """alpha = beta = 1 makes the slab uniform on (0, 1): log p(y) = log p_slab; y in {0, 1} picks a spike."""
+    l = (0.2, -0.1, 0.5)
+    one = _inv_softplus(1.0 - 1e-6)
+    o = torch.tensor([one, one, *l], dtype=torch.float32).view(1, 5, 1).repeat(1, 1, 3)
+    y = torch.tensor([[[0.0, 1.0, 0.37]]])
+    lp = O.spike_slab_logpdf(o, y, "cnp-spikes-beta")
+    lz = math.log(sum(math.exp(v) for v in l))
+    for i in range(3):
+        assert abs(float(lp[0, i]) - (l[i] - lz)) < 1e-5
+    mean, var = O.spike_slab_moments(o, "cnp-spikes-beta")
+    p = [math.exp(v - lz) for v in l]
+    m = p[1] + p[2] * 0.5
+    assert abs(float(mean[0, 0, 0]) - m) < 1e-6
+    assert abs(float(var[0, 0, 0]) - (p[1] + p[2] / 3.0 - m * m)) < 1e-6                   # E[U^2] = 1/3
+    # a non-trivial Beta against scipy
+    from scipy.stats import beta as sbeta
+    o2 = torch.tensor([_inv_softplus(2.5), _inv_softplus(0.7), *l], dtype=torch.float32).view(1, 5, 1)
+    lp2 = float(O.spike_slab_logpdf(o2, torch.tensor([[[0.8]]]), "cnp-spikes-beta"))
+    a, b = 2.5 + 1e-6, 0.7 + 1e-6
+    assert abs(lp2 - ((l[2] - lz) + sbeta.logpdf(0.8, a, b))) < 1e-5
