@@ -122,7 +122,12 @@ class Engine:
             raise NotImplementedError("the hot path expects aux-at-target channels (dim_aux_t > 0), as the "
                                       "reference always configures (train.py:160-166)")
         if precision == "bf16" and any(c != 64 for c in self.cfg.unet_channels):
-            raise NotImplementedError("bf16 tensor-core path is specialised for unet_channels=(64,)*L")
+            # the tcgen05 kernels tile exactly 64 output channels (the reference's default, config.py:2685-2689);
+            # other widths (train_downscaling.py:116-117 lets the user pick them) run the fp32 CUDA-core kernels
+            import warnings
+            warnings.warn(f"unet_channels={self.cfg.unet_channels}: the bf16 tensor-core path is specialised for 64 "
+                          "channels per level; this model runs the fp32 kernels (precision='fp32')", stacklevel=3)
+            self.precision = precision = "fp32"
         self._ws: Dict[tuple, object] = {}
         self._packed: Dict[str, Tuple[int, torch.Tensor]] = {}
         self._scale_cache: Dict[int, Tuple[int, float]] = {}

@@ -144,6 +144,15 @@ class ConvNPModule(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover - arithmetic lives in the engine
         raise RuntimeError("ConvNPModule holds parameters only; use deepsensornz_b200.ConvNP (CUDA engine)")
 
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Loads this module's own checkpoints, and -- SURVEY 8(f)4 -- checkpoints written by upstream DeepSensor
+        (``model.model.load_state_dict(torch.load(path))``: nzdownscale/downscaler/train.py:243-251 fine-tuning,
+        validate_ERA.py:100-111), whose ``nps.Model`` key names differ from the ones here."""
+        if set(state_dict.keys()) == set(self.state_dict().keys()):
+            return super().load_state_dict(state_dict, strict=strict, assign=assign)
+        mapped = map_upstream_state_dict(state_dict, self.state_dict())
+        return super().load_state_dict(mapped, strict=True, assign=assign)
+
     def mlp_dims(self) -> List[int]:
         ls = self.decoder.mlp.layers
         return [ls[0].in_features] + [l.out_features for l in ls] if len(ls) else []
@@ -152,3 +161,48 @@ class ConvNPModule(nn.Module):
 def num_params(module: nn.Module) -> int:
     """``deepsensor.backend.nps.num_params`` (nzdownscale/downscaler/train.py:262)."""
     return sum(int(p.numel()) for p in module.parameters())
+
+
+
+def map_upstream_state_dict(upstream: dict, ours: dict, verbose: bool = False) -> dict:
+    """Map a checkpoint with foreign key names (upstream ``neuralprocesses`` ``Model``) onto this module's keys.
+
+    The upstream package cannot be imported here, so its key NAMES are unknown; what is known is the
+    architecture, hence every tensor SHAPE and the order of layers inside each list (UNet levels 0..L-1 in
+    ``before_turn_layers`` / ``after_turn_layers``, MLP layers in order, one length scale per context set in context
+    order, then the decoder's).  The mapping is therefore by shape sequence: tensors are grouped by shape, in the order
+    the checkpoint lists them, and the i-th upstream tensor of a shape goes to the i-th tensor of that shape here
+    (scalars of shape () and (1,) count as one group).  It refuses -- rather than guess -- unless both sides hold
+    exactly the same multiset of shapes; ``verbose`` prints the resulting table so it can be audited.
+    """
+    def key_of(t):
+        shp = tuple(t.shape)
+        return () if int(torch.as_tensor(t).numel()) == 1 else shp
+
+    def groups(d):
+        g = {}
+        for k, v in d.items():
+            if not torch.is_tensor(v):
+                continue
+            g.setdefault(key_of(v), []).append(k)
+        return g
+
+    gu, go = groups(upstream), groups(ours)
+    if {k: len(v) for k, v in gu.items()} != {k: len(v) for k, v in go.items()}:
+        only_u = {k: len(v) for k, v in gu.items() if len(v) != len(go.get(k, []))}
+        only_o = {k: len(v) for k, v in go.items() if len(v) != len(gu.get(k, []))}
+        raise RuntimeError("checkpoint does not match this ConvNP architecture: tensors per shape differ -- checkpoint "
+                           f"{only_u} vs model {only_o} (unet_channels / dim_yc / likelihood / aux MLP must equal the "
+                           "ones the checkpoint was trained with)")
+    out = {}
+    for shp, names in go.items():
+        for mine, theirs in zip(names, gu[shp]):
+            v = upstream[theirs]
+            out[mine] = v.reshape(ours[mine].shape).to(ours[mine].dtype)
+            if verbose:
+                print(f"  {theirs:70s} -> {mine}  {tuple(ours[mine].shape)}")
+    n_u = sum(int(v.numel()) for v in upstream.values() if torch.is_tensor(v))
+    n_o = sum(int(v.numel()) for v in ours.values())
+    if n_u != n_o:
+        raise RuntimeError(f"checkpoint holds {n_u} values, the model {n_o}")
+    return out

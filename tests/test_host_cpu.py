@@ -132,3 +132,48 @@ def test_shard_tasks_partition(static):
     assert [len(s) for s in shards] == [6, 6]                           # 8 -> 4+4, 5 -> 2+2 (remainder dropped)
     ids = [t["time"] for s in shards for t in s]
     assert len(set(ids)) == len(ids)
+
+
+def test_upstream_style_checkpoint_loads_by_shape_sequence():
+    """``model.model.load_state_dict(torch.load(path))`` (train.py:243-251, validate_ERA.py:100-111) with a
+    checkpoint whose key names are not this module's: mapped by shape sequence, refused when the architecture differs."""
+    from deepsensornz_b200.model import ConvNPConfig, ConvNPModule, map_upstream_state_dict
+    cfg = ConvNPConfig(dim_yc=(3, 6, 1, 1), dim_aux_t=5, encoder_scales=(0.01,) * 4)
+    torch.manual_seed(3)
+    src = ConvNPModule(cfg)
+    own = src.state_dict()
+    # an upstream-looking checkpoint: other names, another interleaving of the tensors (all biases before all weights;
+    # the order WITHIN a shape is the architecture's, which is what the mapping relies on), scalars shaped (1,)
+    order = sorted(own, key=lambda k: own[k].dim())
+    foreign = {}
+    for i, k in enumerate(order):
+        v = own[k].clone()
+        foreign[f"model.coder_{i // 7}.links.{i}.net.{k.split('.')[-1]}"] = v.reshape(1) if v.numel() == 1 else v
+    torch.manual_seed(4)
+    dst = ConvNPModule(cfg)
+    assert not torch.equal(dst.decoder.unet.final_linear.weight, src.decoder.unet.final_linear.weight)
+    dst.load_state_dict(foreign)
+    for (k, a), (_, b) in zip(dst.state_dict().items(), own.items()):
+        assert torch.equal(a, b), k
+    # own checkpoints keep loading by name
+    dst2 = ConvNPModule(cfg)
+    dst2.load_state_dict(own)
+    assert torch.equal(dst2.decoder.mlp.layers[0].weight, src.decoder.mlp.layers[0].weight)
+    # a checkpoint of another architecture is refused, not guessed
+    other = ConvNPModule(ConvNPConfig(dim_yc=(8, 6, 1, 1), dim_aux_t=5, encoder_scales=(0.01,) * 4)).state_dict()
+    with pytest.raises(RuntimeError, match="does not match"):
+        dst.load_state_dict({f"x.{i}": v for i, v in enumerate(other.values())})
+    missing = dict(list(foreign.items())[:-1])
+    with pytest.raises(RuntimeError, match="does not match"):
+        dst.load_state_dict(missing)
+    table = map_upstream_state_dict(foreign, dst.state_dict())
+    assert set(table) == set(own)
+
+
+def test_other_unet_widths_run_the_fp32_kernels():
+    """train_downscaling.py:116-117 lets the user set unet_channels: widths other than 64 are not on the tensor-core path;
+    the model is built with a warning and runs in fp32."""
+    with pytest.warns(UserWarning, match="64"):
+        m = ds.ConvNP(dim_yc=(3, 6, 1, 1), dim_yt=1, dim_aux_t=5, internal_density=50, encoder_scales=(0.01,) * 4,
+                      decoder_scale=0.02, unet_channels=(32, 32, 32, 32), precision="bf16", verbose=False)
+    assert m.engine.precision == "fp32"
