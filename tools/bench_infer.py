@@ -1,62 +1,13 @@
-"""configs[2]: high-res inference -- ConvNP forward onto the 1400x1400 NZ target grid from ERA5 + stations (S3).
-Per task: encoder -> UNet -> on-grid SetConv decoder -> aux MLP head -> mean/std [1400,1400] -> D2H (as predict does)."""
-import json
+"""configs[2]: high-res inference -- ConvNP.predict onto the 1400x1400 NZ target grid from ERA5 + stations (S3).
+Thin wrapper over ``bench.py --workload infer`` (device-resident forward, predict end to end, per-kernel table):
+  python tools/bench_infer.py [tasks]"""
 import os
+import subprocess
 import sys
-import time
 
-import numpy as np
-import torch
-
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench  # noqa: E402
-from deepsensornz_b200 import ConvNP  # noqa: E402
-from deepsensornz_b200.synthetic import make_static, make_task  # noqa: E402
-
-
-def main():
-    precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
-    n_tasks = int(sys.argv[2]) if len(sys.argv) > 2 else 6
-    torch.manual_seed(0)
-    model = ConvNP(precision=precision, **bench.model_kwargs())
-    static = make_static(seed=7, with_aux_hi=True)
-    tasks = [make_task(static, 2016010100 + h, all_context=True) for h in range(n_tasks)]
-    x_hi = static.x_hi
-    eng = model.engine
-    # warm-up
-    model.predict(tasks[:2], X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    pred = model.predict(tasks, X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    key = list(pred.keys())[0]
-    mean = np.asarray(pred[key]["mean"])
-    repeats = []
-    for _ in range(2):          # later calls: allocator caches (pinned staging, result pages) are warm
-        t1 = time.perf_counter()
-        model.predict(tasks, X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
-        torch.cuda.synchronize()
-        repeats.append((time.perf_counter() - t1) / n_tasks)
-    if os.environ.get("CNP_PROFILE_HOST"):
-        import cProfile, pstats, io
-        pr = cProfile.Profile()
-        pr.enable()
-        model.predict(tasks, X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
-        torch.cuda.synchronize()
-        pr.disable()
-        st = io.StringIO()
-        pstats.Stats(pr, stream=st).sort_stats("cumulative").print_stats(28)
-        print(st.getvalue()[:6000])
-    # per-kernel profile of one task
-    eng.profile_start()
-    model.predict(tasks[:1], X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
-    prof = eng.profile_stop()
-    out = {"metric": "convnp_predict_s_per_task", "value": dt / n_tasks, "unit": "s/task", "repeat_calls": [round(r, 6) for r in repeats], "tasks": n_tasks,
-           "precision": precision, "target_grid": list(mean.shape[1:]),
-           "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
-    print(json.dumps(out))
-
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 if __name__ == "__main__":
-    main()
+    n = sys.argv[1] if len(sys.argv) > 1 else "32"
+    sys.exit(subprocess.call([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "infer", "--steps", n,
+                              "--warmup", "3"]))
