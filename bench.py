@@ -20,7 +20,8 @@ stations with 5 aux-at-target channels; internal_density 250 -> 304 x 304 intern
   cpu_baseline : the oracle (torch CPU restatement, "port") on a bounded sample, rank 0 / N=1 only
   loss_check   : the first forward on the initial weights against the committed fp32 oracle value
                  (tests/golden/s2_bench16_loss0.npz) -- the run aborts when it is off by more than the bf16 tolerance
-  inference, multivar : short sub-records of the other two workloads, so that every run carries them
+  inference, multivar, grid608 : short sub-records of the other workloads (configs[2]/[4], configs[3], and
+                 configs[1] at the in-repo default internal_density=500), so that every run carries them
 
 Inference ("infer"): a "step" is one task (one date/hour) predicted onto the 1400 x 1400 target grid (configs[2], and
 configs[4] when sharded by date over N GPUs: no collective).  value = forward only with inputs resident, outputs left on
@@ -530,6 +531,13 @@ def run_ours(args):
         line["multivar"] = {"workload": "configs[3]: dim_yc=(8,6,1,1), Cin=20, B=16 per GPU, device-resident training step",
                             "value": mv["value"], "unit": "tasks/s", "ms_per_step": mv["ms_per_step"], "steps": 10,
                             "gpu_launches": mv["gpu_launches"]}
+        if args.internal_density == PPU:     # the in-repo default density (config.py:2688): 608 x 608 internal grid
+            a500 = argparse.Namespace(**vars(args))
+            a500.internal_density = 500
+            g5 = train_arm(a500, world, rank, local, DIM_YC, 5, 3, profile=False, e2e=False)
+            line["grid608"] = {"workload": "configs[1] at internal_density=500 (608 x 608 internal grid), B=16 per GPU, "
+                                           "device-resident training step", "value": g5["value"], "unit": "tasks/s",
+                               "ms_per_step": g5["ms_per_step"], "steps": 5, "internal_grid": [g5["grid"].n1, g5["grid"].n2]}
         inf = infer_arm(args, world, rank, local, 16, 3, profile=(world == 1))
         line["inference"] = {"workload": "configs[2]/[4]: ConvNP.predict onto 1400x1400, 16 tasks per GPU",
                              "value": inf["value"], "unit": "tasks/s", "ms_per_task": inf["ms_per_step"], "tasks": 16,

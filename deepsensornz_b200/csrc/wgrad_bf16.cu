@@ -319,42 +319,53 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
   if (warp == 1) { tc::fence_after_sync(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
-// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel, in a FIXED order
-// (k = 0, 1, ...: gradients are run-to-run identical, so a CUDA-graph replay equals the eager step bit for bit).
-// Thread = 4 consecutive columns (one 16 B load per partial), WG_RED_KS loads in flight at a time; every (co, ci, tap)
-// is owned by exactly one thread (wg_slot is one-to-one on the valid slots).  The first 64 threads of block 0 also fold
-// the per-CTA bias partials.
+// dw[co][ci][slot] += sum over the K-split CTAs of the partial accumulators written by wgrad_tc_kernel, in a FIXED order:
+// gradients are run-to-run identical, so a CUDA-graph replay equals the eager step bit for bit.
+// Block = 32 column quads (one 16 B load per partial per thread, a warp reads 512 contiguous bytes) x 8 K-slices (one
+// warp each): slice s adds partials s, s+8, s+16, ... in order, the slices meet in shared memory and warp 0 adds them
+// 0..7 in order.  Every (co, ci, tap) is owned by exactly one thread (wg_slot is one-to-one on the valid slots), so the
+// final update is a plain read-modify-write.  (One thread walking all ~29 partials serially was latency-bound: 24 us
+// per launch against 9 us for the atomics version; this form keeps 8x the loads in flight.)
+// Block 0 also folds the per-CTA bias partials.
 constexpr int WG_RED_KS = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
+  __shared__ float4 part[WG_RED_KS][32];
   const int ncols = a.dup ? 128 : 64;
   const int total4 = a.n_pass * a.ws_acc * 128 * (ncols / 4);
+  const int q = threadIdx.x & 31, sl = threadIdx.x >> 5;
   if (a.dbias != nullptr && blockIdx.x == 0 && threadIdx.x < 64) {
     float s = 0.f;
     const int n = a.n_pass * a.ksplit;
     for (int k = 0; k < n; ++k) s += a.ws_bias[(size_t)k * 64 + threadIdx.x];
     a.dbias[threadIdx.x] += s;
   }
-  for (int e = blockIdx.x * 256 + threadIdx.x; e < total4; e += gridDim.x * 256) {
-    const int col = (e % (ncols / 4)) * 4, m = (e / (ncols / 4)) & 127, jj = e / ((ncols / 4) * 128);
-    const int j = jj % a.ws_acc, pass = jj / a.ws_acc;
+  const int e = blockIdx.x * 32 + q;
+  bool valid = e < total4;
+  int col = 0, m = 0, j = 0, pass = 0, slot = -1, ci = 0;
+  if (valid) {
+    col = (e % (ncols / 4)) * 4; m = (e / (ncols / 4)) & 127;
+    const int jj = e / ((ncols / 4) * 128);
+    j = jj % a.ws_acc; pass = jj / a.ws_acc;
     const cnp_wg_pass& ps = a.pass[pass];
-    if (j >= ps.n_acc) continue;
-    int ci;
-    const int slot = wg_slot(a, ps, m, j, col >> 6, &ci);
-    if (slot < 0 || ci >= a.Cin) continue;
+    valid = j < ps.n_acc;
+    if (valid) { slot = wg_slot(a, ps, m, j, col >> 6, &ci); valid = slot >= 0 && ci < a.Cin; }
+  }
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
     const float* src = a.ws + (((size_t)pass * a.ksplit * a.ws_acc + j) * 128 + m) * 128 + col;
     const size_t stride = (size_t)a.ws_acc * 128 * 128;
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k0 = 0; k0 < a.ksplit; k0 += WG_RED_KS) {
-      float4 v[WG_RED_KS];
-#pragma unroll
-      for (int k = 0; k < WG_RED_KS; ++k)
-        v[k] = (k0 + k < a.ksplit) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)(k0 + k) * stride))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < WG_RED_KS; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+#pragma unroll 4
+    for (int k = sl; k < a.ksplit; k += WG_RED_KS) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)k * stride));
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
     }
+  }
+  part[sl][q] = sum;
+  __syncthreads();
+  if (sl == 0 && valid) {
+#pragma unroll
+    for (int s = 1; s < WG_RED_KS; ++s) { const float4 v = part[s][q]; sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
     const int co = col & 63;
     float* dst = a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot;
     const size_t cs = (size_t)a.Cin * a.KK;
@@ -580,7 +591,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   CNP_LAUNCH_CHECK("wgrad_tc_kernel");
   if (a.ws) {
     const int total4 = np * a.ws_acc * 128 * ((a.dup ? 128 : 64) / 4);
-    wgrad_reduce_kernel<<<dim3(cnp_cdiv(total4, 256)), 256, 0, st>>>(a);
+    wgrad_reduce_kernel<<<dim3(cnp_cdiv(total4, 32)), 256, 0, st>>>(a);
     CNP_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   return 0;
