@@ -272,3 +272,24 @@ def test_predict_unnormalises_on_the_device(static):
     unn = m.predict(tasks, unnormalise=False, **kw)
     assert np.array_equal(np.asarray(unn[key]["mean"]), mean_n)
     m.data_processor = None
+
+
+def test_batched_predict_equals_one_task_per_forward(monkeypatch):
+    """predict runs several dates per forward (CONVNP_B200_PREDICT_BATCH, default 4): ragged station counts are padded with
+    masked-out copies of a real point, static sets are uploaded once; every date's mean / std equals its single-task
+    forward (validate_ERA.py:88-92 call form)."""
+    static = make_static(seed=7, n_hi=200, with_aux_hi=True)
+    m = small_model("bf16", seed=8)
+    rng = np.random.default_rng(5)
+    tasks = [make_task(static, 8100 + i, n_stations=int(rng.integers(120, 201)), all_context=True) for i in range(7)]
+    kw = dict(X_t=(static.x_hi, static.x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
+    res = {}
+    for nb in ("1", "4", "3"):
+        monkeypatch.setenv("CONVNP_B200_PREDICT_BATCH", nb)
+        pred = m.predict(tasks, **kw)
+        key = list(pred.keys())[0]
+        res[nb] = (np.asarray(pred[key]["mean"]).copy(), np.asarray(pred[key]["std"]).copy())
+        assert res[nb][0].shape == (7, 200, 200) and np.isfinite(res[nb][0]).all()
+    for nb in ("4", "3"):
+        for a, b in zip(res["1"], res[nb]):
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-6), float(np.abs(a - b).max())
