@@ -243,11 +243,11 @@ def _predict_batched(model, tasks, Xn, aux_dev, nb, aff_mean, aff_std, copy_stre
     ctx_cache = {}
     d2h_stream = torch.cuda.Stream()
 
-    def drain(slot, ids):
+    # pinned -> result array, one job per (date, field): the first touch of the freshly allocated result pages makes a
+    # single thread crawl (3.1 ms per 15.7 MB date on the B200 box's host against 0.56 ms with 6 threads)
+    def drain(slot, k, idx, which):
         events[slot].synchronize()
-        b = len(ids)
-        mean_out[ids[0]:ids[0] + b] = pin[slot][0][:b].numpy()
-        std_out[ids[0]:ids[0] + b] = pin[slot][1][:b].numpy()
+        (mean_out if which == 0 else std_out)[idx] = pin[slot][which][k].numpy()
 
     bar = None
     if progress_bar:
@@ -259,8 +259,8 @@ def _predict_batched(model, tasks, Xn, aux_dev, nb, aff_mean, aff_std, copy_stre
     for gi, ids in enumerate(groups):
         ctxs = first if gi == 0 else _batch_contexts([tasks[i] for i in ids])
         if ctxs is None:
-            for f in futures:
-                if f is not None:
+            for fs in futures:
+                for f in fs or ():
                     f.result()
             return None
         b = len(ids)
@@ -275,7 +275,8 @@ def _predict_batched(model, tasks, Xn, aux_dev, nb, aff_mean, aff_std, copy_stre
             std = std * aff_std[0] + aff_std[1]
         slot = gi % SL
         if futures[slot] is not None:
-            futures[slot].result()
+            for f in futures[slot]:
+                f.result()
         # read-back on its own stream (the other copy engine): it overlaps the next batch's upload and kernels
         ev = torch.cuda.Event()
         ev.record()
@@ -287,11 +288,11 @@ def _predict_batched(model, tasks, Xn, aux_dev, nb, aff_mean, aff_std, copy_stre
             events[slot].record()
         mean.record_stream(d2h_stream)
         std.record_stream(d2h_stream)
-        futures[slot] = pool.submit(drain, slot, ids)
+        futures[slot] = [pool.submit(drain, slot, k, i, w) for k, i in enumerate(ids) for w in (0, 1)]
         if bar is not None:
             bar.update(b)
-    for f in futures:
-        if f is not None:
+    for fs in futures:
+        for f in fs or ():
             f.result()
     if bar is not None:
         bar.close()
@@ -364,7 +365,7 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
     # so it overlaps the launches of the following tasks
     copy_stream = torch.cuda.Stream() if cuda else None
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=int(os.environ.get('CONVNP_B200_DRAIN_THREADS', '3')))
+    pool = ThreadPoolExecutor(max_workers=int(os.environ.get('CONVNP_B200_DRAIN_THREADS', '6')))
     futures = [None, None, None]
     # CUDA-graph replay of the forward for tasks sharing a batch signature (CONVNP_B200_PREDICT_GRAPH=1)
     # Opt-in: with the static context sets cached and three drain threads the eager loop already runs at the pace of

@@ -192,6 +192,7 @@ def test_predict_graph_replay_matches_eager(static, monkeypatch):
     orig = m.engine._call
     monkeypatch.setattr(m.engine, "_call", lambda name, *a, **k: (calls.append(name), orig(name, *a, **k))[1])
     monkeypatch.setenv("CONVNP_B200_PREDICT_GRAPH", "1")
+    monkeypatch.setenv("CONVNP_B200_PREDICT_BATCH", "1")       # one date per forward in both arms (launch counts below)
     pg = m.predict(tasks, X_t=(x1, x2), X_t_is_normalised=True, aux_at_targets_override=aux)
     n_graph = sum(1 for c in calls if c.startswith("cnp_decode_grid"))
     calls.clear()
