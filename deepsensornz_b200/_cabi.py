@@ -126,9 +126,6 @@ _SIGS = {
     "cnp_mlp_head_bwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp,
                                    c_stream]),
     # (2) bf16 tensor-core UNet blocks
-    "cnp_conv_tc_packed_bytes": (_ll, [_i, _i]),
-    "cnp_conv_tc_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
-    "cnp_conv_tc": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
     "cnp_conv_tc2_debug": (C.c_int, [c_fp, _i]),
     "cnp_conv_tc2_set_cluster": (C.c_int, [_i]),
     "cnp_conv_tc2_packed_bytes": (_ll, [_i, _i, _i]),
@@ -150,6 +147,13 @@ _SIGS = {
     "cnp_blk_channel_sum": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, c_stream]),
 }
 
+# only in a `make LEGACY=1` build (first convolution formulation, A/B runs and its own tests)
+_OPTIONAL_SIGS = {
+    "cnp_conv_tc_packed_bytes": (_ll, [_i, _i]),
+    "cnp_conv_tc_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
+    "cnp_conv_tc": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
+}
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -168,6 +172,10 @@ def lib() -> C.CDLL:
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)  # AttributeError if the export is missing
             fn.restype, fn.argtypes = res, args
+        for name, (res, args) in _OPTIONAL_SIGS.items():
+            if hasattr(L, name):
+                fn = getattr(L, name)
+                fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
 

@@ -66,6 +66,7 @@ constexpr int A_BUFS = 2;
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;
 
+#ifdef CNP_LEGACY_CONV_TC   // first formulation (pixels = M, N = 64), kept for A/B runs: make LEGACY=1
 __global__ void __launch_bounds__(256, 1)
 conv_tc_kernel(const __grid_constant__ cnp_conv_args a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -304,6 +305,7 @@ pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int t
     wpk[e] = __float2bfloat16_rn(v);
   }
 }
+#endif  // CNP_LEGACY_CONV_TC
 
 // ---------------------------------------------------------------------------------------------
 // layout conversion  NCHW fp32 <-> blocked bf16  (tests, encoder/decoder interfacing)
@@ -911,6 +913,7 @@ struct cnp_conv_out {
   const cnp_blk* s2d;     // (conv_tc2 only) optional space-to-depth copy of the output
 };
 
+#ifdef CNP_LEGACY_CONV_TC
 // Bytes of packed weights for (kind, n_chunks): stages x 20480.
 CNP_API long long cnp_conv_tc_packed_bytes(int kind, int n_chunks) {
   cnp_conv_plan p;
@@ -975,6 +978,8 @@ CNP_API int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kin
   CNP_LAUNCH_CHECK("conv_tc_kernel");
   return 0;
 }
+
+#endif  // CNP_LEGACY_CONV_TC
 
 CNP_API int cnp_blk_from_nchw_f32(const float* src, long long src_bstride, int B, int C, int H, int W,
                                   const cnp_blk* dst, cudaStream_t st) {

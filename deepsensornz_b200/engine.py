@@ -14,6 +14,7 @@ PyTorch is used for device memory, streams and the tiny [B]-sized loss algebra o
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 import os
@@ -129,6 +130,9 @@ class Engine:
                           "channels per level; this model runs the fp32 kernels (precision='fp32')", stacklevel=3)
             self.precision = precision = "fp32"
         self._ws: Dict[tuple, object] = {}
+        self._sig_lru: "collections.OrderedDict" = collections.OrderedDict()    # batch signature -> workspace keys
+        self._pinned_sigs: set = set()
+        self._cur_sig = None
         self._packed: Dict[str, Tuple[int, torch.Tensor]] = {}
         self._scale_cache: Dict[int, Tuple[int, float]] = {}
         self._enc_tabs: Dict[tuple, tuple] = {}      # band tables of the fused encoder, per (coordinates, grid, scale)
@@ -191,8 +195,39 @@ class Engine:
         self._prof = None
         return out
 
+    # ---- workspace lifetime: the reference steps many batch shapes (one group per station count, plus remainders:
+    # train.py:448-475) and at internal_density 500 every shape owns several GB of activations.  Workspaces are tagged
+    # with the batch signatures that use them; beyond MAX_SIGNATURES live shapes the least recently used one is released
+    # (never one a captured CUDA graph replays from: graphs hold raw pointers).
+    MAX_SIGNATURES = int(os.environ.get("CONVNP_B200_MAX_SHAPES", "4"))
+
+    def _touch_signature(self, sig) -> None:
+        self._cur_sig = sig
+        lru = self._sig_lru
+        if sig in lru:
+            lru.move_to_end(sig)
+            return
+        lru[sig] = set()
+        free = [s for s in lru if s not in self._pinned_sigs and s != sig]
+        while len(lru) - len(self._pinned_sigs & set(lru)) > self.MAX_SIGNATURES and free:
+            old = free.pop(0)
+            keys = lru.pop(old)
+            still = set().union(*lru.values()) if lru else set()
+            for k in keys - still:
+                self._ws.pop(k, None)
+
+    def pin_signature(self) -> None:
+        """The current batch shape is being captured into a CUDA graph: its workspaces must outlive the graph."""
+        if self._cur_sig is not None:
+            self._pinned_sigs.add(self._cur_sig)
+
+    def _tag(self, k) -> None:
+        if self._cur_sig is not None:
+            self._sig_lru.setdefault(self._cur_sig, set()).add(k)
+
     def _buf(self, key, shape, dtype=torch.float32, zero=False):
         k = (key, tuple(shape), dtype)
+        self._tag(k)
         t = self._ws.get(k)
         if t is None:
             t = torch.zeros(shape, dtype=dtype, device=self.device) if zero else \
@@ -202,6 +237,7 @@ class Engine:
 
     def _blk(self, key, B, CB, H, W) -> _Blk:
         k = (key, B, CB, H, W, "blk")
+        self._tag(k)
         t = self._ws.get(k)
         if t is None:
             t = _Blk(B, CB, H, W, self.device)
@@ -210,6 +246,8 @@ class Engine:
 
     def release_workspaces(self):
         self._ws.clear()
+        self._sig_lru.clear()
+        self._pinned_sigs.clear()
         self._packed.clear()
         self._pack_reqs.clear()
         self._enc_tabs.clear()
@@ -1055,6 +1093,7 @@ class Engine:
         self._require_cuda()
         cfg, g, B, Nt = self.cfg, batch.grid, batch.B, batch.Nt
         self.generation += 1
+        self._touch_signature((B, Nt, g.n1, g.n2, tuple(tuple(c.y.shape[1:]) for c in batch.contexts)))
         if self.precision == "bf16":
             self._prepack_all()
         if batch.ready is not None:   # uploaded on a copy stream: order after the copy, keep the allocator informed

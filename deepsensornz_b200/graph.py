@@ -96,6 +96,7 @@ class GraphedTrainStep:
         finally:
             eng.force_pack = False
         self.launches = eng.launches - l0
+        eng.pin_signature()        # the graph replays from the engine's workspaces of this batch shape
         if eng.precision == "bf16" and not eng.packs_recorded:
             raise RuntimeError("graph capture recorded no weight-packing kernels")
         # the captured backward writes into THESE gradient tensors (they live in the graph's private pool); an eager

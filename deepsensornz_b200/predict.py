@@ -114,6 +114,7 @@ class _GraphedForward:
             self.graph.capture_begin(capture_error_mode="thread_local")
             out = model.engine.forward(static, with_loss=False)
             self.graph.capture_end()
+        model.engine.pin_signature()
         main.wait_stream(side)
         self.mean, self.std = out["mean"], out["std"]
 

@@ -148,6 +148,7 @@ enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD 
                            cnp_up_phase_weights()[py], packed with k = 4; output sy = sx = 2, ay = py, ax = 0 */ };
 enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2, CNP_WG_K5S1_NARROW = 3 /* 1..8 source chunks */ };
 
+#ifdef CNP_LEGACY_CONV_TC   /* first formulation (pixels = M operand), only built with `make LEGACY=1` */
 long long cnp_conv_tc_packed_bytes(int kind, int n_chunks);
 int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_chunks, int py, int px, int co_off,
                      void* wpk, cnp_stream_t s);
@@ -155,6 +156,7 @@ int cnp_conv_tc_pack(const float* w, int Cout, int Cin, int k, int kind, int n_c
  * CNP_K5S2 reads the 32-chunk space-to-depth tensor; CNP_K5S2_DGRAD produces output phase (py,px). */
 int cnp_conv_tc(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, const cnp_conv_out* out,
                 int B, cnp_stream_t s);
+#endif
 /* Second formulation (weights = M operand, pixels = N operand; runs at the tcgen05 floor, see conv_tc2.cu).
  * n_out = 64: two output rows share one MMA (PAIR); n_out = 128: 128 output channels per call (WIDE, used for
  * the input gradient of the 128->64 layers).  n_chunks: 2, 4, .. 16 source chunks for the 5x5 kinds (2 = the folded

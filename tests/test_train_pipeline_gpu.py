@@ -147,3 +147,25 @@ def test_second_forward_before_backward_is_refused(static):
     l3 = m.loss_fn(t1, normalise=True)     # and the engine is still usable
     l3.backward()
     assert all(torch.isfinite(p.grad).all() for p in m.model.parameters() if p.requires_grad)
+
+
+def test_workspaces_of_old_batch_shapes_are_released(static):
+    """the reference steps one batch shape per station-count group; the engine keeps the workspaces of the
+    last few shapes only (a shape a CUDA graph replays from is never released)."""
+    m = small_model("bf16", seed=6)
+    eng = m.engine
+    eng.MAX_SIGNATURES = 2
+    sizes = []
+    for k, nst in enumerate((200, 190, 180, 170, 160)):
+        t = concat_tasks([make_task(static, 9000 + 10 * k + i, n_stations=nst) for i in range(2)])
+        loss = m.loss_fn(t, normalise=True)
+        loss.backward()
+        sizes.append(len(eng._ws))
+        assert len(eng._sig_lru) <= 2
+    assert sizes[-1] <= sizes[1] + 2          # does not grow with the number of shapes seen
+    # a shape that came back after eviction still gives the same loss
+    t = concat_tasks([make_task(static, 9000 + i, n_stations=200) for i in range(2)])
+    with torch.no_grad():
+        a = float(m.loss_fn(t, normalise=True))
+        b = float(m.loss_fn(t, normalise=True))
+    assert a == b and np.isfinite(a)
