@@ -75,12 +75,14 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md).  The sampler process
+    is started EARLY (nvidia-smi takes seconds to come up when 8 ranks start one each) and runs until the arm ends; the
+    summary uses the samples that arrived between ``mark_start`` and ``mark_end`` (the timed region), or -- when the region
+    is shorter than the sampling period -- the nearest ones."""
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
-
-    def __enter__(self):
+        self.t0 = self.t1 = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -92,26 +94,40 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
-        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def __enter__(self):
+        self.t0 = time.perf_counter()
+        return self
 
     def __exit__(self, *a):
-        if self.proc is not None and not self.rows:
-            time.sleep(0.05)   # very short timed regions: give the sampler one period
+        self.t1 = time.perf_counter()
+
+    def close(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
+            self.proc = None
 
     def summary(self):
+        if self.proc is not None and self.t1 is not None:
+            time.sleep(0.06)          # let the sample that covers the end of the region arrive
+        rows = list(self.rows)
+        inside = [r for t, r in rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.03]
+        where = "timed region"
+        if not inside and rows and self.t0 is not None:
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            where = "nearest samples (region shorter than the sampling period)"
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -121,7 +137,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 _STATIC = {}
@@ -307,6 +323,7 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
     """Device-resident and end-to-end training throughput for one model shape; returns the fields of the JSON line."""
     from deepsensornz_b200 import ConvNP, concat_tasks, train_epoch
     barrier, timed = make_timer(world)
+    clk = ClockSampler(local)
     torch.manual_seed(0)
     model = ConvNP(precision=args.precision, **model_kwargs(args.internal_density, dim_yc))
     if world > 1:
@@ -356,11 +373,12 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
     run(dev[0])
     # ---- device-resident throughput ----
     launches0 = eng.launches
-    with ClockSampler(local) as clk:
+    with clk:
         ms = timed(lambda i: run(dev[i % 2]), steps)
     launches = (eng.launches - launches0) if gs is None else graph_launches * steps
     out.update(value=world * BATCH * steps / (ms * 1e-3), ms_per_step=ms / steps, gpu_launches=launches,
                cuda_graph=gs is not None, clocks=clk.summary(), grid=dev[0].grid)
+    clk.close()
     # ---- end to end: train_epoch over lists of raw numpy tasks (the reference's call form) ----
     if e2e:
         gs = run = None
@@ -429,6 +447,7 @@ def infer_arm(args, world, rank, local, n_tasks, warmup, profile=True):
     from deepsensornz_b200 import ConvNP, Task
     from deepsensornz_b200.synthetic import make_task
     barrier, timed = make_timer(world)
+    clk = ClockSampler(local)
     torch.manual_seed(0)
     model = ConvNP(precision=args.precision, **model_kwargs(args.internal_density))
     eng = model.engine
@@ -459,11 +478,12 @@ def infer_arm(args, world, rank, local, n_tasks, warmup, profile=True):
     for i in range(max(warmup, 3)):
         fwd(i)
     l0 = eng.launches
-    with ClockSampler(local) as clk:
+    with clk:
         ms = timed(fwd, n_tasks)
     launches = eng.launches - l0
     out = dict(value=world * n_tasks / (ms * 1e-3), ms_per_step=ms / n_tasks, gpu_launches=launches, clocks=clk.summary(),
                grid=dev[0].grid)
+    clk.close()
     # ---- end to end: ConvNP.predict (validate_ERA.py:88-92 / outputs/infer.py:96-103) ----
     model.predict(tasks[:max(3, min(warmup, n_tasks))], **kw)
     res = {}

@@ -288,7 +288,7 @@ def _predict_batched(model, tasks, Xn, aux_dev, nb, aff_mean, aff_std, copy_stre
         with torch.cuda.stream(d2h_stream):
             pin[slot][0][:b].copy_(mean, non_blocking=True)
             pin[slot][1][:b].copy_(std, non_blocking=True)
-            events[slot] = torch.cuda.Event()
+            events[slot] = torch.cuda.Event(blocking=True)     # drain threads sleep on it instead of spinning
             events[slot].record()
         mean.record_stream(d2h_stream)
         std.record_stream(d2h_stream)
@@ -369,7 +369,10 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
     # so it overlaps the launches of the following tasks
     copy_stream = torch.cuda.Stream() if cuda else None
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=int(os.environ.get('CONVNP_B200_DRAIN_THREADS', '6')))
+    # drain threads: 6 on a GPU of its own; with one process per GPU of a box (torchrun sets LOCAL_WORLD_SIZE) the host
+    # cores are shared -- 8 processes x 6 spinning threads on 16 cores ran 4x slower per date than one process
+    cores_per_proc = (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    pool = ThreadPoolExecutor(max_workers=int(os.environ.get("CONVNP_B200_DRAIN_THREADS", max(2, min(6, cores_per_proc - 1)))))
     futures = [None, None, None]
     # CUDA-graph replay of the forward for tasks sharing a batch signature (CONVNP_B200_PREDICT_GRAPH=1)
     # Opt-in: with the static context sets cached and three drain threads the eager loop already runs at the pace of
@@ -460,12 +463,12 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
                 with torch.cuda.stream(copy_stream):
                     pin[slot][0].copy_(mean, non_blocking=True)
                     pin[slot][1].copy_(std, non_blocking=True)
-                    events[slot] = torch.cuda.Event()
+                    events[slot] = torch.cuda.Event(blocking=True)
                     events[slot].record()
             else:
                 pin[slot][0].copy_(mean, non_blocking=True)
                 pin[slot][1].copy_(std, non_blocking=True)
-                events[slot] = torch.cuda.Event()
+                events[slot] = torch.cuda.Event(blocking=True)
                 events[slot].record()
             futures[slot] = pool.submit(drain, slot, idx)
         else:
