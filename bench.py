@@ -24,8 +24,8 @@ stations with 5 aux-at-target channels; internal_density 250 -> 304 x 304 intern
                  configs[1] at the in-repo default internal_density=500), so that every run carries them
 
 Inference ("infer"): a "step" is one task (one date/hour) predicted onto the 1400 x 1400 target grid (configs[2], and
-configs[4] when sharded by date over N GPUs: no collective).  value = forward only with inputs resident, outputs left on
-the device; e2e = ``ConvNP.predict(tasks, X_t=...)`` with H2D of the per-hour sets and the D2H of mean + std (15.7 MB per
+configs[4] when sharded by date over N GPUs: no collective).  value = forward only with inputs resident (4 dates per
+launch sequence, as ``predict`` runs them), outputs left on the device; e2e = ``ConvNP.predict(tasks, X_t=...)`` with H2D of the per-hour sets and the D2H of mean + std (15.7 MB per
 task) inside the timed region; roofline = the fused tensor-core decoder (``decode_grid_tc``).
 
 One process per GPU; under torchrun the gradient bucket is all-reduced with NCCL (weak scaling: every rank steps its own
@@ -459,30 +459,34 @@ def infer_arm(args, world, rank, local, n_tasks, warmup, profile=True):
              for h in range(n_tasks)]
     kw = dict(X_t=(x_hi, x_hi), X_t_is_normalised=True, aux_at_targets_override=static.aux_hi)
     # ---- device-resident: inputs uploaded once, forward only, outputs stay on the device ----
-    nres = min(n_tasks, 8)
+    # the same forward ``predict`` runs: CONVNP_B200_PREDICT_BATCH (default 4) dates per launch sequence
+    from deepsensornz_b200.predict import _batch_contexts
+    nb = max(1, min(int(os.environ.get("CONVNP_B200_PREDICT_BATCH", "4")), n_tasks))
+    n_groups = min(max(1, n_tasks // nb), 4)
     aux_dev = torch.from_numpy(static.aux_hi[None]).to(eng.device)
     dev = []
-    for t in tasks[:nres]:
-        t2 = Task({k: v for k, v in t.items() if k not in ("Y_t", "Y_t_aux", "X_t")})
-        t2["ops"] = []
-        t2["X_t"], t2["Y_t"] = [(x_hi[None], x_hi[None])], []
-        db = eng.upload(model.stage_task(t2, pinned=False))
+    for gi in range(n_groups):
+        group = tasks[gi * nb:(gi + 1) * nb]
+        xt = (np.broadcast_to(x_hi[None], (len(group), x_hi.size)), np.broadcast_to(x_hi[None], (len(group), x_hi.size)))
+        db = eng.upload(eng.stage_host(_batch_contexts(group), xt, None, None, pinned=False))
         db.aux_t = aux_dev
         dev.append(db)
     torch.cuda.synchronize()
+    n_fwd = max(1, n_tasks // nb)          # forwards in the timed region; each covers nb dates
 
     def fwd(i):
         with torch.no_grad():
-            eng.forward(dev[i % nres], with_loss=False)
+            eng.forward(dev[i % n_groups], with_loss=False)
 
     for i in range(max(warmup, 3)):
         fwd(i)
     l0 = eng.launches
     with clk:
-        ms = timed(fwd, n_tasks)
+        ms = timed(fwd, n_fwd)
     launches = eng.launches - l0
-    out = dict(value=world * n_tasks / (ms * 1e-3), ms_per_step=ms / n_tasks, gpu_launches=launches, clocks=clk.summary(),
-               grid=dev[0].grid)
+    n_done = n_fwd * nb
+    out = dict(value=world * n_done / (ms * 1e-3), ms_per_step=ms / n_done, gpu_launches=launches, clocks=clk.summary(),
+               grid=dev[0].grid, dates_per_forward=nb)
     clk.close()
     # ---- end to end: ConvNP.predict (validate_ERA.py:88-92 / outputs/infer.py:96-103) ----
     model.predict(tasks[:max(3, min(warmup, n_tasks))], **kw)
@@ -508,6 +512,10 @@ def infer_arm(args, world, rank, local, n_tasks, warmup, profile=True):
             fwd(i)
         prof = eng.profile_stop()
         del os.environ["CNP_NO_PREPACK"], os.environ["CNP_NO_MULTISTREAM"]
+        for v in prof.values():            # per DATE (a launch covers nb dates)
+            v["ms"] /= nb
+            v["flops"] /= nb
+            v["bytes"] /= nb
         pk = peaks()
         name = "cnp_decode_grid_tc_fwd"
         if name in prof:
@@ -561,6 +569,7 @@ def run_ours(args):
         inf = infer_arm(args, world, rank, local, 16, 3, profile=(world == 1))
         line["inference"] = {"workload": "configs[2]/[4]: ConvNP.predict onto 1400x1400, 16 tasks per GPU",
                              "value": inf["value"], "unit": "tasks/s", "ms_per_task": inf["ms_per_step"], "tasks": 16,
+                             "dates_per_forward": inf["dates_per_forward"],
                              "e2e": inf["e2e"], "roofline": inf.get("roofline"), "gpu_launches": inf["gpu_launches"]}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

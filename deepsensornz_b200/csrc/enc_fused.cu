@@ -114,34 +114,49 @@ __device__ __forceinline__ const cnp_enc_set& sweep_decode(const cnp_sweep_args&
   return a.S.s[k];
 }
 
+// one thread = one grid column j of HR consecutive input rows: the band of a column (start, length, tap weights) is
+// looked up once and shared by the rows
+constexpr int HR = 2;
 template <int C, bool MASK>
-__device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p, int j, int n1, int n2) {
+__device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p0r, int j, int n1, int n2) {
   const int N1 = st.N1, N2 = st.N2;
   const int q0 = __ldg(st.tab_i + 2 * n1 + j), len = __ldg(st.tab_i + 2 * n1 + n2 + j);
   const float* w2 = st.tab_w + st.KB * n1 + j;
   const int plane = N1 * N2;                       // (a context field has far fewer than 2^30 cells)
-  const float* yb = st.y + (size_t)b * C * plane + p * N2 + q0;
-  const float* mb = MASK ? st.mask + (size_t)b * plane + p * N2 + q0 : nullptr;
-  float acc[C + 1];
+  const int nr = min(HR, N1 - p0r);
+  const float* yb = st.y + (size_t)b * C * plane + p0r * N2 + q0;
+  const float* mb = MASK ? st.mask + (size_t)b * plane + p0r * N2 + q0 : nullptr;
+  float acc[HR][C + 1];
 #pragma unroll
-  for (int c = 0; c <= C; ++c) acc[c] = 0.f;
-#pragma unroll 4
+  for (int r = 0; r < HR; ++r)
+#pragma unroll
+    for (int c = 0; c <= C; ++c) acc[r][c] = 0.f;
+#pragma unroll 2
   for (int k = 0; k < len; ++k) {
     const float w = __ldg(w2 + k * n2);
-    float v[C];
-    bool nan_any = false;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { v[c] = __ldg(yb + c * plane + k); nan_any |= isnan(v[c]); }
-    float valid = MASK ? __ldg(mb + k) : 1.f;
-    if (nan_any) valid = 0.f;
-    acc[0] = fmaf(valid, w, acc[0]);
+    for (int r = 0; r < HR; ++r) {
+      if (r < nr) {
+        float v[C];
+        bool nan_any = false;
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[1 + c] = fmaf(nan_any ? 0.f : (MASK ? v[c] * valid : v[c]), w, acc[1 + c]);
+        for (int c = 0; c < C; ++c) { v[c] = __ldg(yb + c * plane + r * N2 + k); nan_any |= isnan(v[c]); }
+        float valid = MASK ? __ldg(mb + r * N2 + k) : 1.f;
+        if (nan_any) valid = 0.f;
+        acc[r][0] = fmaf(valid, w, acc[r][0]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[r][1 + c] = fmaf(nan_any ? 0.f : (MASK ? v[c] * valid : v[c]), w, acc[r][1 + c]);
+      }
+    }
   }
   const int tplane = N1 * n2;
-  float* T = st.T + (size_t)b * (C + 1) * tplane + p * n2 + j;
+  float* T = st.T + (size_t)b * (C + 1) * tplane + p0r * n2 + j;
 #pragma unroll
-  for (int c = 0; c <= C; ++c) T[c * tplane] = acc[c];
+  for (int r = 0; r < HR; ++r)
+    if (r < nr) {
+#pragma unroll
+      for (int c = 0; c <= C; ++c) T[c * tplane + r * n2] = acc[r][c];
+    }
 }
 
 #define CNP_SWITCH_C(Cv, ...)                     \
@@ -156,13 +171,16 @@ __device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p, 
     default: { constexpr int CC = 8; __VA_ARGS__; } break; \
   }
 
+// One instantiation per (channel count, mask present): every launch covers the gridded sets with that signature, so the
+// register allocation is the one of ITS channel count (a single kernel switching over 1..8 channels ran every set at the
+// 8-channel allocation: 72-126 registers, 24-34 % occupancy).
+template <int C, bool MASK>
 __global__ void __launch_bounds__(SW)
 enc_hpass_kernel(const __grid_constant__ cnp_sweep_args a) {
   int b, p, j;
   const cnp_enc_set& st = sweep_decode(a, &b, &p, &j);
   if (j >= a.n2) return;
-  if (st.mask) { CNP_SWITCH_C(st.C, hpass_elem<CC, true>(st, b, p, j, a.n1, a.n2)) }
-  else { CNP_SWITCH_C(st.C, hpass_elem<CC, false>(st, b, p, j, a.n1, a.n2)) }
+  hpass_elem<C, MASK>(st, b, p * HR, j, a.n1, a.n2);
 }
 
 // one thread = 4 adjacent columns of one (task, grid row): the T rows are read with 16 B loads (n2 % 4 == 0), the
@@ -221,19 +239,19 @@ __device__ __forceinline__ void vpass_elem(const cnp_enc_set& st, int b, int i, 
   for (int c = 1; c <= C; ++c) V[c * plane] = acc[c] * inv;
 }
 
-// VEC: the block sweeps 4 * SW columns, 4 per thread (needs n2 % 4 == 0 and 16 B aligned T / V planes)
-template <bool VEC>
-__global__ void __launch_bounds__(SW, 4)
+// VEC: the block sweeps 4 columns per thread (needs n2 % 4 == 0 and 16 B aligned T / V planes)
+template <int C, bool VEC>
+__global__ void __launch_bounds__(SW)
 enc_vpass_kernel(const __grid_constant__ cnp_sweep_args a, float eps) {
   int b, i, j;
   const cnp_enc_set& st = sweep_decode(a, &b, &i, &j);
   if (VEC) {
     j *= 4;
     if (j >= a.n2) return;
-    CNP_SWITCH_C(st.C, vpass_elem4<CC>(st, b, i, j, a.n1, a.n2, eps))
+    vpass_elem4<C>(st, b, i, j, a.n1, a.n2, eps);
   } else {
     if (j >= a.n2) return;
-    CNP_SWITCH_C(st.C, vpass_elem<CC>(st, b, i, j, a.n1, a.n2, eps))
+    vpass_elem<C>(st, b, i, j, a.n1, a.n2, eps);
   }
 }
 
@@ -473,7 +491,8 @@ static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who)
   return 0;
 }
 
-static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, int cols_per_block,
+// sweep arguments over the gridded sets with ``C`` channels (and, when ``mask`` >= 0, with / without a mask tensor)
+static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, int cols_per_block, int C, int mask,
                          cnp_sweep_args* a) {
   memset(a, 0, sizeof(*a));
   a->n1 = n1; a->n2 = n2; a->bpr = cnp_cdiv(n2, cols_per_block);
@@ -481,9 +500,9 @@ static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool v
   long long blocks = 0;
   for (int k = 0; k < sets->n_sets; ++k) {
     const cnp_enc_set& s = sets->s[k];
-    if (s.kind != 1) continue;
+    if (s.kind != 1 || s.C != C || (mask >= 0 && (s.mask != nullptr) != (mask != 0))) continue;
     a->S.s[n] = s;
-    a->rows[n] = vertical ? n1 : s.N1;
+    a->rows[n] = vertical ? n1 : cnp_cdiv(s.N1, HR);      // the horizontal pass sweeps HR input rows per thread
     a->blk0[n] = (int)blocks;
     blocks += (long long)(s.batched ? B : 1) * a->rows[n] * a->bpr;
     CNP_REQUIRE(blocks < (1LL << 31) && (long long)(s.batched ? B : 1) * (s.C + 1) * s.N1 * n2 < (1LL << 40),
@@ -495,16 +514,49 @@ static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool v
   return 0;
 }
 
+template <int C>
+static int ef_launch_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
+  for (int mask = 0; mask < 2; ++mask) {
+    cnp_sweep_args a;
+    if (int rc = ef_sweep_args(sets, B, n1, n2, false, SW, C, mask, &a)) return rc;
+    if (a.S.n_sets == 0) continue;
+    if (mask) enc_hpass_kernel<C, true><<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
+    else enc_hpass_kernel<C, false><<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
+    CNP_LAUNCH_CHECK("enc_hpass_kernel");
+  }
+  return 0;
+}
+
+template <int C>
+static int ef_launch_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, float eps, bool vec, int threads, cudaStream_t st) {
+  cnp_sweep_args a;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, true, vec ? 4 * threads : threads, C, -1, &a)) return rc;
+  if (a.S.n_sets == 0) return 0;
+  if (vec) enc_vpass_kernel<C, true><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
+  else enc_vpass_kernel<C, false><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
+  CNP_LAUNCH_CHECK("enc_vpass_kernel");
+  return 0;
+}
+
+#define CNP_FOR_EACH_C(CALL)                                                                         \
+  do {                                                                                               \
+    int rc__ = 0;                                                                                    \
+    { constexpr int CC = 1; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 2; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 3; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 4; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 5; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 6; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 7; rc__ = CALL; if (rc__) return rc__; }                                    \
+    { constexpr int CC = 8; rc__ = CALL; if (rc__) return rc__; }                                    \
+  } while (0)
+
 // Launch 1: horizontal band pass of every gridded set of ``sets`` (off-grid sets are skipped) into their T workspaces
 // ([B or 1][C+1][N1][n2] floats each).
 CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_hpass: bad arguments");
   if (int rc = ef_check_sets(sets, 1 << 30, "encode_hpass")) return rc;
-  cnp_sweep_args a;
-  if (int rc = ef_sweep_args(sets, B, n1, n2, false, SW, &a)) return rc;
-  if (a.S.n_sets == 0) return 0;
-  enc_hpass_kernel<<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
-  CNP_LAUNCH_CHECK("enc_hpass_kernel");
+  CNP_FOR_EACH_C(ef_launch_hpass<CC>(sets, B, n1, n2, st));    // one launch per channel count in use
   return 0;
 }
 
@@ -523,12 +575,7 @@ CNP_API int cnp_encode_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, fl
   // vector form: a block of `threads` lanes covers 4 * threads columns of one row (304 columns: 96 lanes, 79 % active)
   int threads = SW;
   if (vec) { threads = ((cnp_cdiv(n2, 4) + 31) / 32) * 32; if (threads > SW) threads = SW; }
-  cnp_sweep_args a;
-  if (int rc = ef_sweep_args(sets, B, n1, n2, true, vec ? 4 * threads : threads, &a)) return rc;
-  if (a.S.n_sets == 0) return 0;
-  if (vec) enc_vpass_kernel<true><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
-  else enc_vpass_kernel<false><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
-  CNP_LAUNCH_CHECK("enc_vpass_kernel");
+  CNP_FOR_EACH_C(ef_launch_vpass<CC>(sets, B, n1, n2, eps, vec, threads, st));
   return 0;
 }
 
