@@ -116,7 +116,7 @@ __device__ __forceinline__ const cnp_enc_set& sweep_decode(const cnp_sweep_args&
 
 // one thread = one grid column j of HR consecutive input rows: the band of a column (start, length, tap weights) is
 // looked up once and shared by the rows
-constexpr int HR = 2;
+constexpr int HR = 1;   // (2 rows per thread measured no faster: 42 vs 39 us, more registers)
 template <int C, bool MASK>
 __device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p0r, int j, int n1, int n2) {
   const int N1 = st.N1, N2 = st.N2;
@@ -171,16 +171,16 @@ __device__ __forceinline__ void hpass_elem(const cnp_enc_set& st, int b, int p0r
     default: { constexpr int CC = 8; __VA_ARGS__; } break; \
   }
 
-// One instantiation per (channel count, mask present): every launch covers the gridded sets with that signature, so the
-// register allocation is the one of ITS channel count (a single kernel switching over 1..8 channels ran every set at the
-// 8-channel allocation: 72-126 registers, 24-34 % occupancy).
-template <int C, bool MASK>
+// (One instantiation per channel count, launched back to back, was measured SLOWER: the launches of the small shared
+// sets serialise behind the big one -- 54 + 51 us against 39 + 37 us for one launch per sweep that switches over 1..8
+// channels at the 8-channel register allocation.)
 __global__ void __launch_bounds__(SW)
 enc_hpass_kernel(const __grid_constant__ cnp_sweep_args a) {
   int b, p, j;
   const cnp_enc_set& st = sweep_decode(a, &b, &p, &j);
   if (j >= a.n2) return;
-  hpass_elem<C, MASK>(st, b, p * HR, j, a.n1, a.n2);
+  if (st.mask) { CNP_SWITCH_C(st.C, hpass_elem<CC, true>(st, b, p * HR, j, a.n1, a.n2)) }
+  else { CNP_SWITCH_C(st.C, hpass_elem<CC, false>(st, b, p * HR, j, a.n1, a.n2)) }
 }
 
 // one thread = 4 adjacent columns of one (task, grid row): the T rows are read with 16 B loads (n2 % 4 == 0), the
@@ -240,18 +240,18 @@ __device__ __forceinline__ void vpass_elem(const cnp_enc_set& st, int b, int i, 
 }
 
 // VEC: the block sweeps 4 columns per thread (needs n2 % 4 == 0 and 16 B aligned T / V planes)
-template <int C, bool VEC>
-__global__ void __launch_bounds__(SW)
+template <bool VEC>
+__global__ void __launch_bounds__(SW, 4)
 enc_vpass_kernel(const __grid_constant__ cnp_sweep_args a, float eps) {
   int b, i, j;
   const cnp_enc_set& st = sweep_decode(a, &b, &i, &j);
   if (VEC) {
     j *= 4;
     if (j >= a.n2) return;
-    vpass_elem4<C>(st, b, i, j, a.n1, a.n2, eps);
+    CNP_SWITCH_C(st.C, vpass_elem4<CC>(st, b, i, j, a.n1, a.n2, eps))
   } else {
     if (j >= a.n2) return;
-    vpass_elem<C>(st, b, i, j, a.n1, a.n2, eps);
+    CNP_SWITCH_C(st.C, vpass_elem<CC>(st, b, i, j, a.n1, a.n2, eps))
   }
 }
 
@@ -491,8 +491,7 @@ static int ef_check_sets(const cnp_enc_sets* sets, int c_total, const char* who)
   return 0;
 }
 
-// sweep arguments over the gridded sets with ``C`` channels (and, when ``mask`` >= 0, with / without a mask tensor)
-static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, int cols_per_block, int C, int mask,
+static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool vertical, int cols_per_block,
                          cnp_sweep_args* a) {
   memset(a, 0, sizeof(*a));
   a->n1 = n1; a->n2 = n2; a->bpr = cnp_cdiv(n2, cols_per_block);
@@ -500,7 +499,7 @@ static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool v
   long long blocks = 0;
   for (int k = 0; k < sets->n_sets; ++k) {
     const cnp_enc_set& s = sets->s[k];
-    if (s.kind != 1 || s.C != C || (mask >= 0 && (s.mask != nullptr) != (mask != 0))) continue;
+    if (s.kind != 1) continue;
     a->S.s[n] = s;
     a->rows[n] = vertical ? n1 : cnp_cdiv(s.N1, HR);      // the horizontal pass sweeps HR input rows per thread
     a->blk0[n] = (int)blocks;
@@ -514,49 +513,16 @@ static int ef_sweep_args(const cnp_enc_sets* sets, int B, int n1, int n2, bool v
   return 0;
 }
 
-template <int C>
-static int ef_launch_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
-  for (int mask = 0; mask < 2; ++mask) {
-    cnp_sweep_args a;
-    if (int rc = ef_sweep_args(sets, B, n1, n2, false, SW, C, mask, &a)) return rc;
-    if (a.S.n_sets == 0) continue;
-    if (mask) enc_hpass_kernel<C, true><<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
-    else enc_hpass_kernel<C, false><<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
-    CNP_LAUNCH_CHECK("enc_hpass_kernel");
-  }
-  return 0;
-}
-
-template <int C>
-static int ef_launch_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, float eps, bool vec, int threads, cudaStream_t st) {
-  cnp_sweep_args a;
-  if (int rc = ef_sweep_args(sets, B, n1, n2, true, vec ? 4 * threads : threads, C, -1, &a)) return rc;
-  if (a.S.n_sets == 0) return 0;
-  if (vec) enc_vpass_kernel<C, true><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
-  else enc_vpass_kernel<C, false><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
-  CNP_LAUNCH_CHECK("enc_vpass_kernel");
-  return 0;
-}
-
-#define CNP_FOR_EACH_C(CALL)                                                                         \
-  do {                                                                                               \
-    int rc__ = 0;                                                                                    \
-    { constexpr int CC = 1; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 2; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 3; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 4; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 5; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 6; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 7; rc__ = CALL; if (rc__) return rc__; }                                    \
-    { constexpr int CC = 8; rc__ = CALL; if (rc__) return rc__; }                                    \
-  } while (0)
-
 // Launch 1: horizontal band pass of every gridded set of ``sets`` (off-grid sets are skipped) into their T workspaces
 // ([B or 1][C+1][N1][n2] floats each).
 CNP_API int cnp_encode_hpass(const cnp_enc_sets* sets, int B, int n1, int n2, cudaStream_t st) {
   CNP_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "encode_hpass: bad arguments");
   if (int rc = ef_check_sets(sets, 1 << 30, "encode_hpass")) return rc;
-  CNP_FOR_EACH_C(ef_launch_hpass<CC>(sets, B, n1, n2, st));    // one launch per channel count in use
+  cnp_sweep_args a;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, false, SW, &a)) return rc;
+  if (a.S.n_sets == 0) return 0;
+  enc_hpass_kernel<<<(unsigned)a.blk0[a.S.n_sets], SW, 0, st>>>(a);
+  CNP_LAUNCH_CHECK("enc_hpass_kernel");
   return 0;
 }
 
@@ -575,7 +541,12 @@ CNP_API int cnp_encode_vpass(const cnp_enc_sets* sets, int B, int n1, int n2, fl
   // vector form: a block of `threads` lanes covers 4 * threads columns of one row (304 columns: 96 lanes, 79 % active)
   int threads = SW;
   if (vec) { threads = ((cnp_cdiv(n2, 4) + 31) / 32) * 32; if (threads > SW) threads = SW; }
-  CNP_FOR_EACH_C(ef_launch_vpass<CC>(sets, B, n1, n2, eps, vec, threads, st));
+  cnp_sweep_args a;
+  if (int rc = ef_sweep_args(sets, B, n1, n2, true, vec ? 4 * threads : threads, &a)) return rc;
+  if (a.S.n_sets == 0) return 0;
+  if (vec) enc_vpass_kernel<true><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
+  else enc_vpass_kernel<false><<<(unsigned)a.blk0[a.S.n_sets], threads, 0, st>>>(a, eps);
+  CNP_LAUNCH_CHECK("enc_vpass_kernel");
   return 0;
 }
 
