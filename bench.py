@@ -436,6 +436,30 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
                                "share_of_step": d["ms"] / tot_ms, "avg_launch_ms": d["ms"] / d["launches"],
                                "flops_per_launch": d["flops"] / d["launches"]}
         out["kernels"] = kernel_table(prof, 2, pk)
+        # the SetConv encoder as a whole, launched back to back (the per-launch events above include ~8 us of launch
+        # latency per small kernel because the GPU idles between them): algorithmic bytes = every context tensor once
+        # (fields shared by the batch once per step) + the blocked bf16 UNet input
+        if args.precision == "bf16" and eng.encode_blocked(dev[0]) is not None:
+            reps = 20
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                blk = eng.encode_blocked(dev[0])
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / reps * 1e3
+            g = dev[0].grid
+            by = sum(4.0 * (c.y.numel() + (c.mask.numel() if c.mask is not None else 0) +
+                            sum(v.numel() for v in (c.x if isinstance(c.x, tuple) else (c.x,)))) for c in dev[0].contexts)
+            by += 2.0 * BATCH * blk.CB * 8 * g.n1 * g.n2
+            out["setconv_encoder"] = {"kernels": "enc_hpass + enc_vpass + enc_fused (enc_fused.cu), 3 launches back to back",
+                                      "us_per_step": us, "algorithmic_mb": by / 1e6, "gbs": by / (us * 1e-6) / 1e9,
+                                      "frac_hbm": by / (us * 1e-6) / 1e9 / pk["hbm"], "peak_gbs": pk["hbm"],
+                                      "survey_8d_mb": 13.1 * BATCH,
+                                      "frac_hbm_survey_8d": 13.1e6 * BATCH / (us * 1e-6) / 1e9 / pk["hbm"],
+                                      "note": "survey_8d_mb = SURVEY 8(d)'s per-task figure (G = 320, Cin = 20, static sets "
+                                              "re-read per task) x 16 tasks"}
     eng.release_workspaces()
     del model, opt, eng
     torch.cuda.empty_cache()

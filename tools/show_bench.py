@@ -10,5 +10,5 @@ for k, v in d.get("kernels", {}).items():
     tot += v["ms_per_step"]
     print(f"{k:34s} {v['launches']:3d} {v['ms_per_step']:8.3f} ms  {'' if v['tflops'] is None else round(v['tflops'],1)} {'' if v['gbs'] is None else round(v['gbs'],1)} {'' if not v.get('frac_hbm') else round(v['frac_hbm'],3)}")
 print("sum of kernel ms", round(tot, 3))
-for k in ("multivar", "grid608", "inference", "cpu_baseline"):
+for k in ("setconv_encoder", "multivar", "grid608", "inference", "cpu_baseline"):
     if k in d: print(k, {kk: vv for kk, vv in d[k].items() if kk not in ("roofline",)})
