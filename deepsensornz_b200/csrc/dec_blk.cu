@@ -107,28 +107,32 @@ dec_blk_dg_kernel(const float* __restrict__ df, const float* __restrict__ Wf, in
   dg[((size_t)b * Nt + t) * DH_C + k] = s;
 }
 
-// dWf[c,k] += sum_{b,t} df[b,c,t] g[b,t,k];  dbf[c] += sum_{b,t} df[b,c,t] sw[b,t]      one block per (c, b)
+// dWf[c,k] += sum_{b,t} df[b,c,t] g[b,t,k];  dbf[c] += sum_{b,t} df[b,c,t] sw[b,t]      one block per output channel c,
+// tasks and targets walked in order: a fixed summation order (run-to-run identical gradients; the first version ran one
+// block per (c, b) and met in dWf with atomics)
 __global__ void __launch_bounds__(64)
-dec_blk_dw_kernel(const float* __restrict__ df, const float* __restrict__ g, const float* __restrict__ sw, int Cz, int Nt,
-                  float* __restrict__ dWf, float* __restrict__ dbf) {
-  const int c = blockIdx.x, b = blockIdx.y, k = threadIdx.x;
-  const float* dfr = df + ((size_t)b * Cz + c) * Nt;
-  const float* gb = g + (size_t)b * Nt * DH_C + k;
+dec_blk_dw_kernel(const float* __restrict__ df, const float* __restrict__ g, const float* __restrict__ sw, int B, int Cz,
+                  int Nt, float* __restrict__ dWf, float* __restrict__ dbf) {
+  const int c = blockIdx.x, k = threadIdx.x;
   float s0 = 0.f, s1 = 0.f, sb = 0.f;
-  int t = 0;
-  for (; t + 1 < Nt; t += 2) {
-    const float d0 = __ldg(dfr + t), d1 = __ldg(dfr + t + 1);
-    s0 = fmaf(d0, __ldg(gb + (size_t)t * DH_C), s0);
-    s1 = fmaf(d1, __ldg(gb + (size_t)(t + 1) * DH_C), s1);
-    if (k == 0) sb += d0 * __ldg(sw + (size_t)b * Nt + t) + d1 * __ldg(sw + (size_t)b * Nt + t + 1);
+  for (int b = 0; b < B; ++b) {
+    const float* dfr = df + ((size_t)b * Cz + c) * Nt;
+    const float* gb = g + (size_t)b * Nt * DH_C + k;
+    int t = 0;
+    for (; t + 1 < Nt; t += 2) {
+      const float d0 = __ldg(dfr + t), d1 = __ldg(dfr + t + 1);
+      s0 = fmaf(d0, __ldg(gb + (size_t)t * DH_C), s0);
+      s1 = fmaf(d1, __ldg(gb + (size_t)(t + 1) * DH_C), s1);
+      if (k == 0) sb += d0 * __ldg(sw + (size_t)b * Nt + t) + d1 * __ldg(sw + (size_t)b * Nt + t + 1);
+    }
+    if (t < Nt) {
+      const float d0 = __ldg(dfr + t);
+      s0 = fmaf(d0, __ldg(gb + (size_t)t * DH_C), s0);
+      if (k == 0) sb += d0 * __ldg(sw + (size_t)b * Nt + t);
+    }
   }
-  if (t < Nt) {
-    const float d0 = __ldg(dfr + t);
-    s0 = fmaf(d0, __ldg(gb + (size_t)t * DH_C), s0);
-    if (k == 0) sb += d0 * __ldg(sw + (size_t)b * Nt + t);
-  }
-  atomicAdd(dWf + (size_t)c * DH_C + k, s0 + s1);
-  if (k == 0 && dbf) atomicAdd(dbf + c, sb);
+  dWf[(size_t)c * DH_C + k] += s0 + s1;
+  if (k == 0 && dbf) dbf[c] += sb;
 }
 
 // d_h[b,k,i,j] = (h > 0) * sum_t dg[b,t,k] w1[i,t] w2[j,t], written densely in the blocked layout.
@@ -252,7 +256,7 @@ CNP_API int cnp_dec_blk_bwd_params(const float* df, const float* g, const float*
   dim3 grid(Nt, B);
   dec_blk_dg_kernel<<<grid, 64, 0, st>>>(df, Wf, Cz, Nt, dg);
   CNP_LAUNCH_CHECK("dec_blk_dg_kernel");
-  dec_blk_dw_kernel<<<dim3(Cz, B), 64, 0, st>>>(df, g, sw, Cz, Nt, dWf, dbf);
+  dec_blk_dw_kernel<<<Cz, 64, 0, st>>>(df, g, sw, B, Cz, Nt, dWf, dbf);
   CNP_LAUNCH_CHECK("dec_blk_dw_kernel");
   return 0;
 }

@@ -217,7 +217,7 @@ constexpr int BW_PTS = 8;
 __global__ void __launch_bounds__(256)
 mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal, int Cf,
                     const float* __restrict__ aux, int Ca, const float* __restrict__ yt, int Nt,
-                    const float* __restrict__ dlogp, float* __restrict__ df) {
+                    const float* __restrict__ dlogp, float* __restrict__ df, float* __restrict__ gws, int ws_stride) {
   extern __shared__ __align__(16) float smem[];
   const Offsets o = make_offsets(p);
   const int L = p.n_layers;
@@ -308,7 +308,11 @@ mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
     }
   }
   __syncthreads();
-  // weight / bias gradients for this block's points
+  // weight / bias gradients for this block's points: with a workspace every block stores its partial sums
+  // ([block][W_0, b_0, W_1, b_1, ...], plain layout) and mlp_head_reduce_kernel adds the blocks in a fixed order
+  // (run-to-run identical gradients); without one they meet in dW / db through atomics
+  float* part = gws ? gws + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * ws_stride : nullptr;
+  int poff = 0;
   for (int l = 0; l < L; ++l) {
     const int in = p.dims[l], out = p.dims[l + 1];
     const float* A = acts + aoff[l] * BW_PTS;
@@ -317,13 +321,32 @@ mlp_head_bwd_kernel(cnp_mlp_params p, const float* __restrict__ f, int f_ctotal,
       const int oo = e / in, i = e % in;
       float s = 0.f;
       for (int pt = 0; pt < npts; ++pt) s = fmaf(G[pt * out + oo], A[pt * in + i], s);
-      atomicAdd(p.dW[l] + e, s);
+      if (part) part[poff + e] = s; else atomicAdd(p.dW[l] + e, s);
     }
+    poff += in * out;
     for (int oo = threadIdx.x; oo < out; oo += blockDim.x) {
       float s = 0.f;
       for (int pt = 0; pt < npts; ++pt) s += G[pt * out + oo];
-      atomicAdd(p.db[l] + oo, s);
+      if (part) part[poff + oo] = s; else atomicAdd(p.db[l] + oo, s);
     }
+    poff += out;
+  }
+}
+
+// dW_l / db_l += sum over the blocks of mlp_head_bwd_kernel, block 0 first: one thread per parameter
+__global__ void __launch_bounds__(256)
+mlp_head_reduce_kernel(cnp_mlp_params p, const float* __restrict__ ws, int ws_stride, int nblk) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= ws_stride) return;
+  float s = 0.f;
+  for (int k = 0; k < nblk; ++k) s += __ldg(ws + (size_t)k * ws_stride + e);
+  int off = e;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const int nw = p.dims[l] * p.dims[l + 1], nb = p.dims[l + 1];
+    if (off < nw) { p.dW[l][off] += s; return; }
+    off -= nw;
+    if (off < nb) { p.db[l][off] += s; return; }
+    off -= nb;
   }
 }
 
@@ -363,8 +386,19 @@ CNP_API int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctot
   return 0;
 }
 
+// Bytes of the optional partial-sum workspace of cnp_mlp_head_bwd (one slice of all MLP gradients per block).
+CNP_API long long cnp_mlp_head_bwd_workspace_bytes(const cnp_mlp_params* p, int B, int Nt) {
+  if (!p || p->n_layers < 1 || p->n_layers > CNP_MLP_MAX_LAYERS) return 0;
+  long long per = 0;
+  for (int l = 0; l < p->n_layers; ++l) per += (long long)p->dims[l] * p->dims[l + 1] + p->dims[l + 1];
+  return per * cnp_cdiv(Nt, BW_PTS) * B * (long long)sizeof(float);
+}
+
+// workspace (or NULL): with it the parameter gradients are reduced over the blocks in a fixed order (run-to-run
+// identical); without it they meet in dW / db through fp32 atomics.
 CNP_API int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
-                             const float* yt, int B, int Nt, const float* dlogp, float* df, cudaStream_t st) {
+                             const float* yt, int B, int Nt, const float* dlogp, float* df, void* workspace,
+                             long long workspace_bytes, cudaStream_t st) {
   if (int e = check_params(p, Cf, Ca)) return e;
   CNP_REQUIRE(B > 0 && Nt >= 0 && f_ctotal >= Cf && yt && dlogp && df, "mlp_head_bwd: bad arguments");
   for (int l = 0; l < p->n_layers; ++l) CNP_REQUIRE(p->dW[l] && p->db[l], "mlp_head_bwd: missing gradient buffers");
@@ -377,7 +411,14 @@ CNP_API int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctot
   static size_t attr_b = 0;
   if (smem > attr_b) { cudaFuncSetAttribute(mlp_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_b = smem; }
   dim3 grid(cnp_cdiv(Nt, BW_PTS), B);
-  mlp_head_bwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, dlogp, df);
+  const long long need = cnp_mlp_head_bwd_workspace_bytes(p, B, Nt);
+  float* ws = (workspace && workspace_bytes >= need) ? reinterpret_cast<float*>(workspace) : nullptr;
+  const int nblk = (int)(grid.x * grid.y), stride = (int)(need / sizeof(float) / nblk);
+  mlp_head_bwd_kernel<<<grid, 256, smem, st>>>(*p, f, f_ctotal, Cf, aux, Ca, yt, Nt, dlogp, df, ws, stride);
   CNP_LAUNCH_CHECK("mlp_head_bwd_kernel");
+  if (ws) {
+    mlp_head_reduce_kernel<<<cnp_cdiv(stride, 256), 256, 0, st>>>(*p, ws, stride, nblk);
+    CNP_LAUNCH_CHECK("mlp_head_reduce_kernel");
+  }
   return 0;
 }

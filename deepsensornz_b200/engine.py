@@ -1258,8 +1258,10 @@ class Engine:
         Cz = cfg.unet_out_channels
         df = self._buf("df", (B, Cz, Nt))
         p = self._mlp_params(grads)
+        hwsb = _cabi.lib().cnp_mlp_head_bwd_workspace_bytes(C.byref(p), B, Nt)
+        hws = self._buf("head_bwd_ws", (max(1, hwsb // 4),))
         self._call("cnp_mlp_head_bwd", C.byref(p), _ptr(f), Cz, Cz, _ptr(batch.aux_t), cfg.dim_aux_t, _ptr(batch.yt), B,
-                   Nt, _ptr(dlogp), _ptr(df), _stream())
+                   Nt, _ptr(dlogp), _ptr(df), _ptr(hws), hwsb, _stream())
         s2 = self._scale2(self.module.decoder.set_conv.log_scale)
         if z is None:
             A = ctx["A"]

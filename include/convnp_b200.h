@@ -273,8 +273,12 @@ int cnp_mlp_head_fwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int 
 int cnp_mlp_head_points_fwd(const cnp_mlp_params* p, const float* f, long long f_bstride, int Cf, const float* aux,
                             long long aux_bstride, int Ca, int B, long long npts, float* mean, float* stdv,
                             cnp_stream_t s);
+/* workspace (cnp_mlp_head_bwd_workspace_bytes) or NULL: with it dW / db are reduced over the blocks in a fixed order
+ * (run-to-run identical), without it through fp32 atomics */
+long long cnp_mlp_head_bwd_workspace_bytes(const cnp_mlp_params* p, int B, int Nt);
 int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
-                     const float* yt, int B, int Nt, const float* dlogp /*[B]*/, float* df, cnp_stream_t s);
+                     const float* yt, int B, int Nt, const float* dlogp /*[B]*/, float* df, void* workspace,
+                     long long workspace_bytes, cnp_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -169,3 +169,36 @@ def test_workspaces_of_old_batch_shapes_are_released(static):
         a = float(m.loss_fn(t, normalise=True))
         b = float(m.loss_fn(t, normalise=True))
     assert a == b and np.isfinite(a)
+
+
+def test_training_is_run_to_run_deterministic_and_graph_equals_eager(static):
+    """Every reduction of the bf16 training step runs in a fixed order (K-split weight gradients and their bias sums
+    through a workspace, MLP / final-1x1 gradients per block then in block order, the float64 log-pdf per task): two
+    runs give bit-identical weights, and the CUDA-graph replay equals the eager step bit for bit."""
+    groups = [[make_task(static, 1200 + 4 * k + i) for i in range(4)] for k in range(3)]
+
+    def run(mode):
+        m = small_model("bf16", seed=12)
+        opt = torch.optim.AdamW(m.model.parameters(), lr=1e-3, fused=True, capturable=True)
+        dev = [m._to_device(concat_tasks(g)) for g in groups]
+        losses = []
+
+        def eager(b):
+            opt.zero_grad(set_to_none=True)
+            loss = m.loss_fn(b, normalise=True)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+
+        losses.append(eager(dev[0]))
+        gs = GraphedTrainStep(m, opt, dev[0], warm=True) if mode == "graph" else None
+        for k in range(1, 5):
+            losses.append(float(gs.step(dev[k % 3])) if gs is not None else eager(dev[k % 3]))
+        torch.cuda.synchronize()
+        return losses, torch.cat([p.detach().flatten() for p in m.model.parameters()]).clone()
+
+    l1, w1 = run("eager")
+    l2, w2 = run("eager")
+    l3, w3 = run("graph")
+    assert l1 == l2 and torch.equal(w1, w2)
+    assert l1 == l3 and torch.equal(w1, w3)
