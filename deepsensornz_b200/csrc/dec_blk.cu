@@ -107,32 +107,34 @@ dec_blk_dg_kernel(const float* __restrict__ df, const float* __restrict__ Wf, in
   dg[((size_t)b * Nt + t) * DH_C + k] = s;
 }
 
-// dWf[c,k] += sum_{b,t} df[b,c,t] g[b,t,k];  dbf[c] += sum_{b,t} df[b,c,t] sw[b,t]      one block per output channel c,
-// tasks and targets walked in order: a fixed summation order (run-to-run identical gradients; the first version ran one
-// block per (c, b) and met in dWf with atomics)
-__global__ void __launch_bounds__(64)
+// dWf[c,k] += sum_{b,t} df[b,c,t] g[b,t,k];  dbf[c] += sum_{b,t} df[b,c,t] sw[b,t]      one block per output channel c:
+// 8 slices of the (task, target) range per hidden channel k, each walked in order, then added 0..7 -- a fixed summation
+// order (run-to-run identical gradients; the first version ran one block per (c, b) and met in dWf with atomics)
+constexpr int DW_PARTS = 8;
+__global__ void __launch_bounds__(64 * DW_PARTS)
 dec_blk_dw_kernel(const float* __restrict__ df, const float* __restrict__ g, const float* __restrict__ sw, int B, int Cz,
                   int Nt, float* __restrict__ dWf, float* __restrict__ dbf) {
-  const int c = blockIdx.x, k = threadIdx.x;
-  float s0 = 0.f, s1 = 0.f, sb = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float* dfr = df + ((size_t)b * Cz + c) * Nt;
-    const float* gb = g + (size_t)b * Nt * DH_C + k;
-    int t = 0;
-    for (; t + 1 < Nt; t += 2) {
-      const float d0 = __ldg(dfr + t), d1 = __ldg(dfr + t + 1);
-      s0 = fmaf(d0, __ldg(gb + (size_t)t * DH_C), s0);
-      s1 = fmaf(d1, __ldg(gb + (size_t)(t + 1) * DH_C), s1);
-      if (k == 0) sb += d0 * __ldg(sw + (size_t)b * Nt + t) + d1 * __ldg(sw + (size_t)b * Nt + t + 1);
-    }
-    if (t < Nt) {
-      const float d0 = __ldg(dfr + t);
-      s0 = fmaf(d0, __ldg(gb + (size_t)t * DH_C), s0);
-      if (k == 0) sb += d0 * __ldg(sw + (size_t)b * Nt + t);
-    }
+  __shared__ float ps[DW_PARTS][64], pb[DW_PARTS];
+  const int c = blockIdx.x, k = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int total = B * Nt, per = (total + DW_PARTS - 1) / DW_PARTS;
+  const int e0 = part * per, e1 = min(total, e0 + per);
+  float s = 0.f, sb = 0.f;
+  for (int e = e0; e < e1; ++e) {
+    const int b = e / Nt, t = e - b * Nt;
+    const float d = __ldg(df + ((size_t)b * Cz + c) * Nt + t);
+    s = fmaf(d, __ldg(g + ((size_t)b * Nt + t) * DH_C + k), s);
+    if (k == 0) sb += d * __ldg(sw + (size_t)b * Nt + t);
   }
-  dWf[(size_t)c * DH_C + k] += s0 + s1;
-  if (k == 0 && dbf) dbf[c] += sb;
+  ps[part][k] = s;
+  if (k == 0) pb[part] = sb;
+  __syncthreads();
+  if (part == 0) {
+    float a = 0.f, ab = 0.f;
+#pragma unroll
+    for (int q = 0; q < DW_PARTS; ++q) { a += ps[q][k]; ab += pb[q]; }
+    dWf[(size_t)c * DH_C + k] += a;
+    if (k == 0 && dbf) dbf[c] += ab;
+  }
 }
 
 // d_h[b,k,i,j] = (h > 0) * sum_t dg[b,t,k] w1[i,t] w2[j,t], written densely in the blocked layout.
@@ -256,7 +258,7 @@ CNP_API int cnp_dec_blk_bwd_params(const float* df, const float* g, const float*
   dim3 grid(Nt, B);
   dec_blk_dg_kernel<<<grid, 64, 0, st>>>(df, Wf, Cz, Nt, dg);
   CNP_LAUNCH_CHECK("dec_blk_dg_kernel");
-  dec_blk_dw_kernel<<<Cz, 64, 0, st>>>(df, g, sw, B, Cz, Nt, dWf, dbf);
+  dec_blk_dw_kernel<<<Cz, 64 * DW_PARTS, 0, st>>>(df, g, sw, B, Cz, Nt, dWf, dbf);
   CNP_LAUNCH_CHECK("dec_blk_dw_kernel");
   return 0;
 }
