@@ -73,9 +73,9 @@ LIKELIHOODS = {"cnp": 0, "het": 0, "bernoulli-gamma": 1, "cnp-spikes-beta": 2, "
 LIK_CHANNELS = {0: 2, 1: 4, 2: 5}      # head inputs per target variable
 
 # conv_tc kinds (must match conv_bf16.cu)
-KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD, KIND_UP_PHASE = range(7)
+KIND_K5S1, KIND_K1, KIND_K5S2, KIND_K5S1_DGRAD, KIND_K1_DGRAD, KIND_K5S2_DGRAD, KIND_UP_PHASE, KIND_UP_PHASE_DGRAD = range(8)
 # conv_tc_wgrad kinds (must match wgrad_bf16.cu)
-WG_K5S1, WG_K1, WG_K5S2, WG_K5S1_NARROW = range(4)
+WG_K5S1, WG_K1, WG_K5S2, WG_K5S1_NARROW, WG_UP_PHASE, WG_K5S1_T = range(6)
 
 _i, _d, _f, _ll = C.c_int, C.c_double, C.c_float, C.c_longlong
 _GRID = [_d, _i, _d, _i, _d]  # start1, n1, start2, n2, res
@@ -135,6 +135,12 @@ _SIGS = {
     "cnp_blk_from_nchw_f32": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
     "cnp_blk_from_nchw_f32_ones": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), _i, C.c_ulonglong, c_stream]),
     "cnp_up_phase_weights": (C.c_int, [c_fp, _i, _i, c_fp, c_stream]),
+    "cnp_up_strips_fwd": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, c_stream]),
+    "cnp_up_strips_scatter": (C.c_int, [C.POINTER(CnpBlk), C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, c_stream]),
+    "cnp_up_dy_split": (C.c_int, [C.POINTER(CnpBlk), C.POINTER(CnpBlk), C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, c_stream]),
+    "cnp_up_strips_bwd_fold": (C.c_int, [C.POINTER(CnpBlk), C.POINTER(CnpBlk), C.POINTER(CnpBlk), C.POINTER(CnpBlk), _i, _i,
+                                         c_stream]),
+    "cnp_up_wgrad_fold": (C.c_int, [c_fp, c_fp, _i, _i, c_fp, c_stream]),
     "cnp_fold_in_fwd": (C.c_int, [c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_fold_in_bwd": (C.c_int, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_stream]),
     "cnp_blk_to_nchw_f32": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, _ll, c_stream]),

@@ -37,6 +37,7 @@ struct cnp_c2_plan {
   int kb_chunk0[C2_MAX_KB];     // first of the 2 source chunks of this 16-channel K block
   int kb_wci0[C2_MAX_KB];       // weight input-channel base (packing)
   int kb_type[C2_MAX_KB];       // position list used by this K block
+  int kb_wsel[C2_MAX_KB];       // which of several stacked weight tensors this K block reads (packing; phase dgrad)
   int t_npos[C2_MAX_TYPES];
   short t_boff[C2_MAX_TYPES][C2_MAX_POS];          // B start, in window pixels (row*pitch + col)
   signed char t_tap[C2_MAX_TYPES][C2_MAX_POS][4];  // (ky0,kx0) of group 0, (ky1,kx1) of group 1; -1 = zero block
@@ -559,7 +560,8 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 __global__ void __launch_bounds__(256)
 pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transposed, int wide, int co_off,
              __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_c2_plan plan, int total_pos,
-             long long group_stride /* elements between the weight tensors of lane groups 0 and 1 (0: the same tensor) */) {
+             long long group_stride /* elements between the weight tensors of lane groups 0 and 1 (0: the same tensor) */,
+             long long wsel_stride /* elements between the stacked weight tensors selected per K block (plan.kb_wsel) */) {
   const long long total = (long long)total_pos * 2048;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     const int c = (int)(e & 7), m = (int)((e >> 3) & 127), k8 = (int)((e >> 10) & 1);
@@ -576,7 +578,7 @@ pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transpos
       if (!transposed) {
         if (nn < Cout && kc < Cin) v = w[(size_t)g * group_stride + (((size_t)nn * Cin + kc) * k + ky) * k + kx];
       } else {
-        if (kc < Cout && nn < Cin) v = w[(((size_t)kc * Cin + nn) * k + ky) * k + kx];
+        if (kc < Cout && nn < Cin) v = w[(size_t)plan.kb_wsel[kb] * wsel_stride + (((size_t)kc * Cin + nn) * k + ky) * k + kx];
       }
     }
     wpk[e] = __float2bfloat16_rn(v);
@@ -587,7 +589,7 @@ pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transpos
 // host-side plan construction
 // ---------------------------------------------------------------------------------------------
 enum { KIND_K5S1 = 0, KIND_K1 = 1, KIND_K5S2 = 2, KIND_K5S1_DGRAD = 3, KIND_K1_DGRAD = 4, KIND_K5S2_DGRAD = 5,
-       KIND_UP_PHASE = 6 };
+       KIND_UP_PHASE = 6, KIND_UP_PHASE_DGRAD = 7 };
 
 struct Tap { int roff, coff, wky, wkx; };
 
@@ -689,6 +691,22 @@ int build_plan2(int kind, int n_chunks, int pitch, int py, int px, int wide, cnp
       }
     if (int e = add_type(p, 0, taps, nt, pitch, 0, taps1, nt1)) return e;
     for (int g = 0; g < n_chunks / 2; ++g) add_kb(2 * g, 16 * g, 0);
+  } else if (kind == KIND_UP_PHASE_DGRAD) {
+    // Input gradient of the polyphase resize-convolution at LOW resolution: the source is the space-to-depth copy of dY
+    // (chunk = (a*2+b)*8 + c holds dY[2i+a, 2j+b]), the reduction runs over the 4 phases x 64 channels, and phase (a, b)
+    // contributes its 4x4 taps (p, q) at window offsets (4-a-p, 4-b-q) of a 5x5 window:
+    //   dx[r, c] = sum_{a,b,p,q} Wp[a,b,:,ci,p,q] . dY_ab[r + 2 - a - p, c + 2 - b - q]
+    // 16 K blocks x 16 positions = 256 tap-GEMMs per low-res pixel against 4 x 100 for dgrad + upsample^T.  The weights are
+    // the four phase tensors [a][b][Cout][Cin][4][4] (cnp_up_phase_weights), selected per K block.
+    CNP_REQUIRE(n_chunks == 32 && wide, "conv plan: the up-phase dgrad reads the 4x8-chunk phase tensor of dY and produces 128 channels");
+    for (int ph = 0; ph < 4; ++ph) {
+      const int a = ph >> 1, b = ph & 1;
+      int nt = 0;
+      for (int pp = 0; pp < 4; ++pp)
+        for (int qq = 0; qq < 4; ++qq) taps[nt++] = Tap{4 - a - pp, 4 - b - qq, pp, qq};
+      if (int e = add_type(p, ph, taps, nt, pitch, 1)) return e;     // one tap per position for both lane groups
+      for (int g = 0; g < 4; ++g) { add_kb(ph * 8 + 2 * g, 16 * g, ph); p->kb_wsel[p->n_kb - 1] = ph; }
+    }
   } else {
     CNP_REQUIRE(false, "conv plan: unknown kind %d", kind);
   }
@@ -798,11 +816,13 @@ CNP_API int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind
   cnp_c2_plan p;
   if (int e = build_plan2(kind, n_chunks, 8, py, px, n_out == 128, &p)) return e;
   const int total_pos = plan_total_pos(p);
-  CNP_REQUIRE(kind != KIND_UP_PHASE || k == 4, "conv_tc2_pack: the up-phase kind packs 4x4 phase weights [2][Cout][Cin][4][4]");
-  const int transposed = (kind >= KIND_K5S1_DGRAD && kind <= KIND_K5S2_DGRAD) ? 1 : 0;
+  CNP_REQUIRE((kind != KIND_UP_PHASE && kind != KIND_UP_PHASE_DGRAD) || k == 4,
+              "conv_tc2_pack: the up-phase kinds pack 4x4 phase weights ([2][Cout][Cin][4][4] of one row phase / all four)");
+  const int transposed = ((kind >= KIND_K5S1_DGRAD && kind <= KIND_K5S2_DGRAD) || kind == KIND_UP_PHASE_DGRAD) ? 1 : 0;
   pack2_kernel<<<128, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, co_off,
                                     reinterpret_cast<__nv_bfloat16*>(wpk), p, total_pos,
-                                    kind == KIND_UP_PHASE ? (long long)Cout * Cin * 16 : 0ll);
+                                    kind == KIND_UP_PHASE ? (long long)Cout * Cin * 16 : 0ll,
+                                    kind == KIND_UP_PHASE_DGRAD ? (long long)Cout * Cin * 16 : 0ll);
   CNP_LAUNCH_CHECK("pack2_kernel");
   return 0;
 }

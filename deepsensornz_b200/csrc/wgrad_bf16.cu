@@ -28,7 +28,7 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 
-#define CNP_WG_MAX_PASS 5
+#define CNP_WG_MAX_PASS 8
 #define CNP_WG_MAX_ACC 5
 
 
@@ -41,6 +41,7 @@ struct cnp_wg_pass {
   int slot[CNP_WG_MAX_ACC][2][2];   // tap index (ky*k+kx) of [accumulator][row half][column half], -1 = discard
   int ci0, ci1;                // input-channel base of the two row halves
   int ky0, n_grp;              // narrow inputs: the pass covers kernel rows ky0 .. ky0 + n_grp - 1 (one row group each)
+  int dy_chunk0;               // first dY chunk of this pass (phase kind: 16 * row phase)
 };
 
 struct cnp_wg_args {
@@ -55,6 +56,8 @@ struct cnp_wg_args {
   int cluster;                   // 5: the five ky passes of a K-split slice form a cluster and share the dY stream
   int narrow;                    // >0: chunks per row group -- the 16 X planes are [kernel row][chunk] (few input channels)
   int grp_shift;                 // narrow: pixel shift between consecutive row groups (= padded row pitch)
+  int dy_pair;                   // 1: the N = 128 operand is [dY chunks c0..c0+7 (p) ; chunks c0+8..c0+15 (p-1)] -- two x-phases
+  int bias_grp;                  // passes that see the same dY tiles (bias sums are dealt round-robin inside a group)
   cnp_wg_pass pass[CNP_WG_MAX_PASS];
 };
 
@@ -171,7 +174,8 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
     if (tc::elect_one()) {
       long long doff[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) doff[c] = (long long)(c & 7) * a.dy_plane - (c >> 3) * 8;   // 8..15 (dup): one pixel earlier
+      for (int c = 0; c < 16; ++c)   // 8..15 (dup): one pixel earlier; phase pairs: the second x-phase's chunks
+        doff[c] = (long long)(ps.dy_chunk0 + (a.dy_pair ? c : (c & 7))) * a.dy_plane - (c >> 3) * 8;
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
         const int s = it % WG_STAGES;
@@ -216,6 +220,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         const uint32_t acc0 = it > 0 ? 1u : 0u;
         const bool fast = nks == 8;
         if (fast && ps.n_acc == 3) wg_issue<3, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
+        else if (fast && ps.n_acc == 4) wg_issue<4, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
         else if (fast && ps.n_acc == 2) wg_issue<2, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
         else if (fast && ps.n_acc == 5) wg_issue<5, 0, 7>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
         else wg_issue_n(ps.n_acc, 0, nks - 1, tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc0);
@@ -226,6 +231,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         }
         const uint32_t acc1 = (it > 0 || nks > 1) ? 1u : 0u;
         if (fast && ps.n_acc == 3) wg_issue<3, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
+        else if (fast && ps.n_acc == 4) wg_issue<4, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
         else if (fast && ps.n_acc == 2) wg_issue<2, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
         else if (fast && ps.n_acc == 5) wg_issue<5, 7, 8>(tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
         else wg_issue_n(ps.n_acc, nks - 1, nks, tmem_base, ncols, xs16, astep, ds16, lbo, a_hi, b_hi, idesc, acc1);
@@ -249,7 +255,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
         const int s = it % WG_STAGES;
         tc::mbar_wait(full + s, (it / WG_STAGES) & 1);
         const uint8_t* ds = smem + s * stage_b + x_tile_b;
-        if ((int)(it % (uint32_t)a.n_pass) == (int)blockIdx.y)
+        if ((int)(it % (uint32_t)a.bias_grp) == (int)blockIdx.y % a.bias_grp)
         for (int px = et; px < P; px += 128) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -257,6 +263,15 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
             const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
 #pragma unroll
             for (int i = 0; i < 8; ++i) bs[c * 8 + i] += __bfloat162float(pb[i]);
+          }
+          if (a.dy_pair) {     // the second x-phase (its copy lies one pixel earlier: the sum over all tiles is the same)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(ds + (8 + c) * dy_plane_b + px * 16);
+              const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(&pk);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bs[c * 8 + i] += __bfloat162float(pb[i]);
+            }
           }
         }
         __syncwarp();
@@ -410,7 +425,7 @@ blk_channel_sum_kernel(const __nv_bfloat16* __restrict__ v, long long bs, int cb
 
 }  // namespace
 
-enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2, WG_K5S1_NARROW = 3 };
+enum { WG_K5S1 = 0, WG_K1 = 1, WG_K5S2 = 2, WG_K5S1_NARROW = 3, WG_UP_PHASE = 4, WG_K5S1_T = 5 };
 
 // dw (+=) torch layout [64][Cin][k][k] fp32; dbias (+=) [64] fp32 or NULL (sum of dy over batch and pixels).  x: source view (n_chunks = 8 or 16; 32 = phase tensor for
 // the stride-2 layers), dy: 8-chunk gradient view at the accumulator resolution.
@@ -426,6 +441,8 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   CNP_REQUIRE(x->H == dy->H && x->W == dy->W, "conv_tc_wgrad: x and dy must share the accumulator geometry");
   cnp_wg_args a;
   memset(&a, 0, sizeof(a));
+  const bool tswap = kind == WG_K5S1_T;      // same reduction, gradient stored with the taps transposed (column strips)
+  if (tswap) kind = WG_K5S1;
   const int H = dy->H, W = dy->W, Hp = H + 4, Wp = W + 4;
   a.x_plane = (long long)Hp * Wp * 8; a.dy_plane = a.x_plane;
   a.x = reinterpret_cast<const __nv_bfloat16*>(x->base) + (long long)x->cb_off * a.x_plane; a.x_bs = x->bstride;
@@ -443,12 +460,13 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   // inputs the second dY copy makes the stage L2-bound (measured 18 % slower), so those keep N = 64.
   // narrow kind: N = 128 measured 120 us against 151 us for five N = 64 MMAs per K step (16 channels, 304^2, B = 16)
   static const bool narrow_nodup = getenv("CNP_WGRAD_NARROW_NODUP") != nullptr;
-  a.dup = ((!no_dup && kind == WG_K5S1 && n_chunks == 16) || (kind == WG_K5S1_NARROW && !narrow_nodup)) ? 1 : 0;
+  a.dup = ((!no_dup && kind == WG_K5S1 && n_chunks == 16) || (kind == WG_K5S1_NARROW && !narrow_nodup) ||
+           kind == WG_UP_PHASE) ? 1 : 0;
   auto clear_slots = [](cnp_wg_pass& p) {
     for (int j = 0; j < CNP_WG_MAX_ACC; ++j)
       for (int h = 0; h < 2; ++h) p.slot[j][h][0] = p.slot[j][h][1] = -1;
   };
-  auto tap = [](int ky, int kx) { return (kx >= 0 && kx < 5) ? ky * 5 + kx : -1; };
+  auto tap = [tswap](int ky, int kx) { return (kx >= 0 && kx < 5) ? (tswap ? kx * 5 + ky : ky * 5 + kx) : -1; };
   if (kind == WG_K5S1) {
     CNP_REQUIRE(n_chunks == 8 || n_chunks == 16, "conv_tc_wgrad: 5x5 needs 8 or 16 source chunks");
     CNP_REQUIRE(Cin == n_chunks * 8, "conv_tc_wgrad: Cin mismatch");
@@ -519,9 +537,31 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
           for (int j = 0; j < 3; ++j) { p.slot[j][0][0] = tap(ky, 2 * j); p.slot[j][1][0] = tap(ky, 2 * j + 1); }
         }
       }
+  } else if (kind == WG_UP_PHASE) {
+    // Polyphase resize-convolution (up_poly.cu): x = the LOW-res input (16 chunks), dy = the space-to-depth copy of dY
+    // (32 chunks: (a*2+b)*8 + c).  dw = the phase gradients [a][b][64][Cin][4][4]:
+    //   dWp[a,b,co,ci,p,q] = sum dY_ab[i, j] x[i + a + p - 2, j + b + q - 2]
+    // One pass per (a, p); the N = 128 operand is [dY_a0(pix) ; dY_a1(pix - 1)], so the X operand at column offset j - 2
+    // yields tap q = j of BOTH x-phases: 4 MMAs of N = 128 per 16-pixel K step, all 8 halves useful (64 tap-GEMMs per
+    // low-res pixel against 4 x 30 slots of the 5x5 kernel on the upsampled tensor).
+    CNP_REQUIRE(n_chunks == 16 && Cin == 128, "conv_tc_wgrad: the up-phase kind needs a 128-channel low-res input");
+    a.KK = 16;
+    a.dy_pair = 1;
+    for (int ra = 0; ra < 2; ++ra)
+      for (int pp = 0; pp < 4; ++pp, ++np) {
+        cnp_wg_pass& p = a.pass[np];
+        clear_slots(p);
+        p.chunk0 = 0; p.shift_px = -1; p.ci0 = 0; p.ci1 = 64; p.dy_chunk0 = 16 * ra;
+        p.base_off = (ra + pp - 2) * Wp - 2;
+        p.n_acc = 4; p.a0 = 0; p.astep = 1;
+        for (int j = 0; j < 4; ++j)
+          for (int h = 0; h < 2; ++h)
+            for (int b = 0; b < 2; ++b) p.slot[j][h][b] = (ra * 2 + b) * 64 * Cin * 16 + pp * 4 + j;
+      }
   } else {
     CNP_REQUIRE(false, "conv_tc_wgrad: unknown kind %d", kind);
   }
+  a.bias_grp = kind == WG_UP_PHASE ? 4 : np;
   if (a.dup) {
     // the shifted dY copy sums dY[p-1]: run one pixel further so that it still covers the last interior pixel
     a.tiles_per_img = cnp_cdiv(p_end - a.p_start + 1, a.P);

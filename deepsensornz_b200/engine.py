@@ -795,10 +795,17 @@ class Engine:
 
     def _do_pack(self, key: str, req, buf: torch.Tensor) -> None:
         """Pack (and, for the first layer, fold the initial 1x1 into) one weight tensor on the current stream."""
-        w, kind, n_chunks, py, px, co_off, n_out, fold = req
+        w, kind, n_chunks, py, px, co_off, n_out, fold, pre = req
         ver = self._pack_version(req)
         Cout, Cin, k, _ = w.shape
         src = w
+        if pre == "tswap":        # column strips of the polyphase resize-convolution: the same layer, taps transposed
+            src = self._buf(f"tsw.{key}", tuple(w.shape))
+            src.copy_(w.detach().transpose(2, 3))
+        elif pre == "phase":      # 4x4 phase weights [2][2][Cout][Cin][4][4] of Upsample(x2, bilinear) + Conv 5x5
+            wp = self._buf(f"wp.{key}", (2, 2, Cout, Cin, 4, 4))
+            self._call("cnp_up_phase_weights", _ptr(w), Cout, Cin, _ptr(wp), _stream())
+            src, k = (wp[py] if kind == _cabi.KIND_UP_PHASE else wp), 4
         if fold is not None:
             w1, b1 = fold
             Cp = n_chunks * 8
@@ -811,9 +818,10 @@ class Engine:
         self._packed[key] = (ver, buf)
 
     def _packed_weights(self, key: str, w: torch.Tensor, kind: int, n_chunks: int, py=0, px=0, co_off=0,
-                        n_out=64, fold=None) -> torch.Tensor:
-        """``fold=(W1, b1)``: ``w`` is the first 5x5 and the packed tensor is the folded 5x5 over [x ; 1] (fold_in.cu)."""
-        req = (w, kind, n_chunks, py, px, co_off, n_out, fold)
+                        n_out=64, fold=None, pre=None) -> torch.Tensor:
+        """``fold=(W1, b1)``: ``w`` is the first 5x5 and the packed tensor is the folded 5x5 over [x ; 1] (fold_in.cu).
+        ``pre``: "tswap" packs the tap-transposed weights, "phase" the polyphase weights derived from ``w``."""
+        req = (w, kind, n_chunks, py, px, co_off, n_out, fold, pre)
         self._pack_reqs[key] = req
         if self._pack_event is not None:          # first consumer of the step: order after the side-stream packing
             torch.cuda.current_stream().wait_event(self._pack_event)
@@ -841,6 +849,10 @@ class Engine:
             kdim = n_chunks * 8
         elif kind == K.KIND_K5S2:
             kdim = 64 * 25
+        elif kind == K.KIND_UP_PHASE:            # both x-phases: 2 x 64 outputs per low-res pixel, 16 taps each
+            kdim = 2 * n_chunks * 8 * 16
+        elif kind == K.KIND_UP_PHASE_DGRAD:      # 4 phases x 64 channels x 16 taps
+            kdim = 4 * 64 * 16
         else:
             kdim = 64 * (3 if py == 0 else 2) * (5 if px == 2 else (3 if px == 0 else 2))   # px = 2: both x-phases
         fl = 2.0 * B * x.H * x.W * n_out * kdim
@@ -860,6 +872,76 @@ class Engine:
         o.accumulate = int(accumulate)
         o._keep = (bias, mask)
         return o
+
+    # ---- polyphase resize-convolution (up_poly.cu) -------------------------------------------
+    @staticmethod
+    def _up_poly_ok(x: "_Blk") -> bool:
+        """128-channel decoder levels of at least 8 x 8 low-res pixels; CNP_NO_POLYPHASE=1 keeps Upsample + Conv."""
+        return x.CB == 16 and x.H >= 8 and x.W >= 8 and not os.environ.get("CNP_NO_POLYPHASE")
+
+    def _up_strip_blks(self, key: str, B: int, CB: int, H: int, W: int):
+        """Row / column strip tensors of a level whose LOW-res size is H x W (up_poly.cu layout)."""
+        return self._blk(f"{key}.rows", 2 * B, CB, 6, 2 * W), self._blk(f"{key}.cols", 2 * B, CB, 6, 2 * H)
+
+    def _up_poly_fwd(self, key: str, x: "_Blk", w: torch.Tensor, bias: torch.Tensor, dst: CnpBlk, B: int) -> dict:
+        """dst (8 chunks at 2H x 2W) = relu(conv5x5(bilinear_up2x(x)) + bias) without the upsampled tensor: two phase
+        launches for the interior, the standard kernel on four strips for the 4-pixel band.  Returns the strips of the
+        upsampled tensor (the band's weight gradient needs them)."""
+        K = _cabi
+        S = _stream()
+        ncb, H, W = x.CB, x.H, x.W
+        for a in (0, 1):
+            wpk = self._packed_weights(f"{key}.ph{a}", w, K.KIND_UP_PHASE, ncb, py=a, pre="phase")
+            self._conv_tc(x.view(0), ncb, wpk, K.KIND_UP_PHASE,
+                          self._out_blk(dst, bias=bias, relu=True, scatter=(2, a, 2, 0)), B, py=a)
+        u_rows, u_cols = self._up_strip_blks(f"{key}.u", B, ncb, H, W)
+        self._call("cnp_up_strips_fwd", C.byref(x.view(0)), ncb, C.byref(u_rows.view()), C.byref(u_cols.view()), B, S)
+        o_rows, o_cols = self._up_strip_blks(f"{key}.o", B, 8, H, W)
+        wpk = self._packed_weights(key, w, K.KIND_K5S1, ncb)
+        self._conv_tc(u_rows.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(o_rows.view(0), bias=bias, relu=True), 2 * B)
+        wpk = self._packed_weights(f"{key}.t", w, K.KIND_K5S1, ncb, pre="tswap")
+        self._conv_tc(u_cols.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(o_cols.view(0), bias=bias, relu=True), 2 * B)
+        self._call("cnp_up_strips_scatter", C.byref(o_rows.view()), C.byref(o_cols.view()), C.byref(dst), B, S)
+        return {"u_rows": u_rows, "u_cols": u_cols}
+
+    def _up_poly_bwd(self, key: str, x: "_Blk", w: torch.Tensor, dy: CnpBlk, dx: "_Blk", saved: dict,
+                     gw: torch.Tensor, gb: torch.Tensor, B: int, mask: Optional["_Blk"] = None) -> None:
+        """Backward of ``_up_poly_fwd``: gw += dL/dw, gb += dL/dbias, dx (all chunks of x) = mask * dL/dx; dy is the
+        gradient w.r.t. the layer's pre-activation (8 chunks at 2H x 2W)."""
+        K = _cabi
+        S = _stream()
+        ncb, H, W = x.CB, x.H, x.W
+        Cin = ncb * 8
+        s2d = self._blk(f"{key}.dys2d", B, 32, H, W)
+        dy_rows, dy_cols = self._up_strip_blks(f"{key}.dy", B, 8, H, W)
+        self._call("cnp_up_dy_split", C.byref(dy), C.byref(s2d.view()), C.byref(dy_rows.view()), C.byref(dy_cols.view()),
+                   B, S)
+        wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
+        ws = self._buf("wgrad_ws", (wsb // 4,))
+        # weight gradient: phase gradients at low resolution + the strips' 5x5 gradients, folded into gw
+        dwp = self._buf(f"{key}.dwp", (2, 2, 64, Cin, 4, 4))
+        dwp.zero_()
+        self._call("cnp_conv_tc_wgrad", C.byref(x.view(0)), ncb, C.byref(s2d.view(0)), K.WG_UP_PHASE, _ptr(dwp), _ptr(gb),
+                   Cin, B, _ptr(ws), wsb, S, work=(2.0 * B * H * W * 4 * 64 * Cin * 16, 0.0))
+        u_rows, u_cols = saved["u_rows"], saved["u_cols"]
+        self._call("cnp_conv_tc_wgrad", C.byref(u_rows.view(0)), ncb, C.byref(dy_rows.view(0)), K.WG_K5S1, _ptr(gw),
+                   _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
+        # column strips are transposed images convolved with the tap-transposed weights: the gradient w.r.t. those,
+        # stored tap-transposed (WG_K5S1_T), is the gradient w.r.t. w itself
+        self._call("cnp_conv_tc_wgrad", C.byref(u_cols.view(0)), ncb, C.byref(dy_cols.view(0)), K.WG_K5S1_T, _ptr(gw),
+                   _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * H * 64 * Cin * 25, 0.0))
+        self._call("cnp_up_wgrad_fold", _ptr(dwp), None, 64, Cin, _ptr(gw), S)
+        # input gradient: one low-res launch over the four dY phases, then the band through the strips
+        wpk = self._packed_weights(f"{key}.dg.ph", w, K.KIND_UP_PHASE_DGRAD, 32, n_out=128, pre="phase")
+        mk = mask.view(0) if mask is not None else None
+        self._conv_tc(s2d.view(0), 32, wpk, K.KIND_UP_PHASE_DGRAD, self._out_blk(dx.view(0), mask=mk), B, n_out=128)
+        du_rows, du_cols = self._up_strip_blks(f"{key}.du", B, ncb, H, W)
+        wpk = self._packed_weights(f"{key}.dg.00", w, K.KIND_K5S1_DGRAD, 8, 0, 0, 0, 128)
+        self._conv_tc(dy_rows.view(0), 8, wpk, K.KIND_K5S1_DGRAD, self._out_blk(du_rows.view(0)), 2 * B, n_out=128)
+        wpk = self._packed_weights(f"{key}.dg.t", w, K.KIND_K5S1_DGRAD, 8, 0, 0, 0, 128, pre="tswap")
+        self._conv_tc(dy_cols.view(0), 8, wpk, K.KIND_K5S1_DGRAD, self._out_blk(du_cols.view(0)), 2 * B, n_out=128)
+        self._call("cnp_up_strips_bwd_fold", C.byref(du_rows.view()), C.byref(du_cols.view()), C.byref(dx.view()),
+                   C.byref(mk) if mk is not None else None, ncb, B, S)
 
     def _unet_fwd_bf16(self, enc: Optional[torch.Tensor], B: int, n1: int, n2: int, need_z: bool = True,
                        x_aug: Optional["_Blk"] = None) -> Tuple[Optional[torch.Tensor], dict]:
@@ -914,9 +996,16 @@ class Engine:
             x = cat[i]
         A["phases"] = phases
         ups = [None] * L
+        polys = [None] * L
         h_last = self._blk("h_last", B, 8, n1, n2)
         for i in range(L - 1, -1, -1):
             inp, ncb = cat[i], cat[i].CB
+            if st[i] == 2 and self._up_poly_ok(cat[i]):
+                # resize-convolution without the upsampled tensor (polyphase interior + strips for the band)
+                lyr = u.after_turn_layers[i]
+                dst = cat[i - 1].view(8) if i > 0 else h_last.view(0)
+                polys[i] = self._up_poly_fwd(f"after{i}", cat[i], lyr.weight, lyr.bias, dst, B)
+                continue
             if st[i] == 2:
                 up = self._blk(f"up{i}", B, ncb, 2 * res[i][0], 2 * res[i][1])
                 self._call("cnp_blk_upsample2x_fwd", C.byref(inp.view()), ncb, C.byref(up.view()), B, S)
@@ -926,7 +1015,7 @@ class Engine:
             dst = cat[i - 1].view(8) if i > 0 else h_last.view(0)
             wpk = self._packed_weights(f"after{i}", lyr.weight, K.KIND_K5S1, ncb)
             self._conv_tc(inp.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(dst, bias=lyr.bias, relu=True), B)
-        A["ups"], A["h_last"] = ups, h_last
+        A["ups"], A["h_last"], A["polys"] = ups, h_last, polys
         if not need_z:   # training: the decoder runs on h_last and the final 1x1 moves behind it (dec_blk.cu)
             return None, A
         z = self._buf("z", (B, 64, n1, n2))
@@ -993,6 +1082,12 @@ class Engine:
         for i in range(0, L):
             name = P + f"after_turn_layers.{i}"
             lyr = u.after_turn_layers[i]
+            if A["polys"][i] is not None:
+                self._up_poly_bwd(f"after{i}", cat[i], lyr.weight, dy_blk.view(dy_cb), d_cat[i], A["polys"][i],
+                                  grads[name + ".weight"], grads[name + ".bias"], B, mask=cat[i])
+                if i < L - 1:
+                    dy_blk, dy_cb = d_cat[i], 8
+                continue
             x_in = ups[i]
             nch = x_in.CB * 8
             wgrad_tc(x_in.view(0), x_in.CB, dy_blk.view(dy_cb), K.WG_K5S1, name, nch)

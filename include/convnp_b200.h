@@ -143,10 +143,17 @@ typedef struct cnp_conv_out {
 } cnp_conv_out;
 
 enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5,
-       CNP_UP_PHASE = 6 /* building block, not yet used by the engine: row phase py of conv5x5(bilinear_up2x(x)) as a 4x4
-                           convolution of the REPLICATE-padded low-res x; both x-phases per call; weights from
-                           cnp_up_phase_weights()[py], packed with k = 4; output sy = sx = 2, ay = py, ax = 0 */ };
-enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2, CNP_WG_K5S1_NARROW = 3 /* 1..8 source chunks */ };
+       CNP_UP_PHASE = 6 /* row phase py of conv5x5(bilinear_up2x(x)) as a 4x4 convolution of the low-res x (whatever its
+                           2-pixel ring holds is the padding: zeros in the engine, exact 2 low-res pixels off the border);
+                           both x-phases per call; weights from cnp_up_phase_weights()[py], packed with k = 4; output
+                           sy = sx = 2, ay = py, ax = 0 */,
+       CNP_UP_PHASE_DGRAD = 7 /* its input gradient at LOW resolution: source = the 32-chunk space-to-depth copy of dY
+                           (cnp_up_dy_split), weights = all four phase tensors of cnp_up_phase_weights() packed with
+                           k = 4, n_out = 128 */ };
+enum { CNP_WG_K5S1 = 0, CNP_WG_K1 = 1, CNP_WG_K5S2 = 2, CNP_WG_K5S1_NARROW = 3 /* 1..8 source chunks */,
+       CNP_WG_UP_PHASE = 4 /* x = low-res input (16 chunks), dy = space-to-depth dY (32 chunks);
+                              dw += [2][2][64][128][4][4] phase gradients (fold back with cnp_up_wgrad_fold) */,
+       CNP_WG_K5S1_T = 5  /* CNP_WG_K5S1 with the gradient stored tap-transposed: dw[co][ci][kx][ky] (column strips) */ };
 
 #ifdef CNP_LEGACY_CONV_TC   /* first formulation (pixels = M operand), only built with `make LEGACY=1` */
 long long cnp_conv_tc_packed_bytes(int kind, int n_chunks);
@@ -197,6 +204,21 @@ int cnp_blk_from_nchw_f32_ones(const float* src, long long src_bstride, int B, i
  * wf [Cout][Cp][k*k] = W5 . [W1 | b1] (channels Cin+1..Cp-1 zero); bwd maps the folded gradient dwf back (+=). */
 /* wp [2 row phase][2 x-phase][Cout][Cin][4][4] <- w5 [Cout][Cin][5][5]: polyphase weights of Upsample(x2, bilinear) + Conv 5x5 */
 int cnp_up_phase_weights(const float* w5, int Cout, int Cin, float* wp, cnp_stream_t s);
+/* Polyphase resize-convolution, band handling (up_poly.cu; tools/polyphase_strips.py states the decomposition):
+ * replaces torch.nn.Upsample(x2, bilinear) + Conv2d(5, padding=2) of neuralprocesses' UNet decoder levels.
+ * Strip tensors are blocked images [2B][chunks][6+4][L+4][8]: image s*B + b, s = 0 low edge / 1 high edge;
+ * rows: L = 2W high-res columns; cols: L = 2H, strip row = high-res column (transposed).
+ *   cnp_up_strips_fwd     : strips of bilinear_up2x(x)
+ *   cnp_up_strips_scatter : band outputs of the strip convolutions -> the high-res destination (8 chunks)
+ *   cnp_up_dy_split       : dY -> space-to-depth copy with the band zeroed (32 chunks, low res) + band strips
+ *   cnp_up_strips_bwd_fold: dx += mask(act > 0) * up2x^T(strip gradients w.r.t. the upsampled tensor)
+ *   cnp_up_wgrad_fold     : dw5 += fold^T(phase gradients) + tap-transposed column-strip gradient */
+int cnp_up_strips_fwd(const cnp_blk* x, int n_chunks, const cnp_blk* rows, const cnp_blk* cols, int B, cnp_stream_t s);
+int cnp_up_strips_scatter(const cnp_blk* rows, const cnp_blk* cols, const cnp_blk* dst, int B, cnp_stream_t s);
+int cnp_up_dy_split(const cnp_blk* dy, const cnp_blk* s2d, const cnp_blk* rows, const cnp_blk* cols, int B, cnp_stream_t s);
+int cnp_up_strips_bwd_fold(const cnp_blk* rows, const cnp_blk* cols, const cnp_blk* dx, const cnp_blk* act /*or NULL*/,
+                           int n_chunks, int B, cnp_stream_t s);
+int cnp_up_wgrad_fold(const float* dwp, const float* dwt /*or NULL*/, int Cout, int Cin, float* dw5 /*+=*/, cnp_stream_t s);
 int cnp_fold_in_fwd(const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin, int Cp, int k,
                     float* wf, cnp_stream_t s);
 int cnp_fold_in_bwd(const float* dwf, const float* w5, const float* w1, const float* b1, int Cout, int Cmid, int Cin,
