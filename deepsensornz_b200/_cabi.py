@@ -54,6 +54,8 @@ class CnpConvOut(C.Structure):
         ("mask", C.POINTER(CnpBlk)),
         ("accumulate", C.c_int),
         ("s2d", C.POINTER(CnpBlk)),
+        ("s2d_c0", C.c_int),
+        ("s2d_band", C.c_int),
     ]
 
 
@@ -132,6 +134,7 @@ _SIGS = {
     "cnp_conv_tc2_packed_bytes": (_ll, [_i, _i, _i]),
     "cnp_conv_tc2_pack": (C.c_int, [c_fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, c_fp, c_stream]),
     "cnp_conv_tc2": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, _i, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
+    "cnp_conv_tc2_w2": (C.c_int, [C.POINTER(CnpBlk), _i, c_fp, c_fp, _i, _i, _i, _i, _i, C.POINTER(CnpConvOut), _i, c_stream]),
     "cnp_blk_from_nchw_f32": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), c_stream]),
     "cnp_blk_from_nchw_f32_ones": (C.c_int, [c_fp, _ll, _i, _i, _i, _i, C.POINTER(CnpBlk), _i, C.c_ulonglong, c_stream]),
     "cnp_up_phase_weights": (C.c_int, [c_fp, _i, _i, c_fp, c_stream]),

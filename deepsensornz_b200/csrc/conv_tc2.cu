@@ -46,6 +46,7 @@ struct cnp_c2_plan {
 struct cnp_c2_args {
   const __nv_bfloat16* x; long long x_bs; int x_Hp, x_Wp;
   const uint8_t* w;
+  const uint8_t* w2; int w2_from_b;   // optional second packed weight tensor, used by the images b >= w2_from_b (strips)
   int B, H, W;
   int TW, TH, pitch, N, nacc, rpa, plane_sm, tiles_x, tiles_y;
   int wide;
@@ -60,6 +61,7 @@ struct cnp_c2_args {
   const __nv_bfloat16* mask; long long mask_bs; int mask_cb_off;
   int accumulate;
   __nv_bfloat16* s2d; long long s2d_bs;   // optional second output: space-to-depth copy (32 chunks at half resolution)
+  int s2d_c0, s2d_band;          // ... of the 8 output chunks from s2d_c0 on, skipping a band of s2d_band half-res pixels
   int dbg_flags;                 // profiling only: 1 = epilogue stops after the TMEM load, 2 = skips the global stores
   long long* dbg;                // optional [grid][8] cycle counters (cnp_conv_tc2_debug), else NULL
   cnp_c2_plan plan;
@@ -201,6 +203,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       for (int it = 0; it < n_iter; ++it) {
         if (a_cluster == 1 && (int)blockIdx.x + it * (int)gridDim.x >= ntiles) break;
         const uint8_t* wsrc = a.w;
+        if (a.w2 && decode_work(a, (int)blockIdx.x + it * (int)gridDim.x).b >= a.w2_from_b) wsrc = a.w2;
         for (int kb = 0; kb < a.plan.n_kb; ++kb) {
           const int npos = a.plan.t_npos[a.plan.kb_type[kb]];
           for (int s0 = 0; s0 < npos; s0 += C2_STAGE_POS, ++w_it) {
@@ -525,12 +528,15 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(obase + (long long)c * oplane * 8) =
                   make_uint4(wv[c * 4], wv[c * 4 + 1], wv[c * 4 + 2], wv[c * 4 + 3]);
-            if (a.s2d) {
+            const int sc0 = chunk0 - a.out_c_off - a.s2d_c0;     // WIDE: only the quadrants holding chunks s2d_c0 .. +7
+            if (a.s2d && sc0 >= 0 && sc0 < 8 && (oy >> 1) >= a.s2d_band && (oy >> 1) < (a.H >> 1) - a.s2d_band &&
+                (ox >> 1) >= a.s2d_band && (ox >> 1) < (a.W >> 1) - a.s2d_band) {
               // phase plane p = (y&1)*2 + (x&1) holds pixel (y/2, x/2): the input layout of the next stride-2 layer
+              // (and, with a band, of the polyphase resize-convolution's backward: up_poly.cu)
               const int H2p = (a.H >> 1) + 4, W2p = (a.W >> 1) + 4;
               const int ph = (oy & 1) * 2 + (ox & 1);
               __nv_bfloat16* sb = a.s2d + (long long)b * a.s2d_bs +
-                                  (((long long)(ph * 8 + chunk0 - a.out_c_off) * H2p + (oy >> 1) + 2) * W2p + (ox >> 1) + 2) * 8;
+                                  (((long long)(ph * 8 + sc0) * H2p + (oy >> 1) + 2) * W2p + (ox >> 1) + 2) * 8;
               const long long splane = (long long)H2p * W2p * 8;
 #pragma unroll
               for (int c = 0; c < 4; ++c)
@@ -788,6 +794,8 @@ struct cnp_conv_out {
   const cnp_blk* mask;
   int accumulate;
   const cnp_blk* s2d;    // optional: also write the space-to-depth copy of the output (32 chunks, half resolution)
+  int s2d_c0;            // first of the 8 output chunks that are copied (0; 8 = second half of a 128-channel output)
+  int s2d_band;          // half-res pixels along every edge that are NOT written (stay zero)
 };
 
 // Debug aid: when buf != NULL every later cnp_conv_tc2 launch writes, per CTA, 8 int64 counters
@@ -819,7 +827,8 @@ CNP_API int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind
   CNP_REQUIRE((kind != KIND_UP_PHASE && kind != KIND_UP_PHASE_DGRAD) || k == 4,
               "conv_tc2_pack: the up-phase kinds pack 4x4 phase weights ([2][Cout][Cin][4][4] of one row phase / all four)");
   const int transposed = ((kind >= KIND_K5S1_DGRAD && kind <= KIND_K5S2_DGRAD) || kind == KIND_UP_PHASE_DGRAD) ? 1 : 0;
-  pack2_kernel<<<128, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, co_off,
+  const int pack_blocks = total_pos * 2048 / (256 * 4) < 128 ? 128 : (total_pos * 2048 / (256 * 4) > 592 ? 592 : total_pos * 2048 / (256 * 4));
+  pack2_kernel<<<pack_blocks, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, co_off,
                                     reinterpret_cast<__nv_bfloat16*>(wpk), p, total_pos,
                                     kind == KIND_UP_PHASE ? (long long)Cout * Cin * 16 : 0ll,
                                     kind == KIND_UP_PHASE_DGRAD ? (long long)Cout * Cin * 16 : 0ll);
@@ -830,8 +839,24 @@ CNP_API int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind
 // Tensor-core convolution producing n_out (64 or 128) output channels at chunks [out.cb_off, +n_out/8).
 // x: blocked source whose chunks [x->cb_off, x->cb_off + n_chunks) are the reduction dimension;
 // (x->H, x->W) is the accumulator grid.
+static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, const void* wpk2, int w2_from_b, int kind, int py,
+                           int px, int n_out, const cnp_conv_out* o, int B, cudaStream_t st);
+
 CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, int n_out,
                          const cnp_conv_out* o, int B, cudaStream_t st) {
+  return conv_tc2_launch(x, n_chunks, wpk, nullptr, 0, kind, py, px, n_out, o, B, st);
+}
+
+// Same launch with TWO packed weight tensors: images b < w2_from_b use wpk, the others wpk2 (same kind and geometry).
+// One launch then serves the row strips and the tap-transposed column strips of a square level (up_poly.cu).
+CNP_API int cnp_conv_tc2_w2(const cnp_blk* x, int n_chunks, const void* wpk, const void* wpk2, int w2_from_b, int kind,
+                            int py, int px, int n_out, const cnp_conv_out* o, int B, cudaStream_t st) {
+  CNP_REQUIRE(wpk2 && w2_from_b > 0 && w2_from_b < B, "conv_tc2_w2: needs a second weight tensor and 0 < w2_from_b < B");
+  return conv_tc2_launch(x, n_chunks, wpk, wpk2, w2_from_b, kind, py, px, n_out, o, B, st);
+}
+
+static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, const void* wpk2, int w2_from_b, int kind, int py,
+                           int px, int n_out, const cnp_conv_out* o, int B, cudaStream_t st) {
   CNP_REQUIRE(x && o && wpk && B > 0, "conv_tc2: bad arguments");
   CNP_REQUIRE(n_out == 64 || n_out == 128, "conv_tc2: n_out must be 64 or 128");
   cnp_c2_args a;
@@ -841,12 +866,13 @@ CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int ki
   a.x = reinterpret_cast<const __nv_bfloat16*>(x->base) + (long long)x->cb_off * a.x_Hp * a.x_Wp * 8;
   a.x_bs = x->bstride;
   a.w = reinterpret_cast<const uint8_t*>(wpk);
+  a.w2 = reinterpret_cast<const uint8_t*>(wpk2); a.w2_from_b = w2_from_b;
   a.wide = n_out == 128;
   a.pxpair = ((kind == KIND_K5S2_DGRAD && px == 2) || kind == KIND_UP_PHASE) ? 1 : 0;
   CNP_REQUIRE(!a.pxpair || (o->mode == 0 && o->sx == 2 && o->ax == 0 && !o->s2d),
               "conv_tc2: the x-phase pair writes a blocked output with sx = 2, ax = 0");
   a.out_mode = o->mode;
-  a.cluster = g_c2_cluster;
+  a.cluster = wpk2 ? 1 : g_c2_cluster;    // the multicast weight stream assumes one tensor for the CTA pair
   if (int e = build_plan2(kind, n_chunks, 8, py, px, a.wide, &a.plan)) return e;   // position count only
   choose_geometry(&a, plan_total_pos(a.plan));
   CNP_REQUIRE(a.N > 0, "conv_tc2: no tile geometry for %d x %d", a.H, a.W);
@@ -859,10 +885,12 @@ CNP_API int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int ki
     a.out = o->blk.base; a.out_bs = o->blk.bstride; a.out_c_off = o->blk.cb_off;
     a.out_Hp = o->blk.H + 4; a.out_Wp = o->blk.W + 4;
     if (o->s2d) {
-      CNP_REQUIRE(n_out == 64 && o->sy == 1 && o->sx == 1 && o->blk.H % 2 == 0 && o->blk.W % 2 == 0 &&
-                  o->s2d->H == o->blk.H / 2 && o->s2d->W == o->blk.W / 2 && o->s2d->cb_off == 0,
+      CNP_REQUIRE(o->sy == 1 && o->sx == 1 && o->blk.H % 2 == 0 && o->blk.W % 2 == 0 &&
+                  o->s2d->H == o->blk.H / 2 && o->s2d->W == o->blk.W / 2 && o->s2d->cb_off == 0 && o->s2d_band >= 0 &&
+                  (o->s2d_c0 == 0 || (n_out == 128 && o->s2d_c0 == 8)),
                   "conv_tc2: space-to-depth output geometry mismatch");
       a.s2d = reinterpret_cast<__nv_bfloat16*>(o->s2d->base); a.s2d_bs = o->s2d->bstride;
+      a.s2d_c0 = o->s2d_c0; a.s2d_band = o->s2d_band;
     }
     if (o->mask) {
       CNP_REQUIRE(o->mask->H == o->blk.H && o->mask->W == o->blk.W, "conv_tc2: mask geometry mismatch");

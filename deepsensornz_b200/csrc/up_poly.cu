@@ -117,7 +117,7 @@ up_strips_scatter_kernel(blkv rows, blkv cols, blkv dst, int H2, int W2, int B) 
 __global__ void __launch_bounds__(256)
 up_dy_split_kernel(blkv dy, int H, int W, int B, blkv s2d, blkv rows, blkv cols) {
   const int H2 = 2 * H, W2 = 2 * W;
-  const long long n1 = (long long)B * 8 * H * W;
+  const long long n1 = s2d.p ? (long long)B * 8 * H * W : 0;
   const int L = W2 + H2;
   const long long n2 = (long long)B * 8 * 2 * UP_SR * L;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n1 + n2; e += (long long)gridDim.x * 256) {
@@ -299,11 +299,15 @@ CNP_API int cnp_up_strips_scatter(const cnp_blk* rows, const cnp_blk* cols, cons
 // dy (8 chunks, 2H x 2W) -> s2d (32 chunks = phase (a*2+b)*8 + chunk at H x W, band zeroed) + band strips.
 CNP_API int cnp_up_dy_split(const cnp_blk* dy, const cnp_blk* s2d, const cnp_blk* rows, const cnp_blk* cols, int B,
                             cudaStream_t st) {
-  CNP_REQUIRE(dy && s2d && B > 0 && dy->H == 2 * s2d->H && dy->W == 2 * s2d->W && s2d->H >= 8 && s2d->W >= 8 &&
-              s2d->cb_off == 0 && strips_ok(rows, cols, s2d->H, s2d->W), "up_dy_split: geometry mismatch");
-  const int H = s2d->H, W = s2d->W;
-  const long long total = (long long)B * 8 * H * W + (long long)B * 8 * 2 * UP_SR * (2 * W + 2 * H);
-  up_dy_split_kernel<<<grid_for(total), 256, 0, st>>>(view_of(dy), H, W, B, view_of(s2d), view_of(rows), view_of(cols));
+  CNP_REQUIRE(dy && B > 0 && dy->H % 2 == 0 && dy->W % 2 == 0 && dy->H >= 16 && dy->W >= 16 &&
+              (!s2d || (dy->H == 2 * s2d->H && dy->W == 2 * s2d->W && s2d->cb_off == 0)) &&
+              strips_ok(rows, cols, dy->H / 2, dy->W / 2), "up_dy_split: geometry mismatch");
+  const int H = dy->H / 2, W = dy->W / 2;
+  blkv sv;
+  sv.p = nullptr; sv.bs = 0; sv.Hp = sv.Wp = 0;
+  if (s2d) sv = view_of(s2d);
+  const long long total = (s2d ? (long long)B * 8 * H * W : 0) + (long long)B * 8 * 2 * UP_SR * (2 * W + 2 * H);
+  up_dy_split_kernel<<<grid_for(total), 256, 0, st>>>(view_of(dy), H, W, B, sv, view_of(rows), view_of(cols));
   CNP_LAUNCH_CHECK("up_dy_split_kernel");
   return 0;
 }

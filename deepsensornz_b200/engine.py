@@ -105,8 +105,9 @@ class _Blk:
         slack = (16 * (W + 4) + 512) * 8  # tile over-reads past the last plane stay inside the allocation
         self.t = torch.zeros(B * self.bstride + slack, dtype=torch.bfloat16, device=device)
 
-    def view(self, cb_off: int = 0) -> CnpBlk:
-        return CnpBlk(self.t.data_ptr(), self.bstride, cb_off, self.H, self.W)
+    def view(self, cb_off: int = 0, b_off: int = 0) -> CnpBlk:
+        """View from chunk ``cb_off`` (and image ``b_off``) on."""
+        return CnpBlk(self.t.data_ptr() + 2 * b_off * self.bstride, self.bstride, cb_off, self.H, self.W)
 
     def zero_(self):
         self.t.zero_()
@@ -137,6 +138,8 @@ class Engine:
         self._scale_cache: Dict[int, Tuple[int, float]] = {}
         self._enc_tabs: Dict[tuple, tuple] = {}      # band tables of the fused encoder, per (coordinates, grid, scale)
         self._pack_reqs: Dict[str, tuple] = {}     # every packing seen so far -> re-issued up front on a side stream
+        self._wp_ver: Dict[str, tuple] = {}        # polyphase weights per level: (weight version, forced-pack epoch)
+        self._pack_epoch = 0
         self._pack_stream = None
         self._pack_event = None
         self._pack_event_bwd = None
@@ -761,6 +764,7 @@ class Engine:
         if self.force_pack or self.weights_dirty:
             self.packs_recorded = 0
             self._forced = set()
+            self._pack_epoch += 1
         if os.environ.get("CNP_NO_PREPACK"):
             return
         force = self.force_pack or self.weights_dirty
@@ -803,8 +807,11 @@ class Engine:
             src = self._buf(f"tsw.{key}", tuple(w.shape))
             src.copy_(w.detach().transpose(2, 3))
         elif pre == "phase":      # 4x4 phase weights [2][2][Cout][Cin][4][4] of Upsample(x2, bilinear) + Conv 5x5
-            wp = self._buf(f"wp.{key}", (2, 2, Cout, Cin, 4, 4))
-            self._call("cnp_up_phase_weights", _ptr(w), Cout, Cin, _ptr(wp), _stream())
+            lk = key.split(".")[0]                       # the three packings of a level share one phase tensor
+            wp = self._buf(f"wp.{lk}", (2, 2, Cout, Cin, 4, 4))
+            if self._wp_ver.get(lk) != (ver, self._pack_epoch):
+                self._call("cnp_up_phase_weights", _ptr(w), Cout, Cin, _ptr(wp), _stream())
+                self._wp_ver[lk] = (ver, self._pack_epoch)
             src, k = (wp[py] if kind == _cabi.KIND_UP_PHASE else wp), 4
         if fold is not None:
             w1, b1 = fold
@@ -841,7 +848,7 @@ class Engine:
         self._do_pack(key, req, buf)
         return buf
 
-    def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0, n_out=64):
+    def _conv_tc(self, x: CnpBlk, n_chunks, wpk, kind, out: CnpConvOut, B, py=0, px=0, n_out=64, wpk2=None, w2_from_b=0):
         K = _cabi
         if kind in (K.KIND_K5S1, K.KIND_K5S1_DGRAD):
             kdim = n_chunks * 8 * 25
@@ -856,6 +863,10 @@ class Engine:
         else:
             kdim = 64 * (3 if py == 0 else 2) * (5 if px == 2 else (3 if px == 0 else 2))   # px = 2: both x-phases
         fl = 2.0 * B * x.H * x.W * n_out * kdim
+        if wpk2 is not None:
+            self._call("cnp_conv_tc2_w2", C.byref(x), n_chunks, _ptr(wpk), _ptr(wpk2), w2_from_b, kind, py, px, n_out,
+                       C.byref(out), B, _stream(), work=(fl, 0.0))
+            return
         self._call("cnp_conv_tc2", C.byref(x), n_chunks, _ptr(wpk), kind, py, px, n_out, C.byref(out), B, _stream(),
                    work=(fl, 0.0))
 
@@ -876,12 +887,38 @@ class Engine:
     # ---- polyphase resize-convolution (up_poly.cu) -------------------------------------------
     @staticmethod
     def _up_poly_ok(x: "_Blk") -> bool:
-        """128-channel decoder levels of at least 8 x 8 low-res pixels; CNP_NO_POLYPHASE=1 keeps Upsample + Conv."""
-        return x.CB == 16 and x.H >= 8 and x.W >= 8 and not os.environ.get("CNP_NO_POLYPHASE")
+        """128-channel decoder levels; CNP_NO_POLYPHASE=1 keeps Upsample + Conv.  The band costs ~0.4 ms of small launches
+        per level whatever its size (a strip tile streams the whole packed weight tensor), the interior saves 36 % of a
+        cost that grows with the pixel count: measured break-even near 110 x 110 low-res pixels at B = 16
+        (152 -> 304: 0.25 ms saved, 76 -> 152: 0.3 ms lost).  CNP_POLYPHASE_MIN_PIXELS overrides the threshold (tests)."""
+        if os.environ.get("CNP_NO_POLYPHASE") or x.CB != 16 or x.H < 8 or x.W < 8:
+            return False
+        return x.B * x.H * x.W >= int(os.environ.get("CNP_POLYPHASE_MIN_PIXELS", 16 * 110 * 110))
 
     def _up_strip_blks(self, key: str, B: int, CB: int, H: int, W: int):
-        """Row / column strip tensors of a level whose LOW-res size is H x W (up_poly.cu layout)."""
-        return self._blk(f"{key}.rows", 2 * B, CB, 6, 2 * W), self._blk(f"{key}.cols", 2 * B, CB, 6, 2 * H)
+        """Row / column strip tensors of a level whose LOW-res size is H x W (up_poly.cu layout) as a pair of
+        (buffer, first image).  A square level keeps both in ONE tensor of 4B images -- rows first -- so that a single
+        launch with two weight tensors (cnp_conv_tc2_w2) serves them."""
+        if H == W:
+            t = self._blk(f"{key}.rc", 4 * B, CB, 6, 2 * W)
+            return (t, 0), (t, 2 * B)
+        return (self._blk(f"{key}.rows", 2 * B, CB, 6, 2 * W), 0), (self._blk(f"{key}.cols", 2 * B, CB, 6, 2 * H), 0)
+
+    def _strip_conv(self, src, dst, n_chunks, w, key, kind, n_out, B, bias=None, relu=False):
+        """The standard 5x5 kernel (``kind``) on the row strips and, tap-transposed, on the column strips."""
+        (sr, sr0), (sc, sc0) = src
+        (dr, dr0), (dc, dc0) = dst
+        dg = ".dg" if kind == _cabi.KIND_K5S1_DGRAD else ""
+        wr = self._packed_weights(f"{key}{dg}.00" if dg else key, w, kind, n_chunks, 0, 0, 0, n_out)
+        wc = self._packed_weights(f"{key}{dg}.t", w, kind, n_chunks, 0, 0, 0, n_out, pre="tswap")
+        if sr is sc and dr is dc:
+            self._conv_tc(sr.view(0), n_chunks, wr, kind, self._out_blk(dr.view(0), bias=bias, relu=relu), 4 * B,
+                          n_out=n_out, wpk2=wc, w2_from_b=2 * B)
+            return
+        self._conv_tc(sr.view(0, sr0), n_chunks, wr, kind, self._out_blk(dr.view(0, dr0), bias=bias, relu=relu), 2 * B,
+                      n_out=n_out)
+        self._conv_tc(sc.view(0, sc0), n_chunks, wc, kind, self._out_blk(dc.view(0, dc0), bias=bias, relu=relu), 2 * B,
+                      n_out=n_out)
 
     def _up_poly_fwd(self, key: str, x: "_Blk", w: torch.Tensor, bias: torch.Tensor, dst: CnpBlk, B: int) -> dict:
         """dst (8 chunks at 2H x 2W) = relu(conv5x5(bilinear_up2x(x)) + bias) without the upsampled tensor: two phase
@@ -894,15 +931,13 @@ class Engine:
             wpk = self._packed_weights(f"{key}.ph{a}", w, K.KIND_UP_PHASE, ncb, py=a, pre="phase")
             self._conv_tc(x.view(0), ncb, wpk, K.KIND_UP_PHASE,
                           self._out_blk(dst, bias=bias, relu=True, scatter=(2, a, 2, 0)), B, py=a)
-        u_rows, u_cols = self._up_strip_blks(f"{key}.u", B, ncb, H, W)
-        self._call("cnp_up_strips_fwd", C.byref(x.view(0)), ncb, C.byref(u_rows.view()), C.byref(u_cols.view()), B, S)
-        o_rows, o_cols = self._up_strip_blks(f"{key}.o", B, 8, H, W)
-        wpk = self._packed_weights(key, w, K.KIND_K5S1, ncb)
-        self._conv_tc(u_rows.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(o_rows.view(0), bias=bias, relu=True), 2 * B)
-        wpk = self._packed_weights(f"{key}.t", w, K.KIND_K5S1, ncb, pre="tswap")
-        self._conv_tc(u_cols.view(0), ncb, wpk, K.KIND_K5S1, self._out_blk(o_cols.view(0), bias=bias, relu=True), 2 * B)
-        self._call("cnp_up_strips_scatter", C.byref(o_rows.view()), C.byref(o_cols.view()), C.byref(dst), B, S)
-        return {"u_rows": u_rows, "u_cols": u_cols}
+        sv = lambda p: C.byref(p[0].view(0, p[1]))
+        u = self._up_strip_blks(f"{key}.u", B, ncb, H, W)
+        self._call("cnp_up_strips_fwd", C.byref(x.view(0)), ncb, sv(u[0]), sv(u[1]), B, S)
+        o = self._up_strip_blks(f"{key}.o", B, 8, H, W)
+        self._strip_conv(u, o, ncb, w, key, K.KIND_K5S1, 64, B, bias=bias, relu=True)
+        self._call("cnp_up_strips_scatter", sv(o[0]), sv(o[1]), C.byref(dst), B, S)
+        return {"u": u}
 
     def _up_poly_bwd(self, key: str, x: "_Blk", w: torch.Tensor, dy: CnpBlk, dx: "_Blk", saved: dict,
                      gw: torch.Tensor, gb: torch.Tensor, B: int, mask: Optional["_Blk"] = None) -> None:
@@ -912,10 +947,12 @@ class Engine:
         S = _stream()
         ncb, H, W = x.CB, x.H, x.W
         Cin = ncb * 8
+        sv = lambda p: C.byref(p[0].view(0, p[1]))
         s2d = self._blk(f"{key}.dys2d", B, 32, H, W)
-        dy_rows, dy_cols = self._up_strip_blks(f"{key}.dy", B, 8, H, W)
-        self._call("cnp_up_dy_split", C.byref(dy), C.byref(s2d.view()), C.byref(dy_rows.view()), C.byref(dy_cols.view()),
-                   B, S)
+        dys = self._up_strip_blks(f"{key}.dy", B, 8, H, W)
+        # the producer's epilogue may already have written the space-to-depth copy (``saved["s2d_done"]``)
+        self._call("cnp_up_dy_split", C.byref(dy), None if saved.get("s2d_done") else C.byref(s2d.view()), sv(dys[0]),
+                   sv(dys[1]), B, S)
         wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
         ws = self._buf("wgrad_ws", (wsb // 4,))
         # weight gradient: phase gradients at low resolution + the strips' 5x5 gradients, folded into gw
@@ -923,24 +960,21 @@ class Engine:
         dwp.zero_()
         self._call("cnp_conv_tc_wgrad", C.byref(x.view(0)), ncb, C.byref(s2d.view(0)), K.WG_UP_PHASE, _ptr(dwp), _ptr(gb),
                    Cin, B, _ptr(ws), wsb, S, work=(2.0 * B * H * W * 4 * 64 * Cin * 16, 0.0))
-        u_rows, u_cols = saved["u_rows"], saved["u_cols"]
-        self._call("cnp_conv_tc_wgrad", C.byref(u_rows.view(0)), ncb, C.byref(dy_rows.view(0)), K.WG_K5S1, _ptr(gw),
+        u = saved["u"]
+        self._call("cnp_conv_tc_wgrad", sv(u[0]), ncb, sv(dys[0]), K.WG_K5S1, _ptr(gw),
                    _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
         # column strips are transposed images convolved with the tap-transposed weights: the gradient w.r.t. those,
         # stored tap-transposed (WG_K5S1_T), is the gradient w.r.t. w itself
-        self._call("cnp_conv_tc_wgrad", C.byref(u_cols.view(0)), ncb, C.byref(dy_cols.view(0)), K.WG_K5S1_T, _ptr(gw),
+        self._call("cnp_conv_tc_wgrad", sv(u[1]), ncb, sv(dys[1]), K.WG_K5S1_T, _ptr(gw),
                    _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * H * 64 * Cin * 25, 0.0))
         self._call("cnp_up_wgrad_fold", _ptr(dwp), None, 64, Cin, _ptr(gw), S)
         # input gradient: one low-res launch over the four dY phases, then the band through the strips
         wpk = self._packed_weights(f"{key}.dg.ph", w, K.KIND_UP_PHASE_DGRAD, 32, n_out=128, pre="phase")
         mk = mask.view(0) if mask is not None else None
         self._conv_tc(s2d.view(0), 32, wpk, K.KIND_UP_PHASE_DGRAD, self._out_blk(dx.view(0), mask=mk), B, n_out=128)
-        du_rows, du_cols = self._up_strip_blks(f"{key}.du", B, ncb, H, W)
-        wpk = self._packed_weights(f"{key}.dg.00", w, K.KIND_K5S1_DGRAD, 8, 0, 0, 0, 128)
-        self._conv_tc(dy_rows.view(0), 8, wpk, K.KIND_K5S1_DGRAD, self._out_blk(du_rows.view(0)), 2 * B, n_out=128)
-        wpk = self._packed_weights(f"{key}.dg.t", w, K.KIND_K5S1_DGRAD, 8, 0, 0, 0, 128, pre="tswap")
-        self._conv_tc(dy_cols.view(0), 8, wpk, K.KIND_K5S1_DGRAD, self._out_blk(du_cols.view(0)), 2 * B, n_out=128)
-        self._call("cnp_up_strips_bwd_fold", C.byref(du_rows.view()), C.byref(du_cols.view()), C.byref(dx.view()),
+        du = self._up_strip_blks(f"{key}.du", B, ncb, H, W)
+        self._strip_conv(dys, du, 8, w, key, K.KIND_K5S1_DGRAD, 128, B)
+        self._call("cnp_up_strips_bwd_fold", sv(du[0]), sv(du[1]), C.byref(dx.view()),
                    C.byref(mk) if mk is not None else None, ncb, B, S)
 
     def _unet_fwd_bf16(self, enc: Optional[torch.Tensor], B: int, n1: int, n2: int, need_z: bool = True,
@@ -1059,13 +1093,18 @@ class Engine:
                        work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
 
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
-                     accumulate=False, phase=None):
+                     accumulate=False, phase=None, s2d: Optional[_Blk] = None):
             # 128 input channels (the skip concatenations): one WIDE launch; 64: one PAIR launch
             py, px = phase if phase is not None else (0, 0)
             wpk = self._packed_weights(f"{key}.dg.{py}{px}", w, kind, 8, py, px, 0, n_out_ch)
             mk = mask.view(mask_cb) if mask is not None else None
             sc = (2, py, 2, px if px < 2 else 0) if phase is not None else (1, 0, 1, 0)
             o = self._out_blk(dst.view(dst_cb), mask=mk, accumulate=accumulate, scatter=sc)
+            if s2d is not None:
+                # chunks 8..15 of this gradient are dY of the next (polyphase) decoder level: the epilogue also writes
+                # their space-to-depth copy, band left zero (what cnp_up_dy_split would otherwise produce in a pass of its own)
+                o._s2d_view = s2d.view()
+                o.s2d, o.s2d_c0, o.s2d_band = C.pointer(o._s2d_view), 8, 2
             self._conv_tc(dy, 8, wpk, kind, o, B, py, px, n_out_ch)
 
         # final 1x1 (already folded into the decoder when dz is the blocked d_h_last)
@@ -1097,7 +1136,13 @@ class Engine:
                 self._call("cnp_blk_upsample2x_bwd", C.byref(d_up.view()), x_in.CB, C.byref(d_cat[i].view()),
                            C.byref(cat[i].view()), 0, B, S)
             else:
-                dgrad_tc(dy_blk.view(dy_cb), lyr.weight, f"after{i}", K.KIND_K5S1_DGRAD, nch, d_cat[i], 0, cat[i], 0)
+                nxt = A["polys"][i + 1] if i + 1 < L else None
+                s2d = None
+                if nxt is not None and nch == 128 and not os.environ.get("CNP_NO_S2D_EPILOGUE"):
+                    s2d = self._blk(f"after{i + 1}.dys2d", B, 32, cat[i + 1].H, cat[i + 1].W)
+                    nxt["s2d_done"] = True
+                dgrad_tc(dy_blk.view(dy_cb), lyr.weight, f"after{i}", K.KIND_K5S1_DGRAD, nch, d_cat[i], 0, cat[i], 0,
+                         s2d=s2d)
             if i < L - 1:
                 dy_blk, dy_cb = d_cat[i], 8
         if up_done is not None:          # gradients of the head, the final 1x1 and the up path are complete

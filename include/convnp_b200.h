@@ -140,6 +140,8 @@ typedef struct cnp_conv_out {
   const cnp_blk* mask; /* zero the result where mask <= 0 (ReLU backward), or NULL */
   int accumulate;      /* out += result */
   const cnp_blk* s2d;  /* cnp_conv_tc2 only: also write the space-to-depth copy (32 chunks, half size) or NULL */
+  int s2d_c0;          /* first of the 8 output chunks copied there: 0, or 8 with n_out = 128 */
+  int s2d_band;        /* half-res pixels along every edge left unwritten (zero): the band of the polyphase backward */
 } cnp_conv_out;
 
 enum { CNP_K5S1 = 0, CNP_K1 = 1, CNP_K5S2 = 2, CNP_K5S1_DGRAD = 3, CNP_K1_DGRAD = 4, CNP_K5S2_DGRAD = 5,
@@ -177,6 +179,10 @@ int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind, int n_
                       int n_out, void* wpk, cnp_stream_t s);
 int cnp_conv_tc2(const cnp_blk* x, int n_chunks, const void* wpk, int kind, int py, int px, int n_out,
                  const cnp_conv_out* out, int B, cnp_stream_t s);
+/* the same launch with a second packed weight tensor for the images b >= w2_from_b (row strips + tap-transposed column
+ * strips of a square level in one launch) */
+int cnp_conv_tc2_w2(const cnp_blk* x, int n_chunks, const void* wpk, const void* wpk2, int w2_from_b, int kind, int py,
+                    int px, int n_out, const cnp_conv_out* out, int B, cnp_stream_t s);
 /* workspace (optional, cnp_conv_tc_wgrad_workspace_bytes()): the K-split partial sums are written there and folded
  * by a second kernel; without it they are reduced with fp32 atomics straight into dw. */
 long long cnp_conv_tc_wgrad_workspace_bytes(void);
@@ -210,7 +216,8 @@ int cnp_up_phase_weights(const float* w5, int Cout, int Cin, float* wp, cnp_stre
  * rows: L = 2W high-res columns; cols: L = 2H, strip row = high-res column (transposed).
  *   cnp_up_strips_fwd     : strips of bilinear_up2x(x)
  *   cnp_up_strips_scatter : band outputs of the strip convolutions -> the high-res destination (8 chunks)
- *   cnp_up_dy_split       : dY -> space-to-depth copy with the band zeroed (32 chunks, low res) + band strips
+ *   cnp_up_dy_split       : dY -> space-to-depth copy with the band zeroed (32 chunks, low res; NULL when the producer's
+ *                           epilogue wrote it: cnp_conv_out.s2d / s2d_c0 / s2d_band) + band strips
  *   cnp_up_strips_bwd_fold: dx += mask(act > 0) * up2x^T(strip gradients w.r.t. the upsampled tensor)
  *   cnp_up_wgrad_fold     : dw5 += fold^T(phase gradients) + tap-transposed column-strip gradient */
 int cnp_up_strips_fwd(const cnp_blk* x, int n_chunks, const cnp_blk* rows, const cnp_blk* cols, int B, cnp_stream_t s);

@@ -225,6 +225,7 @@ def test_model_with_and_without_polyphase(monkeypatch):
     static = make_static(seed=7, n_hi=120)
     task = concat_tasks([make_task(static, 700 + i) for i in range(2)])
     out = {}
+    monkeypatch.setenv("CNP_POLYPHASE_MIN_PIXELS", "0")        # small grids: below the engine's break-even threshold
     for mode in ("poly", "std"):
         if mode == "std":
             monkeypatch.setenv("CNP_NO_POLYPHASE", "1")
@@ -242,5 +243,65 @@ def test_model_with_and_without_polyphase(monkeypatch):
     for n in g0:
         a, b = g1[n].double().flatten(), g0[n].double().flatten()
         cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-300))
-        assert cos > 0.999, (n, cos)
-        assert rel_err(g1[n], g0[n]) < 5e-2, n
+        assert cos > 0.9999, (n, cos)
+        assert rel_err(g1[n], g0[n]) < 3e-2, n
+
+
+def test_wide_dgrad_epilogue_writes_the_band_zeroed_space_to_depth_copy():
+    """The 128-channel input gradient (WIDE) whose chunks 8..15 are dY of the next polyphase level can write their
+    space-to-depth copy itself (cnp_conv_out.s2d / s2d_c0 = 8 / s2d_band = 2): same bytes as cnp_up_dy_split."""
+    torch.manual_seed(8)
+    B, h, w = 2, 24, 40                       # high-res size of the gradient; the next level is 12 x 20
+    dy = torch.randn(B, 64, h, w, device="cuda").bfloat16().float()
+    wt = (torch.randn(64, 128, 5, 5, device="cuda") * 0.05)
+    act = torch.randn(B, 128, h, w, device="cuda").bfloat16().float()
+    dyb, actb = _to_blk(dy), _to_blk(act)
+    dst = _Blk(B, 16, h, w, dy.device)
+    s2d = _Blk(B, 32, h // 2, w // 2, dy.device)
+    o = _out(dst.view(0), mask=actb.view(0))
+    sview = s2d.view()
+    o.s2d, o.s2d_c0, o.s2d_band = C.pointer(sview), 8, 2
+    _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S1_DGRAD, 8, n_out=128).data_ptr(),
+               _cabi.KIND_K5S1_DGRAD, 0, 0, 128, C.byref(o), B, _S())
+    want = _Blk(B, 32, h // 2, w // 2, dy.device)
+    rows, cols = _Blk(2 * B, 8, 6, w, dy.device), _Blk(2 * B, 8, 6, h, dy.device)
+    _cabi.call("cnp_up_dy_split", C.byref(dst.view(8)), C.byref(want.view()), C.byref(rows.view()), C.byref(cols.view()),
+               B, _S())
+    assert torch.equal(s2d.t, want.t)
+    assert float(_from_blk(s2d, 256).abs().max()) > 0
+    # the plain output is what it was without the second output
+    dst2 = _Blk(B, 16, h, w, dy.device)
+    o2 = _out(dst2.view(0), mask=actb.view(0))
+    _cabi.call("cnp_conv_tc2", C.byref(dyb.view()), 8, _pack(wt, _cabi.KIND_K5S1_DGRAD, 8, n_out=128).data_ptr(),
+               _cabi.KIND_K5S1_DGRAD, 0, 0, 128, C.byref(o2), B, _S())
+    assert torch.equal(dst.t, dst2.t)
+    # strips only (s2d = NULL): the same strips
+    rows2, cols2 = _Blk(2 * B, 8, 6, w, dy.device), _Blk(2 * B, 8, 6, h, dy.device)
+    _cabi.call("cnp_up_dy_split", C.byref(dst.view(8)), None, C.byref(rows2.view()), C.byref(cols2.view()), B, _S())
+    assert torch.equal(rows.t, rows2.t) and torch.equal(cols.t, cols2.t)
+
+
+@pytest.mark.parametrize("kind,n_out,cin", [("fwd", 64, 128), ("dgrad", 128, 64)])
+def test_conv_with_two_weight_tensors_equals_two_launches(kind, n_out, cin):
+    """cnp_conv_tc2_w2: images b >= w2_from_b use the second packed tensor (row strips + tap-transposed column strips of a
+    square level in one launch) -- bit-identical to two launches."""
+    torch.manual_seed(9)
+    B, h, w = 8, 6, 88
+    x = torch.randn(B, cin, h, w, device="cuda").bfloat16().float()
+    wt = torch.randn(64, 128, 5, 5, device="cuda") * 0.05
+    wtt = wt.transpose(2, 3).contiguous()
+    K = _cabi.KIND_K5S1 if kind == "fwd" else _cabi.KIND_K5S1_DGRAD
+    w1, w2 = _pack(wt, K, cin // 8, n_out=n_out), _pack(wtt, K, cin // 8, n_out=n_out)
+    xb = _to_blk(x)
+    one = _Blk(B, n_out // 8, h, w, x.device)
+    _cabi.call("cnp_conv_tc2_w2", C.byref(xb.view()), cin // 8, w1.data_ptr(), w2.data_ptr(), B // 2, K, 0, 0, n_out,
+               C.byref(_out(one.view())), B, _S())
+    two = _Blk(B, n_out // 8, h, w, x.device)
+    _cabi.call("cnp_conv_tc2", C.byref(xb.view(0, 0)), cin // 8, w1.data_ptr(), K, 0, 0, n_out, C.byref(_out(two.view(0, 0))),
+               B // 2, _S())
+    _cabi.call("cnp_conv_tc2", C.byref(xb.view(0, B // 2)), cin // 8, w2.data_ptr(), K, 0, 0, n_out,
+               C.byref(_out(two.view(0, B // 2))), B // 2, _S())
+    assert torch.equal(one.t, two.t)
+    ref = F.conv2d(x[B // 2:].double(), wtt.bfloat16().double(), padding=2) if kind == "fwd" else \
+        F.conv_transpose2d(x[B // 2:].double(), wtt.bfloat16().double(), padding=2)
+    assert rel_err(_from_blk(one, n_out)[B // 2:], ref) < 1e-2
