@@ -161,58 +161,99 @@ __device__ __forceinline__ float up_wgt_t(int Y, int r, int n) {
 
 // input gradient of the band: the strips' gradients w.r.t. the upsampled tensor, gathered through the transposed
 // bilinear map onto the low-res pixels within 4 of the border, ReLU-masked by act > 0 and ADDED to dx.
-__global__ void __launch_bounds__(256)
+// The map is separable, so a thread owns a LINE of four outputs across the band and sweeps its strip once:
+//   part A (row bands): thread = (edge s, column c): horizontal combination of the 4 strip pixels around c for each of the
+//           6 strip rows, then the vertical weights of its 4 output rows; the threads of the 4 outermost columns also
+//           gather what the column strips contribute to the corner squares;
+//   part B (column bands, rows 4 .. H-5): thread = (edge s, row r), the same on the transposed strips.
+// 24 strip loads per 4 outputs (the first version gathered 16..32 per output: 55 us at 152 x 152, B = 16).
+// Needs H, W >= 12 (the two strips of a dimension must not overlap).
+__device__ __forceinline__ void fold_store(const blkv& dx, const blkv& act, int b, int chunk, int r, int c, const float* acc) {
+  float old[8], av[8], v[8];
+  __nv_bfloat16* d = dx.at(b, chunk, r, c);
+  unpk(*reinterpret_cast<const uint4*>(d), old);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = acc[k];
+  if (act.p) {
+    unpk(ldg16(act.at(b, chunk, r, c)), av);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = av[k] > 0.f ? v[k] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) old[k] += v[k];
+  *reinterpret_cast<uint4*>(d) = pk(old);
+}
+
+__global__ void __launch_bounds__(128)
 up_strips_bwd_fold_kernel(blkv rows, blkv cols, blkv dx, blkv act, int H, int W, int CB, int B) {
   const int H2 = 2 * H, W2 = 2 * W;
-  const int nr = 8 * W, nc = 8 * (H - 8);
-  const long long total = (long long)B * CB * (nr + nc);
-  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    int i = (int)(e % (nr + nc));
-    const int chunk = (int)((e / (nr + nc)) % CB), b = (int)(e / (nr + nc) / CB);
-    int r, c;
-    if (i < nr) { c = i % W; const int k = i / W; r = k < 4 ? k : H - 8 + k; }
-    else { i -= nr; r = 4 + i % (H - 8); const int k = i / (H - 8); c = k < 4 ? k : W - 8 + k; }
-    float acc[8];
+  const int nA = 2 * W, nB = 2 * (H - 8);
+  const long long total = (long long)B * CB * (nA + nB);
+  for (long long e = (long long)blockIdx.x * 128 + threadIdx.x; e < total; e += (long long)gridDim.x * 128) {
+    const int i = (int)(e % (nA + nB));
+    const int chunk = (int)((e / (nA + nB)) % CB), b = (int)(e / (nA + nB) / CB);
+    const bool partA = i < nA;
+    // line coordinate u along the edge, n = its extent; the 4 outputs lie across the band at v0 .. v0+3 (extent m)
+    const int s = partA ? i / W : (i - nA) / (H - 8);
+    const int u = partA ? i % W : 4 + (i - nA) % (H - 8);
+    const int n = partA ? W : H, m = partA ? H : W;
+    const blkv& strip = partA ? rows : cols;
+    const int v0 = s ? m - 4 : 0;                 // first output across the band
+    const int t0 = s ? 2 * m - UP_SR : 0;         // high-res index of strip row 0
+    float acc[4][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int Y = max(2 * r - 1, 0); Y <= min(2 * r + 2, H2 - 1); ++Y) {
-      const float wy = up_wgt_t(Y, r, H);
-      for (int X = max(2 * c - 1, 0); X <= min(2 * c + 2, W2 - 1); ++X) {
-        const float wgt = wy * up_wgt_t(X, c, W);
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = 0.f;
+    const int x_lo = max(2 * u - 1, 0), x_hi = min(2 * u + 2, 2 * n - 1);
+#pragma unroll
+    for (int t = 0; t < UP_SR; ++t) {
+      float h[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) h[c8] = 0.f;
+      for (int X = x_lo; X <= x_hi; ++X) {
+        const float wgt = up_wgt_t(X, u, n);
         float v[8];
-        if (Y < UP_SR) {
-          unpk(ldg16(rows.at(b, chunk, Y, X)), v);
+        unpk(ldg16(strip.at(s * B + b, chunk, t, X)), v);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
-        }
-        if (Y >= H2 - UP_SR) {
-          unpk(ldg16(rows.at(B + b, chunk, Y - (H2 - UP_SR), X)), v);
+        for (int c8 = 0; c8 < 8; ++c8) h[c8] = fmaf(wgt, v[c8], h[c8]);
+      }
+      const int Y = t0 + t;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
-        }
-        if (X < UP_SR) {
-          unpk(ldg16(cols.at(b, chunk, X, Y)), v);
+      for (int k = 0; k < 4; ++k) {
+        const int d = Y - 2 * (v0 + k);
+        if (d >= -1 && d <= 2) {
+          const float wy = up_wgt_t(Y, v0 + k, m);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
-        }
-        if (X >= W2 - UP_SR) {
-          unpk(ldg16(cols.at(B + b, chunk, X - (W2 - UP_SR), Y)), v);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+          for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = fmaf(wy, h[c8], acc[k][c8]);
         }
       }
     }
-    float old[8], av[8];
-    __nv_bfloat16* d = dx.at(b, chunk, r, c);
-    unpk(*reinterpret_cast<const uint4*>(d), old);
-    if (act.p) {
-      unpk(ldg16(act.at(b, chunk, r, c)), av);
+    if (partA && (u < 4 || u >= W - 4)) {
+      // corner squares: the column strip of this side reaches rows 2 .. 2H-3 of the upsampled tensor
+      const int sc = u < 4 ? 0 : 1;
+      const int X0 = sc ? W2 - UP_SR : 0;
+      for (int tx = 0; tx < UP_SR; ++tx) {
+        const int X = X0 + tx, dxx = X - 2 * u;
+        if (dxx < -1 || dxx > 2) continue;
+        const float wx = up_wgt_t(X, u, W);
+        for (int k = 0; k < 4; ++k) {
+          const int r = v0 + k;
+          for (int Y = max(2 * r - 1, 0); Y <= min(2 * r + 2, H2 - 1); ++Y) {
+            const float wgt = wx * up_wgt_t(Y, r, H);
+            float v[8];
+            unpk(ldg16(cols.at(sc * B + b, chunk, tx, Y)), v);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = av[k] > 0.f ? acc[k] : 0.f;
+            for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = fmaf(wgt, v[c8], acc[k][c8]);
+          }
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) old[k] += acc[k];
-    *reinterpret_cast<uint4*>(d) = pk(old);
+    for (int k = 0; k < 4; ++k) {
+      if (partA) fold_store(dx, act, b, chunk, v0 + k, u, acc[k]);
+      else fold_store(dx, act, b, chunk, u, v0 + k, acc[k]);
+    }
   }
 }
 
@@ -315,13 +356,13 @@ CNP_API int cnp_up_dy_split(const cnp_blk* dy, const cnp_blk* s2d, const cnp_blk
 // dx (n_chunks chunks, H x W) += mask(act > 0) * bilinear_up2x^T(strip gradients); act may be NULL.
 CNP_API int cnp_up_strips_bwd_fold(const cnp_blk* rows, const cnp_blk* cols, const cnp_blk* dx, const cnp_blk* act,
                                    int n_chunks, int B, cudaStream_t st) {
-  CNP_REQUIRE(dx && n_chunks > 0 && B > 0 && dx->H >= 8 && dx->W >= 8 && strips_ok(rows, cols, dx->H, dx->W) &&
-              (!act || (act->H == dx->H && act->W == dx->W)), "up_strips_bwd_fold: geometry mismatch");
+  CNP_REQUIRE(dx && n_chunks > 0 && B > 0 && dx->H >= 12 && dx->W >= 12 && strips_ok(rows, cols, dx->H, dx->W) &&
+              (!act || (act->H == dx->H && act->W == dx->W)), "up_strips_bwd_fold: needs at least 12 x 12 low-res pixels");
   blkv a;
   a.p = nullptr; a.bs = 0; a.Hp = a.Wp = 0;
   if (act) a = view_of(act);
-  const long long total = (long long)B * n_chunks * (8 * dx->W + 8 * (dx->H - 8));
-  up_strips_bwd_fold_kernel<<<grid_for(total), 256, 0, st>>>(view_of(rows), view_of(cols), view_of(dx), a, dx->H, dx->W,
+  const long long total = (long long)B * n_chunks * (2 * dx->W + 2 * (dx->H - 8));
+  up_strips_bwd_fold_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(view_of(rows), view_of(cols), view_of(dx), a, dx->H, dx->W,
                                                            n_chunks, B);
   CNP_LAUNCH_CHECK("up_strips_bwd_fold_kernel");
   return 0;

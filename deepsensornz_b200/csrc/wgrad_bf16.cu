@@ -28,7 +28,7 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 
-#define CNP_WG_MAX_PASS 8
+#define CNP_WG_MAX_PASS 10
 #define CNP_WG_MAX_ACC 5
 
 
@@ -42,12 +42,14 @@ struct cnp_wg_pass {
   int ci0, ci1;                // input-channel base of the two row halves
   int ky0, n_grp;              // narrow inputs: the pass covers kernel rows ky0 .. ky0 + n_grp - 1 (one row group each)
   int dy_chunk0;               // first dY chunk of this pass (phase kind: 16 * row phase)
+  int img0, n_img;             // images this pass reduces over (n_img = 0: all B)
 };
 
 struct cnp_wg_args {
   const __nv_bfloat16* x; long long x_bs; long long x_plane;   // elements
   const __nv_bfloat16* dy; long long dy_bs; long long dy_plane;
   float* dw; float* dbias; int Cin, KK;
+  float* dw2; int dw2_from_pass; // passes >= dw2_from_pass accumulate into dw2 instead of dw (row / column strips in one launch)
   float* ws;                     // optional partial-sum workspace [pass][ksplit][acc][128][64]; NULL = atomics into dw
   float* ws_bias;                // with ws: per-CTA bias partials [pass][ksplit][64]
   int B, P, p_start, tiles_per_img, ksplit, n_pass;
@@ -119,7 +121,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const cnp_wg_pass& ps = a.pass[blockIdx.y];
-  const int total_tiles = a.B * a.tiles_per_img;
+  const int total_tiles = (ps.n_img ? ps.n_img : a.B) * a.tiles_per_img;
 
   if (threadIdx.x == 0) {
     const bool bias_cta0 = (a.dbias != nullptr);
@@ -157,7 +159,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
         const int s = it % WG_STAGES;
         tc::mbar_wait(empty + s, ((it / WG_STAGES) & 1) ^ 1);
-        const int b = t / a.tiles_per_img, ti = t % a.tiles_per_img;
+        const int b = ps.img0 + t / a.tiles_per_img, ti = t % a.tiles_per_img;
         const long long p0 = a.p_start + (long long)ti * P;
         uint8_t* xs = smem + s * stage_b;
         tc::mbar_expect_tx(full + s, tx);       // the whole stage (X planes from here, dY planes from warp 6)
@@ -180,7 +182,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
       for (int t = blockIdx.x; t < total_tiles; t += a.ksplit, ++it) {
         const int s = it % WG_STAGES;
         tc::mbar_wait(empty + s, ((it / WG_STAGES) & 1) ^ 1);
-        const int b = t / a.tiles_per_img, ti = t % a.tiles_per_img;
+        const int b = ps.img0 + t / a.tiles_per_img, ti = t % a.tiles_per_img;
         const long long p0 = a.p_start + (long long)ti * P;
         uint8_t* ds = smem + s * stage_b + x_tile_b;
         const __nv_bfloat16* db = a.dy + (long long)b * a.dy_bs + p0 * 8;
@@ -321,7 +323,7 @@ wgrad_tc_kernel(const __grid_constant__ cnp_wg_args a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int co = (hc & 1) * 32 + i;
-              atomicAdd(a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot, v[i]);
+              atomicAdd(((a.dw2 && (int)blockIdx.y >= a.dw2_from_pass) ? a.dw2 : a.dw) + ((size_t)co * a.Cin + ci) * a.KK + slot, v[i]);
             }
           }
         }
@@ -382,7 +384,7 @@ wgrad_reduce_kernel(const __grid_constant__ cnp_wg_args a) {
 #pragma unroll
     for (int s = 1; s < WG_RED_KS; ++s) { const float4 v = part[s][q]; sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; }
     const int co = col & 63;
-    float* dst = a.dw + ((size_t)co * a.Cin + ci) * a.KK + slot;
+    float* dst = ((a.dw2 && pass >= a.dw2_from_pass) ? a.dw2 : a.dw) + ((size_t)co * a.Cin + ci) * a.KK + slot;
     const size_t cs = (size_t)a.Cin * a.KK;
     dst[0] += sum.x; dst[cs] += sum.y; dst[2 * cs] += sum.z; dst[3 * cs] += sum.w;
   }
@@ -435,8 +437,26 @@ CNP_API long long cnp_conv_tc_wgrad_workspace_bytes(void) {
   return (long long)148 * 5 * 128 * 128 * sizeof(float) + (long long)148 * 64 * sizeof(float);
 }
 
+static int wgrad_launch(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dw2, int b_split,
+                        float* dbias, int Cin, int B, void* workspace, long long workspace_bytes, cudaStream_t st);
+
 CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dbias,
                               int Cin, int B, void* workspace, long long workspace_bytes, cudaStream_t st) {
+  return wgrad_launch(x, n_chunks, dy, kind, dw, nullptr, 0, dbias, Cin, B, workspace, workspace_bytes, st);
+}
+
+// 5x5 stride-1 weight gradient of TWO image groups in one launch: images [0, b_split) accumulate into dw, images
+// [b_split, B) into dw2 (both torch layout, +=).  The polyphase level's row strips and (transposed) column strips are
+// such a pair (up_poly.cu); cnp_up_wgrad_fold adds dw2 tap-transposed.
+CNP_API int cnp_conv_tc_wgrad_pair(const cnp_blk* x, int n_chunks, const cnp_blk* dy, float* dw, float* dw2, int b_split,
+                                   float* dbias, int Cin, int B, void* workspace, long long workspace_bytes,
+                                   cudaStream_t st) {
+  CNP_REQUIRE(dw2 && b_split > 0 && b_split < B, "conv_tc_wgrad_pair: needs a second gradient and 0 < b_split < B");
+  return wgrad_launch(x, n_chunks, dy, 0 /* WG_K5S1 */, dw, dw2, b_split, dbias, Cin, B, workspace, workspace_bytes, st);
+}
+
+static int wgrad_launch(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw, float* dw2, int b_split,
+                        float* dbias, int Cin, int B, void* workspace, long long workspace_bytes, cudaStream_t st) {
   CNP_REQUIRE(x && dy && dw && B > 0, "conv_tc_wgrad: bad arguments");
   CNP_REQUIRE(x->H == dy->H && x->W == dy->W, "conv_tc_wgrad: x and dy must share the accumulator geometry");
   cnp_wg_args a;
@@ -562,6 +582,17 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
     CNP_REQUIRE(false, "conv_tc_wgrad: unknown kind %d", kind);
   }
   a.bias_grp = kind == WG_UP_PHASE ? 4 : np;
+  if (dw2) {
+    // second image group: the same passes again, over images [b_split, B), into dw2
+    CNP_REQUIRE(kind == WG_K5S1 && 2 * np <= CNP_WG_MAX_PASS, "conv_tc_wgrad_pair: 5x5 stride-1 only");
+    for (int i = 0; i < np; ++i) {
+      a.pass[np + i] = a.pass[i];
+      a.pass[i].img0 = 0; a.pass[i].n_img = b_split;
+      a.pass[np + i].img0 = b_split; a.pass[np + i].n_img = B - b_split;
+    }
+    a.dw2 = dw2; a.dw2_from_pass = np;
+    np *= 2;
+  }
   if (a.dup) {
     // the shifted dY copy sums dY[p-1]: run one pixel further so that it still covers the last interior pixel
     a.tiles_per_img = cnp_cdiv(p_end - a.p_start + 1, a.P);
@@ -571,7 +602,7 @@ CNP_API int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy,
   a.n_pass = np;
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int total_tiles = B * a.tiles_per_img;
+  const int total_tiles = (dw2 ? (b_split < B - b_split ? b_split : B - b_split) : B) * a.tiles_per_img;
   a.ksplit = sms / np;
   if (a.ksplit > total_tiles) a.ksplit = total_tiles;
   if (a.ksplit < 1) a.ksplit = 1;

@@ -67,8 +67,14 @@ def _unet_z(m, batch):
 
 
 @pytest.mark.parametrize("name", ["s1_single", "s2_batch4", "s4_multivar8"])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_training_shapes_match_golden(mg, name, precision):
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16+polyphase"])
+def test_training_shapes_match_golden(mg, name, precision, monkeypatch):
+    """"bf16+polyphase": the polyphase resize-convolution forced on for every 128-channel decoder level (the engine only
+    uses it from B x 110 x 110 low-res pixels on, i.e. at the bench batch of 16; these cases have B = 1 and 4)."""
+    case = precision
+    if precision.endswith("+polyphase"):
+        monkeypatch.setenv("CNP_POLYPHASE_MIN_PIXELS", "0")
+        precision = "bf16"
     gold = np.load(os.path.join(GDIR, name + ".npz"))
     # the golden weights make the UNet matter: zeroing one up-path layer moves the oracle's loss by far more than 1 %
     assert abs(float(gold["loss_after0_zeroed"]) - float(gold["loss"])) > 0.01 * abs(float(gold["loss"]))
@@ -79,7 +85,7 @@ def test_training_shapes_match_golden(mg, name, precision):
     batch = m._to_device(task)
     g = batch.grid
     assert [g.start1, g.n1, g.start2, g.n2, g.res] == list(gold["grid"]) and (g.n1, g.n2) == (304, 304)
-    rec = dict(case=name, precision=precision)
+    rec = dict(case=name, precision=case)
     # encoder (fp32 in both modes) and the UNet output z, an intermediate the loss alone would not pin
     enc, z = _unet_z(m, batch)
     rec["enc_sum"] = rel_err(enc.double().sum(dim=(0, 2, 3)), gold["enc_sum"])
@@ -128,9 +134,13 @@ def test_training_shapes_match_golden(mg, name, precision):
         assert worst["norm"] < 5e-2 and worst["probe"] < 0.15 and worst["full"] < 5e-2, (rec, detail)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_highres_inference_matches_golden(mg, precision):
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16+polyphase"])
+def test_highres_inference_matches_golden(mg, precision, monkeypatch):
     """S3: one task decoded onto the 1400 x 1400 on-grid targets (validate_ERA.py:88-92 shape)."""
+    case = precision
+    if precision.endswith("+polyphase"):
+        monkeypatch.setenv("CNP_POLYPHASE_MIN_PIXELS", "0")
+        precision = "bf16"
     gold = np.load(os.path.join(GDIR, "s3_grid1400.npz"))
     tol = FP32_TOL if precision == "fp32" else BF16_TOL
     m = mg.build_model("s3_grid1400", precision)
@@ -143,7 +153,7 @@ def test_highres_inference_matches_golden(mg, precision):
     assert tuple(mean.shape) == (1400, 1400)
     s = mg.GRID_SAMPLE
     scale_m, scale_s = float(gold["mean_absmax"]), float(gold["std_max"])
-    rec = dict(case="s3_grid1400", precision=precision,
+    rec = dict(case="s3_grid1400", precision=case,
                mean=float((mean[::s, ::s].cpu() - torch.from_numpy(gold["mean_sample"])).abs().max()) / scale_m,
                std=float((std[::s, ::s].cpu() - torch.from_numpy(gold["std_sample"])).abs().max()) / scale_s,
                mean_rows=rel_err(mean.double().sum(dim=1), gold["mean_rowsum"]),

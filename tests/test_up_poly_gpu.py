@@ -217,34 +217,37 @@ def test_up_poly_layer_forward_backward(h, w):
 
 
 def test_model_with_and_without_polyphase(monkeypatch):
-    """Same model, same batch: the engine with the polyphase levels (default) against CNP_NO_POLYPHASE=1 (Upsample + Conv
-    kernels) -- predictions, loss and every gradient agree to bf16 rounding, and both sit within the bf16 tolerance of
-    the oracle (tests/test_gpu_parity.py checks the default path against the oracle on its own)."""
+    """Same model, same batch: the engine with the polyphase levels against CNP_NO_POLYPHASE=1 (Upsample + Conv kernels),
+    both in bf16, judged against the engine's fp32 mode (itself 1e-5 from the oracle, tests/test_gpu_parity.py): the
+    predictions and the loss agree to bf16 rounding, and every gradient of the polyphase path is as close to the fp32
+    gradient as the standard bf16 path is (a band, transposition or fold error shows up as a multiple of that noise)."""
     from deepsensornz_b200 import concat_tasks
     from deepsensornz_b200.synthetic import make_static, make_task
     static = make_static(seed=7, n_hi=120)
     task = concat_tasks([make_task(static, 700 + i) for i in range(2)])
     out = {}
     monkeypatch.setenv("CNP_POLYPHASE_MIN_PIXELS", "0")        # small grids: below the engine's break-even threshold
-    for mode in ("poly", "std"):
+    for mode in ("poly", "std", "fp32"):
         if mode == "std":
             monkeypatch.setenv("CNP_NO_POLYPHASE", "1")
         else:
             monkeypatch.delenv("CNP_NO_POLYPHASE", raising=False)
-        m = small_model("bf16", ppu=100)
+        m = small_model("fp32" if mode == "fp32" else "bf16", ppu=100)
         pred = m(task)
         loss = m.loss_fn(task, normalise=True)
         loss.backward()
-        out[mode] = (torch.as_tensor(pred["mean"]).clone(), torch.as_tensor(pred["std"]).clone(), float(loss),
+        out[mode] = (torch.as_tensor(pred["mean"]).clone(), torch.as_tensor(pred["std"]).clone(), float(loss.detach()),
                      {n: p.grad.detach().clone() for n, p in m.model.named_parameters() if p.grad is not None})
-    (m1, s1, l1, g1), (m0, s0, l0, g0) = out["poly"], out["std"]
+    (m1, s1, l1, g1), (m0, s0, l0, g0), (_, _, lr, gr) = out["poly"], out["std"], out["fp32"]
     assert rel_err(m1, m0) < 1e-2 and rel_err(s1, s0) < 1e-2
-    assert abs(l1 - l0) / abs(l0) < 5e-3
-    for n in g0:
-        a, b = g1[n].double().flatten(), g0[n].double().flatten()
-        cos = float((a @ b) / (a.norm() * b.norm()).clamp(min=1e-300))
-        assert cos > 0.9999, (n, cos)
-        assert rel_err(g1[n], g0[n]) < 3e-2, n
+    assert abs(l1 - l0) / abs(l0) < 5e-3 and abs(l1 - lr) / abs(lr) < 5e-3
+
+    def dist(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-300))
+
+    for n in gr:
+        e1, e0 = dist(g1[n], gr[n]), dist(g0[n], gr[n])
+        assert e1 < 1.5 * e0 + 2e-3, (n, e1, e0)
 
 
 def test_wide_dgrad_epilogue_writes_the_band_zeroed_space_to_depth_copy():
