@@ -153,6 +153,8 @@ _SIGS = {
     "cnp_blk_space_to_depth": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_stream]),
     "cnp_conv_tc_wgrad_workspace_bytes": (_ll, []),
     "cnp_conv_tc_wgrad": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), _i, c_fp, c_fp, _i, _i, c_fp, _ll, c_stream]),
+    "cnp_conv_tc_wgrad_pair": (C.c_int, [C.POINTER(CnpBlk), _i, C.POINTER(CnpBlk), c_fp, c_fp, _i, c_fp, _i, _i, c_fp, _ll,
+                                         c_stream]),
     "cnp_conv1x1_in_wgrad": (C.c_int, [c_fp, _ll, _i, C.POINTER(CnpBlk), _i, c_fp, c_fp, c_stream]),
     "cnp_blk_channel_sum": (C.c_int, [C.POINTER(CnpBlk), _i, _i, c_fp, c_stream]),
 }

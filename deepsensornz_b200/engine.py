@@ -891,7 +891,7 @@ class Engine:
         per level whatever its size (a strip tile streams the whole packed weight tensor), the interior saves 36 % of a
         cost that grows with the pixel count: measured break-even near 110 x 110 low-res pixels at B = 16
         (152 -> 304: 0.25 ms saved, 76 -> 152: 0.3 ms lost).  CNP_POLYPHASE_MIN_PIXELS overrides the threshold (tests)."""
-        if os.environ.get("CNP_NO_POLYPHASE") or x.CB != 16 or x.H < 8 or x.W < 8:
+        if os.environ.get("CNP_NO_POLYPHASE") or x.CB != 16 or x.H < 12 or x.W < 12:
             return False
         return x.B * x.H * x.W >= int(os.environ.get("CNP_POLYPHASE_MIN_PIXELS", 16 * 110 * 110))
 
@@ -961,13 +961,22 @@ class Engine:
         self._call("cnp_conv_tc_wgrad", C.byref(x.view(0)), ncb, C.byref(s2d.view(0)), K.WG_UP_PHASE, _ptr(dwp), _ptr(gb),
                    Cin, B, _ptr(ws), wsb, S, work=(2.0 * B * H * W * 4 * 64 * Cin * 16, 0.0))
         u = saved["u"]
-        self._call("cnp_conv_tc_wgrad", sv(u[0]), ncb, sv(dys[0]), K.WG_K5S1, _ptr(gw),
-                   _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
-        # column strips are transposed images convolved with the tap-transposed weights: the gradient w.r.t. those,
-        # stored tap-transposed (WG_K5S1_T), is the gradient w.r.t. w itself
-        self._call("cnp_conv_tc_wgrad", sv(u[1]), ncb, sv(dys[1]), K.WG_K5S1_T, _ptr(gw),
-                   _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * H * 64 * Cin * 25, 0.0))
-        self._call("cnp_up_wgrad_fold", _ptr(dwp), None, 64, Cin, _ptr(gw), S)
+        # column strips are transposed images convolved with the tap-transposed weights: their gradient, transposed
+        # back, is the gradient w.r.t. w itself
+        if u[0][0] is u[1][0]:
+            # square level: both strip groups in one launch (rows -> gw, columns -> dwt), the fold transposes dwt
+            dwt = self._buf(f"{key}.dwt", (64, Cin, 5, 5))
+            dwt.zero_()
+            self._call("cnp_conv_tc_wgrad_pair", C.byref(u[0][0].view(0)), ncb, C.byref(dys[0][0].view(0)), _ptr(gw),
+                       _ptr(dwt), 2 * B, _ptr(gb), Cin, 4 * B, _ptr(ws), wsb, S,
+                       work=(2.0 * 4 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
+            self._call("cnp_up_wgrad_fold", _ptr(dwp), _ptr(dwt), 64, Cin, _ptr(gw), S)
+        else:
+            self._call("cnp_conv_tc_wgrad", sv(u[0]), ncb, sv(dys[0]), K.WG_K5S1, _ptr(gw),
+                       _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
+            self._call("cnp_conv_tc_wgrad", sv(u[1]), ncb, sv(dys[1]), K.WG_K5S1_T, _ptr(gw),
+                       _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * H * 64 * Cin * 25, 0.0))
+            self._call("cnp_up_wgrad_fold", _ptr(dwp), None, 64, Cin, _ptr(gw), S)
         # input gradient: one low-res launch over the four dY phases, then the band through the strips
         wpk = self._packed_weights(f"{key}.dg.ph", w, K.KIND_UP_PHASE_DGRAD, 32, n_out=128, pre="phase")
         mk = mask.view(0) if mask is not None else None

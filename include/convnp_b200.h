@@ -189,6 +189,10 @@ long long cnp_conv_tc_wgrad_workspace_bytes(void);
 int cnp_conv_tc_wgrad(const cnp_blk* x, int n_chunks, const cnp_blk* dy, int kind, float* dw /*+= [64][Cin][k][k]*/,
                       float* dbias /*+= [64] or NULL*/, int Cin, int B, void* workspace, long long workspace_bytes,
                       cnp_stream_t s);
+/* CNP_WG_K5S1 over two image groups in one launch: images [0, b_split) -> dw, [b_split, B) -> dw2 (both +=) */
+int cnp_conv_tc_wgrad_pair(const cnp_blk* x, int n_chunks, const cnp_blk* dy, float* dw, float* dw2, int b_split,
+                           float* dbias /*+= or NULL*/, int Cin, int B, void* workspace, long long workspace_bytes,
+                           cnp_stream_t s);
 int cnp_blk_channel_sum(const cnp_blk* v, int n_chunks, int B, float* out /*+=*/, cnp_stream_t s);
 int cnp_conv1x1_in_bf16(const float* x /*fp32 NCHW*/, long long x_bstride, const float* w, const float* bias, int B,
                         int Cin, int Cout, const cnp_blk* out, cnp_stream_t s);

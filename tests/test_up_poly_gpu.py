@@ -165,7 +165,7 @@ def test_wgrad_tap_transposed_kind():
     assert rel_err(g, wd.grad) < 1e-4
 
 
-@pytest.mark.parametrize("h,w", [(8, 8), (19, 23), (38, 38), (12, 76)])
+@pytest.mark.parametrize("h,w", [(12, 12), (19, 23), (38, 38), (12, 76), (13, 40)])
 def test_up_poly_layer_forward_backward(h, w):
     """The whole decoder level through the engine's orchestration: forward everywhere (band included), dx with the ReLU
     mask of the producer, dW5, dbias -- against float64 autograd and against the engine's Upsample + Conv path."""
