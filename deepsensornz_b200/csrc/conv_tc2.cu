@@ -568,12 +568,21 @@ pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transpos
              __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_c2_plan plan, int total_pos,
              long long group_stride /* elements between the weight tensors of lane groups 0 and 1 (0: the same tensor) */,
              long long wsel_stride /* elements between the stacked weight tensors selected per K block (plan.kb_wsel) */) {
+  // (K block, local position) of every global position, built once per block in shared memory: indexing the by-value
+  // plan with run-time subscripts makes every thread keep a private copy of the 2 KB struct (the 256-position plan of the
+  // phase dgrad took 124 us to pack that way)
+  __shared__ unsigned char pos_kb[C2_MAX_KB * C2_MAX_POS];
+  __shared__ unsigned char pos_lp[C2_MAX_KB * C2_MAX_POS];
+  if (threadIdx.x == 0) {
+    int g = 0;
+    for (int kb = 0; kb < plan.n_kb; ++kb)
+      for (int lp = 0; lp < plan.t_npos[plan.kb_type[kb]]; ++lp, ++g) { pos_kb[g] = (unsigned char)kb; pos_lp[g] = (unsigned char)lp; }
+  }
+  __syncthreads();
   const long long total = (long long)total_pos * 2048;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     const int c = (int)(e & 7), m = (int)((e >> 3) & 127), k8 = (int)((e >> 10) & 1);
-    int gp = (int)(e >> 11);   // global position index
-    int kb = 0;
-    while (gp >= plan.t_npos[plan.kb_type[kb]]) { gp -= plan.t_npos[plan.kb_type[kb]]; ++kb; }
+    const int kb = pos_kb[e >> 11], gp = pos_lp[e >> 11];
     const int type = plan.kb_type[kb];
     const int g = m >> 6, n = m & 63;
     const int ky = plan.t_tap[type][gp][wide ? 0 : 2 * g], kx = plan.t_tap[type][gp][wide ? 1 : 2 * g + 1];
@@ -920,6 +929,9 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   // last round costs 1/nacc of a tile (1632 tiles on 148 SMs: 11.33 rounds instead of 12)
   a.n_work = ntiles; a.split_from = ntiles; a.split = 1;
   {
+    // (measured: letting the split items take two rounds -- 76 left-over tiles of 3 accumulators -> 228 items -- is SLOWER
+    // than one round of whole tiles, 2.86 vs 2.69 ms per step: a single-accumulator item still streams the whole weight
+    // tensor, so it is L2-bound and costs far more than a third of a tile)
     const int full = (ntiles / grid) * grid, left = ntiles - full;
     if (left > 0 && a.nacc > 1 && left * a.nacc <= grid && full > 0) {
       a.split_from = full; a.split = a.nacc; a.n_work = full + left * a.nacc;

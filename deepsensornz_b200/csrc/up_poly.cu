@@ -162,11 +162,10 @@ __device__ __forceinline__ float up_wgt_t(int Y, int r, int n) {
 // input gradient of the band: the strips' gradients w.r.t. the upsampled tensor, gathered through the transposed
 // bilinear map onto the low-res pixels within 4 of the border, ReLU-masked by act > 0 and ADDED to dx.
 // The map is separable, so a thread owns a LINE of four outputs across the band and sweeps its strip once:
-//   part A (row bands): thread = (edge s, column c): horizontal combination of the 4 strip pixels around c for each of the
-//           6 strip rows, then the vertical weights of its 4 output rows; the threads of the 4 outermost columns also
-//           gather what the column strips contribute to the corner squares;
-//   part B (column bands, rows 4 .. H-5): thread = (edge s, row r), the same on the transposed strips.
-// 24 strip loads per 4 outputs (the first version gathered 16..32 per output: 55 us at 152 x 152, B = 16).
+//   part A (row bands, columns 4 .. W-5): thread = (edge s, column c): the 24 strip pixels around c in flight at once,
+//           combined horizontally per strip row, then with the vertical weights of its 4 output rows;
+//   part B (column bands, rows 4 .. H-5): thread = (edge s, row r), the same on the transposed strips;
+//   part C (corner squares): one output per thread, gathered from the row strip AND the column strip of its corner.
 // Needs H, W >= 12 (the two strips of a dimension must not overlap).
 __device__ __forceinline__ void fold_store(const blkv& dx, const blkv& act, int b, int chunk, int r, int c, const float* acc) {
   float old[8], av[8], v[8];
@@ -184,69 +183,96 @@ __device__ __forceinline__ void fold_store(const blkv& dx, const blkv& act, int 
   *reinterpret_cast<uint4*>(d) = pk(old);
 }
 
+// the four high-res neighbours 2u-1 .. 2u+2 of low-res index u: clamped indices and weights (0 outside the image)
+__device__ __forceinline__ void fold_taps(int u, int n, int* idx, float* wgt) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int X = 2 * u - 1 + j;
+    const bool ok = X >= 0 && X < 2 * n;
+    idx[j] = ok ? X : 0;
+    wgt[j] = ok ? up_wgt_t(X, u, n) : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 up_strips_bwd_fold_kernel(blkv rows, blkv cols, blkv dx, blkv act, int H, int W, int CB, int B) {
-  const int H2 = 2 * H, W2 = 2 * W;
-  const int nA = 2 * W, nB = 2 * (H - 8);
-  const long long total = (long long)B * CB * (nA + nB);
+  // items per (image, chunk): part A = 2 (W - 8) row-band lines, part B = 2 (H - 8) column-band lines, part C = the 64
+  // outputs of the four corner squares (they see BOTH strips: one output per thread)
+  const int nA = 2 * (W - 8), nB = 2 * (H - 8), nC = 64;
+  const long long total = (long long)B * CB * (nA + nB + nC);
   for (long long e = (long long)blockIdx.x * 128 + threadIdx.x; e < total; e += (long long)gridDim.x * 128) {
-    const int i = (int)(e % (nA + nB));
-    const int chunk = (int)((e / (nA + nB)) % CB), b = (int)(e / (nA + nB) / CB);
+    const int i = (int)(e % (nA + nB + nC));
+    const int chunk = (int)((e / (nA + nB + nC)) % CB), b = (int)(e / (nA + nB + nC) / CB);
+    if (i >= nA + nB) {
+      const int q = i - nA - nB, s = q >> 5, sc = (q >> 4) & 1, k = (q >> 2) & 3, l = q & 3;
+      const int r = (s ? H - 4 : 0) + k, c = (sc ? W - 4 : 0) + l;
+      int yi[4], xi[4]; float wy[4], wx[4];
+      fold_taps(r, H, yi, wy);
+      fold_taps(c, W, xi, wx);
+      const int ty0 = s ? 2 * H - UP_SR : 0, tx0 = sc ? 2 * W - UP_SR : 0;
+      float acc[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) acc[c8] = 0.f;
+#pragma unroll
+      for (int jy = 0; jy < 4; ++jy)
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) {
+          const float wgt = wy[jy] * wx[jx];
+          const int ty = yi[jy] - ty0, tx = xi[jx] - tx0;
+          float v[8];
+          if (wgt != 0.f && ty >= 0 && ty < UP_SR) {
+            unpk(ldg16(rows.at(s * B + b, chunk, ty, xi[jx])), v);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) acc[c8] = fmaf(wgt, v[c8], acc[c8]);
+          }
+          if (wgt != 0.f && tx >= 0 && tx < UP_SR) {
+            unpk(ldg16(cols.at(sc * B + b, chunk, tx, yi[jy])), v);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) acc[c8] = fmaf(wgt, v[c8], acc[c8]);
+          }
+        }
+      fold_store(dx, act, b, chunk, r, c, acc);
+      continue;
+    }
     const bool partA = i < nA;
-    // line coordinate u along the edge, n = its extent; the 4 outputs lie across the band at v0 .. v0+3 (extent m)
-    const int s = partA ? i / W : (i - nA) / (H - 8);
-    const int u = partA ? i % W : 4 + (i - nA) % (H - 8);
+    // line coordinate u along the edge (extent n); the 4 outputs lie across the band at v0 .. v0+3 (extent m)
+    const int s = partA ? i / (W - 8) : (i - nA) / (H - 8);
+    const int u = 4 + (partA ? i % (W - 8) : (i - nA) % (H - 8));
     const int n = partA ? W : H, m = partA ? H : W;
     const blkv& strip = partA ? rows : cols;
     const int v0 = s ? m - 4 : 0;                 // first output across the band
     const int t0 = s ? 2 * m - UP_SR : 0;         // high-res index of strip row 0
+    int xi[4]; float wx[4];
+    fold_taps(u, n, xi, wx);
+    uint4 raw[UP_SR][4];
+#pragma unroll
+    for (int t = 0; t < UP_SR; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) raw[t][j] = ldg16(strip.at(s * B + b, chunk, t, xi[j]));
     float acc[4][8];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = 0.f;
-    const int x_lo = max(2 * u - 1, 0), x_hi = min(2 * u + 2, 2 * n - 1);
 #pragma unroll
     for (int t = 0; t < UP_SR; ++t) {
       float h[8];
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) h[c8] = 0.f;
-      for (int X = x_lo; X <= x_hi; ++X) {
-        const float wgt = up_wgt_t(X, u, n);
-        float v[8];
-        unpk(ldg16(strip.at(s * B + b, chunk, t, X)), v);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) h[c8] = fmaf(wgt, v[c8], h[c8]);
+      for (int j = 0; j < 4; ++j) {
+        float v[8];
+        unpk(raw[t][j], v);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) h[c8] = fmaf(wx[j], v[c8], h[c8]);
       }
       const int Y = t0 + t;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int d = Y - 2 * (v0 + k);
-        if (d >= -1 && d <= 2) {
-          const float wy = up_wgt_t(Y, v0 + k, m);
+        const float wy = (d >= -1 && d <= 2) ? up_wgt_t(Y, v0 + k, m) : 0.f;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = fmaf(wy, h[c8], acc[k][c8]);
-        }
-      }
-    }
-    if (partA && (u < 4 || u >= W - 4)) {
-      // corner squares: the column strip of this side reaches rows 2 .. 2H-3 of the upsampled tensor
-      const int sc = u < 4 ? 0 : 1;
-      const int X0 = sc ? W2 - UP_SR : 0;
-      for (int tx = 0; tx < UP_SR; ++tx) {
-        const int X = X0 + tx, dxx = X - 2 * u;
-        if (dxx < -1 || dxx > 2) continue;
-        const float wx = up_wgt_t(X, u, W);
-        for (int k = 0; k < 4; ++k) {
-          const int r = v0 + k;
-          for (int Y = max(2 * r - 1, 0); Y <= min(2 * r + 2, H2 - 1); ++Y) {
-            const float wgt = wx * up_wgt_t(Y, r, H);
-            float v[8];
-            unpk(ldg16(cols.at(sc * B + b, chunk, tx, Y)), v);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = fmaf(wgt, v[c8], acc[k][c8]);
-          }
-        }
+        for (int c8 = 0; c8 < 8; ++c8) acc[k][c8] = fmaf(wy, h[c8], acc[k][c8]);
       }
     }
 #pragma unroll
@@ -361,7 +387,7 @@ CNP_API int cnp_up_strips_bwd_fold(const cnp_blk* rows, const cnp_blk* cols, con
   blkv a;
   a.p = nullptr; a.bs = 0; a.Hp = a.Wp = 0;
   if (act) a = view_of(act);
-  const long long total = (long long)B * n_chunks * (2 * dx->W + 2 * (dx->H - 8));
+  const long long total = (long long)B * n_chunks * (2 * (dx->W - 8) + 2 * (dx->H - 8) + 64);
   up_strips_bwd_fold_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(view_of(rows), view_of(cols), view_of(dx), a, dx->H, dx->W,
                                                            n_chunks, B);
   CNP_LAUNCH_CHECK("up_strips_bwd_fold_kernel");

@@ -141,6 +141,7 @@ class Engine:
         self._wp_ver: Dict[str, tuple] = {}        # polyphase weights per level: (weight version, forced-pack epoch)
         self._pack_epoch = 0
         self._pack_stream = None
+        self._wgrad_stream = None
         self._pack_event = None
         self._pack_event_bwd = None
         self._side_streams: List[torch.cuda.Stream] = []
@@ -940,11 +941,15 @@ class Engine:
         return {"u": u}
 
     def _up_poly_bwd(self, key: str, x: "_Blk", w: torch.Tensor, dy: CnpBlk, dx: "_Blk", saved: dict,
-                     gw: torch.Tensor, gb: torch.Tensor, B: int, mask: Optional["_Blk"] = None) -> None:
+                     gw: torch.Tensor, gb: torch.Tensor, B: int, mask: Optional["_Blk"] = None,
+                     on_wgrad_stream=None) -> None:
         """Backward of ``_up_poly_fwd``: gw += dL/dw, gb += dL/dbias, dx (all chunks of x) = mask * dL/dx; dy is the
-        gradient w.r.t. the layer's pre-activation (8 chunks at 2H x 2W)."""
+        gradient w.r.t. the layer's pre-activation (8 chunks at 2H x 2W).  ``on_wgrad_stream(fn)``: runner for the
+        launches that only produce parameter gradients (the UNet backward's side stream)."""
         K = _cabi
         S = _stream()
+        if on_wgrad_stream is None:
+            on_wgrad_stream = lambda fn: fn()
         ncb, H, W = x.CB, x.H, x.W
         Cin = ncb * 8
         sv = lambda p: C.byref(p[0].view(0, p[1]))
@@ -953,30 +958,34 @@ class Engine:
         # the producer's epilogue may already have written the space-to-depth copy (``saved["s2d_done"]``)
         self._call("cnp_up_dy_split", C.byref(dy), None if saved.get("s2d_done") else C.byref(s2d.view()), sv(dys[0]),
                    sv(dys[1]), B, S)
-        wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
-        ws = self._buf("wgrad_ws", (wsb // 4,))
-        # weight gradient: phase gradients at low resolution + the strips' 5x5 gradients, folded into gw
-        dwp = self._buf(f"{key}.dwp", (2, 2, 64, Cin, 4, 4))
-        dwp.zero_()
-        self._call("cnp_conv_tc_wgrad", C.byref(x.view(0)), ncb, C.byref(s2d.view(0)), K.WG_UP_PHASE, _ptr(dwp), _ptr(gb),
-                   Cin, B, _ptr(ws), wsb, S, work=(2.0 * B * H * W * 4 * 64 * Cin * 16, 0.0))
-        u = saved["u"]
-        # column strips are transposed images convolved with the tap-transposed weights: their gradient, transposed
-        # back, is the gradient w.r.t. w itself
-        if u[0][0] is u[1][0]:
-            # square level: both strip groups in one launch (rows -> gw, columns -> dwt), the fold transposes dwt
-            dwt = self._buf(f"{key}.dwt", (64, Cin, 5, 5))
-            dwt.zero_()
-            self._call("cnp_conv_tc_wgrad_pair", C.byref(u[0][0].view(0)), ncb, C.byref(dys[0][0].view(0)), _ptr(gw),
-                       _ptr(dwt), 2 * B, _ptr(gb), Cin, 4 * B, _ptr(ws), wsb, S,
-                       work=(2.0 * 4 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
-            self._call("cnp_up_wgrad_fold", _ptr(dwp), _ptr(dwt), 64, Cin, _ptr(gw), S)
-        else:
-            self._call("cnp_conv_tc_wgrad", sv(u[0]), ncb, sv(dys[0]), K.WG_K5S1, _ptr(gw),
-                       _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
-            self._call("cnp_conv_tc_wgrad", sv(u[1]), ncb, sv(dys[1]), K.WG_K5S1_T, _ptr(gw),
-                       _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * H * 64 * Cin * 25, 0.0))
-            self._call("cnp_up_wgrad_fold", _ptr(dwp), None, 64, Cin, _ptr(gw), S)
+
+        def weight_gradient():
+            S = _stream()
+            wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
+            ws = self._buf("wgrad_ws", (wsb // 4,))
+            # weight gradient: phase gradients at low resolution + the strips' 5x5 gradients, folded into gw
+            dwp = self._buf(f"{key}.dwp", (2, 2, 64, Cin, 4, 4))
+            dwp.zero_()
+            self._call("cnp_conv_tc_wgrad", C.byref(x.view(0)), ncb, C.byref(s2d.view(0)), K.WG_UP_PHASE, _ptr(dwp), _ptr(gb),
+                       Cin, B, _ptr(ws), wsb, S, work=(2.0 * B * H * W * 4 * 64 * Cin * 16, 0.0))
+            u = saved["u"]
+            # column strips are transposed images convolved with the tap-transposed weights: their gradient, transposed
+            # back, is the gradient w.r.t. w itself
+            if u[0][0] is u[1][0]:
+                # square level: both strip groups in one launch (rows -> gw, columns -> dwt), the fold transposes dwt
+                dwt = self._buf(f"{key}.dwt", (64, Cin, 5, 5))
+                dwt.zero_()
+                self._call("cnp_conv_tc_wgrad_pair", C.byref(u[0][0].view(0)), ncb, C.byref(dys[0][0].view(0)), _ptr(gw),
+                           _ptr(dwt), 2 * B, _ptr(gb), Cin, 4 * B, _ptr(ws), wsb, S,
+                           work=(2.0 * 4 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
+                self._call("cnp_up_wgrad_fold", _ptr(dwp), _ptr(dwt), 64, Cin, _ptr(gw), S)
+            else:
+                self._call("cnp_conv_tc_wgrad", sv(u[0]), ncb, sv(dys[0]), K.WG_K5S1, _ptr(gw),
+                           _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * W * 64 * Cin * 25, 0.0))
+                self._call("cnp_conv_tc_wgrad", sv(u[1]), ncb, sv(dys[1]), K.WG_K5S1_T, _ptr(gw),
+                           _ptr(gb), Cin, 2 * B, _ptr(ws), wsb, S, work=(2.0 * 2 * B * 6 * 2 * H * 64 * Cin * 25, 0.0))
+                self._call("cnp_up_wgrad_fold", _ptr(dwp), None, 64, Cin, _ptr(gw), S)
+        on_wgrad_stream(weight_gradient)
         # input gradient: one low-res launch over the four dY phases, then the band through the strips
         wpk = self._packed_weights(f"{key}.dg.ph", w, K.KIND_UP_PHASE_DGRAD, 32, n_out=128, pre="phase")
         mk = mask.view(0) if mask is not None else None
@@ -1093,13 +1102,40 @@ class Engine:
                        _ptr(grads[name + ".weight"]), _ptr(grads[name + ".bias"]), Bn, Cin, H, W, dy.shape[1], k,
                        stride, S)
 
+        # Weight gradients run on their own stream: a layer's wgrad and dgrad both consume dY and nothing downstream of
+        # the backward reads a weight gradient before the optimiser, so the wgrad chain only has to wait for "dY ready"
+        # and the two chains fill each other's tails (every big kernel here is a persistent launch whose last round
+        # leaves SMs idle).  One workspace, used in stream order.  CNP_NO_WGRAD_STREAM=1 keeps a single stream.
+        main_stream = torch.cuda.current_stream()
+        wg_stream = None
+        if not (os.environ.get("CNP_NO_WGRAD_STREAM") or os.environ.get("CNP_NO_MULTISTREAM")) and self._prof is None:
+            if self._wgrad_stream is None:
+                self._wgrad_stream = torch.cuda.Stream()
+            wg_stream = self._wgrad_stream
+
+        def on_wgrad_stream(fn):
+            """Run ``fn`` (launches that only produce weight / bias gradients) after everything issued so far."""
+            if wg_stream is None:
+                fn()
+                return
+            ev = torch.cuda.Event()
+            ev.record(main_stream)
+            wg_stream.wait_event(ev)
+            with torch.cuda.stream(wg_stream):
+                fn()
+
+        def join_wgrad_stream():
+            if wg_stream is not None:
+                main_stream.wait_stream(wg_stream)
+
         def wgrad_tc(x: CnpBlk, n_chunks, dy: CnpBlk, kind, name, Cin):
             kk = 1 if kind == K.WG_K1 else 25
             wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
             ws = self._buf("wgrad_ws", (wsb // 4,))
-            self._call("cnp_conv_tc_wgrad", C.byref(x), n_chunks, C.byref(dy), kind, _ptr(grads[name + ".weight"]),
-                       _ptr(grads[name + ".bias"]), Cin, B, _ptr(ws), wsb, S,
-                       work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0))
+            on_wgrad_stream(lambda: self._call(
+                "cnp_conv_tc_wgrad", C.byref(x), n_chunks, C.byref(dy), kind, _ptr(grads[name + ".weight"]),
+                _ptr(grads[name + ".bias"]), Cin, B, _ptr(ws), wsb, _stream(),
+                work=(2.0 * B * dy.H * dy.W * 64 * Cin * kk, 0.0)))
 
         def dgrad_tc(dy: CnpBlk, w, key, kind, n_out_ch, dst: _Blk, dst_cb, mask: Optional[_Blk], mask_cb,
                      accumulate=False, phase=None, s2d: Optional[_Blk] = None):
@@ -1132,7 +1168,8 @@ class Engine:
             lyr = u.after_turn_layers[i]
             if A["polys"][i] is not None:
                 self._up_poly_bwd(f"after{i}", cat[i], lyr.weight, dy_blk.view(dy_cb), d_cat[i], A["polys"][i],
-                                  grads[name + ".weight"], grads[name + ".bias"], B, mask=cat[i])
+                                  grads[name + ".weight"], grads[name + ".bias"], B, mask=cat[i],
+                                  on_wgrad_stream=on_wgrad_stream)
                 if i < L - 1:
                     dy_blk, dy_cb = d_cat[i], 8
                 continue
@@ -1155,6 +1192,7 @@ class Engine:
             if i < L - 1:
                 dy_blk, dy_cb = d_cat[i], 8
         if up_done is not None:          # gradients of the head, the final 1x1 and the up path are complete
+            join_wgrad_stream()
             up_done()
         for i in range(L - 1, -1, -1):
             name = P + f"before_turn_layers.{i}"
@@ -1166,15 +1204,18 @@ class Engine:
                 il = u.initial_linear
                 cp = x_src.CB * 8
                 dwf = self._buf("dwf0", (64, cp, 5, 5))
-                dwf.zero_()
                 wsb = _cabi.lib().cnp_conv_tc_wgrad_workspace_bytes()
                 ws = self._buf("wgrad_ws", (wsb // 4,))
-                self._call("cnp_conv_tc_wgrad", C.byref(x_src.view(0)), x_src.CB, C.byref(d_cat[0].view(0)),
-                           K.WG_K5S1_NARROW, _ptr(dwf), _ptr(grads[name + ".bias"]), cp, B, _ptr(ws), wsb, S,
-                           work=(2.0 * B * n1 * n2 * 64 * cp * 25, 0.0))
-                self._call("cnp_fold_in_bwd", _ptr(dwf), _ptr(lyr.weight), _ptr(il.weight), _ptr(il.bias), 64, 64,
-                           cfg.in_channels, cp, 5, _ptr(grads[name + ".weight"]),
-                           _ptr(grads[P + "initial_linear.weight"]), _ptr(grads[P + "initial_linear.bias"]), S)
+
+                def first_layer_wgrad():
+                    dwf.zero_()
+                    self._call("cnp_conv_tc_wgrad", C.byref(x_src.view(0)), x_src.CB, C.byref(d_cat[0].view(0)),
+                               K.WG_K5S1_NARROW, _ptr(dwf), _ptr(grads[name + ".bias"]), cp, B, _ptr(ws), wsb, _stream(),
+                               work=(2.0 * B * n1 * n2 * 64 * cp * 25, 0.0))
+                    self._call("cnp_fold_in_bwd", _ptr(dwf), _ptr(lyr.weight), _ptr(il.weight), _ptr(il.bias), 64, 64,
+                               cfg.in_channels, cp, 5, _ptr(grads[name + ".weight"]),
+                               _ptr(grads[P + "initial_linear.weight"]), _ptr(grads[P + "initial_linear.bias"]), _stream())
+                on_wgrad_stream(first_layer_wgrad)
                 continue
             if st[i] == 2:
                 wgrad_tc(A["phases"][i].view(0), 32, d_cat[i].view(0), K.WG_K5S2, name, 64)
@@ -1218,6 +1259,7 @@ class Engine:
                 dgrad_tc(d_cat[0].view(0), lyr.weight, "before0", K.KIND_K5S1_DGRAD, 64, d_init, 0, None, 0)
                 self._call("cnp_conv1x1_in_wgrad", _ptr(enc), enc.stride(0), cfg.in_channels, C.byref(d_init.view(0)), B,
                            _ptr(grads[P + "initial_linear.weight"]), _ptr(grads[P + "initial_linear.bias"]), S)
+        join_wgrad_stream()
 
     # ------------------------------------------------------------------------------------------
     # (3)+(4) decoder, head
