@@ -926,19 +926,48 @@ class Engine:
         launches for the interior, the standard kernel on four strips for the 4-pixel band.  Returns the strips of the
         upsampled tensor (the band's weight gradient needs them)."""
         K = _cabi
-        S = _stream()
         ncb, H, W = x.CB, x.H, x.W
-        for a in (0, 1):
-            wpk = self._packed_weights(f"{key}.ph{a}", w, K.KIND_UP_PHASE, ncb, py=a, pre="phase")
-            self._conv_tc(x.view(0), ncb, wpk, K.KIND_UP_PHASE,
-                          self._out_blk(dst, bias=bias, relu=True, scatter=(2, a, 2, 0)), B, py=a)
         sv = lambda p: C.byref(p[0].view(0, p[1]))
         u = self._up_strip_blks(f"{key}.u", B, ncb, H, W)
-        self._call("cnp_up_strips_fwd", C.byref(x.view(0)), ncb, sv(u[0]), sv(u[1]), B, S)
         o = self._up_strip_blks(f"{key}.o", B, 8, H, W)
-        self._strip_conv(u, o, ncb, w, key, K.KIND_K5S1, 64, B, bias=bias, relu=True)
-        self._call("cnp_up_strips_scatter", sv(o[0]), sv(o[1]), C.byref(dst), B, S)
+        wpk = [self._packed_weights(f"{key}.ph{a}", w, K.KIND_UP_PHASE, ncb, py=a, pre="phase") for a in (0, 1)]
+
+        def phase(a):
+            self._conv_tc(x.view(0), ncb, wpk[a], K.KIND_UP_PHASE,
+                          self._out_blk(dst, bias=bias, relu=True, scatter=(2, a, 2, 0)), B, py=a)
+
+        def strips():
+            self._call("cnp_up_strips_fwd", C.byref(x.view(0)), ncb, sv(u[0]), sv(u[1]), B, _stream())
+            self._strip_conv(u, o, ncb, w, key, K.KIND_K5S1, 64, B, bias=bias, relu=True)
+
+        # the two row phases and the strips are independent until the scatter: three streams, so that the tail of one
+        # persistent launch (816 tiles on 148 SMs: a half-empty last round) is filled by the next
+        self._fork_join([lambda: phase(0), lambda: phase(1), strips])
+        self._call("cnp_up_strips_scatter", sv(o[0]), sv(o[1]), C.byref(dst), B, _stream())
         return {"u": u}
+
+    def _fork_join(self, fns) -> None:
+        """Run ``fns[0]`` on the current stream and the others on side streams forked from it; join before returning.
+        Single stream under the per-call profiler or CNP_NO_MULTISTREAM=1."""
+        if self._prof is not None or os.environ.get("CNP_NO_MULTISTREAM") or len(fns) == 1:
+            for fn in fns:
+                fn()
+            return
+        if len(self._side_streams) < 4:
+            self._side_streams = [torch.cuda.Stream() for _ in range(4)]
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        used = []
+        for k, fn in enumerate(fns[1:]):
+            ss = self._side_streams[k % 4]
+            ss.wait_event(fork)
+            with torch.cuda.stream(ss):
+                fn()
+            used.append(ss)
+        fns[0]()
+        for ss in used:
+            main.wait_stream(ss)
 
     def _up_poly_bwd(self, key: str, x: "_Blk", w: torch.Tensor, dy: CnpBlk, dx: "_Blk", saved: dict,
                      gw: torch.Tensor, gb: torch.Tensor, B: int, mask: Optional["_Blk"] = None,
@@ -989,11 +1018,16 @@ class Engine:
         # input gradient: one low-res launch over the four dY phases, then the band through the strips
         wpk = self._packed_weights(f"{key}.dg.ph", w, K.KIND_UP_PHASE_DGRAD, 32, n_out=128, pre="phase")
         mk = mask.view(0) if mask is not None else None
-        self._conv_tc(s2d.view(0), 32, wpk, K.KIND_UP_PHASE_DGRAD, self._out_blk(dx.view(0), mask=mk), B, n_out=128)
         du = self._up_strip_blks(f"{key}.du", B, ncb, H, W)
-        self._strip_conv(dys, du, 8, w, key, K.KIND_K5S1_DGRAD, 128, B)
+        # pack on the current stream first (a side stream must not be the first consumer of the packing event)
+        self._packed_weights(f"{key}.dg.00", w, K.KIND_K5S1_DGRAD, 8, 0, 0, 0, 128)
+        self._packed_weights(f"{key}.dg.t", w, K.KIND_K5S1_DGRAD, 8, 0, 0, 0, 128, pre="tswap")
+        self._fork_join([
+            lambda: self._conv_tc(s2d.view(0), 32, wpk, K.KIND_UP_PHASE_DGRAD, self._out_blk(dx.view(0), mask=mk), B,
+                                  n_out=128),
+            lambda: self._strip_conv(dys, du, 8, w, key, K.KIND_K5S1_DGRAD, 128, B)])
         self._call("cnp_up_strips_bwd_fold", sv(du[0]), sv(du[1]), C.byref(dx.view()),
-                   C.byref(mk) if mk is not None else None, ncb, B, S)
+                   C.byref(mk) if mk is not None else None, ncb, B, _stream())
 
     def _unet_fwd_bf16(self, enc: Optional[torch.Tensor], B: int, n1: int, n2: int, need_z: bool = True,
                        x_aug: Optional["_Blk"] = None) -> Tuple[Optional[torch.Tensor], dict]:
