@@ -49,6 +49,7 @@ struct cnp_c2_args {
   const uint8_t* w2; int w2_from_b;   // optional second packed weight tensor, used by the images b >= w2_from_b (strips)
   int B, H, W;
   int TW, TH, pitch, N, nacc, rpa, plane_sm, tiles_x, tiles_y;
+  int nbuf;                     // 2: two accumulator sets of 256 TMEM columns -- the epilogue of tile t overlaps the MMAs of t+1
   int wide;
   int pxpair;                   // stride-2 dgrad: lane group g = output x-phase g (both phases of a row in one launch)
   int n_work, split_from, split;  // work items: tiles [0, split_from) whole, the leftover tiles of the last round
@@ -140,9 +141,9 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   uint64_t* a_empty = bars + 2;        // [2]
   uint64_t* w_full = bars + 4;         // [3]
   uint64_t* w_empty = bars + 7;        // [3]
-  uint64_t* acc_full = bars + 10;      // [1]
-  uint64_t* acc_empty = bars + 11;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* acc_full = bars + 10;      // [2]
+  uint64_t* acc_empty = bars + 12;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   __shared__ uint32_t pos_tbl[C2_MAX_TYPES][C2_MAX_POS + 2];   // B offsets (16 B units) of the generic plans
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,8 +152,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < C2_ABUFS; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
     for (int i = 0; i < C2_WSTAGES; ++i) { tc::mbar_init(w_full + i, 1); tc::mbar_init(w_empty + i, (uint32_t)a_cluster); }
-    tc::mbar_init(acc_full, 1);
-    tc::mbar_init(acc_empty, C2_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, C2_EPI_WARPS); }
     tc::mbar_fence_init();
   }
   if (warp == 3) tc::tmem_alloc(tmem_slot, 512);
@@ -258,6 +258,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
         const int npos = a.plan.t_npos[type];
         const int np = min(C2_STAGE_POS, npos - s0);
         const int ws = w_it % C2_WSTAGES, buf = a_it & 1;
+        const uint32_t tmem_acc = tmem_base + (a.nbuf > 1 ? (t_it & 1u) * 256u : 0u);   // this tile's accumulator set
         int n_s0 = s0 + C2_STAGE_POS, n_kb = kb, n_tile = tile;
         uint32_t n_a_it = a_it;
         if (n_s0 >= npos) {
@@ -272,13 +273,13 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
           // stage = window row s0/5, positions = 5 consecutive pixels: only 32-bit adds between MMAs
           const uint32_t w_lo = ((w_base >> 4) & 0x3FFFu) | w_lbo;
           const uint32_t b_lo = ((a16 + (uint32_t)(s0 / C2_STAGE_POS) * (uint32_t)a.pitch) & 0x3FFFu) | b_lbo;
-          if (nacc == 3) issue_row<3, 0, 4>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
-          else if (nacc == 2) issue_row<2, 0, 4>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
-          else issue_row_n<0, 4>(nacc, tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
+          if (nacc == 3) issue_row<3, 0, 4>(tmem_acc, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
+          else if (nacc == 2) issue_row<2, 0, 4>(tmem_acc, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
+          else issue_row_n<0, 4>(nacc, tmem_acc, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, first);
           if (!tile_end) wait_stage(n_s0, n_a_it, w_it + 1);
-          if (nacc == 3) issue_row<3, 4, 5>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
-          else if (nacc == 2) issue_row<2, 4, 5>(tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
-          else issue_row_n<4, 5>(nacc, tmem_base, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
+          if (nacc == 3) issue_row<3, 4, 5>(tmem_acc, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
+          else if (nacc == 2) issue_row<2, 4, 5>(tmem_acc, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
+          else issue_row_n<4, 5>(nacc, tmem_acc, w_lo, b_lo, desc_hi, idesc, Ncols, acc_step16, 1u);
         } else {
           // generic plans (stride-2, 1x1): offsets of the stage's <= 5 positions come from shared memory, loaded
           // together up front so the MMAs are separated only by 32-bit adds
@@ -295,11 +296,11 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
               if (nacc == 3) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
-                  tc::mma_bf16_ss_lohi(tmem_base + j * Ncols, w_lo0 + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + j * acc_step16,
+                  tc::mma_bf16_ss_lohi(tmem_acc + j * Ncols, w_lo0 + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + j * acc_step16,
                                        desc_hi, idesc, accf);
               } else {
                 for (int j = 0; j < nacc; ++j)
-                  tc::mma_bf16_ss_lohi(tmem_base + j * Ncols, w_lo0 + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + j * acc_step16,
+                  tc::mma_bf16_ss_lohi(tmem_acc + j * Ncols, w_lo0 + p * (C2_POS_BYTES >> 4), desc_hi, b_lo + j * acc_step16,
                                        desc_hi, idesc, accf);
               }
             }
@@ -309,12 +310,14 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
         if (kb_end) tc::mma_commit(a_empty + buf);
         ++w_it;
         if (tile_end) {
-          tc::mma_commit(acc_full);
+          tc::mma_commit(acc_full + (a.nbuf > 1 ? (t_it & 1u) : 0u));
           ++t_it;
           if (n_tile >= ntiles) break;
           nacc = tile_nacc(n_tile);
           if (a.dbg) t0 = clock64();
-          tc::mbar_wait(acc_empty, (t_it & 1) ^ 1);     // the epilogue has drained the accumulators
+          // the epilogue has drained the accumulator set the next tile uses (two sets: its use before last)
+          if (a.nbuf > 1) tc::mbar_wait(acc_empty + (t_it & 1u), ((t_it >> 1) & 1u) ^ 1u);
+          else tc::mbar_wait(acc_empty, (t_it & 1) ^ 1);
           if (a.dbg) c_acc += clock64() - t0;
           wait_stage(0, n_a_it, w_it);
         }
@@ -380,7 +383,9 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
           }
         }
       }
-      tc::mbar_wait(acc_full, t_it & 1);
+      const uint32_t abuf = a.nbuf > 1 ? (t_it & 1u) : 0u;
+      const uint32_t tmem_acc = tmem_base + abuf * 256u;
+      tc::mbar_wait(acc_full + abuf, a.nbuf > 1 ? ((t_it >> 1) & 1u) : (t_it & 1u));
       const long long te0 = a.dbg ? clock64() : 0;
       tc::fence_after_sync();
       const int n_items = wk.nacc * ncb;
@@ -403,7 +408,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             // (The first version -- thread = channel, 32 two-byte stores + 16 word loads per block -- kept the
             // shared-memory instruction pipe busy for half of the epilogue: tools/bench_conv.py stall counters.)
             uint32_t ra[16], rb[16];
-            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs);
+            const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs);
             tc::tmem_ld_16x256b_x4(t0, ra);
             tc::tmem_ld_16x256b_x4(t0 + (16u << 16), rb);
             tc::tmem_ld_wait();
@@ -441,7 +446,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             __syncwarp();
           } else {
           float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs), v);
+          tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs), v);
           tc::tmem_ld_wait();
           if (a.dbg_flags & 1) { float sacc = 0.f;
 #pragma unroll
@@ -547,7 +552,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(acc_empty);
+      if (lane == 0) tc::mbar_arrive(acc_empty + abuf);
       if (a.dbg && ew == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] += clock64() - te0;
     }
   }
@@ -757,7 +762,13 @@ size_t c2_smem_bytes(int plane_sm, int out_mode) {
 //   L2    : weights (mma_per_acc x 4 KB) + windows are re-read per tile; ~30 B/clk/SM when all SMs stream;
 //   epilogue (not overlapped with the MMAs): ~18 cycles per accumulator column.
 // Minimise waves x (max(MMA, L2) + epilogue).
-void choose_geometry(cnp_c2_args* a, int mma_per_acc) {
+// Two accumulator sets (nbuf = 2, nacc * N <= 256 columns each): the epilogue of a tile overlaps the MMAs of the next one,
+// a tile then costs max(main loop, epilogue) instead of their sum -- pays on the layers with a short K loop or a heavy
+// epilogue (the folded first layer: 30 positions; the stride-2 input gradients: 40 / 60 positions and a masked
+// read-modify-write epilogue), not on the 128-channel layers, whose weight stream needs 3 accumulators per tile to stay
+// under the L2 rate.  epi_col: epilogue cycles per accumulator column (18 plain; the mask and the accumulate target are
+// global loads issued from the epilogue).
+void choose_geometry(cnp_c2_args* a, int mma_per_acc, double epi_col, bool allow_nbuf2) {
   const int rpa = (a->wide || a->pxpair) ? 1 : 2;
   double best = 1e300;
   for (int N = 32; N <= 256; N += 32) {
@@ -781,11 +792,15 @@ void choose_geometry(cnp_c2_args* a, int mma_per_acc) {
       const double mma_c = (double)mma_per_acc * nacc * cyc;
       // weights are shared by the CTA pair when launched as clusters of 2 (multicast): half the bytes per CTA
       const double l2_c = ((double)mma_per_acc * 4096.0 + (double)n_kb * 2.0 * (TH + 4) * pitch * 16.0) / 30.0;
-      const double cost = (double)waves * ((mma_c > l2_c ? mma_c : l2_c) + 18.0 * nacc * N + 1500.0);
-      if (cost < best) {
-        best = cost;
-        a->N = N; a->nacc = nacc; a->rpa = rpa; a->TW = TW; a->TH = TH; a->pitch = pitch; a->plane_sm = plane_sm;
-        a->tiles_x = tiles_x; a->tiles_y = tiles_y;
+      const double main_c = (mma_c > l2_c ? mma_c : l2_c) + 1500.0, epi_c = epi_col * nacc * N;
+      for (int nbuf = 1; nbuf <= ((allow_nbuf2 && nacc * N <= 256) ? 2 : 1); ++nbuf) {
+        const double cost = nbuf == 1 ? (double)waves * (main_c + epi_c)
+                                      : (double)waves * (main_c > epi_c ? main_c : epi_c) + (main_c < epi_c ? main_c : epi_c);
+        if (cost < best) {
+          best = cost;
+          a->N = N; a->nacc = nacc; a->rpa = rpa; a->TW = TW; a->TH = TH; a->pitch = pitch; a->plane_sm = plane_sm;
+          a->tiles_x = tiles_x; a->tiles_y = tiles_y; a->nbuf = nbuf;
+        }
       }
     }
   }
@@ -883,7 +898,13 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   a.out_mode = o->mode;
   a.cluster = wpk2 ? 1 : g_c2_cluster;    // the multicast weight stream assumes one tensor for the CTA pair
   if (int e = build_plan2(kind, n_chunks, 8, py, px, a.wide, &a.plan)) return e;   // position count only
-  choose_geometry(&a, plan_total_pos(a.plan));
+  // Opt-in (CNP_DOUBLE_ACC=1): measured on B200 it LOSES wherever the model picks it -- masked WIDE dgrad at 304^2 503 ->
+  // 743 us, stride-2 dgrad phases 127 -> 373 us / 45 -> 155 us -- because a set of <= 256 columns means one accumulator of
+  // N = 160, and every tile re-streams the whole packed weight tensor from L2 for a third of the MMAs: the weight stream,
+  // not the epilogue, bounds short tiles (same finding as the two-round tail split above).
+  static const bool nbuf2 = getenv("CNP_DOUBLE_ACC") != nullptr;
+  choose_geometry(&a, plan_total_pos(a.plan), 18.0 + (o->mode == 0 && o->mask ? 30.0 : 0.0) + (o->accumulate ? 40.0 : 0.0),
+                  nbuf2);
   CNP_REQUIRE(a.N > 0, "conv_tc2: no tile geometry for %d x %d", a.H, a.W);
   if (int e = build_plan2(kind, n_chunks, a.pitch, py, px, a.wide, &a.plan)) return e;
   a.out_mode = o->mode;
