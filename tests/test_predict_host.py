@@ -74,3 +74,35 @@ def test_signature_groups_padded_batches_and_separates_grids():
     hb = _pad_offgrid(_host_batch(21))
     hb.contexts[0].x_host = (np.linspace(0, 1, 5)[None] + 1e-3, np.linspace(0, 1, 6)[None])   # other grid coordinates
     assert _inference_signature(hb) != s21
+
+
+def test_result_pool_recycles_only_unreferenced_arrays(monkeypatch):
+    """predict's result arrays come from a pool (first-touch page faults bound predict end to end): an array is handed
+    out again only when nothing -- no view, no view of a view, no tensor made from it -- references it any more."""
+    import numpy as np
+    import torch
+    from deepsensornz_b200.predict import _ResultPool
+    p = _ResultPool()
+    a, b = p.take((4, 50, 60))[0], p.take((4, 50, 60))[0]
+    pa, pb = a.ctypes.data, b.ctypes.data
+    assert pa != pb and a.shape == (4, 50, 60) and a.dtype == np.float32
+    v = a[1:3, ::2]                       # a strided view of a view keeps the owner alive
+    del a
+    c = p.take((4, 50, 60))[0]
+    assert c.ctypes.data not in (pa, pb)
+    del v
+    d = p.take((2, 50, 60))[0]            # a smaller request fits the idle owner
+    assert d.ctypes.data == pa and p.hits == 1
+    t = torch.from_numpy(d)
+    del d
+    assert p.take((2, 50, 60))[0].ctypes.data != pa
+    del t
+    assert p.take((4, 50, 60))[0].ctypes.data == pa
+    # cap: requests over the cap bypass the pool, a cap of 0 disables it
+    monkeypatch.setenv("CONVNP_B200_RESULT_POOL_MB", "0")
+    q = _ResultPool()
+    x = q.take((8, 8))[0]
+    px = x.ctypes.data
+    del x
+    q.take((8, 8))
+    assert q.hits == 0 and q.misses == 0 and px
