@@ -133,6 +133,36 @@ class _ResultPool:
 _result_pool = _ResultPool()
 
 
+def _fingerprint(a: np.ndarray):
+    """(address, shape, sum of ~2048 strided samples) of a C-contiguous array, else None: guards device copies that are
+    kept across ``predict`` calls against a buffer that was freed and re-used, or rewritten in place, in between."""
+    if not isinstance(a, np.ndarray) or not a.flags.c_contiguous or a.size == 0:
+        return None
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 2048)
+    return (a.__array_interface__["data"][0], a.shape, str(a.dtype), float(np.nansum(flat[::step], dtype=np.float64)))
+
+
+def _persistent_ctx_cache(model, tasks) -> dict:
+    """The ``ctx_cache`` of ``Engine.stage_host`` (device copies of the gridded static context sets, keyed on buffer
+    identity, validated by weak references) kept on the model between ``predict`` calls, reset when the sampled content
+    of any gridded context array of the first task changed."""
+    from .task import same_buffer
+    fps = []
+    if tasks:
+        t0, t1 = tasks[0], tasks[-1]
+        for k, (x, y) in enumerate(zip(t0.get("X_c", ()), t0.get("Y_c", ()))):
+            # static sets only (the same buffer in the first and the last task): per-date grids change from call to call
+            if isinstance(x, tuple) and isinstance(y, np.ndarray) and (len(tasks) == 1 or same_buffer([y, t1["Y_c"][k]])):
+                fps.append(_fingerprint(y))
+    fps = tuple(fps)
+    ent = model.__dict__.get("_predict_ctx")
+    if ent is None or ent[0] != fps or None in fps or len(ent[1]) > 32:
+        ent = (fps, {})
+        model.__dict__["_predict_ctx"] = ent
+    return ent[1]
+
+
 def _pinned_ring(model, shape, slots: int):
     """``slots`` pairs (mean, std) of pinned read-back buffers, kept on the model: page-locking ~190 MB per call
     (cudaHostAlloc) cost more than the whole prediction of a 32-date range (2.2 against 1.0 ms per date)."""
@@ -360,7 +390,7 @@ def _predict_batched(model, tasks, Xn, aux_dev, nb, aff_mean, aff_std, copy_stre
     pin = None if direct else _pinned_ring(model, (nb, P, Q), SL)
     events = [None] * SL
     futures = [None] * SL
-    ctx_cache = {}
+    ctx_cache = _persistent_ctx_cache(model, tasks)
     d2h_stream = torch.cuda.Stream()
 
     # pinned -> result array, one job per (date, field): the first touch of the freshly allocated result pages makes a
@@ -454,8 +484,21 @@ def predict(model, tasks, X_t, X_t_mask=None, X_t_is_normalised: bool = False, a
     eng = model.engine
     aux_dev = None
     if aux is not None:
-        t = torch.from_numpy(np.ascontiguousarray(aux[np.newaxis]))
-        aux_dev = t.pin_memory().to(eng.device, non_blocking=True) if torch.cuda.is_available() else t
+        # the device copy of the static aux-at-target tensor (39 MB at 1400 x 1400) survives across calls while the
+        # host array is the same live buffer with the same sampled content (``_fingerprint``)
+        fp = _fingerprint(aux)
+        ent = model.__dict__.get("_predict_aux")
+        if ent is not None and fp is not None and ent[0] == fp and ent[1]() is not None:
+            aux_dev = ent[2]
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(aux[np.newaxis]))
+            aux_dev = t.pin_memory().to(eng.device, non_blocking=True) if torch.cuda.is_available() else t
+            own = aux if aux.base is None else aux.base
+            try:
+                import weakref
+                model.__dict__["_predict_aux"] = (fp, weakref.ref(own), aux_dev) if fp is not None else None
+            except TypeError:
+                model.__dict__["_predict_aux"] = None
     it = tasks
     if progress_bar:
         try:

@@ -106,3 +106,28 @@ def test_result_pool_recycles_only_unreferenced_arrays(monkeypatch):
     del x
     q.take((8, 8))
     assert q.hits == 0 and q.misses == 0 and px
+
+
+def test_static_device_copies_persist_across_predict_calls_only_while_unchanged():
+    """The fingerprint that lets predict keep the aux-at-target tensor and the static context sets on the device between
+    calls notices an in-place rewrite and a different buffer."""
+    import numpy as np
+    from deepsensornz_b200.predict import _fingerprint, _persistent_ctx_cache
+    a = np.arange(10000, dtype=np.float32).reshape(100, 100)
+    fp = _fingerprint(a)
+    assert fp == _fingerprint(a) and _fingerprint(a[:, ::2]) is None          # non-contiguous: never kept
+    a[0, 0] = 123.0                                                            # sample 0 is always part of the sum
+    assert _fingerprint(a) != fp
+    assert _fingerprint(a.copy())[0] != _fingerprint(a)[0]
+
+    class M:                                                                   # stand-in for the model object
+        pass
+    m = M()
+    static = np.ones((1, 8, 8), np.float32)
+    mk = lambda i: {"X_c": [(np.arange(8.), np.arange(8.)), (np.arange(8.), np.arange(8.))],
+                    "Y_c": [np.full((1, 8, 8), float(i), np.float32), static]}
+    c1 = _persistent_ctx_cache(m, [mk(0), mk(1)])
+    c1["x"] = 1
+    assert _persistent_ctx_cache(m, [mk(2), mk(3)]) is c1                      # per-date grids differ: still the same cache
+    static[0, 0, 0] = 5.0
+    assert _persistent_ctx_cache(m, [mk(0), mk(1)]) is not c1                  # the static set changed: reset
