@@ -521,12 +521,19 @@ def infer_arm(args, world, rank, local, n_tasks, warmup, profile=True):
     def run(_):
         res["pred"] = model.predict(tasks, **kw)
 
+    from deepsensornz_b200.predict import _result_pool as _pool
     model.predict(tasks[:3], **kw)
     ms_first = timed(run, 1)
     res.clear()
     run(0)              # second call of this size: the pool page-locks the recycled arrays (once)
     res.clear()
-    ms_e2e = timed(run, 1)
+    # three timed calls, the median reported (all three listed): on the shared host of a GPU box a single call now and
+    # then stalls for tens of milliseconds in the driver or the kernel (seen as 3-5 ms per date outliers)
+    calls = []
+    for _ in range(3):
+        res.clear()
+        calls.append(timed(run, 1))
+    ms_e2e = sorted(calls)[1]
     key = list(res["pred"].keys())[0]
     mean = np.asarray(res["pred"][key]["mean"])
     assert mean.shape == (n_tasks, 1400, 1400) and np.isfinite(mean).all()
@@ -534,6 +541,8 @@ def infer_arm(args, world, rank, local, n_tasks, warmup, profile=True):
     out["e2e"] = {"value": world * n_tasks / (ms_e2e * 1e-3), "unit": "tasks/s", "h2d_bytes_per_step": per_task_h2d,
                   "d2h_bytes_per_step": 2 * 1400 * 1400 * 4, "ms_per_step": ms_e2e / n_tasks,
                   "first_call_ms_per_step": ms_first / n_tasks,
+                  "timed_calls_ms_per_step": [c / n_tasks for c in calls], "reported": "median of the three timed calls",
+                  "result_pool": {"hits": _pool.hits, "misses": _pool.misses, "page_locked_arrays": len(_pool._pinned)},
                   "result_arrays": "third call of this size: result arrays recycled from the previous (dropped) result and "
                                    "page-locked, so every read-back is one DMA into the array the caller receives; "
                                    "first_call_ms_per_step is the same call on freshly allocated pageable arrays",
