@@ -348,12 +348,16 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     const int m = q * 32 + lane;
     const int g = m >> 6;
     const int ch = a.wide ? m : (m & 63);                    // output channel of this thread (TMEM lane)
-    const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (q & 1) * 4);   // first of this warp's 4 output chunks
+    // x-phase pairs: the 32 lanes of a quadrant are [16 channels of x-phase 0 | the same 16 channels of x-phase 1] (see
+    // pack2_kernel), so that a thread ends up with BOTH output pixels 2x, 2x+1 of two chunks: 32 B stores / loads
+    const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (a.pxpair ? q * 2 : (q & 1) * 4));   // first output chunk of this warp
     const float bias_v = a.bias ? __ldg(a.bias + ch) : 0.f;
     // bias of the four channels this thread holds in the fragment distribution: warp channel base + lane/4 + {0,8,16,24}
     float bias4[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) bias4[i] = a.bias ? __ldg(a.bias + (ch - lane) + (lane >> 2) + 8 * i) : 0.f;
+    for (int i = 0; i < 4; ++i)
+      bias4[i] = !a.bias ? 0.f : (a.pxpair ? __ldg(a.bias + 16 * q + (lane >> 2) + 8 * (i & 1))
+                                           : __ldg(a.bias + (ch - lane) + (lane >> 2) + 8 * i));
     uint32_t* my_stg = stg + ew * stg_words;
     const long long oplane = (long long)a.out_Hp * a.out_Wp;
     const int ncb = a.N >> 5;
@@ -371,9 +375,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
           const int y = y0 + j * a.rpa + ((a.wide || a.pxpair) ? 0 : g);
           if (y >= a.H || xs >= a.TW || x0 + xs >= a.W) continue;
           const int xx = min(x0 + xs + lane, a.W - 1);
-          const long long pix = (long long)(y * a.sy + a.ay + 2) * a.out_Wp + (xx * a.sx + a.ax + (a.pxpair ? g : 0) + 2);
+          const long long pix = (long long)(y * a.sy + a.ay + 2) * a.out_Wp + (xx * a.sx + a.ax + 2);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
+            if (a.pxpair && c >= 2) break;
             if (a.mask)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mask + (long long)b * a.mask_bs +
                            ((long long)(a.mask_cb_off + chunk0 - a.out_c_off + c) * oplane + pix) * 8));
@@ -493,8 +498,48 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             for (int i = 0; i < 16; ++i) xacc ^= wv[i];
             if (xacc == 0x12345678u) a.dbg[0] = 1;
             continue; }
-          if (lane < nvalid) {
-            const int ox = (x0 + xs + lane) * a.sx + a.ax + (a.pxpair ? g : 0);
+          if (a.pxpair) {
+            // wv = [x-phase 0: chunk0, chunk0+1 | x-phase 1: chunk0, chunk0+1]; output pixels 2x and 2x+1 of a chunk are
+            // 32 contiguous bytes: one 256-bit access per chunk for the mask, the accumulate target and the store
+            if (lane < nvalid) {
+              const int ox = (x0 + xs + lane) * a.sx + a.ax;
+              const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
+              __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
+                                     ((long long)chunk0 * oplane + pix) * 8;
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t v8[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { v8[i] = wv[4 * c + i]; v8[4 + i] = wv[8 + 4 * c + i]; }
+                if (a.mask) {
+                  uint32_t mk[8];
+                  tc::ldg256_nc(a.mask + (long long)b * a.mask_bs +
+                                ((long long)(a.mask_cb_off + chunk0 - a.out_c_off + c) * oplane + pix) * 8, mk);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float2 mf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mk[i]));
+                    uint32_t keep = 0;
+                    if (mf.x > 0.f) keep |= 0x0000ffffu;
+                    if (mf.y > 0.f) keep |= 0xffff0000u;
+                    v8[i] &= keep;
+                  }
+                }
+                if (a.accumulate) {
+                  uint32_t old[8];
+                  tc::ld256(obase + (long long)c * oplane * 8, old);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
+                    const float2 nf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v8[i]));
+                    const __nv_bfloat162 r = __floats2bfloat162_rn(of.x + nf.x, of.y + nf.y);
+                    v8[i] = *reinterpret_cast<const uint32_t*>(&r);
+                  }
+                }
+                tc::st256(obase + (long long)c * oplane * 8, v8);
+              }
+            }
+          } else if (lane < nvalid) {
+            const int ox = (x0 + xs + lane) * a.sx + a.ax;
             const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
                                    ((long long)chunk0 * oplane + pix) * 8;
@@ -569,7 +614,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 //   transposed (dgrad): "output channel" indexes the conv's INPUT channels and k its OUTPUT channels.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transposed, int wide, int co_off,
+pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transposed, int wide, int pxpair, int co_off,
              __nv_bfloat16* __restrict__ wpk, const __grid_constant__ cnp_c2_plan plan, int total_pos,
              long long group_stride /* elements between the weight tensors of lane groups 0 and 1 (0: the same tensor) */,
              long long wsel_stride /* elements between the stacked weight tensors selected per K block (plan.kb_wsel) */) {
@@ -589,7 +634,9 @@ pack2_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int transpos
     const int c = (int)(e & 7), m = (int)((e >> 3) & 127), k8 = (int)((e >> 10) & 1);
     const int kb = pos_kb[e >> 11], gp = pos_lp[e >> 11];
     const int type = plan.kb_type[kb];
-    const int g = m >> 6, n = m & 63;
+    // PAIR: m = 64 g + n.  x-phase pairs: every 32-lane quadrant holds [16 channels of group 0 | the same of group 1], so
+    // that an epilogue thread owns both x-phases of its pixel (conv_tc2_kernel)
+    const int g = pxpair ? (m >> 4) & 1 : m >> 6, n = pxpair ? (m >> 5) * 16 + (m & 15) : m & 63;
     const int ky = plan.t_tap[type][gp][wide ? 0 : 2 * g], kx = plan.t_tap[type][gp][wide ? 1 : 2 * g + 1];
     float v = 0.f;
     if (ky >= 0) {
@@ -852,7 +899,8 @@ CNP_API int cnp_conv_tc2_pack(const float* w, int Cout, int Cin, int k, int kind
               "conv_tc2_pack: the up-phase kinds pack 4x4 phase weights ([2][Cout][Cin][4][4] of one row phase / all four)");
   const int transposed = ((kind >= KIND_K5S1_DGRAD && kind <= KIND_K5S2_DGRAD) || kind == KIND_UP_PHASE_DGRAD) ? 1 : 0;
   const int pack_blocks = total_pos * 2048 / (256 * 4) < 128 ? 128 : (total_pos * 2048 / (256 * 4) > 592 ? 592 : total_pos * 2048 / (256 * 4));
-  pack2_kernel<<<pack_blocks, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, co_off,
+  const int pxpair = ((kind == KIND_K5S2_DGRAD && px == 2) || kind == KIND_UP_PHASE) ? 1 : 0;
+  pack2_kernel<<<pack_blocks, 256, 0, st>>>(w, Cout, Cin, k, transposed, n_out == 128, pxpair, co_off,
                                     reinterpret_cast<__nv_bfloat16*>(wpk), p, total_pos,
                                     kind == KIND_UP_PHASE ? (long long)Cout * Cin * 16 : 0ll,
                                     kind == KIND_UP_PHASE_DGRAD ? (long long)Cout * Cin * 16 : 0ll);
