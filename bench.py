@@ -423,7 +423,7 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
             ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
             tot_ms = sum(v["ms"] for v in prof.values())
             traffic = None     # DRAM bytes per launch from the committed ncu pass of the same command
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
             if os.path.exists(tpath) and args.internal_density == PPU and tuple(dim_yc) == DIM_YC:
                 with open(tpath) as f:
                     traffic = json.load(f).get("conv_tc2_kernel", {}).get("dram_bytes_per_launch")
@@ -433,6 +433,8 @@ def train_arm(args, world, rank, local, dim_yc, steps, warmup, profile=True, e2e
                                "traffic": traffic,
                                "peak_source": f"{pk['source']}: bf16_tflops (burst -- the kernel is timed per launch with "
                                               "CUDA events in a serial pass)",
+                               "flops_counted": "as issued: the polyphase launches count their 4x4-tap phase convolutions, not "
+                                                "the 5x5 taps on the upsampled tensor they replace (1.56x more)",
                                "share_of_step": d["ms"] / tot_ms, "avg_launch_ms": d["ms"] / d["launches"],
                                "flops_per_launch": d["flops"] / d["launches"]}
         out["kernels"] = kernel_table(prof, 2, pk)
