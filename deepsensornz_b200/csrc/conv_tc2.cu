@@ -84,6 +84,14 @@ constexpr int C2_THREADS = 32 * (4 + C2_EPI_WARPS);
 constexpr int C2_STG_WORDS_BF16 = 32 * 20;               // per-warp transpose buffer [32 px][64 B of channels + 16 B pad]
 constexpr int C2_STG_WORDS_F32 = 32 * 36;                // fp32 output: [32 ch][36 floats]
 
+// ReLU-backward keep mask of a packed bf16 pair: 0xffff per half whose value is > 0 (non-zero magnitude, sign clear).
+// Integer form, both halves at once: 5 instructions per word instead of two conversions, two compares and two selects --
+// the mask arithmetic sits on the critical path of an epilogue warp (3 warps per scheduler, little to overlap with).
+__device__ __forceinline__ uint32_t relu_keep(uint32_t w) {
+  const uint32_t nz = ((w & 0x7fff7fffu) + 0x7fff7fffu) & 0x80008000u;   // bit 15 / 31: magnitude != 0
+  return ((nz & ~w) >> 15) * 0xffffu;
+}
+
 struct c2_work { int b, y0, x0, nacc; };
 __device__ __forceinline__ c2_work decode_work(const cnp_c2_args& a, int w) {
   int tile = w, j = 0;
@@ -516,13 +524,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
                   tc::ldg256_nc(a.mask + (long long)b * a.mask_bs +
                                 ((long long)(a.mask_cb_off + chunk0 - a.out_c_off + c) * oplane + pix) * 8, mk);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float2 mf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mk[i]));
-                    uint32_t keep = 0;
-                    if (mf.x > 0.f) keep |= 0x0000ffffu;
-                    if (mf.y > 0.f) keep |= 0xffff0000u;
-                    v8[i] &= keep;
-                  }
+                  for (int i = 0; i < 8; ++i) v8[i] &= relu_keep(mk[i]);
                 }
                 if (a.accumulate) {
                   uint32_t old[8];
@@ -549,15 +551,8 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const uint4 mk = __ldg(reinterpret_cast<const uint4*>(mbase + (long long)c * oplane * 8));
-                const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mk);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 mf = __bfloat1622float2(m2[i]);
-                  uint32_t keep = 0;
-                  if (mf.x > 0.f) keep |= 0x0000ffffu;
-                  if (mf.y > 0.f) keep |= 0xffff0000u;
-                  wv[c * 4 + i] &= keep;
-                }
+                wv[c * 4] &= relu_keep(mk.x); wv[c * 4 + 1] &= relu_keep(mk.y);
+                wv[c * 4 + 2] &= relu_keep(mk.z); wv[c * 4 + 3] &= relu_keep(mk.w);
               }
             }
             if (a.accumulate) {
