@@ -944,10 +944,15 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   // Opt-in (CNP_DOUBLE_ACC=1): measured on B200 it LOSES wherever the model picks it -- masked WIDE dgrad at 304^2 503 ->
   // 743 us, stride-2 dgrad phases 127 -> 373 us / 45 -> 155 us -- because a set of <= 256 columns means one accumulator of
   // N = 160, and every tile re-streams the whole packed weight tensor from L2 for a third of the MMAs: the weight stream,
-  // not the epilogue, bounds short tiles (same finding as the two-round tail split above).
-  static const bool nbuf2 = getenv("CNP_DOUBLE_ACC") != nullptr;
+  // not the epilogue, bounds short tiles (same finding as the two-round tail split above).  CNP_DOUBLE_ACC=narrow restricts it to the folded first layer
+  // (one K block: N = 64 x 4 accumulators x 2 sets is chosen, 137 against 127 us).
+  static const char* nbuf2_env = getenv("CNP_DOUBLE_ACC");
+  const bool nbuf2 = nbuf2_env != nullptr && (strcmp(nbuf2_env, "narrow") != 0 || a.plan.n_kb == 1);
   choose_geometry(&a, plan_total_pos(a.plan), 18.0 + (o->mode == 0 && o->mask ? 30.0 : 0.0) + (o->accumulate ? 40.0 : 0.0),
                   nbuf2);
+  if (getenv("CNP_C2_VERBOSE"))
+    fprintf(stderr, "conv_tc2 kind %d chunks %d %dx%d: N %d nacc %d nbuf %d tiles %d\n", kind, n_chunks, a.H, a.W, a.N, a.nacc,
+            a.nbuf, B * a.tiles_x * a.tiles_y);
   CNP_REQUIRE(a.N > 0, "conv_tc2: no tile geometry for %d x %d", a.H, a.W);
   if (int e = build_plan2(kind, n_chunks, a.pitch, py, px, a.wide, &a.plan)) return e;
   a.out_mode = o->mode;
