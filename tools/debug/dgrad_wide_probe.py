@@ -24,14 +24,17 @@ nb2 = _cabi.lib().cnp_conv_tc2_packed_bytes(K, 8, 128)
 wp2 = torch.empty(nb2 // 2, dtype=torch.bfloat16, device=dev)
 _cabi.call("cnp_conv_tc2_pack", wt.data_ptr(), 64, 128, 5, K, 8, 0, 0, 0, 128, wp2.data_ptr(), S())
 fl = 2.0 * B * H * H * 64 * 128 * 25
-for name in ("plain", "mask", "mask+s2d"):
-    o = out_blk(dx.view(0), mask=act.view(0) if name != "plain" else None)
+for name in ("plain", "mask", "mask(L2-resident: one image shared by the batch)", "mask+s2d"):
+    mv = act.view(0)
+    if "L2" in name:
+        mv.bstride = 0
+    o = out_blk(dx.view(0), mask=mv if name != "plain" else None)
     if name == "mask+s2d":
         sv = s2d.view()
         o.s2d, o.s2d_c0, o.s2d_band = C.pointer(sv), 8, 2
     run = lambda: _cabi.call("cnp_conv_tc2", C.byref(dy.view()), 8, wp2.data_ptr(), K, 0, 0, 128, C.byref(o), B, S())
     t = timeit(run)
-    print(f"{name:9s}: {t * 1e3:7.1f} us  {fl / t / 1e9:7.1f} TF")
+    print(f"{name:12s}: {t * 1e3:7.1f} us  {fl / t / 1e9:7.1f} TF")
     for flags in (0, 1, 2):
         dbg = torch.zeros(148, 8, dtype=torch.int64, device=dev)
         _cabi.call("cnp_conv_tc2_debug", dbg.data_ptr(), flags)
