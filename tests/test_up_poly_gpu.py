@@ -19,6 +19,11 @@ from tests.util import rel_err, small_model
 pytestmark = pytest.mark.gpu
 
 
+def _slack_is_zero(blk):
+    """nothing was written past the last image of a blocked buffer (its allocation carries a zeroed over-read slack)"""
+    return float(blk.t[blk.B * blk.bstride:].abs().max()) == 0
+
+
 def _up(x):
     return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
 
@@ -42,6 +47,7 @@ def test_strips_of_the_upsampled_tensor(c, h, w):
     r_ref, c_ref = _strip_views(_up(x.double()), B, 2 * h, 2 * w)
     assert rel_err(_from_blk(rows, c), r_ref) < 4e-3 and rel_err(_from_blk(cols, c), c_ref) < 4e-3
     assert _pad_is_zero(rows, 2 * B, c // 8, 6, 2 * w) and _pad_is_zero(cols, 2 * B, c // 8, 6, 2 * h)
+    assert _slack_is_zero(rows) and _slack_is_zero(cols)
     # the same bf16 values as the full upsampling kernel (the band must not depend on which path produced it)
     full = _Blk(B, c // 8, 2 * h, 2 * w, x.device)
     _cabi.call("cnp_blk_upsample2x_fwd", C.byref(xb.view()), c // 8, C.byref(full.view()), B, _S())
@@ -74,6 +80,8 @@ def test_dy_split_partitions_every_pixel_once(h, w):
     back[:, :, :, :6] += c[:B].transpose(2, 3); back[:, :, :, 2 * w - 6:] += c[B:].transpose(2, 3)
     assert torch.equal(back, dy)
     assert _pad_is_zero(s2d, B, 32, h, w)
+    assert _slack_is_zero(s2d) and _slack_is_zero(rows) and _slack_is_zero(cols)
+    assert _pad_is_zero(rows, 2 * B, 8, 6, 2 * w) and _pad_is_zero(cols, 2 * B, 8, 6, 2 * h)
 
 
 @pytest.mark.parametrize("h,w", [(8, 8), (19, 23), (38, 12)])
@@ -202,6 +210,12 @@ def test_up_poly_layer_forward_backward(h, w):
     assert rel_err(gw, dw_ref) < 1e-2
     assert rel_err(gb, db_ref) < 1e-3
     assert _pad_is_zero(dxb, B, 16, h, w)
+    assert _slack_is_zero(dxb) and _slack_is_zero(dst)
+    for k, blk in eng._ws.items():                      # every strip / space-to-depth workspace of the level
+        if isinstance(blk, _Blk) and str(k[0]).startswith(f"t{h}x{w}."):
+            assert _slack_is_zero(blk), k
+            if ".dy" in str(k[0]) or ".dys2d" in str(k[0]):
+                assert _pad_is_zero(blk, blk.B, blk.CB, blk.H, blk.W), k
     # the path it replaces, same inputs: upsample kernel + standard conv / dgrad / wgrad
     up = _Blk(B, 16, 2 * h, 2 * w, x.device)
     _cabi.call("cnp_blk_upsample2x_fwd", C.byref(xb.view()), 16, C.byref(up.view()), B, _S())
