@@ -369,31 +369,45 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     uint32_t* my_stg = stg + ew * stg_words;
     const long long oplane = (long long)a.out_Hp * a.out_Wp;
     const int ncb = a.N >> 5;
+    // The epilogue is instruction-bound (ncu: 0.7 warp instructions per scheduler per cycle), so its index arithmetic is
+    // kept off the per-item path: this warp's items (accumulator j, column block cb) are STEPPED -- h, h+3, h+6 ... of
+    // nacc x ncb, the same sequence for every tile -- instead of divided out of an item index, and every global address is
+    // a per-tile 64-bit base of this thread plus a 32-bit element offset of the item.
+    const int it_j0 = h / ncb, it_cb0 = h - it_j0 * ncb;
+    const int it_dj = (C2_EPI_WARPS / 4) / ncb, it_dcb = (C2_EPI_WARPS / 4) - it_dj * ncb;
+    const int gsel = (a.wide || a.pxpair) ? 0 : g;                      // PAIR: lane group = second row of the accumulator
+    const int row_eoff = a.rpa * a.sy * a.out_Wp * 8;                   // element offset between accumulators (rows)
+    const int col_eoff = 32 * a.sx * 8;                                 // ... between column blocks
+    const int cplane = (int)(oplane * 8);                               // ... between chunk planes
     uint32_t t_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t_it) {
       const c2_work wk = decode_work(a, tile);
       const int b = wk.b, y0 = wk.y0, x0 = wk.x0;
+      // per-tile bases of this thread (pixel x0 + lane of row y0 [+ lane group], chunk chunk0)
+      const long long pix_t = (long long)((y0 + gsel) * a.sy + a.ay + 2) * a.out_Wp + ((x0 + lane) * a.sx + a.ax + 2);
+      __nv_bfloat16* const obase_t = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
+                                     ((long long)chunk0 * oplane + pix_t) * 8;
+      const __nv_bfloat16* const mbase_t = a.mask ? a.mask + (long long)b * a.mask_bs +
+          ((long long)(a.mask_cb_off + chunk0 - a.out_c_off) * oplane + pix_t) * 8 : nullptr;
       if (a.out_mode == 0 && (a.mask || a.accumulate)) {
         // The MMAs of this tile are still running and these warps would only wait: pull the ReLU-mask (and the
         // accumulate target) lines of the tile into L2 now, so the epilogue's loads are not DRAM round trips issued
         // while the tensor pipe is idle (masked WIDE dgrad at 304^2: 555 us against 444 us unmasked before this).
-        const int n_it = wk.nacc * ncb;
-        for (int item = h; item < n_it; item += C2_EPI_WARPS / 4) {
-          const int j = item / ncb, xs = (item - j * ncb) * 32;
-          const int y = y0 + j * a.rpa + ((a.wide || a.pxpair) ? 0 : g);
-          if (y >= a.H || xs >= a.TW || x0 + xs >= a.W) continue;
-          const int xx = min(x0 + xs + lane, a.W - 1);
-          const long long pix = (long long)(y * a.sy + a.ay + 2) * a.out_Wp + (xx * a.sx + a.ax + 2);
+        for (int j = it_j0, cb = it_cb0; j < wk.nacc;) {
+          const int xs = cb * 32;
+          if (y0 + j * a.rpa + gsel < a.H && xs < a.TW && x0 + xs < a.W) {
+            // lanes past the image edge prefetch the last valid pixel's line
+            const int over = x0 + xs + lane - (a.W - 1);
+            const int eoff = j * row_eoff + cb * col_eoff - (over > 0 ? over * a.sx * 8 : 0);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (a.pxpair && c >= 2) break;
-            if (a.mask)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mask + (long long)b * a.mask_bs +
-                           ((long long)(a.mask_cb_off + chunk0 - a.out_c_off + c) * oplane + pix) * 8));
-            if (a.accumulate)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(a.out) +
-                           (long long)b * a.out_bs + ((long long)(chunk0 + c) * oplane + pix) * 8));
+            for (int c = 0; c < 4; ++c) {
+              if (a.pxpair && c >= 2) break;
+              if (a.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(mbase_t + eoff + c * cplane));
+              if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(obase_t + eoff + c * cplane));
+            }
           }
+          cb += it_dcb; j += it_dj;
+          if (cb >= ncb) { cb -= ncb; ++j; }
         }
       }
       const uint32_t abuf = a.nbuf > 1 ? (t_it & 1u) : 0u;
@@ -401,13 +415,13 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       tc::mbar_wait(acc_full + abuf, a.nbuf > 1 ? ((t_it >> 1) & 1u) : (t_it & 1u));
       const long long te0 = a.dbg ? clock64() : 0;
       tc::fence_after_sync();
-      const int n_items = wk.nacc * ncb;
-      for (int item = h; item < n_items; item += C2_EPI_WARPS / 4) {
-        const int j = item / ncb, cb = item - j * ncb;
-        const int ty = j * a.rpa + ((a.wide || a.pxpair) ? 0 : g);
-        const int y = y0 + ty;
+      for (int j = it_j0, cb = it_cb0, jn, cbn; j < wk.nacc; j = jn, cb = cbn) {
+        cbn = cb + it_dcb; jn = j + it_dj;
+        if (cbn >= ncb) { cbn -= ncb; ++jn; }
+        const int y = y0 + j * a.rpa + gsel;
         if (y >= a.H) continue;                              // warp-uniform
         const int oy = y * a.sy + a.ay;
+        const int eoff = j * row_eoff + cb * col_eoff;       // this item's element offset from the per-tile bases
         {
           const int xs = cb * 32;
           if (xs >= a.TW || x0 + xs >= a.W) continue;        // warp-uniform
@@ -434,10 +448,14 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               float f[8];
-              f[0] = __uint_as_float(ra[4 * k]) + bias4[0];     f[1] = __uint_as_float(ra[4 * k + 1]) + bias4[0];
-              f[2] = __uint_as_float(ra[4 * k + 2]) + bias4[1]; f[3] = __uint_as_float(ra[4 * k + 3]) + bias4[1];
-              f[4] = __uint_as_float(rb[4 * k]) + bias4[2];     f[5] = __uint_as_float(rb[4 * k + 1]) + bias4[2];
-              f[6] = __uint_as_float(rb[4 * k + 2]) + bias4[3]; f[7] = __uint_as_float(rb[4 * k + 3]) + bias4[3];
+              f[0] = __uint_as_float(ra[4 * k]);     f[1] = __uint_as_float(ra[4 * k + 1]);
+              f[2] = __uint_as_float(ra[4 * k + 2]); f[3] = __uint_as_float(ra[4 * k + 3]);
+              f[4] = __uint_as_float(rb[4 * k]);     f[5] = __uint_as_float(rb[4 * k + 1]);
+              f[6] = __uint_as_float(rb[4 * k + 2]); f[7] = __uint_as_float(rb[4 * k + 3]);
+              if (a.bias) {                          // (the input gradients have none: 32 FADDs per item less)
+                f[0] += bias4[0]; f[1] += bias4[0]; f[2] += bias4[1]; f[3] += bias4[1];
+                f[4] += bias4[2]; f[5] += bias4[2]; f[6] += bias4[3]; f[7] += bias4[3];
+              }
               if (a.relu) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -510,10 +528,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             // wv = [x-phase 0: chunk0, chunk0+1 | x-phase 1: chunk0, chunk0+1]; output pixels 2x and 2x+1 of a chunk are
             // 32 contiguous bytes: one 256-bit access per chunk for the mask, the accumulate target and the store
             if (lane < nvalid) {
-              const int ox = (x0 + xs + lane) * a.sx + a.ax;
-              const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
-              __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
-                                     ((long long)chunk0 * oplane + pix) * 8;
+              __nv_bfloat16* obase = obase_t + eoff;
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 uint32_t v8[8];
@@ -521,14 +536,13 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
                 for (int i = 0; i < 4; ++i) { v8[i] = wv[4 * c + i]; v8[4 + i] = wv[8 + 4 * c + i]; }
                 if (a.mask) {
                   uint32_t mk[8];
-                  tc::ldg256_nc(a.mask + (long long)b * a.mask_bs +
-                                ((long long)(a.mask_cb_off + chunk0 - a.out_c_off + c) * oplane + pix) * 8, mk);
+                  tc::ldg256_nc(mbase_t + eoff + c * cplane, mk);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v8[i] &= relu_keep(mk[i]);
                 }
                 if (a.accumulate) {
                   uint32_t old[8];
-                  tc::ld256(obase + (long long)c * oplane * 8, old);
+                  tc::ld256(obase + c * cplane, old);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
@@ -537,20 +551,16 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
                     v8[i] = *reinterpret_cast<const uint32_t*>(&r);
                   }
                 }
-                tc::st256(obase + (long long)c * oplane * 8, v8);
+                tc::st256(obase + c * cplane, v8);
               }
             }
           } else if (lane < nvalid) {
-            const int ox = (x0 + xs + lane) * a.sx + a.ax;
-            const long long pix = (long long)(oy + 2) * a.out_Wp + (ox + 2);
-            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
-                                   ((long long)chunk0 * oplane + pix) * 8;
+            __nv_bfloat16* obase = obase_t + eoff;
             if (a.mask) {
-              const __nv_bfloat16* mbase = a.mask + (long long)b * a.mask_bs +
-                                           ((long long)(a.mask_cb_off + chunk0 - a.out_c_off) * oplane + pix) * 8;
+              const __nv_bfloat16* mbase = mbase_t + eoff;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const uint4 mk = __ldg(reinterpret_cast<const uint4*>(mbase + (long long)c * oplane * 8));
+                const uint4 mk = __ldg(reinterpret_cast<const uint4*>(mbase + c * cplane));
                 wv[c * 4] &= relu_keep(mk.x); wv[c * 4 + 1] &= relu_keep(mk.y);
                 wv[c * 4 + 2] &= relu_keep(mk.z); wv[c * 4 + 3] &= relu_keep(mk.w);
               }
@@ -558,7 +568,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             if (a.accumulate) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const uint4 old = *reinterpret_cast<const uint4*>(obase + (long long)c * oplane * 8);
+                const uint4 old = *reinterpret_cast<const uint4*>(obase + c * cplane);
                 const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -571,9 +581,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(obase + (long long)c * oplane * 8) =
+              *reinterpret_cast<uint4*>(obase + c * cplane) =
                   make_uint4(wv[c * 4], wv[c * 4 + 1], wv[c * 4 + 2], wv[c * 4 + 3]);
             const int sc0 = chunk0 - a.out_c_off - a.s2d_c0;     // WIDE: only the quadrants holding chunks s2d_c0 .. +7
+            const int ox = (x0 + xs + lane) * a.sx + a.ax;
             if (a.s2d && sc0 >= 0 && sc0 < 8 && (oy >> 1) >= a.s2d_band && (oy >> 1) < (a.H >> 1) - a.s2d_band &&
                 (ox >> 1) >= a.s2d_band && (ox >> 1) < (a.W >> 1) - a.s2d_band) {
               // phase plane p = (y&1)*2 + (x&1) holds pixel (y/2, x/2): the input layout of the next stride-2 layer
