@@ -133,7 +133,13 @@ __device__ __forceinline__ void issue_row_n(int nacc, uint32_t tmem, uint32_t w_
 
 // CL = true: instantiation with the cluster / multicast code.  A kernel that contains cluster instructions is scheduled
 // differently even in a plain launch (measured ~15 % slower on the wgrad kernel), hence two instantiations.
-template <bool CL>
+// EPI: epilogue specialisation.  The epilogue is sensitive to every instruction and live register (adding code it never
+// executed slowed the unmasked WIDE dgrad by 5 %), so the hot configurations get their flags as compile-time constants:
+//   0 generic (every flag read at run time: fp32 output, debug counters, anything else)
+//   1 blocked bf16 output, no mask, no accumulate, no x-phase pair   (forward layers)
+//   2 blocked bf16 output, ReLU mask, no accumulate, no x-phase pair (input gradients of the decoder levels)
+//   3 blocked bf16 output, x-phase pair (polyphase forward; stride-2 input gradients: mask / accumulate at run time)
+template <bool CL, int EPI>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   const int a_cluster = CL ? a.cluster : 1;
@@ -350,6 +356,13 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue ==============================================================
+    constexpr bool EG = EPI == 0;
+    const bool f_mode0 = EG ? a.out_mode == 0 : true;                       // blocked bf16 output
+    const bool f_px = EG ? a.pxpair != 0 : EPI == 3;
+    const bool f_mask = (EG || EPI == 3) ? a.mask != nullptr : EPI == 2;
+    const bool f_acc = (EG || EPI == 3) ? a.accumulate != 0 : false;
+    const int f_dbgf = EG ? a.dbg_flags : 0;
+    long long* const f_dbg = EG ? a.dbg : nullptr;
     const int ew = warp - 4;
     const int q = warp & 3;           // TMEM lane quadrant this warp may read
     const int h = ew >> 2;            // this quadrant's (accumulator, column block) items are dealt round-robin to its warps
@@ -358,13 +371,13 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     const int ch = a.wide ? m : (m & 63);                    // output channel of this thread (TMEM lane)
     // x-phase pairs: the 32 lanes of a quadrant are [16 channels of x-phase 0 | the same 16 channels of x-phase 1] (see
     // pack2_kernel), so that a thread ends up with BOTH output pixels 2x, 2x+1 of two chunks: 32 B stores / loads
-    const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (a.pxpair ? q * 2 : (q & 1) * 4));   // first output chunk of this warp
+    const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (f_px ? q * 2 : (q & 1) * 4));   // first output chunk of this warp
     const float bias_v = a.bias ? __ldg(a.bias + ch) : 0.f;
     // bias of the four channels this thread holds in the fragment distribution: warp channel base + lane/4 + {0,8,16,24}
     float bias4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      bias4[i] = !a.bias ? 0.f : (a.pxpair ? __ldg(a.bias + 16 * q + (lane >> 2) + 8 * (i & 1))
+      bias4[i] = !a.bias ? 0.f : (f_px ? __ldg(a.bias + 16 * q + (lane >> 2) + 8 * (i & 1))
                                            : __ldg(a.bias + (ch - lane) + (lane >> 2) + 8 * i));
     uint32_t* my_stg = stg + ew * stg_words;
     const long long oplane = (long long)a.out_Hp * a.out_Wp;
@@ -375,7 +388,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     // a per-tile 64-bit base of this thread plus a 32-bit element offset of the item.
     const int it_j0 = h / ncb, it_cb0 = h - it_j0 * ncb;
     const int it_dj = (C2_EPI_WARPS / 4) / ncb, it_dcb = (C2_EPI_WARPS / 4) - it_dj * ncb;
-    const int gsel = (a.wide || a.pxpair) ? 0 : g;                      // PAIR: lane group = second row of the accumulator
+    const int gsel = (a.wide || f_px) ? 0 : g;                      // PAIR: lane group = second row of the accumulator
     const int row_eoff = a.rpa * a.sy * a.out_Wp * 8;                   // element offset between accumulators (rows)
     const int col_eoff = 32 * a.sx * 8;                                 // ... between column blocks
     const int cplane = (int)(oplane * 8);                               // ... between chunk planes
@@ -387,9 +400,9 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       const long long pix_t = (long long)((y0 + gsel) * a.sy + a.ay + 2) * a.out_Wp + ((x0 + lane) * a.sx + a.ax + 2);
       __nv_bfloat16* const obase_t = reinterpret_cast<__nv_bfloat16*>(a.out) + (long long)b * a.out_bs +
                                      ((long long)chunk0 * oplane + pix_t) * 8;
-      const __nv_bfloat16* const mbase_t = a.mask ? a.mask + (long long)b * a.mask_bs +
+      const __nv_bfloat16* const mbase_t = f_mask ? a.mask + (long long)b * a.mask_bs +
           ((long long)(a.mask_cb_off + chunk0 - a.out_c_off) * oplane + pix_t) * 8 : nullptr;
-      if (a.out_mode == 0 && (a.mask || a.accumulate)) {
+      if (f_mode0 && (f_mask || f_acc)) {
         // The MMAs of this tile are still running and these warps would only wait: pull the ReLU-mask (and the
         // accumulate target) lines of the tile into L2 now, so the epilogue's loads are not DRAM round trips issued
         // while the tensor pipe is idle (masked WIDE dgrad at 304^2: 555 us against 444 us unmasked before this).
@@ -401,9 +414,9 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             const int eoff = j * row_eoff + cb * col_eoff - (over > 0 ? over * a.sx * 8 : 0);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              if (a.pxpair && c >= 2) break;
-              if (a.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(mbase_t + eoff + c * cplane));
-              if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(obase_t + eoff + c * cplane));
+              if (f_px && c >= 2) break;
+              if (f_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(mbase_t + eoff + c * cplane));
+              if (f_acc) asm volatile("prefetch.global.L2 [%0];" ::"l"(obase_t + eoff + c * cplane));
             }
           }
           cb += it_dcb; j += it_dj;
@@ -413,7 +426,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       const uint32_t abuf = a.nbuf > 1 ? (t_it & 1u) : 0u;
       const uint32_t tmem_acc = tmem_base + abuf * 256u;
       tc::mbar_wait(acc_full + abuf, a.nbuf > 1 ? ((t_it >> 1) & 1u) : (t_it & 1u));
-      const long long te0 = a.dbg ? clock64() : 0;
+      const long long te0 = f_dbg ? clock64() : 0;
       tc::fence_after_sync();
       for (int j = it_j0, cb = it_cb0, jn, cbn; j < wk.nacc; j = jn, cb = cbn) {
         cbn = cb + it_dcb; jn = j + it_dj;
@@ -427,7 +440,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
           if (xs >= a.TW || x0 + xs >= a.W) continue;        // warp-uniform
           const int nvalid = min(min(a.TW - xs, a.W - x0 - xs), 32);   // valid pixels of this block
           uint32_t wv[16];
-          if (a.out_mode == 0) {
+          if (f_mode0) {
             // ---- blocked bf16: [channel = TMEM lane][pixel] -> [pixel = thread][32 channels] ----
             // The accumulator block is read in the mma-fragment distribution (two 16-lane halves), bias / ReLU are
             // applied, pairs are packed to bf16 and four stmatrix.x4.trans write the block transposed into shared
@@ -439,10 +452,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             tc::tmem_ld_16x256b_x4(t0, ra);
             tc::tmem_ld_16x256b_x4(t0 + (16u << 16), rb);
             tc::tmem_ld_wait();
-            if (a.dbg_flags & 1) { uint32_t xacc = 0;
+            if (f_dbgf & 1) { uint32_t xacc = 0;
 #pragma unroll
               for (int i = 0; i < 16; ++i) xacc ^= ra[i] ^ rb[i];
-              if (xacc == 0x12345678u) a.dbg[0] = 1;
+              if (xacc == 0x12345678u) f_dbg[0] = 1;
               continue; }
             const uint32_t srow = tc::smem_u32(my_stg) + (uint32_t)(lane & 7) * 80u + (uint32_t)(lane >> 3) * 16u;
 #pragma unroll
@@ -479,10 +492,10 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
           float v[32];
           tc::tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * a.N + xs), v);
           tc::tmem_ld_wait();
-          if (a.dbg_flags & 1) { float sacc = 0.f;
+          if (f_dbgf & 1) { float sacc = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) sacc += v[i];
-            if (sacc == 1.2345e-30f) a.dbg[0] = 1;
+            if (sacc == 1.2345e-30f) f_dbg[0] = 1;
             continue; }
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -506,25 +519,25 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
               const int c = k * 4 + (lane >> 3);
               const float4 val = *reinterpret_cast<const float4*>(stf + c * 36 + px4);
               float* dst = dst0 + c * cstride;
-              if (px4 + 3 < nvalid && !a.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              if (px4 + 3 < nvalid && !f_acc && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 *reinterpret_cast<float4*>(dst) = val;
               } else {
                 const float vv[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (px4 + i < nvalid) dst[i] = a.accumulate ? dst[i] + vv[i] : vv[i];
+                  if (px4 + i < nvalid) dst[i] = f_acc ? dst[i] + vv[i] : vv[i];
               }
             }
             __syncwarp();
             continue;
           }
           }
-          if (a.dbg_flags & 2) { uint32_t xacc = 0;
+          if (f_dbgf & 2) { uint32_t xacc = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) xacc ^= wv[i];
-            if (xacc == 0x12345678u) a.dbg[0] = 1;
+            if (xacc == 0x12345678u) f_dbg[0] = 1;
             continue; }
-          if (a.pxpair) {
+          if (f_px) {
             // wv = [x-phase 0: chunk0, chunk0+1 | x-phase 1: chunk0, chunk0+1]; output pixels 2x and 2x+1 of a chunk are
             // 32 contiguous bytes: one 256-bit access per chunk for the mask, the accumulate target and the store
             if (lane < nvalid) {
@@ -534,13 +547,13 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
                 uint32_t v8[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { v8[i] = wv[4 * c + i]; v8[4 + i] = wv[8 + 4 * c + i]; }
-                if (a.mask) {
+                if (f_mask) {
                   uint32_t mk[8];
                   tc::ldg256_nc(mbase_t + eoff + c * cplane, mk);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v8[i] &= relu_keep(mk[i]);
                 }
-                if (a.accumulate) {
+                if (f_acc) {
                   uint32_t old[8];
                   tc::ld256(obase + c * cplane, old);
 #pragma unroll
@@ -556,7 +569,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
             }
           } else if (lane < nvalid) {
             __nv_bfloat16* obase = obase_t + eoff;
-            if (a.mask) {
+            if (f_mask) {
               const __nv_bfloat16* mbase = mbase_t + eoff;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
@@ -565,7 +578,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
                 wv[c * 4 + 2] &= relu_keep(mk.z); wv[c * 4 + 3] &= relu_keep(mk.w);
               }
             }
-            if (a.accumulate) {
+            if (f_acc) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const uint4 old = *reinterpret_cast<const uint4*>(obase + c * cplane);
@@ -604,7 +617,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(acc_empty + abuf);
-      if (a.dbg && ew == 0 && lane == 0) a.dbg[blockIdx.x * 8 + 5] += clock64() - te0;
+      if (f_dbg && ew == 0 && lane == 0) f_dbg[blockIdx.x * 8 + 5] += clock64() - te0;
     }
   }
   tc::fence_before_sync();
@@ -996,8 +1009,11 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   const size_t smem = c2_smem_bytes(a.plane_sm, a.out_mode);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cnp_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr = smem;
   }
@@ -1027,10 +1043,22 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   attrs[0].val.clusterDim.x = a.cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   if (a.cluster > 1) {
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, a);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, 0>, a);
     if (le != cudaSuccess) { cnp_set_error("conv_tc2_kernel: %s", cudaGetErrorString(le)); return (int)le; }
   } else {   // plain launch when no cluster is requested (cluster-attribute launches place CTAs differently)
-    conv_tc2_kernel<false><<<grid, C2_THREADS, smem, st>>>(a);
+    static const bool generic_only = getenv("CNP_C2_GENERIC_EPILOGUE") != nullptr;
+    int epi = 0;
+    if (!generic_only && !a.dbg && a.dbg_flags == 0 && a.out_mode == 0) {
+      if (a.pxpair) epi = 3;
+      else if (a.mask && !a.accumulate) epi = 2;
+      else if (!a.mask && !a.accumulate) epi = 1;
+    }
+    switch (epi) {
+      case 1: conv_tc2_kernel<false, 1><<<grid, C2_THREADS, smem, st>>>(a); break;
+      case 2: conv_tc2_kernel<false, 2><<<grid, C2_THREADS, smem, st>>>(a); break;
+      case 3: conv_tc2_kernel<false, 3><<<grid, C2_THREADS, smem, st>>>(a); break;
+      default: conv_tc2_kernel<false, 0><<<grid, C2_THREADS, smem, st>>>(a); break;
+    }
   }
   CNP_LAUNCH_CHECK("conv_tc2_kernel");
   return 0;
