@@ -134,11 +134,10 @@ __device__ __forceinline__ void issue_row_n(int nacc, uint32_t tmem, uint32_t w_
 // CL = true: instantiation with the cluster / multicast code.  A kernel that contains cluster instructions is scheduled
 // differently even in a plain launch (measured ~15 % slower on the wgrad kernel), hence two instantiations.
 // EPI: epilogue specialisation.  The epilogue is sensitive to every instruction and live register (adding code it never
-// executed slowed the unmasked WIDE dgrad by 5 %), so the hot configurations get their flags as compile-time constants:
-//   0 generic (every flag read at run time: fp32 output, debug counters, anything else)
-//   1 blocked bf16 output, no mask, no accumulate, no x-phase pair   (forward layers)
-//   2 blocked bf16 output, ReLU mask, no accumulate, no x-phase pair (input gradients of the decoder levels)
-//   3 blocked bf16 output, x-phase pair (polyphase forward; stride-2 input gradients: mask / accumulate at run time)
+// executed slowed the unmasked WIDE dgrad by 5 %), so the configurations the engine launches get their flags as
+// compile-time constants: EPI < 0 = generic (every flag read at run time: fp32 output, debug counters, anything else),
+// EPI >= 0 = blocked bf16 output with exactly the flag bits below set.
+enum { EF_MASK = 1, EF_ACC = 2, EF_PX = 4, EF_WIDE = 8, EF_BIASRELU = 16, EF_S2D = 32 };
 template <bool CL, int EPI>
 __global__ void __launch_bounds__(C2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
@@ -356,11 +355,15 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     }
   } else if (warp >= 4) {
     // ===================== epilogue ==============================================================
-    constexpr bool EG = EPI == 0;
+    constexpr bool EG = EPI < 0;
     const bool f_mode0 = EG ? a.out_mode == 0 : true;                       // blocked bf16 output
-    const bool f_px = EG ? a.pxpair != 0 : EPI == 3;
-    const bool f_mask = (EG || EPI == 3) ? a.mask != nullptr : EPI == 2;
-    const bool f_acc = (EG || EPI == 3) ? a.accumulate != 0 : false;
+    const bool f_px = EG ? a.pxpair != 0 : (EPI & EF_PX) != 0;
+    const bool f_mask = EG ? a.mask != nullptr : (EPI & EF_MASK) != 0;
+    const bool f_acc = EG ? a.accumulate != 0 : (EPI & EF_ACC) != 0;
+    const bool f_wide = EG ? a.wide != 0 : (EPI & EF_WIDE) != 0;
+    const bool f_bias = EG ? a.bias != nullptr : (EPI & EF_BIASRELU) != 0;
+    const bool f_relu = EG ? a.relu != 0 : (EPI & EF_BIASRELU) != 0;
+    const bool f_s2d = EG ? a.s2d != nullptr : (EPI & EF_S2D) != 0;
     const int f_dbgf = EG ? a.dbg_flags : 0;
     long long* const f_dbg = EG ? a.dbg : nullptr;
     const int ew = warp - 4;
@@ -368,16 +371,16 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     const int h = ew >> 2;            // this quadrant's (accumulator, column block) items are dealt round-robin to its warps
     const int m = q * 32 + lane;
     const int g = m >> 6;
-    const int ch = a.wide ? m : (m & 63);                    // output channel of this thread (TMEM lane)
+    const int ch = f_wide ? m : (m & 63);                    // output channel of this thread (TMEM lane)
     // x-phase pairs: the 32 lanes of a quadrant are [16 channels of x-phase 0 | the same 16 channels of x-phase 1] (see
     // pack2_kernel), so that a thread ends up with BOTH output pixels 2x, 2x+1 of two chunks: 32 B stores / loads
-    const int chunk0 = a.out_c_off + (a.wide ? q * 4 : (f_px ? q * 2 : (q & 1) * 4));   // first output chunk of this warp
-    const float bias_v = a.bias ? __ldg(a.bias + ch) : 0.f;
+    const int chunk0 = a.out_c_off + (f_wide ? q * 4 : (f_px ? q * 2 : (q & 1) * 4));   // first output chunk of this warp
+    const float bias_v = f_bias ? __ldg(a.bias + ch) : 0.f;
     // bias of the four channels this thread holds in the fragment distribution: warp channel base + lane/4 + {0,8,16,24}
     float bias4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      bias4[i] = !a.bias ? 0.f : (f_px ? __ldg(a.bias + 16 * q + (lane >> 2) + 8 * (i & 1))
+      bias4[i] = !f_bias ? 0.f : (f_px ? __ldg(a.bias + 16 * q + (lane >> 2) + 8 * (i & 1))
                                            : __ldg(a.bias + (ch - lane) + (lane >> 2) + 8 * i));
     uint32_t* my_stg = stg + ew * stg_words;
     const long long oplane = (long long)a.out_Hp * a.out_Wp;
@@ -388,7 +391,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     // a per-tile 64-bit base of this thread plus a 32-bit element offset of the item.
     const int it_j0 = h / ncb, it_cb0 = h - it_j0 * ncb;
     const int it_dj = (C2_EPI_WARPS / 4) / ncb, it_dcb = (C2_EPI_WARPS / 4) - it_dj * ncb;
-    const int gsel = (a.wide || f_px) ? 0 : g;                      // PAIR: lane group = second row of the accumulator
+    const int gsel = (f_wide || f_px) ? 0 : g;                      // PAIR: lane group = second row of the accumulator
     const int row_eoff = a.rpa * a.sy * a.out_Wp * 8;                   // element offset between accumulators (rows)
     const int col_eoff = 32 * a.sx * 8;                                 // ... between column blocks
     const int cplane = (int)(oplane * 8);                               // ... between chunk planes
@@ -465,11 +468,11 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
               f[2] = __uint_as_float(ra[4 * k + 2]); f[3] = __uint_as_float(ra[4 * k + 3]);
               f[4] = __uint_as_float(rb[4 * k]);     f[5] = __uint_as_float(rb[4 * k + 1]);
               f[6] = __uint_as_float(rb[4 * k + 2]); f[7] = __uint_as_float(rb[4 * k + 3]);
-              if (a.bias) {                          // (the input gradients have none: 32 FADDs per item less)
+              if (f_bias) {                          // (the input gradients have none: 32 FADDs per item less)
                 f[0] += bias4[0]; f[1] += bias4[0]; f[2] += bias4[1]; f[3] += bias4[1];
                 f[4] += bias4[2]; f[5] += bias4[2]; f[6] += bias4[3]; f[7] += bias4[3];
               }
-              if (a.relu) {
+              if (f_relu) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
               }
@@ -500,7 +503,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             v[i] += bias_v;
-            if (a.relu) v[i] = v[i] < 0.f ? 0.f : v[i];
+            if (f_relu) v[i] = v[i] < 0.f ? 0.f : v[i];
           }
           {
             // fp32 NCHW: stage [channel = lane][32 px] (row stride 36 floats), re-read as 4 channels x 8 groups of
@@ -598,7 +601,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
                   make_uint4(wv[c * 4], wv[c * 4 + 1], wv[c * 4 + 2], wv[c * 4 + 3]);
             const int sc0 = chunk0 - a.out_c_off - a.s2d_c0;     // WIDE: only the quadrants holding chunks s2d_c0 .. +7
             const int ox = (x0 + xs + lane) * a.sx + a.ax;
-            if (a.s2d && sc0 >= 0 && sc0 < 8 && (oy >> 1) >= a.s2d_band && (oy >> 1) < (a.H >> 1) - a.s2d_band &&
+            if (f_s2d && sc0 >= 0 && sc0 < 8 && (oy >> 1) >= a.s2d_band && (oy >> 1) < (a.H >> 1) - a.s2d_band &&
                 (ox >> 1) >= a.s2d_band && (ox >> 1) < (a.W >> 1) - a.s2d_band) {
               // phase plane p = (y&1)*2 + (x&1) holds pixel (y/2, x/2): the input layout of the next stride-2 layer
               // (and, with a band, of the polyphase resize-convolution's backward: up_poly.cu)
@@ -1009,11 +1012,13 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   const size_t smem = c2_smem_bytes(a.plane_sm, a.out_mode);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+#define C2_ATTR(CLF, F) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<CLF, (F)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    C2_ATTR(false, -1) C2_ATTR(true, -1) C2_ATTR(false, EF_BIASRELU) C2_ATTR(false, EF_BIASRELU | EF_S2D)
+    C2_ATTR(false, EF_PX | EF_BIASRELU) C2_ATTR(false, EF_MASK | EF_WIDE) C2_ATTR(false, EF_MASK | EF_WIDE | EF_S2D)
+    C2_ATTR(false, EF_WIDE) C2_ATTR(false, 0) C2_ATTR(false, EF_MASK) C2_ATTR(false, EF_PX | EF_MASK | EF_ACC)
+    C2_ATTR(false, EF_MASK | EF_ACC)
+#undef C2_ATTR
     if (e != cudaSuccess) { cnp_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr = smem;
   }
@@ -1043,22 +1048,29 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   attrs[0].val.clusterDim.x = a.cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   if (a.cluster > 1) {
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, 0>, a);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, -1>, a);
     if (le != cudaSuccess) { cnp_set_error("conv_tc2_kernel: %s", cudaGetErrorString(le)); return (int)le; }
   } else {   // plain launch when no cluster is requested (cluster-attribute launches place CTAs differently)
     static const bool generic_only = getenv("CNP_C2_GENERIC_EPILOGUE") != nullptr;
-    int epi = 0;
-    if (!generic_only && !a.dbg && a.dbg_flags == 0 && a.out_mode == 0) {
-      if (a.pxpair) epi = 3;
-      else if (a.mask && !a.accumulate) epi = 2;
-      else if (!a.mask && !a.accumulate) epi = 1;
-    }
+    int epi = -1;
+    if (!generic_only && !a.dbg && a.dbg_flags == 0 && a.out_mode == 0 && (a.bias != nullptr) == (a.relu != 0))
+      epi = (a.mask ? EF_MASK : 0) | (a.accumulate ? EF_ACC : 0) | (a.pxpair ? EF_PX : 0) | (a.wide ? EF_WIDE : 0) |
+            (a.bias ? EF_BIASRELU : 0) | (a.s2d ? EF_S2D : 0);
+#define C2_LAUNCH_EPI(F) case (F): conv_tc2_kernel<false, (F)><<<grid, C2_THREADS, smem, st>>>(a); break;
     switch (epi) {
-      case 1: conv_tc2_kernel<false, 1><<<grid, C2_THREADS, smem, st>>>(a); break;
-      case 2: conv_tc2_kernel<false, 2><<<grid, C2_THREADS, smem, st>>>(a); break;
-      case 3: conv_tc2_kernel<false, 3><<<grid, C2_THREADS, smem, st>>>(a); break;
-      default: conv_tc2_kernel<false, 0><<<grid, C2_THREADS, smem, st>>>(a); break;
+      C2_LAUNCH_EPI(EF_BIASRELU)                          // forward layers, strips
+      C2_LAUNCH_EPI(EF_BIASRELU | EF_S2D)                 // forward + space-to-depth copy for the stride-2 layer behind it
+      C2_LAUNCH_EPI(EF_PX | EF_BIASRELU)                  // polyphase forward
+      C2_LAUNCH_EPI(EF_MASK | EF_WIDE)                    // input gradient of a 128-channel level
+      C2_LAUNCH_EPI(EF_MASK | EF_WIDE | EF_S2D)           // ... that also hands dY to a polyphase level
+      C2_LAUNCH_EPI(EF_WIDE)                              // ... unmasked (before Upsample^T; strips)
+      C2_LAUNCH_EPI(0)                                    // 64-channel input gradient, unmasked
+      C2_LAUNCH_EPI(EF_MASK)
+      C2_LAUNCH_EPI(EF_PX | EF_MASK | EF_ACC)             // stride-2 input gradient onto the skip gradient
+      C2_LAUNCH_EPI(EF_MASK | EF_ACC)                     // stride-1 down-path input gradient onto the skip gradient
+      default: conv_tc2_kernel<false, -1><<<grid, C2_THREADS, smem, st>>>(a); break;
     }
+#undef C2_LAUNCH_EPI
   }
   CNP_LAUNCH_CHECK("conv_tc2_kernel");
   return 0;
