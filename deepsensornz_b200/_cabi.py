@@ -128,6 +128,7 @@ _SIGS = {
     "cnp_mlp_head_bwd_workspace_bytes": (_ll, [C.POINTER(CnpMlpParams), _i, _i]),
     "cnp_mlp_head_bwd": (C.c_int, [C.POINTER(CnpMlpParams), c_fp, _i, _i, c_fp, _i, c_fp, _i, _i, c_fp, c_fp, c_fp, _ll,
                                    c_stream]),
+    "cnp_loss_mean": (C.c_int, [c_fp, c_fp, _i, _i, c_fp, c_fp, c_stream]),
     # (2) bf16 tensor-core UNet blocks
     "cnp_conv_tc2_debug": (C.c_int, [c_fp, _i]),
     "cnp_conv_tc2_set_cluster": (C.c_int, [_i]),

@@ -34,17 +34,20 @@ class _LossFn(torch.autograd.Function):
     def forward(ctx, engine: Engine, batch: DeviceBatch, normalise: bool, *params):
         out = engine.forward(batch, with_loss=True)
         logp, count = out["logp"], out["count"]
-        denom = count.clamp(min=1).to(torch.float64) if normalise else torch.ones_like(logp)
-        loss = -(logp / denom).mean()
+        # one launch for the scalar algebra: loss = -mean_b(logp_b / N_b) in float64 and the backward's seed d loss / d logp
+        loss = torch.empty((), dtype=torch.float64, device=logp.device)
+        coef = torch.empty(logp.shape[0], dtype=torch.float32, device=logp.device)
+        engine._call("cnp_loss_mean", logp.data_ptr(), count.data_ptr(), int(logp.shape[0]), int(normalise), loss.data_ptr(),
+                     coef.data_ptr(), torch.cuda.current_stream().cuda_stream)
         ctx.engine, ctx.batch, ctx.fctx = engine, batch, out["ctx"]
-        ctx.denom = denom
+        ctx.coef = coef
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         eng: Engine = ctx.engine
         B = ctx.batch.B
-        dlogp = (-(grad_out.to(torch.float64)) / (B * ctx.denom)).to(torch.float32).contiguous()
+        dlogp = ctx.coef * grad_out.to(torch.float32)
         grads = eng.backward(ctx.batch, ctx.fctx, dlogp)
         outs = []
         for n, p in eng.module.named_parameters():

@@ -207,6 +207,22 @@ head_logp_kernel(const float* __restrict__ mean, const float* __restrict__ var, 
   if (lane == 0) { logp[b] = lp; count[b] = cnt; }
 }
 
+// loss = -mean_b(logp_b / max(N_b, 1)) (or -mean_b logp_b) in float64, summed in task order, and the seed of the backward
+// dlogp_b = d loss / d logp_b = -1 / (B max(N_b, 1)) as fp32 -- one launch instead of the dozen one-element torch kernels
+// (clamp, casts, div, mean, neg; and their mirror images in the backward) that used to sit between the head and the backward.
+__global__ void __launch_bounds__(32)
+loss_mean_kernel(const double* __restrict__ logp, const int* __restrict__ count, int B, int normalise,
+                 double* __restrict__ loss, float* __restrict__ dlogp) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const double den = normalise ? (double)max(count[b], 1) : 1.0;
+    s += logp[b] / den;
+    dlogp[b] = (float)(-1.0 / ((double)B * den));
+  }
+  *loss = -s / (double)B;
+}
+
 // ---------------------------------------------------------------------------------------------
 // backward: grid (chunks, B), BW_PTS points per block
 //   dlogp[b] = d loss / d logp_b (already includes -1/(B*N_b)); outputs df (first Cf channels),
@@ -420,5 +436,14 @@ CNP_API int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctot
     mlp_head_reduce_kernel<<<cnp_cdiv(stride, 256), 256, 0, st>>>(*p, ws, stride, nblk);
     CNP_LAUNCH_CHECK("mlp_head_reduce_kernel");
   }
+  return 0;
+}
+
+// loss (float64 scalar) = -mean_b(logp_b [/ max(count_b, 1)]); dlogp [B] fp32 = d loss / d logp.
+CNP_API int cnp_loss_mean(const double* logp, const int* count, int B, int normalise, double* loss, float* dlogp,
+                          cudaStream_t st) {
+  CNP_REQUIRE(logp && count && loss && dlogp && B > 0, "loss_mean: bad arguments");
+  loss_mean_kernel<<<1, 32, 0, st>>>(logp, count, B, normalise, loss, dlogp);
+  CNP_LAUNCH_CHECK("loss_mean_kernel");
   return 0;
 }

@@ -312,6 +312,9 @@ long long cnp_mlp_head_bwd_workspace_bytes(const cnp_mlp_params* p, int B, int N
 int cnp_mlp_head_bwd(const cnp_mlp_params* p, const float* f, int f_ctotal, int Cf, const float* aux, int Ca,
                      const float* yt, int B, int Nt, const float* dlogp /*[B]*/, float* df, void* workspace,
                      long long workspace_bytes, cnp_stream_t s);
+/* loss (float64 scalar) = -mean_b(logp_b [/ max(count_b, 1)]) summed in task order, and dlogp [B] fp32 = d loss / d logp:
+ * the scalar arithmetic of ConvNP.loss_fn(task, normalise=...) + train_epoch's batch mean (train.py:370, 388-394) */
+int cnp_loss_mean(const double* logp, const int* count, int B, int normalise, double* loss, float* dlogp, cnp_stream_t s);
 
 #ifdef __cplusplus
 }
