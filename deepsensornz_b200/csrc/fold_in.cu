@@ -107,8 +107,8 @@ up_phase_weights_kernel(const float* __restrict__ w5, int Cout, int Cin, float* 
 
 }  // namespace
 
-// Phase weights of the polyphase resize-convolution (groundwork for replacing Upsample + Conv 5x5 of the UNet decoder
-// levels): wp [2 (row phase)][2 (x-phase)][Cout][Cin][4][4] fp32 from w5 [Cout][Cin][5][5].
+// Phase weights of the polyphase resize-convolution (Upsample + Conv 5x5 of the UNet decoder levels without the upsampled
+// tensor, DESIGN.md 4.5, up_poly.cu): wp [2 (row phase)][2 (x-phase)][Cout][Cin][4][4] fp32 from w5 [Cout][Cin][5][5].
 CNP_API int cnp_up_phase_weights(const float* w5, int Cout, int Cin, float* wp, cudaStream_t st) {
   CNP_REQUIRE(w5 && wp && Cout > 0 && Cin > 0, "up_phase_weights: bad arguments");
   up_phase_weights_kernel<<<cnp_cdiv(4 * Cout * Cin * 16, 256), 256, 0, st>>>(w5, Cout, Cin, wp);

@@ -1,4 +1,7 @@
-"""CPU check of the identity behind the planned polyphase resize-convolution (tools/polyphase_check.py):
+"""CPU checks of the identities behind the polyphase resize-convolution.  tools/polyphase_check.py: the
+first formulation (replicate-padded input minus a frame term); tools/polyphase_strips.py: the decomposition the engine
+uses (phase kernels inside, standard kernels on strips for the band) -- forward, dx, dW5, dbias in float64.
+First formulation:
 conv5x5(zero_pad(bilinear_up2x(x))) == four 4x4 phase convolutions of the replicate-padded input minus the 5x5
 convolution of a two-pixel frame -- exact in float64, and the frame term only reaches outputs within 2 pixels of the border."""
 import os
@@ -41,3 +44,13 @@ def test_polyphase_position_plan_matches_phase_convolutions():
     y, n_pos = P.upconv_by_plan(x, w)
     assert n_pos == 20
     assert float((y - P.upconv_polyphase(x, w)).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("h,w", [(9, 11), (8, 8), (5, 12), (19, 38)])
+def test_strip_decomposition_forward_and_backward(h, w):
+    """The partition the engine runs (interior: four 4x4 phase convolutions on the zero-ringed tensor; band of 2 low-res
+    pixels: the 5x5 convolution on strips of the upsampled tensor, column strips transposed; every dY pixel used once in
+    the backward; strips' input gradient folded through the transposed bilinear map) equals autograd of Upsample + Conv."""
+    import polyphase_strips as S
+    ey, ex, ew, eb = S.check(H=h, W=w, seed=h * 31 + w)
+    assert ey < 1e-12 and ex < 1e-12 and ew < 1e-11 and eb < 1e-11

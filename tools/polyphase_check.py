@@ -1,4 +1,6 @@
-"""Groundwork for the next structural step: the resize-convolution of upstream's UNet decoder levels,
+"""First formulation of the polyphase resize-convolution (the engine uses the strip decomposition of
+tools/polyphase_strips.py, which needs no replicate padding and no frame term): the resize-convolution of upstream's
+UNet decoder levels,
 
     y = conv5x5(zero_pad_2(bilinear_up2x(x)))          (torch.nn.Upsample(scale_factor=2, mode="bilinear") + Conv2d(k=5, padding=2))
 
