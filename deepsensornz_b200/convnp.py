@@ -46,7 +46,6 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         eng: Engine = ctx.engine
-        B = ctx.batch.B
         dlogp = ctx.coef * grad_out.to(torch.float32)
         grads = eng.backward(ctx.batch, ctx.fctx, dlogp)
         outs = []
