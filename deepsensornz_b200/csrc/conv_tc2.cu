@@ -79,7 +79,8 @@ constexpr int C2_STAGE_POS = 5;
 constexpr int C2_STAGE_BYTES = C2_STAGE_POS * C2_POS_BYTES;
 constexpr int C2_WSTAGES = 3;
 constexpr int C2_ABUFS = 2;
-constexpr int C2_EPI_WARPS = 12;
+constexpr int C2_EPI_WARPS = 12;                        // generic instantiation (123 registers per thread)
+constexpr int C2_EPI_WARPS_SPEC = 16;                   // specialised epilogues (<= 102 registers): 4 warps per TMEM quadrant
 constexpr int C2_THREADS = 32 * (4 + C2_EPI_WARPS);
 constexpr int C2_STG_WORDS_BF16 = 32 * 20;               // per-warp transpose buffer [32 px][64 B of channels + 16 B pad]
 constexpr int C2_STG_WORDS_F32 = 32 * 36;                // fp32 output: [32 ch][36 floats]
@@ -138,8 +139,11 @@ __device__ __forceinline__ void issue_row_n(int nacc, uint32_t tmem, uint32_t w_
 // compile-time constants: EPI < 0 = generic (every flag read at run time: fp32 output, debug counters, anything else),
 // EPI >= 0 = blocked bf16 output with exactly the flag bits below set.
 enum { EF_MASK = 1, EF_ACC = 2, EF_PX = 4, EF_WIDE = 8, EF_BIASRELU = 16, EF_S2D = 32 };
-template <bool CL, int EPI>
-__global__ void __launch_bounds__(C2_THREADS, 1)
+// EW: epilogue warps.  An item of the epilogue is a chain of latencies (TMEM load, transposition through shared memory,
+// global accesses), so the epilogue's length is set by how many items are in flight: the specialised instantiations fit
+// 16 epilogue warps (640 threads x <= 102 registers) where the generic one has 12.
+template <bool CL, int EPI, int EW>
+__global__ void __launch_bounds__(32 * (4 + EW), 1)
 conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   const int a_cluster = CL ? a.cluster : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -149,7 +153,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   uint8_t* w_smem = smem + C2_ABUFS * abuf_bytes;
   uint32_t* stg = reinterpret_cast<uint32_t*>(w_smem + C2_WSTAGES * C2_STAGE_BYTES);
   const int stg_words = a.out_mode == 1 ? C2_STG_WORDS_F32 : C2_STG_WORDS_BF16;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + C2_EPI_WARPS * stg_words);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + EW * stg_words);
   uint64_t* a_full = bars;             // [2]
   uint64_t* a_empty = bars + 2;        // [2]
   uint64_t* w_full = bars + 4;         // [3]
@@ -165,7 +169,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < C2_ABUFS; ++i) { tc::mbar_init(a_full + i, 1); tc::mbar_init(a_empty + i, 1); }
     for (int i = 0; i < C2_WSTAGES; ++i) { tc::mbar_init(w_full + i, 1); tc::mbar_init(w_empty + i, (uint32_t)a_cluster); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, C2_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(acc_full + i, 1); tc::mbar_init(acc_empty + i, EW); }
     tc::mbar_fence_init();
   }
   if (warp == 3) tc::tmem_alloc(tmem_slot, 512);
@@ -390,7 +394,7 @@ conv_tc2_kernel(const __grid_constant__ cnp_c2_args a) {
     // nacc x ncb, the same sequence for every tile -- instead of divided out of an item index, and every global address is
     // a per-tile 64-bit base of this thread plus a 32-bit element offset of the item.
     const int it_j0 = h / ncb, it_cb0 = h - it_j0 * ncb;
-    const int it_dj = (C2_EPI_WARPS / 4) / ncb, it_dcb = (C2_EPI_WARPS / 4) - it_dj * ncb;
+    const int it_dj = (EW / 4) / ncb, it_dcb = (EW / 4) - it_dj * ncb;
     const int gsel = (f_wide || f_px) ? 0 : g;                      // PAIR: lane group = second row of the accumulator
     const int row_eoff = a.rpa * a.sy * a.out_Wp * 8;                   // element offset between accumulators (rows)
     const int col_eoff = 32 * a.sx * 8;                                 // ... between column blocks
@@ -819,8 +823,8 @@ int num_sms2() {
   return g2_num_sms;
 }
 
-size_t c2_smem_bytes(int plane_sm, int out_mode) {
-  const size_t stg = (size_t)C2_EPI_WARPS * (out_mode == 1 ? C2_STG_WORDS_F32 : C2_STG_WORDS_BF16) * 4;
+size_t c2_smem_bytes(int plane_sm, int out_mode, int epi_warps) {
+  const size_t stg = (size_t)epi_warps * (out_mode == 1 ? C2_STG_WORDS_F32 : C2_STG_WORDS_BF16) * 4;
   return (size_t)C2_ABUFS * 2 * plane_sm * 16 + (size_t)C2_WSTAGES * C2_STAGE_BYTES + stg + 16 * 8;
 }
 
@@ -837,7 +841,7 @@ size_t c2_smem_bytes(int plane_sm, int out_mode) {
 // read-modify-write epilogue), not on the 128-channel layers, whose weight stream needs 3 accumulators per tile to stay
 // under the L2 rate.  epi_col: epilogue cycles per accumulator column (18 plain; the mask and the accumulate target are
 // global loads issued from the epilogue).
-void choose_geometry(cnp_c2_args* a, int mma_per_acc, double epi_col, bool allow_nbuf2) {
+void choose_geometry(cnp_c2_args* a, int mma_per_acc, double epi_col, bool allow_nbuf2, int epi_warps) {
   const int rpa = (a->wide || a->pxpair) ? 1 : 2;
   double best = 1e300;
   for (int N = 32; N <= 256; N += 32) {
@@ -853,7 +857,7 @@ void choose_geometry(cnp_c2_args* a, int mma_per_acc, double epi_col, bool allow
       const int TH = nacc * rpa;
       const int pitch = TW + 4;
       const int plane_sm = (TH + 4) * pitch + (N > pitch ? N - pitch : 0) + 8;
-      if (c2_smem_bytes(plane_sm, a->out_mode) > 225 * 1024) continue;
+      if (c2_smem_bytes(plane_sm, a->out_mode, epi_warps) > 225 * 1024) continue;
       const int tiles_y = cnp_cdiv(a->H, TH);
       const long long tiles = (long long)a->B * tiles_x * tiles_y;
       const long long waves = (tiles + num_sms2() - 1) / num_sms2();
@@ -973,10 +977,23 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   // N = 160, and every tile re-streams the whole packed weight tensor from L2 for a third of the MMAs: the weight stream,
   // not the epilogue, bounds short tiles (same finding as the two-round tail split above).  CNP_DOUBLE_ACC=narrow restricts it to the folded first layer
   // (one K block: N = 64 x 4 accumulators x 2 sets is chosen, 137 against 127 us).
+  // epilogue instantiation (flag set known from the arguments) and, with it, the number of epilogue warps
+  static const bool generic_only = getenv("CNP_C2_GENERIC_EPILOGUE") != nullptr;
+  int epi = -1;
+  if (!generic_only && a.cluster == 1 && !g_c2_dbg && g_c2_dbg_flags == 0 && o->mode == 0 && (o->bias != nullptr) == (o->relu != 0)) {
+    epi = (o->mask ? EF_MASK : 0) | (o->accumulate ? EF_ACC : 0) | (a.pxpair ? EF_PX : 0) | (a.wide ? EF_WIDE : 0) |
+          (o->bias ? EF_BIASRELU : 0) | (o->s2d ? EF_S2D : 0);
+    static const int supported[] = {EF_BIASRELU, EF_BIASRELU | EF_S2D, EF_PX | EF_BIASRELU, EF_MASK | EF_WIDE,
+                                    EF_MASK | EF_WIDE | EF_S2D, EF_WIDE, 0, EF_MASK, EF_PX | EF_MASK | EF_ACC, EF_MASK | EF_ACC};
+    bool ok = false;
+    for (int f : supported) ok = ok || f == epi;
+    if (!ok) epi = -1;
+  }
+  const int epi_warps = epi >= 0 ? C2_EPI_WARPS_SPEC : C2_EPI_WARPS;
   static const char* nbuf2_env = getenv("CNP_DOUBLE_ACC");
   const bool nbuf2 = nbuf2_env != nullptr && (strcmp(nbuf2_env, "narrow") != 0 || a.plan.n_kb == 1);
   choose_geometry(&a, plan_total_pos(a.plan), 18.0 + (o->mode == 0 && o->mask ? 30.0 : 0.0) + (o->accumulate ? 40.0 : 0.0),
-                  nbuf2);
+                  nbuf2, epi_warps);
   if (getenv("CNP_C2_VERBOSE"))
     fprintf(stderr, "conv_tc2 kind %d chunks %d %dx%d: N %d nacc %d nbuf %d tiles %d\n", kind, n_chunks, a.H, a.W, a.N, a.nacc,
             a.nbuf, B * a.tiles_x * a.tiles_y);
@@ -1009,15 +1026,16 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   }
   a.bias = o->bias; a.relu = o->relu; a.accumulate = o->accumulate;
   a.dbg = g_c2_dbg; a.dbg_flags = g_c2_dbg_flags;
-  const size_t smem = c2_smem_bytes(a.plane_sm, a.out_mode);
+  const size_t smem = c2_smem_bytes(a.plane_sm, a.out_mode, epi_warps);
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaSuccess;
-#define C2_ATTR(CLF, F) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<CLF, (F)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    C2_ATTR(false, -1) C2_ATTR(true, -1) C2_ATTR(false, EF_BIASRELU) C2_ATTR(false, EF_BIASRELU | EF_S2D)
-    C2_ATTR(false, EF_PX | EF_BIASRELU) C2_ATTR(false, EF_MASK | EF_WIDE) C2_ATTR(false, EF_MASK | EF_WIDE | EF_S2D)
-    C2_ATTR(false, EF_WIDE) C2_ATTR(false, 0) C2_ATTR(false, EF_MASK) C2_ATTR(false, EF_PX | EF_MASK | EF_ACC)
-    C2_ATTR(false, EF_MASK | EF_ACC)
+#define C2_ATTR(CLF, F, EWN) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc2_kernel<CLF, (F), EWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define C2_ATTR_S(F) C2_ATTR(false, F, C2_EPI_WARPS_SPEC)
+    C2_ATTR(false, -1, C2_EPI_WARPS) C2_ATTR(true, -1, C2_EPI_WARPS) C2_ATTR_S(EF_BIASRELU) C2_ATTR_S(EF_BIASRELU | EF_S2D)
+    C2_ATTR_S(EF_PX | EF_BIASRELU) C2_ATTR_S(EF_MASK | EF_WIDE) C2_ATTR_S(EF_MASK | EF_WIDE | EF_S2D)
+    C2_ATTR_S(EF_WIDE) C2_ATTR_S(0) C2_ATTR_S(EF_MASK) C2_ATTR_S(EF_PX | EF_MASK | EF_ACC) C2_ATTR_S(EF_MASK | EF_ACC)
+#undef C2_ATTR_S
 #undef C2_ATTR
     if (e != cudaSuccess) { cnp_set_error("conv_tc2: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr = smem;
@@ -1048,15 +1066,10 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
   attrs[0].val.clusterDim.x = a.cluster; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   if (a.cluster > 1) {
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, -1>, a);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, -1, C2_EPI_WARPS>, a);
     if (le != cudaSuccess) { cnp_set_error("conv_tc2_kernel: %s", cudaGetErrorString(le)); return (int)le; }
   } else {   // plain launch when no cluster is requested (cluster-attribute launches place CTAs differently)
-    static const bool generic_only = getenv("CNP_C2_GENERIC_EPILOGUE") != nullptr;
-    int epi = -1;
-    if (!generic_only && !a.dbg && a.dbg_flags == 0 && a.out_mode == 0 && (a.bias != nullptr) == (a.relu != 0))
-      epi = (a.mask ? EF_MASK : 0) | (a.accumulate ? EF_ACC : 0) | (a.pxpair ? EF_PX : 0) | (a.wide ? EF_WIDE : 0) |
-            (a.bias ? EF_BIASRELU : 0) | (a.s2d ? EF_S2D : 0);
-#define C2_LAUNCH_EPI(F) case (F): conv_tc2_kernel<false, (F)><<<grid, C2_THREADS, smem, st>>>(a); break;
+#define C2_LAUNCH_EPI(F) case (F): conv_tc2_kernel<false, (F), C2_EPI_WARPS_SPEC><<<grid, 32 * (4 + C2_EPI_WARPS_SPEC), smem, st>>>(a); break;
     switch (epi) {
       C2_LAUNCH_EPI(EF_BIASRELU)                          // forward layers, strips
       C2_LAUNCH_EPI(EF_BIASRELU | EF_S2D)                 // forward + space-to-depth copy for the stride-2 layer behind it
@@ -1068,7 +1081,7 @@ static int conv_tc2_launch(const cnp_blk* x, int n_chunks, const void* wpk, cons
       C2_LAUNCH_EPI(EF_MASK)
       C2_LAUNCH_EPI(EF_PX | EF_MASK | EF_ACC)             // stride-2 input gradient onto the skip gradient
       C2_LAUNCH_EPI(EF_MASK | EF_ACC)                     // stride-1 down-path input gradient onto the skip gradient
-      default: conv_tc2_kernel<false, -1><<<grid, C2_THREADS, smem, st>>>(a); break;
+      default: conv_tc2_kernel<false, -1, C2_EPI_WARPS><<<grid, C2_THREADS, smem, st>>>(a); break;
     }
 #undef C2_LAUNCH_EPI
   }
